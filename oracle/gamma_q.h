@@ -1,0 +1,97 @@
+/* oracle/gamma_q.h -- TEST INFRASTRUCTURE (parity oracle); never linked into the product library.
+ *
+ * Regularized upper incomplete gamma function Q(a,x) = Gamma(a,x)/Gamma(a), fp64.
+ *
+ * The reference calls boost::math::gamma_q / gamma_q_inv (Boost.Math 1.84.0, a Conan dependency
+ * pinned in /root/reference/conanfile.txt:2 that is NOT present under /root/reference) through
+ * core/safe_gamma_math.h:46-83.  Boost's implementation cannot be compiled here, so this header
+ * restates the published algorithm (power series for x < a+1, Legendre continued fraction evaluated
+ * with the modified Lentz method otherwise; Abramowitz & Stegun 6.5.29 / 6.5.31).
+ * PARITY UNPINNED for the values of Q(a,x): the reference's own tests at this boundary
+ * (tests/safe_gamma_math_tests.cpp:35-63) compare Boost against itself plus three trivial absolutes,
+ * which this implementation reproduces (Q(271.4,6601)=0, Q(1000,100)=1, Q(a,0)=1); tests/ also
+ * cross-check it against scipy.special.gammaincc.  It only ever affects the single above-root
+ * candidate region of an SPR study.
+ */
+#ifndef DPHY_ORACLE_GAMMA_Q_H_
+#define DPHY_ORACLE_GAMMA_Q_H_
+
+#include <math.h>
+#include <float.h>
+
+static inline double orc_gamma_p_series(double a, double x) {
+  /* P(a,x) = x^a e^-x / Gamma(a+1) * sum_{n>=0} x^n / ((a+1)...(a+n)) */
+  double sum = 1.0, term = 1.0, ap = a;
+  for (int n = 0; n < 100000; ++n) {
+    ap += 1.0;
+    term *= x / ap;
+    sum += term;
+    if (fabs(term) < fabs(sum) * 1e-17) break;
+  }
+  return sum * exp(a * log(x) - x - lgamma(a + 1.0));
+}
+
+static inline double orc_gamma_q_cf(double a, double x) {
+  /* Q(a,x) = x^a e^-x / Gamma(a) * 1/(x+1-a- 1(1-a)/(x+3-a- 2(2-a)/(x+5-a- ...))) */
+  const double tiny = 1e-300;
+  double b = x + 1.0 - a;
+  double c = 1.0 / tiny;
+  double d = 1.0 / b;
+  double h = d;
+  for (int i = 1; i < 100000; ++i) {
+    double an = -(double)i * ((double)i - a);
+    b += 2.0;
+    d = an * d + b;
+    if (fabs(d) < tiny) d = tiny;
+    c = b + an / c;
+    if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < 1e-16) break;
+  }
+  return exp(a * log(x) - x - lgamma(a)) * h;
+}
+
+static inline double orc_gamma_q(double a, double x) {
+  if (!(a > 0.0) || x < 0.0) return NAN;
+  if (x == 0.0) return 1.0;
+  if (isinf(x)) return 0.0;
+  if (x < a + 1.0) {
+    double p = orc_gamma_p_series(a, x);
+    double q = 1.0 - p;
+    return q < 0.0 ? 0.0 : (q > 1.0 ? 1.0 : q);
+  } else {
+    double q = orc_gamma_q_cf(a, x);
+    return q < 0.0 ? 0.0 : (q > 1.0 ? 1.0 : q);
+  }
+}
+
+/* x such that Q(a,x) = q; bracketing + bisection refined by Newton steps (fp64). */
+static inline double orc_gamma_q_inv(double a, double q) {
+  if (q <= 0.0) return INFINITY;
+  if (q >= 1.0) return 0.0;
+  double lo = 0.0, hi = a > 1.0 ? a : 1.0;
+  while (orc_gamma_q(a, hi) > q) { lo = hi; hi *= 2.0; if (hi > 1e300) return INFINITY; }
+  double x = 0.5 * (lo + hi);
+  for (int it = 0; it < 400; ++it) {
+    double f = orc_gamma_q(a, x) - q;      /* decreasing in x */
+    if (f > 0.0) lo = x; else hi = x;
+    /* Newton step: dQ/dx = -x^(a-1) e^-x / Gamma(a) */
+    double dq = -exp((a - 1.0) * log(x) - x - lgamma(a));
+    double xn = (dq != 0.0 && isfinite(dq)) ? x - f / dq : 0.5 * (lo + hi);
+    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    if (fabs(xn - x) <= 4e-16 * fabs(x)) { x = xn; break; }
+    x = xn;
+  }
+  return x;
+}
+
+static inline double orc_safe_log_gamma_integral(double a, double x_min, double x_max) {
+  /* reference: core/safe_gamma_math.h:88-96 */
+  double q_hi = orc_gamma_q(a, x_min);
+  double q_lo = orc_gamma_q(a, x_max);
+  return log(q_hi - q_lo);
+}
+
+#endif /* DPHY_ORACLE_GAMMA_Q_H_ */
