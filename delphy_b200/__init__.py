@@ -1,0 +1,525 @@
+"""delphy_b200 -- B200-native EMAT log-G + SPR-regraft engine (Python harness over the C ABI).
+
+The product is ``libdelphy_b200.so`` (hand-written sm_100a CUDA behind ``include/delphy_b200.h``); the drop-in for
+the reference is the C++ adapter described in INTEGRATION.md.  This module is the thin ctypes binding the tests and
+bench.py use to drive that same C ABI.  It never imports anything from ``oracle/`` and has no CPU fallback: creating a
+:class:`Context` without a usable CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdelphy_b200.so")
+
+i32p = C.POINTER(C.c_int32)
+u8p = C.POINTER(C.c_uint8)
+f64p = C.POINTER(C.c_double)
+
+
+class DphyError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"delphy_b200 status {status}: {msg}")
+        self.status = status
+
+
+DPHY_OK, ERR_INVALID_ARGUMENT, ERR_OUT_OF_RANGE, ERR_CUDA, ERR_OOM, ERR_INTERNAL = 0, -1, -2, -3, -4, -5
+INT32_MAX = 2**31 - 1
+
+
+class EmatHost(C.Structure):
+    _fields_ = [
+        ("num_nodes", C.c_int32), ("root", C.c_int32), ("includes_run_root", C.c_int32), ("reserved", C.c_int32),
+        ("parent", i32p), ("child0", i32p), ("child1", i32p), ("t", f64p),
+        ("mut_off", i32p), ("mut_site", i32p), ("mut_from", u8p), ("mut_to", u8p), ("mut_t", f64p),
+        ("miss_off", i32p), ("miss_start", i32p), ("miss_end", i32p),
+        ("fs_off", i32p), ("fs_site", i32p), ("fs_from", u8p),
+    ]
+
+
+class SitesHost(C.Structure):
+    _fields_ = [
+        ("num_sites", C.c_int32), ("num_partitions", C.c_int32),
+        ("ref", u8p), ("partition_for_site", i32p), ("nu_l", f64p),
+        ("mu", f64p), ("pi_a", f64p), ("q_ab", f64p),
+    ]
+
+
+class CandidateRegion(C.Structure):
+    _fields_ = [
+        ("branch", C.c_int32), ("mut_idx", C.c_int32), ("t_min", C.c_double), ("t_max", C.c_double),
+        ("min_muts", C.c_int32), ("pad_", C.c_int32), ("log_W_over_Wmax", C.c_double), ("W_over_Wmax", C.c_double),
+    ]
+
+
+REGION_DTYPE = np.dtype([
+    ("branch", "<i4"), ("mut_idx", "<i4"), ("t_min", "<f8"), ("t_max", "<f8"),
+    ("min_muts", "<i4"), ("pad_", "<i4"), ("log_W_over_Wmax", "<f8"), ("W_over_Wmax", "<f8"),
+])
+
+
+class SprRequest(C.Structure):
+    _fields_ = [
+        ("tree", C.c_int32), ("X", C.c_int32), ("t_X", C.c_double),
+        ("start_branch", C.c_int32), ("start_mut_idx", C.c_int32),
+        ("init_min_muts", C.c_int32), ("max_muts_from_start", C.c_int32),
+        ("can_change_root", C.c_int32), ("reserved", C.c_int32),
+        ("lambda_X", C.c_double), ("annealing_factor", C.c_double), ("t_max_tip", C.c_double),
+        ("n_x_deltas", C.c_int32), ("x_delta_site", i32p), ("x_delta_to", u8p),
+        ("n_x_missing", C.c_int32), ("x_missing_start", i32p), ("x_missing_end", i32p),
+    ]
+
+
+class SprSummary(C.Structure):
+    _fields_ = [
+        ("mu", C.c_double), ("log_Wmax", C.c_double), ("sum_W_over_Wmax", C.c_double),
+        ("num_regions", C.c_int32), ("num_missing_at_X", C.c_int32), ("region_offset", C.c_int64),
+    ]
+
+
+class Tallies(C.Structure):
+    _fields_ = [
+        ("num_muts", C.c_int32), ("reserved", C.c_int32), ("num_muts_ab", C.c_int32 * 16),
+        ("T", C.c_double), ("log_root_prior", C.c_double), ("log_G_below_root", C.c_double),
+    ]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [
+        ("num_tips", C.c_int32), ("num_sites", C.c_int32), ("seed", C.c_uint64),
+        ("muts_per_tip", C.c_double), ("tip_date_span_years", C.c_double), ("growth_rate", C.c_double),
+        ("n0_years", C.c_double), ("kappa", C.c_double), ("pi", C.c_double * 4),
+        ("site_rate_heterogeneity", C.c_int32), ("gamma_alpha", C.c_double), ("num_partitions", C.c_int32),
+        ("missing_mean_intervals_per_tip", C.c_double), ("missing_len_min", C.c_double), ("missing_len_max", C.c_double),
+        ("end_gaps", C.c_int32), ("num_root_mutations", C.c_int32), ("caterpillar", C.c_int32),
+    ]
+
+
+class SynthEmat(C.Structure):
+    _fields_ = [
+        ("emat", EmatHost), ("sites", SitesHost), ("mu_used", C.c_double), ("t_max_tip", C.c_double),
+        ("num_mutations", C.c_int64), ("num_intervals", C.c_int64), ("num_from_states", C.c_int64),
+        ("num_missing_sites", C.c_int64), ("max_depth", C.c_int32), ("owner_", C.c_void_p),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc")
+    args = ["make", "-s", "-C", src]
+    if force:
+        subprocess.run(args + ["clean"], check=True)
+    subprocess.run(args, check=True)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.dphy_version.restype = C.c_char_p
+    L.dphy_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.dphy_ctx_destroy.argtypes = [vp]
+    L.dphy_last_error.argtypes = [vp]; L.dphy_last_error.restype = C.c_char_p
+    L.dphy_ctx_synchronize.argtypes = [vp]
+    L.dphy_arena_stats.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.dphy_ctx_stream.argtypes = [vp]; L.dphy_ctx_stream.restype = vp
+    L.dphy_ctx_launch_count.argtypes = [vp]; L.dphy_ctx_launch_count.restype = C.c_int64
+    L.dphy_sites_upload.argtypes = [vp, C.POINTER(SitesHost), C.POINTER(vp)]
+    L.dphy_sites_destroy.argtypes = [vp, vp]
+    L.dphy_sites_set_evo.argtypes = [vp, vp, f64p, f64p, f64p, f64p]
+    L.dphy_calc_state_frequencies_per_partition.argtypes = [vp, vp, i32p]
+    L.dphy_calc_cum_Q_l.argtypes = [vp, vp, f64p]
+    L.dphy_forest_upload.argtypes = [vp, C.c_int32, C.POINTER(EmatHost), i32p, C.c_int32, C.POINTER(vp), C.POINTER(vp)]
+    L.dphy_forest_destroy.argtypes = [vp, vp]
+    L.dphy_forest_num_nodes.argtypes = [vp]; L.dphy_forest_num_nodes.restype = C.c_int64
+    L.dphy_forest_device_bytes.argtypes = [vp]; L.dphy_forest_device_bytes.restype = C.c_int64
+    L.dphy_forest_log_G_algorithmic_bytes.argtypes = [vp]; L.dphy_forest_log_G_algorithmic_bytes.restype = C.c_int64
+    L.dphy_forest_set_node_times.argtypes = [vp, vp, C.c_int32, C.c_int32, i32p, f64p]
+    L.dphy_forest_eval_log_G.argtypes = [vp, vp]
+    L.dphy_forest_get_log_G.argtypes = [vp, vp, f64p, f64p, f64p]
+    L.dphy_forest_get_lambda_i.argtypes = [vp, vp, C.c_int32, f64p]
+    L.dphy_forest_get_num_sites_missing.argtypes = [vp, vp, C.c_int32, i32p]
+    L.dphy_log_G_host.argtypes = [vp, C.POINTER(EmatHost), C.POINTER(SitesHost), f64p, f64p, f64p]
+    L.dphy_forest_calc_tallies.argtypes = [vp, vp, C.POINTER(Tallies)]
+    L.dphy_forest_calc_num_muts_beta_ab.argtypes = [vp, vp, C.c_int32, i32p]
+    L.dphy_forest_calc_num_muts_l.argtypes = [vp, vp, C.c_int32, i32p, i32p]
+    L.dphy_forest_calc_Ttwiddle_beta_a.argtypes = [vp, vp, C.c_int32, f64p]
+    L.dphy_forest_calc_Ttwiddle_l.argtypes = [vp, vp, C.c_int32, f64p, f64p]
+    L.dphy_spr_study_batch.argtypes = [vp, vp, C.c_int32, C.POINTER(SprRequest), C.POINTER(vp)]
+    L.dphy_spr_batch_destroy.argtypes = [vp, vp]
+    L.dphy_spr_batch_get_summaries.argtypes = [vp, vp, C.POINTER(SprSummary)]
+    L.dphy_spr_batch_total_regions.argtypes = [vp, vp]; L.dphy_spr_batch_total_regions.restype = C.c_int64
+    L.dphy_spr_batch_get_regions.argtypes = [vp, vp, C.c_int32, C.POINTER(CandidateRegion), C.c_int64]
+    L.dphy_spr_batch_get_regions.restype = C.c_int64
+    L.dphy_spr_batch_pick_nexus_regions.argtypes = [vp, vp, f64p, i32p]
+    L.dphy_spr_batch_find_region.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_double, i32p]
+    L.dphy_synth_default_params.argtypes = [C.POINTER(SynthParams), C.c_int32]
+    L.dphy_synth_generate.argtypes = [C.POINTER(SynthParams), C.POINTER(C.POINTER(SynthEmat))]
+    L.dphy_synth_free.argtypes = [C.POINTER(SynthEmat)]
+    _LIB = L
+    return L
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(ty)
+
+
+def _np_from(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+class HostEmat:
+    """Numpy-owned flat EMAT (host node order).  Field names follow include/delphy_b200.h."""
+    FIELDS_I32 = ("parent", "child0", "child1", "mut_off", "mut_site", "miss_off", "miss_start", "miss_end", "fs_off", "fs_site")
+    FIELDS_U8 = ("mut_from", "mut_to", "fs_from")
+    FIELDS_F64 = ("t", "mut_t")
+
+    def __init__(self, root, includes_run_root=1, **arrays):
+        self.root = int(root)
+        self.includes_run_root = int(includes_run_root)
+        for k in self.FIELDS_I32:
+            setattr(self, k, np.ascontiguousarray(arrays[k], np.int32))
+        for k in self.FIELDS_U8:
+            setattr(self, k, np.ascontiguousarray(arrays[k], np.uint8))
+        for k in self.FIELDS_F64:
+            setattr(self, k, np.ascontiguousarray(arrays[k], np.float64))
+
+    @property
+    def num_nodes(self):
+        return int(self.parent.shape[0])
+
+    def as_struct(self) -> EmatHost:
+        return EmatHost(self.num_nodes, self.root, self.includes_run_root, 0,
+                        _p(self.parent, i32p), _p(self.child0, i32p), _p(self.child1, i32p), _p(self.t, f64p),
+                        _p(self.mut_off, i32p), _p(self.mut_site, i32p), _p(self.mut_from, u8p), _p(self.mut_to, u8p),
+                        _p(self.mut_t, f64p), _p(self.miss_off, i32p), _p(self.miss_start, i32p), _p(self.miss_end, i32p),
+                        _p(self.fs_off, i32p), _p(self.fs_site, i32p), _p(self.fs_from, u8p))
+
+
+class HostSites:
+    def __init__(self, ref, partition_for_site, nu_l, mu, pi_a, q_ab):
+        self.ref = np.ascontiguousarray(ref, np.uint8)
+        self.partition_for_site = np.ascontiguousarray(partition_for_site, np.int32)
+        self.nu_l = np.ascontiguousarray(nu_l, np.float64)
+        self.mu = np.ascontiguousarray(mu, np.float64).reshape(-1)
+        self.pi_a = np.ascontiguousarray(pi_a, np.float64).reshape(-1, 4)
+        self.q_ab = np.ascontiguousarray(q_ab, np.float64).reshape(-1, 4, 4)
+
+    @property
+    def num_sites(self):
+        return int(self.ref.shape[0])
+
+    @property
+    def num_partitions(self):
+        return int(self.mu.shape[0])
+
+    def as_struct(self) -> SitesHost:
+        return SitesHost(self.num_sites, self.num_partitions, _p(self.ref, u8p), _p(self.partition_for_site, i32p),
+                         _p(self.nu_l, f64p), _p(self.mu, f64p), _p(self.pi_a, f64p), _p(self.q_ab, f64p))
+
+
+def synth_params(config: int = 0, **overrides) -> SynthParams:
+    p = SynthParams()
+    lib().dphy_synth_default_params(C.byref(p), config)
+    for k, v in overrides.items():
+        if k == "pi":
+            for i in range(4):
+                p.pi[i] = v[i]
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def synth_generate(params: SynthParams):
+    """Returns (HostEmat, HostSites, info dict) -- numpy copies of a synthetic EMAT."""
+    L = lib()
+    out = C.POINTER(SynthEmat)()
+    st = L.dphy_synth_generate(C.byref(params), C.byref(out))
+    if st != DPHY_OK:
+        raise DphyError(st, "dphy_synth_generate")
+    try:
+        s = out.contents
+        e = s.emat
+        N = e.num_nodes
+        M = int(e.mut_off[N]); I = int(e.miss_off[N]); F = int(e.fs_off[N])
+        emat = HostEmat(
+            e.root, e.includes_run_root,
+            parent=_np_from(e.parent, N, np.int32), child0=_np_from(e.child0, N, np.int32), child1=_np_from(e.child1, N, np.int32),
+            t=_np_from(e.t, N, np.float64),
+            mut_off=_np_from(e.mut_off, N + 1, np.int32), mut_site=_np_from(e.mut_site, M, np.int32),
+            mut_from=_np_from(e.mut_from, M, np.uint8), mut_to=_np_from(e.mut_to, M, np.uint8), mut_t=_np_from(e.mut_t, M, np.float64),
+            miss_off=_np_from(e.miss_off, N + 1, np.int32), miss_start=_np_from(e.miss_start, I, np.int32), miss_end=_np_from(e.miss_end, I, np.int32),
+            fs_off=_np_from(e.fs_off, N + 1, np.int32), fs_site=_np_from(e.fs_site, F, np.int32), fs_from=_np_from(e.fs_from, F, np.uint8))
+        ss = s.sites
+        Ls, P = ss.num_sites, ss.num_partitions
+        sites = HostSites(_np_from(ss.ref, Ls, np.uint8), _np_from(ss.partition_for_site, Ls, np.int32), _np_from(ss.nu_l, Ls, np.float64),
+                          _np_from(ss.mu, P, np.float64), _np_from(ss.pi_a, P * 4, np.float64), _np_from(ss.q_ab, P * 16, np.float64))
+        info = dict(mu=s.mu_used, t_max_tip=s.t_max_tip, num_mutations=int(s.num_mutations), num_intervals=int(s.num_intervals),
+                    num_from_states=int(s.num_from_states), num_missing_sites=int(s.num_missing_sites), max_depth=int(s.max_depth))
+        return emat, sites, info
+    finally:
+        L.dphy_synth_free(out)
+
+
+class Context:
+    """One CUDA device + stream + device arena (one per host thread / Subrun)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        st = lib().dphy_ctx_create(device, C.byref(self._h))
+        if st != DPHY_OK:
+            raise DphyError(st, "dphy_ctx_create failed: a CUDA device is required (no CPU fallback)")
+
+    def check(self, st: int):
+        if st != DPHY_OK:
+            raise DphyError(st, lib().dphy_last_error(self._h).decode())
+
+    def synchronize(self):
+        self.check(lib().dphy_ctx_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().dphy_ctx_stream(self._h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().dphy_ctx_launch_count(self._h))
+
+    def arena_stats(self):
+        cap, hw = C.c_size_t(), C.c_size_t()
+        self.check(lib().dphy_arena_stats(self._h, C.byref(cap), C.byref(hw)))
+        return cap.value, hw.value
+
+    def close(self):
+        if self._h:
+            lib().dphy_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- one-shot host-buffer call (what the C++ adapter does for Subrun::calc_cur_log_G)
+    def log_G_host(self, emat: HostEmat, sites: HostSites, want_lambda=False):
+        rp, br = C.c_double(), C.c_double()
+        lam = np.zeros(emat.num_nodes, np.float64) if want_lambda else None
+        es, ss = emat.as_struct(), sites.as_struct()
+        self.check(lib().dphy_log_G_host(self._h, C.byref(es), C.byref(ss), C.byref(rp), C.byref(br),
+                                         _p(lam, f64p) if want_lambda else None))
+        return rp.value, br.value, lam
+
+
+class DeviceSites:
+    def __init__(self, ctx: Context, sites: HostSites):
+        self.ctx = ctx
+        self.host = sites
+        self._h = C.c_void_p()
+        ss = sites.as_struct()
+        ctx.check(lib().dphy_sites_upload(ctx._h, C.byref(ss), C.byref(self._h)))
+
+    def set_evo(self, nu_l=None, mu=None, pi_a=None, q_ab=None):
+        h = self.host
+        if nu_l is not None:
+            h.nu_l = np.ascontiguousarray(nu_l, np.float64)
+        if mu is not None:
+            h.mu = np.ascontiguousarray(mu, np.float64).reshape(-1)
+        if pi_a is not None:
+            h.pi_a = np.ascontiguousarray(pi_a, np.float64).reshape(-1, 4)
+        if q_ab is not None:
+            h.q_ab = np.ascontiguousarray(q_ab, np.float64).reshape(-1, 4, 4)
+        self.ctx.check(lib().dphy_sites_set_evo(self.ctx._h, self._h, _p(h.nu_l, f64p), _p(h.mu, f64p), _p(h.pi_a, f64p), _p(h.q_ab, f64p)))
+
+    def state_frequencies(self):
+        out = np.zeros((self.host.num_partitions, 4), np.int32)
+        self.ctx.check(lib().dphy_calc_state_frequencies_per_partition(self.ctx._h, self._h, _p(out, i32p)))
+        return out
+
+    def cum_Q_l(self):
+        out = np.zeros(self.host.num_sites + 1, np.float64)
+        self.ctx.check(lib().dphy_calc_cum_Q_l(self.ctx._h, self._h, _p(out, f64p)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().dphy_sites_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+
+class Forest:
+    """Device-resident batch of EMATs."""
+
+    def __init__(self, ctx: Context, emats, sites_tables, sites_index=None):
+        self.ctx = ctx
+        self.emats = list(emats)
+        self.sites_tables = list(sites_tables)
+        n = len(self.emats)
+        arr = (EmatHost * max(n, 1))(*[e.as_struct() for e in self.emats])
+        idx = np.ascontiguousarray(sites_index if sites_index is not None else np.zeros(n), np.int32)
+        self.sites_index = idx
+        sp = (C.c_void_p * len(self.sites_tables))(*[s._h for s in self.sites_tables])
+        self._h = C.c_void_p()
+        ctx.check(lib().dphy_forest_upload(ctx._h, n, arr, _p(idx, i32p), len(self.sites_tables), sp, C.byref(self._h)))
+
+    @property
+    def num_trees(self):
+        return len(self.emats)
+
+    @property
+    def num_nodes(self):
+        return int(lib().dphy_forest_num_nodes(self._h))
+
+    @property
+    def device_bytes(self):
+        return int(lib().dphy_forest_device_bytes(self._h))
+
+    @property
+    def log_G_algorithmic_bytes(self):
+        return int(lib().dphy_forest_log_G_algorithmic_bytes(self._h))
+
+    def eval_log_G(self):
+        """Asynchronous: enqueue one log-G evaluation of every tree."""
+        self.ctx.check(lib().dphy_forest_eval_log_G(self.ctx._h, self._h))
+
+    def log_G(self):
+        n = self.num_trees
+        rp, br, lg = np.zeros(n), np.zeros(n), np.zeros(n)
+        self.ctx.check(lib().dphy_forest_get_log_G(self.ctx._h, self._h, _p(rp, f64p), _p(br, f64p), _p(lg, f64p)))
+        return rp, br, lg
+
+    def lambda_i(self, tree=0):
+        out = np.zeros(self.emats[tree].num_nodes, np.float64)
+        self.ctx.check(lib().dphy_forest_get_lambda_i(self.ctx._h, self._h, tree, _p(out, f64p)))
+        return out
+
+    def num_sites_missing(self, tree=0):
+        out = np.zeros(self.emats[tree].num_nodes, np.int32)
+        self.ctx.check(lib().dphy_forest_get_num_sites_missing(self.ctx._h, self._h, tree, _p(out, i32p)))
+        return out
+
+    def set_node_times(self, tree, nodes, t):
+        nodes = np.ascontiguousarray(nodes, np.int32); t = np.ascontiguousarray(t, np.float64)
+        self.ctx.check(lib().dphy_forest_set_node_times(self.ctx._h, self._h, tree, len(nodes), _p(nodes, i32p), _p(t, f64p)))
+
+    def tallies(self):
+        out = (Tallies * self.num_trees)()
+        self.ctx.check(lib().dphy_forest_calc_tallies(self.ctx._h, self._h, out))
+        return [dict(num_muts=o.num_muts, num_muts_ab=np.array(o.num_muts_ab[:], np.int32).reshape(4, 4), T=o.T,
+                     log_root_prior=o.log_root_prior, log_G_below_root=o.log_G_below_root) for o in out]
+
+    def num_muts_beta_ab(self, tree=0):
+        P = self.sites_tables[self.sites_index[tree]].host.num_partitions
+        out = np.zeros((P, 4, 4), np.int32)
+        self.ctx.check(lib().dphy_forest_calc_num_muts_beta_ab(self.ctx._h, self._h, tree, _p(out, i32p)))
+        return out
+
+    def num_muts_l(self, tree=0, want_ab=True):
+        L = self.sites_tables[self.sites_index[tree]].host.num_sites
+        out_l = np.zeros(L, np.int32)
+        out_ab = np.zeros((L, 4, 4), np.int32) if want_ab else None
+        self.ctx.check(lib().dphy_forest_calc_num_muts_l(self.ctx._h, self._h, tree, _p(out_l, i32p),
+                                                         _p(out_ab, i32p) if want_ab else None))
+        return out_l, out_ab
+
+    def Ttwiddle_beta_a(self, tree=0):
+        P = self.sites_tables[self.sites_index[tree]].host.num_partitions
+        out = np.zeros((P, 4), np.float64)
+        self.ctx.check(lib().dphy_forest_calc_Ttwiddle_beta_a(self.ctx._h, self._h, tree, _p(out, f64p)))
+        return out
+
+    def Ttwiddle_l(self, tree=0, want_T_l_a=True):
+        L = self.sites_tables[self.sites_index[tree]].host.num_sites
+        out_l = np.zeros(L, np.float64)
+        out_la = np.zeros((L, 4), np.float64) if want_T_l_a else None
+        self.ctx.check(lib().dphy_forest_calc_Ttwiddle_l(self.ctx._h, self._h, tree, _p(out_l, f64p),
+                                                         _p(out_la, f64p) if want_T_l_a else None))
+        return out_l, out_la
+
+    # -- SPR studies
+    def spr_study_batch(self, requests):
+        return SprBatch(self, requests)
+
+    def close(self):
+        if self._h:
+            lib().dphy_forest_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+
+def spr_request(tree, X, t_X, start_branch, start_mut_idx, init_min_muts, lambda_X, t_max_tip,
+                max_muts_from_start=INT32_MAX, can_change_root=True, annealing_factor=0.8,
+                x_deltas=None, x_missing=None):
+    r = SprRequest()
+    r.tree, r.X, r.t_X = tree, X, t_X
+    r.start_branch, r.start_mut_idx, r.init_min_muts = start_branch, start_mut_idx, init_min_muts
+    r.max_muts_from_start, r.can_change_root = max_muts_from_start, int(can_change_root)
+    r.lambda_X, r.annealing_factor, r.t_max_tip = lambda_X, annealing_factor, t_max_tip
+    keep = []
+    if x_deltas is not None:
+        s = np.ascontiguousarray([d[0] for d in x_deltas], np.int32); t = np.ascontiguousarray([d[1] for d in x_deltas], np.uint8)
+        r.n_x_deltas, r.x_delta_site, r.x_delta_to = len(s), _p(s, i32p), _p(t, u8p)
+        keep += [s, t]
+    if x_missing is not None:
+        a = np.ascontiguousarray(x_missing[0], np.int32); b = np.ascontiguousarray(x_missing[1], np.int32)
+        r.n_x_missing, r.x_missing_start, r.x_missing_end = len(a), _p(a, i32p), _p(b, i32p)
+        keep += [a, b]
+    r._keep = keep
+    return r
+
+
+class SprBatch:
+    def __init__(self, forest: Forest, requests):
+        self.forest = forest
+        self.ctx = forest.ctx
+        self.requests = list(requests)
+        n = len(self.requests)
+        arr = (SprRequest * max(n, 1))(*self.requests)
+        self._h = C.c_void_p()
+        self.ctx.check(lib().dphy_spr_study_batch(self.ctx._h, forest._h, n, arr, C.byref(self._h)))
+
+    def summaries(self):
+        out = (SprSummary * max(len(self.requests), 1))()
+        self.ctx.check(lib().dphy_spr_batch_get_summaries(self.ctx._h, self._h, out))
+        return list(out)[:len(self.requests)]
+
+    def total_regions(self):
+        return int(lib().dphy_spr_batch_total_regions(self.ctx._h, self._h))
+
+    def regions(self, request=-1):
+        n = self.total_regions() if request < 0 else self.summaries()[request].num_regions
+        out = np.zeros(max(n, 1), REGION_DTYPE)
+        got = lib().dphy_spr_batch_get_regions(self.ctx._h, self._h, request, _p(out, C.POINTER(CandidateRegion)), n)
+        if got < 0:
+            self.ctx.check(int(got))
+        return out[:got]
+
+    def pick_nexus_regions(self, r):
+        r = np.ascontiguousarray(r, np.float64)
+        out = np.zeros(len(self.requests), np.int32)
+        self.ctx.check(lib().dphy_spr_batch_pick_nexus_regions(self.ctx._h, self._h, _p(r, f64p), _p(out, i32p)))
+        return out
+
+    def find_region(self, request, branch, t):
+        out = C.c_int32(-2)
+        self.ctx.check(lib().dphy_spr_batch_find_region(self.ctx._h, self._h, request, branch, t, C.byref(out)))
+        return out.value
+
+    def close(self):
+        if self._h:
+            lib().dphy_spr_batch_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()

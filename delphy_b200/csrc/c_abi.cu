@@ -1,0 +1,516 @@
+// c_abi.cu -- host side of the C ABI declared in include/delphy_b200.h: context, device arena, upload of the
+// flattened EMATs (host node order -> device DFS order), result download.  No CPU fallback anywhere: if CUDA is not
+// usable every compute entry point fails with DPHY_ERR_CUDA.
+#include "dphy_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+
+namespace dphy {
+
+int set_error(dphy_ctx* ctx, int status, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  return status;
+}
+int check_cuda(dphy_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return DPHY_OK;
+  return set_error(ctx, DPHY_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+namespace {
+
+constexpr size_t kAlign = 256;
+size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+// Pinned staging buffer owned by the ctx, grown geometrically.
+int ensure_pinned(dphy_ctx* ctx, size_t bytes) {
+  if (ctx->pinned_bytes >= bytes) return DPHY_OK;
+  if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+  size_t want = std::max(bytes, (size_t)1 << 20);
+  want = std::max(want, ctx->pinned_bytes * 2);
+  DPHY_CUDA(ctx, cudaMallocHost(&ctx->pinned, want));
+  ctx->pinned_bytes = want;
+  return DPHY_OK;
+}
+
+// A layout planner: reserve() all blocks, then carve them out of one host staging slab and one device slab.
+struct Slab {
+  struct Block { size_t off, bytes; };
+  std::vector<Block> blocks;
+  size_t total = 0;
+  int reserve(size_t bytes) {
+    blocks.push_back({total, bytes});
+    total = align_up(total + std::max<size_t>(bytes, 1));
+    return (int)blocks.size() - 1;
+  }
+  template <typename T> T* at(void* base, int id) const { return reinterpret_cast<T*>(static_cast<char*>(base) + blocks[id].off); }
+};
+
+}  // namespace
+
+// Forests hold a device copy of each SitesDev record; re-sync it after dphy_sites_set_evo changed mu/pi/q.
+int refresh_sites(dphy_ctx* ctx, dphy_forest* fo) {
+  for (size_t i = 0; i < fo->sites.size(); ++i) {
+    if (fo->sites_version[i] != fo->sites[i]->version) {
+      DPHY_CUDA(ctx, cudaMemcpyAsync(const_cast<SitesDev*>(fo->h.sites) + i, &fo->sites[i]->h, sizeof(SitesDev),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+      fo->sites_version[i] = fo->sites[i]->version;
+    }
+  }
+  return DPHY_OK;
+}
+}  // namespace dphy
+
+using namespace dphy;
+
+extern "C" {
+
+const char* dphy_version(void) { return "delphy_b200 0.1 (sm_100a)"; }
+
+int dphy_ctx_create(int device, dphy_ctx** out) {
+  if (!out) return DPHY_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    return DPHY_ERR_CUDA;   // no CPU fallback: the product path requires a CUDA device
+  }
+  auto* ctx = new (std::nothrow) dphy_ctx();
+  if (!ctx) return DPHY_ERR_OUT_OF_MEMORY;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DPHY_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DPHY_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  // keep freed stream-ordered allocations cached in the pool (no cudaMalloc on the hot path after warm-up)
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  ctx->arena.capacity = (size_t)256 << 20;
+  if (cudaMalloc((void**)&ctx->arena.base, ctx->arena.capacity) != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream); delete ctx; return DPHY_ERR_OUT_OF_MEMORY;
+  }
+  *out = ctx;
+  return DPHY_OK;
+}
+
+void dphy_ctx_destroy(dphy_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->arena.base) cudaFree(ctx->arena.base);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* dphy_last_error(const dphy_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context (CUDA device unavailable?)"; }
+
+int dphy_ctx_synchronize(dphy_ctx* ctx) {
+  if (!ctx) return DPHY_ERR_INVALID_ARGUMENT;
+  DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPHY_OK;
+}
+
+int dphy_arena_stats(const dphy_ctx* ctx, size_t* capacity, size_t* high_water) {
+  if (!ctx) return DPHY_ERR_INVALID_ARGUMENT;
+  if (capacity) *capacity = ctx->arena.capacity;
+  if (high_water) *high_water = ctx->arena.high_water;
+  return DPHY_OK;
+}
+
+void* dphy_ctx_stream(dphy_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int64_t dphy_ctx_launch_count(const dphy_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- sites ------------------------------------------------------------------------------------------------------
+static int fill_evo(dphy_ctx* ctx, dphy_sites* s, const double* mu, const double* pi_a, const double* q_ab) {
+  for (int b = 0; b < s->P; ++b) {
+    s->h.mu[b] = mu[b];
+    if (!(mu[b] >= 0.0)) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "mu must be >= 0");
+    for (int a = 0; a < 4; ++a) {
+      s->h.pi[b * 4 + a] = pi_a[b * 4 + a];
+      s->h.log_pi[b * 4 + a] = pi_a[b * 4 + a] != 0.0 ? std::log(pi_a[b * 4 + a]) : 0.0;
+      for (int c = 0; c < 4; ++c) s->h.q[b * 16 + a * 4 + c] = q_ab[b * 16 + a * 4 + c];
+    }
+  }
+  return DPHY_OK;
+}
+
+int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** out) {
+  if (!ctx || !host || !out) return DPHY_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  const int L = host->num_sites, P = host->num_partitions;
+  if (L <= 0) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "num_sites must be > 0");
+  if (P <= 0 || P > kMaxPartitions) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "num_partitions must be in [1,4]");
+  for (int l = 0; l < L; ++l) {
+    if (host->ref[l] > 3) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "ref_sequence holds a non-ACGT state");
+    if (host->partition_for_site[l] < 0 || host->partition_for_site[l] >= P)
+      return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "partition_for_site out of range");
+  }
+  auto* s = new (std::nothrow) dphy_sites();
+  if (!s) return DPHY_ERR_OUT_OF_MEMORY;
+  s->L = L; s->P = P;
+  int st = fill_evo(ctx, s, host->mu, host->pi_a, host->q_ab);
+  if (st != DPHY_OK) { delete s; return st; }
+  cudaSetDevice(ctx->device);
+  Slab slab;
+  const int b_ref = slab.reserve(L), b_part = slab.reserve(L), b_nu = slab.reserve(sizeof(double) * L);
+  const size_t upload_bytes = slab.total;
+  const int b_munu = slab.reserve(sizeof(double) * L), b_cumQ = slab.reserve(sizeof(double) * (L + 1));
+  const int b_freq = slab.reserve(sizeof(int32_t) * kMaxPartitions * 4);
+  const int b_cnu = slab.reserve(sizeof(double) * (size_t)P * 4 * (L + 1));
+  char* dbase = nullptr;
+  if (cudaMalloc((void**)&dbase, slab.total) != cudaSuccess) { delete s; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMalloc(sites)"); }
+  s->bytes = slab.total;
+  st = ensure_pinned(ctx, upload_bytes);
+  if (st != DPHY_OK) { cudaFree(dbase); delete s; return st; }
+  char* hb = static_cast<char*>(ctx->pinned);
+  std::memcpy(slab.at<uint8_t>(hb, b_ref), host->ref, L);
+  uint8_t* hp = slab.at<uint8_t>(hb, b_part);
+  for (int l = 0; l < L; ++l) hp[l] = (uint8_t)host->partition_for_site[l];
+  std::memcpy(slab.at<double>(hb, b_nu), host->nu_l, sizeof(double) * L);
+  s->d_ref = slab.at<uint8_t>(dbase, b_ref); s->d_part = slab.at<uint8_t>(dbase, b_part); s->d_nu = slab.at<double>(dbase, b_nu);
+  s->d_munu = slab.at<double>(dbase, b_munu); s->d_cumQ = slab.at<double>(dbase, b_cumQ);
+  s->d_ref_freq = slab.at<int32_t>(dbase, b_freq); s->d_cum_nu_ba = slab.at<double>(dbase, b_cnu);
+  s->h.L = L; s->h.P = P; s->h.ref = s->d_ref; s->h.part = s->d_part; s->h.nu = s->d_nu; s->h.munu = s->d_munu;
+  s->h.cumQ = s->d_cumQ; s->h.ref_freq = s->d_ref_freq;
+  cudaError_t e = cudaMemcpyAsync(dbase, hb, upload_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) { cudaFree(dbase); delete s; return check_cuda(ctx, e, "H2D sites"); }
+  st = launch_sites_derive(ctx, s);
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sites derive");   // pinned buffer reusable
+  if (st != DPHY_OK) { cudaFree(dbase); delete s; return st; }
+  *out = s;
+  return DPHY_OK;
+}
+
+void dphy_sites_destroy(dphy_ctx* ctx, dphy_sites* s) {
+  if (!s) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (s->d_ref) cudaFree(s->d_ref);   // base of the slab
+  delete s;
+}
+
+int dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* s, const double* nu_l, const double* mu, const double* pi_a, const double* q_ab) {
+  if (!ctx || !s || !mu || !pi_a || !q_ab) return DPHY_ERR_INVALID_ARGUMENT;
+  int st = fill_evo(ctx, s, mu, pi_a, q_ab);
+  if (st != DPHY_OK) return st;
+  if (nu_l) {
+    st = ensure_pinned(ctx, sizeof(double) * s->L);
+    if (st != DPHY_OK) return st;
+    std::memcpy(ctx->pinned, nu_l, sizeof(double) * s->L);
+    DPHY_CUDA(ctx, cudaMemcpyAsync(s->d_nu, ctx->pinned, sizeof(double) * s->L, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  s->version += 1;
+  st = launch_sites_derive(ctx, s);
+  if (st != DPHY_OK) return st;
+  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sites set_evo");
+}
+
+int dphy_calc_state_frequencies_per_partition(dphy_ctx* ctx, dphy_sites* s, int32_t* out) {
+  if (!ctx || !s || !out) return DPHY_ERR_INVALID_ARGUMENT;
+  DPHY_CUDA(ctx, cudaMemcpyAsync(out, s->d_ref_freq, sizeof(int32_t) * s->P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "state frequencies D2H");
+}
+
+int dphy_calc_cum_Q_l(dphy_ctx* ctx, dphy_sites* s, double* out) {
+  if (!ctx || !s || !out) return DPHY_ERR_INVALID_ARGUMENT;
+  DPHY_CUDA(ctx, cudaMemcpyAsync(out, s->d_cumQ, sizeof(double) * (s->L + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "cum_Q_l D2H");
+}
+
+// ---- forest -------------------------------------------------------------------------------------------------------
+int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* trees, const int32_t* sites_index,
+                       int32_t num_sites_tables, dphy_sites* const* sites, dphy_forest** out) {
+  if (!ctx || !out || num_trees < 0 || (num_trees > 0 && (!trees || !sites)) || num_sites_tables <= 0) return DPHY_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  int64_t N = 0, M = 0, I = 0, F = 0, tiles = 0, Mnr = 0;
+  for (int k = 0; k < num_trees; ++k) {
+    const auto& e = trees[k];
+    if (e.num_nodes <= 0) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "empty tree");
+    if (e.root < 0 || e.root >= e.num_nodes) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "root out of range");
+    const int si = sites_index ? sites_index[k] : 0;
+    if (si < 0 || si >= num_sites_tables) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "sites_index out of range");
+    N += e.num_nodes; M += e.mut_off[e.num_nodes]; I += e.miss_off[e.num_nodes]; F += e.fs_off[e.num_nodes];
+    Mnr += e.mut_off[e.num_nodes] - (e.mut_off[e.root + 1] - e.mut_off[e.root]);
+    tiles += (e.num_nodes + kTile - 1) / kTile;
+  }
+  if (N > std::numeric_limits<int32_t>::max() / 2 || M > std::numeric_limits<int32_t>::max() / 2)
+    return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "forest too large for 32-bit positions");
+
+  auto* fo = new (std::nothrow) dphy_forest();
+  if (!fo) return DPHY_ERR_OUT_OF_MEMORY;
+  fo->total_muts = M; fo->total_ivls = I; fo->total_fs = F; fo->total_nonroot_muts = Mnr;
+  fo->sites.assign(sites, sites + num_sites_tables);
+  fo->sites_version.resize(num_sites_tables);
+
+  Slab slab;
+  const int b_trees = slab.reserve(sizeof(TreeDev) * num_trees);
+  const int b_sites = slab.reserve(sizeof(SitesDev) * num_sites_tables);
+  const int b_tile_tree = slab.reserve(sizeof(int32_t) * tiles);
+  const int b_node_id = slab.reserve(sizeof(int32_t) * N), b_parent = slab.reserve(sizeof(int32_t) * N);
+  const int b_depth = slab.reserve(sizeof(int32_t) * N), b_size = slab.reserve(sizeof(int32_t) * N);
+  const int b_post = slab.reserve(sizeof(int32_t) * N), b_pos = slab.reserve(sizeof(int32_t) * N);
+  const int b_t = slab.reserve(sizeof(double) * N);
+  const int b_moff = slab.reserve(sizeof(int32_t) * (N + 1)), b_msite = slab.reserve(sizeof(int32_t) * M);
+  const int b_mft = slab.reserve(M), b_mt = slab.reserve(sizeof(double) * M);
+  const int b_ioff = slab.reserve(sizeof(int32_t) * (N + 1)), b_is = slab.reserve(sizeof(int32_t) * I), b_ie = slab.reserve(sizeof(int32_t) * I);
+  const int b_foff = slab.reserve(sizeof(int32_t) * (N + 1)), b_fsite = slab.reserve(sizeof(int32_t) * F), b_ffrom = slab.reserve(F);
+  const size_t upload_bytes = slab.total;
+  // outputs + workspaces (device only)
+  const int b_lambda = slab.reserve(sizeof(double) * N), b_nsmn = slab.reserve(sizeof(int32_t) * N);
+  const int b_tout = slab.reserve(sizeof(double) * 4 * num_trees), b_tiout = slab.reserve(sizeof(int32_t) * 20 * num_trees);
+  const int b_tagg = slab.reserve(sizeof(double) * tiles), b_tiagg = slab.reserve(sizeof(int32_t) * tiles);
+  const int b_tpart = slab.reserve(sizeof(double) * 2 * tiles), b_tipart = slab.reserve(sizeof(int32_t) * 17 * tiles);
+  const size_t zero_from = slab.total;
+  const int b_tflag = slab.reserve(sizeof(uint32_t) * tiles);
+  const int b_tdone = slab.reserve(sizeof(uint32_t) * num_trees), b_ticket = slab.reserve(sizeof(uint32_t) * 4);
+  const size_t zero_to = slab.total;
+
+  int st = ensure_pinned(ctx, upload_bytes);
+  if (st != DPHY_OK) { delete fo; return st; }
+  char* hb = static_cast<char*>(ctx->pinned);
+  auto* h_trees = slab.at<TreeDev>(hb, b_trees);
+  auto* h_sites = slab.at<SitesDev>(hb, b_sites);
+  auto* h_tile_tree = slab.at<int32_t>(hb, b_tile_tree);
+  auto* h_node_id = slab.at<int32_t>(hb, b_node_id); auto* h_parent = slab.at<int32_t>(hb, b_parent);
+  auto* h_depth = slab.at<int32_t>(hb, b_depth); auto* h_size = slab.at<int32_t>(hb, b_size);
+  auto* h_post = slab.at<int32_t>(hb, b_post); auto* h_pos = slab.at<int32_t>(hb, b_pos);
+  auto* h_t = slab.at<double>(hb, b_t);
+  auto* h_moff = slab.at<int32_t>(hb, b_moff); auto* h_msite = slab.at<int32_t>(hb, b_msite);
+  auto* h_mft = slab.at<uint8_t>(hb, b_mft); auto* h_mt = slab.at<double>(hb, b_mt);
+  auto* h_ioff = slab.at<int32_t>(hb, b_ioff); auto* h_is = slab.at<int32_t>(hb, b_is); auto* h_ie = slab.at<int32_t>(hb, b_ie);
+  auto* h_foff = slab.at<int32_t>(hb, b_foff); auto* h_fsite = slab.at<int32_t>(hb, b_fsite); auto* h_ffrom = slab.at<uint8_t>(hb, b_ffrom);
+
+  for (int i = 0; i < num_sites_tables; ++i) {
+    if (!sites[i]) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "null sites table"); }
+    h_sites[i] = sites[i]->h;
+    fo->sites_version[i] = sites[i]->version;
+  }
+
+  std::vector<int32_t> stack;
+  int32_t base = 0, mpos = 0, ipos = 0, fpos = 0, tile_pos = 0;
+  fo->trees.resize(num_trees);
+  for (int k = 0; k < num_trees; ++k) {
+    const auto& e = trees[k];
+    const int n = e.num_nodes;
+    const int si = sites_index ? sites_index[k] : 0;
+    const int L = sites[si]->L;
+    // DFS pre-order, children[1] before children[0]; encode "exit" visits as ~v on the stack
+    int32_t* pos_of = h_pos + base;
+    std::fill(pos_of, pos_of + n, -1);
+    stack.clear(); stack.push_back(e.root);
+    int32_t next = 0, npost = 0;
+    if (e.parent[e.root] != -1) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "root has a parent"); }
+    while (!stack.empty()) {
+      int32_t v = stack.back(); stack.pop_back();
+      if (v < 0) {   // exit
+        v = ~v;
+        const int32_t p = pos_of[v];
+        h_size[base + p] = next - p;
+        h_post[base + npost++] = base + p;
+        continue;
+      }
+      if (v >= n || pos_of[v] != -1 || next >= n) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "tree topology is not a tree"); }
+      const int32_t p = next++;
+      pos_of[v] = p;
+      h_node_id[base + p] = v;
+      const int32_t par = e.parent[v];
+      h_parent[base + p] = par < 0 ? -1 : base + pos_of[par];
+      h_depth[base + p] = par < 0 ? 0 : h_depth[base + pos_of[par]] + 1;
+      h_t[base + p] = e.t[v];
+      // lists, device order
+      h_moff[base + p] = mpos;
+      for (int i = e.mut_off[v]; i < e.mut_off[v + 1]; ++i) {
+        const int l = e.mut_site[i];
+        if (l < 0 || l >= L) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "mutation site out of range"); }
+        if (e.mut_from[i] > 3 || e.mut_to[i] > 3) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "mutation state not in ACGT"); }
+        h_msite[mpos] = l; h_mft[mpos] = (uint8_t)(e.mut_from[i] << 2 | e.mut_to[i]); h_mt[mpos] = e.mut_t[i]; ++mpos;
+      }
+      h_ioff[base + p] = ipos;
+      for (int i = e.miss_off[v]; i < e.miss_off[v + 1]; ++i) {
+        const int s0 = e.miss_start[i], s1 = e.miss_end[i];
+        if (s0 < 0 || s1 > L || s0 >= s1) {   // core/mutations.h:187-191 throws std::out_of_range
+          delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "Missation out of range");
+        }
+        h_is[ipos] = s0; h_ie[ipos] = s1; ++ipos;
+      }
+      h_foff[base + p] = fpos;
+      for (int i = e.fs_off[v]; i < e.fs_off[v + 1]; ++i) {
+        const int l = e.fs_site[i];
+        if (l < 0 || l >= L) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "Missation out of range"); }
+        h_fsite[fpos] = l; h_ffrom[fpos] = e.fs_from[i]; ++fpos;
+      }
+      const int32_t c0 = e.child0[v], c1 = e.child1[v];
+      stack.push_back(~v);
+      if (c0 >= 0) {
+        if (c1 < 0 || e.parent[c0] != v || e.parent[c1] != v) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "child/parent mismatch"); }
+        stack.push_back(c0); stack.push_back(c1);   // children[1] is popped (visited) first
+      }
+    }
+    if (next != n) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "tree is disconnected"); }
+    TreeDev& T = fo->trees[k];
+    T.node_base = base; T.num_nodes = n; T.sites_id = si; T.first_tile = tile_pos;
+    T.num_tiles = (n + kTile - 1) / kTile; T.includes_run_root = e.includes_run_root; T.root_id = e.root; T.pad = 0;
+    for (int j = 0; j < T.num_tiles; ++j) h_tile_tree[tile_pos++] = k;
+    h_trees[k] = T;
+    base += n;
+  }
+  h_moff[N] = mpos; h_ioff[N] = ipos; h_foff[N] = fpos;
+
+  char* dbase = nullptr;
+  cudaError_t ce = cudaMalloc((void**)&dbase, slab.total);
+  if (ce != cudaSuccess) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMalloc(forest)"); }
+  fo->allocs.push_back(dbase);
+  fo->bytes = slab.total;
+  ce = cudaMemcpyAsync(dbase, hb, upload_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(dbase + zero_from, 0, zero_to - zero_from, ctx->stream);
+  if (ce != cudaSuccess) { cudaFree(dbase); delete fo; return check_cuda(ctx, ce, "H2D forest"); }
+
+  ForestDev& h = fo->h;
+  h.num_trees = num_trees; h.num_nodes = (int32_t)N; h.num_tiles = (int32_t)tiles; h.num_sites_tables = num_sites_tables;
+  h.trees = slab.at<TreeDev>(dbase, b_trees); h.sites = slab.at<SitesDev>(dbase, b_sites);
+  h.tile_tree = slab.at<int32_t>(dbase, b_tile_tree);
+  h.node_id = slab.at<int32_t>(dbase, b_node_id); h.parent_pos = slab.at<int32_t>(dbase, b_parent);
+  h.depth = slab.at<int32_t>(dbase, b_depth); h.subtree_size = slab.at<int32_t>(dbase, b_size);
+  h.post_node = slab.at<int32_t>(dbase, b_post); h.pos_of_node = slab.at<int32_t>(dbase, b_pos);
+  h.t = slab.at<double>(dbase, b_t);
+  h.mut_off = slab.at<int32_t>(dbase, b_moff); h.mut_site = slab.at<int32_t>(dbase, b_msite);
+  h.mut_ft = slab.at<uint8_t>(dbase, b_mft); h.mut_t = slab.at<double>(dbase, b_mt);
+  h.miss_off = slab.at<int32_t>(dbase, b_ioff); h.miss_start = slab.at<int32_t>(dbase, b_is); h.miss_end = slab.at<int32_t>(dbase, b_ie);
+  h.fs_off = slab.at<int32_t>(dbase, b_foff); h.fs_site = slab.at<int32_t>(dbase, b_fsite); h.fs_from = slab.at<uint8_t>(dbase, b_ffrom);
+  fo->d_lambda = slab.at<double>(dbase, b_lambda); fo->d_nsmn = slab.at<int32_t>(dbase, b_nsmn);
+  fo->d_tree_out = slab.at<double>(dbase, b_tout); fo->d_tree_iout = slab.at<int32_t>(dbase, b_tiout);
+  fo->d_tile_agg = slab.at<double>(dbase, b_tagg); fo->d_tile_iagg = slab.at<int32_t>(dbase, b_tiagg);
+  fo->d_tile_part = slab.at<double>(dbase, b_tpart); fo->d_tile_ipart = slab.at<int32_t>(dbase, b_tipart);
+  fo->d_tile_flag = slab.at<uint32_t>(dbase, b_tflag); fo->d_tree_done = slab.at<uint32_t>(dbase, b_tdone);
+  fo->d_ticket = slab.at<uint32_t>(dbase, b_ticket);
+  // the pinned staging buffer is reused by later calls: wait for the copy
+  st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "forest upload");
+  if (st != DPHY_OK) { cudaFree(dbase); delete fo; return st; }
+  *out = fo;
+  return DPHY_OK;
+}
+
+void dphy_forest_destroy(dphy_ctx* ctx, dphy_forest* fo) {
+  if (!fo) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  for (void* p : fo->allocs) cudaFree(p);
+  delete fo;
+}
+
+int64_t dphy_forest_num_nodes(const dphy_forest* fo) { return fo ? fo->h.num_nodes : 0; }
+int64_t dphy_forest_device_bytes(const dphy_forest* fo) { return fo ? (int64_t)fo->bytes : 0; }
+
+int64_t dphy_forest_log_G_algorithmic_bytes(const dphy_forest* fo) {
+  if (!fo) return 0;
+  // N*(4 parent + 8 t + 4+4+4 CSR offsets) + M*(4 site + 1 from|to + 8 t) + M*8 (nu_l gather)
+  //                         + I*(4+4) + I*16 (two cum_Q gathers) + F*(4+1) + F*8 + N*8 (lambda_i written once) + 8/tree
+  const int64_t N = fo->h.num_nodes, M = fo->total_muts, I = fo->total_ivls, F = fo->total_fs;
+  return N * 24 + M * 13 + M * 8 + I * 8 + I * 16 + F * 5 + F * 8 + N * 8 + 8 * (int64_t)fo->h.num_trees;
+}
+
+int dphy_forest_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t count, const int32_t* nodes, const double* t) {
+  if (!ctx || !fo || tree < 0 || tree >= fo->h.num_trees || count < 0 || (count > 0 && (!nodes || !t))) return DPHY_ERR_INVALID_ARGUMENT;
+  const TreeDev& T = fo->trees[tree];
+  std::vector<int32_t> pos(T.num_nodes);
+  DPHY_CUDA(ctx, cudaMemcpyAsync(pos.data(), fo->h.pos_of_node + T.node_base, sizeof(int32_t) * T.num_nodes, cudaMemcpyDeviceToHost, ctx->stream));
+  DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < count; ++i) {
+    if (nodes[i] < 0 || nodes[i] >= T.num_nodes) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "node out of range");
+    DPHY_CUDA(ctx, cudaMemcpyAsync(fo->h.t + T.node_base + pos[nodes[i]], &t[i], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  fo->evaluated = false;
+  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "set_node_times");
+}
+
+// ---- log G ----------------------------------------------------------------------------------------------------------
+int dphy_forest_eval_log_G(dphy_ctx* ctx, dphy_forest* fo) {
+  if (!ctx || !fo) return DPHY_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  int st = launch_log_G(ctx, fo);
+  if (st == DPHY_OK) fo->evaluated = true;
+  return st;
+}
+
+static int fetch_tree_outputs(dphy_ctx* ctx, dphy_forest* fo, std::vector<double>& dout, std::vector<int32_t>* iout) {
+  if (!fo->evaluated) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
+  const int T = fo->h.num_trees;
+  dout.resize((size_t)T * 4);
+  DPHY_CUDA(ctx, cudaMemcpyAsync(dout.data(), fo->d_tree_out, sizeof(double) * 4 * T, cudaMemcpyDeviceToHost, ctx->stream));
+  if (iout) {
+    iout->resize((size_t)T * 20);
+    DPHY_CUDA(ctx, cudaMemcpyAsync(iout->data(), fo->d_tree_iout, sizeof(int32_t) * 20 * T, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "log G D2H");
+}
+
+int dphy_forest_get_log_G(dphy_ctx* ctx, dphy_forest* fo, double* log_root_prior, double* log_G_below_root, double* log_G) {
+  if (!ctx || !fo) return DPHY_ERR_INVALID_ARGUMENT;
+  std::vector<double> d;
+  int st = fetch_tree_outputs(ctx, fo, d, nullptr);
+  if (st != DPHY_OK) return st;
+  for (int k = 0; k < fo->h.num_trees; ++k) {
+    const double rp = d[k * 4 + 0], br = d[k * 4 + 1];
+    if (log_root_prior) log_root_prior[k] = rp;
+    if (log_G_below_root) log_G_below_root[k] = br;
+    if (log_G) log_G[k] = (fo->trees[k].includes_run_root ? rp : 0.0) + br;   // Subrun::calc_cur_log_G
+  }
+  return DPHY_OK;
+}
+
+int dphy_forest_get_lambda_i(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, double* out) {
+  if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
+  if (!fo->evaluated) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
+  const TreeDev& T = fo->trees[tree];
+  DPHY_CUDA(ctx, cudaMemcpyAsync(out, fo->d_lambda + T.node_base, sizeof(double) * T.num_nodes, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "lambda_i D2H");
+}
+
+int dphy_forest_get_num_sites_missing(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t* out) {
+  if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
+  if (!fo->evaluated) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
+  const TreeDev& T = fo->trees[tree];
+  DPHY_CUDA(ctx, cudaMemcpyAsync(out, fo->d_nsmn + T.node_base, sizeof(int32_t) * T.num_nodes, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "nsmn D2H");
+}
+
+int dphy_forest_calc_tallies(dphy_ctx* ctx, dphy_forest* fo, dphy_tallies* out) {
+  if (!ctx || !fo || !out) return DPHY_ERR_INVALID_ARGUMENT;
+  std::vector<double> d; std::vector<int32_t> iv;
+  int st = fetch_tree_outputs(ctx, fo, d, &iv);
+  if (st != DPHY_OK) return st;
+  for (int k = 0; k < fo->h.num_trees; ++k) {
+    dphy_tallies& o = out[k];
+    o.num_muts = iv[k * 20 + 0]; o.reserved = 0;
+    for (int i = 0; i < 16; ++i) o.num_muts_ab[i] = iv[k * 20 + 2 + i];
+    o.log_root_prior = fo->trees[k].includes_run_root ? d[k * 4 + 0] : 0.0;
+    o.log_G_below_root = d[k * 4 + 1];
+    o.T = d[k * 4 + 2];
+  }
+  return DPHY_OK;
+}
+
+int dphy_log_G_host(dphy_ctx* ctx, const dphy_emat_host* tree, const dphy_sites_host* sites, double* log_root_prior,
+                    double* log_G_below_root, double* lambda_i) {
+  if (!ctx || !tree || !sites) return DPHY_ERR_INVALID_ARGUMENT;
+  dphy_sites* s = nullptr; dphy_forest* fo = nullptr;
+  int st = dphy_sites_upload(ctx, sites, &s);
+  if (st != DPHY_OK) return st;
+  int32_t zero = 0;
+  st = dphy_forest_upload(ctx, 1, tree, &zero, 1, &s, &fo);
+  if (st == DPHY_OK) st = dphy_forest_eval_log_G(ctx, fo);
+  if (st == DPHY_OK) st = dphy_forest_get_log_G(ctx, fo, log_root_prior, log_G_below_root, nullptr);
+  if (st == DPHY_OK && lambda_i) st = dphy_forest_get_lambda_i(ctx, fo, 0, lambda_i);
+  dphy_forest_destroy(ctx, fo);
+  dphy_sites_destroy(ctx, s);
+  return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// dphy_internal.h -- internal structures shared by the host side and the sm_100a kernels.
+#ifndef DPHY_INTERNAL_H_
+#define DPHY_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "delphy_b200.h"
+
+namespace dphy {
+
+constexpr int kMaxPartitions = 4;
+constexpr int kTile = 256;          // nodes per CTA tile in the tree-prefix kernels (1 node / thread)
+
+// ---- device arena: the device analogue of the reference's thread-local bump arena (core/scratch_space.h:49-267).
+// One slab per ctx, bump-allocated, reset when a "scope" closes.  All temporaries of a launch sequence come from
+// here, so the hot path performs no cudaMalloc/cudaFree.
+struct Arena {
+  char* base = nullptr;
+  size_t capacity = 0;
+  size_t offset = 0;
+  size_t high_water = 0;
+  void* alloc(size_t bytes, size_t align = 256) {
+    size_t o = (offset + align - 1) / align * align;
+    if (o + bytes > capacity) return nullptr;
+    offset = o + bytes;
+    if (offset > high_water) high_water = offset;
+    return base + o;
+  }
+  size_t mark() const { return offset; }
+  void release(size_t m) { offset = m; }
+};
+
+// Per-sites-table device view (reference sequence + Global_evo_model + derived tables).
+struct SitesDev {
+  int32_t L;
+  int32_t P;
+  const uint8_t* ref;        // [L]
+  const uint8_t* part;       // [L]
+  const double* nu;          // [L]
+  const double* munu;        // [L]  mu_{beta(l)} * nu_l
+  const double* cumQ;        // [L+1] calc_cum_Q_l_for_sequence
+  const int32_t* ref_freq;   // [P*4] state frequencies of the reference sequence per partition
+  double mu[kMaxPartitions];
+  double pi[kMaxPartitions * 4];
+  double q[kMaxPartitions * 16];     // q_ab
+  double log_pi[kMaxPartitions * 4]; // log(pi) (or 0 where pi == 0; see pi)
+};
+
+// Per-tree record.
+struct TreeDev {
+  int32_t node_base;       // first device position of this tree
+  int32_t num_nodes;
+  int32_t sites_id;
+  int32_t first_tile;      // index of the tree's first tile in the global tile list
+  int32_t num_tiles;
+  int32_t includes_run_root;
+  int32_t root_id;         // host node index of the root
+  int32_t pad;
+};
+
+// Flattened forest, device order = per tree DFS pre-order visiting children[1] before children[0]
+// (the order in which Spr_study_builder emits regions below a start region, core/spr_study.cpp:103-128).
+struct ForestDev {
+  int32_t num_trees;
+  int32_t num_nodes;       // total over trees
+  int32_t num_tiles;
+  int32_t num_sites_tables;
+  const TreeDev* trees;
+  const SitesDev* sites;
+  const int32_t* tile_tree;     // [num_tiles]
+  // per device position
+  const int32_t* node_id;       // host node index (within its tree)
+  const int32_t* parent_pos;    // device position of the parent (-1 for a root)
+  const int32_t* depth;         // depth below the tree's root
+  const int32_t* subtree_size;  // nodes in the subtree rooted here (incl. itself)
+  const int32_t* post_node;     // per tree: post-order list of device positions
+  double* t;                    // node times (mutable: displace moves)
+  const int32_t* mut_off;       // [num_nodes+1] CSR, device order
+  const int32_t* mut_site;
+  const uint8_t* mut_ft;        // from << 2 | to
+  double* mut_t;
+  const int32_t* miss_off;      // [num_nodes+1]
+  const int32_t* miss_start;
+  const int32_t* miss_end;
+  const int32_t* fs_off;        // [num_nodes+1]
+  const int32_t* fs_site;
+  const uint8_t* fs_from;
+  // host-order lookup: device position of (tree, host node id) = pos_of_node[tree.node_base + id]
+  const int32_t* pos_of_node;
+};
+
+}  // namespace dphy
+
+struct dphy_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  dphy::Arena arena;
+  std::string last_error;
+  int64_t launches = 0;
+  int sm_count = 148;
+  void* pinned = nullptr;       // small pinned staging buffer for scalar results
+  size_t pinned_bytes = 0;
+};
+
+struct dphy_sites {
+  dphy::SitesDev h{};           // host mirror of the device view (pointers are device pointers)
+  int32_t L = 0, P = 0;
+  uint8_t* d_ref = nullptr; uint8_t* d_part = nullptr; double* d_nu = nullptr; double* d_munu = nullptr;
+  double* d_cumQ = nullptr; int32_t* d_ref_freq = nullptr;
+  // per-(partition,state) cumulative nu tables for O(1) interval tallies (Ttwiddle): [P*4][L+1]
+  double* d_cum_nu_ba = nullptr;
+  size_t bytes = 0;
+  uint64_t version = 1;         // bumped by set_evo; forests re-sync their SitesDev copies lazily
+};
+
+struct dphy_forest {
+  dphy::ForestDev h{};          // host mirror (device pointers)
+  dphy::ForestDev* d_self = nullptr;
+  std::vector<dphy::TreeDev> trees;
+  std::vector<dphy_sites*> sites;
+  std::vector<void*> allocs;    // every cudaMalloc'ed block, freed on destroy
+  size_t bytes = 0;
+  int64_t total_muts = 0, total_ivls = 0, total_fs = 0, total_nonroot_muts = 0;
+  // outputs of the last eval (device)
+  double* d_lambda = nullptr;   // [num_nodes] host order per tree (tree.node_base + node id)
+  int32_t* d_nsmn = nullptr;    // [num_nodes]
+  double* d_tree_out = nullptr; // [num_trees * 4]: root_prior, below_root, T, unused
+  int32_t* d_tree_iout = nullptr; // [num_trees * 20]: num_muts, pad, num_muts_ab[16], ...
+  // look-back workspace
+  double* d_tile_agg = nullptr;     // [num_tiles]
+  int32_t* d_tile_iagg = nullptr;   // [num_tiles]
+  uint32_t* d_tile_flag = nullptr;  // [num_tiles]
+  double* d_tile_part = nullptr;    // [num_tiles * 2] per-tile partial sums (log G, T)
+  int32_t* d_tile_ipart = nullptr;  // [num_tiles * 17]
+  uint32_t* d_tree_done = nullptr;  // [num_trees] tiles finished (for last-tile reduction)
+  uint32_t* d_ticket = nullptr;     // [1] dynamic tile ticket
+  bool evaluated = false;
+  uint32_t epoch = 0;           // look-back flag value of the current launch (flag == epoch means "published")
+  std::vector<uint64_t> sites_version;
+};
+
+namespace dphy {
+int set_error(dphy_ctx* ctx, int status, const std::string& msg);
+int check_cuda(dphy_ctx* ctx, cudaError_t e, const char* what);
+#define DPHY_CUDA(ctx, expr) do { int st__ = dphy::check_cuda((ctx), (expr), #expr); if (st__ != DPHY_OK) return st__; } while (0)
+
+// kernels_sites.cu
+int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s);
+// kernels_logg.cu
+int launch_log_G(dphy_ctx* ctx, dphy_forest* f);
+int refresh_sites(dphy_ctx* ctx, dphy_forest* f);   // c_abi.cu
+}  // namespace dphy
+
+#endif  // DPHY_INTERNAL_H_

@@ -1,0 +1,327 @@
+// kernels_tally.cu -- per-tree tallies that feed the reference's global (Gibbs) moves (sm_100a).
+//
+//   calc_num_muts_beta_ab   core/phylo_tree_calc.cpp:599-610   (int, bit-exact)
+//   calc_num_muts_l         core/phylo_tree_calc.cpp:612-622   (int, bit-exact)
+//   calc_num_muts_l_ab      core/phylo_tree_calc.cpp:624-634   (int, bit-exact)
+//   calc_Ttwiddle_beta_a    core/phylo_tree_calc.cpp:288-369   (fp64)
+//   calc_Ttwiddle_l         core/phylo_tree_calc.cpp:176-222   (fp64)
+//   calc_T_l_a              core/phylo_tree_calc.cpp:130-174   (fp64)
+//
+// The reference's Ttwiddle_beta_a walks the tree carrying the 4P-vector ntwiddle and loops over EVERY missing site
+// of every missation interval.  Here all three time tallies use the "total branch length below" form the reference
+// itself uses for calc_T_l_a: in DFS pre-order the subtree of p is the contiguous range [p, p+size), so
+// T_below(p) = PL[p+size-1] - PL[p] with PL the inclusive scan of branch lengths -- one plain scan -- and every
+// mutation / interval / from-state override becomes an independent term.  Per-site interval loops are replaced by
+// look-ups in cumulative tables (cum_nu_ba for Ttwiddle_beta_a; a +-T difference array scanned once for the
+// per-site outputs).
+#include "dphy_internal.h"
+#include "device_utils.cuh"
+
+namespace dphy {
+
+// ---- inclusive scan of branch lengths over one tree's device positions --------------------------------------------
+// Same single-pass scheme as the log-G kernel: tile aggregate published with a release flag, predecessors of the
+// same tree summed in a fixed order.
+__global__ void __launch_bounds__(kTile) tally_branch_len_scan_kernel(ForestDev f, int tree, double* __restrict__ PL,
+                                                                      double* tile_agg, uint32_t* tile_flag,
+                                                                      uint32_t* ticket, uint32_t epoch) {
+  __shared__ double s_ws[kTile / 32];
+  __shared__ double s_prefix;
+  __shared__ int s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const TreeDev T = f.trees[tree];
+  const int p = T.node_base + tile * kTile + tid;
+  double len = 0.0;
+  if (p < T.node_base + T.num_nodes) {
+    const int par = f.parent_pos[p];
+    if (par >= 0) len = f.t[p] - f.t[par];
+  }
+  double tot;
+  const double incl = block_scan_incl<double, kTile>(len, s_ws, &tot);
+  if (tid == 0) {
+    tile_agg[tile] = tot;
+    __threadfence();
+    st_release_u32(tile_flag + tile, epoch);
+    if (tile == T.num_tiles - 1) ticket[0] = 0u;   // every ticket has been handed out: re-arm
+  }
+  if (warp == 0) {
+    double acc = 0.0;
+    for (int j0 = 0; j0 < tile; j0 += 32) {
+      const int j = j0 + lane;
+      if (j < tile) {
+        while (ld_acquire_u32(tile_flag + j) != epoch) { __nanosleep(20); }
+        acc += ld_cg_f64(tile_agg + j);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_prefix = acc;
+  }
+  __syncthreads();
+  if (p < T.node_base + T.num_nodes) PL[p - T.node_base] = s_prefix + incl;
+}
+
+struct TallyOut {
+  int32_t* num_muts_beta_ab;  // [P*16] or null
+  int32_t* num_muts_l;        // [L] or null
+  int32_t* num_muts_l_ab;     // [L*16] or null
+  double* beta_a_part;        // [num_tiles * 16] per-tile partials of Ttwiddle_beta_a, or null
+  double* Ttw_l;              // [L] or null (atomic scatter)
+  double* T_l_a;              // [L*4] or null
+  double* miss_diff;          // [L+1] difference array of T_below_miss (needed when Ttw_l or T_l_a)
+};
+
+// One thread per node of the tree.  kTime: evaluate the time tallies (needs PL).
+template <bool kTime>
+__global__ void __launch_bounds__(kTile) tally_events_kernel(ForestDev f, int tree, const double* __restrict__ PL,
+                                                             const double* __restrict__ cum_nu_ba, TallyOut out) {
+  __shared__ int s_bab[kMaxPartitions * 16];
+  __shared__ double s_ws[kTile / 32];
+  const int tid = threadIdx.x;
+  const TreeDev T = f.trees[tree];
+  const SitesDev& S = f.sites[T.sites_id];
+  const int L = S.L, P = S.P;
+  if (tid < kMaxPartitions * 16) s_bab[tid] = 0;
+  __syncthreads();
+  const int q = blockIdx.x * kTile + tid;
+  const int p = T.node_base + q;
+  const bool active = q < T.num_nodes;
+  double acc[kMaxPartitions * 4];
+#pragma unroll
+  for (int k = 0; k < kMaxPartitions * 4; ++k) acc[k] = 0.0;
+
+  if (active) {
+    const int par = f.parent_pos[p];
+    const bool is_root = par < 0;
+    double Tb = 0.0, len = 0.0, tN = 0.0;
+    if (kTime) {
+      const int last = q + f.subtree_size[p] - 1;
+      Tb = PL[last] - PL[q];
+      tN = f.t[p];
+      len = is_root ? 0.0 : tN - f.t[par];
+    }
+    for (int i = f.mut_off[p]; i < f.mut_off[p + 1]; ++i) {
+      const int l = f.mut_site[i], ft = f.mut_ft[i], from = ft >> 2, to = ft & 3;
+      const int pt = S.part[l];
+      if (!is_root) {   // "mutations" above the root are just deltas from the reference sequence
+        if (out.num_muts_beta_ab) atomicAdd(&s_bab[pt * 16 + ft], 1);
+        if (out.num_muts_l) atomicAdd(out.num_muts_l + l, 1);
+        if (out.num_muts_l_ab) atomicAdd(out.num_muts_l_ab + (size_t)l * 16 + ft, 1);
+      }
+      if (kTime) {
+        const double Tbm = Tb + (is_root ? 0.0 : tN - f.mut_t[i]);
+        if (out.beta_a_part) {
+          const double w = S.nu[l] * Tbm;
+#pragma unroll
+          for (int k = 0; k < kMaxPartitions * 4; ++k) {
+            if (k == pt * 4 + from) acc[k] -= w;
+            if (k == pt * 4 + to) acc[k] += w;
+          }
+        }
+        if (out.Ttw_l) atomicAdd(out.Ttw_l + l, ((-S.q[pt * 16 + to * 5]) - (-S.q[pt * 16 + from * 5])) * Tbm);
+        if (out.T_l_a) { atomicAdd(out.T_l_a + (size_t)l * 4 + from, -Tbm); atomicAdd(out.T_l_a + (size_t)l * 4 + to, Tbm); }
+      }
+    }
+    if (kTime) {
+      const double Tbmiss = Tb + len;
+      for (int i = f.miss_off[p]; i < f.miss_off[p + 1]; ++i) {
+        const int s = f.miss_start[i], e = f.miss_end[i];
+        if (out.beta_a_part) {
+#pragma unroll
+          for (int k = 0; k < kMaxPartitions * 4; ++k) {
+            if (k < P * 4) {
+              const double* c = cum_nu_ba + (size_t)k * (L + 1);
+              acc[k] -= (c[e] - c[s]) * Tbmiss;
+            }
+          }
+        }
+        if (out.miss_diff) { atomicAdd(out.miss_diff + s, Tbmiss); atomicAdd(out.miss_diff + e, -Tbmiss); }
+      }
+      for (int i = f.fs_off[p]; i < f.fs_off[p + 1]; ++i) {
+        const int l = f.fs_site[i], from = f.fs_from[i], rf = S.ref[l], pt = S.part[l];
+        if (out.beta_a_part) {
+          const double w = S.nu[l] * Tbmiss;
+#pragma unroll
+          for (int k = 0; k < kMaxPartitions * 4; ++k) {
+            if (k == pt * 4 + rf) acc[k] += w;      // undo the ref-seq assumption
+            if (k == pt * 4 + from) acc[k] -= w;    // apply the correct from-state
+          }
+        }
+        if (out.Ttw_l) atomicAdd(out.Ttw_l + l, ((-S.q[pt * 16 + rf * 5]) - (-S.q[pt * 16 + from * 5])) * Tbmiss);
+        if (out.T_l_a) { atomicAdd(out.T_l_a + (size_t)l * 4 + rf, Tbmiss); atomicAdd(out.T_l_a + (size_t)l * 4 + from, -Tbmiss); }
+      }
+    }
+  }
+  if (kTime && out.beta_a_part) {
+#pragma unroll
+    for (int k = 0; k < kMaxPartitions * 4; ++k) {
+      const double v = block_sum<double, kTile>(acc[k], s_ws);
+      if (tid == 0) out.beta_a_part[(size_t)blockIdx.x * 16 + k] = v;
+    }
+  }
+  __syncthreads();
+  if (out.num_muts_beta_ab && tid < P * 16 && s_bab[tid] != 0) atomicAdd(out.num_muts_beta_ab + tid, s_bab[tid]);
+}
+
+// Ttwiddle_beta_a = ntwiddle_ref * T_total + sum over tiles (fixed order).
+__global__ void tally_beta_a_finalize_kernel(ForestDev f, int tree, const double* __restrict__ PL,
+                                             const double* __restrict__ cum_nu_ba, const double* __restrict__ part,
+                                             int num_tiles, double* __restrict__ out) {
+  const TreeDev T = f.trees[tree];
+  const SitesDev& S = f.sites[T.sites_id];
+  const int k = threadIdx.x;
+  if (k >= S.P * 4) return;
+  const double Ttot = PL[T.num_nodes - 1];
+  double v = cum_nu_ba[(size_t)k * (S.L + 1) + S.L] * Ttot;
+  for (int j = 0; j < num_tiles; ++j) v += part[(size_t)j * 16 + k];
+  out[k] = v;
+}
+
+// Per-site finalize: scan the +-T_below_miss difference array over sites, then add the no-mutation baseline
+// (T_total - missing time) * [state == ref].  One CTA, chunk per thread (L is at most a few 1e5).
+__global__ void __launch_bounds__(1024) tally_sites_finalize_kernel(ForestDev f, int tree, const double* __restrict__ PL,
+                                                                    const double* __restrict__ miss_diff,
+                                                                    double* __restrict__ Ttw_l, double* __restrict__ T_l_a) {
+  __shared__ double s_ws[32];
+  const TreeDev T = f.trees[tree];
+  const SitesDev& S = f.sites[T.sites_id];
+  const int L = S.L, tid = threadIdx.x;
+  const double Ttot = PL[T.num_nodes - 1];
+  const int chunk = (L + 1023) / 1024;
+  const int l0 = min(tid * chunk, L), l1 = min(l0 + chunk, L);
+  double tot = 0.0;
+  for (int l = l0; l < l1; ++l) tot += miss_diff[l];
+  double bt;
+  const double incl = block_scan_incl<double, 1024>(tot, s_ws, &bt);
+  double run = incl - tot;
+  for (int l = l0; l < l1; ++l) {
+    run += miss_diff[l];
+    const double base = Ttot - run;       // time during which site l is present with the reference state (before mutations)
+    const int a = S.ref[l], pt = S.part[l];
+    if (Ttw_l) Ttw_l[l] += (-S.q[pt * 16 + a * 5]) * base;
+    if (T_l_a) T_l_a[(size_t)l * 4 + a] += base;
+  }
+}
+
+// ---- host-side launchers -------------------------------------------------------------------------------------------
+static int scan_branch_lengths(dphy_ctx* ctx, dphy_forest* fo, int tree, double** PL_out) {
+  const TreeDev& T = fo->trees[tree];
+  double* PL = (double*)ctx->arena.alloc(sizeof(double) * T.num_nodes);
+  if (!PL) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (tally PL)");
+  fo->epoch += 1; if (fo->epoch == 0) fo->epoch = 1;
+  tally_branch_len_scan_kernel<<<T.num_tiles, kTile, 0, ctx->stream>>>(fo->h, tree, PL, fo->d_tile_agg + T.first_tile,
+                                                                       fo->d_tile_flag + T.first_tile, fo->d_ticket + 2, fo->epoch);
+  ctx->launches += 1;
+  *PL_out = PL;
+  return check_cuda(ctx, cudaGetLastError(), "tally_branch_len_scan_kernel");
+}
+
+int tally_num_muts(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* out_beta_ab, int32_t* out_l, int32_t* out_l_ab) {
+  const TreeDev& T = fo->trees[tree];
+  const dphy_sites* s = fo->sites[T.sites_id];
+  int st = refresh_sites(ctx, fo);
+  if (st != DPHY_OK) return st;
+  const size_t mark = ctx->arena.mark();
+  const int L = s->L, P = s->P;
+  TallyOut o{};
+  if (out_beta_ab) o.num_muts_beta_ab = (int32_t*)ctx->arena.alloc(sizeof(int32_t) * P * 16);
+  if (out_l) o.num_muts_l = (int32_t*)ctx->arena.alloc(sizeof(int32_t) * L);
+  if (out_l_ab) o.num_muts_l_ab = (int32_t*)ctx->arena.alloc(sizeof(int32_t) * (size_t)L * 16);
+  if ((out_beta_ab && !o.num_muts_beta_ab) || (out_l && !o.num_muts_l) || (out_l_ab && !o.num_muts_l_ab)) {
+    ctx->arena.release(mark);
+    return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (num_muts tallies)");
+  }
+  if (o.num_muts_beta_ab) DPHY_CUDA(ctx, cudaMemsetAsync(o.num_muts_beta_ab, 0, sizeof(int32_t) * P * 16, ctx->stream));
+  if (o.num_muts_l) DPHY_CUDA(ctx, cudaMemsetAsync(o.num_muts_l, 0, sizeof(int32_t) * L, ctx->stream));
+  if (o.num_muts_l_ab) DPHY_CUDA(ctx, cudaMemsetAsync(o.num_muts_l_ab, 0, sizeof(int32_t) * (size_t)L * 16, ctx->stream));
+  tally_events_kernel<false><<<T.num_tiles, kTile, 0, ctx->stream>>>(fo->h, tree, nullptr, nullptr, o);
+  ctx->launches += 1;
+  st = check_cuda(ctx, cudaGetLastError(), "tally_events_kernel<false>");
+  if (st == DPHY_OK && out_beta_ab) st = check_cuda(ctx, cudaMemcpyAsync(out_beta_ab, o.num_muts_beta_ab, sizeof(int32_t) * P * 16, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (st == DPHY_OK && out_l) st = check_cuda(ctx, cudaMemcpyAsync(out_l, o.num_muts_l, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (st == DPHY_OK && out_l_ab) st = check_cuda(ctx, cudaMemcpyAsync(out_l_ab, o.num_muts_l_ab, sizeof(int32_t) * (size_t)L * 16, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "num_muts tallies");
+  ctx->arena.release(mark);
+  return st;
+}
+
+int tally_times(dphy_ctx* ctx, dphy_forest* fo, int tree, double* out_beta_a, double* out_l, double* out_l_a) {
+  const TreeDev& T = fo->trees[tree];
+  const dphy_sites* s = fo->sites[T.sites_id];
+  int st = refresh_sites(ctx, fo);
+  if (st != DPHY_OK) return st;
+  const size_t mark = ctx->arena.mark();
+  const int L = s->L, P = s->P;
+  double* PL = nullptr;
+  st = scan_branch_lengths(ctx, fo, tree, &PL);
+  if (st != DPHY_OK) { ctx->arena.release(mark); return st; }
+  TallyOut o{};
+  double* d_beta_a = nullptr;
+  if (out_beta_a) {
+    o.beta_a_part = (double*)ctx->arena.alloc(sizeof(double) * 16 * T.num_tiles);
+    d_beta_a = (double*)ctx->arena.alloc(sizeof(double) * 16);
+  }
+  if (out_l) o.Ttw_l = (double*)ctx->arena.alloc(sizeof(double) * L);
+  if (out_l_a) o.T_l_a = (double*)ctx->arena.alloc(sizeof(double) * (size_t)L * 4);
+  if (out_l || out_l_a) o.miss_diff = (double*)ctx->arena.alloc(sizeof(double) * (L + 1));
+  if ((out_beta_a && (!o.beta_a_part || !d_beta_a)) || (out_l && !o.Ttw_l) || (out_l_a && !o.T_l_a) || ((out_l || out_l_a) && !o.miss_diff)) {
+    ctx->arena.release(mark);
+    return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (time tallies)");
+  }
+  if (o.Ttw_l) DPHY_CUDA(ctx, cudaMemsetAsync(o.Ttw_l, 0, sizeof(double) * L, ctx->stream));
+  if (o.T_l_a) DPHY_CUDA(ctx, cudaMemsetAsync(o.T_l_a, 0, sizeof(double) * (size_t)L * 4, ctx->stream));
+  if (o.miss_diff) DPHY_CUDA(ctx, cudaMemsetAsync(o.miss_diff, 0, sizeof(double) * (L + 1), ctx->stream));
+  tally_events_kernel<true><<<T.num_tiles, kTile, 0, ctx->stream>>>(fo->h, tree, PL, s->d_cum_nu_ba, o);
+  ctx->launches += 1;
+  st = check_cuda(ctx, cudaGetLastError(), "tally_events_kernel<true>");
+  if (st == DPHY_OK && out_beta_a) {
+    tally_beta_a_finalize_kernel<<<1, 32, 0, ctx->stream>>>(fo->h, tree, PL, s->d_cum_nu_ba, o.beta_a_part, T.num_tiles, d_beta_a);
+    ctx->launches += 1;
+    st = check_cuda(ctx, cudaGetLastError(), "tally_beta_a_finalize_kernel");
+    if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(out_beta_a, d_beta_a, sizeof(double) * P * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  }
+  if (st == DPHY_OK && (out_l || out_l_a)) {
+    tally_sites_finalize_kernel<<<1, 1024, 0, ctx->stream>>>(fo->h, tree, PL, o.miss_diff, o.Ttw_l, o.T_l_a);
+    ctx->launches += 1;
+    st = check_cuda(ctx, cudaGetLastError(), "tally_sites_finalize_kernel");
+    if (st == DPHY_OK && out_l) st = check_cuda(ctx, cudaMemcpyAsync(out_l, o.Ttw_l, sizeof(double) * L, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+    if (st == DPHY_OK && out_l_a) st = check_cuda(ctx, cudaMemcpyAsync(out_l_a, o.T_l_a, sizeof(double) * (size_t)L * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  }
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "time tallies");
+  ctx->arena.release(mark);
+  return st;
+}
+
+}  // namespace dphy
+
+using namespace dphy;
+
+extern "C" {
+
+int dphy_forest_calc_num_muts_beta_ab(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t* out) {
+  if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  return tally_num_muts(ctx, fo, tree, out, nullptr, nullptr);
+}
+
+int dphy_forest_calc_num_muts_l(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t* out_l, int32_t* out_l_ab) {
+  if (!ctx || !fo || (!out_l && !out_l_ab) || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  return tally_num_muts(ctx, fo, tree, nullptr, out_l, out_l_ab);
+}
+
+int dphy_forest_calc_Ttwiddle_beta_a(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, double* out) {
+  if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  return tally_times(ctx, fo, tree, out, nullptr, nullptr);
+}
+
+int dphy_forest_calc_Ttwiddle_l(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, double* out_l, double* out_l_a) {
+  if (!ctx || !fo || (!out_l && !out_l_a) || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  return tally_times(ctx, fo, tree, nullptr, out_l, out_l_a);
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+/* delphy_b200.h -- C ABI of the B200-native EMAT log-G + SPR-regraft engine.
+ *
+ * This is the drop-in boundary for Delphy's data-parallel hot path.  The reference has
+ * no plugin/FFI layer for this path: the boundary is the set of C++ free functions and structs declared in
+ * core/phylo_tree_calc.h, core/spr_study.h and core/spr_move.h (all file:line citations below are relative
+ * to the reference checkout).  A C++ adapter with the reference's exact signatures flattens a
+ * delphy::Phylo_tree / Global_evo_model into the plain arrays below and calls these entry points.
+ *
+ * Conventions (mirroring the reference's only extern "C" surface, tools/delphy_wasm.cpp:56-90):
+ *   - context pointer first, raw pointers + sizes, no C++/torch types;
+ *   - every call returns DPHY_OK (0) or a negative dphy_status; dphy_last_error() gives the message
+ *     (the reference throws std::out_of_range / std::invalid_argument or CHECK-aborts, core/mutations.h:187-191;
+ *      the adapter re-throws from the status);
+ *   - host inputs are borrowed for the duration of the call only; outputs are caller-owned host buffers;
+ *   - one dphy_ctx per host thread / Subrun (core/run.cpp:682-693 runs one Subrun per worker thread);
+ *     a ctx owns one CUDA stream and one device arena (the device analogue of core/scratch_space.h:49-267).
+ *   - there is NO CPU fallback: every compute entry point fails with DPHY_ERR_CUDA if no device is usable.
+ */
+#ifndef DELPHY_B200_H_
+#define DELPHY_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dphy_status {
+  DPHY_OK = 0,
+  DPHY_ERR_INVALID_ARGUMENT = -1,   /* std::invalid_argument in the reference */
+  DPHY_ERR_OUT_OF_RANGE = -2,       /* std::out_of_range in the reference (e.g. core/mutations.h:187-191) */
+  DPHY_ERR_CUDA = -3,               /* no device / launch failure (no CPU fallback exists) */
+  DPHY_ERR_OUT_OF_MEMORY = -4,
+  DPHY_ERR_INTERNAL = -5            /* a CHECK(...) in the reference */
+} dphy_status;
+
+typedef struct dphy_ctx dphy_ctx;         /* device + stream + arena */
+typedef struct dphy_sites dphy_sites;     /* device copy of ref_sequence + Global_evo_model + derived per-site tables */
+typedef struct dphy_forest dphy_forest;   /* device-resident batch of EMATs (partition parts and/or independent chains) */
+typedef struct dphy_spr_batch dphy_spr_batch; /* device-resident results of a batch of SPR studies */
+
+/* One EMAT == one delphy::Phylo_tree (core/phylo_tree.h:14-63, core/tree.h:181-220) flattened to SoA + CSR,
+ * in HOST node order.  Letters are Real_seq_letter codes A=0,C=1,G=2,T=3 (core/sequence.h:155). */
+typedef struct dphy_emat_host {
+  int32_t num_nodes;
+  int32_t root;                /* Tree::root */
+  int32_t includes_run_root;   /* Subrun::includes_run_root_ : add calc_log_root_prior to log G (core/subrun.cpp:58-68) */
+  int32_t reserved;
+  const int32_t* parent;       /* [N] Node::parent, -1 == k_no_node */
+  const int32_t* child0;       /* [N] Binary_node::children[0], -1 for tips */
+  const int32_t* child1;       /* [N] Binary_node::children[1] */
+  const double*  t;            /* [N] Phylo_node::t */
+  const int32_t* mut_off;      /* [N+1] CSR offsets into the mutation arrays (root's list included) */
+  const int32_t* mut_site;     /* Mutation::site (core/mutations.h:21-29); per branch sorted by (t, site) */
+  const uint8_t* mut_from;
+  const uint8_t* mut_to;
+  const double*  mut_t;
+  const int32_t* miss_off;     /* [N+1] CSR offsets into Missation_map::intervals (core/mutations.h:124-137) */
+  const int32_t* miss_start;
+  const int32_t* miss_end;
+  const int32_t* fs_off;       /* [N+1] CSR offsets into Missation_map::from_states */
+  const int32_t* fs_site;
+  const uint8_t* fs_from;
+} dphy_emat_host;
+
+/* Reference sequence + Global_evo_model (core/evo_model.h:12-48). */
+typedef struct dphy_sites_host {
+  int32_t num_sites;
+  int32_t num_partitions;
+  const uint8_t* ref;                  /* [L] Phylo_tree::ref_sequence */
+  const int32_t* partition_for_site;   /* [L] */
+  const double*  nu_l;                 /* [L] */
+  const double*  mu;                   /* [P] Site_evo_model::mu */
+  const double*  pi_a;                 /* [P][4] */
+  const double*  q_ab;                 /* [P][4][4]; q_a(a) == -q_ab[a][a] */
+} dphy_sites_host;
+
+/* Byte-for-byte the layout of delphy::Candidate_region (core/spr_study.h:17-32), 48 bytes. */
+typedef struct dphy_candidate_region {
+  int32_t branch;
+  int32_t mut_idx;
+  double  t_min;
+  double  t_max;
+  int32_t min_muts;
+  int32_t pad_;
+  double  log_W_over_Wmax;
+  double  W_over_Wmax;
+} dphy_candidate_region;
+
+/* Inputs of one SPR study == Spr_study_builder{tree, X, t_X, missing_at_X} + .max_muts_from_start +
+ * .seed_fill_from(branch, mut_idx, deltas, can_change_root) + Spr_study{builder, lambda_X, f, t_X, t_max_tip}
+ * (core/spr_study.h:69-205).  missing_at_X and X's sequence are reconstructed on the device from the EMAT
+ * (reconstruct_missing_sites_at / view_of_sequence_at, core/phylo_tree_calc.cpp:19-56), unless X == -1
+ * (k_no_node, the build_usher_like_tree mode, core/phylo_tree.cpp:918-932), in which case the caller passes
+ * X's sequence as deltas from the reference sequence plus its missing intervals. */
+typedef struct dphy_spr_request {
+  int32_t tree;                 /* index of the EMAT inside the forest */
+  int32_t X;                    /* node being pruned (host node index), or -1 */
+  double  t_X;
+  int32_t start_branch;         /* seed_fill_from(init_branch, init_mut_idx, ...) */
+  int32_t start_mut_idx;
+  int32_t init_min_muts;        /* == ssize(init_to_X_deltas) */
+  int32_t max_muts_from_start;  /* INT32_MAX == unbounded */
+  int32_t can_change_root;
+  int32_t reserved;
+  double  lambda_X;
+  double  annealing_factor;
+  double  t_max_tip;
+  /* only read when X == -1: */
+  int32_t n_x_deltas;  const int32_t* x_delta_site;  const uint8_t* x_delta_to;     /* X's state where != ref */
+  int32_t n_x_missing; const int32_t* x_missing_start; const int32_t* x_missing_end;
+} dphy_spr_request;
+
+/* Outputs of Spr_study::Spr_study (core/spr_study.cpp:226-385). */
+typedef struct dphy_spr_summary {
+  double  mu;                 /* lambda_X / (L - #sites missing at X)  (:239) */
+  double  log_Wmax;
+  double  sum_W_over_Wmax;
+  int32_t num_regions;
+  int32_t num_missing_at_X;
+  int64_t region_offset;      /* first region of this study inside the batch's region array */
+} dphy_spr_summary;
+
+/* Integer and floating tallies of Run::recalc_derived_quantities / global moves (core/run.cpp:437-478). */
+typedef struct dphy_tallies {
+  int32_t num_muts;                 /* calc_num_muts            core/phylo_tree_calc.cpp:577-585 */
+  int32_t reserved;
+  int32_t num_muts_ab[16];          /* calc_num_muts_ab         :587-597 */
+  double  T;                        /* calc_T                   :120-128 */
+  double  log_root_prior;           /* calc_log_root_prior      :467-504 (0 if !includes_run_root) */
+  double  log_G_below_root;         /* calc_log_G_below_root    :515-543 */
+} dphy_tallies;
+
+/* ---- context ----------------------------------------------------------------------------------------- */
+int  dphy_ctx_create(int device, dphy_ctx** out);
+void dphy_ctx_destroy(dphy_ctx* ctx);
+const char* dphy_last_error(const dphy_ctx* ctx);
+int  dphy_ctx_synchronize(dphy_ctx* ctx);
+/* Device arena replacing scratch_space (core/scratch_space.h:49-267): stats + explicit reset (scope close). */
+int  dphy_arena_stats(const dphy_ctx* ctx, size_t* capacity, size_t* high_water);
+/* cudaStream_t of the ctx as a void* (so callers can record CUDA events on the launching stream). */
+void* dphy_ctx_stream(dphy_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+int64_t dphy_ctx_launch_count(const dphy_ctx* ctx);
+
+/* ---- sites / evo model ------------------------------------------------------------------------------- */
+int  dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** out);
+void dphy_sites_destroy(dphy_ctx* ctx, dphy_sites* sites);
+/* Subrun::set_evo (core/subrun.h:29-30): new mu/pi/q/nu_l; recomputes cum_Q_l on the device. */
+int  dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* sites, const double* nu_l, const double* mu,
+                        const double* pi_a, const double* q_ab);
+/* calc_state_frequencies_per_partition_of (core/phylo_tree_calc.cpp:95-106) -> out[P*4] */
+int  dphy_calc_state_frequencies_per_partition(dphy_ctx* ctx, dphy_sites* sites, int32_t* out);
+/* calc_cum_Q_l_for_sequence (core/phylo_tree_calc.cpp:379-388) -> out[L+1] */
+int  dphy_calc_cum_Q_l(dphy_ctx* ctx, dphy_sites* sites, double* out);
+
+/* ---- forest (batch of EMATs) -------------------------------------------------------------------------- */
+/* trees[i] uses sites[sites_index[i]].  All host arrays are copied; nothing is retained. */
+int  dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* trees,
+                        const int32_t* sites_index, int32_t num_sites_tables, dphy_sites* const* sites,
+                        dphy_forest** out);
+void dphy_forest_destroy(dphy_ctx* ctx, dphy_forest* forest);
+int64_t dphy_forest_num_nodes(const dphy_forest* forest);
+int64_t dphy_forest_device_bytes(const dphy_forest* forest);
+/* algorithmic bytes of one log-G evaluation over the whole forest (SURVEY.md section 8d formula) */
+int64_t dphy_forest_log_G_algorithmic_bytes(const dphy_forest* forest);
+/* Update node times in place (accepted inner_node/tip displace moves, core/subrun.cpp:223-231,276-284). */
+int  dphy_forest_set_node_times(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, int32_t count,
+                                const int32_t* nodes, const double* t);
+
+/* ---- log G ------------------------------------------------------------------------------------------- */
+/* One launch evaluates, for EVERY tree of the forest: calc_lambda_i (core/phylo_tree_calc.cpp:420-436),
+ * calc_num_sites_missing_at_every_node (:67-76), calc_log_root_prior (:467-504) and calc_log_G_below_root
+ * (:515-543).  Asynchronous on the ctx stream; results stay on the device until fetched. */
+int  dphy_forest_eval_log_G(dphy_ctx* ctx, dphy_forest* forest);
+/* out arrays are [num_trees]; any may be NULL.  log_G = (includes_run_root ? root_prior : 0) + below_root
+ * (Subrun::calc_cur_log_G, core/subrun.cpp:58-68).  Synchronizes the ctx stream. */
+int  dphy_forest_get_log_G(dphy_ctx* ctx, dphy_forest* forest, double* log_root_prior, double* log_G_below_root,
+                           double* log_G);
+/* calc_lambda_i result of the last eval for one tree, host node order, out[num_nodes]. */
+int  dphy_forest_get_lambda_i(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, double* out);
+/* calc_num_sites_missing_at_every_node of the last eval for one tree, host node order. */
+int  dphy_forest_get_num_sites_missing(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, int32_t* out);
+
+/* One-shot, host-buffers-in / host-scalars-out evaluation of a single EMAT (the call the C++ adapter makes for
+ * Subrun::calc_cur_log_G when nothing is resident): uploads, evaluates, downloads.  lambda_i may be NULL. */
+int  dphy_log_G_host(dphy_ctx* ctx, const dphy_emat_host* tree, const dphy_sites_host* sites,
+                     double* log_root_prior, double* log_G_below_root, double* lambda_i);
+
+/* ---- tallies ------------------------------------------------------------------------------------------ */
+/* calc_num_muts / _ab / calc_T + the log-G pieces for every tree; out[num_trees]. */
+int  dphy_forest_calc_tallies(dphy_ctx* ctx, dphy_forest* forest, dphy_tallies* out);
+/* calc_num_muts_beta_ab (core/phylo_tree_calc.cpp:599-610) -> out[P*16] for one tree */
+int  dphy_forest_calc_num_muts_beta_ab(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, int32_t* out);
+/* calc_num_muts_l (:612-622) -> out[L];  calc_num_muts_l_ab (:624-634) -> out[L*16] (either may be NULL) */
+int  dphy_forest_calc_num_muts_l(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, int32_t* out_l, int32_t* out_l_ab);
+/* calc_Ttwiddle_beta_a (:288-369) -> out[P*4] for one tree */
+int  dphy_forest_calc_Ttwiddle_beta_a(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, double* out);
+/* calc_Ttwiddle_l (:176-222) -> out_l[L];  calc_T_l_a (:130-174) -> out_l_a[L*4] (either may be NULL) */
+int  dphy_forest_calc_Ttwiddle_l(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, double* out_l, double* out_l_a);
+
+/* ---- SPR regraft study -------------------------------------------------------------------------------- */
+/* Runs a batch of SPR studies (Spr_study_builder::seed_fill_from + Spr_study ctor) in one pass over the forest.
+ * Regions of study i are emitted in the reference's DFS order (core/spr_study.cpp:26-128) at
+ * regions[summary[i].region_offset ...].  Asynchronous; results stay on the device. */
+int  dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* forest, int32_t num_requests, const dphy_spr_request* requests,
+                          dphy_spr_batch** out);
+void dphy_spr_batch_destroy(dphy_ctx* ctx, dphy_spr_batch* batch);
+/* summaries[num_requests]; synchronizes. */
+int  dphy_spr_batch_get_summaries(dphy_ctx* ctx, dphy_spr_batch* batch, dphy_spr_summary* summaries);
+/* total regions over the batch (after synchronizing) */
+int64_t dphy_spr_batch_total_regions(dphy_ctx* ctx, dphy_spr_batch* batch);
+/* copies the regions of study `request` (or of all studies if request < 0) to out[cap]; returns count or <0 */
+int64_t dphy_spr_batch_get_regions(dphy_ctx* ctx, dphy_spr_batch* batch, int32_t request,
+                                   dphy_candidate_region* out, int64_t cap);
+/* Spr_study::pick_nexus_region (core/spr_study.cpp:404-422) with the caller's uniform draw r in [0,sum_W): the
+ * device does the CDF search (prefix sums); out_region_idx[i] for every study i given r[i]. */
+int  dphy_spr_batch_pick_nexus_regions(dphy_ctx* ctx, dphy_spr_batch* batch, const double* r, int32_t* out_region_idx);
+/* Spr_study::find_region (core/spr_study.cpp:474-484) for study `request` */
+int  dphy_spr_batch_find_region(dphy_ctx* ctx, dphy_spr_batch* batch, int32_t request, int32_t branch, double t,
+                                int32_t* out_region_idx);
+
+/* ---- synthetic EMATs (bench / tests input generator) -------------------------------- */
+typedef struct dphy_synth_params {
+  int32_t num_tips;
+  int32_t num_sites;
+  uint64_t seed;
+  double  muts_per_tip;          /* target M / n (SURVEY: ~1.5) */
+  double  tip_date_span_years;   /* tips uniform over this span */
+  double  growth_rate;           /* exponential-growth coalescent g (1/yr) */
+  double  n0_years;              /* N(0) in years */
+  double  kappa;                 /* HKY transition/transversion ratio */
+  double  pi[4];                 /* stationary frequencies */
+  int32_t site_rate_heterogeneity; /* 0: nu_l == 1;  1: nu_l ~ Gamma(alpha, alpha) */
+  double  gamma_alpha;
+  int32_t num_partitions;        /* 1, or 2 (mpox-hack-like split, core/run.cpp:359-435) */
+  double  missing_mean_intervals_per_tip;   /* Geometric mean; 0 disables missing data */
+  double  missing_len_min, missing_len_max; /* LogUniform interval length */
+  int32_t end_gaps;              /* add 5'/3' end gaps */
+  int32_t num_root_mutations;    /* root "mutations" at t=-DBL_MAX (as partition parts have, core/run.cpp:148-154) */
+  int32_t caterpillar;           /* 1: ladder topology (the reference's random initial tree, core/phylo_tree.cpp) */
+} dphy_synth_params;
+
+typedef struct dphy_synth_emat {     /* owns its arrays; free with dphy_synth_free */
+  dphy_emat_host emat;
+  dphy_sites_host sites;
+  double mu_used;
+  double t_max_tip;
+  int64_t num_mutations, num_intervals, num_from_states, num_missing_sites;
+  int32_t max_depth;
+  void* owner_;
+} dphy_synth_emat;
+
+void dphy_synth_default_params(dphy_synth_params* p, int32_t config /* 1..5 == BASELINE.json configs[0..4] */);
+int  dphy_synth_generate(const dphy_synth_params* p, dphy_synth_emat** out);
+void dphy_synth_free(dphy_synth_emat* s);
+
+const char* dphy_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DELPHY_B200_H_ */

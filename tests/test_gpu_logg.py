@@ -1,0 +1,164 @@
+"""GPU parity: the CUDA log-G / tallies path (through the C ABI) vs the oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): integers bit-exact; fp64 log-likelihood pieces <= 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+import delphy_b200 as db
+from emat_fixtures import complex_tree
+from helpers import from_oracle, rel_err, synth, to_oracle
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = db.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle("oracle")
+
+
+def _check_tree(ctx, orc, emat, sites, check_lists=True):
+    e, s = to_oracle(emat, sites)
+    ds = db.DeviceSites(ctx, sites)
+    fo = db.Forest(ctx, [emat], [ds])
+    try:
+        np.testing.assert_array_equal(ds.state_frequencies(), orc.state_frequencies(s))
+        cq = orc.cum_Q_l(s)
+        assert rel_err(ds.cum_Q_l()[1:], cq[1:]) <= 1e-12
+        fo.eval_log_G()
+        rp, br, lg = fo.log_G()
+        lam_o = orc.lambda_i(e, s, cq)
+        assert rel_err(fo.lambda_i(0), lam_o) <= RTOL
+        np.testing.assert_array_equal(fo.num_sites_missing(0), orc.nsmn(e, s))
+        want_rp = orc.log_root_prior(e, s)
+        want_br = orc.log_G_below_root(e, s, lam_o)
+        assert rp[0] == pytest.approx(want_rp, rel=RTOL)
+        assert br[0] == pytest.approx(want_br, rel=RTOL)
+        assert lg[0] == pytest.approx(want_rp + want_br, rel=RTOL)
+        tl = fo.tallies()[0]
+        assert tl["num_muts"] == orc.num_muts(e, s)
+        np.testing.assert_array_equal(tl["num_muts_ab"], orc.num_muts_ab(e, s))
+        assert tl["T"] == pytest.approx(orc.T(e, s), rel=RTOL)
+        if check_lists:
+            np.testing.assert_array_equal(fo.num_muts_beta_ab(0), orc.num_muts_beta_ab(e, s))
+            nl, nlab = fo.num_muts_l(0)
+            np.testing.assert_array_equal(nl, orc.num_muts_l(e, s))
+            np.testing.assert_array_equal(nlab, orc.num_muts_l_ab(e, s))
+            want = orc.Ttwiddle_beta_a(e, s)
+            np.testing.assert_allclose(fo.Ttwiddle_beta_a(0), want, rtol=RTOL, atol=1e-9 * np.abs(want).max())
+            tw, tla = fo.Ttwiddle_l(0)
+            want_l, want_la = orc.Ttwiddle_l(e, s), orc.T_l_a(e, s)
+            np.testing.assert_allclose(tw, want_l, rtol=RTOL, atol=1e-9 * np.abs(want_l).max())
+            np.testing.assert_allclose(tla, want_la, rtol=RTOL, atol=1e-9 * np.abs(want_la).max())
+    finally:
+        fo.close(); ds.close()
+
+
+def test_reference_kat_fixture(ctx, orc):
+    """The reference's own 5-node fixture (tests/phylo_tree_calc_tests.cpp:14-116), P=2, non-reversible Q."""
+    e, s, _ = complex_tree()
+    emat, sites = from_oracle(e, s)
+    _check_tree(ctx, orc, emat, sites)
+    # absolute known answers from the reference's tests
+    ds = db.DeviceSites(ctx, sites); fo = db.Forest(ctx, [emat], [ds])
+    tl = fo.tallies()[0]
+    assert tl["num_muts"] == 5                                      # :441
+    np.testing.assert_array_equal(fo.num_sites_missing(0), [1, 2, 2, 2, 2])   # :497
+    np.testing.assert_array_equal(fo.num_muts_l(0)[0], [4, 1, 0, 0])          # :471
+    assert tl["T"] == pytest.approx(8.0, abs=1e-9)                   # :236
+    fo.close(); ds.close()
+
+
+def test_root_prior_zero_pi(ctx, orc):
+    """pi == 0 edge cases (tests/phylo_tree_calc_tests.cpp:355-379)."""
+    e, s, _ = complex_tree()
+    s.pi_a[0] = [0.3, 0.7, 0.0, 0.0]; s.pi_a[1] = [0.3, 0.0, 0.7, 0.0]
+    emat, sites = from_oracle(e, s)
+    rp, _, _ = ctx.log_G_host(emat, sites)
+    assert rp == pytest.approx(orc.log_root_prior(e, s), rel=RTOL)
+    s.pi_a[0] = [0.0, 0.3, 0.7, 0.0]
+    emat, sites = from_oracle(e, s)
+    rp, _, _ = ctx.log_G_host(emat, sites)
+    assert rp == -np.inf
+
+
+@pytest.mark.parametrize("cfg,ov", [
+    (0, {}),
+    (0, dict(num_root_mutations=7, num_partitions=2, site_rate_heterogeneity=1)),
+    (0, dict(caterpillar=1, num_tips=700)),
+    (0, dict(num_tips=2, num_sites=50, missing_len_max=20.0)),
+    (0, dict(num_tips=257, missing_mean_intervals_per_tip=0.0, end_gaps=0)),
+    (1, {}),
+    (2, {}),
+    (3, {}),
+])
+def test_synthetic_parity(ctx, orc, cfg, ov):
+    emat, sites, _ = synth(cfg, **ov)
+    _check_tree(ctx, orc, emat, sites)
+
+
+def test_forest_batch_matches_single(ctx, orc):
+    """Several EMATs (different trees, two site tables) evaluated in one launch == each evaluated alone."""
+    items = [synth(0, seed=11), synth(0, seed=12, num_tips=300), synth(1, seed=13), synth(0, seed=14, num_partitions=2)]
+    tables = [db.DeviceSites(ctx, it[1]) for it in items]
+    fo = db.Forest(ctx, [it[0] for it in items], tables, sites_index=np.arange(len(items)))
+    fo.eval_log_G()
+    rp, br, lg = fo.log_G()
+    for k, (emat, sites, _) in enumerate(items):
+        e, s = to_oracle(emat, sites)
+        lam = orc.lambda_i(e, s)
+        assert rel_err(fo.lambda_i(k), lam) <= RTOL
+        assert br[k] == pytest.approx(orc.log_G_below_root(e, s, lam), rel=RTOL)
+        assert rp[k] == pytest.approx(orc.log_root_prior(e, s), rel=RTOL)
+        np.testing.assert_array_equal(fo.num_sites_missing(k), orc.nsmn(e, s))
+    # bit-reproducible run to run
+    fo.eval_log_G()
+    rp2, br2, _ = fo.log_G()
+    assert np.array_equal(br, br2) and np.array_equal(rp, rp2)
+    fo.close()
+    for t in tables:
+        t.close()
+
+
+def test_set_evo_and_node_times(ctx, orc):
+    emat, sites, _ = synth(1)
+    ds = db.DeviceSites(ctx, sites); fo = db.Forest(ctx, [emat], [ds])
+    # Subrun::set_evo: new mu / nu
+    rng = np.random.default_rng(5)
+    sites.mu = sites.mu * 1.7
+    sites.nu_l = rng.gamma(2.0, 0.5, size=sites.num_sites)
+    ds.set_evo(nu_l=sites.nu_l, mu=sites.mu)
+    e, s = to_oracle(emat, sites)
+    fo.eval_log_G()
+    _, br, _ = fo.log_G()
+    assert br[0] == pytest.approx(orc.log_G_below_root(e, s), rel=RTOL)
+    # a displaced inner node (core/subrun.cpp:223-231): move the root a little earlier
+    emat.t[emat.root] -= 0.01
+    fo.set_node_times(0, [emat.root], [emat.t[emat.root]])
+    e, s = to_oracle(emat, sites)
+    fo.eval_log_G()
+    _, br, _ = fo.log_G()
+    assert br[0] == pytest.approx(orc.log_G_below_root(e, s), rel=RTOL)
+    fo.close(); ds.close()
+
+
+def test_error_behaviour(ctx):
+    """Out-of-range sites are rejected like the reference's std::out_of_range (core/mutations.h:187-191)."""
+    emat, sites, _ = synth(0)
+    bad = db.HostEmat(emat.root, 1, **{k: getattr(emat, k).copy() for k in db.HostEmat.FIELDS_I32 + db.HostEmat.FIELDS_U8 + db.HostEmat.FIELDS_F64})
+    bad.miss_end[0] = sites.num_sites + 5
+    ds = db.DeviceSites(ctx, sites)
+    with pytest.raises(db.DphyError) as ei:
+        db.Forest(ctx, [bad], [ds])
+    assert ei.value.status == db.ERR_OUT_OF_RANGE
+    ds.close()
