@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- EMAT log-lik evals/s + SPR candidates scored/s on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch: a full log-G evaluation (calc_lambda_i + calc_log_root_prior
++ calc_log_G_below_root) of every EMAT of a forest of `--chains` independent synthetic
+100k-tip x 29,903-site EMATs (BASELINE.json configs[3] shape; the forest is larger than the 126 MB L2 so the
+timed kernels stream from HBM), followed by a batch of full (unbounded) SPR regraft studies on one of them.
+
+  value         = log-lik evals/s, inputs resident in HBM (whole job, all ranks)
+  spr_*         = SPR candidate regions scored/s, same step
+  e2e           = the same log-lik metric through the C ABI with HOST buffers (upload + eval + download per step)
+  roofline      = algorithmic bytes of the log-G kernel / its CUDA-event duration vs the measured HBM peak
+  cpu_baseline  = the reference's own CPU code (oracle/_ref, compiled from /root/reference) on the box's host cores
+
+Multi-GPU (torchrun): each rank owns its own forest of chains (weak scaling; the path shards over independent
+EMATs with no data-path collective -- SURVEY.md section 8e); NCCL is used for the barrier and the max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "EMAT log-lik evals/s (+ spr_candidates_per_s)"
+UNIT = "evals/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=4, help="synthetic shape: 1..5 == BASELINE.json configs[0..4]")
+    ap.add_argument("--chains", type=int, default=16, help="independent EMATs per GPU (forest must exceed L2)")
+    ap.add_argument("--spr-studies", type=int, default=16, help="full SPR studies per step (0 disables)")
+    ap.add_argument("--e2e-chains", type=int, default=4)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(cfg, chains):
+    shapes = {1: "200-tip x 29,903-site", 2: "1,600-tip x 18,959-site (nu_l on)", 3: "10k-tip x 29,903-site",
+              4: "100k-tip x 29,903-site", 5: "50k-tip x 197,000-site (heavy missing)"}
+    return f"synthetic {shapes.get(cfg, 'small')} EMAT x {chains} independent chains per GPU"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline_run(emat, sites, budget_s, threads, t_max_tip, spr_xs=None):
+    """Times the reference's own CPU functions (oracle/_ref) -- or the oracle port if _ref is absent -- on a bounded
+    sample of the same workload.  bench.py is one of the three places allowed to execute oracle/."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
+    import oracle_lib as ol
+    from helpers import to_oracle
+    e, s = to_oracle(emat, sites)
+    es, ss = e.as_struct(), s.as_struct()
+    out = {}
+    if ol.ref_available():
+        lib = ol.ref()
+        kind = "reference"
+        lg = C.c_double()
+        t1 = lib.ref_bench_log_G(C.byref(es), C.byref(ss), 2, threads, C.byref(lg))      # calibration
+        per = max(t1 / 2, 1e-6)
+        reps = max(2, int(budget_s / per))
+        t = lib.ref_bench_log_G(C.byref(es), C.byref(ss), reps, threads, C.byref(lg))
+        out.update(value=threads * reps / t, unit=UNIT, cores=threads, kind=kind, log_G=lg.value,
+                   sample=f"{reps} evals/thread x {threads} threads of one {emat.num_nodes}-node EMAT "
+                          f"(calc_lambda_i + calc_log_root_prior + calc_log_G_below_root), {t:.1f} s")
+        if spr_xs is not None and len(spr_xs):
+            xs = np.ascontiguousarray(spr_xs, np.int32)
+            nreg = C.c_int64()
+            t0 = lib.ref_bench_spr(C.byref(es), C.byref(ss), xs.ctypes.data_as(ol.i32p), min(len(xs), threads), threads, 0.8,
+                                   t_max_tip, C.byref(nreg))
+            per_x = max(t0 / max(1, min(len(xs), threads)) * threads, 1e-6) / threads
+            n_x = int(max(threads, min(len(xs), budget_s / max(per_x, 1e-9) * 1.0)))
+            n_x = min(n_x, len(xs))
+            t = lib.ref_bench_spr(C.byref(es), C.byref(ss), xs.ctypes.data_as(ol.i32p), n_x, threads, 0.8, t_max_tip, C.byref(nreg))
+            out["spr"] = dict(value=nreg.value / t, unit="candidates/s", cores=threads, kind=kind,
+                              sample=f"{n_x} full SPR studies (reconstruct_missing_sites_at + seed_fill_from + Spr_study), "
+                                     f"{nreg.value} regions, {t:.1f} s")
+    else:
+        o = ol.Oracle("oracle")
+        kind = "port"
+        cq = o.cum_Q_l(s)
+        t0 = time.perf_counter(); n = 0
+        while time.perf_counter() - t0 < budget_s or n < 2:
+            lam = o.lambda_i(e, s, cq); o.log_root_prior(e, s); o.log_G_below_root(e, s, lam); n += 1
+        t = time.perf_counter() - t0
+        out.update(value=n / t, unit=UNIT, cores=1, kind=kind, sample=f"{n} evals of one {emat.num_nodes}-node EMAT, 1 thread, {t:.1f} s")
+    return out
+
+
+def pick_spr_nodes(emat, n, seed=1234):
+    rng = np.random.default_rng(seed)
+    cand = np.array([v for v in rng.permutation(emat.num_nodes)[: 8 * n + 8] if v != emat.root and emat.parent[v] != emat.root], np.int32)
+    return cand[:n]
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import delphy_b200 as db
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path, all host threads, rank 0 only
+        if rank != 0:
+            return 0
+        threads = host_cores()
+        emat, sites, info = db.synth_generate(db.synth_params(args.config))
+        spr_xs = pick_spr_nodes(emat, max(args.spr_studies, threads)) if args.spr_studies > 0 else None
+        per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+        vals, sprs = [], []
+        last = None
+        for i in range(args.warmup + args.steps):
+            r = cpu_baseline_run(emat, sites, per_step, threads, info["t_max_tip"], spr_xs)
+            if i >= args.warmup:
+                vals.append(r["value"]); sprs.append(r.get("spr", {}).get("value", 0.0))
+            last = r
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args.config, args.chains), "host_threads": threads},
+                "spr_candidates_per_s": float(np.mean(sprs)) if sprs else None,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": last["kind"], "sample": last["sample"],
+                                 "spr": last.get("spr")},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = db.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    # ---- synthetic inputs: `chains` distinct EMATs per rank (different seeds) --------------------------------------
+    emats, tables, infos = [], [], []
+    base_seed = 20251017 + 1000 * rank
+    for c in range(args.chains):
+        e, s, info = db.synth_generate(db.synth_params(args.config, seed=base_seed + c))
+        emats.append(e); infos.append(info)
+        tables.append(db.DeviceSites(ctx, s))
+    host_sites = [t.host for t in tables]
+    forest = db.Forest(ctx, emats, tables, sites_index=np.arange(args.chains))
+    alg_bytes = forest.log_G_algorithmic_bytes
+
+    # SPR requests: full studies of random attached nodes of chain 0 (seeded as Subrun::spr1_move does)
+    spr_reqs = None
+    spr_xs = pick_spr_nodes(emats[0], args.spr_studies) if args.spr_studies > 0 else np.zeros(0, np.int32)
+    if args.spr_studies > 0 and hasattr(db, "spr_requests_for_attached"):
+        forest.eval_log_G()
+        lam0 = forest.lambda_i(0)
+        spr_reqs = db.spr_requests_for_attached(emats[0], 0, spr_xs, lam0, infos[0]["t_max_tip"])
+
+    def step():
+        forest.eval_log_G()
+        if spr_reqs is not None:
+            b = forest.spr_study_batch(spr_reqs)
+            return b
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        b = step()
+        if b is not None:
+            ctx.synchronize(); b.close()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    s_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    batches = []
+    spr_regions = 0
+    barrier()
+    ev0.record(stream)
+    for i in range(args.steps):
+        k_ev[i][0].record(stream)
+        forest.eval_log_G()
+        k_ev[i][1].record(stream)
+        if spr_reqs is not None:
+            s_ev[i][0].record(stream)
+            batches.append(forest.spr_study_batch(spr_reqs))
+            s_ev[i][1].record(stream)
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    logg_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    spr_ms = float(np.mean([a.elapsed_time(b) for a, b in s_ev])) if spr_reqs is not None else None
+    if batches:
+        spr_regions = batches[-1].total_regions()
+        for b in batches:
+            b.close()
+    # checksum of the timed work (proves the evaluation happened): log G of every chain
+    _, _, lg = forest.log_G()
+
+    t = torch.tensor([elapsed_ms, logg_ms, spr_ms or 0.0], device=f"cuda:{local_rank}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, logg_ms_max, spr_ms_max = [float(x) for x in t.tolist()]
+
+    # ---- e2e: host buffers -> C ABI -> host scalars, copies inside the timed region ------------------------------
+    n_e2e = min(args.e2e_chains, args.chains)
+    e2e_emats = emats[:n_e2e]
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = 0
+    for e in e2e_emats:
+        for k in db.HostEmat.FIELDS_I32 + db.HostEmat.FIELDS_U8 + db.HostEmat.FIELDS_F64:
+            h2d += getattr(e, k).nbytes
+    d2h = n_e2e * 3 * 8
+
+    def e2e_step():
+        fo = db.Forest(ctx, e2e_emats, tables[:n_e2e], sites_index=np.arange(n_e2e))
+        fo.eval_log_G()
+        out = fo.log_G()
+        fo.close()
+        return out
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_out = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    assert np.allclose(e2e_out[2], lg[:n_e2e], rtol=1e-12)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        total_evals = args.chains * args.steps * world
+        value = total_evals / (elapsed_ms * 1e-3)
+        achieved = alg_bytes / (logg_ms_max * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, args.chains), "chains_per_gpu": args.chains,
+                       "nodes_per_chain": emats[0].num_nodes, "mutations_per_chain": infos[0]["num_mutations"],
+                       "missation_intervals_per_chain": infos[0]["num_intervals"], "max_depth": infos[0]["max_depth"],
+                       "forest_device_bytes": forest.device_bytes, "l2": "inputs larger than L2 (forest > 126 MB)" if forest.device_bytes > 130e6 else "forest fits in L2",
+                       "spr_studies_per_step": int(args.spr_studies if spr_reqs is not None else 0), "parallelism": f"chains x{world}"},
+            "loglik_evals_per_s_kernel_only": args.chains * world / (logg_ms_max * 1e-3),
+            "spr_candidates_per_s": (spr_regions * world / (spr_ms_max * 1e-3)) if spr_ms else None,
+            "spr_regions_per_step": spr_regions,
+            "roofline": {"kernel": "emat_log_G_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": logg_ms_max},
+            "e2e": {"value": n_e2e * e2e_steps * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "chains_per_step": n_e2e, "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "log_G_checksum": float(np.sum(lg)),
+        }
+        if spr_ms:
+            spr_alg = spr_regions * 60
+            line["roofline_spr"] = {"bound": "hbm", "achieved": spr_alg / (spr_ms_max * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": spr_alg / (spr_ms_max * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_candidate": 60,
+                                    "launch_ms": spr_ms_max}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_run(emats[0], host_sites[0], args.cpu_seconds, host_cores(), infos[0]["t_max_tip"],
+                                                    spr_xs if spr_reqs is not None else None)
+        print(json.dumps(line))
+    forest.close()
+    for tb in tables:
+        tb.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

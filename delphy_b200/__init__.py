@@ -523,3 +523,34 @@ class SprBatch:
         if self._h:
             lib().dphy_spr_batch_destroy(self.ctx._h, self._h)
             self._h = C.c_void_p()
+
+
+def net_branch_deltas(emat: HostEmat, X: int):
+    """Net (site -> (from, to)) deltas of the mutations on branch X, reversals cancelled
+    (== calc_site_deltas_between(tree, parent(X), X), core/site_deltas.cpp:83-101)."""
+    d = {}
+    for i in range(int(emat.mut_off[X]), int(emat.mut_off[X + 1])):
+        l, fr, to = int(emat.mut_site[i]), int(emat.mut_from[i]), int(emat.mut_to[i])
+        if l in d:
+            f0, _ = d[l]
+            if f0 == to:
+                del d[l]
+            else:
+                d[l] = (f0, to)
+        else:
+            d[l] = (fr, to)
+    return d
+
+
+def spr_requests_for_attached(emat: HostEmat, tree: int, xs, lambda_i, t_max_tip, max_muts_from_start=INT32_MAX,
+                              can_change_root=True, annealing_factor=0.8):
+    """Requests seeded exactly as Subrun::spr1_move seeds its study (core/subrun.cpp:540-553): start region = (sibling
+    of X, 0), initial deltas = the net mutations on branch parent(X)->X."""
+    reqs = []
+    for X in xs:
+        X = int(X)
+        P = int(emat.parent[X])
+        S = int(emat.child1[P]) if int(emat.child0[P]) == X else int(emat.child0[P])
+        reqs.append(spr_request(tree, X, float(emat.t[X]), S, 0, len(net_branch_deltas(emat, X)), float(lambda_i[X]),
+                                float(t_max_tip), max_muts_from_start, can_change_root, annealing_factor))
+    return reqs

@@ -26,17 +26,6 @@ namespace {
 constexpr size_t kAlign = 256;
 size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
-// Pinned staging buffer owned by the ctx, grown geometrically.
-int ensure_pinned(dphy_ctx* ctx, size_t bytes) {
-  if (ctx->pinned_bytes >= bytes) return DPHY_OK;
-  if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
-  size_t want = std::max(bytes, (size_t)1 << 20);
-  want = std::max(want, ctx->pinned_bytes * 2);
-  DPHY_CUDA(ctx, cudaMallocHost(&ctx->pinned, want));
-  ctx->pinned_bytes = want;
-  return DPHY_OK;
-}
-
 // A layout planner: reserve() all blocks, then carve them out of one host staging slab and one device slab.
 struct Slab {
   struct Block { size_t off, bytes; };
@@ -51,6 +40,24 @@ struct Slab {
 };
 
 }  // namespace
+
+// Pinned staging buffer owned by the ctx, grown geometrically.  Copies out of it are asynchronous: the next user waits
+// on the event recorded by release_pinned_async() instead of synchronizing the whole stream.
+int acquire_pinned(dphy_ctx* ctx, size_t bytes, void** out) {
+  if (ctx->pinned_in_flight) { cudaEventSynchronize(ctx->pinned_ev); ctx->pinned_in_flight = false; }
+  if (ctx->pinned_bytes < bytes) {
+    if (ctx->pinned) { cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    DPHY_CUDA(ctx, cudaMallocHost(&ctx->pinned, want));
+    ctx->pinned_bytes = want;
+  }
+  *out = ctx->pinned;
+  return DPHY_OK;
+}
+void release_pinned_async(dphy_ctx* ctx) {
+  if (cudaEventRecord(ctx->pinned_ev, ctx->stream) == cudaSuccess) ctx->pinned_in_flight = true;
+  else cudaStreamSynchronize(ctx->stream);
+}
 
 // Forests hold a device copy of each SitesDev record; re-sync it after dphy_sites_set_evo changed mu/pi/q.
 int refresh_sites(dphy_ctx* ctx, dphy_forest* fo) {
@@ -84,6 +91,7 @@ int dphy_ctx_create(int device, dphy_ctx** out) {
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DPHY_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DPHY_ERR_CUDA; }
+  if (cudaEventCreateWithFlags(&ctx->pinned_ev, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return DPHY_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   // keep freed stream-ordered allocations cached in the pool (no cudaMalloc on the hot path after warm-up)
@@ -106,6 +114,7 @@ void dphy_ctx_destroy(dphy_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->pinned_ev) cudaEventDestroy(ctx->pinned_ev);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -168,9 +177,10 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
   char* dbase = nullptr;
   if (cudaMalloc((void**)&dbase, slab.total) != cudaSuccess) { delete s; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMalloc(sites)"); }
   s->bytes = slab.total;
-  st = ensure_pinned(ctx, upload_bytes);
+  void* hbv = nullptr;
+  st = acquire_pinned(ctx, upload_bytes, &hbv);
   if (st != DPHY_OK) { cudaFree(dbase); delete s; return st; }
-  char* hb = static_cast<char*>(ctx->pinned);
+  char* hb = static_cast<char*>(hbv);
   std::memcpy(slab.at<uint8_t>(hb, b_ref), host->ref, L);
   uint8_t* hp = slab.at<uint8_t>(hb, b_part);
   for (int l = 0; l < L; ++l) hp[l] = (uint8_t)host->partition_for_site[l];
@@ -182,9 +192,9 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
   s->h.cumQ = s->d_cumQ; s->h.ref_freq = s->d_ref_freq;
   cudaError_t e = cudaMemcpyAsync(dbase, hb, upload_bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) { cudaFree(dbase); delete s; return check_cuda(ctx, e, "H2D sites"); }
+  release_pinned_async(ctx);
   st = launch_sites_derive(ctx, s);
-  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sites derive");   // pinned buffer reusable
-  if (st != DPHY_OK) { cudaFree(dbase); delete s; return st; }
+  if (st != DPHY_OK) { cudaStreamSynchronize(ctx->stream); cudaFree(dbase); delete s; return st; }
   *out = s;
   return DPHY_OK;
 }
@@ -201,10 +211,12 @@ int dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* s, const double* nu_l, const d
   int st = fill_evo(ctx, s, mu, pi_a, q_ab);
   if (st != DPHY_OK) return st;
   if (nu_l) {
-    st = ensure_pinned(ctx, sizeof(double) * s->L);
+    void* hbv = nullptr;
+    st = acquire_pinned(ctx, sizeof(double) * s->L, &hbv);
     if (st != DPHY_OK) return st;
-    std::memcpy(ctx->pinned, nu_l, sizeof(double) * s->L);
-    DPHY_CUDA(ctx, cudaMemcpyAsync(s->d_nu, ctx->pinned, sizeof(double) * s->L, cudaMemcpyHostToDevice, ctx->stream));
+    std::memcpy(hbv, nu_l, sizeof(double) * s->L);
+    DPHY_CUDA(ctx, cudaMemcpyAsync(s->d_nu, hbv, sizeof(double) * s->L, cudaMemcpyHostToDevice, ctx->stream));
+    release_pinned_async(ctx);
   }
   s->version += 1;
   st = launch_sites_derive(ctx, s);
@@ -273,9 +285,11 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   const int b_tdone = slab.reserve(sizeof(uint32_t) * num_trees), b_ticket = slab.reserve(sizeof(uint32_t) * 4);
   const size_t zero_to = slab.total;
 
-  int st = ensure_pinned(ctx, upload_bytes);
+  void* hbv = nullptr;
+  int st = acquire_pinned(ctx, upload_bytes, &hbv);
   if (st != DPHY_OK) { delete fo; return st; }
-  char* hb = static_cast<char*>(ctx->pinned);
+  char* hb = static_cast<char*>(hbv);
+  fo->tree_muts.resize(num_trees); fo->tree_max_depth.resize(num_trees);
   auto* h_trees = slab.at<TreeDev>(hb, b_trees);
   auto* h_sites = slab.at<SitesDev>(hb, b_sites);
   auto* h_tile_tree = slab.at<int32_t>(hb, b_tile_tree);
@@ -355,6 +369,8 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
       }
     }
     if (next != n) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "tree is disconnected"); }
+    fo->tree_muts[k] = e.mut_off[n];
+    { int32_t md = 0; for (int i = 0; i < n; ++i) md = std::max(md, h_depth[base + i]); fo->tree_max_depth[k] = md; }
     TreeDev& T = fo->trees[k];
     T.node_base = base; T.num_nodes = n; T.sites_id = si; T.first_tile = tile_pos;
     T.num_tiles = (n + kTile - 1) / kTile; T.includes_run_root = e.includes_run_root; T.root_id = e.root; T.pad = 0;
@@ -391,9 +407,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   fo->d_tile_part = slab.at<double>(dbase, b_tpart); fo->d_tile_ipart = slab.at<int32_t>(dbase, b_tipart);
   fo->d_tile_flag = slab.at<uint32_t>(dbase, b_tflag); fo->d_tree_done = slab.at<uint32_t>(dbase, b_tdone);
   fo->d_ticket = slab.at<uint32_t>(dbase, b_ticket);
-  // the pinned staging buffer is reused by later calls: wait for the copy
-  st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "forest upload");
-  if (st != DPHY_OK) { cudaFree(dbase); delete fo; return st; }
+  release_pinned_async(ctx);   // the staging buffer is reused by later calls once this copy has drained
   *out = fo;
   return DPHY_OK;
 }

@@ -101,8 +101,10 @@ struct dphy_ctx {
   std::string last_error;
   int64_t launches = 0;
   int sm_count = 148;
-  void* pinned = nullptr;       // small pinned staging buffer for scalar results
+  void* pinned = nullptr;       // pinned staging buffer for host->device uploads
   size_t pinned_bytes = 0;
+  cudaEvent_t pinned_ev = nullptr;   // recorded after the last async copy out of `pinned`
+  bool pinned_in_flight = false;
 };
 
 struct dphy_sites {
@@ -124,6 +126,8 @@ struct dphy_forest {
   std::vector<void*> allocs;    // every cudaMalloc'ed block, freed on destroy
   size_t bytes = 0;
   int64_t total_muts = 0, total_ivls = 0, total_fs = 0, total_nonroot_muts = 0;
+  std::vector<int64_t> tree_muts;     // mutations per tree (incl. the root's list)
+  std::vector<int32_t> tree_max_depth;
   // outputs of the last eval (device)
   double* d_lambda = nullptr;   // [num_nodes] host order per tree (tree.node_base + node id)
   int32_t* d_nsmn = nullptr;    // [num_nodes]
@@ -152,6 +156,9 @@ int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s);
 // kernels_logg.cu
 int launch_log_G(dphy_ctx* ctx, dphy_forest* f);
 int refresh_sites(dphy_ctx* ctx, dphy_forest* f);   // c_abi.cu
+// Pinned staging buffer of the ctx: acquire waits for the previous async copy out of it; release records an event.
+int acquire_pinned(dphy_ctx* ctx, size_t bytes, void** out);
+void release_pinned_async(dphy_ctx* ctx);
 }  // namespace dphy
 
 #endif  // DPHY_INTERNAL_H_

@@ -1,12 +1,888 @@
-// kernels_spr.cu -- SPR regraft study (placeholder while the kernels are being written)
+// kernels_spr.cu -- batched SPR regraft studies on the device (sm_100a).
+//
+// Replaces, for a batch of studies in one pass over the forest:
+//   reconstruct_missing_sites_at / view_of_sequence_at      core/phylo_tree_calc.cpp:19-56   (X's state + missing set)
+//   Spr_study_builder::seed_fill_from (restricted DFS)       core/spr_study.cpp:9-128
+//   Spr_study_builder::account_for_Xs_detachment             core/spr_study.cpp:130-209
+//   Spr_study_builder::remove_regions_in_Xs_future           core/spr_study.cpp:211-224
+//   Spr_study::Spr_study (region weights, max, exp, sum)     core/spr_study.cpp:226-385
+//   Spr_study::pick_nexus_region / find_region               core/spr_study.cpp:404-422, :474-484
+//
+// Data-parallel restatement.  The reference walks the tree keeping a hash map of site
+// deltas to X and reports min_muts = |map| per region.  Equivalently, with x_l = X's state and the per-mutation
+// potential d(m) = [m.to != x_l] - [m.from != x_l] (0 where l is missing at X), min_muts(region) =
+// min_muts(start) + H(region) - H(start) where H is the sum of d over the root->region path: one integer tree
+// prefix sum.  The scope test (max_muts_from_start) is the path length in counted mutations, C(start->region) =
+// C(start) + C(region) - 2 C(junction).  The DFS emission order is the pre-order of the region tree re-rooted at the
+// start region; since nodes are stored in DFS order (children[1] first, exactly the order the builder's LIFO work
+// stack produces), the output is a concatenation of O(depth) device-order segments whose bases come from one
+// prefix sum of per-node kept-region counts, so every region's output index is computed independently.
 #include "dphy_internal.h"
-using namespace dphy;
-extern "C" {
-int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest*, int32_t, const dphy_spr_request*, dphy_spr_batch**) { return set_error(ctx, DPHY_ERR_INTERNAL, "spr: not built yet"); }
-void dphy_spr_batch_destroy(dphy_ctx*, dphy_spr_batch*) {}
-int dphy_spr_batch_get_summaries(dphy_ctx* ctx, dphy_spr_batch*, dphy_spr_summary*) { return set_error(ctx, DPHY_ERR_INTERNAL, "spr: not built yet"); }
-int64_t dphy_spr_batch_total_regions(dphy_ctx*, dphy_spr_batch*) { return -1; }
-int64_t dphy_spr_batch_get_regions(dphy_ctx*, dphy_spr_batch*, int32_t, dphy_candidate_region*, int64_t) { return -1; }
-int dphy_spr_batch_pick_nexus_regions(dphy_ctx* ctx, dphy_spr_batch*, const double*, int32_t*) { return set_error(ctx, DPHY_ERR_INTERNAL, "spr: not built yet"); }
-int dphy_spr_batch_find_region(dphy_ctx* ctx, dphy_spr_batch*, int32_t, int32_t, double, int32_t*) { return set_error(ctx, DPHY_ERR_INTERNAL, "spr: not built yet"); }
+#include "device_utils.cuh"
+
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <math_constants.h>
+#include <new>
+#include <vector>
+
+namespace dphy {
+
+struct SprStudy {
+  // ---- inputs (host) ----
+  int32_t tree, X, start_branch, start_mut_idx, init_min_muts, limit, can_change_root, n_x_deltas, n_x_missing, pad0;
+  double t_X, lambda_X, f, t_max_tip;
+  // slab offsets in bytes
+  int64_t off_xtab, off_path, off_xpath, off_H, off_C, off_KB, off_seg, off_regions, off_xd_site, off_xd_to, off_xm_start,
+      off_xm_end, off_part;
+  int32_t region_cap, path_cap;
+  // ---- derived (spr_setup_kernel) ----
+  int32_t node_base, num_nodes, num_tiles, L;
+  int32_t posX, posP, posS, nP, nS, P_is_root;
+  int32_t pos0, k0, n0, root_pos;
+  int32_t path_len, xpath_len;
+  int32_t num_missing, error;
+  double mu;
+  // ---- outputs ----
+  int32_t total_regions, pad1;
+  unsigned long long max_key;
+  double log_Wmax, sum_W;
+};
+
+constexpr int kSegStride = 6;     // ints per path node: baseA, baseOwnDown, baseSub, baseUp, cntUp, sibpos
+constexpr int kNormBlocks = 64;   // blocks per study in the normalisation pass (fixed => deterministic sum)
+
+struct SprBatchDev {
+  SprStudy* studies;
+  char* slab;
+  int32_t* tile_agg;      // [S][max_tiles][3]
+  uint32_t* tile_flag;    // [S][max_tiles]
+  uint32_t* ticket;       // [S][4]
+  int32_t num_studies, max_tiles;
+  uint32_t epoch;
+};
+
+__device__ __forceinline__ unsigned long long f64_order_key(double d) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
 }
+__device__ __forceinline__ double f64_from_order_key(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// ---- Q(a,x): regularized upper incomplete gamma (series / continued fraction), as in safe_gamma_math.h:46-51 -----------
+__device__ double dev_gamma_q(double a, double x) {
+  if (x <= 0.0) return 1.0;
+  if (isinf(x)) return 0.0;
+  if (x < a + 1.0) {
+    double sum = 1.0, term = 1.0, ap = a;
+    for (int n = 0; n < 100000; ++n) { ap += 1.0; term *= x / ap; sum += term; if (fabs(term) < fabs(sum) * 1e-17) break; }
+    double p = sum * exp(a * log(x) - x - lgamma(a + 1.0));
+    double q = 1.0 - p;
+    return q < 0.0 ? 0.0 : (q > 1.0 ? 1.0 : q);
+  }
+  const double tiny = 1e-300;
+  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+  for (int i = 1; i < 100000; ++i) {
+    const double an = -(double)i * ((double)i - a);
+    b += 2.0;
+    d = an * d + b; if (fabs(d) < tiny) d = tiny;
+    c = b + an / c; if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < 1e-16) break;
+  }
+  double q = exp(a * log(x) - x - lgamma(a)) * h;
+  return q < 0.0 ? 0.0 : (q > 1.0 ? 1.0 : q);
+}
+
+// ---- (1) per-study setup: node positions, root path, X's state table -------------------------------------------------------
+__global__ void __launch_bounds__(256) spr_setup_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ int s_ws[8];
+  SprStudy& S = B.studies[blockIdx.x];
+  const int tid = threadIdx.x;
+  const TreeDev T = f.trees[S.tree];
+  const SitesDev& Si = f.sites[T.sites_id];
+  const int L = Si.L;
+  uint8_t* xtab = (uint8_t*)(B.slab + S.off_xtab);
+  int32_t* path = (int32_t*)(B.slab + S.off_path);
+  int32_t* xpath = (int32_t*)(B.slab + S.off_xpath);
+  for (int l = tid; l < L; l += 256) xtab[l] = Si.ref[l];
+  if (tid == 0) {
+    S.node_base = T.node_base; S.num_nodes = T.num_nodes; S.num_tiles = T.num_tiles; S.L = L;
+    S.root_pos = T.node_base; S.error = 0;
+    S.total_regions = 0; S.max_key = 0ULL; S.log_Wmax = 0.0; S.sum_W = 0.0;
+    int posX = -1, posP = -1, posS = -1, nP = 0, nS = 0, Proot = 0;
+    if (S.X >= 0) {
+      posX = f.pos_of_node[T.node_base + S.X];
+      posP = f.parent_pos[posX];
+      if (posP < 0) { S.error = 1; posP = posX; }
+      const int c1 = posP + 1, c0 = posP + 1 + f.subtree_size[posP + 1];
+      posS = (posX == c1) ? c0 : c1;
+      nP = f.mut_off[posP + 1] - f.mut_off[posP];
+      nS = f.mut_off[posS + 1] - f.mut_off[posS];
+      Proot = f.parent_pos[posP] < 0;
+    }
+    S.posX = posX; S.posP = posP; S.posS = posS; S.nP = nP; S.nS = nS; S.P_is_root = Proot;
+    const int pos0 = f.pos_of_node[T.node_base + S.start_branch];
+    S.pos0 = pos0; S.k0 = S.start_mut_idx; S.n0 = f.mut_off[pos0 + 1] - f.mut_off[pos0];
+    if (S.k0 < 0 || S.k0 > S.n0 || (pos0 == T.node_base && S.k0 != S.n0)) S.error = 2;
+    if (posX >= 0 && pos0 >= posX && pos0 < posX + f.subtree_size[posX]) S.error = 3;   // start inside X's subtree
+    int j = 0;
+    for (int a = pos0; a >= 0 && j < S.path_cap; a = f.parent_pos[a]) path[j++] = a;
+    S.path_len = j;
+    j = 0;
+    for (int a = posX; a >= 0 && j < S.path_cap; a = f.parent_pos[a]) xpath[j++] = a;
+    S.xpath_len = j;
+  }
+  __syncthreads();
+  if (S.X >= 0) {
+    // missing_at_X = union of the missation intervals on the X->root path (disjoint along a path by invariant)
+    for (int jj = 0; jj < S.xpath_len; ++jj) {
+      const int a = xpath[jj];
+      for (int i = f.miss_off[a]; i < f.miss_off[a + 1]; ++i) {
+        const int s = f.miss_start[i], e = f.miss_end[i];
+        for (int l = s + tid; l < e; l += 256) xtab[l] |= 4;
+      }
+    }
+    __syncthreads();
+    // X's sequence: reference overlaid with the mutations on the root->X path, in order
+    if (tid == 0) {
+      for (int jj = S.xpath_len - 1; jj >= 0; --jj) {
+        const int a = xpath[jj];
+        for (int i = f.mut_off[a]; i < f.mut_off[a + 1]; ++i) {
+          const int l = f.mut_site[i];
+          xtab[l] = (uint8_t)((xtab[l] & 4) | (f.mut_ft[i] & 3));
+        }
+      }
+    }
+  } else {
+    const int32_t* ms = (const int32_t*)(B.slab + S.off_xm_start);
+    const int32_t* me = (const int32_t*)(B.slab + S.off_xm_end);
+    for (int i = 0; i < S.n_x_missing; ++i)
+      for (int l = ms[i] + tid; l < me[i]; l += 256) xtab[l] |= 4;
+    __syncthreads();
+    const int32_t* ds = (const int32_t*)(B.slab + S.off_xd_site);
+    const uint8_t* dt = (const uint8_t*)(B.slab + S.off_xd_to);
+    for (int i = tid; i < S.n_x_deltas; i += 256) xtab[ds[i]] = (uint8_t)((xtab[ds[i]] & 4) | (dt[i] & 3));
+  }
+  __syncthreads();
+  int cnt = 0;
+  for (int l = tid; l < L; l += 256) cnt += (xtab[l] >> 2) & 1;
+  cnt = block_sum<int, 256>(cnt, s_ws);
+  if (tid == 0) {
+    S.num_missing = cnt;
+    S.mu = S.lambda_X / (double)(L - cnt);   // Spr_study::mu, core/spr_study.cpp:239
+  }
+}
+
+// ---- shared device helpers ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mut_dc(const uint8_t* __restrict__ xtab, int site, int ft, int& dH, int& c) {
+  const int xt = xtab[site];
+  if (xt & 4) { dH = 0; c = 0; return; }
+  const int x = xt & 3, from = ft >> 2, to = ft & 3;
+  dH = (int)(to != x) - (int)(from != x);
+  c = 1;
+}
+
+__device__ __forceinline__ void node_dc(const ForestDev& f, const uint8_t* __restrict__ xtab, int p, int& dH, int& dC) {
+  dH = 0; dC = 0;
+  for (int i = f.mut_off[p]; i < f.mut_off[p + 1]; ++i) {
+    int h, c;
+    mut_dc(xtab, f.mut_site[i], f.mut_ft[i], h, c);
+    dH += h; dC += c;
+  }
+}
+
+// deepest node of the start->root path that contains p in its subtree
+__device__ __forceinline__ int classify(const ForestDev& f, const int32_t* __restrict__ path, int path_len, int p) {
+  int lo = 0, hi = path_len - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int a = path[mid];
+    if (p >= a && p < a + f.subtree_size[a]) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+struct RegionEval { int branch, mut_idx; double t_min, t_max; bool keep; };
+
+// Region (p,k) as the builder reports it AFTER account_for_Xs_detachment and remove_regions_in_Xs_future.
+__device__ __forceinline__ RegionEval eval_region(const ForestDev& f, const SprStudy& S, int p, int k, int np, int moff,
+                                                  double tPar, double tNode) {
+  RegionEval r;
+  r.branch = f.node_id[p];
+  r.mut_idx = k;
+  const bool is_root = (p == S.root_pos);
+  r.t_min = is_root ? -DBL_MAX : (k == 0 ? tPar : f.mut_t[moff + k - 1]);       // spr_study.h:90-95
+  r.t_max = is_root ? tNode : (k == np ? tNode : f.mut_t[moff + k]);            // spr_study.h:96-101
+  r.keep = true;
+  if (!S.can_change_root && is_root) r.keep = false;
+  else if (S.posX >= 0 && (p == S.posS || p == S.posP)) {
+    if (!S.P_is_root) {
+      if (p == S.posS) {
+        if (k == 0) {   // merged with the last region of P
+          const int pm = f.mut_off[S.posP];
+          r.t_min = S.nP == 0 ? f.t[f.parent_pos[S.posP]] : f.mut_t[pm + S.nP - 1];
+        }
+        r.mut_idx += S.nP;
+      } else {
+        if (k == S.nP) r.keep = false; else r.branch = f.node_id[S.posS];
+      }
+    } else if (S.can_change_root) {
+      if (p == S.posS && k == S.nS) { r.mut_idx += S.nP; r.t_min = -DBL_MAX; }
+      else r.keep = false;
+    }
+  }
+  if (r.keep) {
+    if (r.t_min >= S.t_X) r.keep = false;
+    else if (r.t_max > S.t_X) r.t_max = S.t_X;
+  }
+  return r;
+}
+
+// counted-mutation distance from the start region; j = classify(p), Cd = C_down(p,k)
+__device__ __forceinline__ int scope_dist(const SprStudy& S, const int32_t* __restrict__ Cend, const int32_t* __restrict__ path,
+                                          int j, bool on_path, int Cd, int C0) {
+  if (j == 0) return on_path ? abs(Cd - C0) : Cd - C0;
+  if (on_path) return C0 - Cd;
+  const int cj = Cend[path[j] - S.node_base];
+  return (C0 - cj) + (Cd - cj);
+}
+
+__device__ __forceinline__ int c_down_start(const ForestDev& f, const SprStudy& S, const uint8_t* xtab, const int32_t* Cend, int* H0,
+                                            const int32_t* Hend) {
+  // C_down / H_down at the start region (pos0, k0)
+  const int par = f.parent_pos[S.pos0];
+  int c = (par < 0 || S.pos0 == S.root_pos) ? 0 : Cend[par - S.node_base];
+  int h = (par < 0 || S.pos0 == S.root_pos) ? 0 : Hend[par - S.node_base];
+  if (S.pos0 != S.root_pos) {
+    const int mo = f.mut_off[S.pos0];
+    for (int i = 0; i < S.k0; ++i) { int dh, dc; mut_dc(xtab, f.mut_site[mo + i], f.mut_ft[mo + i], dh, dc); c += dc; h += dh; }
+  }
+  *H0 = h;
+  return c;
+}
+
+// number of kept regions on branch p (all filters).  `limited` => needs the scope test.
+__device__ int node_kept_count(const ForestDev& f, const SprStudy& S, const uint8_t* __restrict__ xtab,
+                               const int32_t* __restrict__ Cend, const int32_t* __restrict__ path, int p, bool limited, int C0) {
+  if (S.posX >= 0 && p >= S.posX && p < S.posX + f.subtree_size[S.posX]) return 0;
+  const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
+  const int par = f.parent_pos[p];
+  const double tNode = f.t[p], tPar = par >= 0 ? f.t[par] : 0.0;
+  const bool is_root = p == S.root_pos;
+  int j = 0; bool on_path = false; int Cd = 0;
+  if (limited) {
+    j = classify(f, path, S.path_len, p);
+    on_path = (path[j] == p);
+    Cd = is_root ? 0 : Cend[par - S.node_base];
+  }
+  int cnt = 0;
+  for (int k = is_root ? np : 0; k <= np; ++k) {
+    bool ok = true;
+    if (limited) {
+      ok = scope_dist(S, Cend, path, j, on_path, Cd, C0) <= S.limit;
+      if (k < np) { int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_ft[moff + k], dh, dc); Cd += dc; }
+    }
+    if (ok && eval_region(f, S, p, k, np, moff, tPar, tNode).keep) ++cnt;
+  }
+  return cnt;
+}
+
+// ---- (2) integer tree prefix sums H_end / C_end (+ kept-count scan when the study is unbounded) ------------------------------------
+// phase 0: H (and C) for every study; unbounded studies also get their kept-count scan KB here.
+// phase 1: kept-count scan for bounded studies (needs C from phase 0).
+template <int kPhase>
+__global__ void __launch_bounds__(kTile) spr_scan_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ int s_h[kTile];
+  __shared__ int s_c[kTile];
+  __shared__ int s_ws[kTile / 32];
+  __shared__ int s_pre[3];
+  __shared__ int s_tile;
+  __shared__ int s_C0;
+  const int study = blockIdx.y;
+  SprStudy& S = B.studies[study];
+  if ((int)blockIdx.x >= S.num_tiles || S.error) return;
+  const bool limited = S.limit != INT_MAX;
+  if (kPhase == 1 && !limited) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* ticket = B.ticket + study * 4 + kPhase;
+  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const uint8_t* xtab = (const uint8_t*)(B.slab + S.off_xtab);
+  int32_t* Hend = (int32_t*)(B.slab + S.off_H);
+  int32_t* Cend = (int32_t*)(B.slab + S.off_C);
+  int32_t* KB = (int32_t*)(B.slab + S.off_KB);
+  const int32_t* path = (const int32_t*)(B.slab + S.off_path);
+  const int tile_start = S.node_base + tile * kTile;
+  const int tile_end = min(tile_start + kTile, S.node_base + S.num_nodes);
+  const int p = tile_start + tid;
+  const bool active = p < tile_end;
+  int32_t* agg = B.tile_agg + ((size_t)study * B.max_tiles + tile) * 3;
+  uint32_t* flags = B.tile_flag + (size_t)study * B.max_tiles;
+  const uint32_t epoch = B.epoch + (uint32_t)kPhase;
+
+  int dh = 0, dc = 0, kc = 0;
+  int ih = 0, ic = 0;
+  if (kPhase == 0) {
+    if (active && p != S.root_pos) node_dc(f, xtab, p, dh, dc);   // the root's own list is never crossed by the walk
+    s_h[tid] = dh; s_c[tid] = dc;
+    __syncthreads();
+    int diffh = dh, diffc = dc;
+    if (active) {
+      const int q = p - S.node_base;
+      if (q > 0) {
+        const int c0 = (q - 1) - f.depth[p - 1], c1 = q - f.depth[p];
+        for (int j = c0; j < c1; ++j) {
+          const int a = f.post_node[S.node_base + j];
+          if (a >= tile_start) { diffh -= s_h[a - tile_start]; diffc -= s_c[a - tile_start]; }
+          else { int ah, ac; node_dc(f, xtab, a, ah, ac); diffh -= ah; diffc -= ac; }
+        }
+      }
+    }
+    int toth, totc;
+    ih = block_scan_incl<int, kTile>(diffh, s_ws, &toth);
+    __syncthreads();
+    ic = block_scan_incl<int, kTile>(diffc, s_ws, &totc);
+    __syncthreads();
+    int ik = 0, totk = 0;
+    if (!limited) {
+      if (active) kc = node_kept_count(f, S, xtab, Cend, path, p, false, 0);
+      ik = block_scan_incl<int, kTile>(kc, s_ws, &totk);
+    }
+    if (tid == 0) {
+      agg[0] = toth; agg[1] = totc; agg[2] = totk;
+      __threadfence();
+      st_release_u32(flags + tile, epoch);
+    }
+    if (warp == 0) {
+      int a0 = 0, a1 = 0, a2 = 0;
+      for (int j0 = 0; j0 < tile; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < tile) {
+          while (ld_acquire_u32(flags + j) != epoch) { __nanosleep(20); }
+          const int32_t* g = B.tile_agg + ((size_t)study * B.max_tiles + j) * 3;
+          a0 += ld_cg_i32(g); a1 += ld_cg_i32(g + 1); a2 += ld_cg_i32(g + 2);
+        }
+      }
+      a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+      if (lane == 0) { s_pre[0] = a0; s_pre[1] = a1; s_pre[2] = a2; }
+    }
+    __syncthreads();
+    if (active) {
+      const int q = p - S.node_base;
+      Hend[q] = s_pre[0] + ih;
+      Cend[q] = s_pre[1] + ic;
+      if (!limited) {
+        KB[q] = s_pre[2] + ik - kc;
+        if (q == S.num_nodes - 1) KB[S.num_nodes] = s_pre[2] + ik;
+      }
+    }
+  } else {
+    if (tid == 0) { int H0; s_C0 = c_down_start(f, S, xtab, Cend, &H0, Hend); }
+    __syncthreads();
+    if (active) kc = node_kept_count(f, S, xtab, Cend, path, p, true, s_C0);
+    int totk;
+    const int ik = block_scan_incl<int, kTile>(kc, s_ws, &totk);
+    if (tid == 0) {
+      agg[2] = totk;
+      __threadfence();
+      st_release_u32(flags + tile, epoch);
+    }
+    if (warp == 0) {
+      int a2 = 0;
+      for (int j0 = 0; j0 < tile; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < tile) {
+          while (ld_acquire_u32(flags + j) != epoch) { __nanosleep(20); }
+          a2 += ld_cg_i32(B.tile_agg + ((size_t)study * B.max_tiles + j) * 3 + 2);
+        }
+      }
+      a2 = warp_sum(a2);
+      if (lane == 0) s_pre[2] = a2;
+    }
+    __syncthreads();
+    if (active) {
+      const int q = p - S.node_base;
+      KB[q] = s_pre[2] + ik - kc;
+      if (q == S.num_nodes - 1) KB[S.num_nodes] = s_pre[2] + ik;
+    }
+  }
+}
+
+// ---- (3) segment bases along the start->root path ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spr_segments_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ int s_ws[8];
+  __shared__ int s_carry;
+  __shared__ int s_C0;
+  SprStudy& S = B.studies[blockIdx.x];
+  if (S.error) return;
+  const int tid = threadIdx.x;
+  const uint8_t* xtab = (const uint8_t*)(B.slab + S.off_xtab);
+  const int32_t* Hend = (const int32_t*)(B.slab + S.off_H);
+  const int32_t* Cend = (const int32_t*)(B.slab + S.off_C);
+  const int32_t* KB = (const int32_t*)(B.slab + S.off_KB);
+  const int32_t* path = (const int32_t*)(B.slab + S.off_path);
+  int32_t* seg = (int32_t*)(B.slab + S.off_seg);
+  const bool limited = S.limit != INT_MAX;
+  if (tid == 0) { int H0; s_C0 = c_down_start(f, S, xtab, Cend, &H0, Hend); s_carry = 0; }
+  __syncthreads();
+  const int C0 = s_C0;
+  for (int j0 = 0; j0 < S.path_len; j0 += 256) {
+    const int j = j0 + tid;
+    int cntA = 0, cntOwn = 0, cntSub = 0, cntUp = 0, sibpos = -1;
+    if (j < S.path_len) {
+      const int a = path[j];
+      const int moff = f.mut_off[a], np = f.mut_off[a + 1] - moff;
+      const int par = f.parent_pos[a];
+      const bool is_root = a == S.root_pos;
+      const double tNode = f.t[a], tPar = par >= 0 ? f.t[par] : 0.0;
+      int Cd = is_root ? 0 : Cend[par - S.node_base];
+      const int kA = (j == 0) ? S.k0 : np;
+      for (int k = is_root ? np : 0; k <= np; ++k) {
+        bool ok = true;
+        if (limited) {
+          ok = scope_dist(S, Cend, path, j, true, Cd, C0) <= S.limit;
+          if (k < np) { int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_ft[moff + k], dh, dc); Cd += dc; }
+        }
+        if (ok && eval_region(f, S, a, k, np, moff, tPar, tNode).keep) {
+          if (k == kA) ++cntA; else if (k < kA) ++cntUp; else ++cntOwn;
+        }
+      }
+      const int qa = a - S.node_base;
+      if (j == 0) {
+        sibpos = a + 1;
+        cntSub = KB[qa + f.subtree_size[a]] - KB[qa + 1];
+      } else {
+        const int c1 = a + 1, c0 = a + 1 + f.subtree_size[a + 1];
+        sibpos = (path[j - 1] == c1) ? c0 : c1;
+        const int qs = sibpos - S.node_base;
+        cntSub = KB[qs + f.subtree_size[sibpos]] - KB[qs];
+      }
+    }
+    const int tot = cntA + cntOwn + cntSub + cntUp;
+    int btot;
+    const int incl = block_scan_incl<int, 256>(tot, s_ws, &btot);
+    const int base = s_carry + incl - tot;
+    if (j < S.path_len) {
+      int32_t* sg = seg + (size_t)j * kSegStride;
+      sg[0] = base; sg[1] = base + cntA; sg[2] = base + cntA + cntOwn; sg[3] = base + cntA + cntOwn + cntSub;
+      sg[4] = cntUp; sg[5] = sibpos;
+    }
+    __syncthreads();
+    if (tid == 0) s_carry += btot;
+    __syncthreads();
+  }
+  if (tid == 0) S.total_regions = s_carry;
+}
+
+// ---- (4) emit regions in the reference's DFS order, with raw log-weights ------------------------------------------------------------------
+__device__ __forceinline__ double region_log_W(const ForestDev& f, const SprStudy& S, double t_min, double t_max, int m, double tS) {
+  const double fa = S.f, lam = S.lambda_X, mu = S.mu;
+  if (t_min != -DBL_MAX) {
+    const double t_prime = 0.5 * (t_min + t_max);
+    return log(fa * lam * (t_max - t_min)) + fa * (-lam * (S.t_X - t_prime) + m * log(mu * (S.t_X - t_prime) / 3));
+  }
+  // above-root region (core/spr_study.cpp:334-369)
+  const double s_min = fabs(S.t_X - tS);
+  const double t_early = fmin(S.t_X, tS);
+  const double s_max = s_min + 20.0 * (S.t_max_tip - t_early);
+  const double x_min = lam * fa * s_min, x_max = lam * fa * s_max;
+  if (x_max < 0.01) {
+    const double alpha = fa * m + 1;
+    return -0.6931471805599453 + log(fa * lam) + fa * m * log(mu / 3) + alpha * log(s_max) + log1p(-pow(s_min / s_max, alpha)) - log(alpha);
+  }
+  const double a = fa * m + 1;
+  return -0.6931471805599453 + fa * m * log(mu / (3 * lam * fa)) + lgamma(a) + log(dev_gamma_q(a, x_min) - dev_gamma_q(a, x_max));
+}
+
+__global__ void __launch_bounds__(kTile) spr_emit_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ int s_C0, s_H0;
+  __shared__ double s_wmax[kTile / 32];
+  const int study = blockIdx.y;
+  SprStudy& S = B.studies[study];
+  if ((int)blockIdx.x >= S.num_tiles || S.error) return;
+  const int tid = threadIdx.x;
+  const uint8_t* xtab = (const uint8_t*)(B.slab + S.off_xtab);
+  const int32_t* Hend = (const int32_t*)(B.slab + S.off_H);
+  const int32_t* Cend = (const int32_t*)(B.slab + S.off_C);
+  const int32_t* KB = (const int32_t*)(B.slab + S.off_KB);
+  const int32_t* path = (const int32_t*)(B.slab + S.off_path);
+  const int32_t* seg = (const int32_t*)(B.slab + S.off_seg);
+  dphy_candidate_region* out = (dphy_candidate_region*)(B.slab + S.off_regions);
+  const bool limited = S.limit != INT_MAX;
+  if (tid == 0) { int H0; s_C0 = c_down_start(f, S, xtab, Cend, &H0, Hend); s_H0 = H0; }
+  __syncthreads();
+  const int C0 = s_C0, H0 = s_H0;
+  const int p = S.node_base + blockIdx.x * kTile + tid;
+  double wmax = -CUDART_INF;
+  bool any = false;
+  if (p < S.node_base + S.num_nodes && !(S.posX >= 0 && p >= S.posX && p < S.posX + f.subtree_size[S.posX])) {
+    const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
+    const int par = f.parent_pos[p];
+    const bool is_root = p == S.root_pos;
+    const double tNode = f.t[p], tPar = par >= 0 ? f.t[par] : 0.0;
+    const int j = classify(f, path, S.path_len, p);
+    const bool on_path = path[j] == p;
+    const int32_t* sg = seg + (size_t)j * kSegStride;
+    const int q = p - S.node_base;
+    int Hd = is_root ? 0 : Hend[par - S.node_base];
+    int Cd = (limited && !is_root) ? Cend[par - S.node_base] : 0;
+    const int kA = (j == 0) ? S.k0 : np;
+    int rank = 0, rank_up = 0, rank_own = 0;
+    const int hang_base = on_path ? 0 : sg[2] + (KB[q] - KB[sg[5] - S.node_base]);
+    for (int k = is_root ? np : 0; k <= np; ++k) {
+      bool ok = true;
+      if (limited) ok = scope_dist(S, Cend, path, j, on_path, Cd, C0) <= S.limit;
+      const int Hk = Hd;
+      if (k < np) {
+        int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_ft[moff + k], dh, dc);
+        Hd += dh; Cd += dc;
+      }
+      if (!ok) continue;
+      const RegionEval r = eval_region(f, S, p, k, np, moff, tPar, tNode);
+      if (!r.keep) continue;
+      int idx;
+      if (!on_path) idx = hang_base + rank++;
+      else if (k == kA) idx = sg[0];
+      else if (k > kA) idx = sg[1] + rank_own++;
+      else idx = sg[3] + (sg[4] - 1 - rank_up++);
+      const int m = S.init_min_muts + (Hk - H0);
+      const double lw = region_log_W(f, S, r.t_min, r.t_max, m, tNode);
+      if (idx >= 0 && idx < S.region_cap) {
+        dphy_candidate_region o;
+        o.branch = r.branch; o.mut_idx = r.mut_idx; o.t_min = r.t_min; o.t_max = r.t_max;
+        o.min_muts = m; o.pad_ = 0; o.log_W_over_Wmax = lw; o.W_over_Wmax = 0.0;
+        out[idx] = o;
+      }
+      wmax = any ? fmax(wmax, lw) : lw;   // std::max semantics of the reference's running maximum
+      any = true;
+    }
+  }
+  // block max -> global max (ordered-integer atomicMax: exact, order independent)
+  const int lane = tid & 31, warp = tid >> 5;
+  double wm = warp_max(wmax);
+  if (lane == 0) s_wmax[warp] = wm;
+  __syncthreads();
+  if (warp == 0) {
+    wm = lane < kTile / 32 ? s_wmax[lane] : -CUDART_INF;
+    wm = warp_max(wm);
+    if (lane == 0 && wm > -CUDART_INF) atomicMax(&S.max_key, f64_order_key(wm));
+  }
+}
+
+// ---- (5) normalise: log_W_over_Wmax -= log_Wmax; W = exp(.); sum in a fixed order ------------------------------------------------------------
+__global__ void __launch_bounds__(256) spr_normalize_kernel(SprBatchDev B) {
+  __shared__ double s_ws[8];
+  __shared__ int s_last;
+  const int study = blockIdx.y;
+  SprStudy& S = B.studies[study];
+  if (S.error) return;
+  const int n = min(S.total_regions, S.region_cap);
+  dphy_candidate_region* out = (dphy_candidate_region*)(B.slab + S.off_regions);
+  double* part = (double*)(B.slab + S.off_part);
+  const double lmax = n > 0 ? f64_from_order_key(S.max_key) : 0.0;
+  const int per = (n + kNormBlocks - 1) / kNormBlocks;
+  const int i0 = min((int)blockIdx.x * per, n), i1 = min(i0 + per, n);
+  double acc = 0.0;
+  for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+    const double lw = out[i].log_W_over_Wmax - lmax;
+    const double w = exp(lw);
+    out[i].log_W_over_Wmax = lw;
+    out[i].W_over_Wmax = w;
+    acc += w;
+  }
+  acc = block_sum<double, 256>(acc, s_ws);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = acc;
+    __threadfence();
+    const uint32_t done = atomicAdd(B.ticket + study * 4 + 2, 1u);
+    s_last = done == kNormBlocks - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (int b = 0; b < kNormBlocks; ++b) s += ld_cg_f64(part + b);
+    S.sum_W = s;
+    S.log_Wmax = lmax;
+    B.ticket[study * 4 + 2] = 0u;
+  }
+}
+
+// ---- pick_nexus_region / find_region ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) spr_pick_kernel(SprBatchDev B, const double* __restrict__ r_in, int32_t* __restrict__ out_idx) {
+  __shared__ double s_ws[32];
+  __shared__ int s_found;
+  __shared__ double s_carry;
+  const SprStudy& S = B.studies[blockIdx.x];
+  const int n = min(S.total_regions, S.region_cap);
+  const dphy_candidate_region* reg = (const dphy_candidate_region*)(B.slab + S.off_regions);
+  const double r = r_in[blockIdx.x];
+  if (threadIdx.x == 0) { s_found = INT_MAX; s_carry = 0.0; }
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const double w = i < n ? reg[i].W_over_Wmax : 0.0;
+    double tot;
+    const double incl = block_scan_incl<double, 1024>(w, s_ws, &tot);
+    // the reference scans "if (W_i >= r) pick i; else r -= W_i"  <=>  first i with r - sum_{j<i} W_j <= W_i
+    if (i < n && w >= r - (s_carry + incl - w)) atomicMin(&s_found, i);
+    __syncthreads();
+    if (s_found != INT_MAX) break;
+    if (threadIdx.x == 0) s_carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out_idx[blockIdx.x] = s_found == INT_MAX ? 0 : s_found;
+}
+
+__global__ void __launch_bounds__(256) spr_find_kernel(SprBatchDev B, int study, int branch, double t, int32_t* out_idx) {
+  const SprStudy& S = B.studies[study];
+  const int n = min(S.total_regions, S.region_cap);
+  const dphy_candidate_region* reg = (const dphy_candidate_region*)(B.slab + S.off_regions);
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+    if (reg[i].branch == branch && reg[i].t_min < t && t <= reg[i].t_max) atomicMin(out_idx, i);
+}
+
+}  // namespace dphy
+
+using namespace dphy;
+
+struct dphy_spr_batch {
+  SprBatchDev dev{};
+  void* d_block = nullptr;        // one stream-ordered allocation: studies + workspaces + slab
+  size_t bytes = 0;
+  int32_t num = 0;
+  std::vector<SprStudy> host;     // filled by get_summaries
+  bool fetched = false;
+  dphy_forest* forest = nullptr;
+};
+
+namespace {
+size_t al(size_t x) { return (x + 255) / 256 * 256; }
+}
+
+extern "C" {
+
+int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_spr_request* reqs, dphy_spr_batch** out) {
+  if (!ctx || !fo || !out || n < 0 || (n > 0 && !reqs)) return DPHY_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  int st = refresh_sites(ctx, fo);
+  if (st != DPHY_OK) return st;
+  auto* b = new (std::nothrow) dphy_spr_batch();
+  if (!b) return DPHY_ERR_OUT_OF_MEMORY;
+  b->num = n; b->forest = fo;
+  b->host.resize(n);
+  int max_tiles = 1;
+  size_t off = 0;
+  std::vector<std::pair<size_t, const void*>> copies;   // (slab offset, host ptr) with sizes below
+  std::vector<size_t> copy_bytes;
+  for (int i = 0; i < n; ++i) {
+    const dphy_spr_request& r = reqs[i];
+    SprStudy& S = b->host[i];
+    std::memset(&S, 0, sizeof(S));
+    if (r.tree < 0 || r.tree >= fo->h.num_trees) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: tree index out of range"); }
+    const TreeDev& T = fo->trees[r.tree];
+    const int L = fo->sites[T.sites_id]->L;
+    if (r.X < -1 || r.X >= T.num_nodes) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: X out of range"); }
+    if (r.X == T.root_id) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: X must not be the root (CHECK_NE(X, tree->root))"); }
+    if (r.start_branch < 0 || r.start_branch >= T.num_nodes) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: start branch out of range"); }
+    if (r.start_branch == r.X) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: start region is on branch X"); }
+    if (!(r.lambda_X > 0.0)) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: lambda_X must be > 0"); }
+    S.tree = r.tree; S.X = r.X; S.start_branch = r.start_branch; S.start_mut_idx = r.start_mut_idx;
+    S.init_min_muts = r.init_min_muts; S.limit = r.max_muts_from_start; S.can_change_root = r.can_change_root != 0;
+    S.t_X = r.t_X; S.lambda_X = r.lambda_X; S.f = r.annealing_factor; S.t_max_tip = r.t_max_tip;
+    S.n_x_deltas = r.X < 0 ? r.n_x_deltas : 0; S.n_x_missing = r.X < 0 ? r.n_x_missing : 0;
+    for (int k = 0; k < S.n_x_deltas; ++k)
+      if (r.x_delta_site[k] < 0 || r.x_delta_site[k] >= L || r.x_delta_to[k] > 3) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: X delta out of range"); }
+    for (int k = 0; k < S.n_x_missing; ++k)
+      if (r.x_missing_start[k] < 0 || r.x_missing_end[k] > L || r.x_missing_start[k] >= r.x_missing_end[k]) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: X missing interval out of range"); }
+    max_tiles = std::max(max_tiles, T.num_tiles);
+    const int N = T.num_nodes;
+    // exact upper bound on regions: every non-root node has n+1 regions, the root has 1
+    const int64_t cap64 = (int64_t)N + fo->tree_muts[r.tree] + 1;
+    if (cap64 > INT_MAX) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: region capacity overflow"); }
+    S.region_cap = (int32_t)cap64;
+    S.path_cap = fo->tree_max_depth[r.tree] + 2;
+    S.off_xtab = off; off = al(off + L);
+    S.off_path = off; off = al(off + sizeof(int32_t) * S.path_cap);
+    S.off_xpath = off; off = al(off + sizeof(int32_t) * S.path_cap);
+    S.off_H = off; off = al(off + sizeof(int32_t) * N);
+    S.off_C = off; off = al(off + sizeof(int32_t) * N);
+    S.off_KB = off; off = al(off + sizeof(int32_t) * (N + 1));
+    S.off_seg = off; off = al(off + sizeof(int32_t) * kSegStride * (size_t)S.path_cap);
+    S.off_part = off; off = al(off + sizeof(double) * kNormBlocks);
+    S.off_xd_site = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_deltas));
+    S.off_xd_to = off; off = al(off + std::max(1, S.n_x_deltas));
+    S.off_xm_start = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_missing));
+    S.off_xm_end = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_missing));
+    S.off_regions = off; off = al(off + sizeof(dphy_candidate_region) * (size_t)S.region_cap);
+    if (S.n_x_deltas) {
+      copies.push_back({(size_t)S.off_xd_site, r.x_delta_site}); copy_bytes.push_back(sizeof(int32_t) * S.n_x_deltas);
+      copies.push_back({(size_t)S.off_xd_to, r.x_delta_to}); copy_bytes.push_back(S.n_x_deltas);
+    }
+    if (S.n_x_missing) {
+      copies.push_back({(size_t)S.off_xm_start, r.x_missing_start}); copy_bytes.push_back(sizeof(int32_t) * S.n_x_missing);
+      copies.push_back({(size_t)S.off_xm_end, r.x_missing_end}); copy_bytes.push_back(sizeof(int32_t) * S.n_x_missing);
+    }
+  }
+  const size_t slab_bytes = off;
+  const size_t b_studies = 0;
+  const size_t b_agg = al(b_studies + sizeof(SprStudy) * std::max(1, n));
+  const size_t b_flag = al(b_agg + sizeof(int32_t) * 3 * (size_t)max_tiles * std::max(1, n));
+  const size_t b_ticket = al(b_flag + sizeof(uint32_t) * (size_t)max_tiles * std::max(1, n));
+  const size_t b_slab = al(b_ticket + sizeof(uint32_t) * 4 * std::max(1, n));
+  const size_t total = b_slab + slab_bytes;
+  char* d = nullptr;
+  cudaError_t ce = cudaMallocAsync((void**)&d, total, ctx->stream);
+  if (ce != cudaSuccess) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, std::string("cudaMallocAsync(spr batch): ") + cudaGetErrorString(ce)); }
+  b->d_block = d; b->bytes = total;
+  b->dev.studies = (SprStudy*)(d + b_studies);
+  b->dev.tile_agg = (int32_t*)(d + b_agg);
+  b->dev.tile_flag = (uint32_t*)(d + b_flag);
+  b->dev.ticket = (uint32_t*)(d + b_ticket);
+  b->dev.slab = d + b_slab;
+  b->dev.num_studies = n; b->dev.max_tiles = max_tiles; b->dev.epoch = 1;
+  if (n == 0) { *out = b; return DPHY_OK; }
+  // flags + tickets start at zero; studies + X overlays uploaded through the pinned staging buffer
+  ce = cudaMemsetAsync(d + b_flag, 0, b_slab - b_flag, ctx->stream);
+  size_t stage = sizeof(SprStudy) * n;
+  for (size_t cb : copy_bytes) stage += al(cb);
+  if (ce == cudaSuccess) {
+    void* hbv = nullptr;
+    st = acquire_pinned(ctx, stage, &hbv);
+    if (st != DPHY_OK) { cudaFreeAsync(d, ctx->stream); delete b; return st; }
+    char* hb = (char*)hbv;
+    std::memcpy(hb, b->host.data(), sizeof(SprStudy) * n);
+    ce = cudaMemcpyAsync(b->dev.studies, hb, sizeof(SprStudy) * n, cudaMemcpyHostToDevice, ctx->stream);
+    size_t so = sizeof(SprStudy) * n;
+    for (size_t k = 0; k < copies.size() && ce == cudaSuccess; ++k) {
+      std::memcpy(hb + so, copies[k].second, copy_bytes[k]);
+      ce = cudaMemcpyAsync(b->dev.slab + copies[k].first, hb + so, copy_bytes[k], cudaMemcpyHostToDevice, ctx->stream);
+      so += al(copy_bytes[k]);
+    }
+    release_pinned_async(ctx);
+  }
+  if (ce != cudaSuccess) { cudaFreeAsync(d, ctx->stream); delete b; return check_cuda(ctx, ce, "spr batch upload"); }
+  const dim3 grid_tiles(max_tiles, n);
+  spr_setup_kernel<<<n, 256, 0, ctx->stream>>>(fo->h, b->dev);
+  spr_scan_kernel<0><<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+  bool any_limited = false;
+  for (int i = 0; i < n; ++i) any_limited |= (b->host[i].limit != INT_MAX);
+  int launched = 2;
+  if (any_limited) { spr_scan_kernel<1><<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
+  spr_segments_kernel<<<n, 256, 0, ctx->stream>>>(fo->h, b->dev);
+  spr_emit_kernel<<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+  spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ctx->stream>>>(b->dev);
+  launched += 3;
+  ctx->launches += launched;
+  st = check_cuda(ctx, cudaGetLastError(), "spr kernels launch");
+  if (st != DPHY_OK) { cudaFreeAsync(d, ctx->stream); delete b; return st; }
+  *out = b;
+  return DPHY_OK;
+}
+
+void dphy_spr_batch_destroy(dphy_ctx* ctx, dphy_spr_batch* b) {
+  if (!b) return;
+  if (ctx && b->d_block) { cudaSetDevice(ctx->device); cudaFreeAsync(b->d_block, ctx->stream); }
+  delete b;
+}
+
+static int spr_fetch(dphy_ctx* ctx, dphy_spr_batch* b) {
+  if (b->fetched || b->num == 0) return DPHY_OK;
+  DPHY_CUDA(ctx, cudaMemcpyAsync(b->host.data(), b->dev.studies, sizeof(SprStudy) * b->num, cudaMemcpyDeviceToHost, ctx->stream));
+  DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  b->fetched = true;
+  for (int i = 0; i < b->num; ++i) {
+    if (b->host[i].error == 1) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: X has no parent");
+    if (b->host[i].error == 2) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: start_mut_idx out of range for the start branch");
+    if (b->host[i].error == 3) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: start region lies inside X's subtree");
+    if (b->host[i].total_regions > b->host[i].region_cap) return set_error(ctx, DPHY_ERR_INTERNAL, "spr: region capacity exceeded");
+  }
+  return DPHY_OK;
+}
+
+int dphy_spr_batch_get_summaries(dphy_ctx* ctx, dphy_spr_batch* b, dphy_spr_summary* out) {
+  if (!ctx || !b || !out) return DPHY_ERR_INVALID_ARGUMENT;
+  int st = spr_fetch(ctx, b);
+  if (st != DPHY_OK) return st;
+  int64_t off = 0;
+  for (int i = 0; i < b->num; ++i) {
+    const SprStudy& S = b->host[i];
+    out[i].mu = S.mu; out[i].log_Wmax = S.log_Wmax; out[i].sum_W_over_Wmax = S.sum_W;
+    out[i].num_regions = S.total_regions; out[i].num_missing_at_X = S.num_missing; out[i].region_offset = off;
+    off += S.total_regions;
+  }
+  return DPHY_OK;
+}
+
+int64_t dphy_spr_batch_total_regions(dphy_ctx* ctx, dphy_spr_batch* b) {
+  if (!ctx || !b) return DPHY_ERR_INVALID_ARGUMENT;
+  int st = spr_fetch(ctx, b);
+  if (st != DPHY_OK) return st;
+  int64_t tot = 0;
+  for (int i = 0; i < b->num; ++i) tot += b->host[i].total_regions;
+  return tot;
+}
+
+int64_t dphy_spr_batch_get_regions(dphy_ctx* ctx, dphy_spr_batch* b, int32_t request, dphy_candidate_region* out, int64_t cap) {
+  if (!ctx || !b || (!out && cap > 0) || request >= b->num) return DPHY_ERR_INVALID_ARGUMENT;
+  int st = spr_fetch(ctx, b);
+  if (st != DPHY_OK) return st;
+  int64_t w = 0;
+  const int lo = request < 0 ? 0 : request, hi = request < 0 ? b->num : request + 1;
+  for (int i = lo; i < hi; ++i) {
+    const SprStudy& S = b->host[i];
+    if (w + S.total_regions > cap) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: output capacity too small");
+    if (S.total_regions > 0)
+      DPHY_CUDA(ctx, cudaMemcpyAsync(out + w, b->dev.slab + S.off_regions, sizeof(dphy_candidate_region) * (size_t)S.total_regions,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    w += S.total_regions;
+  }
+  DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return w;
+}
+
+int dphy_spr_batch_pick_nexus_regions(dphy_ctx* ctx, dphy_spr_batch* b, const double* r, int32_t* out_idx) {
+  if (!ctx || !b || !r || !out_idx) return DPHY_ERR_INVALID_ARGUMENT;
+  if (b->num == 0) return DPHY_OK;
+  const size_t mark = ctx->arena.mark();
+  double* d_r = (double*)ctx->arena.alloc(sizeof(double) * b->num);
+  int32_t* d_o = (int32_t*)ctx->arena.alloc(sizeof(int32_t) * b->num);
+  if (!d_r || !d_o) { ctx->arena.release(mark); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (spr pick)"); }
+  DPHY_CUDA(ctx, cudaMemcpyAsync(d_r, r, sizeof(double) * b->num, cudaMemcpyHostToDevice, ctx->stream));
+  spr_pick_kernel<<<b->num, 1024, 0, ctx->stream>>>(b->dev, d_r, d_o);
+  ctx->launches += 1;
+  int st = check_cuda(ctx, cudaGetLastError(), "spr_pick_kernel");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(out_idx, d_o, sizeof(int32_t) * b->num, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "spr pick");
+  ctx->arena.release(mark);
+  return st;
+}
+
+int dphy_spr_batch_find_region(dphy_ctx* ctx, dphy_spr_batch* b, int32_t request, int32_t branch, double t, int32_t* out_idx) {
+  if (!ctx || !b || !out_idx || request < 0 || request >= b->num) return DPHY_ERR_INVALID_ARGUMENT;
+  const size_t mark = ctx->arena.mark();
+  int32_t* d_o = (int32_t*)ctx->arena.alloc(sizeof(int32_t));
+  if (!d_o) { ctx->arena.release(mark); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (spr find)"); }
+  const int32_t init = INT_MAX;
+  DPHY_CUDA(ctx, cudaMemcpyAsync(d_o, &init, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  spr_find_kernel<<<64, 256, 0, ctx->stream>>>(b->dev, request, branch, t, d_o);
+  ctx->launches += 1;
+  int32_t res = INT_MAX;
+  int st = check_cuda(ctx, cudaGetLastError(), "spr_find_kernel");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(&res, d_o, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "spr find");
+  ctx->arena.release(mark);
+  *out_idx = res == INT_MAX ? -1 : res;
+  return st;
+}
+
+}  // extern "C"
