@@ -272,8 +272,12 @@ def main():
         k_ev[i][1].record(stream)
         if spr_reqs is not None:
             s_ev[i][0].record(stream)
-            batches.append(forest.spr_study_batch(spr_reqs))
+            b = forest.spr_study_batch(spr_reqs)
             s_ev[i][1].record(stream)
+            if i + 1 < args.steps:
+                b.close()            # stream-ordered free: the memory is reused by the next step's batch
+            else:
+                batches.append(b)
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)

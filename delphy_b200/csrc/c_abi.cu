@@ -138,6 +138,15 @@ void* dphy_ctx_stream(dphy_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr
 int64_t dphy_ctx_launch_count(const dphy_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---- sites ------------------------------------------------------------------------------------------------------
+static void set_nu_uniform(dphy_sites* s, const double* nu_l) {
+  // no site-rate heterogeneity <=> every nu_l equals the same constant: mu*nu needs no per-site gather
+  bool uni = true;
+  for (int l = 1; l < s->L && uni; ++l) uni = (nu_l[l] == nu_l[0]);
+  s->h.nu_uniform = uni ? 1 : 0;
+  s->h.nu_const = uni ? nu_l[0] : 1.0;
+  s->h.pad = 0;
+}
+
 static int fill_evo(dphy_ctx* ctx, dphy_sites* s, const double* mu, const double* pi_a, const double* q_ab) {
   for (int b = 0; b < s->P; ++b) {
     s->h.mu[b] = mu[b];
@@ -185,6 +194,9 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
   uint8_t* hp = slab.at<uint8_t>(hb, b_part);
   for (int l = 0; l < L; ++l) hp[l] = (uint8_t)host->partition_for_site[l];
   std::memcpy(slab.at<double>(hb, b_nu), host->nu_l, sizeof(double) * L);
+  s->h_ref.assign(host->ref, host->ref + L);
+  s->h_part.assign(hp, hp + L);
+  set_nu_uniform(s, host->nu_l);
   s->d_ref = slab.at<uint8_t>(dbase, b_ref); s->d_part = slab.at<uint8_t>(dbase, b_part); s->d_nu = slab.at<double>(dbase, b_nu);
   s->d_munu = slab.at<double>(dbase, b_munu); s->d_cumQ = slab.at<double>(dbase, b_cumQ);
   s->d_ref_freq = slab.at<int32_t>(dbase, b_freq); s->d_cum_nu_ba = slab.at<double>(dbase, b_cnu);
@@ -215,6 +227,7 @@ int dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* s, const double* nu_l, const d
     st = acquire_pinned(ctx, sizeof(double) * s->L, &hbv);
     if (st != DPHY_OK) return st;
     std::memcpy(hbv, nu_l, sizeof(double) * s->L);
+    set_nu_uniform(s, nu_l);
     DPHY_CUDA(ctx, cudaMemcpyAsync(s->d_nu, hbv, sizeof(double) * s->L, cudaMemcpyHostToDevice, ctx->stream));
     release_pinned_async(ctx);
   }
@@ -289,7 +302,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   int st = acquire_pinned(ctx, upload_bytes, &hbv);
   if (st != DPHY_OK) { delete fo; return st; }
   char* hb = static_cast<char*>(hbv);
-  fo->tree_muts.resize(num_trees); fo->tree_max_depth.resize(num_trees);
+  fo->tree_muts.resize(num_trees); fo->tree_fs.resize(num_trees); fo->tree_max_depth.resize(num_trees);
   auto* h_trees = slab.at<TreeDev>(hb, b_trees);
   auto* h_sites = slab.at<SitesDev>(hb, b_sites);
   auto* h_tile_tree = slab.at<int32_t>(hb, b_tile_tree);
@@ -316,6 +329,8 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     const int n = e.num_nodes;
     const int si = sites_index ? sites_index[k] : 0;
     const int L = sites[si]->L;
+    const uint8_t* hpart = sites[si]->h_part.data();
+    const uint8_t* href = sites[si]->h_ref.data();
     // DFS pre-order, children[1] before children[0]; encode "exit" visits as ~v on the stack
     int32_t* pos_of = h_pos + base;
     std::fill(pos_of, pos_of + n, -1);
@@ -345,7 +360,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
         const int l = e.mut_site[i];
         if (l < 0 || l >= L) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "mutation site out of range"); }
         if (e.mut_from[i] > 3 || e.mut_to[i] > 3) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "mutation state not in ACGT"); }
-        h_msite[mpos] = l; h_mft[mpos] = (uint8_t)(e.mut_from[i] << 2 | e.mut_to[i]); h_mt[mpos] = e.mut_t[i]; ++mpos;
+        h_msite[mpos] = l; h_mft[mpos] = (uint8_t)(hpart[l] << 4 | e.mut_from[i] << 2 | e.mut_to[i]); h_mt[mpos] = e.mut_t[i]; ++mpos;
       }
       h_ioff[base + p] = ipos;
       for (int i = e.miss_off[v]; i < e.miss_off[v + 1]; ++i) {
@@ -359,7 +374,8 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
       for (int i = e.fs_off[v]; i < e.fs_off[v + 1]; ++i) {
         const int l = e.fs_site[i];
         if (l < 0 || l >= L) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "Missation out of range"); }
-        h_fsite[fpos] = l; h_ffrom[fpos] = e.fs_from[i]; ++fpos;
+        if (e.fs_from[i] > 3) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "missation from-state not in ACGT"); }
+        h_fsite[fpos] = l; h_ffrom[fpos] = (uint8_t)(hpart[l] << 4 | href[l] << 2 | e.fs_from[i]); ++fpos;
       }
       const int32_t c0 = e.child0[v], c1 = e.child1[v];
       stack.push_back(~v);
@@ -369,7 +385,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
       }
     }
     if (next != n) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "tree is disconnected"); }
-    fo->tree_muts[k] = e.mut_off[n];
+    fo->tree_muts[k] = e.mut_off[n]; fo->tree_fs[k] = e.fs_off[n];
     { int32_t md = 0; for (int i = 0; i < n; ++i) md = std::max(md, h_depth[base + i]); fo->tree_max_depth[k] = md; }
     TreeDev& T = fo->trees[k];
     T.node_base = base; T.num_nodes = n; T.sites_id = si; T.first_tile = tile_pos;
@@ -398,9 +414,9 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   h.post_node = slab.at<int32_t>(dbase, b_post); h.pos_of_node = slab.at<int32_t>(dbase, b_pos);
   h.t = slab.at<double>(dbase, b_t);
   h.mut_off = slab.at<int32_t>(dbase, b_moff); h.mut_site = slab.at<int32_t>(dbase, b_msite);
-  h.mut_ft = slab.at<uint8_t>(dbase, b_mft); h.mut_t = slab.at<double>(dbase, b_mt);
+  h.mut_code = slab.at<uint8_t>(dbase, b_mft); h.mut_t = slab.at<double>(dbase, b_mt);
   h.miss_off = slab.at<int32_t>(dbase, b_ioff); h.miss_start = slab.at<int32_t>(dbase, b_is); h.miss_end = slab.at<int32_t>(dbase, b_ie);
-  h.fs_off = slab.at<int32_t>(dbase, b_foff); h.fs_site = slab.at<int32_t>(dbase, b_fsite); h.fs_from = slab.at<uint8_t>(dbase, b_ffrom);
+  h.fs_off = slab.at<int32_t>(dbase, b_foff); h.fs_site = slab.at<int32_t>(dbase, b_fsite); h.fs_code = slab.at<uint8_t>(dbase, b_ffrom);
   fo->d_lambda = slab.at<double>(dbase, b_lambda); fo->d_nsmn = slab.at<int32_t>(dbase, b_nsmn);
   fo->d_tree_out = slab.at<double>(dbase, b_tout); fo->d_tree_iout = slab.at<int32_t>(dbase, b_tiout);
   fo->d_tile_agg = slab.at<double>(dbase, b_tagg); fo->d_tile_iagg = slab.at<int32_t>(dbase, b_tiagg);
@@ -427,7 +443,10 @@ int64_t dphy_forest_log_G_algorithmic_bytes(const dphy_forest* fo) {
   // N*(4 parent + 8 t + 4+4+4 CSR offsets) + M*(4 site + 1 from|to + 8 t) + M*8 (nu_l gather)
   //                         + I*(4+4) + I*16 (two cum_Q gathers) + F*(4+1) + F*8 + N*8 (lambda_i written once) + 8/tree
   const int64_t N = fo->h.num_nodes, M = fo->total_muts, I = fo->total_ivls, F = fo->total_fs;
-  return N * 24 + M * 13 + M * 8 + I * 8 + I * 16 + F * 5 + F * 8 + N * 8 + 8 * (int64_t)fo->h.num_trees;
+  int64_t nu_bytes = 0;   // "[nu on: M*8 + F*8]" -- only trees whose site table has site-rate heterogeneity
+  for (size_t k = 0; k < fo->trees.size(); ++k)
+    if (!fo->sites[fo->trees[k].sites_id]->h.nu_uniform) nu_bytes += 8 * (fo->tree_muts[k] + fo->tree_fs[k]);
+  return N * 24 + M * 13 + I * 8 + I * 16 + F * 5 + nu_bytes + N * 8 + 8 * (int64_t)fo->h.num_trees;
 }
 
 int dphy_forest_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t count, const int32_t* nodes, const double* t) {
@@ -483,16 +502,28 @@ int dphy_forest_get_lambda_i(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, doubl
   if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
   if (!fo->evaluated) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
   const TreeDev& T = fo->trees[tree];
-  DPHY_CUDA(ctx, cudaMemcpyAsync(out, fo->d_lambda + T.node_base, sizeof(double) * T.num_nodes, cudaMemcpyDeviceToHost, ctx->stream));
-  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "lambda_i D2H");
+  const size_t mark = ctx->arena.mark();
+  double* tmp = (double*)ctx->arena.alloc(sizeof(double) * T.num_nodes);
+  if (!tmp) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (lambda_i)");
+  int st = gather_lambda_host_order(ctx, fo, tree, tmp);
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(out, tmp, sizeof(double) * T.num_nodes, cudaMemcpyDeviceToHost, ctx->stream), "lambda_i D2H");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "lambda_i D2H");
+  ctx->arena.release(mark);
+  return st;
 }
 
 int dphy_forest_get_num_sites_missing(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t* out) {
   if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
   if (!fo->evaluated) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
   const TreeDev& T = fo->trees[tree];
-  DPHY_CUDA(ctx, cudaMemcpyAsync(out, fo->d_nsmn + T.node_base, sizeof(int32_t) * T.num_nodes, cudaMemcpyDeviceToHost, ctx->stream));
-  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "nsmn D2H");
+  const size_t mark = ctx->arena.mark();
+  int32_t* tmp = (int32_t*)ctx->arena.alloc(sizeof(int32_t) * T.num_nodes);
+  if (!tmp) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (nsmn)");
+  int st = gather_nsmn_host_order(ctx, fo, tree, tmp);
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(out, tmp, sizeof(int32_t) * T.num_nodes, cudaMemcpyDeviceToHost, ctx->stream), "nsmn D2H");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "nsmn D2H");
+  ctx->arena.release(mark);
+  return st;
 }
 
 int dphy_forest_calc_tallies(dphy_ctx* ctx, dphy_forest* fo, dphy_tallies* out) {

@@ -47,6 +47,9 @@ struct SitesDev {
   double pi[kMaxPartitions * 4];
   double q[kMaxPartitions * 16];     // q_ab
   double log_pi[kMaxPartitions * 4]; // log(pi) (or 0 where pi == 0; see pi)
+  int32_t nu_uniform;        // 1 if every nu_l == nu_const (no site-rate heterogeneity): munu needs no gather
+  int32_t pad;
+  double nu_const;
 };
 
 // Per-tree record.
@@ -80,14 +83,14 @@ struct ForestDev {
   double* t;                    // node times (mutable: displace moves)
   const int32_t* mut_off;       // [num_nodes+1] CSR, device order
   const int32_t* mut_site;
-  const uint8_t* mut_ft;        // from << 2 | to
+  const uint8_t* mut_code;      // partition << 4 | from << 2 | to
   double* mut_t;
   const int32_t* miss_off;      // [num_nodes+1]
   const int32_t* miss_start;
   const int32_t* miss_end;
   const int32_t* fs_off;        // [num_nodes+1]
   const int32_t* fs_site;
-  const uint8_t* fs_from;
+  const uint8_t* fs_code;       // partition << 4 | ref << 2 | from
   // host-order lookup: device position of (tree, host node id) = pos_of_node[tree.node_base + id]
   const int32_t* pos_of_node;
 };
@@ -115,6 +118,7 @@ struct dphy_sites {
   // per-(partition,state) cumulative nu tables for O(1) interval tallies (Ttwiddle): [P*4][L+1]
   double* d_cum_nu_ba = nullptr;
   size_t bytes = 0;
+  std::vector<uint8_t> h_ref, h_part;   // host copies (used to pack per-event codes at forest upload)
   uint64_t version = 1;         // bumped by set_evo; forests re-sync their SitesDev copies lazily
 };
 
@@ -127,9 +131,10 @@ struct dphy_forest {
   size_t bytes = 0;
   int64_t total_muts = 0, total_ivls = 0, total_fs = 0, total_nonroot_muts = 0;
   std::vector<int64_t> tree_muts;     // mutations per tree (incl. the root's list)
+  std::vector<int64_t> tree_fs;       // from-state overrides per tree
   std::vector<int32_t> tree_max_depth;
   // outputs of the last eval (device)
-  double* d_lambda = nullptr;   // [num_nodes] host order per tree (tree.node_base + node id)
+  double* d_lambda = nullptr;   // [num_nodes] device order
   int32_t* d_nsmn = nullptr;    // [num_nodes]
   double* d_tree_out = nullptr; // [num_trees * 4]: root_prior, below_root, T, unused
   int32_t* d_tree_iout = nullptr; // [num_trees * 20]: num_muts, pad, num_muts_ab[16], ...
@@ -155,6 +160,8 @@ int check_cuda(dphy_ctx* ctx, cudaError_t e, const char* what);
 int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s);
 // kernels_logg.cu
 int launch_log_G(dphy_ctx* ctx, dphy_forest* f);
+int gather_lambda_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, double* d_dst);
+int gather_nsmn_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* d_dst);
 int refresh_sites(dphy_ctx* ctx, dphy_forest* f);   // c_abi.cu
 // Pinned staging buffer of the ctx: acquire waits for the previous async copy out of it; release records an event.
 int acquire_pinned(dphy_ctx* ctx, size_t bytes, void** out);

@@ -15,10 +15,11 @@
 // slice of the tree's post-order list: post_node[c(q-1) .. c(q)) with c(q) = q - depth[q].  Each CTA owns a tile of
 // kTile consecutive positions of one tree; it (1) computes delta / the mutation part of log G / missing-site counts
 // for its own nodes straight from the CSR lists, (2) forms diff (re-deriving delta for the few nodes that opened in
-// an earlier tile and close in this one), (3) block-scans, publishes its tile aggregate and sums the aggregates of
-// all earlier tiles of the same tree (fixed order => bit-reproducible), (4) writes lambda_i / nsmn and reduces
-// -lambda*(t - t_parent) + mutation terms.  The last CTA to finish a tree folds the per-tile partials in tile
-// order and evaluates the root prior.  Every input byte is read once (plus the re-derived closers).
+// an earlier tile and close in this one), (3) block-scans and writes the tile-local lambda / nsmn (device order) plus
+// per-tile partial sums.  No CTA ever waits for another one: a second, tiny kernel (one CTA per tree) scans the tile
+// aggregates in tile order, folds log G = sum_tiles (A1 - prefix * A2) and evaluates the root prior, and a third
+// streaming kernel adds each tile's prefix to lambda_i / nsmn in place.  Fixed reduction shapes everywhere =>
+// bit-reproducible results.  Every input byte is read once (plus the re-derived closers).
 #include "dphy_internal.h"
 #include "device_utils.cuh"
 
@@ -28,181 +29,202 @@ namespace dphy {
 
 struct LogGParams {
   ForestDev f;
-  double* lambda_out;
-  int32_t* nsmn_out;
-  double* tile_agg;
+  double* lambda_out;    // [num_nodes] device order
+  int32_t* nsmn_out;     // [num_nodes] device order
+  double* tile_agg;      // [num_tiles] sum of diff over the tile; overwritten by the tile's exclusive prefix in pass 2
   int32_t* tile_iagg;
-  uint32_t* tile_flag;
-  double* tile_part;     // [num_tiles * 2]  (log G partial, T partial)
+  double* tile_part;     // [num_tiles * 2]  (A1 = sum[-(lambda_ref+incl) len + g], A2 = sum len)
   int32_t* tile_ipart;   // [num_tiles * 17] (num_muts, num_muts_ab[16])
-  uint32_t* tree_done;   // [num_trees]
-  uint32_t* ticket;      // [2]: tile ticket, tiles done
   double* tree_out;      // [num_trees * 4]: log_root_prior, log_G_below_root, T, lambda_root
   int32_t* tree_iout;    // [num_trees * 20]: num_muts, 0, num_muts_ab[16], 0, 0
-  uint32_t epoch;
 };
 
-// delta lambda across the branch ending at device position p (phylo_tree_calc.h:140-155), the number of sites that
-// go missing on it, and (optionally) the mutation part of calc_branch_log_G (phylo_tree_calc.h:196-203).
-template <bool kWantG>
-__device__ __forceinline__ void branch_terms(const ForestDev& f, const SitesDev& S, const double* __restrict__ sq,
-                                             int p, double tP, double& delta, int& nmiss, double& g,
-                                             int* __restrict__ s_ab) {
+// Capacity (events per chunk) of the flat event buffers in shared memory.
+constexpr int kEvCap = 1536;
+constexpr int kClCap = 1024;
+
+// Sequential re-derivation of delta-lambda / missing-site count of ONE branch (used for the few "foreign closers":
+// nodes that opened in an earlier tile and close inside this one).  phylo_tree_calc.h:121-155.
+__device__ void branch_delta_seq(const ForestDev& f, const SitesDev& S, const double* __restrict__ sq,
+                                 const double* __restrict__ smu, int p, double& delta, int& nmiss) {
+  const bool uni = S.nu_uniform != 0;
   double dm = 0.0;
-  g = 0.0;
-  const int m0 = f.mut_off[p], m1 = f.mut_off[p + 1];
-  for (int i = m0; i < m1; ++i) {
-    const int l = __ldg(f.mut_site + i);
-    const int ft = __ldg(f.mut_ft + i);
-    const int from = ft >> 2, to = ft & 3;
-    const int pt = __ldg(S.part + l);
-    const double mn = __ldg(S.munu + l);
-    const double qf = -sq[pt * 16 + from * 5], qt = -sq[pt * 16 + to * 5];
-    dm += mn * (qt - qf);
-    if (kWantG) {
-      g -= mn * (qf - qt) * (__ldg(f.mut_t + i) - tP);
-      g += log(mn * sq[pt * 16 + from * 4 + to]);
-      atomicAdd(&s_ab[ft], 1);
-    }
+  for (int i = f.mut_off[p]; i < f.mut_off[p + 1]; ++i) {
+    const int code = __ldg(f.mut_code + i);
+    const int pt = code >> 4, from = (code >> 2) & 3, to = code & 3;
+    const double mn = uni ? smu[pt] : __ldg(S.munu + __ldg(f.mut_site + i));
+    dm += mn * ((-sq[pt * 16 + to * 5]) - (-sq[pt * 16 + from * 5]));
   }
   double dmi = 0.0;
   int nm = 0;
-  const int i0 = f.miss_off[p], i1 = f.miss_off[p + 1];
-  for (int i = i0; i < i1; ++i) {
+  for (int i = f.miss_off[p]; i < f.miss_off[p + 1]; ++i) {
     const int s = __ldg(f.miss_start + i), e = __ldg(f.miss_end + i);
     dmi -= __ldg(S.cumQ + e) - __ldg(S.cumQ + s);
     nm += e - s;
   }
-  const int f0 = f.fs_off[p], f1 = f.fs_off[p + 1];
-  for (int i = f0; i < f1; ++i) {
-    const int l = __ldg(f.fs_site + i);
-    const int from = __ldg(f.fs_from + i), rf = __ldg(S.ref + l);
-    const int pt = __ldg(S.part + l);
-    dmi -= __ldg(S.munu + l) * ((-sq[pt * 16 + from * 5]) - (-sq[pt * 16 + rf * 5]));
+  for (int i = f.fs_off[p]; i < f.fs_off[p + 1]; ++i) {
+    const int code = __ldg(f.fs_code + i);
+    const int pt = code >> 4, rf = (code >> 2) & 3, from = code & 3;
+    const double mn = uni ? smu[pt] : __ldg(S.munu + __ldg(f.fs_site + i));
+    dmi -= mn * ((-sq[pt * 16 + from * 5]) - (-sq[pt * 16 + rf * 5]));
   }
   delta = dm + dmi;
   nmiss = nm;
 }
 
+// Flat-over-events + segmented-sum-per-node helper.  All threads of the CTA call it with the same [r0, r1).
+//   ev(i, slot)    : thread-parallel over events i of the tile, writes its contribution(s) to smem slot `slot`
+//   acc(slot)      : the owning node's thread folds the slots of its CSR slice in list order (deterministic)
+template <typename EventFn, typename AccFn>
+__device__ __forceinline__ void flat_segmented(int r0, int r1, const int* __restrict__ s_off, int n_act, EventFn ev, AccFn acc) {
+  const int tid = threadIdx.x;
+  for (int c0 = r0; c0 < r1; c0 += kEvCap) {
+    const int c1 = min(c0 + kEvCap, r1);
+    for (int i = c0 + tid; i < c1; i += kTile) ev(i, i - c0);
+    __syncthreads();
+    if (tid < n_act) {
+      const int lo = max(s_off[tid], c0), hi = min(s_off[tid + 1], c1);
+      for (int i = lo; i < hi; ++i) acc(i - c0);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kTile) emat_log_G_kernel(const LogGParams P) {
   __shared__ double s_q[kMaxPartitions * 16];
+  __shared__ double s_mu[kMaxPartitions];
+  __shared__ double s_bufA[kEvCap];
+  __shared__ double s_bufB[kEvCap];
+  __shared__ int s_off_m[kTile + 1];
+  __shared__ int s_off_i[kTile + 1];
+  __shared__ int s_off_f[kTile + 1];
   __shared__ double s_delta[kTile];
   __shared__ int s_nmiss[kTile];
   __shared__ double s_wsd[kTile / 32];
   __shared__ int s_wsi[kTile / 32];
   __shared__ int s_ab[16];
-  __shared__ int s_cnt[kMaxPartitions * 4];
-  __shared__ double s_prefix;
-  __shared__ int s_iprefix;
-  __shared__ int s_tile;
-  __shared__ int s_is_last;
 
   const ForestDev& f = P.f;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
 
-  if (tid == 0) s_tile = (int)atomicAdd(P.ticket, 1u);
   if (tid < 16) s_ab[tid] = 0;
-  __syncthreads();
-  const int tile = s_tile;
+  const int tile = blockIdx.x;
   const int tree = f.tile_tree[tile];
   const TreeDev T = f.trees[tree];
   const SitesDev& S = f.sites[T.sites_id];
   if (tid < S.P * 16) s_q[tid] = S.q[tid];
-  __syncthreads();
+  if (tid < S.P) s_mu[tid] = S.mu[tid] * S.nu_const;
+  const bool uni = S.nu_uniform != 0;
 
   const int tile_in_tree = tile - T.first_tile;
   const int tile_start = T.node_base + tile_in_tree * kTile;              // global device position
   const int tile_end = min(tile_start + kTile, T.node_base + T.num_nodes);
+  const int n_act = tile_end - tile_start;
   const int p = tile_start + tid;
   const bool active = p < tile_end;
+  const bool has_root = tile_in_tree == 0;                                 // position 0 of a tree is its root
 
-  // ---- (1) own branch terms --------------------------------------------------------------------------------
-  double delta = 0.0, g = 0.0, tP = 0.0, tN = 0.0;
-  int nmiss = 0, par = -1, dep = 0;
+  // ---- (0) node records + CSR offsets of the tile ---------------------------------------------------------------------
+  double tP = 0.0, tN = 0.0;
+  int par = -1, dep = 0;
   if (active) {
     par = f.parent_pos[p];
     dep = f.depth[p];
     tN = f.t[p];
-    if (par >= 0) {
-      tP = f.t[par];
-      branch_terms<true>(f, S, s_q, p, tP, delta, nmiss, g, s_ab);
-    } else {
-      double gg; int dummy_ab[1];
-      // the root's list holds ref->root-sequence "mutations" (t = -DBL_MAX): they shift lambda but are not counted
-      branch_terms<false>(f, S, s_q, p, 0.0, delta, nmiss, gg, dummy_ab);
-    }
+    if (par >= 0) tP = f.t[par];
+    s_off_m[tid] = f.mut_off[p]; s_off_i[tid] = f.miss_off[p]; s_off_f[tid] = f.fs_off[p];
+    if (tid == n_act - 1) { s_off_m[n_act] = f.mut_off[p + 1]; s_off_i[n_act] = f.miss_off[p + 1]; s_off_f[n_act] = f.fs_off[p + 1]; }
   }
-  s_delta[tid] = delta;
-  s_nmiss[tid] = nmiss;
   __syncthreads();
 
-  // ---- (2) diff = own delta - deltas of the nodes whose subtree closes right before this position ---------------
-  double diff = delta;
-  int idiff = nmiss;
-  if (active) {
-    const int q = p - T.node_base;
-    if (q > 0) {
-      const int dprev = f.depth[p - 1];
-      const int c0 = (q - 1) - dprev, c1 = q - dep;
-      double cs = 0.0; int ci = 0;
-      for (int j = c0; j < c1; ++j) {
-        const int a = f.post_node[T.node_base + j];
-        if (a >= tile_start) {
-          cs += s_delta[a - tile_start];
-          ci += s_nmiss[a - tile_start];
-        } else {   // opened in an earlier tile: re-derive its branch delta
-          double da, ga; int na; int dummy_ab[1];
-          branch_terms<false>(f, S, s_q, a, 0.0, da, na, ga, dummy_ab);
-          cs += da; ci += na;
-        }
+  // ---- (1) branch terms: flat over the tile's events, segmented sum per node --------------------------------------------
+  double dm = 0.0, esum = 0.0, dmi = 0.0;
+  int nmiss = 0;
+  const int root_m1 = has_root ? s_off_m[1] : s_off_m[0];   // the root's list ("mutations" above the root) ends here
+  // mutations: dm_i = mu nu (q_to - q_from);  e_i = dm_i * t_i + log(mu nu q_from,to)   [g_node = sum e_i - t_P * dm]
+  flat_segmented(s_off_m[0], s_off_m[n_act], s_off_m, n_act,
+    [&](int i, int slot) {
+      const int code = __ldg(f.mut_code + i);
+      const int pt = code >> 4, from = (code >> 2) & 3, to = code & 3;
+      const double mn = uni ? s_mu[pt] : __ldg(S.munu + __ldg(f.mut_site + i));
+      const double d = mn * ((-s_q[pt * 16 + to * 5]) - (-s_q[pt * 16 + from * 5]));
+      double e = 0.0;
+      if (i >= root_m1) {
+        e = d * __ldg(f.mut_t + i) + log(mn * s_q[pt * 16 + from * 4 + to]);
+        atomicAdd(&s_ab[code & 15], 1);
       }
-      diff -= cs;
-      idiff -= ci;
+      s_bufA[slot] = d; s_bufB[slot] = e;
+    },
+    [&](int slot) { dm += s_bufA[slot]; esum += s_bufB[slot]; });
+  // missation intervals: -(cumQ[end] - cumQ[start]); count of sites going missing
+  flat_segmented(s_off_i[0], s_off_i[n_act], s_off_i, n_act,
+    [&](int i, int slot) {
+      const int s = __ldg(f.miss_start + i), e = __ldg(f.miss_end + i);
+      s_bufA[slot] = __ldg(S.cumQ + e) - __ldg(S.cumQ + s);
+      reinterpret_cast<int*>(s_bufB)[slot] = e - s;
+    },
+    [&](int slot) { dmi -= s_bufA[slot]; nmiss += reinterpret_cast<int*>(s_bufB)[slot]; });
+  // from-state overrides of missing sites
+  flat_segmented(s_off_f[0], s_off_f[n_act], s_off_f, n_act,
+    [&](int i, int slot) {
+      const int code = __ldg(f.fs_code + i);
+      const int pt = code >> 4, rf = (code >> 2) & 3, from = code & 3;
+      const double mn = uni ? s_mu[pt] : __ldg(S.munu + __ldg(f.fs_site + i));
+      s_bufA[slot] = mn * ((-s_q[pt * 16 + from * 5]) - (-s_q[pt * 16 + rf * 5]));
+    },
+    [&](int slot) { dmi -= s_bufA[slot]; });
+  const double delta = dm + dmi;
+  const double g = (active && par >= 0) ? esum - tP * dm : 0.0;
+  s_delta[tid] = active ? delta : 0.0;
+  s_nmiss[tid] = active ? nmiss : 0;
+  __syncthreads();
+
+  // ---- (2) diff = own delta - deltas of the nodes whose subtree closes right before this position ---------------------------
+  // The tile's closers are one contiguous slice of the tree's post-order list; their deltas are gathered in parallel
+  // (in-tile from smem, foreign ones re-derived), then each position folds its own sub-slice in order.
+  double diff = active ? delta : 0.0;
+  int idiff = active ? nmiss : 0;
+  {
+    const int q_first = tile_start - T.node_base, q_last = tile_end - 1 - T.node_base;
+    const int cl0 = q_first == 0 ? 0 : (q_first - 1) - f.depth[tile_start - 1];
+    const int cl1 = q_last - f.depth[tile_end - 1];
+    int my0 = 0, my1 = 0;
+    if (active) {
+      const int q = p - T.node_base;
+      if (q > 0) { my0 = (q - 1) - f.depth[p - 1]; my1 = q - dep; }
+    }
+    int* s_cn = reinterpret_cast<int*>(s_bufB);
+    for (int c0 = cl0; c0 < cl1; c0 += kClCap) {
+      const int c1 = min(c0 + kClCap, cl1);
+      for (int j = c0 + tid; j < c1; j += kTile) {
+        const int a = f.post_node[T.node_base + j];
+        double da; int na;
+        if (a >= tile_start) { da = s_delta[a - tile_start]; na = s_nmiss[a - tile_start]; }
+        else branch_delta_seq(f, S, s_q, s_mu, a, da, na);
+        s_bufA[j - c0] = da; s_cn[j - c0] = na;
+      }
+      __syncthreads();
+      const int lo = max(my0, c0), hi = min(my1, c1);
+      for (int j = lo; j < hi; ++j) { diff -= s_bufA[j - c0]; idiff -= s_cn[j - c0]; }
+      __syncthreads();
     }
   }
 
-  // ---- (3) block scan, publish tile aggregate, gather predecessors ---------------------------------------------------
+  // ---- (3) block scan; tile-local lambda_i / nsmn; per-tile partial sums ------------------------------------------------
   double tot; int itot;
   const double incl = block_scan_incl<double, kTile>(diff, s_wsd, &tot);
   const int iincl = block_scan_incl<int, kTile>(idiff, s_wsi, &itot);
-  if (tid == 0) {
-    P.tile_agg[tile] = tot;
-    P.tile_iagg[tile] = itot;
-    __threadfence();
-    st_release_u32(P.tile_flag + tile, P.epoch);
-  }
-  if (warp == 0) {
-    double acc = 0.0; int iacc = 0;
-    for (int j0 = T.first_tile; j0 < tile; j0 += 32) {
-      const int j = j0 + lane;
-      if (j < tile) {
-        while (ld_acquire_u32(P.tile_flag + j) != P.epoch) { __nanosleep(20); }
-        acc += ld_cg_f64(P.tile_agg + j);
-        iacc += ld_cg_i32(P.tile_iagg + j);
-      }
-    }
-    acc = warp_sum(acc);
-    iacc = warp_sum(iacc);
-    if (lane == 0) { s_prefix = acc; s_iprefix = iacc; }
-  }
-  __syncthreads();
-
-  // ---- (4) lambda_i, nsmn, log-G partials ----------------------------------------------------------------------------
   double contrib = 0.0, tcontrib = 0.0;
   int nmut = 0;
   if (active) {
-    const double lambda_ref = S.cumQ[S.L];
-    const double lam = lambda_ref + (s_prefix + incl);
-    const int id = f.node_id[p];
-    P.lambda_out[T.node_base + id] = lam;
-    P.nsmn_out[T.node_base + id] = s_iprefix + iincl;
+    const double lam_local = S.cumQ[S.L] + incl;     // + the tile's prefix, added in pass 3
+    P.lambda_out[p] = lam_local;
+    P.nsmn_out[p] = iincl;
     if (par >= 0) {
       const double len = tN - tP;
-      contrib = -lam * len + g;
+      contrib = -lam_local * len + g;
       tcontrib = len;
-      nmut = f.mut_off[p + 1] - f.mut_off[p];
-    } else {
-      P.tree_out[tree * 4 + 3] = lam;
+      nmut = s_off_m[tid + 1] - s_off_m[tid];
     }
   }
   const double bsum = block_sum<double, kTile>(contrib, s_wsd);
@@ -210,65 +232,92 @@ __global__ void __launch_bounds__(kTile) emat_log_G_kernel(const LogGParams P) {
   const int msum = block_sum<int, kTile>(nmut, s_wsi);
   __syncthreads();
   if (tid == 0) {
+    P.tile_agg[tile] = tot;
+    P.tile_iagg[tile] = itot;
     P.tile_part[tile * 2 + 0] = bsum;
     P.tile_part[tile * 2 + 1] = tsum;
     P.tile_ipart[tile * 17 + 0] = msum;
   }
   if (tid < 16) P.tile_ipart[tile * 17 + 1 + tid] = s_ab[tid];
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const uint32_t done = atomicAdd(P.tree_done + tree, 1u);
-    s_is_last = (done == (uint32_t)T.num_tiles - 1u);
-    const uint32_t all = atomicAdd(P.ticket + 1, 1u);
-    if (all == (uint32_t)f.num_tiles - 1u) { P.ticket[0] = 0u; P.ticket[1] = 0u; }   // re-arm for the next launch
-  }
-  __syncthreads();
-  if (!s_is_last) return;
+}
 
-  // ---- (5) last CTA of this tree: fold per-tile partials in tile order + root prior --------------------------------------
-  __threadfence();
-  if (tid == 0) P.tree_done[tree] = 0u;
-  if (warp == 0) {
-    double a0 = 0.0, a1 = 0.0; int m = 0;
-    for (int j = T.first_tile + lane; j < T.first_tile + T.num_tiles; j += 32) {
-      a0 += ld_cg_f64(P.tile_part + j * 2 + 0);
-      a1 += ld_cg_f64(P.tile_part + j * 2 + 1);
-      m += ld_cg_i32(P.tile_ipart + j * 17);
+// ---- pass 2: one CTA per tree -- exclusive scan of the tile aggregates (tile order), log G fold, tallies, root prior -----
+__global__ void __launch_bounds__(kTile) emat_log_G_tree_kernel(const LogGParams P) {
+  __shared__ double s_wsd[kTile / 32];
+  __shared__ int s_wsi[kTile / 32];
+  __shared__ int s_cnt[kMaxPartitions * 4];
+  __shared__ double s_carry;
+  __shared__ int s_icarry;
+  const ForestDev& f = P.f;
+  const int tid = threadIdx.x;
+  const int tree = blockIdx.x;
+  const TreeDev T = f.trees[tree];
+  const SitesDev& S = f.sites[T.sites_id];
+  if (tid == 0) { s_carry = 0.0; s_icarry = 0; }
+  __syncthreads();
+  double a1 = 0.0, a2 = 0.0; int m = 0;
+  int ab[16];
+#pragma unroll
+  for (int b = 0; b < 16; ++b) ab[b] = 0;
+  for (int j0 = 0; j0 < T.num_tiles; j0 += kTile) {
+    const int j = T.first_tile + j0 + tid;
+    const bool ok = j0 + tid < T.num_tiles;
+    const double v = ok ? P.tile_agg[j] : 0.0;
+    const int iv = ok ? P.tile_iagg[j] : 0;
+    double tot; int itot;
+    const double incl = block_scan_incl<double, kTile>(v, s_wsd, &tot);
+    const int iincl = block_scan_incl<int, kTile>(iv, s_wsi, &itot);
+    if (ok) {
+      const double pre = s_carry + (incl - v);          // exclusive prefix of this tile
+      const int ipre = s_icarry + (iincl - iv);
+      P.tile_agg[j] = pre;
+      P.tile_iagg[j] = ipre;
+      const double A1 = P.tile_part[j * 2 + 0], A2 = P.tile_part[j * 2 + 1];
+      a1 += A1 - pre * A2;                              // sum over the tile of -(lambda_local + pre) len + g
+      a2 += A2;
+      m += P.tile_ipart[j * 17];
+#pragma unroll
+      for (int b = 0; b < 16; ++b) ab[b] += P.tile_ipart[j * 17 + 1 + b];
     }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); m = warp_sum(m);
-    if (lane == 0) {
-      P.tree_out[tree * 4 + 1] = a0;
-      P.tree_out[tree * 4 + 2] = a1;
-      P.tree_iout[tree * 20 + 0] = m;
-      P.tree_iout[tree * 20 + 1] = 0;
-    }
-  } else if (warp == 1) {
-    for (int b = lane; b < 16; b += 32) {
-      int c = 0;
-      for (int j = T.first_tile; j < T.first_tile + T.num_tiles; ++j) c += ld_cg_i32(P.tile_ipart + j * 17 + 1 + b);
-      P.tree_iout[tree * 20 + 2 + b] = c;
-    }
+    __syncthreads();
+    if (tid == 0) { s_carry += tot; s_icarry += itot; }
+    __syncthreads();
+  }
+  a1 = block_sum<double, kTile>(a1, s_wsd);
+  a2 = block_sum<double, kTile>(a2, s_wsd);
+  m = block_sum<int, kTile>(m, s_wsi);
+  if (tid == 0) {
+    P.tree_out[tree * 4 + 1] = a1;
+    P.tree_out[tree * 4 + 2] = a2;
+    P.tree_out[tree * 4 + 3] = S.cumQ[S.L] + 0.0;   // (lambda at the root is lambda_out[node_base] after pass 3)
+    P.tree_iout[tree * 20 + 0] = m;
+    P.tree_iout[tree * 20 + 1] = 0;
+  }
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    const int c = block_sum<int, kTile>(ab[b], s_wsi);
+    if (tid == 0) P.tree_iout[tree * 20 + 2 + b] = c;
   }
   // root prior (core/phylo_tree_calc.cpp:467-504): reference-sequence state counts per partition, adjusted by the
   // root's "mutations", missing sites and from-state overrides.
+  __syncthreads();
   if (tid < kMaxPartitions * 4) s_cnt[tid] = tid < S.P * 4 ? S.ref_freq[tid] : 0;
   __syncthreads();
   {
     const int r = T.node_base;   // the root is the first position of its tree
     for (int i = f.mut_off[r] + tid; i < f.mut_off[r + 1]; i += kTile) {
-      const int l = f.mut_site[i]; const int ft = f.mut_ft[i]; const int pt = S.part[l];
-      atomicSub(&s_cnt[pt * 4 + (ft >> 2)], 1);
-      atomicAdd(&s_cnt[pt * 4 + (ft & 3)], 1);
+      const int code = f.mut_code[i]; const int pt = code >> 4;
+      atomicSub(&s_cnt[pt * 4 + ((code >> 2) & 3)], 1);
+      atomicAdd(&s_cnt[pt * 4 + (code & 3)], 1);
     }
     for (int i = f.miss_off[r]; i < f.miss_off[r + 1]; ++i) {
       const int s = f.miss_start[i], e = f.miss_end[i];
       for (int l = s + tid; l < e; l += kTile) atomicSub(&s_cnt[S.part[l] * 4 + S.ref[l]], 1);
     }
     for (int i = f.fs_off[r] + tid; i < f.fs_off[r + 1]; i += kTile) {
-      const int l = f.fs_site[i]; const int pt = S.part[l];
-      atomicAdd(&s_cnt[pt * 4 + S.ref[l]], 1);
-      atomicSub(&s_cnt[pt * 4 + f.fs_from[i]], 1);
+      const int code = f.fs_code[i]; const int pt = code >> 4;
+      atomicAdd(&s_cnt[pt * 4 + ((code >> 2) & 3)], 1);
+      atomicSub(&s_cnt[pt * 4 + (code & 3)], 1);
     }
   }
   __syncthreads();
@@ -287,29 +336,58 @@ __global__ void __launch_bounds__(kTile) emat_log_G_kernel(const LogGParams P) {
   }
 }
 
+// ---- pass 3: add each tile's prefix to lambda_i / nsmn in place (streaming) ------------------------------------------------------
+__global__ void __launch_bounds__(kTile) emat_log_G_finish_kernel(const LogGParams P) {
+  const ForestDev& f = P.f;
+  const int tile = blockIdx.x;
+  const TreeDev T = f.trees[f.tile_tree[tile]];
+  const int p = T.node_base + (tile - T.first_tile) * kTile + threadIdx.x;
+  if (p < T.node_base + T.num_nodes) {
+    P.lambda_out[p] += P.tile_agg[tile];
+    P.nsmn_out[p] += P.tile_iagg[tile];
+  }
+}
+
+// host-order gather for the getters: out[id] = src[pos_of_node[id]]
+template <typename V>
+__global__ void gather_host_order_kernel(const int32_t* __restrict__ pos_of_node, const V* __restrict__ src, V* __restrict__ dst,
+                                         int node_base, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[node_base + pos_of_node[node_base + i]];
+}
+
+int gather_lambda_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, double* d_dst) {
+  const TreeDev& T = fo->trees[tree];
+  gather_host_order_kernel<double><<<(T.num_nodes + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->d_lambda, d_dst, T.node_base, T.num_nodes);
+  ctx->launches += 1;
+  return check_cuda(ctx, cudaGetLastError(), "gather_host_order_kernel<double>");
+}
+int gather_nsmn_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* d_dst) {
+  const TreeDev& T = fo->trees[tree];
+  gather_host_order_kernel<int32_t><<<(T.num_nodes + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->d_nsmn, d_dst, T.node_base, T.num_nodes);
+  ctx->launches += 1;
+  return check_cuda(ctx, cudaGetLastError(), "gather_host_order_kernel<int>");
+}
+
 int launch_log_G(dphy_ctx* ctx, dphy_forest* fo) {
   if (fo->h.num_tiles == 0) return DPHY_OK;
+  int st = refresh_sites(ctx, fo);
+  if (st != DPHY_OK) return st;
   LogGParams P;
   P.f = fo->h;
   P.lambda_out = fo->d_lambda;
   P.nsmn_out = fo->d_nsmn;
   P.tile_agg = fo->d_tile_agg;
   P.tile_iagg = fo->d_tile_iagg;
-  P.tile_flag = fo->d_tile_flag;
   P.tile_part = fo->d_tile_part;
   P.tile_ipart = fo->d_tile_ipart;
-  P.tree_done = fo->d_tree_done;
-  P.ticket = fo->d_ticket;
   P.tree_out = fo->d_tree_out;
   P.tree_iout = fo->d_tree_iout;
-  int st = refresh_sites(ctx, fo);
-  if (st != DPHY_OK) return st;
-  fo->epoch += 1;
-  if (fo->epoch == 0) fo->epoch = 1;
-  P.epoch = fo->epoch;
   emat_log_G_kernel<<<fo->h.num_tiles, kTile, 0, ctx->stream>>>(P);
-  ctx->launches += 1;
-  return check_cuda(ctx, cudaGetLastError(), "emat_log_G_kernel launch");
+  emat_log_G_tree_kernel<<<fo->h.num_trees, kTile, 0, ctx->stream>>>(P);
+  emat_log_G_finish_kernel<<<fo->h.num_tiles, kTile, 0, ctx->stream>>>(P);
+  ctx->launches += 3;
+  return check_cuda(ctx, cudaGetLastError(), "emat_log_G kernels launch");
 }
 
 }  // namespace dphy

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) spr_setup_kernel(ForestDev f, SprBatchDev
         const int a = xpath[jj];
         for (int i = f.mut_off[a]; i < f.mut_off[a + 1]; ++i) {
           const int l = f.mut_site[i];
-          xtab[l] = (uint8_t)((xtab[l] & 4) | (f.mut_ft[i] & 3));
+          xtab[l] = (uint8_t)((xtab[l] & 4) | (f.mut_code[i] & 3));
         }
       }
     }
@@ -193,7 +193,7 @@ __device__ __forceinline__ void node_dc(const ForestDev& f, const uint8_t* __res
   dH = 0; dC = 0;
   for (int i = f.mut_off[p]; i < f.mut_off[p + 1]; ++i) {
     int h, c;
-    mut_dc(xtab, f.mut_site[i], f.mut_ft[i], h, c);
+    mut_dc(xtab, f.mut_site[i], f.mut_code[i] & 15, h, c);
     dH += h; dC += c;
   }
 }
@@ -262,7 +262,7 @@ __device__ __forceinline__ int c_down_start(const ForestDev& f, const SprStudy& 
   int h = (par < 0 || S.pos0 == S.root_pos) ? 0 : Hend[par - S.node_base];
   if (S.pos0 != S.root_pos) {
     const int mo = f.mut_off[S.pos0];
-    for (int i = 0; i < S.k0; ++i) { int dh, dc; mut_dc(xtab, f.mut_site[mo + i], f.mut_ft[mo + i], dh, dc); c += dc; h += dh; }
+    for (int i = 0; i < S.k0; ++i) { int dh, dc; mut_dc(xtab, f.mut_site[mo + i], f.mut_code[mo + i] & 15, dh, dc); c += dc; h += dh; }
   }
   *H0 = h;
   return c;
@@ -287,7 +287,7 @@ __device__ int node_kept_count(const ForestDev& f, const SprStudy& S, const uint
     bool ok = true;
     if (limited) {
       ok = scope_dist(S, Cend, path, j, on_path, Cd, C0) <= S.limit;
-      if (k < np) { int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_ft[moff + k], dh, dc); Cd += dc; }
+      if (k < np) { int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc); Cd += dc; }
     }
     if (ok && eval_region(f, S, p, k, np, moff, tPar, tNode).keep) ++cnt;
   }
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256) spr_segments_kernel(ForestDev f, SprBatch
         bool ok = true;
         if (limited) {
           ok = scope_dist(S, Cend, path, j, true, Cd, C0) <= S.limit;
-          if (k < np) { int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_ft[moff + k], dh, dc); Cd += dc; }
+          if (k < np) { int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc); Cd += dc; }
         }
         if (ok && eval_region(f, S, a, k, np, moff, tPar, tNode).keep) {
           if (k == kA) ++cntA; else if (k < kA) ++cntUp; else ++cntOwn;
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(kTile) spr_emit_kernel(ForestDev f, SprBatchDe
       if (limited) ok = scope_dist(S, Cend, path, j, on_path, Cd, C0) <= S.limit;
       const int Hk = Hd;
       if (k < np) {
-        int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_ft[moff + k], dh, dc);
+        int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc);
         Hd += dh; Cd += dc;
       }
       if (!ok) continue;

@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(kTile) tally_events_kernel(ForestDev f, int tr
       len = is_root ? 0.0 : tN - f.t[par];
     }
     for (int i = f.mut_off[p]; i < f.mut_off[p + 1]; ++i) {
-      const int l = f.mut_site[i], ft = f.mut_ft[i], from = ft >> 2, to = ft & 3;
-      const int pt = S.part[l];
+      const int l = f.mut_site[i], code = f.mut_code[i], ft = code & 15, from = ft >> 2, to = ft & 3;
+      const int pt = code >> 4;
       if (!is_root) {   // "mutations" above the root are just deltas from the reference sequence
         if (out.num_muts_beta_ab) atomicAdd(&s_bab[pt * 16 + ft], 1);
         if (out.num_muts_l) atomicAdd(out.num_muts_l + l, 1);
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kTile) tally_events_kernel(ForestDev f, int tr
         if (out.miss_diff) { atomicAdd(out.miss_diff + s, Tbmiss); atomicAdd(out.miss_diff + e, -Tbmiss); }
       }
       for (int i = f.fs_off[p]; i < f.fs_off[p + 1]; ++i) {
-        const int l = f.fs_site[i], from = f.fs_from[i], rf = S.ref[l], pt = S.part[l];
+        const int l = f.fs_site[i], code = f.fs_code[i], from = code & 3, rf = (code >> 2) & 3, pt = code >> 4;
         if (out.beta_a_part) {
           const double w = S.nu[l] * Tbmiss;
 #pragma unroll
