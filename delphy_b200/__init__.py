@@ -166,6 +166,12 @@ def lib() -> C.CDLL:
     L.dphy_spr_batch_get_regions.restype = C.c_int64
     L.dphy_spr_batch_pick_nexus_regions.argtypes = [vp, vp, f64p, i32p]
     L.dphy_spr_batch_find_region.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_double, i32p]
+    L.dphy_partition_generate_stencil.argtypes = [C.POINTER(EmatHost), C.c_int32, C.c_uint64, i32p, i32p]
+    L.dphy_partition_split.argtypes = [C.POINTER(EmatHost), C.POINTER(SitesHost), C.c_int32, i32p, C.POINTER(vp)]
+    L.dphy_partition_num_parts.argtypes = [vp]; L.dphy_partition_num_parts.restype = C.c_int32
+    L.dphy_partition_part.argtypes = [vp, C.c_int32]; L.dphy_partition_part.restype = C.POINTER(EmatHost)
+    L.dphy_partition_orig_index.argtypes = [vp, C.c_int32]; L.dphy_partition_orig_index.restype = i32p
+    L.dphy_partition_free.argtypes = [vp]
     L.dphy_synth_default_params.argtypes = [C.POINTER(SynthParams), C.c_int32]
     L.dphy_synth_generate.argtypes = [C.POINTER(SynthParams), C.POINTER(C.POINTER(SynthEmat))]
     L.dphy_synth_free.argtypes = [C.POINTER(SynthEmat)]
@@ -231,6 +237,44 @@ class HostSites:
     def as_struct(self) -> SitesHost:
         return SitesHost(self.num_sites, self.num_partitions, _p(self.ref, u8p), _p(self.partition_for_site, i32p),
                          _p(self.nu_l, f64p), _p(self.mu, f64p), _p(self.pi_a, f64p), _p(self.q_ab, f64p))
+
+
+def _emat_from_struct(e: EmatHost) -> HostEmat:
+    N = e.num_nodes
+    M = int(e.mut_off[N]); I = int(e.miss_off[N]); F = int(e.fs_off[N])
+    return HostEmat(
+        e.root, e.includes_run_root,
+        parent=_np_from(e.parent, N, np.int32), child0=_np_from(e.child0, N, np.int32), child1=_np_from(e.child1, N, np.int32),
+        t=_np_from(e.t, N, np.float64),
+        mut_off=_np_from(e.mut_off, N + 1, np.int32), mut_site=_np_from(e.mut_site, M, np.int32),
+        mut_from=_np_from(e.mut_from, M, np.uint8), mut_to=_np_from(e.mut_to, M, np.uint8), mut_t=_np_from(e.mut_t, M, np.float64),
+        miss_off=_np_from(e.miss_off, N + 1, np.int32), miss_start=_np_from(e.miss_start, I, np.int32), miss_end=_np_from(e.miss_end, I, np.int32),
+        fs_off=_np_from(e.fs_off, N + 1, np.int32), fs_site=_np_from(e.fs_site, F, np.int32), fs_from=_np_from(e.fs_from, F, np.uint8))
+
+
+def partition_emat(emat: HostEmat, sites: HostSites, num_parts: int, seed: int = 1):
+    """Cut `emat` into <= num_parts independent parts (the reference's Run::repartition).  Returns
+    (list of HostEmat parts, list of orig_tree_index arrays, cut_points); the last part holds the tree's root."""
+    L = lib()
+    es, ss = emat.as_struct(), sites.as_struct()
+    cuts = np.zeros(max(num_parts, 1), np.int32)
+    ncut = C.c_int32(0)
+    st = L.dphy_partition_generate_stencil(C.byref(es), num_parts, seed, _p(cuts, i32p), C.byref(ncut))
+    if st != DPHY_OK:
+        raise DphyError(st, "dphy_partition_generate_stencil")
+    h = C.c_void_p()
+    st = L.dphy_partition_split(C.byref(es), C.byref(ss), ncut.value, _p(cuts, i32p), C.byref(h))
+    if st != DPHY_OK:
+        raise DphyError(st, "dphy_partition_split")
+    try:
+        parts, origs = [], []
+        for i in range(L.dphy_partition_num_parts(h)):
+            pe = L.dphy_partition_part(h, i).contents
+            parts.append(_emat_from_struct(pe))
+            origs.append(_np_from(L.dphy_partition_orig_index(h, i), pe.num_nodes, np.int32))
+        return parts, origs, cuts[:ncut.value].copy()
+    finally:
+        L.dphy_partition_free(h)
 
 
 def synth_params(config: int = 0, **overrides) -> SynthParams:

@@ -255,7 +255,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   if (!ctx || !out || num_trees < 0 || (num_trees > 0 && (!trees || !sites)) || num_sites_tables <= 0) return DPHY_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   cudaSetDevice(ctx->device);
-  int64_t N = 0, M = 0, I = 0, F = 0, tiles = 0, Mnr = 0;
+  int64_t N = 0, M = 0, I = 0, F = 0, tiles = 0, ctiles = 0, Mnr = 0;
   for (int k = 0; k < num_trees; ++k) {
     const auto& e = trees[k];
     if (e.num_nodes <= 0) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "empty tree");
@@ -265,6 +265,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     N += e.num_nodes; M += e.mut_off[e.num_nodes]; I += e.miss_off[e.num_nodes]; F += e.fs_off[e.num_nodes];
     Mnr += e.mut_off[e.num_nodes] - (e.mut_off[e.root + 1] - e.mut_off[e.root]);
     tiles += (e.num_nodes + kTile - 1) / kTile;
+    ctiles += (e.num_nodes + kLgTile - 1) / kLgTile;
   }
   if (N > std::numeric_limits<int32_t>::max() / 2 || M > std::numeric_limits<int32_t>::max() / 2)
     return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "forest too large for 32-bit positions");
@@ -279,14 +280,15 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   const int b_trees = slab.reserve(sizeof(TreeDev) * num_trees);
   const int b_sites = slab.reserve(sizeof(SitesDev) * num_sites_tables);
   const int b_tile_tree = slab.reserve(sizeof(int32_t) * tiles);
+  const int b_ctile_tree = slab.reserve(sizeof(int32_t) * ctiles);
   const int b_node_id = slab.reserve(sizeof(int32_t) * N), b_parent = slab.reserve(sizeof(int32_t) * N);
   const int b_depth = slab.reserve(sizeof(int32_t) * N), b_size = slab.reserve(sizeof(int32_t) * N);
   const int b_post = slab.reserve(sizeof(int32_t) * N), b_pos = slab.reserve(sizeof(int32_t) * N);
   const int b_t = slab.reserve(sizeof(double) * N);
-  const int b_moff = slab.reserve(sizeof(int32_t) * (N + 1)), b_msite = slab.reserve(sizeof(int32_t) * M);
-  const int b_mft = slab.reserve(M), b_mt = slab.reserve(sizeof(double) * M);
-  const int b_ioff = slab.reserve(sizeof(int32_t) * (N + 1)), b_is = slab.reserve(sizeof(int32_t) * I), b_ie = slab.reserve(sizeof(int32_t) * I);
-  const int b_foff = slab.reserve(sizeof(int32_t) * (N + 1)), b_fsite = slab.reserve(sizeof(int32_t) * F), b_ffrom = slab.reserve(F);
+  const int b_moff = slab.reserve(sizeof(int32_t) * (N + 1)), b_msite = slab.reserve(sizeof(int32_t) * M + 64);
+  const int b_mft = slab.reserve(M + 64), b_mt = slab.reserve(sizeof(double) * M + 64);
+  const int b_ioff = slab.reserve(sizeof(int32_t) * (N + 1)), b_is = slab.reserve(sizeof(int2) * I + 64);
+  const int b_foff = slab.reserve(sizeof(int32_t) * (N + 1)), b_fsite = slab.reserve(sizeof(int32_t) * F + 64), b_ffrom = slab.reserve(F + 64);
   const size_t upload_bytes = slab.total;
   // outputs + workspaces (device only)
   const int b_lambda = slab.reserve(sizeof(double) * N), b_nsmn = slab.reserve(sizeof(int32_t) * N);
@@ -306,13 +308,14 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   auto* h_trees = slab.at<TreeDev>(hb, b_trees);
   auto* h_sites = slab.at<SitesDev>(hb, b_sites);
   auto* h_tile_tree = slab.at<int32_t>(hb, b_tile_tree);
+  auto* h_ctile_tree = slab.at<int32_t>(hb, b_ctile_tree);
   auto* h_node_id = slab.at<int32_t>(hb, b_node_id); auto* h_parent = slab.at<int32_t>(hb, b_parent);
   auto* h_depth = slab.at<int32_t>(hb, b_depth); auto* h_size = slab.at<int32_t>(hb, b_size);
   auto* h_post = slab.at<int32_t>(hb, b_post); auto* h_pos = slab.at<int32_t>(hb, b_pos);
   auto* h_t = slab.at<double>(hb, b_t);
   auto* h_moff = slab.at<int32_t>(hb, b_moff); auto* h_msite = slab.at<int32_t>(hb, b_msite);
   auto* h_mft = slab.at<uint8_t>(hb, b_mft); auto* h_mt = slab.at<double>(hb, b_mt);
-  auto* h_ioff = slab.at<int32_t>(hb, b_ioff); auto* h_is = slab.at<int32_t>(hb, b_is); auto* h_ie = slab.at<int32_t>(hb, b_ie);
+  auto* h_ioff = slab.at<int32_t>(hb, b_ioff); auto* h_is = slab.at<int2>(hb, b_is);
   auto* h_foff = slab.at<int32_t>(hb, b_foff); auto* h_fsite = slab.at<int32_t>(hb, b_fsite); auto* h_ffrom = slab.at<uint8_t>(hb, b_ffrom);
 
   for (int i = 0; i < num_sites_tables; ++i) {
@@ -322,7 +325,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   }
 
   std::vector<int32_t> stack;
-  int32_t base = 0, mpos = 0, ipos = 0, fpos = 0, tile_pos = 0;
+  int32_t base = 0, mpos = 0, ipos = 0, fpos = 0, tile_pos = 0, ctile_pos = 0;
   fo->trees.resize(num_trees);
   for (int k = 0; k < num_trees; ++k) {
     const auto& e = trees[k];
@@ -368,7 +371,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
         if (s0 < 0 || s1 > L || s0 >= s1) {   // core/mutations.h:187-191 throws std::out_of_range
           delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "Missation out of range");
         }
-        h_is[ipos] = s0; h_ie[ipos] = s1; ++ipos;
+        h_is[ipos] = make_int2(s0, s1); ++ipos;
       }
       h_foff[base + p] = fpos;
       for (int i = e.fs_off[v]; i < e.fs_off[v + 1]; ++i) {
@@ -391,6 +394,8 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     T.node_base = base; T.num_nodes = n; T.sites_id = si; T.first_tile = tile_pos;
     T.num_tiles = (n + kTile - 1) / kTile; T.includes_run_root = e.includes_run_root; T.root_id = e.root; T.pad = 0;
     for (int j = 0; j < T.num_tiles; ++j) h_tile_tree[tile_pos++] = k;
+    T.first_ctile = ctile_pos; T.num_ctiles = (n + kLgTile - 1) / kLgTile;
+    for (int j = 0; j < T.num_ctiles; ++j) h_ctile_tree[ctile_pos++] = k;
     h_trees[k] = T;
     base += n;
   }
@@ -408,14 +413,15 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   ForestDev& h = fo->h;
   h.num_trees = num_trees; h.num_nodes = (int32_t)N; h.num_tiles = (int32_t)tiles; h.num_sites_tables = num_sites_tables;
   h.trees = slab.at<TreeDev>(dbase, b_trees); h.sites = slab.at<SitesDev>(dbase, b_sites);
-  h.tile_tree = slab.at<int32_t>(dbase, b_tile_tree);
+  h.tile_tree = slab.at<int32_t>(dbase, b_tile_tree); h.ctile_tree = slab.at<int32_t>(dbase, b_ctile_tree);
+  h.num_ctiles = (int32_t)ctiles; h.pad0 = 0;
   h.node_id = slab.at<int32_t>(dbase, b_node_id); h.parent_pos = slab.at<int32_t>(dbase, b_parent);
   h.depth = slab.at<int32_t>(dbase, b_depth); h.subtree_size = slab.at<int32_t>(dbase, b_size);
   h.post_node = slab.at<int32_t>(dbase, b_post); h.pos_of_node = slab.at<int32_t>(dbase, b_pos);
   h.t = slab.at<double>(dbase, b_t);
   h.mut_off = slab.at<int32_t>(dbase, b_moff); h.mut_site = slab.at<int32_t>(dbase, b_msite);
   h.mut_code = slab.at<uint8_t>(dbase, b_mft); h.mut_t = slab.at<double>(dbase, b_mt);
-  h.miss_off = slab.at<int32_t>(dbase, b_ioff); h.miss_start = slab.at<int32_t>(dbase, b_is); h.miss_end = slab.at<int32_t>(dbase, b_ie);
+  h.miss_off = slab.at<int32_t>(dbase, b_ioff); h.miss_se = slab.at<int2>(dbase, b_is);
   h.fs_off = slab.at<int32_t>(dbase, b_foff); h.fs_site = slab.at<int32_t>(dbase, b_fsite); h.fs_code = slab.at<uint8_t>(dbase, b_ffrom);
   fo->d_lambda = slab.at<double>(dbase, b_lambda); fo->d_nsmn = slab.at<int32_t>(dbase, b_nsmn);
   fo->d_tree_out = slab.at<double>(dbase, b_tout); fo->d_tree_iout = slab.at<int32_t>(dbase, b_tiout);

@@ -12,7 +12,10 @@
 namespace dphy {
 
 constexpr int kMaxPartitions = 4;
-constexpr int kTile = 256;          // nodes per CTA tile in the tree-prefix kernels (1 node / thread)
+constexpr int kTile = 256;          // nodes per CTA tile in the SPR / tally kernels (1 node / thread)
+constexpr int kLgThreads = 256;     // log-G kernel: threads per CTA
+constexpr int kLgNPT = 2;           // log-G kernel: nodes per thread
+constexpr int kLgTile = kLgThreads * kLgNPT;   // log-G kernel: nodes per CTA tile
 
 // ---- device arena: the device analogue of the reference's thread-local bump arena (core/scratch_space.h:49-267).
 // One slab per ctx, bump-allocated, reset when a "scope" closes.  All temporaries of a launch sequence come from
@@ -61,6 +64,8 @@ struct TreeDev {
   int32_t num_tiles;
   int32_t includes_run_root;
   int32_t root_id;         // host node index of the root
+  int32_t first_ctile;     // log-G (coarse) tiles of kLgTile nodes
+  int32_t num_ctiles;
   int32_t pad;
 };
 
@@ -71,9 +76,12 @@ struct ForestDev {
   int32_t num_nodes;       // total over trees
   int32_t num_tiles;
   int32_t num_sites_tables;
+  int32_t num_ctiles;
+  int32_t pad0;
   const TreeDev* trees;
   const SitesDev* sites;
   const int32_t* tile_tree;     // [num_tiles]
+  const int32_t* ctile_tree;    // [num_ctiles]
   // per device position
   const int32_t* node_id;       // host node index (within its tree)
   const int32_t* parent_pos;    // device position of the parent (-1 for a root)
@@ -86,8 +94,7 @@ struct ForestDev {
   const uint8_t* mut_code;      // partition << 4 | from << 2 | to
   double* mut_t;
   const int32_t* miss_off;      // [num_nodes+1]
-  const int32_t* miss_start;
-  const int32_t* miss_end;
+  const int2* miss_se;          // (start, end) of each missation interval
   const int32_t* fs_off;        // [num_nodes+1]
   const int32_t* fs_site;
   const uint8_t* fs_code;       // partition << 4 | ref << 2 | from

@@ -24,6 +24,7 @@
 #include "device_utils.cuh"
 
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace dphy {
 
@@ -37,206 +38,325 @@ struct LogGParams {
   int32_t* tile_ipart;   // [num_tiles * 17] (num_muts, num_muts_ab[16])
   double* tree_out;      // [num_trees * 4]: log_root_prior, log_G_below_root, T, lambda_root
   int32_t* tree_iout;    // [num_trees * 20]: num_muts, 0, num_muts_ab[16], 0, 0
+  int32_t debug_mask;    // profiling only (DPHY_DEBUG_MASK): 1 skip mutations, 2 intervals, 4 from-states, 8 closers, 16 foreign closers
 };
 
 // Capacity (events per chunk) of the flat event buffers in shared memory.
 constexpr int kEvCap = 1536;
-constexpr int kClCap = 1024;
 
 // Sequential re-derivation of delta-lambda / missing-site count of ONE branch (used for the few "foreign closers":
 // nodes that opened in an earlier tile and close inside this one).  phylo_tree_calc.h:121-155.
-__device__ void branch_delta_seq(const ForestDev& f, const SitesDev& S, const double* __restrict__ sq,
+__device__ void branch_delta_seq(const ForestDev& f, const SitesDev& S, const double* __restrict__ s_dq,
                                  const double* __restrict__ smu, int p, double& delta, int& nmiss) {
   const bool uni = S.nu_uniform != 0;
   double dm = 0.0;
   for (int i = f.mut_off[p]; i < f.mut_off[p + 1]; ++i) {
     const int code = __ldg(f.mut_code + i);
-    const int pt = code >> 4, from = (code >> 2) & 3, to = code & 3;
-    const double mn = uni ? smu[pt] : __ldg(S.munu + __ldg(f.mut_site + i));
-    dm += mn * ((-sq[pt * 16 + to * 5]) - (-sq[pt * 16 + from * 5]));
+    const double mn = uni ? smu[code >> 4] : __ldg(S.munu + __ldg(f.mut_site + i));
+    dm += mn * s_dq[code];
   }
   double dmi = 0.0;
   int nm = 0;
   for (int i = f.miss_off[p]; i < f.miss_off[p + 1]; ++i) {
-    const int s = __ldg(f.miss_start + i), e = __ldg(f.miss_end + i);
-    dmi -= __ldg(S.cumQ + e) - __ldg(S.cumQ + s);
-    nm += e - s;
+    const int2 se = __ldg(f.miss_se + i);
+    dmi -= __ldg(S.cumQ + se.y) - __ldg(S.cumQ + se.x);
+    nm += se.y - se.x;
   }
   for (int i = f.fs_off[p]; i < f.fs_off[p + 1]; ++i) {
     const int code = __ldg(f.fs_code + i);
-    const int pt = code >> 4, rf = (code >> 2) & 3, from = code & 3;
-    const double mn = uni ? smu[pt] : __ldg(S.munu + __ldg(f.fs_site + i));
-    dmi -= mn * ((-sq[pt * 16 + from * 5]) - (-sq[pt * 16 + rf * 5]));
+    const double mn = uni ? smu[code >> 4] : __ldg(S.munu + __ldg(f.fs_site + i));
+    dmi -= mn * s_dq[code];
   }
   delta = dm + dmi;
   nmiss = nm;
 }
 
 // Flat-over-events + segmented-sum-per-node helper.  All threads of the CTA call it with the same [r0, r1).
-//   ev(i, slot)    : thread-parallel over events i of the tile, writes its contribution(s) to smem slot `slot`
-//   acc(slot)      : the owning node's thread folds the slots of its CSR slice in list order (deterministic)
-template <typename EventFn, typename AccFn>
+//   ev(i)          : thread-parallel over groups of kVec consecutive events starting at the kVec-aligned global index
+//                    i (vector loads); writes the contributions of events i..i+kVec-1 to smem slots (i - c0)..
+//                    Slots of events outside [r0, r1) hold garbage that is never read.
+//   acc(k, slot)   : the thread owning node (tid + k*kLgThreads) folds the slots of that node's CSR slice in list
+//                    order (deterministic)
+template <int kVec, typename EventFn, typename AccFn>
 __device__ __forceinline__ void flat_segmented(int r0, int r1, const int* __restrict__ s_off, int n_act, EventFn ev, AccFn acc) {
   const int tid = threadIdx.x;
-  for (int c0 = r0; c0 < r1; c0 += kEvCap) {
+  for (int c0 = r0 & ~(kVec - 1); c0 < r1; c0 += kEvCap) {
     const int c1 = min(c0 + kEvCap, r1);
-    for (int i = c0 + tid; i < c1; i += kTile) ev(i, i - c0);
+    for (int i = c0 + kVec * tid; i < c1; i += kVec * kLgThreads) ev(i, i - c0);
     __syncthreads();
-    if (tid < n_act) {
-      const int lo = max(s_off[tid], c0), hi = min(s_off[tid + 1], c1);
-      for (int i = lo; i < hi; ++i) acc(i - c0);
+#pragma unroll
+    for (int k = 0; k < kLgNPT; ++k) {
+      const int q = tid + k * kLgThreads;
+      if (q < n_act) {
+        const int lo = max(s_off[q], c0), hi = min(s_off[q + 1], c1);
+        for (int i = lo; i < hi; ++i) acc(k, i - c0);
+      }
     }
     __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(kTile) emat_log_G_kernel(const LogGParams P) {
-  __shared__ double s_q[kMaxPartitions * 16];
+// Tile kernel: kLgTile consecutive device positions of one tree per CTA, kLgNPT nodes per thread (node q = tid +
+// k*kLgThreads, so every per-node global access is coalesced).
+__global__ void __launch_bounds__(kLgThreads) emat_log_G_kernel(const LogGParams P) {
+  __shared__ double s_dq[kMaxPartitions * 16];    // [part<<4 | x<<2 | y] = q_a(y) - q_a(x)
+  __shared__ double s_lq[kMaxPartitions * 16];    // [part<<4 | from<<2 | to] = log(mu nu_const q_from,to)   (uniform nu)
+  __shared__ double s_qft[kMaxPartitions * 16];   // q_ab
+  __shared__ double s_md[kMaxPartitions * 16];    // mu nu_const * s_dq (uniform nu)
   __shared__ double s_mu[kMaxPartitions];
-  __shared__ double s_bufA[kEvCap];
-  __shared__ double s_bufB[kEvCap];
-  __shared__ int s_off_m[kTile + 1];
-  __shared__ int s_off_i[kTile + 1];
-  __shared__ int s_off_f[kTile + 1];
-  __shared__ double s_delta[kTile];
-  __shared__ int s_nmiss[kTile];
-  __shared__ double s_wsd[kTile / 32];
-  __shared__ int s_wsi[kTile / 32];
+  __shared__ __align__(16) double s_bufA[kEvCap];
+  __shared__ __align__(16) double s_bufB[kEvCap];
+  __shared__ int s_off_m[kLgTile + 1];
+  __shared__ int s_off_i[kLgTile + 1];
+  __shared__ int s_off_f[kLgTile + 1];
+  __shared__ double s_delta[kLgTile];             // delta per node, later diff / inclusive scan per node
+  __shared__ int s_nmiss[kLgTile];
+  __shared__ double s_wsd[kLgThreads / 32 * 3];
+  __shared__ int s_wsi[kLgThreads / 32];
   __shared__ int s_ab[16];
 
   const ForestDev& f = P.f;
   const int tid = threadIdx.x;
 
-  if (tid < 16) s_ab[tid] = 0;
   const int tile = blockIdx.x;
-  const int tree = f.tile_tree[tile];
+  const int tree = f.ctile_tree[tile];
   const TreeDev T = f.trees[tree];
   const SitesDev& S = f.sites[T.sites_id];
-  if (tid < S.P * 16) s_q[tid] = S.q[tid];
-  if (tid < S.P) s_mu[tid] = S.mu[tid] * S.nu_const;
   const bool uni = S.nu_uniform != 0;
+  if (tid < 16) s_ab[tid] = 0;
+  if (tid < S.P) s_mu[tid] = S.mu[tid] * S.nu_const;
+  if (tid < S.P * 16) {
+    const int pt = tid >> 4, x = (tid >> 2) & 3, y = tid & 3;
+    const double qxy = S.q[tid];
+    s_qft[tid] = qxy;
+    const double dq = (-S.q[pt * 16 + y * 5]) - (-S.q[pt * 16 + x * 5]);
+    s_dq[tid] = dq;
+    s_md[tid] = S.mu[pt] * S.nu_const * dq;
+    s_lq[tid] = (x != y) ? log(S.mu[pt] * S.nu_const * qxy) : 0.0;
+  } else if (tid < kMaxPartitions * 16) {
+    s_dq[tid] = 0.0; s_md[tid] = 0.0; s_lq[tid] = 0.0; s_qft[tid] = 1.0;
+  }
 
-  const int tile_in_tree = tile - T.first_tile;
-  const int tile_start = T.node_base + tile_in_tree * kTile;              // global device position
-  const int tile_end = min(tile_start + kTile, T.node_base + T.num_nodes);
+  const int tile_in_tree = tile - T.first_ctile;
+  const int tile_start = T.node_base + tile_in_tree * kLgTile;              // global device position
+  const int tile_end = min(tile_start + kLgTile, T.node_base + T.num_nodes);
   const int n_act = tile_end - tile_start;
-  const int p = tile_start + tid;
-  const bool active = p < tile_end;
-  const bool has_root = tile_in_tree == 0;                                 // position 0 of a tree is its root
+  const bool has_root = tile_in_tree == 0;                                   // position 0 of a tree is its root
 
   // ---- (0) node records + CSR offsets of the tile ---------------------------------------------------------------------
-  double tP = 0.0, tN = 0.0;
-  int par = -1, dep = 0;
-  if (active) {
-    par = f.parent_pos[p];
-    dep = f.depth[p];
-    tN = f.t[p];
-    if (par >= 0) tP = f.t[par];
-    s_off_m[tid] = f.mut_off[p]; s_off_i[tid] = f.miss_off[p]; s_off_f[tid] = f.fs_off[p];
-    if (tid == n_act - 1) { s_off_m[n_act] = f.mut_off[p + 1]; s_off_i[n_act] = f.miss_off[p + 1]; s_off_f[n_act] = f.fs_off[p + 1]; }
+  double tP[kLgNPT], tN[kLgNPT];
+  int par[kLgNPT], dep[kLgNPT];
+#pragma unroll
+  for (int k = 0; k < kLgNPT; ++k) {
+    const int q = tid + k * kLgThreads, p = tile_start + q;
+    par[k] = -1; dep[k] = 0; tP[k] = 0.0; tN[k] = 0.0;
+    if (q < n_act) {
+      par[k] = f.parent_pos[p];
+      dep[k] = f.depth[p];
+      tN[k] = f.t[p];
+      s_off_m[q] = f.mut_off[p]; s_off_i[q] = f.miss_off[p]; s_off_f[q] = f.fs_off[p];
+      if (q == n_act - 1) { s_off_m[n_act] = f.mut_off[p + 1]; s_off_i[n_act] = f.miss_off[p + 1]; s_off_f[n_act] = f.fs_off[p + 1]; }
+    }
   }
+#pragma unroll
+  for (int k = 0; k < kLgNPT; ++k) if (par[k] >= 0) tP[k] = f.t[par[k]];
   __syncthreads();
 
   // ---- (1) branch terms: flat over the tile's events, segmented sum per node --------------------------------------------
-  double dm = 0.0, esum = 0.0, dmi = 0.0;
-  int nmiss = 0;
+  double dm[kLgNPT], esum[kLgNPT], dmi[kLgNPT];
+  int nmiss[kLgNPT];
+#pragma unroll
+  for (int k = 0; k < kLgNPT; ++k) { dm[k] = 0.0; esum[k] = 0.0; dmi[k] = 0.0; nmiss[k] = 0; }
   const int root_m1 = has_root ? s_off_m[1] : s_off_m[0];   // the root's list ("mutations" above the root) ends here
   // mutations: dm_i = mu nu (q_to - q_from);  e_i = dm_i * t_i + log(mu nu q_from,to)   [g_node = sum e_i - t_P * dm]
-  flat_segmented(s_off_m[0], s_off_m[n_act], s_off_m, n_act,
-    [&](int i, int slot) {
-      const int code = __ldg(f.mut_code + i);
-      const int pt = code >> 4, from = (code >> 2) & 3, to = code & 3;
-      const double mn = uni ? s_mu[pt] : __ldg(S.munu + __ldg(f.mut_site + i));
-      const double d = mn * ((-s_q[pt * 16 + to * 5]) - (-s_q[pt * 16 + from * 5]));
-      double e = 0.0;
-      if (i >= root_m1) {
-        e = d * __ldg(f.mut_t + i) + log(mn * s_q[pt * 16 + from * 4 + to]);
-        atomicAdd(&s_ab[code & 15], 1);
-      }
-      s_bufA[slot] = d; s_bufB[slot] = e;
-    },
-    [&](int slot) { dm += s_bufA[slot]; esum += s_bufB[slot]; });
+  {
+    const int m_lo = max(root_m1, s_off_m[0]), m_hi = s_off_m[n_act];
+    if (!(P.debug_mask & 1)) flat_segmented<4>(s_off_m[0], s_off_m[n_act], s_off_m, n_act,
+      [&](int i, int slot) {
+        const uchar4 c4 = __ldg(reinterpret_cast<const uchar4*>(f.mut_code + i));
+        const double2 ta = __ldg(reinterpret_cast<const double2*>(f.mut_t + i));
+        const double2 tb = __ldg(reinterpret_cast<const double2*>(f.mut_t + i + 2));
+        const int code[4] = {c4.x & 63, c4.y & 63, c4.z & 63, c4.w & 63};
+        const double tt[4] = {ta.x, ta.y, tb.x, tb.y};
+        double d[4], e[4];
+        if (uni) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { d[u] = s_md[code[u]]; e[u] = d[u] * tt[u] + s_lq[code[u]]; }
+        } else {
+          const int4 l4 = __ldg(reinterpret_cast<const int4*>(f.mut_site + i));
+          const int ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = i + u >= s_off_m[0] && i + u < m_hi;
+            const double mn = ok ? __ldg(S.munu + ll[u]) : 1.0;
+            d[u] = mn * s_dq[code[u]];
+            e[u] = d[u] * tt[u] + ((code[u] >> 2 & 3) != (code[u] & 3) ? log(mn * s_qft[code[u]]) : 0.0);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i + u >= m_lo && i + u < m_hi) atomicAdd(&s_ab[code[u] & 15], 1); else e[u] = 0.0;
+        }
+        *reinterpret_cast<double2*>(s_bufA + slot) = make_double2(d[0], d[1]);
+        *reinterpret_cast<double2*>(s_bufA + slot + 2) = make_double2(d[2], d[3]);
+        *reinterpret_cast<double2*>(s_bufB + slot) = make_double2(e[0], e[1]);
+        *reinterpret_cast<double2*>(s_bufB + slot + 2) = make_double2(e[2], e[3]);
+      },
+      [&](int k, int slot) { dm[k] += s_bufA[slot]; esum[k] += s_bufB[slot]; });
+  }
   // missation intervals: -(cumQ[end] - cumQ[start]); count of sites going missing
-  flat_segmented(s_off_i[0], s_off_i[n_act], s_off_i, n_act,
-    [&](int i, int slot) {
-      const int s = __ldg(f.miss_start + i), e = __ldg(f.miss_end + i);
-      s_bufA[slot] = __ldg(S.cumQ + e) - __ldg(S.cumQ + s);
-      reinterpret_cast<int*>(s_bufB)[slot] = e - s;
-    },
-    [&](int slot) { dmi -= s_bufA[slot]; nmiss += reinterpret_cast<int*>(s_bufB)[slot]; });
+  {
+    const int i_lo = s_off_i[0], i_hi = s_off_i[n_act];
+    if (!(P.debug_mask & 2)) flat_segmented<2>(i_lo, i_hi, s_off_i, n_act,
+      [&](int i, int slot) {
+        const int4 se = __ldg(reinterpret_cast<const int4*>(f.miss_se + i));
+        const bool ok0 = i >= i_lo, ok1 = i + 1 < i_hi;
+        const double a0 = ok0 ? __ldg(S.cumQ + se.y) - __ldg(S.cumQ + se.x) : 0.0;
+        const double a1 = ok1 ? __ldg(S.cumQ + se.w) - __ldg(S.cumQ + se.z) : 0.0;
+        *reinterpret_cast<double2*>(s_bufA + slot) = make_double2(a0, a1);
+        *reinterpret_cast<int2*>(reinterpret_cast<int*>(s_bufB) + slot) = make_int2(se.y - se.x, se.w - se.z);
+      },
+      [&](int k, int slot) { dmi[k] -= s_bufA[slot]; nmiss[k] += reinterpret_cast<int*>(s_bufB)[slot]; });
+  }
   // from-state overrides of missing sites
-  flat_segmented(s_off_f[0], s_off_f[n_act], s_off_f, n_act,
-    [&](int i, int slot) {
-      const int code = __ldg(f.fs_code + i);
-      const int pt = code >> 4, rf = (code >> 2) & 3, from = code & 3;
-      const double mn = uni ? s_mu[pt] : __ldg(S.munu + __ldg(f.fs_site + i));
-      s_bufA[slot] = mn * ((-s_q[pt * 16 + from * 5]) - (-s_q[pt * 16 + rf * 5]));
-    },
-    [&](int slot) { dmi -= s_bufA[slot]; });
-  const double delta = dm + dmi;
-  const double g = (active && par >= 0) ? esum - tP * dm : 0.0;
-  s_delta[tid] = active ? delta : 0.0;
-  s_nmiss[tid] = active ? nmiss : 0;
+  {
+    const int f_lo = s_off_f[0], f_hi = s_off_f[n_act];
+    if (!(P.debug_mask & 4)) flat_segmented<4>(f_lo, f_hi, s_off_f, n_act,
+      [&](int i, int slot) {
+        const uchar4 c4 = __ldg(reinterpret_cast<const uchar4*>(f.fs_code + i));
+        const int code[4] = {c4.x & 63, c4.y & 63, c4.z & 63, c4.w & 63};
+        double d[4];
+        if (uni) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) d[u] = s_md[code[u]];
+        } else {
+          const int4 l4 = __ldg(reinterpret_cast<const int4*>(f.fs_site + i));
+          const int ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = i + u >= f_lo && i + u < f_hi;
+            d[u] = (ok ? __ldg(S.munu + ll[u]) : 1.0) * s_dq[code[u]];
+          }
+        }
+        *reinterpret_cast<double2*>(s_bufA + slot) = make_double2(d[0], d[1]);
+        *reinterpret_cast<double2*>(s_bufA + slot + 2) = make_double2(d[2], d[3]);
+      },
+      [&](int k, int slot) { dmi[k] -= s_bufA[slot]; });
+  }
+  double g[kLgNPT];
+#pragma unroll
+  for (int k = 0; k < kLgNPT; ++k) {
+    const int q = tid + k * kLgThreads;
+    g[k] = par[k] >= 0 ? esum[k] - tP[k] * dm[k] : 0.0;
+    if (q < kLgTile) { s_delta[q] = q < n_act ? dm[k] + dmi[k] : 0.0; s_nmiss[q] = q < n_act ? nmiss[k] : 0; }
+  }
   __syncthreads();
 
   // ---- (2) diff = own delta - deltas of the nodes whose subtree closes right before this position ---------------------------
   // The tile's closers are one contiguous slice of the tree's post-order list; their deltas are gathered in parallel
   // (in-tile from smem, foreign ones re-derived), then each position folds its own sub-slice in order.
-  double diff = active ? delta : 0.0;
-  int idiff = active ? nmiss : 0;
+  double diff[kLgNPT];
+  int idiff[kLgNPT];
   {
     const int q_first = tile_start - T.node_base, q_last = tile_end - 1 - T.node_base;
     const int cl0 = q_first == 0 ? 0 : (q_first - 1) - f.depth[tile_start - 1];
-    const int cl1 = q_last - f.depth[tile_end - 1];
-    int my0 = 0, my1 = 0;
-    if (active) {
-      const int q = p - T.node_base;
-      if (q > 0) { my0 = (q - 1) - f.depth[p - 1]; my1 = q - dep; }
+    const int cl1 = (P.debug_mask & 8) ? cl0 : q_last - f.depth[tile_end - 1];
+    int my0[kLgNPT], my1[kLgNPT];
+#pragma unroll
+    for (int k = 0; k < kLgNPT; ++k) {
+      const int q = tid + k * kLgThreads, p = tile_start + q;
+      my0[k] = 0; my1[k] = 0;
+      diff[k] = q < n_act ? s_delta[q] : 0.0;
+      idiff[k] = q < n_act ? s_nmiss[q] : 0;
+      if (q < n_act) {
+        const int tq = p - T.node_base;
+        if (tq > 0) { my0[k] = (tq - 1) - f.depth[p - 1]; my1[k] = tq - dep[k]; }
+      }
     }
     int* s_cn = reinterpret_cast<int*>(s_bufB);
-    for (int c0 = cl0; c0 < cl1; c0 += kClCap) {
-      const int c1 = min(c0 + kClCap, cl1);
-      for (int j = c0 + tid; j < c1; j += kTile) {
+    for (int c0 = cl0; c0 < cl1; c0 += kEvCap) {
+      const int c1 = min(c0 + kEvCap, cl1);
+      for (int j = c0 + tid; j < c1; j += kLgThreads) {
         const int a = f.post_node[T.node_base + j];
         double da; int na;
         if (a >= tile_start) { da = s_delta[a - tile_start]; na = s_nmiss[a - tile_start]; }
-        else branch_delta_seq(f, S, s_q, s_mu, a, da, na);
+        else if (P.debug_mask & 16) { da = 0.0; na = 0; }
+        else branch_delta_seq(f, S, s_dq, s_mu, a, da, na);
         s_bufA[j - c0] = da; s_cn[j - c0] = na;
       }
       __syncthreads();
-      const int lo = max(my0, c0), hi = min(my1, c1);
-      for (int j = lo; j < hi; ++j) { diff -= s_bufA[j - c0]; idiff -= s_cn[j - c0]; }
+#pragma unroll
+      for (int k = 0; k < kLgNPT; ++k) {
+        const int lo = max(my0[k], c0), hi = min(my1[k], c1);
+        for (int j = lo; j < hi; ++j) { diff[k] -= s_bufA[j - c0]; idiff[k] -= s_cn[j - c0]; }
+      }
       __syncthreads();
     }
   }
 
-  // ---- (3) block scan; tile-local lambda_i / nsmn; per-tile partial sums ------------------------------------------------
+  // ---- (3) inclusive scan of diff over the tile (position order): smem transpose -> blocked serial + block scan ------------
+#pragma unroll
+  for (int k = 0; k < kLgNPT; ++k) {
+    const int q = tid + k * kLgThreads;
+    s_delta[q] = diff[k]; s_nmiss[q] = idiff[k];
+  }
+  __syncthreads();
   double tot; int itot;
-  const double incl = block_scan_incl<double, kTile>(diff, s_wsd, &tot);
-  const int iincl = block_scan_incl<int, kTile>(idiff, s_wsi, &itot);
+  {
+    double loc[kLgNPT]; int iloc[kLgNPT];
+    double run = 0.0; int irun = 0;
+#pragma unroll
+    for (int k = 0; k < kLgNPT; ++k) {
+      run += s_delta[tid * kLgNPT + k]; irun += s_nmiss[tid * kLgNPT + k];
+      loc[k] = run; iloc[k] = irun;
+    }
+    const double incl = block_scan_incl<double, kLgThreads>(run, s_wsd, &tot);
+    const int iincl = block_scan_incl<int, kLgThreads>(irun, s_wsi, &itot);
+    const double base = incl - run; const int ibase = iincl - irun;
+#pragma unroll
+    for (int k = 0; k < kLgNPT; ++k) { s_delta[tid * kLgNPT + k] = base + loc[k]; s_nmiss[tid * kLgNPT + k] = ibase + iloc[k]; }
+  }
+  __syncthreads();
+
+  // ---- (4) tile-local lambda_i / nsmn (device order); per-tile partial sums ----------------------------------------------------
+  const double lambda_ref = S.cumQ[S.L];
   double contrib = 0.0, tcontrib = 0.0;
   int nmut = 0;
-  if (active) {
-    const double lam_local = S.cumQ[S.L] + incl;     // + the tile's prefix, added in pass 3
-    P.lambda_out[p] = lam_local;
-    P.nsmn_out[p] = iincl;
-    if (par >= 0) {
-      const double len = tN - tP;
-      contrib = -lam_local * len + g;
-      tcontrib = len;
-      nmut = s_off_m[tid + 1] - s_off_m[tid];
+#pragma unroll
+  for (int k = 0; k < kLgNPT; ++k) {
+    const int q = tid + k * kLgThreads, p = tile_start + q;
+    if (q < n_act) {
+      const double lam_local = lambda_ref + s_delta[q];     // + the tile's prefix, added in pass 3
+      P.lambda_out[p] = lam_local;
+      P.nsmn_out[p] = s_nmiss[q];
+      if (par[k] >= 0) {
+        const double len = tN[k] - tP[k];
+        contrib += -lam_local * len + g[k];
+        tcontrib += len;
+        nmut += s_off_m[q + 1] - s_off_m[q];
+      }
     }
   }
-  const double bsum = block_sum<double, kTile>(contrib, s_wsd);
-  const double tsum = block_sum<double, kTile>(tcontrib, s_wsd);
-  const int msum = block_sum<int, kTile>(nmut, s_wsi);
-  __syncthreads();
-  if (tid == 0) {
-    P.tile_agg[tile] = tot;
-    P.tile_iagg[tile] = itot;
-    P.tile_part[tile * 2 + 0] = bsum;
-    P.tile_part[tile * 2 + 1] = tsum;
-    P.tile_ipart[tile * 17 + 0] = msum;
+  // three sums with one barrier pair
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    contrib = warp_sum(contrib); tcontrib = warp_sum(tcontrib); nmut = warp_sum(nmut);
+    __syncthreads();
+    if (lane == 0) { s_wsd[warp * 3 + 0] = contrib; s_wsd[warp * 3 + 1] = tcontrib; s_wsd[warp * 3 + 2] = (double)nmut; }
+    __syncthreads();
+    if (warp == 0) {
+      double a = lane < kLgThreads / 32 ? s_wsd[lane * 3 + 0] : 0.0;
+      double b = lane < kLgThreads / 32 ? s_wsd[lane * 3 + 1] : 0.0;
+      double c = lane < kLgThreads / 32 ? s_wsd[lane * 3 + 2] : 0.0;
+      a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+      if (lane == 0) {
+        P.tile_agg[tile] = tot;
+        P.tile_iagg[tile] = itot;
+        P.tile_part[tile * 2 + 0] = a;
+        P.tile_part[tile * 2 + 1] = b;
+        P.tile_ipart[tile * 17 + 0] = (int)c;
+      }
+    }
   }
   if (tid < 16) P.tile_ipart[tile * 17 + 1 + tid] = s_ab[tid];
 }
@@ -259,9 +379,9 @@ __global__ void __launch_bounds__(kTile) emat_log_G_tree_kernel(const LogGParams
   int ab[16];
 #pragma unroll
   for (int b = 0; b < 16; ++b) ab[b] = 0;
-  for (int j0 = 0; j0 < T.num_tiles; j0 += kTile) {
-    const int j = T.first_tile + j0 + tid;
-    const bool ok = j0 + tid < T.num_tiles;
+  for (int j0 = 0; j0 < T.num_ctiles; j0 += kTile) {
+    const int j = T.first_ctile + j0 + tid;
+    const bool ok = j0 + tid < T.num_ctiles;
     const double v = ok ? P.tile_agg[j] : 0.0;
     const int iv = ok ? P.tile_iagg[j] : 0;
     double tot; int itot;
@@ -311,7 +431,7 @@ __global__ void __launch_bounds__(kTile) emat_log_G_tree_kernel(const LogGParams
       atomicAdd(&s_cnt[pt * 4 + (code & 3)], 1);
     }
     for (int i = f.miss_off[r]; i < f.miss_off[r + 1]; ++i) {
-      const int s = f.miss_start[i], e = f.miss_end[i];
+      const int2 se = f.miss_se[i]; const int s = se.x, e = se.y;
       for (int l = s + tid; l < e; l += kTile) atomicSub(&s_cnt[S.part[l] * 4 + S.ref[l]], 1);
     }
     for (int i = f.fs_off[r] + tid; i < f.fs_off[r + 1]; i += kTile) {
@@ -337,14 +457,20 @@ __global__ void __launch_bounds__(kTile) emat_log_G_tree_kernel(const LogGParams
 }
 
 // ---- pass 3: add each tile's prefix to lambda_i / nsmn in place (streaming) ------------------------------------------------------
-__global__ void __launch_bounds__(kTile) emat_log_G_finish_kernel(const LogGParams P) {
+__global__ void __launch_bounds__(kLgThreads) emat_log_G_finish_kernel(const LogGParams P) {
   const ForestDev& f = P.f;
   const int tile = blockIdx.x;
-  const TreeDev T = f.trees[f.tile_tree[tile]];
-  const int p = T.node_base + (tile - T.first_tile) * kTile + threadIdx.x;
-  if (p < T.node_base + T.num_nodes) {
-    P.lambda_out[p] += P.tile_agg[tile];
-    P.nsmn_out[p] += P.tile_iagg[tile];
+  const TreeDev T = f.trees[f.ctile_tree[tile]];
+  const double pre = P.tile_agg[tile];
+  const int ipre = P.tile_iagg[tile];
+  const int p0 = T.node_base + (tile - T.first_ctile) * kLgTile;
+#pragma unroll
+  for (int k = 0; k < kLgNPT; ++k) {
+    const int p = p0 + threadIdx.x + k * kLgThreads;
+    if (p < T.node_base + T.num_nodes) {
+      P.lambda_out[p] += pre;
+      P.nsmn_out[p] += ipre;
+    }
   }
 }
 
@@ -383,9 +509,10 @@ int launch_log_G(dphy_ctx* ctx, dphy_forest* fo) {
   P.tile_ipart = fo->d_tile_ipart;
   P.tree_out = fo->d_tree_out;
   P.tree_iout = fo->d_tree_iout;
-  emat_log_G_kernel<<<fo->h.num_tiles, kTile, 0, ctx->stream>>>(P);
+  { const char* dm = getenv("DPHY_DEBUG_MASK"); P.debug_mask = dm ? atoi(dm) : 0; }
+  emat_log_G_kernel<<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
   emat_log_G_tree_kernel<<<fo->h.num_trees, kTile, 0, ctx->stream>>>(P);
-  emat_log_G_finish_kernel<<<fo->h.num_tiles, kTile, 0, ctx->stream>>>(P);
+  emat_log_G_finish_kernel<<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
   ctx->launches += 3;
   return check_cuda(ctx, cudaGetLastError(), "emat_log_G kernels launch");
 }

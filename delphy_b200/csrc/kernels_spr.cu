@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) spr_setup_kernel(ForestDev f, SprBatchDev
     for (int jj = 0; jj < S.xpath_len; ++jj) {
       const int a = xpath[jj];
       for (int i = f.miss_off[a]; i < f.miss_off[a + 1]; ++i) {
-        const int s = f.miss_start[i], e = f.miss_end[i];
+        const int2 se = f.miss_se[i]; const int s = se.x, e = se.y;
         for (int l = s + tid; l < e; l += 256) xtab[l] |= 4;
       }
     }

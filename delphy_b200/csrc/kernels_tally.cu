@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kTile) tally_events_kernel(ForestDev f, int tr
     if (kTime) {
       const double Tbmiss = Tb + len;
       for (int i = f.miss_off[p]; i < f.miss_off[p + 1]; ++i) {
-        const int s = f.miss_start[i], e = f.miss_end[i];
+        const int2 se = f.miss_se[i]; const int s = se.x, e = se.y;
         if (out.beta_a_part) {
 #pragma unroll
           for (int k = 0; k < kMaxPartitions * 4; ++k) {

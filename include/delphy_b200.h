@@ -221,6 +221,21 @@ int  dphy_spr_batch_pick_nexus_regions(dphy_ctx* ctx, dphy_spr_batch* batch, con
 int  dphy_spr_batch_find_region(dphy_ctx* ctx, dphy_spr_batch* batch, int32_t request, int32_t branch, double t,
                                 int32_t* out_region_idx);
 
+/* ---- tree partitioning (one or more parts per GPU) ------------------------------------------------------------- */
+/* generate_random_partition_stencil (core/tree_partitioning.h:139-194): up to num_parts-1 cut points. */
+typedef struct dphy_partition dphy_partition;
+int  dphy_partition_generate_stencil(const dphy_emat_host* tree, int32_t num_parts, uint64_t seed, int32_t* cut_points,
+                                     int32_t* num_cut_points);
+/* partition_tree + the per-part Phylo_tree construction of Run::repartition (core/tree_partitioning.h:196-239,
+ * core/run.cpp:133-176).  The last part is the one holding the tree's root. */
+int  dphy_partition_split(const dphy_emat_host* tree, const dphy_sites_host* sites, int32_t num_cut_points,
+                          const int32_t* cut_points, dphy_partition** out);
+int32_t dphy_partition_num_parts(const dphy_partition* p);
+const dphy_emat_host* dphy_partition_part(const dphy_partition* p, int32_t i);
+/* orig_tree_index of every node of part i (core/tree_partitioning.h:20-34) */
+const int32_t* dphy_partition_orig_index(const dphy_partition* p, int32_t i);
+void dphy_partition_free(dphy_partition* p);
+
 /* ---- synthetic EMATs (bench / tests input generator) -------------------------------- */
 typedef struct dphy_synth_params {
   int32_t num_tips;

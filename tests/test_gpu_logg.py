@@ -162,3 +162,27 @@ def test_error_behaviour(ctx):
         db.Forest(ctx, [bad], [ds])
     assert ei.value.status == db.ERR_OUT_OF_RANGE
     ds.close()
+
+
+def test_partition_parts_as_forest(ctx, orc):
+    """Run::repartition on the device: the parts of one tree evaluated as a forest in one launch; additive tallies
+    sum to the whole tree's (Run::check_global_and_local_totals_match, core/run.cpp:340-357)."""
+    emat, sites, _ = synth(3)
+    parts, origs, cuts = db.partition_emat(emat, sites, 8, seed=5)
+    assert len(parts) >= 4
+    ds = db.DeviceSites(ctx, sites)
+    whole = db.Forest(ctx, [emat], [ds]); pf = db.Forest(ctx, parts, [ds])
+    whole.eval_log_G(); pf.eval_log_G()
+    _, _, lg_w = whole.log_G(); _, _, lg_p = pf.log_G()
+    assert lg_p.sum() == pytest.approx(lg_w[0], rel=1e-10)
+    tw = whole.tallies()[0]; tp = pf.tallies()
+    assert sum(t["num_muts"] for t in tp) == tw["num_muts"]
+    assert np.array_equal(sum(t["num_muts_ab"] for t in tp), tw["num_muts_ab"])
+    assert sum(t["T"] for t in tp) == pytest.approx(tw["T"], rel=1e-11)
+    lam = whole.lambda_i(0)
+    for k, og in enumerate(origs):
+        np.testing.assert_allclose(pf.lambda_i(k), lam[og], rtol=1e-10)
+        np.testing.assert_array_equal(pf.num_sites_missing(k), whole.num_sites_missing(0)[og])
+    tb = sum(pf.Ttwiddle_beta_a(k) for k in range(len(parts)))
+    np.testing.assert_allclose(tb, whole.Ttwiddle_beta_a(0), rtol=1e-9)
+    whole.close(); pf.close(); ds.close()
