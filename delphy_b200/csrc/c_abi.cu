@@ -4,6 +4,8 @@
 #include "dphy_internal.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -194,8 +196,6 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
   uint8_t* hp = slab.at<uint8_t>(hb, b_part);
   for (int l = 0; l < L; ++l) hp[l] = (uint8_t)host->partition_for_site[l];
   std::memcpy(slab.at<double>(hb, b_nu), host->nu_l, sizeof(double) * L);
-  s->h_ref.assign(host->ref, host->ref + L);
-  s->h_part.assign(hp, hp + L);
   set_nu_uniform(s, host->nu_l);
   s->d_ref = slab.at<uint8_t>(dbase, b_ref); s->d_part = slab.at<uint8_t>(dbase, b_part); s->d_nu = slab.at<double>(dbase, b_nu);
   s->d_munu = slab.at<double>(dbase, b_munu); s->d_cumQ = slab.at<double>(dbase, b_cumQ);
@@ -250,37 +250,122 @@ int dphy_calc_cum_Q_l(dphy_ctx* ctx, dphy_sites* s, double* out) {
 }
 
 // ---- forest -------------------------------------------------------------------------------------------------------
+namespace {
+
+// Host -> device copy of many caller-owned (pageable) arrays: worker threads memcpy 2 MiB chunks into the pinned
+// staging slab while the main thread issues the H2D DMA of every finished chunk, so the memcpy and the PCIe transfer
+// overlap and the host never touches the data more than once.
+struct CopyJob { size_t dst_off; const void* src; size_t bytes; };
+
+int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char* d_base, size_t total) {
+  if (total == 0) return DPHY_OK;
+  constexpr size_t kChunk = (size_t)2 << 20;
+  const size_t nchunks = (total + kChunk - 1) / kChunk;
+  std::sort(jobs.begin(), jobs.end(), [](const CopyJob& a, const CopyJob& b) { return a.dst_off < b.dst_off; });
+  auto fill_chunk = [&](size_t c) {
+    const size_t lo = c * kChunk, hi = std::min(total, lo + kChunk);
+    // first job that may overlap [lo, hi)
+    size_t j = std::upper_bound(jobs.begin(), jobs.end(), lo, [](size_t v, const CopyJob& b) { return v < b.dst_off; }) - jobs.begin();
+    if (j > 0) --j;
+    for (; j < jobs.size() && jobs[j].dst_off < hi; ++j) {
+      const size_t a = std::max(lo, jobs[j].dst_off), b = std::min(hi, jobs[j].dst_off + jobs[j].bytes);
+      if (a < b) std::memcpy(pinned + a, static_cast<const char*>(jobs[j].src) + (a - jobs[j].dst_off), b - a);
+    }
+  };
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t nthreads = std::min<size_t>({nchunks, hw ? hw : 1u, (size_t)8});
+  cudaError_t ce = cudaSuccess;
+  if (nthreads <= 1) {
+    for (size_t c = 0; c < nchunks && ce == cudaSuccess; ++c) {
+      fill_chunk(c);
+      const size_t lo = c * kChunk, hi = std::min(total, lo + kChunk);
+      ce = cudaMemcpyAsync(d_base + lo, pinned + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream);
+    }
+  } else {
+    std::vector<std::atomic<int>> done(nchunks);
+    for (auto& d : done) d.store(0, std::memory_order_relaxed);
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+      for (;;) {
+        const size_t c = next.fetch_add(1, std::memory_order_relaxed);
+        if (c >= nchunks) return;
+        fill_chunk(c);
+        done[c].store(1, std::memory_order_release);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (size_t i = 1; i < nthreads; ++i) pool.emplace_back(worker);
+    for (size_t c = 0; c < nchunks; ++c) {
+      while (!done[c].load(std::memory_order_acquire)) {
+        // help out instead of spinning
+        const size_t h = next.fetch_add(1, std::memory_order_relaxed);
+        if (h < nchunks) { fill_chunk(h); done[h].store(1, std::memory_order_release); } else std::this_thread::yield();
+      }
+      if (ce == cudaSuccess) {
+        const size_t lo = c * kChunk, hi = std::min(total, lo + kChunk);
+        ce = cudaMemcpyAsync(d_base + lo, pinned + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream);
+      }
+    }
+    for (auto& th : pool) th.join();
+  }
+  return check_cuda(ctx, ce, "H2D staged upload");
+}
+
+int flatten_status_to_error(dphy_ctx* ctx, uint32_t bits) {
+  if (bits & kFlattenErrTopology) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "tree topology is not a binary tree rooted at `root`");
+  if (bits & kFlattenErrOffsets) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "CSR offsets are not monotone");
+  if (bits & kFlattenErrMutSite) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "mutation site out of range");
+  if (bits & kFlattenErrMissation) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "Missation out of range");
+  if (bits & kFlattenErrMutState) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "mutation state not in ACGT");
+  if (bits & kFlattenErrFsState) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "missation from-state not in ACGT");
+  return DPHY_OK;
+}
+
+}  // namespace
+
 int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* trees, const int32_t* sites_index,
                        int32_t num_sites_tables, dphy_sites* const* sites, dphy_forest** out) {
   if (!ctx || !out || num_trees < 0 || (num_trees > 0 && (!trees || !sites)) || num_sites_tables <= 0) return DPHY_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   cudaSetDevice(ctx->device);
   int64_t N = 0, M = 0, I = 0, F = 0, tiles = 0, ctiles = 0, Mnr = 0;
+  int max_tree_nodes = 0;
   for (int k = 0; k < num_trees; ++k) {
     const auto& e = trees[k];
     if (e.num_nodes <= 0) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "empty tree");
     if (e.root < 0 || e.root >= e.num_nodes) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "root out of range");
     const int si = sites_index ? sites_index[k] : 0;
     if (si < 0 || si >= num_sites_tables) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "sites_index out of range");
-    N += e.num_nodes; M += e.mut_off[e.num_nodes]; I += e.miss_off[e.num_nodes]; F += e.fs_off[e.num_nodes];
-    Mnr += e.mut_off[e.num_nodes] - (e.mut_off[e.root + 1] - e.mut_off[e.root]);
-    tiles += (e.num_nodes + kTile - 1) / kTile;
-    ctiles += (e.num_nodes + kLgTile - 1) / kLgTile;
+    const int n = e.num_nodes;
+    if (e.mut_off[n] < 0 || e.miss_off[n] < 0 || e.fs_off[n] < 0 || e.mut_off[e.root + 1] < e.mut_off[e.root])
+      return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "CSR offsets are not monotone");
+    N += n; M += e.mut_off[n]; I += e.miss_off[n]; F += e.fs_off[n];
+    Mnr += e.mut_off[n] - (e.mut_off[e.root + 1] - e.mut_off[e.root]);
+    tiles += (n + kTile - 1) / kTile;
+    ctiles += (n + kLgTile - 1) / kLgTile;
+    max_tree_nodes = std::max(max_tree_nodes, n);
   }
-  if (N > std::numeric_limits<int32_t>::max() / 2 || M > std::numeric_limits<int32_t>::max() / 2)
+  if (N > std::numeric_limits<int32_t>::max() / 4 || M > std::numeric_limits<int32_t>::max() / 2 ||
+      I > std::numeric_limits<int32_t>::max() / 2 || F > std::numeric_limits<int32_t>::max() / 2)
     return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "forest too large for 32-bit positions");
+  for (int i = 0; i < num_sites_tables; ++i)
+    if (!sites[i]) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "null sites table");
 
   auto* fo = new (std::nothrow) dphy_forest();
   if (!fo) return DPHY_ERR_OUT_OF_MEMORY;
   fo->total_muts = M; fo->total_ivls = I; fo->total_fs = F; fo->total_nonroot_muts = Mnr;
   fo->sites.assign(sites, sites + num_sites_tables);
   fo->sites_version.resize(num_sites_tables);
+  fo->tree_muts.resize(num_trees); fo->tree_fs.resize(num_trees); fo->tree_max_depth.assign(num_trees, 0);
+  fo->trees.resize(num_trees);
 
+  // ---- the resident forest slab --------------------------------------------------------------------------------------
   Slab slab;
   const int b_trees = slab.reserve(sizeof(TreeDev) * num_trees);
   const int b_sites = slab.reserve(sizeof(SitesDev) * num_sites_tables);
   const int b_tile_tree = slab.reserve(sizeof(int32_t) * tiles);
   const int b_ctile_tree = slab.reserve(sizeof(int32_t) * ctiles);
+  const size_t header_bytes = slab.total;
   const int b_node_id = slab.reserve(sizeof(int32_t) * N), b_parent = slab.reserve(sizeof(int32_t) * N);
   const int b_depth = slab.reserve(sizeof(int32_t) * N), b_size = slab.reserve(sizeof(int32_t) * N);
   const int b_post = slab.reserve(sizeof(int32_t) * N), b_pos = slab.reserve(sizeof(int32_t) * N);
@@ -289,126 +374,97 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   const int b_mft = slab.reserve(M + 64), b_mt = slab.reserve(sizeof(double) * M + 64);
   const int b_ioff = slab.reserve(sizeof(int32_t) * (N + 1)), b_is = slab.reserve(sizeof(int2) * I + 64);
   const int b_foff = slab.reserve(sizeof(int32_t) * (N + 1)), b_fsite = slab.reserve(sizeof(int32_t) * F + 64), b_ffrom = slab.reserve(F + 64);
-  const size_t upload_bytes = slab.total;
-  // outputs + workspaces (device only)
+  // outputs + workspaces
   const int b_lambda = slab.reserve(sizeof(double) * N), b_nsmn = slab.reserve(sizeof(int32_t) * N);
   const int b_tout = slab.reserve(sizeof(double) * 4 * num_trees), b_tiout = slab.reserve(sizeof(int32_t) * 20 * num_trees);
   const int b_tagg = slab.reserve(sizeof(double) * tiles), b_tiagg = slab.reserve(sizeof(int32_t) * tiles);
   const int b_tpart = slab.reserve(sizeof(double) * 2 * tiles), b_tipart = slab.reserve(sizeof(int32_t) * 17 * tiles);
-  const size_t zero_from = slab.total;
   const int b_tflag = slab.reserve(sizeof(uint32_t) * tiles);
   const int b_tdone = slab.reserve(sizeof(uint32_t) * num_trees), b_ticket = slab.reserve(sizeof(uint32_t) * 4);
-  const size_t zero_to = slab.total;
+
+  // ---- the temporary block: raw host-order arrays + flatten workspaces -------------------------------------------------------
+  Slab tmp;
+  const int r_raw = tmp.reserve(sizeof(RawTreeDev) * num_trees);
+  struct RawIds { int parent, c0, c1, t, moff, msite, mfrom, mto, mt, ioff, is, ie, foff, fsite, ffrom; };
+  std::vector<RawIds> rid(num_trees);
+  for (int k = 0; k < num_trees; ++k) {
+    const auto& e = trees[k];
+    const size_t n = e.num_nodes, m = e.mut_off[n], iv = e.miss_off[n], fs = e.fs_off[n];
+    RawIds& r = rid[k];
+    r.parent = tmp.reserve(4 * n); r.c0 = tmp.reserve(4 * n); r.c1 = tmp.reserve(4 * n); r.t = tmp.reserve(8 * n);
+    r.moff = tmp.reserve(4 * (n + 1)); r.msite = tmp.reserve(4 * m); r.mfrom = tmp.reserve(m); r.mto = tmp.reserve(m); r.mt = tmp.reserve(8 * m);
+    r.ioff = tmp.reserve(4 * (n + 1)); r.is = tmp.reserve(4 * iv); r.ie = tmp.reserve(4 * iv);
+    r.foff = tmp.reserve(4 * (n + 1)); r.fsite = tmp.reserve(4 * fs); r.ffrom = tmp.reserve(fs);
+  }
+  const size_t raw_upload_bytes = tmp.total;
+  const int w_arcs0 = tmp.reserve(sizeof(int4) * 2 * N), w_arcs1 = tmp.reserve(sizeof(int4) * 2 * N);
+  const int64_t scan_tiles = (N + 1023) / 1024;
+  const int w_scan = tmp.reserve(sizeof(int32_t) * 3 * scan_tiles);
+  const int w_status = tmp.reserve(sizeof(uint32_t) * 4 + sizeof(int32_t) * num_trees);
+
+  char* dbase = nullptr; char* tbase = nullptr;
+  if (cudaMallocAsync((void**)&dbase, slab.total, ctx->stream) != cudaSuccess) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(forest)"); }
+  if (cudaMallocAsync((void**)&tbase, tmp.total, ctx->stream) != cudaSuccess) {
+    cudaFreeAsync(dbase, ctx->stream); delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(forest staging)");
+  }
+  fo->allocs.push_back(dbase);
+  fo->bytes = slab.total;
+  auto fail = [&](int st) { cudaFreeAsync(tbase, ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo; return st; };
 
   void* hbv = nullptr;
-  int st = acquire_pinned(ctx, upload_bytes, &hbv);
-  if (st != DPHY_OK) { delete fo; return st; }
-  char* hb = static_cast<char*>(hbv);
-  fo->tree_muts.resize(num_trees); fo->tree_fs.resize(num_trees); fo->tree_max_depth.resize(num_trees);
+  int st = acquire_pinned(ctx, header_bytes + raw_upload_bytes, &hbv);
+  if (st != DPHY_OK) return fail(st);
+  char* hb = static_cast<char*>(hbv);          // [header | raw]
+  char* hraw = hb + header_bytes;
+
+  // ---- host side: only the per-tree / per-tile descriptors; the arrays are streamed verbatim ---------------------------
   auto* h_trees = slab.at<TreeDev>(hb, b_trees);
   auto* h_sites = slab.at<SitesDev>(hb, b_sites);
   auto* h_tile_tree = slab.at<int32_t>(hb, b_tile_tree);
   auto* h_ctile_tree = slab.at<int32_t>(hb, b_ctile_tree);
-  auto* h_node_id = slab.at<int32_t>(hb, b_node_id); auto* h_parent = slab.at<int32_t>(hb, b_parent);
-  auto* h_depth = slab.at<int32_t>(hb, b_depth); auto* h_size = slab.at<int32_t>(hb, b_size);
-  auto* h_post = slab.at<int32_t>(hb, b_post); auto* h_pos = slab.at<int32_t>(hb, b_pos);
-  auto* h_t = slab.at<double>(hb, b_t);
-  auto* h_moff = slab.at<int32_t>(hb, b_moff); auto* h_msite = slab.at<int32_t>(hb, b_msite);
-  auto* h_mft = slab.at<uint8_t>(hb, b_mft); auto* h_mt = slab.at<double>(hb, b_mt);
-  auto* h_ioff = slab.at<int32_t>(hb, b_ioff); auto* h_is = slab.at<int2>(hb, b_is);
-  auto* h_foff = slab.at<int32_t>(hb, b_foff); auto* h_fsite = slab.at<int32_t>(hb, b_fsite); auto* h_ffrom = slab.at<uint8_t>(hb, b_ffrom);
-
-  for (int i = 0; i < num_sites_tables; ++i) {
-    if (!sites[i]) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "null sites table"); }
-    h_sites[i] = sites[i]->h;
-    fo->sites_version[i] = sites[i]->version;
-  }
-
-  std::vector<int32_t> stack;
-  int32_t base = 0, mpos = 0, ipos = 0, fpos = 0, tile_pos = 0, ctile_pos = 0;
-  fo->trees.resize(num_trees);
+  auto* h_raw = tmp.at<RawTreeDev>(hraw, r_raw);
+  for (int i = 0; i < num_sites_tables; ++i) { h_sites[i] = sites[i]->h; fo->sites_version[i] = sites[i]->version; }
+  std::vector<CopyJob> jobs;
+  jobs.reserve((size_t)num_trees * 15);
+  int32_t base = 0, tile_pos = 0, ctile_pos = 0;
   for (int k = 0; k < num_trees; ++k) {
     const auto& e = trees[k];
     const int n = e.num_nodes;
-    const int si = sites_index ? sites_index[k] : 0;
-    const int L = sites[si]->L;
-    const uint8_t* hpart = sites[si]->h_part.data();
-    const uint8_t* href = sites[si]->h_ref.data();
-    // DFS pre-order, children[1] before children[0]; encode "exit" visits as ~v on the stack
-    int32_t* pos_of = h_pos + base;
-    std::fill(pos_of, pos_of + n, -1);
-    stack.clear(); stack.push_back(e.root);
-    int32_t next = 0, npost = 0;
-    if (e.parent[e.root] != -1) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "root has a parent"); }
-    while (!stack.empty()) {
-      int32_t v = stack.back(); stack.pop_back();
-      if (v < 0) {   // exit
-        v = ~v;
-        const int32_t p = pos_of[v];
-        h_size[base + p] = next - p;
-        h_post[base + npost++] = base + p;
-        continue;
-      }
-      if (v >= n || pos_of[v] != -1 || next >= n) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "tree topology is not a tree"); }
-      const int32_t p = next++;
-      pos_of[v] = p;
-      h_node_id[base + p] = v;
-      const int32_t par = e.parent[v];
-      h_parent[base + p] = par < 0 ? -1 : base + pos_of[par];
-      h_depth[base + p] = par < 0 ? 0 : h_depth[base + pos_of[par]] + 1;
-      h_t[base + p] = e.t[v];
-      // lists, device order
-      h_moff[base + p] = mpos;
-      for (int i = e.mut_off[v]; i < e.mut_off[v + 1]; ++i) {
-        const int l = e.mut_site[i];
-        if (l < 0 || l >= L) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "mutation site out of range"); }
-        if (e.mut_from[i] > 3 || e.mut_to[i] > 3) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "mutation state not in ACGT"); }
-        h_msite[mpos] = l; h_mft[mpos] = (uint8_t)(hpart[l] << 4 | e.mut_from[i] << 2 | e.mut_to[i]); h_mt[mpos] = e.mut_t[i]; ++mpos;
-      }
-      h_ioff[base + p] = ipos;
-      for (int i = e.miss_off[v]; i < e.miss_off[v + 1]; ++i) {
-        const int s0 = e.miss_start[i], s1 = e.miss_end[i];
-        if (s0 < 0 || s1 > L || s0 >= s1) {   // core/mutations.h:187-191 throws std::out_of_range
-          delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "Missation out of range");
-        }
-        h_is[ipos] = make_int2(s0, s1); ++ipos;
-      }
-      h_foff[base + p] = fpos;
-      for (int i = e.fs_off[v]; i < e.fs_off[v + 1]; ++i) {
-        const int l = e.fs_site[i];
-        if (l < 0 || l >= L) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "Missation out of range"); }
-        if (e.fs_from[i] > 3) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "missation from-state not in ACGT"); }
-        h_fsite[fpos] = l; h_ffrom[fpos] = (uint8_t)(hpart[l] << 4 | href[l] << 2 | e.fs_from[i]); ++fpos;
-      }
-      const int32_t c0 = e.child0[v], c1 = e.child1[v];
-      stack.push_back(~v);
-      if (c0 >= 0) {
-        if (c1 < 0 || e.parent[c0] != v || e.parent[c1] != v) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "child/parent mismatch"); }
-        stack.push_back(c0); stack.push_back(c1);   // children[1] is popped (visited) first
-      }
-    }
-    if (next != n) { delete fo; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "tree is disconnected"); }
-    fo->tree_muts[k] = e.mut_off[n]; fo->tree_fs[k] = e.fs_off[n];
-    { int32_t md = 0; for (int i = 0; i < n; ++i) md = std::max(md, h_depth[base + i]); fo->tree_max_depth[k] = md; }
+    const size_t m = e.mut_off[n], iv = e.miss_off[n], fs = e.fs_off[n];
     TreeDev& T = fo->trees[k];
-    T.node_base = base; T.num_nodes = n; T.sites_id = si; T.first_tile = tile_pos;
+    T.node_base = base; T.num_nodes = n; T.sites_id = sites_index ? sites_index[k] : 0; T.first_tile = tile_pos;
     T.num_tiles = (n + kTile - 1) / kTile; T.includes_run_root = e.includes_run_root; T.root_id = e.root; T.pad = 0;
     for (int j = 0; j < T.num_tiles; ++j) h_tile_tree[tile_pos++] = k;
     T.first_ctile = ctile_pos; T.num_ctiles = (n + kLgTile - 1) / kLgTile;
     for (int j = 0; j < T.num_ctiles; ++j) h_ctile_tree[ctile_pos++] = k;
     h_trees[k] = T;
+    fo->tree_muts[k] = (int64_t)m; fo->tree_fs[k] = (int64_t)fs;
+    const RawIds& r = rid[k];
+    RawTreeDev& R = h_raw[k];
+    R.parent = tmp.at<int32_t>(tbase, r.parent); R.child0 = tmp.at<int32_t>(tbase, r.c0); R.child1 = tmp.at<int32_t>(tbase, r.c1);
+    R.t = tmp.at<double>(tbase, r.t);
+    R.mut_off = tmp.at<int32_t>(tbase, r.moff); R.mut_site = tmp.at<int32_t>(tbase, r.msite);
+    R.mut_from = tmp.at<uint8_t>(tbase, r.mfrom); R.mut_to = tmp.at<uint8_t>(tbase, r.mto); R.mut_t = tmp.at<double>(tbase, r.mt);
+    R.miss_off = tmp.at<int32_t>(tbase, r.ioff); R.miss_start = tmp.at<int32_t>(tbase, r.is); R.miss_end = tmp.at<int32_t>(tbase, r.ie);
+    R.fs_off = tmp.at<int32_t>(tbase, r.foff); R.fs_site = tmp.at<int32_t>(tbase, r.fsite); R.fs_from = tmp.at<uint8_t>(tbase, r.ffrom);
+    R.root = e.root; R.num_nodes = n; R.num_muts = (int32_t)m; R.num_ivls = (int32_t)iv; R.num_fs = (int32_t)fs; R.pad = 0;
+    auto add = [&](int id, const void* src, size_t bytes) { if (bytes) jobs.push_back({tmp.blocks[id].off, src, bytes}); };
+    add(r.parent, e.parent, 4 * (size_t)n); add(r.c0, e.child0, 4 * (size_t)n); add(r.c1, e.child1, 4 * (size_t)n); add(r.t, e.t, 8 * (size_t)n);
+    add(r.moff, e.mut_off, 4 * ((size_t)n + 1)); add(r.msite, e.mut_site, 4 * m); add(r.mfrom, e.mut_from, m); add(r.mto, e.mut_to, m); add(r.mt, e.mut_t, 8 * m);
+    add(r.ioff, e.miss_off, 4 * ((size_t)n + 1)); add(r.is, e.miss_start, 4 * iv); add(r.ie, e.miss_end, 4 * iv);
+    add(r.foff, e.fs_off, 4 * ((size_t)n + 1)); add(r.fsite, e.fs_site, 4 * fs); add(r.ffrom, e.fs_from, fs);
     base += n;
   }
-  h_moff[N] = mpos; h_ioff[N] = ipos; h_foff[N] = fpos;
 
-  char* dbase = nullptr;
-  cudaError_t ce = cudaMalloc((void**)&dbase, slab.total);
-  if (ce != cudaSuccess) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMalloc(forest)"); }
-  fo->allocs.push_back(dbase);
-  fo->bytes = slab.total;
-  ce = cudaMemcpyAsync(dbase, hb, upload_bytes, cudaMemcpyHostToDevice, ctx->stream);
-  if (ce == cudaSuccess) ce = cudaMemsetAsync(dbase + zero_from, 0, zero_to - zero_from, ctx->stream);
-  if (ce != cudaSuccess) { cudaFree(dbase); delete fo; return check_cuda(ctx, ce, "H2D forest"); }
+  cudaError_t ce = cudaMemcpyAsync(dbase, hb, header_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(dbase + header_bytes, 0, slab.total - header_bytes, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(tbase + tmp.blocks[w_status].off, 0, tmp.blocks[w_status].bytes, ctx->stream);
+  if (ce != cudaSuccess) return fail(check_cuda(ctx, ce, "H2D forest header"));
+  // the RawTreeDev records were written straight into the pinned slab above; everything in [0, raw_upload_bytes) not
+  // covered by a job (those records, alignment gaps) is copied as it lies
+  st = staged_upload(ctx, hraw, jobs, tbase, raw_upload_bytes);
+  release_pinned_async(ctx);
+  if (st != DPHY_OK) return fail(st);
 
   ForestDev& h = fo->h;
   h.num_trees = num_trees; h.num_nodes = (int32_t)N; h.num_tiles = (int32_t)tiles; h.num_sites_tables = num_sites_tables;
@@ -429,15 +485,44 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   fo->d_tile_part = slab.at<double>(dbase, b_tpart); fo->d_tile_ipart = slab.at<int32_t>(dbase, b_tipart);
   fo->d_tile_flag = slab.at<uint32_t>(dbase, b_tflag); fo->d_tree_done = slab.at<uint32_t>(dbase, b_tdone);
   fo->d_ticket = slab.at<uint32_t>(dbase, b_ticket);
-  release_pinned_async(ctx);   // the staging buffer is reused by later calls once this copy has drained
+
+  // ---- device side: Euler tour + list ranking -> DFS order; CSR offsets; lists ------------------------------------------
+  FlattenParams P{};
+  P.trees = h.trees; P.sites = h.sites; P.tile_tree = h.tile_tree; P.raw = tmp.at<RawTreeDev>(tbase, r_raw);
+  P.arcs[0] = tmp.at<int4>(tbase, w_arcs0); P.arcs[1] = tmp.at<int4>(tbase, w_arcs1);
+  P.scan_tiles = tmp.at<int32_t>(tbase, w_scan);
+  P.status = tmp.at<uint32_t>(tbase, w_status); P.max_depth = reinterpret_cast<int32_t*>(P.status + 4);
+  P.num_nodes = (int32_t)N; P.total_muts = (int32_t)M; P.total_ivls = (int32_t)I; P.total_fs = (int32_t)F;
+  P.node_id = const_cast<int32_t*>(h.node_id); P.parent_pos = const_cast<int32_t*>(h.parent_pos);
+  P.depth = const_cast<int32_t*>(h.depth); P.subtree_size = const_cast<int32_t*>(h.subtree_size);
+  P.post_node = const_cast<int32_t*>(h.post_node); P.pos_of_node = const_cast<int32_t*>(h.pos_of_node);
+  P.t = h.t;
+  P.mut_off = const_cast<int32_t*>(h.mut_off); P.mut_site = const_cast<int32_t*>(h.mut_site);
+  P.mut_code = const_cast<uint8_t*>(h.mut_code); P.mut_t = h.mut_t;
+  P.miss_off = const_cast<int32_t*>(h.miss_off); P.miss_se = const_cast<int2*>(h.miss_se);
+  P.fs_off = const_cast<int32_t*>(h.fs_off); P.fs_site = const_cast<int32_t*>(h.fs_site); P.fs_code = const_cast<uint8_t*>(h.fs_code);
+  st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes);
+  if (st != DPHY_OK) return fail(st);
+  std::vector<int32_t> status(4 + num_trees, 0);
+  ce = cudaMemcpyAsync(status.data(), P.status, sizeof(int32_t) * status.size(), cudaMemcpyDeviceToHost, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) return fail(check_cuda(ctx, ce, "forest flatten"));
+  st = flatten_status_to_error(ctx, (uint32_t)status[0]);
+  if (st != DPHY_OK) return fail(st);
+  for (int k = 0; k < num_trees; ++k) fo->tree_max_depth[k] = status[4 + k];
+  cudaFreeAsync(tbase, ctx->stream);
   *out = fo;
   return DPHY_OK;
 }
 
 void dphy_forest_destroy(dphy_ctx* ctx, dphy_forest* fo) {
   if (!fo) return;
-  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  for (void* p : fo->allocs) cudaFree(p);
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    for (void* p : fo->allocs) cudaFreeAsync(p, ctx->stream);   // stream-ordered: returns to the pool, no device sync
+  } else {
+    for (void* p : fo->allocs) cudaFree(p);
+  }
   delete fo;
 }
 
@@ -457,16 +542,24 @@ int64_t dphy_forest_log_G_algorithmic_bytes(const dphy_forest* fo) {
 
 int dphy_forest_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t count, const int32_t* nodes, const double* t) {
   if (!ctx || !fo || tree < 0 || tree >= fo->h.num_trees || count < 0 || (count > 0 && (!nodes || !t))) return DPHY_ERR_INVALID_ARGUMENT;
-  const TreeDev& T = fo->trees[tree];
-  std::vector<int32_t> pos(T.num_nodes);
-  DPHY_CUDA(ctx, cudaMemcpyAsync(pos.data(), fo->h.pos_of_node + T.node_base, sizeof(int32_t) * T.num_nodes, cudaMemcpyDeviceToHost, ctx->stream));
-  DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < count; ++i) {
-    if (nodes[i] < 0 || nodes[i] >= T.num_nodes) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "node out of range");
-    DPHY_CUDA(ctx, cudaMemcpyAsync(fo->h.t + T.node_base + pos[nodes[i]], &t[i], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  }
+  if (count == 0) return DPHY_OK;
+  cudaSetDevice(ctx->device);
+  const size_t mark = ctx->arena.mark();
+  int32_t* d_nodes = (int32_t*)ctx->arena.alloc(sizeof(int32_t) * count);
+  double* d_vals = (double*)ctx->arena.alloc(sizeof(double) * count);
+  uint32_t* d_status = (uint32_t*)ctx->arena.alloc(sizeof(uint32_t));
+  if (!d_nodes || !d_vals || !d_status) { ctx->arena.release(mark); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (set_node_times)"); }
+  uint32_t status = 0;
+  int st = check_cuda(ctx, cudaMemcpyAsync(d_nodes, nodes, sizeof(int32_t) * count, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(d_vals, t, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemsetAsync(d_status, 0, sizeof(uint32_t), ctx->stream), "memset");
+  if (st == DPHY_OK) st = launch_set_node_times(ctx, fo, tree, d_nodes, d_vals, count, d_status);
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(&status, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "set_node_times");
+  ctx->arena.release(mark);
   fo->evaluated = false;
-  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "set_node_times");
+  if (st == DPHY_OK && status) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "node out of range");
+  return st;
 }
 
 // ---- log G ----------------------------------------------------------------------------------------------------------

@@ -102,6 +102,40 @@ struct ForestDev {
   const int32_t* pos_of_node;
 };
 
+// ---- device-side flattening (kernels_flatten.cu) ----------------------------------------------------------------------
+// One EMAT as uploaded: the caller's arrays, HOST node order, copied verbatim into a temporary device block.
+struct RawTreeDev {
+  const int32_t* parent; const int32_t* child0; const int32_t* child1; const double* t;
+  const int32_t* mut_off; const int32_t* mut_site; const uint8_t* mut_from; const uint8_t* mut_to; const double* mut_t;
+  const int32_t* miss_off; const int32_t* miss_start; const int32_t* miss_end;
+  const int32_t* fs_off; const int32_t* fs_site; const uint8_t* fs_from;
+  int32_t root, num_nodes, num_muts, num_ivls, num_fs, pad;
+};
+
+enum : uint32_t {
+  kFlattenErrTopology = 1u,    // not a binary tree rooted at `root` (child/parent mismatch, cycle, unreachable nodes)
+  kFlattenErrOffsets = 2u,     // CSR offsets not monotone / inconsistent with the array lengths
+  kFlattenErrMutSite = 4u,     // mutation site out of range            (std::out_of_range in the reference)
+  kFlattenErrMutState = 8u,    // mutation from/to not in ACGT
+  kFlattenErrMissation = 16u,  // missation interval / from-state site out of range (core/mutations.h:187-191)
+  kFlattenErrFsState = 32u,    // missation from-state not in ACGT
+};
+
+struct FlattenParams {
+  const TreeDev* trees; const SitesDev* sites; const int32_t* tile_tree; const RawTreeDev* raw;
+  int4* arcs[2];               // ping-pong Euler-tour arcs: (succ, #enter arcs to the end, #arcs to the end, -)
+  int32_t* scan_tiles;         // [ceil(num_nodes / 1024) * 3]
+  uint32_t* status;            // [1] error bits
+  int32_t* max_depth;          // [num_trees]
+  int32_t num_nodes, total_muts, total_ivls, total_fs;
+  // outputs (device order): the ForestDev arrays, writable
+  int32_t* node_id; int32_t* parent_pos; int32_t* depth; int32_t* subtree_size; int32_t* post_node; int32_t* pos_of_node;
+  double* t;
+  int32_t* mut_off; int32_t* mut_site; uint8_t* mut_code; double* mut_t;
+  int32_t* miss_off; int2* miss_se;
+  int32_t* fs_off; int32_t* fs_site; uint8_t* fs_code;
+};
+
 }  // namespace dphy
 
 struct dphy_ctx {
@@ -125,7 +159,6 @@ struct dphy_sites {
   // per-(partition,state) cumulative nu tables for O(1) interval tallies (Ttwiddle): [P*4][L+1]
   double* d_cum_nu_ba = nullptr;
   size_t bytes = 0;
-  std::vector<uint8_t> h_ref, h_part;   // host copies (used to pack per-event codes at forest upload)
   uint64_t version = 1;         // bumped by set_evo; forests re-sync their SitesDev copies lazily
 };
 
@@ -170,6 +203,9 @@ int launch_log_G(dphy_ctx* ctx, dphy_forest* f);
 int gather_lambda_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, double* d_dst);
 int gather_nsmn_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* d_dst);
 int refresh_sites(dphy_ctx* ctx, dphy_forest* f);   // c_abi.cu
+// kernels_flatten.cu
+int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max_tree_nodes);
+int launch_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count, uint32_t* d_status);
 // Pinned staging buffer of the ctx: acquire waits for the previous async copy out of it; release records an event.
 int acquire_pinned(dphy_ctx* ctx, size_t bytes, void** out);
 void release_pinned_async(dphy_ctx* ctx);

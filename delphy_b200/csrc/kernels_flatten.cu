@@ -1,0 +1,258 @@
+// kernels_flatten.cu -- device-side flattening of host-order EMATs into the forest layout (sm_100a).
+//
+// The reference keeps a Phylo_tree as an index-based AoS binary tree (core/tree.h:181-220, core/phylo_tree.h:14-63);
+// the C ABI receives it as SoA + CSR arrays in HOST node order.  Every kernel of the hot path wants DFS pre-order
+// (children[1] first -- the order of Spr_study_builder's LIFO work stack, core/spr_study.cpp:103-128).  Doing that
+// re-ordering on the host costs a sequential, cache-hostile DFS per upload and dominated the end-to-end time, so the
+// host now only streams the raw arrays to the device and the re-ordering happens here:
+//
+//   1. Euler tour: every node gets an "enter" and an "exit" arc; succ(enter v) = enter(child1 v) or exit(v) for a tip;
+//      succ(exit v) = enter(child0 of parent) if v is children[1], exit(parent) if v is children[0], end for the root.
+//   2. Wyllie list ranking (pointer jumping, ceil(log2(2N)) rounds, ping-pong buffers) carrying two suffix counters:
+//      E = #enter arcs and A = #arcs from here to the end of the tour.  Then
+//         pre-order index  = N - E[enter v]            subtree size = E[enter v] - E[exit v]
+//         depth            = 2 pre - (2N - A[enter v]) post-order index = (2N - A[exit v]) - (N - E[exit v])
+//   3. scatter node records to device order, exclusive-scan the per-node list lengths into the device CSR offsets,
+//      gather the mutation / missation / from-state lists (packing partition|from|to codes, validating ranges).
+//
+// All validation the reference performs by CHECK / std::out_of_range (core/mutations.h:187-191, core/phylo_tree.cpp:18-135
+// for the topology part) is folded into these kernels and reported through one status word.
+#include "dphy_internal.h"
+#include "device_utils.cuh"
+
+namespace dphy {
+
+constexpr int kScanItems = 4;                       // items per thread in the offset scans
+constexpr int kScanTile = kTile * kScanItems;       // 1024 positions per scan tile
+
+__device__ __forceinline__ void flag_error(FlattenParams& P, uint32_t bit) { atomicOr(P.status, bit); }
+
+// ---- (1) Euler-tour arcs + topology validation ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile) flatten_arcs_init_kernel(FlattenParams P) {
+  const int tile = blockIdx.x;
+  const int tree = P.tile_tree[tile];
+  const TreeDev T = P.trees[tree];
+  const RawTreeDev R = P.raw[tree];
+  const int v = (tile - T.first_tile) * kTile + threadIdx.x;
+  if (v >= T.num_nodes) return;
+  const int n = T.num_nodes;
+  const int g = T.node_base + v;
+  const int par = R.parent[v], c0 = R.child0[v], c1 = R.child1[v];
+  bool ok = true;
+  const bool is_root = (v == R.root);
+  const bool internal = (c0 >= 0 || c1 >= 0);
+  if (internal) {
+    ok = c0 >= 0 && c1 >= 0 && c0 < n && c1 < n && c0 != c1 && c0 != v && c1 != v;
+    if (ok) ok = R.parent[c0] == v && R.parent[c1] == v;
+  }
+  if (is_root) ok = ok && par == -1;
+  else {
+    ok = ok && par >= 0 && par < n && par != v;
+    if (ok) ok = (R.child0[par] == v) != (R.child1[par] == v);
+  }
+  int succ_enter, succ_exit;
+  if (!ok) {
+    flag_error(P, kFlattenErrTopology);
+    succ_enter = 2 * g + 1; succ_exit = -1;          // harmless self-contained list
+  } else {
+    succ_enter = internal ? 2 * (T.node_base + c1) : 2 * g + 1;
+    if (is_root) succ_exit = -1;
+    else if (R.child1[par] == v) succ_exit = 2 * (T.node_base + R.child0[par]);
+    else succ_exit = 2 * (T.node_base + par) + 1;
+  }
+  P.arcs[0][2 * g] = make_int4(succ_enter, 1, 1, 0);
+  P.arcs[0][2 * g + 1] = make_int4(succ_exit, 0, 1, 0);
+}
+
+// ---- (2) one pointer-jumping round -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flatten_rank_round_kernel(const int4* __restrict__ src, int4* __restrict__ dst, int num_arcs) {
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  if (a >= num_arcs) return;
+  int4 x = src[a];
+  if (x.x >= 0) {
+    const int4 y = __ldg(src + x.x);
+    x.x = y.x; x.y += y.y; x.z += y.z;
+  }
+  dst[a] = x;
+}
+
+// ---- (3a) node records to device order; per-node list lengths ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile) flatten_nodes_kernel(FlattenParams P, int final_buf) {
+  const int tile = blockIdx.x;
+  const int tree = P.tile_tree[tile];
+  const TreeDev T = P.trees[tree];
+  const RawTreeDev R = P.raw[tree];
+  const int v = (tile - T.first_tile) * kTile + threadIdx.x;
+  if (v >= T.num_nodes) return;
+  const int n = T.num_nodes;
+  const int g = T.node_base + v;
+  const int4* arcs = P.arcs[final_buf];
+  const int4 en = arcs[2 * g], ex = arcs[2 * g + 1];
+  const int pre = n - en.y;
+  const int pos_a = 2 * n - en.z;
+  const int depth = 2 * pre - pos_a;
+  const int size = en.y - ex.y;
+  const int post = (2 * n - ex.z) - (n - ex.y);
+  bool ok = en.x < 0 && ex.x < 0 && pre >= 0 && pre < n && size >= 1 && pre + size <= n && post >= 0 && post < n && depth >= 0;
+  if (v == R.root) ok = ok && en.y == n && en.z == 2 * n;     // every node is reachable from the root
+  if (!ok) { flag_error(P, kFlattenErrTopology); return; }
+  const int p = T.node_base + pre;
+  P.node_id[p] = v;
+  P.pos_of_node[g] = pre;
+  P.depth[p] = depth;
+  P.subtree_size[p] = size;
+  P.t[p] = R.t[v];
+  P.post_node[T.node_base + post] = p;
+  const int par = R.parent[v];
+  P.parent_pos[p] = par < 0 ? -1 : T.node_base + (n - arcs[2 * (T.node_base + par)].y);
+  int cm = R.mut_off[v + 1] - R.mut_off[v], ci = R.miss_off[v + 1] - R.miss_off[v], cf = R.fs_off[v + 1] - R.fs_off[v];
+  if (cm < 0 || ci < 0 || cf < 0 || R.mut_off[v] < 0 || R.miss_off[v] < 0 || R.fs_off[v] < 0 ||
+      R.mut_off[v + 1] > R.num_muts || R.miss_off[v + 1] > R.num_ivls || R.fs_off[v + 1] > R.num_fs) {
+    flag_error(P, kFlattenErrOffsets); cm = ci = cf = 0;
+  }
+  P.mut_off[p] = cm; P.miss_off[p] = ci; P.fs_off[p] = cf;
+  atomicMax(P.max_depth + tree, depth);
+}
+
+// ---- (3b) exclusive scan of the three length arrays, in place, over the whole forest ------------------------------------------------------------
+__global__ void __launch_bounds__(kTile) flatten_scan_reduce_kernel(FlattenParams P) {
+  __shared__ int s_ws[kTile / 32];
+  const int base = blockIdx.x * kScanTile;
+  int a = 0, b = 0, c = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int i = base + k * kTile + threadIdx.x;
+    if (i < P.num_nodes) { a += P.mut_off[i]; b += P.miss_off[i]; c += P.fs_off[i]; }
+  }
+  a = block_sum<int, kTile>(a, s_ws);
+  b = block_sum<int, kTile>(b, s_ws);
+  c = block_sum<int, kTile>(c, s_ws);
+  if (threadIdx.x == 0) { P.scan_tiles[blockIdx.x * 3 + 0] = a; P.scan_tiles[blockIdx.x * 3 + 1] = b; P.scan_tiles[blockIdx.x * 3 + 2] = c; }
+}
+
+__global__ void __launch_bounds__(1024) flatten_scan_spine_kernel(FlattenParams P, int num_scan_tiles) {
+  __shared__ int s_ws[32];
+  __shared__ int s_carry[3];
+  if (threadIdx.x < 3) s_carry[threadIdx.x] = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < num_scan_tiles; j0 += 1024) {
+    const int j = j0 + threadIdx.x;
+    const bool ok = j < num_scan_tiles;
+    int tot[3];
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      const int v = ok ? P.scan_tiles[j * 3 + w] : 0;
+      const int incl = block_scan_incl<int, 1024>(v, s_ws, &tot[w]);
+      if (ok) P.scan_tiles[j * 3 + w] = s_carry[w] + incl - v;
+      __syncthreads();
+    }
+    if (threadIdx.x < 3) s_carry[threadIdx.x] += tot[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    P.mut_off[P.num_nodes] = s_carry[0]; P.miss_off[P.num_nodes] = s_carry[1]; P.fs_off[P.num_nodes] = s_carry[2];
+    if (s_carry[0] != P.total_muts || s_carry[1] != P.total_ivls || s_carry[2] != P.total_fs) atomicOr(P.status, kFlattenErrOffsets);
+  }
+}
+
+__global__ void __launch_bounds__(kTile) flatten_scan_apply_kernel(FlattenParams P) {
+  __shared__ int s_ws[kTile / 32];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  int32_t* arrs[3] = {P.mut_off, P.miss_off, P.fs_off};
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    int v[kScanItems], run = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < P.num_nodes ? arrs[w][base + k] : 0; run += v[k]; }
+    int tot;
+    const int incl = block_scan_incl<int, kTile>(run, s_ws, &tot);
+    int ex = P.scan_tiles[blockIdx.x * 3 + w] + incl - run;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { if (base + k < P.num_nodes) arrs[w][base + k] = ex; ex += v[k]; }
+    __syncthreads();
+  }
+}
+
+// ---- (3c) lists to device order: packed codes + range validation -------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile) flatten_events_kernel(FlattenParams P) {
+  const int tile = blockIdx.x;
+  const int tree = P.tile_tree[tile];
+  const TreeDev T = P.trees[tree];
+  const RawTreeDev R = P.raw[tree];
+  const SitesDev& S = P.sites[T.sites_id];
+  const int q = (tile - T.first_tile) * kTile + threadIdx.x;
+  if (q >= T.num_nodes) return;
+  const int p = T.node_base + q;
+  const int v = P.node_id[p];
+  const int L = S.L;
+  uint32_t err = 0;
+  {
+    const int src = R.mut_off[v], dst = P.mut_off[p], cnt = P.mut_off[p + 1] - dst;
+    for (int i = 0; i < cnt; ++i) {
+      int l = R.mut_site[src + i];
+      const int from = R.mut_from[src + i], to = R.mut_to[src + i];
+      if (l < 0 || l >= L) { err |= kFlattenErrMutSite; l = 0; }
+      if (from > 3 || to > 3) err |= kFlattenErrMutState;
+      P.mut_site[dst + i] = l;
+      P.mut_code[dst + i] = (uint8_t)(S.part[l] << 4 | (from & 3) << 2 | (to & 3));
+      P.mut_t[dst + i] = R.mut_t[src + i];
+    }
+  }
+  {
+    const int src = R.miss_off[v], dst = P.miss_off[p], cnt = P.miss_off[p + 1] - dst;
+    for (int i = 0; i < cnt; ++i) {
+      int s0 = R.miss_start[src + i], s1 = R.miss_end[src + i];
+      if (s0 < 0 || s1 > L || s0 >= s1) { err |= kFlattenErrMissation; s0 = 0; s1 = 1; }   // core/mutations.h:187-191
+      P.miss_se[dst + i] = make_int2(s0, s1);
+    }
+  }
+  {
+    const int src = R.fs_off[v], dst = P.fs_off[p], cnt = P.fs_off[p + 1] - dst;
+    for (int i = 0; i < cnt; ++i) {
+      int l = R.fs_site[src + i];
+      const int from = R.fs_from[src + i];
+      if (l < 0 || l >= L) { err |= kFlattenErrMissation; l = 0; }
+      if (from > 3) err |= kFlattenErrFsState;
+      P.fs_site[dst + i] = l;
+      P.fs_code[dst + i] = (uint8_t)(S.part[l] << 4 | S.ref[l] << 2 | (from & 3));
+    }
+  }
+  if (err) flag_error(P, err);
+}
+
+// Accepted displace moves (core/subrun.cpp:223-231,276-284): scatter new node times by host node index.
+__global__ void set_node_times_kernel(const int32_t* __restrict__ pos_of_node, double* __restrict__ t, int node_base, int num_nodes,
+                                      const int32_t* __restrict__ nodes, const double* __restrict__ vals, int count, uint32_t* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int v = nodes[i];
+  if (v < 0 || v >= num_nodes) { atomicOr(status, 1u); return; }
+  t[node_base + pos_of_node[node_base + v]] = vals[i];
+}
+
+int launch_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count, uint32_t* d_status) {
+  const TreeDev& T = fo->trees[tree];
+  set_node_times_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->h.t, T.node_base, T.num_nodes, d_nodes, d_vals, count, d_status);
+  ctx->launches += 1;
+  return check_cuda(ctx, cudaGetLastError(), "set_node_times_kernel");
+}
+
+int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max_tree_nodes) {
+  if (P.num_nodes == 0) return DPHY_OK;
+  const int num_arcs = 2 * P.num_nodes;
+  flatten_arcs_init_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
+  int rounds = 0;
+  while ((1LL << rounds) < 2LL * max_tree_nodes) ++rounds;
+  for (int r = 0; r < rounds; ++r)
+    flatten_rank_round_kernel<<<(num_arcs + 255) / 256, 256, 0, ctx->stream>>>(P.arcs[r & 1], P.arcs[(r + 1) & 1], num_arcs);
+  flatten_nodes_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P, rounds & 1);
+  const int nst = (P.num_nodes + kScanTile - 1) / kScanTile;
+  flatten_scan_reduce_kernel<<<nst, kTile, 0, ctx->stream>>>(P);
+  flatten_scan_spine_kernel<<<1, 1024, 0, ctx->stream>>>(P, nst);
+  flatten_scan_apply_kernel<<<nst, kTile, 0, ctx->stream>>>(P);
+  flatten_events_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
+  ctx->launches += 6 + rounds;
+  return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch");
+}
+
+}  // namespace dphy

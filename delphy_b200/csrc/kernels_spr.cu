@@ -35,7 +35,7 @@ struct SprStudy {
   int32_t tree, X, start_branch, start_mut_idx, init_min_muts, limit, can_change_root, n_x_deltas, n_x_missing, pad0;
   double t_X, lambda_X, f, t_max_tip;
   // slab offsets in bytes
-  int64_t off_xtab, off_path, off_xpath, off_H, off_C, off_KB, off_seg, off_regions, off_xd_site, off_xd_to, off_xm_start,
+  int64_t off_xtab, off_xkey, off_path, off_xpath, off_H, off_C, off_KB, off_seg, off_regions, off_xd_site, off_xd_to, off_xm_start,
       off_xm_end, off_part;
   int32_t region_cap, path_cap;
   // ---- derived (spr_setup_kernel) ----
@@ -100,25 +100,34 @@ __device__ double dev_gamma_q(double a, double x) {
   return q < 0.0 ? 0.0 : (q > 1.0 ? 1.0 : q);
 }
 
-// ---- (1) per-study setup: node positions, root path, X's state table -------------------------------------------------------
-__global__ void __launch_bounds__(256) spr_setup_kernel(ForestDev f, SprBatchDev B) {
-  __shared__ int s_ws[8];
+// ---- (1) per-study setup: node positions, root paths, X's state table -------------------------------------------------------
+// Everything is block-parallel: no thread ever chases parent pointers.  In DFS pre-order the ancestors of q are exactly
+// the positions p <= q with p + subtree_size[p] > q, and the ancestor at depth d goes to slot depth[q] - d of the path,
+// so both root paths are built by one coalesced sweep over subtree_size.  X's sequence is the reference sequence
+// overlaid with the LAST mutation per site on the root->X path: every path mutation posts (ordinal << 2 | to) with an
+// atomicMax on a per-site key, ordinals coming from a block scan of the per-branch list lengths in root->X order.
+constexpr int kSetupThreads = 1024;
+
+__global__ void __launch_bounds__(kSetupThreads) spr_setup_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ int s_ws[kSetupThreads / 32];
+  __shared__ int s_carry;
   SprStudy& S = B.studies[blockIdx.x];
   const int tid = threadIdx.x;
   const TreeDev T = f.trees[S.tree];
   const SitesDev& Si = f.sites[T.sites_id];
   const int L = Si.L;
   uint8_t* xtab = (uint8_t*)(B.slab + S.off_xtab);
+  uint32_t* xkey = (uint32_t*)(B.slab + S.off_xkey);
   int32_t* path = (int32_t*)(B.slab + S.off_path);
   int32_t* xpath = (int32_t*)(B.slab + S.off_xpath);
-  for (int l = tid; l < L; l += 256) xtab[l] = Si.ref[l];
+  for (int l = tid; l < L; l += kSetupThreads) { xtab[l] = Si.ref[l]; xkey[l] = 0u; }
   if (tid == 0) {
     S.node_base = T.node_base; S.num_nodes = T.num_nodes; S.num_tiles = T.num_tiles; S.L = L;
     S.root_pos = T.node_base; S.error = 0;
     S.total_regions = 0; S.max_key = 0ULL; S.log_Wmax = 0.0; S.sum_W = 0.0;
     int posX = -1, posP = -1, posS = -1, nP = 0, nS = 0, Proot = 0;
     if (S.X >= 0) {
-      posX = f.pos_of_node[T.node_base + S.X];
+      posX = T.node_base + f.pos_of_node[T.node_base + S.X];
       posP = f.parent_pos[posX];
       if (posP < 0) { S.error = 1; posP = posX; }
       const int c1 = posP + 1, c0 = posP + 1 + f.subtree_size[posP + 1];
@@ -128,52 +137,74 @@ __global__ void __launch_bounds__(256) spr_setup_kernel(ForestDev f, SprBatchDev
       Proot = f.parent_pos[posP] < 0;
     }
     S.posX = posX; S.posP = posP; S.posS = posS; S.nP = nP; S.nS = nS; S.P_is_root = Proot;
-    const int pos0 = f.pos_of_node[T.node_base + S.start_branch];
+    const int pos0 = T.node_base + f.pos_of_node[T.node_base + S.start_branch];
     S.pos0 = pos0; S.k0 = S.start_mut_idx; S.n0 = f.mut_off[pos0 + 1] - f.mut_off[pos0];
     if (S.k0 < 0 || S.k0 > S.n0 || (pos0 == T.node_base && S.k0 != S.n0)) S.error = 2;
     if (posX >= 0 && pos0 >= posX && pos0 < posX + f.subtree_size[posX]) S.error = 3;   // start inside X's subtree
-    int j = 0;
-    for (int a = pos0; a >= 0 && j < S.path_cap; a = f.parent_pos[a]) path[j++] = a;
-    S.path_len = j;
-    j = 0;
-    for (int a = posX; a >= 0 && j < S.path_cap; a = f.parent_pos[a]) xpath[j++] = a;
-    S.xpath_len = j;
+    S.path_len = min(f.depth[pos0] + 1, S.path_cap);
+    S.xpath_len = posX >= 0 ? min(f.depth[posX] + 1, S.path_cap) : 0;
+    s_carry = 0;
   }
   __syncthreads();
-  if (S.X >= 0) {
-    // missing_at_X = union of the missation intervals on the X->root path (disjoint along a path by invariant)
-    for (int jj = 0; jj < S.xpath_len; ++jj) {
-      const int a = xpath[jj];
-      for (int i = f.miss_off[a]; i < f.miss_off[a + 1]; ++i) {
-        const int2 se = f.miss_se[i]; const int s = se.x, e = se.y;
-        for (int l = s + tid; l < e; l += 256) xtab[l] |= 4;
+  {
+    const int pos0 = S.pos0, posX = S.posX;
+    const int d0 = S.path_len - 1, dX = S.xpath_len - 1;
+    const int hi = max(pos0, posX);
+    for (int p = T.node_base + tid; p <= hi; p += kSetupThreads) {
+      const int end = p + f.subtree_size[p];
+      const bool a0 = p <= pos0 && end > pos0, aX = posX >= 0 && p <= posX && end > posX;
+      if (a0 || aX) {
+        const int d = f.depth[p];
+        if (a0 && d0 - d >= 0) path[d0 - d] = p;
+        if (aX && dX - d >= 0) xpath[dX - d] = p;
       }
     }
-    __syncthreads();
-    // X's sequence: reference overlaid with the mutations on the root->X path, in order
-    if (tid == 0) {
-      for (int jj = S.xpath_len - 1; jj >= 0; --jj) {
-        const int a = xpath[jj];
-        for (int i = f.mut_off[a]; i < f.mut_off[a + 1]; ++i) {
-          const int l = f.mut_site[i];
-          xtab[l] = (uint8_t)((xtab[l] & 4) | (f.mut_code[i] & 3));
-        }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  if (S.X >= 0) {
+    // missing_at_X = union of the missation intervals on the X->root path (disjoint along a path by invariant):
+    // one warp per path node, lanes stride over the sites of each interval
+    for (int jj = warp; jj < S.xpath_len; jj += kSetupThreads / 32) {
+      const int a = xpath[jj];
+      for (int i = f.miss_off[a]; i < f.miss_off[a + 1]; ++i) {
+        const int2 se = f.miss_se[i];
+        for (int l = se.x + lane; l < se.y; l += 32) xtab[l] |= 4;
       }
+    }
+    // X's sequence: last mutation per site on the root->X path
+    for (int j0 = 0; j0 < S.xpath_len; j0 += kSetupThreads) {
+      const int j = j0 + tid;                                   // j counts from the ROOT end of the path
+      const int a = j < S.xpath_len ? xpath[S.xpath_len - 1 - j] : -1;
+      const int mo = a >= 0 ? f.mut_off[a] : 0, cnt = a >= 0 ? f.mut_off[a + 1] - mo : 0;
+      int tot;
+      const int incl = block_scan_incl<int, kSetupThreads>(cnt, s_ws, &tot);
+      const int base = s_carry + incl - cnt;
+      if (base + cnt >= (1 << 29)) S.error = 4;
+      for (int i = 0; i < cnt; ++i)
+        atomicMax(xkey + f.mut_site[mo + i], ((uint32_t)(base + i + 1) << 2) | (uint32_t)(f.mut_code[mo + i] & 3));
+      __syncthreads();
+      if (tid == 0) s_carry += tot;
+      __syncthreads();
     }
   } else {
     const int32_t* ms = (const int32_t*)(B.slab + S.off_xm_start);
     const int32_t* me = (const int32_t*)(B.slab + S.off_xm_end);
-    for (int i = 0; i < S.n_x_missing; ++i)
-      for (int l = ms[i] + tid; l < me[i]; l += 256) xtab[l] |= 4;
-    __syncthreads();
+    for (int i = warp; i < S.n_x_missing; i += kSetupThreads / 32)
+      for (int l = ms[i] + lane; l < me[i]; l += 32) xtab[l] |= 4;
     const int32_t* ds = (const int32_t*)(B.slab + S.off_xd_site);
     const uint8_t* dt = (const uint8_t*)(B.slab + S.off_xd_to);
-    for (int i = tid; i < S.n_x_deltas; i += 256) xtab[ds[i]] = (uint8_t)((xtab[ds[i]] & 4) | (dt[i] & 3));
+    for (int i = tid; i < S.n_x_deltas; i += kSetupThreads) atomicMax(xkey + ds[i], ((uint32_t)(i + 1) << 2) | (uint32_t)(dt[i] & 3));
   }
   __syncthreads();
   int cnt = 0;
-  for (int l = tid; l < L; l += 256) cnt += (xtab[l] >> 2) & 1;
-  cnt = block_sum<int, 256>(cnt, s_ws);
+  for (int l = tid; l < L; l += kSetupThreads) {
+    const uint32_t k = xkey[l];
+    uint8_t x = xtab[l];
+    if (k) { x = (uint8_t)((x & 4) | (k & 3)); xtab[l] = x; }
+    cnt += (x >> 2) & 1;
+  }
+  cnt = block_sum<int, kSetupThreads>(cnt, s_ws);
   if (tid == 0) {
     S.num_missing = cnt;
     S.mu = S.lambda_X / (double)(L - cnt);   // Spr_study::mu, core/spr_study.cpp:239
@@ -712,6 +743,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     S.region_cap = (int32_t)cap64;
     S.path_cap = fo->tree_max_depth[r.tree] + 2;
     S.off_xtab = off; off = al(off + L);
+    S.off_xkey = off; off = al(off + sizeof(uint32_t) * (size_t)L);
     S.off_path = off; off = al(off + sizeof(int32_t) * S.path_cap);
     S.off_xpath = off; off = al(off + sizeof(int32_t) * S.path_cap);
     S.off_H = off; off = al(off + sizeof(int32_t) * N);
@@ -772,7 +804,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   }
   if (ce != cudaSuccess) { cudaFreeAsync(d, ctx->stream); delete b; return check_cuda(ctx, ce, "spr batch upload"); }
   const dim3 grid_tiles(max_tiles, n);
-  spr_setup_kernel<<<n, 256, 0, ctx->stream>>>(fo->h, b->dev);
+  spr_setup_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
   spr_scan_kernel<0><<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev);
   bool any_limited = false;
   for (int i = 0; i < n; ++i) any_limited |= (b->host[i].limit != INT_MAX);
@@ -804,6 +836,7 @@ static int spr_fetch(dphy_ctx* ctx, dphy_spr_batch* b) {
     if (b->host[i].error == 1) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: X has no parent");
     if (b->host[i].error == 2) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: start_mut_idx out of range for the start branch");
     if (b->host[i].error == 3) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: start region lies inside X's subtree");
+    if (b->host[i].error == 4) return set_error(ctx, DPHY_ERR_INTERNAL, "spr: more than 2^29 mutations on the root->X path");
     if (b->host[i].total_regions > b->host[i].region_cap) return set_error(ctx, DPHY_ERR_INTERNAL, "spr: region capacity exceeded");
   }
   return DPHY_OK;

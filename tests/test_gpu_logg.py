@@ -186,3 +186,77 @@ def test_partition_parts_as_forest(ctx, orc):
     tb = sum(pf.Ttwiddle_beta_a(k) for k in range(len(parts)))
     np.testing.assert_allclose(tb, whole.Ttwiddle_beta_a(0), rtol=1e-9)
     whole.close(); pf.close(); ds.close()
+
+
+def _copy_emat(emat):
+    return db.HostEmat(emat.root, 1, **{k: getattr(emat, k).copy() for k in db.HostEmat.FIELDS_I32 + db.HostEmat.FIELDS_U8 + db.HostEmat.FIELDS_F64})
+
+
+def test_flatten_rejects_bad_topology(ctx):
+    """The device-side flattening (Euler tour + list ranking) validates what the reference CHECKs in
+    assert_tree_integrity (core/tree.h) -- cycles, child/parent mismatches, unreachable nodes, bad CSR offsets."""
+    emat, sites, _ = synth(0)
+    ds = db.DeviceSites(ctx, sites)
+    inner = int(next(v for v in range(emat.num_nodes) if emat.child0[v] >= 0 and v != emat.root))
+    tip = int(next(v for v in range(emat.num_nodes) if emat.child0[v] < 0))
+
+    bad = _copy_emat(emat); bad.child0[inner] = bad.child1[inner]                 # same child twice
+    with pytest.raises(db.DphyError) as ei:
+        db.Forest(ctx, [bad], [ds])
+    assert ei.value.status == db.ERR_INVALID_ARGUMENT
+
+    bad = _copy_emat(emat); bad.parent[tip] = (int(bad.parent[tip]) + 1) % emat.num_nodes   # parent does not own the child
+    with pytest.raises(db.DphyError):
+        db.Forest(ctx, [bad], [ds])
+
+    bad = _copy_emat(emat)                                                        # a 2-cycle detached from the root
+    a, b = inner, int(emat.child0[inner])
+    if emat.child0[b] >= 0:
+        bad.parent[a] = b; bad.child0[b] = a
+        with pytest.raises(db.DphyError):
+            db.Forest(ctx, [bad], [ds])
+
+    bad = _copy_emat(emat); bad.mut_off[3] = bad.mut_off[emat.num_nodes] + 7      # offsets not monotone
+    with pytest.raises(db.DphyError):
+        db.Forest(ctx, [bad], [ds])
+
+    bad = _copy_emat(emat)
+    if len(bad.mut_site):
+        bad.mut_site[0] = sites.num_sites                                          # site out of range
+        with pytest.raises(db.DphyError) as ei:
+            db.Forest(ctx, [bad], [ds])
+        assert ei.value.status == db.ERR_OUT_OF_RANGE
+    # the context stays usable after a rejected upload
+    fo = db.Forest(ctx, [emat], [ds]); fo.eval_log_G(); fo.log_G(); fo.close()
+    ds.close()
+
+
+def test_upload_order_independence(ctx, orc):
+    """Relabelling the host node indices changes nothing: the device order comes from the topology alone."""
+    emat, sites, _ = synth(0, seed=77)
+    rng = np.random.default_rng(3)
+    n = emat.num_nodes
+    perm = rng.permutation(n).astype(np.int32)          # new index of old node v
+    inv = np.argsort(perm).astype(np.int32)             # old index of new node w
+    def remap(a):
+        return np.where(a >= 0, perm[np.maximum(a, 0)], -1).astype(np.int32)
+    def csr(off, *arrs):
+        cnt = (off[1:] - off[:-1])[inv]
+        noff = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+        idx = np.concatenate([np.arange(off[v], off[v + 1]) for v in inv]) if len(arrs[0]) else np.zeros(0, np.int64)
+        return (noff,) + tuple(a[idx.astype(np.int64)] for a in arrs)
+    moff, msite, mfrom, mto, mt = csr(emat.mut_off, emat.mut_site, emat.mut_from, emat.mut_to, emat.mut_t)
+    ioff, istart, iend = csr(emat.miss_off, emat.miss_start, emat.miss_end)
+    foff, fsite, ffrom = csr(emat.fs_off, emat.fs_site, emat.fs_from)
+    shuffled = db.HostEmat(int(perm[emat.root]), 1, parent=remap(emat.parent)[inv], child0=remap(emat.child0)[inv],
+                           child1=remap(emat.child1)[inv], t=emat.t[inv], mut_off=moff, mut_site=msite, mut_from=mfrom,
+                           mut_to=mto, mut_t=mt, miss_off=ioff, miss_start=istart, miss_end=iend, fs_off=foff,
+                           fs_site=fsite, fs_from=ffrom)
+    ds = db.DeviceSites(ctx, sites)
+    fo = db.Forest(ctx, [emat, shuffled], [ds])
+    fo.eval_log_G()
+    rp, br, lg = fo.log_G()
+    assert br[0] == br[1] and rp[0] == rp[1]            # same device order => bit-identical sums
+    np.testing.assert_array_equal(fo.lambda_i(0), fo.lambda_i(1)[perm])
+    np.testing.assert_array_equal(fo.num_sites_missing(0), fo.num_sites_missing(1)[perm])
+    fo.close(); ds.close()

@@ -175,3 +175,24 @@ def test_request_validation(ctx):
     with pytest.raises(db.DphyError):
         fo.spr_study_batch([db.spr_request(0, 1, 0.0, emat.num_nodes + 3, 0, 0, 1.0, 0.0)])
     fo.close(); ds.close()
+
+
+def test_studies_on_every_tree_of_a_forest(ctx, orc):
+    """Studies addressed to trees other than the first one of a forest (device positions are forest-global)."""
+    items = [synth(0, seed=31), synth(0, seed=32, num_tips=150), synth(1, seed=33)]
+    tables = [db.DeviceSites(ctx, it[1]) for it in items]
+    fo = db.Forest(ctx, [it[0] for it in items], tables, sites_index=np.arange(len(items)))
+    reqs, meta = [], []
+    for k, (emat, sites, info) in enumerate(items):
+        lam = fo.lambda_i(k)
+        xs = [int(v) for v in np.random.default_rng(k).permutation(emat.num_nodes) if v != emat.root][:6]
+        reqs += db.spr_requests_for_attached(emat, k, xs, lam, info["t_max_tip"], 1 if k == 1 else INF)
+        meta += [(k, X, lam) for X in xs]
+    batch = fo.spr_study_batch(reqs)
+    for i, (k, X, lam) in enumerate(meta):
+        e, s = to_oracle(items[k][0], items[k][1])
+        want, _ = orc.spr_study_from_attached(e, s, X, lam, 1 if k == 1 else INF, True, 0.8, items[k][2]["t_max_tip"])
+        _cmp_regions(batch.regions(i), want)
+    batch.close(); fo.close()
+    for t in tables:
+        t.close()
