@@ -149,6 +149,24 @@ static void set_nu_uniform(dphy_sites* s, const double* nu_l) {
   s->h.pad = 0;
 }
 
+static void fill_tables(dphy_sites* s) {
+  for (int i = 0; i < kMaxPartitions * 16; ++i) {
+    const int pt = i >> 4, x = (i >> 2) & 3, y = i & 3;
+    if (pt < s->P) {
+      const double dq = (-s->h.q[pt * 16 + y * 5]) - (-s->h.q[pt * 16 + x * 5]);
+      s->h.tab_dq[i] = dq;
+      s->h.tab_md[i] = s->h.mu[pt] * s->h.nu_const * dq;
+      s->h.tab_lq[i] = x != y ? std::log(s->h.mu[pt] * s->h.nu_const * s->h.q[i]) : 0.0;
+    } else {
+      s->h.tab_dq[i] = 0.0; s->h.tab_md[i] = 0.0; s->h.tab_lq[i] = 0.0;
+    }
+  }
+  for (int i = 0; i < kMaxPartitions * 4; ++i) {
+    const int pt = i >> 2, a = i & 3;
+    s->h.tab_muq[i] = pt < s->P ? s->h.mu[pt] * s->h.nu_const * (-s->h.q[pt * 16 + a * 5]) : 0.0;
+  }
+}
+
 static int fill_evo(dphy_ctx* ctx, dphy_sites* s, const double* mu, const double* pi_a, const double* q_ab) {
   for (int b = 0; b < s->P; ++b) {
     s->h.mu[b] = mu[b];
@@ -197,6 +215,7 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
   for (int l = 0; l < L; ++l) hp[l] = (uint8_t)host->partition_for_site[l];
   std::memcpy(slab.at<double>(hb, b_nu), host->nu_l, sizeof(double) * L);
   set_nu_uniform(s, host->nu_l);
+  fill_tables(s);
   s->d_ref = slab.at<uint8_t>(dbase, b_ref); s->d_part = slab.at<uint8_t>(dbase, b_part); s->d_nu = slab.at<double>(dbase, b_nu);
   s->d_munu = slab.at<double>(dbase, b_munu); s->d_cumQ = slab.at<double>(dbase, b_cumQ);
   s->d_ref_freq = slab.at<int32_t>(dbase, b_freq); s->d_cum_nu_ba = slab.at<double>(dbase, b_cnu);
@@ -231,6 +250,7 @@ int dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* s, const double* nu_l, const d
     DPHY_CUDA(ctx, cudaMemcpyAsync(s->d_nu, hbv, sizeof(double) * s->L, cudaMemcpyHostToDevice, ctx->stream));
     release_pinned_async(ctx);
   }
+  fill_tables(s);
   s->version += 1;
   st = launch_sites_derive(ctx, s);
   if (st != DPHY_OK) return st;
@@ -348,8 +368,12 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   if (N > std::numeric_limits<int32_t>::max() / 4 || M > std::numeric_limits<int32_t>::max() / 2 ||
       I > std::numeric_limits<int32_t>::max() / 2 || F > std::numeric_limits<int32_t>::max() / 2)
     return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "forest too large for 32-bit positions");
-  for (int i = 0; i < num_sites_tables; ++i)
+  int maxP = 1;
+  for (int i = 0; i < num_sites_tables; ++i) {
     if (!sites[i]) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "null sites table");
+    maxP = std::max(maxP, sites[i]->P);
+  }
+  const int fsw_stride = 4 * maxP;
 
   auto* fo = new (std::nothrow) dphy_forest();
   if (!fo) return DPHY_ERR_OUT_OF_MEMORY;
@@ -365,6 +389,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   const int b_sites = slab.reserve(sizeof(SitesDev) * num_sites_tables);
   const int b_tile_tree = slab.reserve(sizeof(int32_t) * tiles);
   const int b_ctile_tree = slab.reserve(sizeof(int32_t) * ctiles);
+  const int b_ctiles = slab.reserve(sizeof(CTileDesc) * ctiles);
   const size_t header_bytes = slab.total;
   const int b_node_id = slab.reserve(sizeof(int32_t) * N), b_parent = slab.reserve(sizeof(int32_t) * N);
   const int b_depth = slab.reserve(sizeof(int32_t) * N), b_size = slab.reserve(sizeof(int32_t) * N);
@@ -374,8 +399,11 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   const int b_mft = slab.reserve(M + 64), b_mt = slab.reserve(sizeof(double) * M + 64);
   const int b_ioff = slab.reserve(sizeof(int32_t) * (N + 1)), b_is = slab.reserve(sizeof(int2) * I + 64);
   const int b_foff = slab.reserve(sizeof(int32_t) * (N + 1)), b_fsite = slab.reserve(sizeof(int32_t) * F + 64), b_ffrom = slab.reserve(F + 64);
+  const int b_fsw = slab.reserve(sizeof(int16_t) * (size_t)fsw_stride * N + 64);
   // outputs + workspaces
   const int b_lambda = slab.reserve(sizeof(double) * N), b_nsmn = slab.reserve(sizeof(int32_t) * N);
+  const int b_fastl = slab.reserve(sizeof(int32_t) * ctiles), b_slowl = slab.reserve(sizeof(int32_t) * ctiles);
+  const int b_strad = slab.reserve(sizeof(int32_t) * 2 * N), b_sdd = slab.reserve(sizeof(double) * N), b_sdn = slab.reserve(sizeof(int32_t) * N);
   const int b_tout = slab.reserve(sizeof(double) * 4 * num_trees), b_tiout = slab.reserve(sizeof(int32_t) * 20 * num_trees);
   const int b_tagg = slab.reserve(sizeof(double) * tiles), b_tiagg = slab.reserve(sizeof(int32_t) * tiles);
   const int b_tpart = slab.reserve(sizeof(double) * 2 * tiles), b_tipart = slab.reserve(sizeof(int32_t) * 17 * tiles);
@@ -422,6 +450,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   auto* h_sites = slab.at<SitesDev>(hb, b_sites);
   auto* h_tile_tree = slab.at<int32_t>(hb, b_tile_tree);
   auto* h_ctile_tree = slab.at<int32_t>(hb, b_ctile_tree);
+  auto* h_ctiles = slab.at<CTileDesc>(hb, b_ctiles);
   auto* h_raw = tmp.at<RawTreeDev>(hraw, r_raw);
   for (int i = 0; i < num_sites_tables; ++i) { h_sites[i] = sites[i]->h; fo->sites_version[i] = sites[i]->version; }
   std::vector<CopyJob> jobs;
@@ -436,7 +465,12 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     T.num_tiles = (n + kTile - 1) / kTile; T.includes_run_root = e.includes_run_root; T.root_id = e.root; T.pad = 0;
     for (int j = 0; j < T.num_tiles; ++j) h_tile_tree[tile_pos++] = k;
     T.first_ctile = ctile_pos; T.num_ctiles = (n + kLgTile - 1) / kLgTile;
-    for (int j = 0; j < T.num_ctiles; ++j) h_ctile_tree[ctile_pos++] = k;
+    for (int j = 0; j < T.num_ctiles; ++j) {
+      CTileDesc& d = h_ctiles[ctile_pos];
+      std::memset(&d, 0, sizeof(d));
+      d.tile_start = base + j * kLgTile; d.n_act = std::min(kLgTile, n - j * kLgTile); d.node_base = base; d.sites_id = T.sites_id;
+      h_ctile_tree[ctile_pos++] = k;
+    }
     h_trees[k] = T;
     fo->tree_muts[k] = (int64_t)m; fo->tree_fs[k] = (int64_t)fs;
     const RawIds& r = rid[k];
@@ -470,7 +504,8 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   h.num_trees = num_trees; h.num_nodes = (int32_t)N; h.num_tiles = (int32_t)tiles; h.num_sites_tables = num_sites_tables;
   h.trees = slab.at<TreeDev>(dbase, b_trees); h.sites = slab.at<SitesDev>(dbase, b_sites);
   h.tile_tree = slab.at<int32_t>(dbase, b_tile_tree); h.ctile_tree = slab.at<int32_t>(dbase, b_ctile_tree);
-  h.num_ctiles = (int32_t)ctiles; h.pad0 = 0;
+  h.num_ctiles = (int32_t)ctiles; h.pad0 = 0; h.ctiles = slab.at<CTileDesc>(dbase, b_ctiles);
+  h.fast_ctiles = slab.at<int32_t>(dbase, b_fastl); h.slow_ctiles = slab.at<int32_t>(dbase, b_slowl);
   h.node_id = slab.at<int32_t>(dbase, b_node_id); h.parent_pos = slab.at<int32_t>(dbase, b_parent);
   h.depth = slab.at<int32_t>(dbase, b_depth); h.subtree_size = slab.at<int32_t>(dbase, b_size);
   h.post_node = slab.at<int32_t>(dbase, b_post); h.pos_of_node = slab.at<int32_t>(dbase, b_pos);
@@ -479,12 +514,14 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   h.mut_code = slab.at<uint8_t>(dbase, b_mft); h.mut_t = slab.at<double>(dbase, b_mt);
   h.miss_off = slab.at<int32_t>(dbase, b_ioff); h.miss_se = slab.at<int2>(dbase, b_is);
   h.fs_off = slab.at<int32_t>(dbase, b_foff); h.fs_site = slab.at<int32_t>(dbase, b_fsite); h.fs_code = slab.at<uint8_t>(dbase, b_ffrom);
+  h.fsw = slab.at<int16_t>(dbase, b_fsw); h.fsw_stride = fsw_stride; h.pad1 = 0;
   fo->d_lambda = slab.at<double>(dbase, b_lambda); fo->d_nsmn = slab.at<int32_t>(dbase, b_nsmn);
   fo->d_tree_out = slab.at<double>(dbase, b_tout); fo->d_tree_iout = slab.at<int32_t>(dbase, b_tiout);
   fo->d_tile_agg = slab.at<double>(dbase, b_tagg); fo->d_tile_iagg = slab.at<int32_t>(dbase, b_tiagg);
   fo->d_tile_part = slab.at<double>(dbase, b_tpart); fo->d_tile_ipart = slab.at<int32_t>(dbase, b_tipart);
   fo->d_tile_flag = slab.at<uint32_t>(dbase, b_tflag); fo->d_tree_done = slab.at<uint32_t>(dbase, b_tdone);
   fo->d_ticket = slab.at<uint32_t>(dbase, b_ticket);
+  fo->d_strad_list = slab.at<int32_t>(dbase, b_strad); fo->d_sd_delta = slab.at<double>(dbase, b_sdd); fo->d_sd_n = slab.at<int32_t>(dbase, b_sdn);
 
   // ---- device side: Euler tour + list ranking -> DFS order; CSR offsets; lists ------------------------------------------
   FlattenParams P{};
@@ -492,6 +529,9 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   P.arcs[0] = tmp.at<int4>(tbase, w_arcs0); P.arcs[1] = tmp.at<int4>(tbase, w_arcs1);
   P.scan_tiles = tmp.at<int32_t>(tbase, w_scan);
   P.status = tmp.at<uint32_t>(tbase, w_status); P.max_depth = reinterpret_cast<int32_t*>(P.status + 4);
+  P.strad_list = fo->d_strad_list;
+  P.ctiles = const_cast<CTileDesc*>(h.ctiles); P.fast_ctiles = const_cast<int32_t*>(h.fast_ctiles);
+  P.slow_ctiles = const_cast<int32_t*>(h.slow_ctiles); P.num_ctiles = (int32_t)ctiles;
   P.num_nodes = (int32_t)N; P.total_muts = (int32_t)M; P.total_ivls = (int32_t)I; P.total_fs = (int32_t)F;
   P.node_id = const_cast<int32_t*>(h.node_id); P.parent_pos = const_cast<int32_t*>(h.parent_pos);
   P.depth = const_cast<int32_t*>(h.depth); P.subtree_size = const_cast<int32_t*>(h.subtree_size);
@@ -501,6 +541,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   P.mut_code = const_cast<uint8_t*>(h.mut_code); P.mut_t = h.mut_t;
   P.miss_off = const_cast<int32_t*>(h.miss_off); P.miss_se = const_cast<int2*>(h.miss_se);
   P.fs_off = const_cast<int32_t*>(h.fs_off); P.fs_site = const_cast<int32_t*>(h.fs_site); P.fs_code = const_cast<uint8_t*>(h.fs_code);
+  P.fsw = const_cast<int16_t*>(h.fsw); P.fsw_stride = fsw_stride;
   st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes);
   if (st != DPHY_OK) return fail(st);
   std::vector<int32_t> status(4 + num_trees, 0);
@@ -510,6 +551,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   st = flatten_status_to_error(ctx, (uint32_t)status[0]);
   if (st != DPHY_OK) return fail(st);
   for (int k = 0; k < num_trees; ++k) fo->tree_max_depth[k] = status[4 + k];
+  fo->num_strad = status[1]; fo->num_fast_ctiles = status[2]; fo->num_slow_ctiles = status[3];
   cudaFreeAsync(tbase, ctx->stream);
   *out = fo;
   return DPHY_OK;

@@ -53,7 +53,21 @@ struct SitesDev {
   int32_t nu_uniform;        // 1 if every nu_l == nu_const (no site-rate heterogeneity): munu needs no gather
   int32_t pad;
   double nu_const;
+  // 64-entry tables indexed by the packed event code (partition << 4 | x << 2 | y), refreshed by every set_evo:
+  double tab_dq[kMaxPartitions * 16];   // q_a(y) - q_a(x)
+  double tab_md[kMaxPartitions * 16];   // mu nu_const (q_a(y) - q_a(x))              (uniform nu only)
+  double tab_lq[kMaxPartitions * 16];   // log(mu nu_const q_xy), 0 on the diagonal   (uniform nu only)
+  double tab_muq[kMaxPartitions * 4];   // mu nu_const q_a(a)                          (uniform nu only)
 };
+
+// Per log-G tile descriptor: everything the streaming kernel needs to issue its bulk copies without touching memory first.
+struct alignas(16) CTileDesc {
+  int32_t tile_start, n_act, node_base, sites_id;   // written by the host at upload
+  int32_t m0, m1, i0, i1;                           // event ranges of the tile (CSR offsets at its first / past-last node)
+  int32_t f0, f1, cl0, cl1;                         // cl*: the tile's slice of the tree's post-order list (closers)
+  int32_t stage_bytes, pad0, pad1, pad2;            // upper bound of the bytes staged in shared memory for this tile
+};
+constexpr int kStageBytes = 36 * 1024;              // shared-memory stage of the streaming log-G kernel
 
 // Per-tree record.
 struct TreeDev {
@@ -82,6 +96,9 @@ struct ForestDev {
   const SitesDev* sites;
   const int32_t* tile_tree;     // [num_tiles]
   const int32_t* ctile_tree;    // [num_ctiles]
+  const CTileDesc* ctiles;      // [num_ctiles]
+  const int32_t* fast_ctiles;   // tiles whose staged bytes fit kStageBytes (streaming kernel) ...
+  const int32_t* slow_ctiles;   // ... and the others (direct-from-global kernel)
   // per device position
   const int32_t* node_id;       // host node index (within its tree)
   const int32_t* parent_pos;    // device position of the parent (-1 for a root)
@@ -98,6 +115,10 @@ struct ForestDev {
   const int32_t* fs_off;        // [num_nodes+1]
   const int32_t* fs_site;
   const uint8_t* fs_code;       // partition << 4 | ref << 2 | from
+  // from-state overrides folded per branch: fsw[p * fsw_stride + part*4 + a] = #(overrides whose reference state is a)
+  // - #(overrides whose from-state is a).  With uniform site rates the branch's delta-lambda term is a 4-term dot product.
+  const int16_t* fsw;
+  int32_t fsw_stride, pad1;
   // host-order lookup: device position of (tree, host node id) = pos_of_node[tree.node_base + id]
   const int32_t* pos_of_node;
 };
@@ -125,7 +146,9 @@ struct FlattenParams {
   const TreeDev* trees; const SitesDev* sites; const int32_t* tile_tree; const RawTreeDev* raw;
   int4* arcs[2];               // ping-pong Euler-tour arcs: (succ, #enter arcs to the end, #arcs to the end, -)
   int32_t* scan_tiles;         // [ceil(num_nodes / 1024) * 3]
-  uint32_t* status;            // [1] error bits
+  uint32_t* status;            // [0] error bits, [1] number of straddlers, [2] fast tiles, [3] slow tiles
+  CTileDesc* ctiles; int32_t* fast_ctiles; int32_t* slow_ctiles; int32_t num_ctiles;
+  int32_t* strad_list;         // (device position, sites table) of the nodes whose subtree closes in a later log-G tile than it opens
   int32_t* max_depth;          // [num_trees]
   int32_t num_nodes, total_muts, total_ivls, total_fs;
   // outputs (device order): the ForestDev arrays, writable
@@ -134,6 +157,7 @@ struct FlattenParams {
   int32_t* mut_off; int32_t* mut_site; uint8_t* mut_code; double* mut_t;
   int32_t* miss_off; int2* miss_se;
   int32_t* fs_off; int32_t* fs_site; uint8_t* fs_code;
+  int16_t* fsw; int32_t fsw_stride;
 };
 
 }  // namespace dphy
@@ -149,6 +173,7 @@ struct dphy_ctx {
   size_t pinned_bytes = 0;
   cudaEvent_t pinned_ev = nullptr;   // recorded after the last async copy out of `pinned`
   bool pinned_in_flight = false;
+  bool logg_attr_set = false;   // opt-in dynamic shared memory of the log-G tile kernel
 };
 
 struct dphy_sites {
@@ -178,6 +203,10 @@ struct dphy_forest {
   int32_t* d_nsmn = nullptr;    // [num_nodes]
   double* d_tree_out = nullptr; // [num_trees * 4]: root_prior, below_root, T, unused
   int32_t* d_tree_iout = nullptr; // [num_trees * 20]: num_muts, pad, num_muts_ab[16], ...
+  // straddlers (log-G): nodes whose subtree crosses a log-G tile boundary; their deltas are precomputed per evaluation
+  int32_t* d_strad_list = nullptr; int32_t num_strad = 0;
+  int32_t num_fast_ctiles = 0, num_slow_ctiles = 0;
+  double* d_sd_delta = nullptr; int32_t* d_sd_n = nullptr;
   // look-back workspace
   double* d_tile_agg = nullptr;     // [num_tiles]
   int32_t* d_tile_iagg = nullptr;   // [num_tiles]

@@ -112,6 +112,11 @@ __global__ void __launch_bounds__(kTile) flatten_nodes_kernel(FlattenParams P, i
   }
   P.mut_off[p] = cm; P.miss_off[p] = ci; P.fs_off[p] = cf;
   atomicMax(P.max_depth + tree, depth);
+  // straddler: closes (is subtracted from the running lambda) at position pre+size, which lies in a later log-G tile
+  if (pre + size < n && pre / kLgTile != (pre + size) / kLgTile) {
+    const uint32_t slot = atomicAdd(P.status + 1, 1u);
+    P.strad_list[2 * slot] = p; P.strad_list[2 * slot + 1] = T.sites_id;
+  }
 }
 
 // ---- (3b) exclusive scan of the three length arrays, in place, over the whole forest ------------------------------------------------------------
@@ -208,16 +213,45 @@ __global__ void __launch_bounds__(kTile) flatten_events_kernel(FlattenParams P) 
   }
   {
     const int src = R.fs_off[v], dst = P.fs_off[p], cnt = P.fs_off[p + 1] - dst;
+    int w[kMaxPartitions * 4];
+#pragma unroll
+    for (int k = 0; k < kMaxPartitions * 4; ++k) w[k] = 0;
     for (int i = 0; i < cnt; ++i) {
       int l = R.fs_site[src + i];
       const int from = R.fs_from[src + i];
       if (l < 0 || l >= L) { err |= kFlattenErrMissation; l = 0; }
       if (from > 3) err |= kFlattenErrFsState;
+      const int pt = S.part[l], rf = S.ref[l];
       P.fs_site[dst + i] = l;
-      P.fs_code[dst + i] = (uint8_t)(S.part[l] << 4 | S.ref[l] << 2 | (from & 3));
+      P.fs_code[dst + i] = (uint8_t)(pt << 4 | rf << 2 | (from & 3));
+#pragma unroll
+      for (int k = 0; k < kMaxPartitions * 4; ++k) w[k] += (int)(k == pt * 4 + rf) - (int)(k == pt * 4 + (from & 3));
     }
+#pragma unroll
+    for (int k = 0; k < kMaxPartitions * 4; ++k) if (k < P.fsw_stride) P.fsw[(size_t)p * P.fsw_stride + k] = (int16_t)w[k];
   }
   if (err) flag_error(P, err);
+}
+
+// ---- (4) log-G tile descriptors: event ranges, closer slice, staging size; fast / slow classification ---------------------------
+__global__ void __launch_bounds__(256) flatten_ctiles_kernel(FlattenParams P) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= P.num_ctiles) return;
+  CTileDesc d = P.ctiles[j];
+  const int p0 = d.tile_start, p1 = d.tile_start + d.n_act;
+  d.m0 = P.mut_off[p0]; d.m1 = P.mut_off[p1];
+  d.i0 = P.miss_off[p0]; d.i1 = P.miss_off[p1];
+  d.f0 = P.fs_off[p0]; d.f1 = P.fs_off[p1];
+  const int q_first = p0 - d.node_base, q_last = p1 - 1 - d.node_base;
+  d.cl0 = q_first == 0 ? 0 : (q_first - 1) - P.depth[p0 - 1];
+  d.cl1 = q_last - P.depth[p1 - 1];
+  const int n = d.n_act, nm = d.m1 - d.m0, ni = d.i1 - d.i0, nf = d.f1 - d.f0, nc = d.cl1 - d.cl0;
+  // every staged array may be over-fetched by < 32 bytes (16-byte alignment of both ends)
+  d.stage_bytes = (4 * n + 32) * 2 + (8 * n + 32) + (4 * (n + 1) + 32) * 2 + (2 * P.fsw_stride * n + 32) + (nm + 32) + (8 * nm + 32) +
+                  (8 * ni + 32) + (4 * nc + 32);
+  P.ctiles[j] = d;
+  if (d.stage_bytes <= kStageBytes && nm >= 0 && ni >= 0 && nf >= 0 && nc >= 0) P.fast_ctiles[atomicAdd(P.status + 2, 1u)] = j;
+  else P.slow_ctiles[atomicAdd(P.status + 3, 1u)] = j;
 }
 
 // Accepted displace moves (core/subrun.cpp:223-231,276-284): scatter new node times by host node index.
@@ -251,7 +285,8 @@ int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max
   flatten_scan_spine_kernel<<<1, 1024, 0, ctx->stream>>>(P, nst);
   flatten_scan_apply_kernel<<<nst, kTile, 0, ctx->stream>>>(P);
   flatten_events_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
-  ctx->launches += 6 + rounds;
+  flatten_ctiles_kernel<<<(P.num_ctiles + 255) / 256, 256, 0, ctx->stream>>>(P);
+  ctx->launches += 7 + rounds;
   return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch");
 }
 

@@ -1,29 +1,34 @@
-// kernels_logg.cu -- single-pass EMAT log-G evaluation for a whole forest (sm_100a).
+// kernels_logg.cu -- EMAT log-G evaluation for a whole forest (sm_100a).
 //
-// Replaces, for every tree of the forest in ONE launch:
+// Replaces, for every tree of the forest in ONE evaluation:
 //   calc_lambda_i                          core/phylo_tree_calc.cpp:420-436  (+ phylo_tree_calc.h:121-155)
 //   calc_num_sites_missing_at_every_node   core/phylo_tree_calc.cpp:67-76
 //   calc_log_root_prior                    core/phylo_tree_calc.cpp:467-504
 //   calc_log_G_below_root                  core/phylo_tree_calc.cpp:515-543  (+ phylo_tree_calc.h:185-206)
 //   calc_num_muts / calc_num_muts_ab / calc_T   core/phylo_tree_calc.cpp:577-597, :120-128
 //
-// Formulation.  The reference computes lambda_i with a pre-order walk (lambda_child = lambda_parent + delta of
-// the branch) and then sums branch terms in node-index order.  Here nodes are stored in DFS pre-order, so the set
-// of ancestors of position q is "everything opened at or before q and not yet closed".  With
-//     diff[q] = delta[q] - sum_{a : subtree of a ends right before q} delta[a]
-// lambda[q] = lambda_ref + inclusive_prefix_sum(diff)[q]: a plain scan.  The nodes closing at q are a contiguous
-// slice of the tree's post-order list: post_node[c(q-1) .. c(q)) with c(q) = q - depth[q].  Each CTA owns a tile of
-// kTile consecutive positions of one tree; it (1) computes delta / the mutation part of log G / missing-site counts
-// for its own nodes straight from the CSR lists, (2) forms diff (re-deriving delta for the few nodes that opened in
-// an earlier tile and close in this one), (3) block-scans and writes the tile-local lambda / nsmn (device order) plus
-// per-tile partial sums.  No CTA ever waits for another one: a second, tiny kernel (one CTA per tree) scans the tile
-// aggregates in tile order, folds log G = sum_tiles (A1 - prefix * A2) and evaluates the root prior, and a third
-// streaming kernel adds each tile's prefix to lambda_i / nsmn in place.  Fixed reduction shapes everywhere =>
-// bit-reproducible results.  Every input byte is read once (plus the re-derived closers).
+// Formulation.  The reference computes lambda_i with a pre-order walk (lambda_child = lambda_parent + delta of the
+// branch) and then sums branch terms in node-index order.  Here nodes are stored in DFS pre-order and the per-branch
+// lists in CSR in that same order, so
+//   * the events of consecutive nodes are consecutive in memory: every thread walks the short lists of its own two
+//     nodes with batched, predicated loads and the warp as a whole still streams whole cache lines;
+//   * D[q], the pre-order inclusive prefix of the branch deltas, is one block scan;
+//   * the nodes whose subtree closes right before position q are the contiguous slice post_node[c(q-1) .. c(q)),
+//     c(q) = q - depth[q], of the tree's post-order list, so the sum of the deltas of everything already closed is a
+//     prefix over that list evaluated at c(q);
+//   * lambda[q] = lambda_ref + D[q] - CL[c(q)]: two scans and two gathers.
+// Each CTA owns a tile of kLgTile consecutive positions of one tree and works on tile-local prefixes (magnitudes stay
+// O(tile), so differences of prefixes lose nothing that matters at the 1e-9 tolerance).  Closers that opened in an
+// earlier tile ("straddlers": subtree closes in a later tile than it opens; listed once at upload) get their delta from a tiny
+// pre-kernel, so no CTA ever waits for another one.  A one-CTA-per-tree kernel then scans the tile aggregates and
+// folds log G = sum_tiles (A1 - prefix * A2).  lambda_i / nsmn stay on the device as (tile-local value, tile prefix): each
+// is written exactly once per evaluation, and the getters add the two when the host asks for them.
+// Fixed reduction shapes everywhere => bit-reproducible results.
 #include "dphy_internal.h"
 #include "device_utils.cuh"
 
 #include <math_constants.h>
+#include <algorithm>
 #include <cstdlib>
 
 namespace dphy {
@@ -32,28 +37,71 @@ struct LogGParams {
   ForestDev f;
   double* lambda_out;    // [num_nodes] device order
   int32_t* nsmn_out;     // [num_nodes] device order
-  double* tile_agg;      // [num_tiles] sum of diff over the tile; overwritten by the tile's exclusive prefix in pass 2
+  double* tile_agg;      // [num_ctiles] sum of diff over the tile; overwritten by the tile's exclusive prefix in pass 2
   int32_t* tile_iagg;
-  double* tile_part;     // [num_tiles * 2]  (A1 = sum[-(lambda_ref+incl) len + g], A2 = sum len)
-  int32_t* tile_ipart;   // [num_tiles * 17] (num_muts, num_muts_ab[16])
+  double* tile_part;     // [num_ctiles * 2]  (A1 = sum[-(lambda_ref+incl) len + g], A2 = sum len)
+  int32_t* tile_ipart;   // [num_ctiles * 17] (num_muts, num_muts_ab[16])
   double* tree_out;      // [num_trees * 4]: log_root_prior, log_G_below_root, T, lambda_root
   int32_t* tree_iout;    // [num_trees * 20]: num_muts, 0, num_muts_ab[16], 0, 0
-  int32_t debug_mask;    // profiling only (DPHY_DEBUG_MASK): 1 skip mutations, 2 intervals, 4 from-states, 8 closers, 16 foreign closers
+  double* sd_delta;      // [num_nodes] delta-lambda of the straddlers (sparse)
+  int32_t* sd_n;         // [num_nodes] missing-site count of the straddlers (sparse)
+  const int32_t* strad_list;   // device positions of the straddlers
+  int32_t num_strad;
+  int32_t debug_mask;    // profiling only (DPHY_DEBUG_MASK): 1 skip mutations, 2 intervals, 4 from-states, 8 closers
 };
 
-// Capacity (events per chunk) of the flat event buffers in shared memory.
-constexpr int kEvCap = 1536;
+constexpr int kNW = kLgThreads / 32;
 
-// Sequential re-derivation of delta-lambda / missing-site count of ONE branch (used for the few "foreign closers":
-// nodes that opened in an earlier tile and close inside this one).  phylo_tree_calc.h:121-155.
-__device__ void branch_delta_seq(const ForestDev& f, const SitesDev& S, const double* __restrict__ s_dq,
-                                 const double* __restrict__ smu, int p, double& delta, int& nmiss) {
+// conflict-free smem slot of event s (each thread owns a run of consecutive events)
+__device__ __forceinline__ int pad_idx(int s) { return s + (s >> 3); }
+
+struct LogGSmem {
+  double dl[kLgTile];          // delta-lambda of every node of the tile
+  int dn[kLgTile];             // sites going missing on every branch of the tile
+  double clx[kLgTile + 2];     // exclusive prefix over the current chunk of the tile's closer list
+  int cln[kLgTile + 2];
+  double wsd[kNW * 3];
+  int wsi[kNW];
+  int ab[4 * 16];
+};
+
+// Exclusive block scan of up to (double, double, int) with ONE barrier pair; totals returned to every thread.
+template <bool kB, bool kC>
+__device__ __forceinline__ void block_scan_excl3(double& a, double& b, int& c, double& ta, double& tb, int& tc, LogGSmem& sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double ia = a, ib = b; int ic = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double ua = __shfl_up_sync(0xffffffffu, ia, o);
+    double ub = 0.0; int uc = 0;
+    if (kB) ub = __shfl_up_sync(0xffffffffu, ib, o);
+    if (kC) uc = __shfl_up_sync(0xffffffffu, ic, o);
+    if (lane >= o) { ia += ua; if (kB) ib += ub; if (kC) ic += uc; }
+  }
+  if (lane == 31) { sm.wsd[warp * 3] = ia; if (kB) sm.wsd[warp * 3 + 1] = ib; if (kC) sm.wsi[warp] = ic; }
+  __syncthreads();
+  double pa = 0.0, pb = 0.0; int pc = 0;
+  ta = 0.0; tb = 0.0; tc = 0;
+#pragma unroll
+  for (int w = 0; w < kNW; ++w) {          // fixed order: deterministic
+    const double wa = sm.wsd[w * 3];
+    if (w < warp) pa += wa;
+    ta += wa;
+    if (kB) { const double wb = sm.wsd[w * 3 + 1]; if (w < warp) pb += wb; tb += wb; }
+    if (kC) { const int wc = sm.wsi[w]; if (w < warp) pc += wc; tc += wc; }
+  }
+  a = pa + ia - a; if (kB) b = pb + ib - b; if (kC) c = pc + ic - c;
+  __syncthreads();                         // wsd / wsi may be rewritten by the next scan
+}
+
+// Sequential delta-lambda / missing-site count of ONE branch (phylo_tree_calc.h:121-155); used for the straddlers.
+__device__ void branch_delta_seq(const ForestDev& f, const SitesDev& S, int p, double& delta, int& nmiss) {
   const bool uni = S.nu_uniform != 0;
   double dm = 0.0;
   for (int i = f.mut_off[p]; i < f.mut_off[p + 1]; ++i) {
-    const int code = __ldg(f.mut_code + i);
-    const double mn = uni ? smu[code >> 4] : __ldg(S.munu + __ldg(f.mut_site + i));
-    dm += mn * s_dq[code];
+    const int code = __ldg(f.mut_code + i), pt = code >> 4, x = (code >> 2) & 3, y = code & 3;
+    const double mn = uni ? S.mu[pt] * S.nu_const : __ldg(S.munu + __ldg(f.mut_site + i));
+    dm += mn * ((-S.q[pt * 16 + y * 5]) - (-S.q[pt * 16 + x * 5]));
   }
   double dmi = 0.0;
   int nm = 0;
@@ -63,309 +111,482 @@ __device__ void branch_delta_seq(const ForestDev& f, const SitesDev& S, const do
     nm += se.y - se.x;
   }
   for (int i = f.fs_off[p]; i < f.fs_off[p + 1]; ++i) {
-    const int code = __ldg(f.fs_code + i);
-    const double mn = uni ? smu[code >> 4] : __ldg(S.munu + __ldg(f.fs_site + i));
-    dmi -= mn * s_dq[code];
+    const int code = __ldg(f.fs_code + i), pt = code >> 4, x = (code >> 2) & 3, y = code & 3;
+    const double mn = uni ? S.mu[pt] * S.nu_const : __ldg(S.munu + __ldg(f.fs_site + i));
+    dmi -= mn * ((-S.q[pt * 16 + y * 5]) - (-S.q[pt * 16 + x * 5]));
   }
   delta = dm + dmi;
   nmiss = nm;
 }
 
-// Flat-over-events + segmented-sum-per-node helper.  All threads of the CTA call it with the same [r0, r1).
-//   ev(i)          : thread-parallel over groups of kVec consecutive events starting at the kVec-aligned global index
-//                    i (vector loads); writes the contributions of events i..i+kVec-1 to smem slots (i - c0)..
-//                    Slots of events outside [r0, r1) hold garbage that is never read.
-//   acc(k, slot)   : the thread owning node (tid + k*kLgThreads) folds the slots of that node's CSR slice in list
-//                    order (deterministic)
-template <int kVec, typename EventFn, typename AccFn>
-__device__ __forceinline__ void flat_segmented(int r0, int r1, const int* __restrict__ s_off, int n_act, EventFn ev, AccFn acc) {
-  const int tid = threadIdx.x;
-  for (int c0 = r0 & ~(kVec - 1); c0 < r1; c0 += kEvCap) {
-    const int c1 = min(c0 + kEvCap, r1);
-    for (int i = c0 + kVec * tid; i < c1; i += kVec * kLgThreads) ev(i, i - c0);
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kLgNPT; ++k) {
-      const int q = tid + k * kLgThreads;
-      if (q < n_act) {
-        const int lo = max(s_off[q], c0), hi = min(s_off[q + 1], c1);
-        for (int i = lo; i < hi; ++i) acc(k, i - c0);
-      }
-    }
-    __syncthreads();
-  }
+// ---- pass 0: deltas of the straddlers (nodes whose subtree closes in a later log-G tile than it opens) ------------------------
+__global__ void __launch_bounds__(128) emat_log_G_straddler_kernel(const LogGParams P) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= P.num_strad) return;
+  const int2 ent = __ldg(reinterpret_cast<const int2*>(P.strad_list) + i);     // (device position, sites table)
+  double d; int n;
+  branch_delta_seq(P.f, P.f.sites[ent.y], ent.x, d, n);
+  P.sd_delta[ent.x] = d;
+  P.sd_n[ent.x] = n;
 }
 
-// Tile kernel: kLgTile consecutive device positions of one tree per CTA, kLgNPT nodes per thread (node q = tid +
-// k*kLgThreads, so every per-node global access is coalesced).
-__global__ void __launch_bounds__(kLgThreads) emat_log_G_kernel(const LogGParams P) {
-  __shared__ double s_dq[kMaxPartitions * 16];    // [part<<4 | x<<2 | y] = q_a(y) - q_a(x)
-  __shared__ double s_lq[kMaxPartitions * 16];    // [part<<4 | from<<2 | to] = log(mu nu_const q_from,to)   (uniform nu)
-  __shared__ double s_qft[kMaxPartitions * 16];   // q_ab
-  __shared__ double s_md[kMaxPartitions * 16];    // mu nu_const * s_dq (uniform nu)
-  __shared__ double s_mu[kMaxPartitions];
-  __shared__ __align__(16) double s_bufA[kEvCap];
-  __shared__ __align__(16) double s_bufB[kEvCap];
-  __shared__ int s_off_m[kLgTile + 1];
-  __shared__ int s_off_i[kLgTile + 1];
-  __shared__ int s_off_f[kLgTile + 1];
-  __shared__ double s_delta[kLgTile];             // delta per node, later diff / inclusive scan per node
-  __shared__ int s_nmiss[kLgTile];
-  __shared__ double s_wsd[kLgThreads / 32 * 3];
-  __shared__ int s_wsi[kLgThreads / 32];
-  __shared__ int s_ab[16];
+// ---- pass 1 --------------------------------------------------------------------------------------------------------------------
+// kLgTile consecutive device positions of one tree per tile; thread tid owns the two consecutive positions 2 tid and
+// 2 tid + 1.  Two kernels share the back half (scan of the deltas, closers, outputs):
+//   * emat_log_G_stream_kernel: persistent CTAs; the tile's node records, event lists and closer slice -- all contiguous
+//     ranges thanks to the DFS/CSR layout -- are staged in shared memory by 1-D bulk async copies (TMA engine,
+//     mbarrier-tracked, two stages deep) while the previous tile is being computed, so HBM streams continuously;
+//     per-node sums come from flat prefix scans over the staged events (no variable-length per-node loop).
+//   * emat_log_G_tile_kernel: one CTA per tile straight from global memory (thread-per-node list walks); handles tiles
+//     whose staging would not fit kStageBytes and forests with per-site rate heterogeneity.
+struct NodeRegs {
+  int par[2], dep[2], om[3];
+  double tN[2], tP[2];
+  double dm[2], es[2], dmi[2];
+  int nmiss[2];
+};
 
-  const ForestDev& f = P.f;
+template <bool kPostInSmem>
+__device__ __forceinline__ void tile_back_half(const LogGParams& P, LogGSmem& sm, const NodeRegs& R, int tile, int tile_start, int n_act,
+                                               int node_base, int cl0, int cl1, const int32_t* post /* post[j], j in [cl0, cl1) */,
+                                               double lambda_ref) {
   const int tid = threadIdx.x;
+  const int q0 = 2 * tid;
+  const bool act0 = q0 < n_act, act1 = q0 + 1 < n_act;
+  const int q_first = tile_start - node_base;
+  const double d0 = act0 ? R.dm[0] + R.dmi[0] : 0.0, d1 = act1 ? R.dm[1] + R.dmi[1] : 0.0;
+  const int n0 = act0 ? R.nmiss[0] : 0, n1 = act1 ? R.nmiss[1] : 0;
+  sm.dl[q0] = d0; sm.dl[q0 + 1] = d1;
+  sm.dn[q0] = n0; sm.dn[q0 + 1] = n1;
 
-  const int tile = blockIdx.x;
-  const int tree = f.ctile_tree[tile];
-  const TreeDev T = f.trees[tree];
-  const SitesDev& S = f.sites[T.sites_id];
-  const bool uni = S.nu_uniform != 0;
-  if (tid < 16) s_ab[tid] = 0;
-  if (tid < S.P) s_mu[tid] = S.mu[tid] * S.nu_const;
-  if (tid < S.P * 16) {
-    const int pt = tid >> 4, x = (tid >> 2) & 3, y = tid & 3;
-    const double qxy = S.q[tid];
-    s_qft[tid] = qxy;
-    const double dq = (-S.q[pt * 16 + y * 5]) - (-S.q[pt * 16 + x * 5]);
-    s_dq[tid] = dq;
-    s_md[tid] = S.mu[pt] * S.nu_const * dq;
-    s_lq[tid] = (x != y) ? log(S.mu[pt] * S.nu_const * qxy) : 0.0;
-  } else if (tid < kMaxPartitions * 16) {
-    s_dq[tid] = 0.0; s_md[tid] = 0.0; s_lq[tid] = 0.0; s_qft[tid] = 1.0;
-  }
-
-  const int tile_in_tree = tile - T.first_ctile;
-  const int tile_start = T.node_base + tile_in_tree * kLgTile;              // global device position
-  const int tile_end = min(tile_start + kLgTile, T.node_base + T.num_nodes);
-  const int n_act = tile_end - tile_start;
-  const bool has_root = tile_in_tree == 0;                                   // position 0 of a tree is its root
-
-  // ---- (0) node records + CSR offsets of the tile ---------------------------------------------------------------------
-  double tP[kLgNPT], tN[kLgNPT];
-  int par[kLgNPT], dep[kLgNPT];
-#pragma unroll
-  for (int k = 0; k < kLgNPT; ++k) {
-    const int q = tid + k * kLgThreads, p = tile_start + q;
-    par[k] = -1; dep[k] = 0; tP[k] = 0.0; tN[k] = 0.0;
-    if (q < n_act) {
-      par[k] = f.parent_pos[p];
-      dep[k] = f.depth[p];
-      tN[k] = f.t[p];
-      s_off_m[q] = f.mut_off[p]; s_off_i[q] = f.miss_off[p]; s_off_f[q] = f.fs_off[p];
-      if (q == n_act - 1) { s_off_m[n_act] = f.mut_off[p + 1]; s_off_i[n_act] = f.miss_off[p + 1]; s_off_f[n_act] = f.fs_off[p + 1]; }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < kLgNPT; ++k) if (par[k] >= 0) tP[k] = f.t[par[k]];
-  __syncthreads();
-
-  // ---- (1) branch terms: flat over the tile's events, segmented sum per node --------------------------------------------
-  double dm[kLgNPT], esum[kLgNPT], dmi[kLgNPT];
-  int nmiss[kLgNPT];
-#pragma unroll
-  for (int k = 0; k < kLgNPT; ++k) { dm[k] = 0.0; esum[k] = 0.0; dmi[k] = 0.0; nmiss[k] = 0; }
-  const int root_m1 = has_root ? s_off_m[1] : s_off_m[0];   // the root's list ("mutations" above the root) ends here
-  // mutations: dm_i = mu nu (q_to - q_from);  e_i = dm_i * t_i + log(mu nu q_from,to)   [g_node = sum e_i - t_P * dm]
+  // ---- D = inclusive prefix of the deltas over the tile's positions ------------------------------------------------------------
+  double D[2]; int Dn[2];
   {
-    const int m_lo = max(root_m1, s_off_m[0]), m_hi = s_off_m[n_act];
-    if (!(P.debug_mask & 1)) flat_segmented<4>(s_off_m[0], s_off_m[n_act], s_off_m, n_act,
-      [&](int i, int slot) {
-        const uchar4 c4 = __ldg(reinterpret_cast<const uchar4*>(f.mut_code + i));
-        const double2 ta = __ldg(reinterpret_cast<const double2*>(f.mut_t + i));
-        const double2 tb = __ldg(reinterpret_cast<const double2*>(f.mut_t + i + 2));
-        const int code[4] = {c4.x & 63, c4.y & 63, c4.z & 63, c4.w & 63};
-        const double tt[4] = {ta.x, ta.y, tb.x, tb.y};
-        double d[4], e[4];
-        if (uni) {
+    double a = d0 + d1, b = 0.0, ta, tb; int c = n0 + n1, tc2;
+    block_scan_excl3<false, true>(a, b, c, ta, tb, tc2, sm);       // also publishes dl / dn to the whole CTA
+    D[0] = a + d0; D[1] = D[0] + d1;
+    Dn[0] = c + n0; Dn[1] = Dn[0] + n1;
+  }
+
+  // ---- closers: prefix over the tile's slice of the post-order list, gathered at c(q) = q - depth[q] --------------------------
+  double CL[2] = {0.0, 0.0};
+  int CLn[2] = {0, 0};
+  {
+    const int myc0 = act0 ? (q_first + q0) - R.dep[0] : cl0, myc1 = act1 ? (q_first + q0 + 1) - R.dep[1] : cl0;
+    double carry = 0.0; int icarry = 0;
+    for (int c0 = cl0; c0 < cl1; c0 += kLgTile) {
+      double a[2] = {0.0, 0.0}; int n[2] = {0, 0};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) { d[u] = s_md[code[u]]; e[u] = d[u] * tt[u] + s_lq[code[u]]; }
-        } else {
-          const int4 l4 = __ldg(reinterpret_cast<const int4*>(f.mut_site + i));
-          const int ll[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const bool ok = i + u >= s_off_m[0] && i + u < m_hi;
-            const double mn = ok ? __ldg(S.munu + ll[u]) : 1.0;
-            d[u] = mn * s_dq[code[u]];
-            e[u] = d[u] * tt[u] + ((code[u] >> 2 & 3) != (code[u] & 3) ? log(mn * s_qft[code[u]]) : 0.0);
-          }
+      for (int u = 0; u < 2; ++u) {
+        const int j = c0 + 2 * tid + u;
+        if (j < cl1) {
+          const int p = kPostInSmem ? post[j] : __ldg(post + j);
+          const int qa = p - tile_start;
+          if (qa >= 0) { a[u] = sm.dl[qa]; n[u] = sm.dn[qa]; }
+          else { a[u] = __ldg(P.sd_delta + p); n[u] = __ldg(P.sd_n + p); }     // straddler: opened in an earlier tile
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (i + u >= m_lo && i + u < m_hi) atomicAdd(&s_ab[code[u] & 15], 1); else e[u] = 0.0;
-        }
-        *reinterpret_cast<double2*>(s_bufA + slot) = make_double2(d[0], d[1]);
-        *reinterpret_cast<double2*>(s_bufA + slot + 2) = make_double2(d[2], d[3]);
-        *reinterpret_cast<double2*>(s_bufB + slot) = make_double2(e[0], e[1]);
-        *reinterpret_cast<double2*>(s_bufB + slot + 2) = make_double2(e[2], e[3]);
-      },
-      [&](int k, int slot) { dm[k] += s_bufA[slot]; esum[k] += s_bufB[slot]; });
-  }
-  // missation intervals: -(cumQ[end] - cumQ[start]); count of sites going missing
-  {
-    const int i_lo = s_off_i[0], i_hi = s_off_i[n_act];
-    if (!(P.debug_mask & 2)) flat_segmented<2>(i_lo, i_hi, s_off_i, n_act,
-      [&](int i, int slot) {
-        const int4 se = __ldg(reinterpret_cast<const int4*>(f.miss_se + i));
-        const bool ok0 = i >= i_lo, ok1 = i + 1 < i_hi;
-        const double a0 = ok0 ? __ldg(S.cumQ + se.y) - __ldg(S.cumQ + se.x) : 0.0;
-        const double a1 = ok1 ? __ldg(S.cumQ + se.w) - __ldg(S.cumQ + se.z) : 0.0;
-        *reinterpret_cast<double2*>(s_bufA + slot) = make_double2(a0, a1);
-        *reinterpret_cast<int2*>(reinterpret_cast<int*>(s_bufB) + slot) = make_int2(se.y - se.x, se.w - se.z);
-      },
-      [&](int k, int slot) { dmi[k] -= s_bufA[slot]; nmiss[k] += reinterpret_cast<int*>(s_bufB)[slot]; });
-  }
-  // from-state overrides of missing sites
-  {
-    const int f_lo = s_off_f[0], f_hi = s_off_f[n_act];
-    if (!(P.debug_mask & 4)) flat_segmented<4>(f_lo, f_hi, s_off_f, n_act,
-      [&](int i, int slot) {
-        const uchar4 c4 = __ldg(reinterpret_cast<const uchar4*>(f.fs_code + i));
-        const int code[4] = {c4.x & 63, c4.y & 63, c4.z & 63, c4.w & 63};
-        double d[4];
-        if (uni) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) d[u] = s_md[code[u]];
-        } else {
-          const int4 l4 = __ldg(reinterpret_cast<const int4*>(f.fs_site + i));
-          const int ll[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const bool ok = i + u >= f_lo && i + u < f_hi;
-            d[u] = (ok ? __ldg(S.munu + ll[u]) : 1.0) * s_dq[code[u]];
-          }
-        }
-        *reinterpret_cast<double2*>(s_bufA + slot) = make_double2(d[0], d[1]);
-        *reinterpret_cast<double2*>(s_bufA + slot + 2) = make_double2(d[2], d[3]);
-      },
-      [&](int k, int slot) { dmi[k] -= s_bufA[slot]; });
-  }
-  double g[kLgNPT];
-#pragma unroll
-  for (int k = 0; k < kLgNPT; ++k) {
-    const int q = tid + k * kLgThreads;
-    g[k] = par[k] >= 0 ? esum[k] - tP[k] * dm[k] : 0.0;
-    if (q < kLgTile) { s_delta[q] = q < n_act ? dm[k] + dmi[k] : 0.0; s_nmiss[q] = q < n_act ? nmiss[k] : 0; }
-  }
-  __syncthreads();
-
-  // ---- (2) diff = own delta - deltas of the nodes whose subtree closes right before this position ---------------------------
-  // The tile's closers are one contiguous slice of the tree's post-order list; their deltas are gathered in parallel
-  // (in-tile from smem, foreign ones re-derived), then each position folds its own sub-slice in order.
-  double diff[kLgNPT];
-  int idiff[kLgNPT];
-  {
-    const int q_first = tile_start - T.node_base, q_last = tile_end - 1 - T.node_base;
-    const int cl0 = q_first == 0 ? 0 : (q_first - 1) - f.depth[tile_start - 1];
-    const int cl1 = (P.debug_mask & 8) ? cl0 : q_last - f.depth[tile_end - 1];
-    int my0[kLgNPT], my1[kLgNPT];
-#pragma unroll
-    for (int k = 0; k < kLgNPT; ++k) {
-      const int q = tid + k * kLgThreads, p = tile_start + q;
-      my0[k] = 0; my1[k] = 0;
-      diff[k] = q < n_act ? s_delta[q] : 0.0;
-      idiff[k] = q < n_act ? s_nmiss[q] : 0;
-      if (q < n_act) {
-        const int tq = p - T.node_base;
-        if (tq > 0) { my0[k] = (tq - 1) - f.depth[p - 1]; my1[k] = tq - dep[k]; }
       }
-    }
-    int* s_cn = reinterpret_cast<int*>(s_bufB);
-    for (int c0 = cl0; c0 < cl1; c0 += kEvCap) {
-      const int c1 = min(c0 + kEvCap, cl1);
-      for (int j = c0 + tid; j < c1; j += kLgThreads) {
-        const int a = f.post_node[T.node_base + j];
-        double da; int na;
-        if (a >= tile_start) { da = s_delta[a - tile_start]; na = s_nmiss[a - tile_start]; }
-        else if (P.debug_mask & 16) { da = 0.0; na = 0; }
-        else branch_delta_seq(f, S, s_dq, s_mu, a, da, na);
-        s_bufA[j - c0] = da; s_cn[j - c0] = na;
-      }
+      double sa = a[0] + a[1], sb = 0.0, ta, tb; int sc = n[0] + n[1], tc2;
+      block_scan_excl3<false, true>(sa, sb, sc, ta, tb, tc2, sm);
+      sm.clx[2 * tid] = carry + sa; sm.clx[2 * tid + 1] = carry + sa + a[0];
+      sm.cln[2 * tid] = icarry + sc; sm.cln[2 * tid + 1] = icarry + sc + n[0];
+      carry += ta; icarry += tc2;
+      if (tid == 0) { sm.clx[kLgTile] = carry; sm.cln[kLgTile] = icarry; }
       __syncthreads();
-#pragma unroll
-      for (int k = 0; k < kLgNPT; ++k) {
-        const int lo = max(my0[k], c0), hi = min(my1[k], c1);
-        for (int j = lo; j < hi; ++j) { diff[k] -= s_bufA[j - c0]; idiff[k] -= s_cn[j - c0]; }
-      }
+      if (myc0 > c0 && myc0 <= c0 + kLgTile) { CL[0] = sm.clx[myc0 - c0]; CLn[0] = sm.cln[myc0 - c0]; }
+      if (myc1 > c0 && myc1 <= c0 + kLgTile) { CL[1] = sm.clx[myc1 - c0]; CLn[1] = sm.cln[myc1 - c0]; }
       __syncthreads();
     }
   }
 
-  // ---- (3) inclusive scan of diff over the tile (position order): smem transpose -> blocked serial + block scan ------------
-#pragma unroll
-  for (int k = 0; k < kLgNPT; ++k) {
-    const int q = tid + k * kLgThreads;
-    s_delta[q] = diff[k]; s_nmiss[q] = idiff[k];
-  }
-  __syncthreads();
-  double tot; int itot;
-  {
-    double loc[kLgNPT]; int iloc[kLgNPT];
-    double run = 0.0; int irun = 0;
-#pragma unroll
-    for (int k = 0; k < kLgNPT; ++k) {
-      run += s_delta[tid * kLgNPT + k]; irun += s_nmiss[tid * kLgNPT + k];
-      loc[k] = run; iloc[k] = irun;
-    }
-    const double incl = block_scan_incl<double, kLgThreads>(run, s_wsd, &tot);
-    const int iincl = block_scan_incl<int, kLgThreads>(irun, s_wsi, &itot);
-    const double base = incl - run; const int ibase = iincl - irun;
-#pragma unroll
-    for (int k = 0; k < kLgNPT; ++k) { s_delta[tid * kLgNPT + k] = base + loc[k]; s_nmiss[tid * kLgNPT + k] = ibase + iloc[k]; }
-  }
-  __syncthreads();
-
-  // ---- (4) tile-local lambda_i / nsmn (device order); per-tile partial sums ----------------------------------------------------
-  const double lambda_ref = S.cumQ[S.L];
+  // ---- tile-local lambda_i / nsmn (device order); per-tile partial sums ----------------------------------------------------------
   double contrib = 0.0, tcontrib = 0.0;
   int nmut = 0;
 #pragma unroll
-  for (int k = 0; k < kLgNPT; ++k) {
-    const int q = tid + k * kLgThreads, p = tile_start + q;
+  for (int k = 0; k < 2; ++k) {
+    const int q = q0 + k, p = tile_start + q;
     if (q < n_act) {
-      const double lam_local = lambda_ref + s_delta[q];     // + the tile's prefix, added in pass 3
+      const double loc = D[k] - CL[k];
+      const int iloc = Dn[k] - CLn[k];
+      const double lam_local = lambda_ref + loc;     // + the tile's prefix (tile_agg after pass 2)
       P.lambda_out[p] = lam_local;
-      P.nsmn_out[p] = s_nmiss[q];
-      if (par[k] >= 0) {
-        const double len = tN[k] - tP[k];
-        contrib += -lam_local * len + g[k];
+      P.nsmn_out[p] = iloc;
+      if (q == n_act - 1) { P.tile_agg[tile] = loc; P.tile_iagg[tile] = iloc; }
+      if (R.par[k] >= 0) {
+        const double len = R.tN[k] - R.tP[k];
+        contrib += -lam_local * len + (R.es[k] - R.tP[k] * R.dm[k]);
         tcontrib += len;
-        nmut += s_off_m[q + 1] - s_off_m[q];
+        nmut += R.om[k + 1] - R.om[k];
       }
     }
   }
-  // three sums with one barrier pair
+  // three sums with one barrier
   {
     const int lane = tid & 31, warp = tid >> 5;
     contrib = warp_sum(contrib); tcontrib = warp_sum(tcontrib); nmut = warp_sum(nmut);
-    __syncthreads();
-    if (lane == 0) { s_wsd[warp * 3 + 0] = contrib; s_wsd[warp * 3 + 1] = tcontrib; s_wsd[warp * 3 + 2] = (double)nmut; }
+    if (lane == 0) { sm.wsd[warp * 3 + 0] = contrib; sm.wsd[warp * 3 + 1] = tcontrib; sm.wsd[warp * 3 + 2] = (double)nmut; }
     __syncthreads();
     if (warp == 0) {
-      double a = lane < kLgThreads / 32 ? s_wsd[lane * 3 + 0] : 0.0;
-      double b = lane < kLgThreads / 32 ? s_wsd[lane * 3 + 1] : 0.0;
-      double c = lane < kLgThreads / 32 ? s_wsd[lane * 3 + 2] : 0.0;
+      double a = lane < kNW ? sm.wsd[lane * 3 + 0] : 0.0;
+      double b = lane < kNW ? sm.wsd[lane * 3 + 1] : 0.0;
+      double c = lane < kNW ? sm.wsd[lane * 3 + 2] : 0.0;
       a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
       if (lane == 0) {
-        P.tile_agg[tile] = tot;
-        P.tile_iagg[tile] = itot;
         P.tile_part[tile * 2 + 0] = a;
         P.tile_part[tile * 2 + 1] = b;
         P.tile_ipart[tile * 17 + 0] = (int)c;
       }
     }
   }
-  if (tid < 16) P.tile_ipart[tile * 17 + 1 + tid] = s_ab[tid];
+  if (tid < 16) P.tile_ipart[tile * 17 + 1 + tid] = sm.ab[tid] + sm.ab[16 + tid] + sm.ab[32 + tid] + sm.ab[48 + tid];
+}
+
+// ---- pass 1, direct-from-global variant -------------------------------------------------------------------------------------------
+constexpr int kIvlBatch = 4;   // missation intervals in flight per node per round
+constexpr int kMutBatch = 2;   // mutations in flight per node per round
+
+__global__ void __launch_bounds__(kLgThreads, 4) emat_log_G_tile_kernel(const LogGParams P, const int32_t* __restrict__ tile_list) {
+  __shared__ LogGSmem sm;
+  const ForestDev& f = P.f;
+  const int tid = threadIdx.x;
+  const int tile = tile_list ? tile_list[blockIdx.x] : (int)blockIdx.x;
+  const int4 ct = __ldg(reinterpret_cast<const int4*>(f.ctiles + tile));
+  const int4 cl = __ldg(reinterpret_cast<const int4*>(f.ctiles + tile) + 2);
+  const int tile_start = ct.x, n_act = ct.y, node_base = ct.z;
+  const SitesDev& S = f.sites[ct.w];
+  const bool uni = S.nu_uniform != 0;
+  const double* __restrict__ cumQ = S.cumQ;
+  if (tid < 64) sm.ab[tid] = 0;
+
+  // ---- node records ----------------------------------------------------------------------------------------------------------------
+  NodeRegs R;
+  const int q0 = 2 * tid, p0 = tile_start + q0;
+  const bool act0 = q0 < n_act, act1 = q0 + 1 < n_act;
+  int oi[3] = {0, 0, 0}, of[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) { R.par[k] = -1; R.dep[k] = 0; R.tN[k] = 0.0; R.tP[k] = 0.0; R.dm[k] = 0.0; R.es[k] = 0.0; R.dmi[k] = 0.0; R.nmiss[k] = 0; }
+  R.om[0] = R.om[1] = R.om[2] = 0;
+  if (act0) {
+    R.par[0] = f.parent_pos[p0]; R.dep[0] = f.depth[p0]; R.tN[0] = f.t[p0];
+    R.om[0] = f.mut_off[p0]; oi[0] = f.miss_off[p0]; of[0] = f.fs_off[p0];
+    R.om[1] = f.mut_off[p0 + 1]; oi[1] = f.miss_off[p0 + 1]; of[1] = f.fs_off[p0 + 1];
+    R.om[2] = R.om[1]; oi[2] = oi[1]; of[2] = of[1];
+  }
+  if (act1) {
+    R.par[1] = f.parent_pos[p0 + 1]; R.dep[1] = f.depth[p0 + 1]; R.tN[1] = f.t[p0 + 1];
+    R.om[2] = f.mut_off[p0 + 2]; oi[2] = f.miss_off[p0 + 2]; of[2] = f.fs_off[p0 + 2];
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) if (R.par[k] >= 0) R.tP[k] = f.t[R.par[k]];
+
+  // ---- per-node sums over the branch lists (list order => deterministic) -----------------------------------------------------------
+  // missation intervals: -(cumQ[end] - cumQ[start]); count of sites going missing
+  if (!(P.debug_mask & 2)) {
+    const int c0 = oi[1] - oi[0], c1 = oi[2] - oi[1];
+    const int cmax = max(c0, c1);
+    for (int j = 0; j < cmax; j += kIvlBatch) {
+      int2 se[2][kIvlBatch];
+#pragma unroll
+      for (int u = 0; u < kIvlBatch; ++u) {
+        se[0][u] = j + u < c0 ? __ldg(f.miss_se + oi[0] + j + u) : make_int2(0, 0);
+        se[1][u] = j + u < c1 ? __ldg(f.miss_se + oi[1] + j + u) : make_int2(0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kIvlBatch; ++u) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          // (0,0) for an absent interval: cumQ[0] - cumQ[0] == 0 exactly, so the arithmetic stays branch-free
+          R.dmi[k] -= __ldg(cumQ + se[k][u].y) - __ldg(cumQ + se[k][u].x);
+          R.nmiss[k] += se[k][u].y - se[k][u].x;
+        }
+      }
+    }
+  }
+  // mutations: d_i = mu nu (q_to - q_from);  e_i = d_i * t_i + log(mu nu q_from,to)   [g_node = sum e_i - t_P * sum d_i]
+  if (!(P.debug_mask & 1)) {
+    const int c0 = R.om[1] - R.om[0], c1 = R.om[2] - R.om[1];
+    const int cmax = max(c0, c1);
+    for (int j = 0; j < cmax; j += kMutBatch) {
+#pragma unroll
+      for (int u = 0; u < kMutBatch; ++u) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (j + u < (k == 0 ? c0 : c1)) {
+            const int i = R.om[k] + j + u;
+            const int code = __ldg(f.mut_code + i) & 63;
+            const double tm = __ldg(f.mut_t + i);
+            double dd, lg;
+            if (uni) { dd = __ldg(S.tab_md + code); lg = __ldg(S.tab_lq + code); }
+            else {
+              const double mn = __ldg(S.munu + __ldg(f.mut_site + i));
+              dd = mn * __ldg(S.tab_dq + code);
+              lg = ((code >> 2) & 3) != (code & 3) ? log(mn * S.q[code]) : 0.0;
+            }
+            R.dm[k] += dd;
+            if (R.par[k] >= 0) {     // the root's list ("mutations" above the root) is not part of log G nor of the counts
+              R.es[k] += dd * tm + lg;
+              atomicAdd(&sm.ab[(tid & 3) * 16 + (code & 15)], 1);
+            }
+          }
+        }
+      }
+    }
+  }
+  // from-state overrides of missing sites: folded per-branch state counts when the site rates are uniform, lists otherwise
+  if (!(P.debug_mask & 4)) {
+    if (uni) {
+      for (int k2 = 0; k2 < f.fsw_stride; ++k2) {
+        const double mq = __ldg(S.tab_muq + k2);
+        if (act0) R.dmi[0] += mq * (double)__ldg(f.fsw + (size_t)p0 * f.fsw_stride + k2);
+        if (act1) R.dmi[1] += mq * (double)__ldg(f.fsw + (size_t)(p0 + 1) * f.fsw_stride + k2);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        for (int i = of[k]; i < of[k + 1]; ++i) {
+          const int code = __ldg(f.fs_code + i) & 63;
+          R.dmi[k] -= __ldg(S.munu + __ldg(f.fs_site + i)) * __ldg(S.tab_dq + code);
+        }
+      }
+    }
+  }
+  tile_back_half<false>(P, sm, R, tile, tile_start, n_act, node_base, cl.z, (P.debug_mask & 8) ? cl.z : cl.w,
+                        f.post_node + node_base, __ldg(cumQ + S.L));
+}
+
+// ---- pass 1, streaming variant ---------------------------------------------------------------------------------------------------------
+constexpr int kStages = 2;
+constexpr int kWorkBytes = 20 * 1024;          // per-interval site counts of the tile being computed (4 B each)
+
+struct StageMap {
+  CTileDesc d;
+  uint32_t o_par, o_dep, o_t, o_om, o_oi, o_fsw, o_mc, o_mt, o_ise, o_post, tile, pad;
+};
+
+struct StreamSmem {
+  LogGSmem lg;
+  unsigned long long bar[kStages];
+  StageMap map[kStages];
+  alignas(16) CTileDesc next_desc;   // descriptor of the tile that will refill the current stage (prefetched with cp.async)
+};
+constexpr size_t kStreamSmemBytes = ((sizeof(StreamSmem) + 127) / 128) * 128 + kWorkBytes + (size_t)kStages * kStageBytes;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One thread: plan the 10 bulk copies of a tile (16-byte aligned on both ends), arm the stage's mbarrier, issue them.
+__device__ __forceinline__ void issue_tile(const ForestDev& f, StreamSmem& sm, char* stage_base, int stage, int tile, const CTileDesc& d) {
+  StageMap& M = sm.map[stage];
+  M.d = d; M.tile = (uint32_t)tile;
+  const void* src[10]; uint32_t dst[10], bytes[10];
+  uint32_t cur = 0;
+  auto plan = [&](int k, const void* base, size_t first_byte, size_t nbytes, uint32_t& off_out) {
+    const uintptr_t s0 = (uintptr_t)base + first_byte, a0 = s0 & ~(uintptr_t)15;
+    const uint32_t lead = (uint32_t)(s0 - a0);
+    bytes[k] = nbytes ? (uint32_t)((lead + nbytes + 15) & ~(size_t)15) : 0u;
+    src[k] = (const void*)a0; dst[k] = cur; off_out = cur + lead; cur += bytes[k];
+  };
+  const size_t p0 = (size_t)d.tile_start, n = (size_t)d.n_act;
+  plan(0, f.parent_pos, 4 * p0, 4 * n, M.o_par);
+  plan(1, f.depth, 4 * p0, 4 * n, M.o_dep);
+  plan(2, f.t, 8 * p0, 8 * n, M.o_t);
+  plan(3, f.mut_off, 4 * p0, 4 * (n + 1), M.o_om);
+  plan(4, f.miss_off, 4 * p0, 4 * (n + 1), M.o_oi);
+  plan(5, f.fsw, 2 * (size_t)f.fsw_stride * p0, 2 * (size_t)f.fsw_stride * n, M.o_fsw);
+  plan(6, f.mut_code, (size_t)d.m0, (size_t)(d.m1 - d.m0), M.o_mc);
+  plan(7, f.mut_t, 8 * (size_t)d.m0, 8 * (size_t)(d.m1 - d.m0), M.o_mt);
+  plan(8, f.miss_se, 8 * (size_t)d.i0, 8 * (size_t)(d.i1 - d.i0), M.o_ise);
+  plan(9, f.post_node, 4 * (size_t)(d.node_base + d.cl0), 4 * (size_t)(d.cl1 - d.cl0), M.o_post);
+  fence_proxy_async();                     // the stage was last read through the generic proxy
+  mbar_arrive_expect_tx(&sm.bar[stage], cur);
+#pragma unroll
+  for (int k = 0; k < 10; ++k) if (bytes[k]) bulk_g2s(stage_base + dst[k], src[k], bytes[k], &sm.bar[stage]);
+}
+
+__global__ void __launch_bounds__(kLgThreads, 2) emat_log_G_stream_kernel(const LogGParams P, int num_tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smem_raw);
+  int* s_n = reinterpret_cast<int*>(smem_raw + ((sizeof(StreamSmem) + 127) / 128) * 128);
+  char* stages = reinterpret_cast<char*>(s_n) + kWorkBytes;
+  const ForestDev& f = P.f;
+  const int tid = threadIdx.x;
+  const int my_count = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&sm.bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int next_tile = -1;           // (thread 0) tile that refills the stage consumed in the current iteration
+  if (tid == 0) {
+    for (int s = 0; s < kStages && s < my_count; ++s) {
+      const int t = f.fast_ctiles[blockIdx.x + s * gridDim.x];
+      issue_tile(f, sm, stages + (size_t)s * kStageBytes, s, t, f.ctiles[t]);
+    }
+    if (kStages < my_count) next_tile = f.fast_ctiles[blockIdx.x + kStages * gridDim.x];
+  }
+  const int stride = f.fsw_stride;
+
+  for (int it = 0; it < my_count; ++it) {
+    const int stage = it % kStages;
+    const uint32_t parity = (uint32_t)(it / kStages) & 1u;
+    // the issuing thread prefetches the descriptor of the tile that will refill this stage (asynchronously, into smem)
+    // and looks up the one after it, so that neither load is exposed when the stage is released
+    const int refill = next_tile;
+    if (tid == 0) {
+      if (refill >= 0) {
+        const char* src = reinterpret_cast<const char*>(f.ctiles + refill);
+        const uint32_t dst = smem_u32(&sm.next_desc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * k), "l"(src + 16 * k) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      next_tile = it + kStages + 1 < my_count ? f.fast_ctiles[blockIdx.x + (it + kStages + 1) * gridDim.x] : -1;
+    }
+    if (tid < 64) sm.lg.ab[tid] = 0;
+    __syncthreads();
+    mbar_wait(&sm.bar[stage], parity);
+
+    const StageMap& M = sm.map[stage];
+    char* sb = stages + (size_t)stage * kStageBytes;
+    const int tile = (int)M.tile;
+    const int tile_start = M.d.tile_start, n_act = M.d.n_act, node_base = M.d.node_base;
+    const SitesDev& S = f.sites[M.d.sites_id];
+    const double* __restrict__ cumQ = S.cumQ;
+    const int* s_par = reinterpret_cast<const int*>(sb + M.o_par);
+    const int* s_dep = reinterpret_cast<const int*>(sb + M.o_dep);
+    const double* s_t = reinterpret_cast<const double*>(sb + M.o_t);
+    const int* s_om = reinterpret_cast<const int*>(sb + M.o_om);
+    const int* s_oi = reinterpret_cast<const int*>(sb + M.o_oi);
+    const int16_t* s_fsw = reinterpret_cast<const int16_t*>(sb + M.o_fsw);
+    const uint8_t* s_mc = reinterpret_cast<const uint8_t*>(sb + M.o_mc);
+    const double* s_mt = reinterpret_cast<const double*>(sb + M.o_mt);
+    int2* s_ise = reinterpret_cast<int2*>(sb + M.o_ise);
+    const int32_t* s_post = reinterpret_cast<const int32_t*>(sb + M.o_post);
+    const int m0 = M.d.m0, i0 = M.d.i0;
+    const int ni = (P.debug_mask & 2) ? 0 : M.d.i1 - i0;
+    const int cl0 = M.d.cl0, cl1 = (P.debug_mask & 8) ? cl0 : M.d.cl1;
+
+    // ---- (A) flat over the staged missation intervals: resolve the two cumQ gathers (the only global reads of the tile's
+    //      event work), in place: (start, end) -> cumQ[end] - cumQ[start]; the site counts go to the work buffer ----------------
+    {
+      double* s_a = reinterpret_cast<double*>(s_ise);
+      for (int i = tid; i < ni; i += 4 * kLgThreads) {
+        int2 se[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) se[u] = i + u * kLgThreads < ni ? s_ise[i + u * kLgThreads] : make_int2(0, 0);
+        double a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = __ldg(cumQ + se[u].y) - __ldg(cumQ + se[u].x);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i + u * kLgThreads < ni) { s_a[i + u * kLgThreads] = a[u]; s_n[i + u * kLgThreads] = se[u].y - se[u].x; }
+        }
+      }
+    }
+
+    // ---- node records (from the stage) ---------------------------------------------------------------------------------------------
+    NodeRegs R;
+    const int q0 = 2 * tid;
+    const bool act0 = q0 < n_act, act1 = q0 + 1 < n_act;
+    int oi[3] = {i0, i0, i0};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { R.par[k] = -1; R.dep[k] = 0; R.tN[k] = 0.0; R.tP[k] = 0.0; R.dm[k] = 0.0; R.es[k] = 0.0; R.dmi[k] = 0.0; R.nmiss[k] = 0; }
+    R.om[0] = R.om[1] = R.om[2] = m0;
+    if (act0) {
+      R.par[0] = s_par[q0]; R.dep[0] = s_dep[q0]; R.tN[0] = s_t[q0];
+      R.om[0] = s_om[q0]; oi[0] = s_oi[q0];
+      R.om[1] = s_om[q0 + 1]; oi[1] = s_oi[q0 + 1];
+      R.om[2] = R.om[1]; oi[2] = oi[1];
+    }
+    if (act1) {
+      R.par[1] = s_par[q0 + 1]; R.dep[1] = s_dep[q0 + 1]; R.tN[1] = s_t[q0 + 1];
+      R.om[2] = s_om[q0 + 2]; oi[2] = s_oi[q0 + 2];
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (R.par[k] >= 0) {
+        const int qp = R.par[k] - tile_start;
+        R.tP[k] = qp >= 0 ? s_t[qp] : __ldg(f.t + R.par[k]);   // the parent is usually in the same tile
+      }
+    }
+    // mutations: d_i = mu nu (q_to - q_from);  e_i = d_i * t_i + log(mu nu q_from,to)   [g_node = sum e_i - t_P * sum d_i]
+    if (!(P.debug_mask & 1)) {
+      const int c0 = R.om[1] - R.om[0], c1 = R.om[2] - R.om[1];
+      const int b0 = R.om[0] - m0, b1 = R.om[1] - m0;
+      const int cmax = max(c0, c1);
+      for (int j = 0; j < cmax; ++j) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (j < (k == 0 ? c0 : c1)) {
+            const int i = (k == 0 ? b0 : b1) + j;
+            const int code = s_mc[i] & 63;
+            const double dd = __ldg(S.tab_md + code);
+            R.dm[k] += dd;
+            if (R.par[k] >= 0) {     // the root's list ("mutations" above the root) is not part of log G nor of the counts
+              R.es[k] += dd * s_mt[i] + __ldg(S.tab_lq + code);
+              atomicAdd(&sm.lg.ab[(tid & 3) * 16 + (code & 15)], 1);
+            }
+          }
+        }
+      }
+    }
+    // from-state overrides, folded per branch at upload: delta -= mu nu sum_a q_a (#from == a) - (#ref == a)
+    if (!(P.debug_mask & 4)) {
+      for (int k2 = 0; k2 < stride; ++k2) {
+        const double mq = __ldg(S.tab_muq + k2);
+        if (act0) R.dmi[0] += mq * (double)s_fsw[(size_t)q0 * stride + k2];
+        if (act1) R.dmi[1] += mq * (double)s_fsw[(size_t)(q0 + 1) * stride + k2];
+      }
+    }
+    __syncthreads();                       // (A) is complete
+    // missation intervals of my two branches
+    {
+      const double* s_a = reinterpret_cast<const double*>(s_ise);
+      const int c0 = ni ? oi[1] - oi[0] : 0, c1 = ni ? oi[2] - oi[1] : 0;
+      const int b0 = oi[0] - i0, b1 = oi[1] - i0;
+      const int cmax = max(c0, c1);
+      for (int j = 0; j < cmax; ++j) {
+        if (j < c0) { R.dmi[0] -= s_a[b0 + j]; R.nmiss[0] += s_n[b0 + j]; }
+        if (j < c1) { R.dmi[1] -= s_a[b1 + j]; R.nmiss[1] += s_n[b1 + j]; }
+      }
+    }
+
+    tile_back_half<true>(P, sm.lg, R, tile, tile_start, n_act, node_base, cl0, cl1, s_post - cl0, __ldg(cumQ + S.L));
+
+    __syncthreads();                       // everybody is done with the stage (and with lg.ab)
+    if (tid == 0 && refill >= 0) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      issue_tile(f, sm, stages + (size_t)stage * kStageBytes, stage, refill, sm.next_desc);
+    }
+  }
 }
 
 // ---- pass 2: one CTA per tree -- exclusive scan of the tile aggregates (tile order), log G fold, tallies, root prior -----
-__global__ void __launch_bounds__(kTile) emat_log_G_tree_kernel(const LogGParams P) {
-  __shared__ double s_wsd[kTile / 32];
-  __shared__ int s_wsi[kTile / 32];
+constexpr int kTreeThreads = 1024;
+__global__ void __launch_bounds__(kTreeThreads) emat_log_G_tree_kernel(const LogGParams P) {
+  __shared__ double s_wsd[kTreeThreads / 32];
+  __shared__ int s_wsi[kTreeThreads / 32];
   __shared__ int s_cnt[kMaxPartitions * 4];
+  __shared__ int s_ab[16];
   __shared__ double s_carry;
   __shared__ int s_icarry;
   const ForestDev& f = P.f;
@@ -374,19 +595,18 @@ __global__ void __launch_bounds__(kTile) emat_log_G_tree_kernel(const LogGParams
   const TreeDev T = f.trees[tree];
   const SitesDev& S = f.sites[T.sites_id];
   if (tid == 0) { s_carry = 0.0; s_icarry = 0; }
+  if (tid < 16) s_ab[tid] = 0;
+  if (tid < kMaxPartitions * 4) s_cnt[tid] = tid < S.P * 4 ? S.ref_freq[tid] : 0;
   __syncthreads();
   double a1 = 0.0, a2 = 0.0; int m = 0;
-  int ab[16];
-#pragma unroll
-  for (int b = 0; b < 16; ++b) ab[b] = 0;
-  for (int j0 = 0; j0 < T.num_ctiles; j0 += kTile) {
+  for (int j0 = 0; j0 < T.num_ctiles; j0 += kTreeThreads) {
     const int j = T.first_ctile + j0 + tid;
     const bool ok = j0 + tid < T.num_ctiles;
     const double v = ok ? P.tile_agg[j] : 0.0;
     const int iv = ok ? P.tile_iagg[j] : 0;
     double tot; int itot;
-    const double incl = block_scan_incl<double, kTile>(v, s_wsd, &tot);
-    const int iincl = block_scan_incl<int, kTile>(iv, s_wsi, &itot);
+    const double incl = block_scan_incl<double, kTreeThreads>(v, s_wsd, &tot);
+    const int iincl = block_scan_incl<int, kTreeThreads>(iv, s_wsi, &itot);
     if (ok) {
       const double pre = s_carry + (incl - v);          // exclusive prefix of this tile
       const int ipre = s_icarry + (iincl - iv);
@@ -396,16 +616,19 @@ __global__ void __launch_bounds__(kTile) emat_log_G_tree_kernel(const LogGParams
       a1 += A1 - pre * A2;                              // sum over the tile of -(lambda_local + pre) len + g
       a2 += A2;
       m += P.tile_ipart[j * 17];
-#pragma unroll
-      for (int b = 0; b < 16; ++b) ab[b] += P.tile_ipart[j * 17 + 1 + b];
     }
     __syncthreads();
     if (tid == 0) { s_carry += tot; s_icarry += itot; }
     __syncthreads();
   }
-  a1 = block_sum<double, kTile>(a1, s_wsd);
-  a2 = block_sum<double, kTile>(a2, s_wsd);
-  m = block_sum<int, kTile>(m, s_wsi);
+  // num_muts_ab: 16 bins x tiles, summed by 16-thread groups (integer adds: order irrelevant)
+  for (int idx = tid; idx < T.num_ctiles * 16; idx += kTreeThreads) {
+    const int c = P.tile_ipart[(size_t)(T.first_ctile + (idx >> 4)) * 17 + 1 + (idx & 15)];
+    if (c) atomicAdd(&s_ab[idx & 15], c);
+  }
+  a1 = block_sum<double, kTreeThreads>(a1, s_wsd);
+  a2 = block_sum<double, kTreeThreads>(a2, s_wsd);
+  m = block_sum<int, kTreeThreads>(m, s_wsi);
   if (tid == 0) {
     P.tree_out[tree * 4 + 1] = a1;
     P.tree_out[tree * 4 + 2] = a2;
@@ -413,34 +636,27 @@ __global__ void __launch_bounds__(kTile) emat_log_G_tree_kernel(const LogGParams
     P.tree_iout[tree * 20 + 0] = m;
     P.tree_iout[tree * 20 + 1] = 0;
   }
-#pragma unroll
-  for (int b = 0; b < 16; ++b) {
-    const int c = block_sum<int, kTile>(ab[b], s_wsi);
-    if (tid == 0) P.tree_iout[tree * 20 + 2 + b] = c;
-  }
   // root prior (core/phylo_tree_calc.cpp:467-504): reference-sequence state counts per partition, adjusted by the
   // root's "mutations", missing sites and from-state overrides.
-  __syncthreads();
-  if (tid < kMaxPartitions * 4) s_cnt[tid] = tid < S.P * 4 ? S.ref_freq[tid] : 0;
-  __syncthreads();
   {
     const int r = T.node_base;   // the root is the first position of its tree
-    for (int i = f.mut_off[r] + tid; i < f.mut_off[r + 1]; i += kTile) {
+    for (int i = f.mut_off[r] + tid; i < f.mut_off[r + 1]; i += kTreeThreads) {
       const int code = f.mut_code[i]; const int pt = code >> 4;
       atomicSub(&s_cnt[pt * 4 + ((code >> 2) & 3)], 1);
       atomicAdd(&s_cnt[pt * 4 + (code & 3)], 1);
     }
     for (int i = f.miss_off[r]; i < f.miss_off[r + 1]; ++i) {
       const int2 se = f.miss_se[i]; const int s = se.x, e = se.y;
-      for (int l = s + tid; l < e; l += kTile) atomicSub(&s_cnt[S.part[l] * 4 + S.ref[l]], 1);
+      for (int l = s + tid; l < e; l += kTreeThreads) atomicSub(&s_cnt[S.part[l] * 4 + S.ref[l]], 1);
     }
-    for (int i = f.fs_off[r] + tid; i < f.fs_off[r + 1]; i += kTile) {
+    for (int i = f.fs_off[r] + tid; i < f.fs_off[r + 1]; i += kTreeThreads) {
       const int code = f.fs_code[i]; const int pt = code >> 4;
       atomicAdd(&s_cnt[pt * 4 + ((code >> 2) & 3)], 1);
       atomicSub(&s_cnt[pt * 4 + (code & 3)], 1);
     }
   }
   __syncthreads();
+  if (tid < 16) P.tree_iout[tree * 20 + 2 + tid] = s_ab[tid];
   if (tid == 0) {
     double lp = 0.0;
     bool impossible = false;
@@ -456,49 +672,41 @@ __global__ void __launch_bounds__(kTile) emat_log_G_tree_kernel(const LogGParams
   }
 }
 
-// ---- pass 3: add each tile's prefix to lambda_i / nsmn in place (streaming) ------------------------------------------------------
-__global__ void __launch_bounds__(kLgThreads) emat_log_G_finish_kernel(const LogGParams P) {
-  const ForestDev& f = P.f;
-  const int tile = blockIdx.x;
-  const TreeDev T = f.trees[f.ctile_tree[tile]];
-  const double pre = P.tile_agg[tile];
-  const int ipre = P.tile_iagg[tile];
-  const int p0 = T.node_base + (tile - T.first_ctile) * kLgTile;
-#pragma unroll
-  for (int k = 0; k < kLgNPT; ++k) {
-    const int p = p0 + threadIdx.x + k * kLgThreads;
-    if (p < T.node_base + T.num_nodes) {
-      P.lambda_out[p] += pre;
-      P.nsmn_out[p] += ipre;
-    }
-  }
-}
-
-// host-order gather for the getters: out[id] = src[pos_of_node[id]]
+// ---- getters: lambda_i / nsmn are kept on the device as (tile-local value, exclusive prefix of the tile); the two are
+// combined when somebody asks for them, in host node order: out[id] = local[pos] + prefix[tile(pos)].
 template <typename V>
-__global__ void gather_host_order_kernel(const int32_t* __restrict__ pos_of_node, const V* __restrict__ src, V* __restrict__ dst,
-                                         int node_base, int n) {
+__global__ void gather_host_order_kernel(const int32_t* __restrict__ pos_of_node, const V* __restrict__ src, const V* __restrict__ tile_prefix,
+                                         V* __restrict__ dst, int node_base, int first_ctile, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[node_base + pos_of_node[node_base + i]];
+  if (i < n) {
+    const int pos = pos_of_node[node_base + i];
+    dst[i] = src[node_base + pos] + tile_prefix[first_ctile + pos / kLgTile];
+  }
 }
 
 int gather_lambda_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, double* d_dst) {
   const TreeDev& T = fo->trees[tree];
-  gather_host_order_kernel<double><<<(T.num_nodes + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->d_lambda, d_dst, T.node_base, T.num_nodes);
+  gather_host_order_kernel<double><<<(T.num_nodes + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->d_lambda, fo->d_tile_agg, d_dst,
+                                                                                       T.node_base, T.first_ctile, T.num_nodes);
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "gather_host_order_kernel<double>");
 }
 int gather_nsmn_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* d_dst) {
   const TreeDev& T = fo->trees[tree];
-  gather_host_order_kernel<int32_t><<<(T.num_nodes + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->d_nsmn, d_dst, T.node_base, T.num_nodes);
+  gather_host_order_kernel<int32_t><<<(T.num_nodes + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->d_nsmn, fo->d_tile_iagg, d_dst,
+                                                                                        T.node_base, T.first_ctile, T.num_nodes);
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "gather_host_order_kernel<int>");
 }
 
 int launch_log_G(dphy_ctx* ctx, dphy_forest* fo) {
-  if (fo->h.num_tiles == 0) return DPHY_OK;
+  if (fo->h.num_ctiles == 0) return DPHY_OK;
   int st = refresh_sites(ctx, fo);
   if (st != DPHY_OK) return st;
+  if (!ctx->logg_attr_set) {
+    DPHY_CUDA(ctx, cudaFuncSetAttribute(emat_log_G_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmemBytes));
+    ctx->logg_attr_set = true;
+  }
   LogGParams P;
   P.f = fo->h;
   P.lambda_out = fo->d_lambda;
@@ -509,11 +717,35 @@ int launch_log_G(dphy_ctx* ctx, dphy_forest* fo) {
   P.tile_ipart = fo->d_tile_ipart;
   P.tree_out = fo->d_tree_out;
   P.tree_iout = fo->d_tree_iout;
+  P.sd_delta = fo->d_sd_delta;
+  P.sd_n = fo->d_sd_n;
+  P.strad_list = fo->d_strad_list;
+  P.num_strad = fo->num_strad;
   { const char* dm = getenv("DPHY_DEBUG_MASK"); P.debug_mask = dm ? atoi(dm) : 0; }
-  emat_log_G_kernel<<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
-  emat_log_G_tree_kernel<<<fo->h.num_trees, kTile, 0, ctx->stream>>>(P);
-  emat_log_G_finish_kernel<<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
-  ctx->launches += 3;
+  if (P.num_strad > 0) {
+    emat_log_G_straddler_kernel<<<(P.num_strad + 127) / 128, 128, 0, ctx->stream>>>(P);
+    ctx->launches += 1;
+  }
+  // the streaming kernel needs uniform site rates (it stages neither the event sites nor the munu gathers)
+  bool all_uniform = true;
+  for (const dphy_sites* s : fo->sites) all_uniform = all_uniform && s->h.nu_uniform;
+  if (P.debug_mask & 32) all_uniform = false;
+  if (all_uniform) {
+    if (fo->num_fast_ctiles > 0) {
+      const int grid = std::min(fo->num_fast_ctiles, 2 * ctx->sm_count);
+      emat_log_G_stream_kernel<<<grid, kLgThreads, kStreamSmemBytes, ctx->stream>>>(P, fo->num_fast_ctiles);
+      ctx->launches += 1;
+    }
+    if (fo->num_slow_ctiles > 0) {
+      emat_log_G_tile_kernel<<<fo->num_slow_ctiles, kLgThreads, 0, ctx->stream>>>(P, fo->h.slow_ctiles);
+      ctx->launches += 1;
+    }
+  } else {
+    emat_log_G_tile_kernel<<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);
+    ctx->launches += 1;
+  }
+  emat_log_G_tree_kernel<<<fo->h.num_trees, kTreeThreads, 0, ctx->stream>>>(P);
+  ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "emat_log_G kernels launch");
 }
 

@@ -12,7 +12,7 @@ for c in range(chains):
 fo = db.Forest(ctx, ems, tabs, sites_index=np.arange(chains))
 st = torch.cuda.ExternalStream(ctx.stream)
 print("alg bytes", fo.log_G_algorithmic_bytes, "device bytes", fo.device_bytes, "max_depth", info["max_depth"])
-for mask in [0, 1, 2, 4, 7, 8, 16, 15]:
+for mask in [0, 1, 2, 4, 8, 15, 32, 47]:
     os.environ["DPHY_DEBUG_MASK"] = str(mask)
     for _ in range(3): fo.eval_log_G()
     ctx.synchronize()
