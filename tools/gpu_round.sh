@@ -13,6 +13,6 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_r
 cat $OUT/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'emat_log_G_kernel|spr_scan_kernel|spr_emit_kernel|spr_setup_kernel' -s 8 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'emat_log_G_stream_kernel|emat_log_G_tile_kernel|spr_scan_kernel|spr_emit_kernel' -s 8 -c 4 \
   -o $OUT/prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --chains 16 > $OUT/ncu_full.log 2>&1
 ls -la $OUT
