@@ -137,6 +137,7 @@ def lib() -> C.CDLL:
     L.dphy_arena_stats.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.dphy_ctx_stream.argtypes = [vp]; L.dphy_ctx_stream.restype = vp
     L.dphy_ctx_launch_count.argtypes = [vp]; L.dphy_ctx_launch_count.restype = C.c_int64
+    L.dphy_ctx_set_log_G_path.argtypes = [vp, C.c_int]
     L.dphy_sites_upload.argtypes = [vp, C.POINTER(SitesHost), C.POINTER(vp)]
     L.dphy_sites_destroy.argtypes = [vp, vp]
     L.dphy_sites_set_evo.argtypes = [vp, vp, f64p, f64p, f64p, f64p]
@@ -343,6 +344,10 @@ class Context:
     @property
     def launches(self) -> int:
         return int(lib().dphy_ctx_launch_count(self._h))
+
+    def set_log_G_path(self, path: str = "auto"):
+        """'auto': folded fast path when every site table has uniform nu_l; 'general': always the per-event kernels."""
+        self.check(lib().dphy_ctx_set_log_G_path(self._h, {"auto": 0, "general": 1}[path]))
 
     def arena_stats(self):
         cap, hw = C.c_size_t(), C.c_size_t()

@@ -136,6 +136,12 @@ int dphy_arena_stats(const dphy_ctx* ctx, size_t* capacity, size_t* high_water) 
   return DPHY_OK;
 }
 
+int dphy_ctx_set_log_G_path(dphy_ctx* ctx, int path) {
+  if (!ctx || (path != DPHY_LOG_G_PATH_AUTO && path != DPHY_LOG_G_PATH_GENERAL)) return DPHY_ERR_INVALID_ARGUMENT;
+  ctx->logg_path = path;
+  return DPHY_OK;
+}
+
 void* dphy_ctx_stream(dphy_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t dphy_ctx_launch_count(const dphy_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -203,6 +209,7 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
   const int b_munu = slab.reserve(sizeof(double) * L), b_cumQ = slab.reserve(sizeof(double) * (L + 1));
   const int b_freq = slab.reserve(sizeof(int32_t) * kMaxPartitions * 4);
   const int b_cnu = slab.reserve(sizeof(double) * (size_t)P * 4 * (L + 1));
+  const int b_cref = slab.reserve(sizeof(int32_t) * (size_t)P * 4 * (L + 1));
   char* dbase = nullptr;
   if (cudaMalloc((void**)&dbase, slab.total) != cudaSuccess) { delete s; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMalloc(sites)"); }
   s->bytes = slab.total;
@@ -219,12 +226,14 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
   s->d_ref = slab.at<uint8_t>(dbase, b_ref); s->d_part = slab.at<uint8_t>(dbase, b_part); s->d_nu = slab.at<double>(dbase, b_nu);
   s->d_munu = slab.at<double>(dbase, b_munu); s->d_cumQ = slab.at<double>(dbase, b_cumQ);
   s->d_ref_freq = slab.at<int32_t>(dbase, b_freq); s->d_cum_nu_ba = slab.at<double>(dbase, b_cnu);
+  s->d_cref = slab.at<int32_t>(dbase, b_cref);
   s->h.L = L; s->h.P = P; s->h.ref = s->d_ref; s->h.part = s->d_part; s->h.nu = s->d_nu; s->h.munu = s->d_munu;
-  s->h.cumQ = s->d_cumQ; s->h.ref_freq = s->d_ref_freq;
+  s->h.cumQ = s->d_cumQ; s->h.ref_freq = s->d_ref_freq; s->h.cref = s->d_cref;
   cudaError_t e = cudaMemcpyAsync(dbase, hb, upload_bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) { cudaFree(dbase); delete s; return check_cuda(ctx, e, "H2D sites"); }
   release_pinned_async(ctx);
   st = launch_sites_derive(ctx, s);
+  if (st == DPHY_OK) st = launch_sites_ref_counts(ctx, s);
   if (st != DPHY_OK) { cudaStreamSynchronize(ctx->stream); cudaFree(dbase); delete s; return st; }
   *out = s;
   return DPHY_OK;
@@ -400,6 +409,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   const int b_ioff = slab.reserve(sizeof(int32_t) * (N + 1)), b_is = slab.reserve(sizeof(int2) * I + 64);
   const int b_foff = slab.reserve(sizeof(int32_t) * (N + 1)), b_fsite = slab.reserve(sizeof(int32_t) * F + 64), b_ffrom = slab.reserve(F + 64);
   const int b_fsw = slab.reserve(sizeof(int16_t) * (size_t)fsw_stride * N + 64);
+  const int b_bw = slab.reserve(sizeof(int32_t) * (size_t)fsw_stride * N + 64);
   // outputs + workspaces
   const int b_lambda = slab.reserve(sizeof(double) * N), b_nsmn = slab.reserve(sizeof(int32_t) * N);
   const int b_fastl = slab.reserve(sizeof(int32_t) * ctiles), b_slowl = slab.reserve(sizeof(int32_t) * ctiles);
@@ -515,6 +525,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   h.miss_off = slab.at<int32_t>(dbase, b_ioff); h.miss_se = slab.at<int2>(dbase, b_is);
   h.fs_off = slab.at<int32_t>(dbase, b_foff); h.fs_site = slab.at<int32_t>(dbase, b_fsite); h.fs_code = slab.at<uint8_t>(dbase, b_ffrom);
   h.fsw = slab.at<int16_t>(dbase, b_fsw); h.fsw_stride = fsw_stride; h.pad1 = 0;
+  h.bw = slab.at<int32_t>(dbase, b_bw);
   fo->d_lambda = slab.at<double>(dbase, b_lambda); fo->d_nsmn = slab.at<int32_t>(dbase, b_nsmn);
   fo->d_tree_out = slab.at<double>(dbase, b_tout); fo->d_tree_iout = slab.at<int32_t>(dbase, b_tiout);
   fo->d_tile_agg = slab.at<double>(dbase, b_tagg); fo->d_tile_iagg = slab.at<int32_t>(dbase, b_tiagg);
@@ -542,6 +553,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   P.miss_off = const_cast<int32_t*>(h.miss_off); P.miss_se = const_cast<int2*>(h.miss_se);
   P.fs_off = const_cast<int32_t*>(h.fs_off); P.fs_site = const_cast<int32_t*>(h.fs_site); P.fs_code = const_cast<uint8_t*>(h.fs_code);
   P.fsw = const_cast<int16_t*>(h.fsw); P.fsw_stride = fsw_stride;
+  P.bw = const_cast<int32_t*>(h.bw);
   st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes);
   if (st != DPHY_OK) return fail(st);
   std::vector<int32_t> status(4 + num_trees, 0);
@@ -553,6 +565,10 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   for (int k = 0; k < num_trees; ++k) fo->tree_max_depth[k] = status[4 + k];
   fo->num_strad = status[1]; fo->num_fast_ctiles = status[2]; fo->num_slow_ctiles = status[3];
   cudaFreeAsync(tbase, ctx->stream);
+  // structure-only outputs (nsmn, num_muts tallies) come from one general pass now; later evaluations of a forest whose site
+  // rates are uniform take the folded fast path and leave them untouched
+  st = launch_log_G_general(ctx, fo);
+  if (st != DPHY_OK) { cudaStreamSynchronize(ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo; return st; }
   *out = fo;
   return DPHY_OK;
 }

@@ -46,6 +46,7 @@ struct SitesDev {
   const double* munu;        // [L]  mu_{beta(l)} * nu_l
   const double* cumQ;        // [L+1] calc_cum_Q_l_for_sequence
   const int32_t* ref_freq;   // [P*4] state frequencies of the reference sequence per partition
+  const int32_t* cref;       // [P*4][L+1] cref[(b*4+a)*(L+1)+l] = #{l' < l : partition(l') == b, ref[l'] == a}  (structure only)
   double mu[kMaxPartitions];
   double pi[kMaxPartitions * 4];
   double q[kMaxPartitions * 16];     // q_ab
@@ -119,6 +120,12 @@ struct ForestDev {
   // - #(overrides whose from-state is a).  With uniform site rates the branch's delta-lambda term is a 4-term dot product.
   const int16_t* fsw;
   int32_t fsw_stride, pad1;
+  // every per-branch list folded into one weight vector (structure only, built at upload by fold_branch_weights_kernel):
+  //   bw[p * fsw_stride + part*4 + a] = #(mutations to a) - #(mutations from a) - #(sites going missing whose reference state is a)
+  //                                     + #(overrides whose reference state is a) - #(overrides whose from-state is a)
+  // With uniform site rates the branch's delta-lambda (core/phylo_tree_calc.h:121-155) is  sum_k mu nu q_a(a) bw[k];
+  // for the root, ref_freq + bw is the state count vector of calc_log_root_prior (core/phylo_tree_calc.cpp:467-504).
+  const int32_t* bw;
   // host-order lookup: device position of (tree, host node id) = pos_of_node[tree.node_base + id]
   const int32_t* pos_of_node;
 };
@@ -158,6 +165,7 @@ struct FlattenParams {
   int32_t* miss_off; int2* miss_se;
   int32_t* fs_off; int32_t* fs_site; uint8_t* fs_code;
   int16_t* fsw; int32_t fsw_stride;
+  int32_t* bw;
 };
 
 }  // namespace dphy
@@ -174,6 +182,7 @@ struct dphy_ctx {
   cudaEvent_t pinned_ev = nullptr;   // recorded after the last async copy out of `pinned`
   bool pinned_in_flight = false;
   bool logg_attr_set = false;   // opt-in dynamic shared memory of the log-G tile kernel
+  int logg_path = 0;            // DPHY_LOG_G_PATH_*: 0 auto (folded fast path when every site table has uniform nu), 1 general
 };
 
 struct dphy_sites {
@@ -183,6 +192,7 @@ struct dphy_sites {
   double* d_cumQ = nullptr; int32_t* d_ref_freq = nullptr;
   // per-(partition,state) cumulative nu tables for O(1) interval tallies (Ttwiddle): [P*4][L+1]
   double* d_cum_nu_ba = nullptr;
+  int32_t* d_cref = nullptr;    // [P*4][L+1] cumulative reference-state counts (structure only; built once at upload)
   size_t bytes = 0;
   uint64_t version = 1;         // bumped by set_evo; forests re-sync their SitesDev copies lazily
 };
@@ -216,6 +226,7 @@ struct dphy_forest {
   uint32_t* d_tree_done = nullptr;  // [num_trees] tiles finished (for last-tile reduction)
   uint32_t* d_ticket = nullptr;     // [1] dynamic tile ticket
   bool evaluated = false;
+  bool struct_valid = false;    // nsmn / num_muts tallies (structure-only outputs of the general log-G pass) are current
   uint32_t epoch = 0;           // look-back flag value of the current launch (flag == epoch means "published")
   std::vector<uint64_t> sites_version;
 };
@@ -227,8 +238,10 @@ int check_cuda(dphy_ctx* ctx, cudaError_t e, const char* what);
 
 // kernels_sites.cu
 int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s);
+int launch_sites_ref_counts(dphy_ctx* ctx, dphy_sites* s);
 // kernels_logg.cu
-int launch_log_G(dphy_ctx* ctx, dphy_forest* f);
+int launch_log_G(dphy_ctx* ctx, dphy_forest* f);            // picks the path (ctx->logg_path, site tables, struct_valid)
+int launch_log_G_general(dphy_ctx* ctx, dphy_forest* f);    // every output incl. nsmn and the num_muts tallies
 int gather_lambda_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, double* d_dst);
 int gather_nsmn_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* d_dst);
 int refresh_sites(dphy_ctx* ctx, dphy_forest* f);   // c_abi.cu

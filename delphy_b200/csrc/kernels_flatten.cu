@@ -233,6 +233,41 @@ __global__ void __launch_bounds__(kTile) flatten_events_kernel(FlattenParams P) 
   if (err) flag_error(P, err);
 }
 
+// ---- (3d) every per-branch list folded into one 4P-vector of state counts (see ForestDev::bw) --------------------------------------
+// Structure only: depends on the tree, its lists, the reference sequence and the partition map -- not on the evo model.
+__global__ void __launch_bounds__(kTile) fold_branch_weights_kernel(FlattenParams P) {
+  const int tile = blockIdx.x;
+  const int tree = P.tile_tree[tile];
+  const TreeDev T = P.trees[tree];
+  const SitesDev& S = P.sites[T.sites_id];
+  const int q = (tile - T.first_tile) * kTile + threadIdx.x;
+  if (q >= T.num_nodes) return;
+  const int p = T.node_base + q;
+  const int stride = P.fsw_stride;
+  const size_t Lp1 = (size_t)S.L + 1;
+  int w[kMaxPartitions * 4];
+#pragma unroll
+  for (int k = 0; k < kMaxPartitions * 4; ++k) w[k] = 0;
+  for (int i = P.mut_off[p]; i < P.mut_off[p + 1]; ++i) {
+    const int code = P.mut_code[i], pt = code >> 4, x = (code >> 2) & 3, y = code & 3;
+#pragma unroll
+    for (int k = 0; k < kMaxPartitions * 4; ++k) w[k] += (int)(k == pt * 4 + y) - (int)(k == pt * 4 + x);
+  }
+  for (int i = P.miss_off[p]; i < P.miss_off[p + 1]; ++i) {
+    const int2 se = P.miss_se[i];
+#pragma unroll
+    for (int k = 0; k < kMaxPartitions * 4; ++k)
+      if (k < S.P * 4) w[k] -= __ldg(S.cref + k * Lp1 + se.y) - __ldg(S.cref + k * Lp1 + se.x);
+  }
+  for (int i = P.fs_off[p]; i < P.fs_off[p + 1]; ++i) {
+    const int code = P.fs_code[i], pt = code >> 4, rf = (code >> 2) & 3, fr = code & 3;
+#pragma unroll
+    for (int k = 0; k < kMaxPartitions * 4; ++k) w[k] += (int)(k == pt * 4 + rf) - (int)(k == pt * 4 + fr);
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxPartitions * 4; ++k) if (k < stride) P.bw[(size_t)p * stride + k] = w[k];
+}
+
 // ---- (4) log-G tile descriptors: event ranges, closer slice, staging size; fast / slow classification ---------------------------
 __global__ void __launch_bounds__(256) flatten_ctiles_kernel(FlattenParams P) {
   const int j = blockIdx.x * 256 + threadIdx.x;
@@ -285,8 +320,9 @@ int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max
   flatten_scan_spine_kernel<<<1, 1024, 0, ctx->stream>>>(P, nst);
   flatten_scan_apply_kernel<<<nst, kTile, 0, ctx->stream>>>(P);
   flatten_events_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
+  fold_branch_weights_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
   flatten_ctiles_kernel<<<(P.num_ctiles + 255) / 256, 256, 0, ctx->stream>>>(P);
-  ctx->launches += 7 + rounds;
+  ctx->launches += 8 + rounds;
   return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch");
 }
 

@@ -672,6 +672,226 @@ __global__ void __launch_bounds__(kTreeThreads) emat_log_G_tree_kernel(const Log
   }
 }
 
+// ---- folded fast path (uniform site rates) ------------------------------------------------------------------------------------------------
+// With no site-rate heterogeneity every term of a branch's delta-lambda is  mu nu q_a(a)  times an integer that depends only
+// on the tree (ForestDev::bw, built once at upload): the kernel never touches the missation / from-state lists, and the
+// delta of a straddling closer is a 4P-term dot product gathered in place (no pre-pass).  The mutation lists are still
+// walked, in list order, for the  sum_m [ d_m (t_m - t_P) + log(mu nu q_from,to) ]  part of calc_branch_log_G
+// (core/phylo_tree_calc.h:185-206).  nsmn and the num_muts tallies do not depend on the evo model nor on times: they come
+// from the general pass that runs once at upload.  One CTA per tile of kLgTile positions, ~40 registers, 8.4 KB of shared
+// memory => 6-8 CTAs per SM keep enough independent loads in flight to cover HBM latency without any staging.
+struct FoldSmem {
+  double dl[kLgTile];
+  double clx[kLgTile + 2];
+  double wsd[kNW * 2];
+  double muq[kMaxPartitions * 4];
+};
+
+__device__ __forceinline__ double block_scan_excl1(double& a, double* wsd) {   // returns the block total; a <- exclusive prefix
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double ia = a;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double ua = __shfl_up_sync(0xffffffffu, ia, o);
+    if (lane >= o) ia += ua;
+  }
+  if (lane == 31) wsd[warp] = ia;
+  __syncthreads();
+  double pa = 0.0, ta = 0.0;
+#pragma unroll
+  for (int w = 0; w < kNW; ++w) {          // fixed order: deterministic
+    const double wa = wsd[w];
+    if (w < warp) pa += wa;
+    ta += wa;
+  }
+  a = pa + ia - a;
+  __syncthreads();                         // wsd may be rewritten by the next scan
+  return ta;
+}
+
+// delta-lambda of branch p from its folded weights; the same expression serves the tile's own nodes and the straddlers,
+// so what a closer subtracts is bit-identical to what its opening added
+__device__ __forceinline__ double folded_delta(const int32_t* __restrict__ bw, int stride, const double* muq, int p) {
+  const int4* w4 = reinterpret_cast<const int4*>(bw + (size_t)p * stride);
+  double d = 0.0;
+  for (int k = 0; k < stride; k += 4) {
+    const int4 w = __ldg(w4 + (k >> 2));
+    d += muq[k] * (double)w.x + muq[k + 1] * (double)w.y + muq[k + 2] * (double)w.z + muq[k + 3] * (double)w.w;
+  }
+  return d;
+}
+
+__global__ void __launch_bounds__(kLgThreads, 5) emat_log_G_folded_kernel(const LogGParams P) {
+  __shared__ FoldSmem sm;
+  const ForestDev& f = P.f;
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int4 ct = __ldg(reinterpret_cast<const int4*>(f.ctiles + tile));
+  const int4 cl = __ldg(reinterpret_cast<const int4*>(f.ctiles + tile) + 2);
+  const int tile_start = ct.x, n_act = ct.y, node_base = ct.z;
+  const SitesDev& S = f.sites[ct.w];
+  const int stride = f.fsw_stride;
+  if (tid < kMaxPartitions * 4) sm.muq[tid] = S.tab_muq[tid];
+  __syncthreads();
+
+  // ---- node records: 2 consecutive positions per thread ------------------------------------------------------------------------------
+  const int q0 = 2 * tid, p0 = tile_start + q0;
+  const bool act0 = q0 < n_act, act1 = q0 + 1 < n_act;
+  int dep[2] = {0, 0};
+  bool nonroot[2] = {false, false};
+  double len[2] = {0.0, 0.0}, d[2] = {0.0, 0.0}, g[2] = {0.0, 0.0};
+  {
+    int par[2] = {-1, -1}, om[3] = {0, 0, 0};
+    double tN[2] = {0.0, 0.0};
+    if (act0) {
+      par[0] = __ldg(f.parent_pos + p0); dep[0] = __ldg(f.depth + p0); tN[0] = f.t[p0];
+      om[0] = __ldg(f.mut_off + p0); om[1] = __ldg(f.mut_off + p0 + 1); om[2] = om[1];
+      d[0] = folded_delta(f.bw, stride, sm.muq, p0);
+    }
+    if (act1) {
+      par[1] = __ldg(f.parent_pos + p0 + 1); dep[1] = __ldg(f.depth + p0 + 1); tN[1] = f.t[p0 + 1];
+      om[2] = __ldg(f.mut_off + p0 + 2);
+      d[1] = folded_delta(f.bw, stride, sm.muq, p0 + 1);
+    }
+    // ---- mutations (list order): g_node = sum_m [d_m t_m + log(mu nu q_from,to)] - t_P sum_m d_m ---------------------------------------
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (par[k] >= 0) {       // the root's list ("mutations" above the root) is not part of log G
+        const double tP = f.t[par[k]];
+        double es = 0.0, ds = 0.0;
+        for (int i = om[k]; i < om[k + 1]; ++i) {
+          const int code = __ldg(f.mut_code + i) & 63;
+          const double dd = __ldg(S.tab_md + code);
+          es += dd * f.mut_t[i] + __ldg(S.tab_lq + code);
+          ds += dd;
+        }
+        g[k] = es - tP * ds;
+        len[k] = tN[k] - tP;
+        nonroot[k] = true;
+      }
+    }
+  }
+
+  // ---- D = inclusive prefix of the deltas over the tile's positions ----------------------------------------------------------------------
+  sm.dl[q0] = d[0]; sm.dl[q0 + 1] = d[1];
+  double D0, D1;
+  {
+    double a = d[0] + d[1];
+    block_scan_excl1(a, sm.wsd);            // its barriers also publish dl to the whole CTA
+    D0 = a + d[0]; D1 = D0 + d[1];
+  }
+
+  // ---- closers: prefix over the tile's slice of the post-order list, gathered at c(q) = q - depth[q] ----------------------------------
+  double CL0 = 0.0, CL1 = 0.0;
+  {
+    const int cl0 = cl.z, cl1 = cl.w;
+    const int q_first = tile_start - node_base;
+    const int myc0 = act0 ? (q_first + q0) - dep[0] : cl0, myc1 = act1 ? (q_first + q0 + 1) - dep[1] : cl0;
+    const int32_t* __restrict__ post = f.post_node + node_base;
+    double carry = 0.0;
+    for (int c0 = cl0; c0 < cl1; c0 += kLgTile) {
+      double a[2] = {0.0, 0.0};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = c0 + 2 * tid + u;
+        if (j < cl1) {
+          const int p = __ldg(post + j);
+          const int qa = p - tile_start;
+          a[u] = qa >= 0 ? sm.dl[qa] : folded_delta(f.bw, stride, sm.muq, p);   // straddler: opened in an earlier tile
+        }
+      }
+      double sa = a[0] + a[1];
+      const double ta = block_scan_excl1(sa, sm.wsd);
+      sm.clx[2 * tid] = carry + sa; sm.clx[2 * tid + 1] = carry + sa + a[0];
+      carry += ta;
+      if (tid == 0) sm.clx[kLgTile] = carry;
+      __syncthreads();
+      if (myc0 > c0 && myc0 <= c0 + kLgTile) CL0 = sm.clx[myc0 - c0];
+      if (myc1 > c0 && myc1 <= c0 + kLgTile) CL1 = sm.clx[myc1 - c0];
+      __syncthreads();
+    }
+  }
+
+  // ---- tile-local lambda_i (device order); per-tile partial sums ---------------------------------------------------------------------------
+  const double lambda_ref = __ldg(S.cumQ + S.L);
+  double contrib = 0.0, tcontrib = 0.0;
+  if (act0) {
+    const double loc = D0 - CL0, lam = lambda_ref + loc;       // + the tile's prefix (tile_agg after pass 2)
+    P.lambda_out[p0] = lam;
+    if (q0 == n_act - 1) P.tile_agg[tile] = loc;
+    if (nonroot[0]) { contrib += -lam * len[0] + g[0]; tcontrib += len[0]; }
+  }
+  if (act1) {
+    const double loc = D1 - CL1, lam = lambda_ref + loc;
+    P.lambda_out[p0 + 1] = lam;
+    if (q0 + 1 == n_act - 1) P.tile_agg[tile] = loc;
+    if (nonroot[1]) { contrib += -lam * len[1] + g[1]; tcontrib += len[1]; }
+  }
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    contrib = warp_sum(contrib); tcontrib = warp_sum(tcontrib);
+    if (lane == 0) { sm.wsd[warp * 2 + 0] = contrib; sm.wsd[warp * 2 + 1] = tcontrib; }
+    __syncthreads();
+    if (warp == 0) {
+      double a = lane < kNW ? sm.wsd[lane * 2 + 0] : 0.0;
+      double b = lane < kNW ? sm.wsd[lane * 2 + 1] : 0.0;
+      a = warp_sum(a); b = warp_sum(b);
+      if (lane == 0) { P.tile_part[tile * 2 + 0] = a; P.tile_part[tile * 2 + 1] = b; }
+    }
+  }
+}
+
+// pass 2 of the folded path: one CTA per tree -- exclusive scan of the tile aggregates, log G fold, root prior from the root's
+// folded weights (ref_freq + bw[root] is exactly the state count vector of core/phylo_tree_calc.cpp:467-504).
+__global__ void __launch_bounds__(kTreeThreads) emat_log_G_folded_tree_kernel(const LogGParams P) {
+  __shared__ double s_wsd[kTreeThreads / 32];
+  __shared__ double s_carry;
+  const ForestDev& f = P.f;
+  const int tid = threadIdx.x;
+  const int tree = blockIdx.x;
+  const TreeDev T = f.trees[tree];
+  const SitesDev& S = f.sites[T.sites_id];
+  if (tid == 0) s_carry = 0.0;
+  __syncthreads();
+  double a1 = 0.0, a2 = 0.0;
+  for (int j0 = 0; j0 < T.num_ctiles; j0 += kTreeThreads) {
+    const int j = T.first_ctile + j0 + tid;
+    const bool ok = j0 + tid < T.num_ctiles;
+    const double v = ok ? P.tile_agg[j] : 0.0;
+    double tot;
+    const double incl = block_scan_incl<double, kTreeThreads>(v, s_wsd, &tot);
+    if (ok) {
+      const double pre = s_carry + (incl - v);          // exclusive prefix of this tile
+      P.tile_agg[j] = pre;
+      const double A1 = P.tile_part[j * 2 + 0], A2 = P.tile_part[j * 2 + 1];
+      a1 += A1 - pre * A2;                              // sum over the tile of -(lambda_local + pre) len + g
+      a2 += A2;
+    }
+    __syncthreads();
+    if (tid == 0) s_carry += tot;
+    __syncthreads();
+  }
+  a1 = block_sum<double, kTreeThreads>(a1, s_wsd);
+  a2 = block_sum<double, kTreeThreads>(a2, s_wsd);
+  if (tid == 0) {
+    P.tree_out[tree * 4 + 1] = a1;
+    P.tree_out[tree * 4 + 2] = a2;
+    P.tree_out[tree * 4 + 3] = S.cumQ[S.L] + 0.0;
+    const int32_t* wr = f.bw + (size_t)T.node_base * f.fsw_stride;   // the root is the first position of its tree
+    double lp = 0.0;
+    bool impossible = false;
+    for (int b = 0; b < S.P; ++b) {
+      for (int a = 0; a < 4; ++a) {
+        const double pi = S.pi[b * 4 + a];
+        const int c = S.ref_freq[b * 4 + a] + wr[b * 4 + a];
+        if (pi != 0.0) lp += c * log(pi);
+        else if (c != 0) impossible = true;
+      }
+    }
+    P.tree_out[tree * 4 + 0] = impossible ? -CUDART_INF : lp;
+  }
+}
+
 // ---- getters: lambda_i / nsmn are kept on the device as (tile-local value, exclusive prefix of the tile); the two are
 // combined when somebody asks for them, in host node order: out[id] = local[pos] + prefix[tile(pos)].
 template <typename V>
@@ -699,7 +919,7 @@ int gather_nsmn_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* d_
   return check_cuda(ctx, cudaGetLastError(), "gather_host_order_kernel<int>");
 }
 
-int launch_log_G(dphy_ctx* ctx, dphy_forest* fo) {
+int launch_log_G_general(dphy_ctx* ctx, dphy_forest* fo) {
   if (fo->h.num_ctiles == 0) return DPHY_OK;
   int st = refresh_sites(ctx, fo);
   if (st != DPHY_OK) return st;
@@ -746,7 +966,34 @@ int launch_log_G(dphy_ctx* ctx, dphy_forest* fo) {
   }
   emat_log_G_tree_kernel<<<fo->h.num_trees, kTreeThreads, 0, ctx->stream>>>(P);
   ctx->launches += 1;
-  return check_cuda(ctx, cudaGetLastError(), "emat_log_G kernels launch");
+  st = check_cuda(ctx, cudaGetLastError(), "emat_log_G kernels launch");
+  if (st == DPHY_OK) fo->struct_valid = true;
+  return st;
+}
+
+static int launch_log_G_folded(dphy_ctx* ctx, dphy_forest* fo) {
+  int st = refresh_sites(ctx, fo);
+  if (st != DPHY_OK) return st;
+  LogGParams P{};
+  P.f = fo->h;
+  P.lambda_out = fo->d_lambda;
+  P.tile_agg = fo->d_tile_agg;
+  P.tile_part = fo->d_tile_part;
+  P.tree_out = fo->d_tree_out;
+  emat_log_G_folded_kernel<<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
+  emat_log_G_folded_tree_kernel<<<fo->h.num_trees, kTreeThreads, 0, ctx->stream>>>(P);
+  ctx->launches += 2;
+  return check_cuda(ctx, cudaGetLastError(), "emat_log_G folded kernels launch");
+}
+
+int launch_log_G(dphy_ctx* ctx, dphy_forest* fo) {
+  if (fo->h.num_ctiles == 0) return DPHY_OK;
+  bool all_uniform = true;
+  for (const dphy_sites* s : fo->sites) all_uniform = all_uniform && s->h.nu_uniform;
+  // the folded path leaves nsmn and the num_muts tallies alone: they must have been produced by a general pass since the
+  // last structural change (dphy_forest_upload runs one)
+  if (ctx->logg_path == 0 && all_uniform && fo->struct_valid) return launch_log_G_folded(ctx, fo);
+  return launch_log_G_general(ctx, fo);
 }
 
 }  // namespace dphy

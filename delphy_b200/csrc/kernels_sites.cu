@@ -77,6 +77,34 @@ __global__ void __launch_bounds__(kScanThreads) sites_derive_kernel(
   }
 }
 
+// Cumulative reference-state counts per (partition, state): cref[(b*4+a)*(L+1) + l] = #{l' < l : beta(l') == b, ref[l'] == a}.
+// Structure only (reference sequence + partition map), so it is built once per sites table.  One CTA per (b, a) row.
+// fold_branch_weights_kernel uses it to turn a missation interval into the 4P state counts of the sites it hides.
+__global__ void __launch_bounds__(kScanThreads) sites_ref_counts_kernel(int L, const uint8_t* __restrict__ ref,
+                                                                        const uint8_t* __restrict__ part, int32_t* __restrict__ cref) {
+  __shared__ int s_ws[kScanThreads / 32];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const int chunk = (L + kScanThreads - 1) / kScanThreads;
+  const int l0 = min(tid * chunk, L), l1 = min(l0 + chunk, L);
+  int c = 0;
+  for (int l = l0; l < l1; ++l) c += (part[l] * 4 + ref[l] == k);
+  int tot;
+  const int incl = block_scan_incl<int, kScanThreads>(c, s_ws, &tot);
+  int run = incl - c;
+  int32_t* out = cref + (size_t)k * (L + 1);
+  if (tid == 0) out[0] = 0;
+  for (int l = l0; l < l1; ++l) {
+    run += (part[l] * 4 + ref[l] == k);
+    out[l + 1] = run;
+  }
+}
+
+int launch_sites_ref_counts(dphy_ctx* ctx, dphy_sites* s) {
+  sites_ref_counts_kernel<<<s->P * 4, kScanThreads, 0, ctx->stream>>>(s->L, s->d_ref, s->d_part, s->d_cref);
+  ctx->launches += 1;
+  return check_cuda(ctx, cudaGetLastError(), "sites_ref_counts_kernel launch");
+}
+
 int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s) {
   // mu and q live in the SitesDev host mirror; stage them through the arena
   size_t mark = ctx->arena.mark();

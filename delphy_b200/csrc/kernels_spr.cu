@@ -36,7 +36,7 @@ struct SprStudy {
   double t_X, lambda_X, f, t_max_tip;
   // slab offsets in bytes
   int64_t off_xtab, off_xkey, off_path, off_xpath, off_H, off_C, off_KB, off_seg, off_regions, off_xd_site, off_xd_to, off_xm_start,
-      off_xm_end, off_part;
+      off_xm_end, off_part, off_pae;
   int32_t region_cap, path_cap;
   // ---- derived (spr_setup_kernel) ----
   int32_t node_base, num_nodes, num_tiles, L;
@@ -44,6 +44,8 @@ struct SprStudy {
   int32_t pos0, k0, n0, root_pos;
   int32_t path_len, xpath_len;
   int32_t num_missing, error;
+  int32_t C0, H0;          // counted-mutation depth / Hamming potential at the start region (set once H and C are scanned)
+  int32_t scanned, pad2;   // bit 0: tile prefixes of H and C are final; bit 1: of the kept-region counts
   double mu;
   // ---- outputs ----
   int32_t total_regions, pad1;
@@ -57,8 +59,8 @@ constexpr int kNormBlocks = 64;   // blocks per study in the normalisation pass 
 struct SprBatchDev {
   SprStudy* studies;
   char* slab;
-  int32_t* tile_agg;      // [S][max_tiles][3]
-  uint32_t* tile_flag;    // [S][max_tiles]
+  int32_t* tile_agg;      // [S][max_tiles + 1][3]: per-tile totals of (H, C, kept regions), then their exclusive prefixes
+  uint32_t* tile_flag;    // unused
   uint32_t* ticket;       // [S][4]
   int32_t num_studies, max_tiles;
   uint32_t epoch;
@@ -74,7 +76,7 @@ __device__ __forceinline__ double f64_from_order_key(unsigned long long k) {
 }
 
 // ---- Q(a,x): regularized upper incomplete gamma (series / continued fraction), as in safe_gamma_math.h:46-51 -----------
-__device__ double dev_gamma_q(double a, double x) {
+__device__ __noinline__ double dev_gamma_q(double a, double x) {
   if (x <= 0.0) return 1.0;
   if (isinf(x)) return 0.0;
   if (x < a + 1.0) {
@@ -101,14 +103,65 @@ __device__ double dev_gamma_q(double a, double x) {
 }
 
 // ---- (1) per-study setup: node positions, root paths, X's state table -------------------------------------------------------
-// Everything is block-parallel: no thread ever chases parent pointers.  In DFS pre-order the ancestors of q are exactly
+// Everything is grid-parallel: no thread ever chases parent pointers.  In DFS pre-order the ancestors of q are exactly
 // the positions p <= q with p + subtree_size[p] > q, and the ancestor at depth d goes to slot depth[q] - d of the path,
-// so both root paths are built by one coalesced sweep over subtree_size.  X's sequence is the reference sequence
-// overlaid with the LAST mutation per site on the root->X path: every path mutation posts (ordinal << 2 | to) with an
-// atomicMax on a per-site key, ordinals coming from a block scan of the per-branch list lengths in root->X order.
+// so both root paths are built by one coalesced sweep over subtree_size (spr_paths_kernel, grid = position chunks x studies).
+// X's sequence is the reference sequence overlaid with the LAST mutation per site on the root->X path: every path mutation
+// posts (ordinal << 2 | to) with an atomicMax on a per-site key, ordinals coming from a block scan of the per-branch list
+// lengths in root->X order (spr_xtab_kernel, one CTA per study).
 constexpr int kSetupThreads = 1024;
 
-__global__ void __launch_bounds__(kSetupThreads) spr_setup_kernel(ForestDev f, SprBatchDev B) {
+__global__ void __launch_bounds__(kSetupThreads) spr_paths_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ int s_v[4];   // pos0, posX, depth[pos0], depth[posX]
+  SprStudy& S = B.studies[blockIdx.y];
+  const int tid = threadIdx.x;
+  const TreeDev T = f.trees[S.tree];
+  if ((long long)blockIdx.x * kSetupThreads >= T.num_nodes) return;
+  if (tid == 0) {
+    const int pos0 = T.node_base + f.pos_of_node[T.node_base + S.start_branch];
+    const int posX = S.X >= 0 ? T.node_base + f.pos_of_node[T.node_base + S.X] : -1;
+    s_v[0] = pos0; s_v[1] = posX; s_v[2] = f.depth[pos0]; s_v[3] = posX >= 0 ? f.depth[posX] : -1;
+    if (blockIdx.x == 0) {
+      S.node_base = T.node_base; S.num_nodes = T.num_nodes; S.num_tiles = T.num_tiles; S.L = f.sites[T.sites_id].L;
+      S.root_pos = T.node_base; S.error = 0; S.scanned = 0; S.C0 = 0; S.H0 = 0;
+      S.total_regions = 0; S.max_key = 0ULL; S.log_Wmax = 0.0; S.sum_W = 0.0;
+      int posP = -1, posS = -1, nP = 0, nS = 0, Proot = 0;
+      if (posX >= 0) {
+        posP = f.parent_pos[posX];
+        if (posP < 0) { S.error = 1; posP = posX; }
+        const int c1 = posP + 1, c0 = posP + 1 + f.subtree_size[posP + 1];
+        posS = (posX == c1) ? c0 : c1;
+        nP = f.mut_off[posP + 1] - f.mut_off[posP];
+        nS = f.mut_off[posS + 1] - f.mut_off[posS];
+        Proot = f.parent_pos[posP] < 0;
+      }
+      S.posX = posX; S.posP = posP; S.posS = posS; S.nP = nP; S.nS = nS; S.P_is_root = Proot;
+      S.pos0 = pos0; S.k0 = S.start_mut_idx; S.n0 = f.mut_off[pos0 + 1] - f.mut_off[pos0];
+      if (S.k0 < 0 || S.k0 > S.n0 || (pos0 == T.node_base && S.k0 != S.n0)) S.error = 2;
+      if (posX >= 0 && pos0 >= posX && pos0 < posX + f.subtree_size[posX]) S.error = 3;   // start inside X's subtree
+      S.path_len = min(s_v[2] + 1, S.path_cap);
+      S.xpath_len = posX >= 0 ? min(s_v[3] + 1, S.path_cap) : 0;
+    }
+  }
+  __syncthreads();
+  const int pos0 = s_v[0], posX = s_v[1];
+  const int d0 = min(s_v[2] + 1, S.path_cap) - 1, dX = posX >= 0 ? min(s_v[3] + 1, S.path_cap) - 1 : -1;
+  const int p = T.node_base + blockIdx.x * kSetupThreads + tid;
+  if (p <= max(pos0, posX)) {
+    const int end = p + f.subtree_size[p];
+    const bool a0 = p <= pos0 && end > pos0, aX = posX >= 0 && p <= posX && end > posX;
+    if (a0 || aX) {
+      const int d = f.depth[p];
+      if (a0 && d0 - d >= 0) {
+        ((int32_t*)(B.slab + S.off_path))[d0 - d] = p;
+        ((int2*)(B.slab + S.off_pae))[d0 - d] = make_int2(p, end);     // classify() searches these nested [start, end) ranges
+      }
+      if (aX && dX - d >= 0) ((int32_t*)(B.slab + S.off_xpath))[dX - d] = p;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSetupThreads) spr_xtab_kernel(ForestDev f, SprBatchDev B) {
   __shared__ int s_ws[kSetupThreads / 32];
   __shared__ int s_carry;
   SprStudy& S = B.studies[blockIdx.x];
@@ -116,56 +169,18 @@ __global__ void __launch_bounds__(kSetupThreads) spr_setup_kernel(ForestDev f, S
   const TreeDev T = f.trees[S.tree];
   const SitesDev& Si = f.sites[T.sites_id];
   const int L = Si.L;
+  const int xpath_len = S.xpath_len, X = S.X;
   uint8_t* xtab = (uint8_t*)(B.slab + S.off_xtab);
   uint32_t* xkey = (uint32_t*)(B.slab + S.off_xkey);
-  int32_t* path = (int32_t*)(B.slab + S.off_path);
-  int32_t* xpath = (int32_t*)(B.slab + S.off_xpath);
+  const int32_t* xpath = (const int32_t*)(B.slab + S.off_xpath);
   for (int l = tid; l < L; l += kSetupThreads) { xtab[l] = Si.ref[l]; xkey[l] = 0u; }
-  if (tid == 0) {
-    S.node_base = T.node_base; S.num_nodes = T.num_nodes; S.num_tiles = T.num_tiles; S.L = L;
-    S.root_pos = T.node_base; S.error = 0;
-    S.total_regions = 0; S.max_key = 0ULL; S.log_Wmax = 0.0; S.sum_W = 0.0;
-    int posX = -1, posP = -1, posS = -1, nP = 0, nS = 0, Proot = 0;
-    if (S.X >= 0) {
-      posX = T.node_base + f.pos_of_node[T.node_base + S.X];
-      posP = f.parent_pos[posX];
-      if (posP < 0) { S.error = 1; posP = posX; }
-      const int c1 = posP + 1, c0 = posP + 1 + f.subtree_size[posP + 1];
-      posS = (posX == c1) ? c0 : c1;
-      nP = f.mut_off[posP + 1] - f.mut_off[posP];
-      nS = f.mut_off[posS + 1] - f.mut_off[posS];
-      Proot = f.parent_pos[posP] < 0;
-    }
-    S.posX = posX; S.posP = posP; S.posS = posS; S.nP = nP; S.nS = nS; S.P_is_root = Proot;
-    const int pos0 = T.node_base + f.pos_of_node[T.node_base + S.start_branch];
-    S.pos0 = pos0; S.k0 = S.start_mut_idx; S.n0 = f.mut_off[pos0 + 1] - f.mut_off[pos0];
-    if (S.k0 < 0 || S.k0 > S.n0 || (pos0 == T.node_base && S.k0 != S.n0)) S.error = 2;
-    if (posX >= 0 && pos0 >= posX && pos0 < posX + f.subtree_size[posX]) S.error = 3;   // start inside X's subtree
-    S.path_len = min(f.depth[pos0] + 1, S.path_cap);
-    S.xpath_len = posX >= 0 ? min(f.depth[posX] + 1, S.path_cap) : 0;
-    s_carry = 0;
-  }
-  __syncthreads();
-  {
-    const int pos0 = S.pos0, posX = S.posX;
-    const int d0 = S.path_len - 1, dX = S.xpath_len - 1;
-    const int hi = max(pos0, posX);
-    for (int p = T.node_base + tid; p <= hi; p += kSetupThreads) {
-      const int end = p + f.subtree_size[p];
-      const bool a0 = p <= pos0 && end > pos0, aX = posX >= 0 && p <= posX && end > posX;
-      if (a0 || aX) {
-        const int d = f.depth[p];
-        if (a0 && d0 - d >= 0) path[d0 - d] = p;
-        if (aX && dX - d >= 0) xpath[dX - d] = p;
-      }
-    }
-  }
+  if (tid == 0) s_carry = 0;
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  if (S.X >= 0) {
+  if (X >= 0) {
     // missing_at_X = union of the missation intervals on the X->root path (disjoint along a path by invariant):
     // one warp per path node, lanes stride over the sites of each interval
-    for (int jj = warp; jj < S.xpath_len; jj += kSetupThreads / 32) {
+    for (int jj = warp; jj < xpath_len; jj += kSetupThreads / 32) {
       const int a = xpath[jj];
       for (int i = f.miss_off[a]; i < f.miss_off[a + 1]; ++i) {
         const int2 se = f.miss_se[i];
@@ -173,9 +188,9 @@ __global__ void __launch_bounds__(kSetupThreads) spr_setup_kernel(ForestDev f, S
       }
     }
     // X's sequence: last mutation per site on the root->X path
-    for (int j0 = 0; j0 < S.xpath_len; j0 += kSetupThreads) {
+    for (int j0 = 0; j0 < xpath_len; j0 += kSetupThreads) {
       const int j = j0 + tid;                                   // j counts from the ROOT end of the path
-      const int a = j < S.xpath_len ? xpath[S.xpath_len - 1 - j] : -1;
+      const int a = j < xpath_len ? xpath[xpath_len - 1 - j] : -1;
       const int mo = a >= 0 ? f.mut_off[a] : 0, cnt = a >= 0 ? f.mut_off[a + 1] - mo : 0;
       int tot;
       const int incl = block_scan_incl<int, kSetupThreads>(cnt, s_ws, &tot);
@@ -229,13 +244,41 @@ __device__ __forceinline__ void node_dc(const ForestDev& f, const uint8_t* __res
   }
 }
 
-// deepest node of the start->root path that contains p in its subtree
-__device__ __forceinline__ int classify(const ForestDev& f, const int32_t* __restrict__ path, int path_len, int p) {
-  int lo = 0, hi = path_len - 1;
+// Per-study view used by the scan / segments / emit kernels.  The tree prefix sums H_end, C_end and the kept-region base KB
+// are stored two-level: a tile-local value per node plus one exclusive prefix per tile of kTile nodes (filled by
+// spr_tile_prefix), so that no kernel ever waits on another CTA and nothing is rewritten in place.
+struct SprView {
+  const uint8_t* xtab;
+  const int32_t* Hloc; const int32_t* Cloc; const int32_t* KBloc;
+  const int32_t* agg;          // [num_tiles + 1][3]
+  const int32_t* path; const int2* pae; const int32_t* seg;
+  int node_base, path_len;
+  __device__ __forceinline__ int H(int q) const { return Hloc[q] + agg[(q / kTile) * 3 + 0]; }
+  __device__ __forceinline__ int C(int q) const { return Cloc[q] + agg[(q / kTile) * 3 + 1]; }
+  __device__ __forceinline__ int KB(int q) const { return KBloc[q] + agg[(q / kTile) * 3 + 2]; }
+};
+
+__device__ __forceinline__ SprView make_view(const SprBatchDev& B, const SprStudy& S, int study) {
+  SprView V;
+  V.xtab = (const uint8_t*)(B.slab + S.off_xtab);
+  V.Hloc = (const int32_t*)(B.slab + S.off_H);
+  V.Cloc = (const int32_t*)(B.slab + S.off_C);
+  V.KBloc = (const int32_t*)(B.slab + S.off_KB);
+  V.agg = B.tile_agg + (size_t)study * (B.max_tiles + 1) * 3;
+  V.path = (const int32_t*)(B.slab + S.off_path);
+  V.pae = (const int2*)(B.slab + S.off_pae);
+  V.seg = (const int32_t*)(B.slab + S.off_seg);
+  V.node_base = S.node_base; V.path_len = S.path_len;
+  return V;
+}
+
+// deepest node of the start->root path that contains p in its subtree: binary search over the nested [start, end) ranges
+__device__ __forceinline__ int classify(const SprView& V, int p) {
+  int lo = 0, hi = V.path_len - 1;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    const int a = path[mid];
-    if (p >= a && p < a + f.subtree_size[a]) hi = mid; else lo = mid + 1;
+    const int2 ae = __ldg(V.pae + mid);
+    if (p >= ae.x && p < ae.y) hi = mid; else lo = mid + 1;
   }
   return lo;
 }
@@ -277,31 +320,15 @@ __device__ __forceinline__ RegionEval eval_region(const ForestDev& f, const SprS
 }
 
 // counted-mutation distance from the start region; j = classify(p), Cd = C_down(p,k)
-__device__ __forceinline__ int scope_dist(const SprStudy& S, const int32_t* __restrict__ Cend, const int32_t* __restrict__ path,
-                                          int j, bool on_path, int Cd, int C0) {
+__device__ __forceinline__ int scope_dist(const SprView& V, int j, bool on_path, int Cd, int C0) {
   if (j == 0) return on_path ? abs(Cd - C0) : Cd - C0;
   if (on_path) return C0 - Cd;
-  const int cj = Cend[path[j] - S.node_base];
+  const int cj = V.C(V.path[j] - V.node_base);
   return (C0 - cj) + (Cd - cj);
 }
 
-__device__ __forceinline__ int c_down_start(const ForestDev& f, const SprStudy& S, const uint8_t* xtab, const int32_t* Cend, int* H0,
-                                            const int32_t* Hend) {
-  // C_down / H_down at the start region (pos0, k0)
-  const int par = f.parent_pos[S.pos0];
-  int c = (par < 0 || S.pos0 == S.root_pos) ? 0 : Cend[par - S.node_base];
-  int h = (par < 0 || S.pos0 == S.root_pos) ? 0 : Hend[par - S.node_base];
-  if (S.pos0 != S.root_pos) {
-    const int mo = f.mut_off[S.pos0];
-    for (int i = 0; i < S.k0; ++i) { int dh, dc; mut_dc(xtab, f.mut_site[mo + i], f.mut_code[mo + i] & 15, dh, dc); c += dc; h += dh; }
-  }
-  *H0 = h;
-  return c;
-}
-
 // number of kept regions on branch p (all filters).  `limited` => needs the scope test.
-__device__ int node_kept_count(const ForestDev& f, const SprStudy& S, const uint8_t* __restrict__ xtab,
-                               const int32_t* __restrict__ Cend, const int32_t* __restrict__ path, int p, bool limited, int C0) {
+__device__ int node_kept_count(const ForestDev& f, const SprStudy& S, const SprView& V, int p, bool limited, int C0) {
   if (S.posX >= 0 && p >= S.posX && p < S.posX + f.subtree_size[S.posX]) return 0;
   const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
   const int par = f.parent_pos[p];
@@ -309,16 +336,16 @@ __device__ int node_kept_count(const ForestDev& f, const SprStudy& S, const uint
   const bool is_root = p == S.root_pos;
   int j = 0; bool on_path = false; int Cd = 0;
   if (limited) {
-    j = classify(f, path, S.path_len, p);
-    on_path = (path[j] == p);
-    Cd = is_root ? 0 : Cend[par - S.node_base];
+    j = classify(V, p);
+    on_path = (V.path[j] == p);
+    Cd = is_root ? 0 : V.C(par - S.node_base);
   }
   int cnt = 0;
   for (int k = is_root ? np : 0; k <= np; ++k) {
     bool ok = true;
     if (limited) {
-      ok = scope_dist(S, Cend, path, j, on_path, Cd, C0) <= S.limit;
-      if (k < np) { int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc); Cd += dc; }
+      ok = scope_dist(V, j, on_path, Cd, C0) <= S.limit;
+      if (k < np) { int dh, dc; mut_dc(V.xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc); Cd += dc; }
     }
     if (ok && eval_region(f, S, p, k, np, moff, tPar, tNode).keep) ++cnt;
   }
@@ -326,161 +353,175 @@ __device__ int node_kept_count(const ForestDev& f, const SprStudy& S, const uint
 }
 
 // ---- (2) integer tree prefix sums H_end / C_end (+ kept-count scan when the study is unbounded) ------------------------------------
-// phase 0: H (and C) for every study; unbounded studies also get their kept-count scan KB here.
-// phase 1: kept-count scan for bounded studies (needs C from phase 0).
+// H_end(q) = sum of the per-branch potentials dH over q and its ancestors.  In DFS pre-order that is the running sum of
+// (dH of the node opening at q) - (dH of every node whose subtree closes right before q).  A node a closes right before position
+// a + subtree_size[a], so each tile gathers its closers -- the contiguous slice post_node[c(first-1) .. c(last)) of the post-order
+// list -- flat, one closer per thread, and subtracts them with shared-memory integer atomics (exact, order-free).  Closers that
+// opened in an earlier tile recompute their potential from their own (short) mutation list.  No CTA waits on another one: each
+// tile writes tile-local prefixes + its totals, and spr_tile_prefix turns the totals into per-tile exclusive prefixes.
+// phase 0: H and C for every study; unbounded studies also get their kept-count scan here.
+// phase 1: kept-count scan for bounded studies (needs the final C).
 template <int kPhase>
 __global__ void __launch_bounds__(kTile) spr_scan_kernel(ForestDev f, SprBatchDev B) {
   __shared__ int s_h[kTile];
   __shared__ int s_c[kTile];
+  __shared__ int s_dh[kTile];
+  __shared__ int s_dc[kTile];
   __shared__ int s_ws[kTile / 32];
-  __shared__ int s_pre[3];
-  __shared__ int s_tile;
-  __shared__ int s_C0;
   const int study = blockIdx.y;
-  SprStudy& S = B.studies[study];
-  if ((int)blockIdx.x >= S.num_tiles || S.error) return;
+  const SprStudy& S = B.studies[study];
+  const int tile = blockIdx.x;
+  if (tile >= S.num_tiles || S.error) return;
   const bool limited = S.limit != INT_MAX;
   if (kPhase == 1 && !limited) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t* ticket = B.ticket + study * 4 + kPhase;
-  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
-  __syncthreads();
-  const int tile = s_tile;
-  const uint8_t* xtab = (const uint8_t*)(B.slab + S.off_xtab);
-  int32_t* Hend = (int32_t*)(B.slab + S.off_H);
-  int32_t* Cend = (int32_t*)(B.slab + S.off_C);
-  int32_t* KB = (int32_t*)(B.slab + S.off_KB);
-  const int32_t* path = (const int32_t*)(B.slab + S.off_path);
-  const int tile_start = S.node_base + tile * kTile;
-  const int tile_end = min(tile_start + kTile, S.node_base + S.num_nodes);
+  const int tid = threadIdx.x;
+  const SprView V = make_view(B, S, study);
+  int32_t* Hloc = (int32_t*)(B.slab + S.off_H);
+  int32_t* Cloc = (int32_t*)(B.slab + S.off_C);
+  int32_t* KBloc = (int32_t*)(B.slab + S.off_KB);
+  int32_t* agg = B.tile_agg + ((size_t)study * (B.max_tiles + 1) + tile) * 3;
+  const int node_base = S.node_base, N = S.num_nodes;
+  const int tile_start = node_base + tile * kTile;
+  const int tile_end = min(tile_start + kTile, node_base + N);
   const int p = tile_start + tid;
   const bool active = p < tile_end;
-  int32_t* agg = B.tile_agg + ((size_t)study * B.max_tiles + tile) * 3;
-  uint32_t* flags = B.tile_flag + (size_t)study * B.max_tiles;
-  const uint32_t epoch = B.epoch + (uint32_t)kPhase;
+  const int q = p - node_base;
 
-  int dh = 0, dc = 0, kc = 0;
-  int ih = 0, ic = 0;
   if (kPhase == 0) {
-    if (active && p != S.root_pos) node_dc(f, xtab, p, dh, dc);   // the root's own list is never crossed by the walk
-    s_h[tid] = dh; s_c[tid] = dc;
+    int dh = 0, dc = 0;
+    if (active && p != S.root_pos) node_dc(f, V.xtab, p, dh, dc);   // the root's own list is never crossed by the walk
+    s_h[tid] = dh; s_c[tid] = dc; s_dh[tid] = dh; s_dc[tid] = dc;
     __syncthreads();
-    int diffh = dh, diffc = dc;
-    if (active) {
-      const int q = p - S.node_base;
-      if (q > 0) {
-        const int c0 = (q - 1) - f.depth[p - 1], c1 = q - f.depth[p];
-        for (int j = c0; j < c1; ++j) {
-          const int a = f.post_node[S.node_base + j];
-          if (a >= tile_start) { diffh -= s_h[a - tile_start]; diffc -= s_c[a - tile_start]; }
-          else { int ah, ac; node_dc(f, xtab, a, ah, ac); diffh -= ah; diffc -= ac; }
-        }
+    {
+      const int q_first = tile_start - node_base, q_last = tile_end - 1 - node_base;
+      const int c0 = q_first == 0 ? 0 : (q_first - 1) - f.depth[tile_start - 1];
+      const int c1 = q_last - f.depth[tile_end - 1];
+      for (int j = c0 + tid; j < c1; j += kTile) {
+        const int a = f.post_node[node_base + j];
+        int ah, ac;
+        if (a >= tile_start) { ah = s_h[a - tile_start]; ac = s_c[a - tile_start]; }
+        else node_dc(f, V.xtab, a, ah, ac);
+        const int qc = a + f.subtree_size[a] - tile_start;        // position right after a's subtree: inside this tile
+        if (ah) atomicSub(&s_dh[qc], ah);
+        if (ac) atomicSub(&s_dc[qc], ac);
       }
     }
-    int toth, totc;
-    ih = block_scan_incl<int, kTile>(diffh, s_ws, &toth);
     __syncthreads();
-    ic = block_scan_incl<int, kTile>(diffc, s_ws, &totc);
+    int toth, totc, totk = 0;
+    const int ih = block_scan_incl<int, kTile>(s_dh[tid], s_ws, &toth);
     __syncthreads();
-    int ik = 0, totk = 0;
+    const int ic = block_scan_incl<int, kTile>(s_dc[tid], s_ws, &totc);
+    __syncthreads();
+    int kc = 0, ik = 0;
     if (!limited) {
-      if (active) kc = node_kept_count(f, S, xtab, Cend, path, p, false, 0);
+      if (active) kc = node_kept_count(f, S, V, p, false, 0);
       ik = block_scan_incl<int, kTile>(kc, s_ws, &totk);
     }
-    if (tid == 0) {
-      agg[0] = toth; agg[1] = totc; agg[2] = totk;
-      __threadfence();
-      st_release_u32(flags + tile, epoch);
-    }
-    if (warp == 0) {
-      int a0 = 0, a1 = 0, a2 = 0;
-      for (int j0 = 0; j0 < tile; j0 += 32) {
-        const int j = j0 + lane;
-        if (j < tile) {
-          while (ld_acquire_u32(flags + j) != epoch) { __nanosleep(20); }
-          const int32_t* g = B.tile_agg + ((size_t)study * B.max_tiles + j) * 3;
-          a0 += ld_cg_i32(g); a1 += ld_cg_i32(g + 1); a2 += ld_cg_i32(g + 2);
-        }
-      }
-      a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-      if (lane == 0) { s_pre[0] = a0; s_pre[1] = a1; s_pre[2] = a2; }
-    }
-    __syncthreads();
     if (active) {
-      const int q = p - S.node_base;
-      Hend[q] = s_pre[0] + ih;
-      Cend[q] = s_pre[1] + ic;
+      Hloc[q] = ih; Cloc[q] = ic;
       if (!limited) {
-        KB[q] = s_pre[2] + ik - kc;
-        if (q == S.num_nodes - 1) KB[S.num_nodes] = s_pre[2] + ik;
+        KBloc[q] = ik - kc;
+        if (q == N - 1) KBloc[N] = (N % kTile) ? ik : 0;      // KB(N): one past the end, same tile unless N is a tile multiple
       }
     }
+    if (tid == 0) { agg[0] = toth; agg[1] = totc; agg[2] = totk; }
   } else {
-    if (tid == 0) { int H0; s_C0 = c_down_start(f, S, xtab, Cend, &H0, Hend); }
-    __syncthreads();
-    if (active) kc = node_kept_count(f, S, xtab, Cend, path, p, true, s_C0);
-    int totk;
+    int kc = 0, totk;
+    if (active) kc = node_kept_count(f, S, V, p, true, S.C0);
     const int ik = block_scan_incl<int, kTile>(kc, s_ws, &totk);
-    if (tid == 0) {
-      agg[2] = totk;
-      __threadfence();
-      st_release_u32(flags + tile, epoch);
-    }
-    if (warp == 0) {
-      int a2 = 0;
-      for (int j0 = 0; j0 < tile; j0 += 32) {
-        const int j = j0 + lane;
-        if (j < tile) {
-          while (ld_acquire_u32(flags + j) != epoch) { __nanosleep(20); }
-          a2 += ld_cg_i32(B.tile_agg + ((size_t)study * B.max_tiles + j) * 3 + 2);
-        }
-      }
-      a2 = warp_sum(a2);
-      if (lane == 0) s_pre[2] = a2;
-    }
-    __syncthreads();
     if (active) {
-      const int q = p - S.node_base;
-      KB[q] = s_pre[2] + ik - kc;
-      if (q == S.num_nodes - 1) KB[S.num_nodes] = s_pre[2] + ik;
+      KBloc[q] = ik - kc;
+      if (q == N - 1) KBloc[N] = (N % kTile) ? ik : 0;
     }
+    if (tid == 0) agg[2] = totk;
   }
 }
 
-// ---- (3) segment bases along the start->root path ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) spr_segments_kernel(ForestDev f, SprBatchDev B) {
-  __shared__ int s_ws[8];
+// Exclusive scan over the tiles of one study of the components in `want` that are not final yet (bit 0: H and C, bit 1: kept
+// counts); entry [num_tiles] receives the totals.  Once H and C are final the start region's (C0, H0) are derived.  Called
+// by a whole CTA of kSetupThreads threads; ends with a barrier.
+__device__ void spr_tile_prefix(const ForestDev& f, SprBatchDev& B, SprStudy& S, int study, int want, int* s_ws, int* s_carry) {
+  const int tid = threadIdx.x;
+  const int todo = want & ~S.scanned;
+  __syncthreads();
+  if (todo == 0) return;
+  int32_t* agg = B.tile_agg + (size_t)study * (B.max_tiles + 1) * 3;
+  const int nt = S.num_tiles;
+  for (int comp = 0; comp < 3; ++comp) {
+    if (!((comp < 2 ? 1 : 2) & todo)) continue;
+    if (tid == 0) *s_carry = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < nt; j0 += kSetupThreads) {
+      const int j = j0 + tid;
+      const int v = j < nt ? agg[j * 3 + comp] : 0;
+      int tot;
+      const int incl = block_scan_incl<int, kSetupThreads>(v, s_ws, &tot);
+      if (j < nt) agg[j * 3 + comp] = *s_carry + incl - v;
+      __syncthreads();
+      if (tid == 0) *s_carry += tot;
+      __syncthreads();
+    }
+    if (tid == 0) agg[nt * 3 + comp] = *s_carry;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (todo & 1) {
+      // C_down / H_down at the start region (pos0, k0)
+      const SprView V = make_view(B, S, study);
+      const int par = f.parent_pos[S.pos0];
+      const bool top = par < 0 || S.pos0 == S.root_pos;
+      int c = top ? 0 : V.C(par - S.node_base);
+      int h = top ? 0 : V.H(par - S.node_base);
+      if (S.pos0 != S.root_pos) {
+        const int mo = f.mut_off[S.pos0];
+        for (int i = 0; i < S.k0; ++i) { int dh, dc; mut_dc(V.xtab, f.mut_site[mo + i], f.mut_code[mo + i] & 15, dh, dc); c += dc; h += dh; }
+      }
+      S.C0 = c; S.H0 = h;
+    }
+    S.scanned |= todo;
+    __threadfence_block();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSetupThreads) spr_tile_prefix_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ int s_ws[kSetupThreads / 32];
   __shared__ int s_carry;
-  __shared__ int s_C0;
   SprStudy& S = B.studies[blockIdx.x];
   if (S.error) return;
+  spr_tile_prefix(f, B, S, blockIdx.x, S.limit != INT_MAX ? 1 : 3, s_ws, &s_carry);
+}
+
+// ---- (3) segment bases along the start->root path ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ int s_ws[kSetupThreads / 32];
+  __shared__ int s_carry;
+  SprStudy& S = B.studies[blockIdx.x];
+  if (S.error) return;
+  spr_tile_prefix(f, B, S, blockIdx.x, 3, s_ws, &s_carry);
   const int tid = threadIdx.x;
-  const uint8_t* xtab = (const uint8_t*)(B.slab + S.off_xtab);
-  const int32_t* Hend = (const int32_t*)(B.slab + S.off_H);
-  const int32_t* Cend = (const int32_t*)(B.slab + S.off_C);
-  const int32_t* KB = (const int32_t*)(B.slab + S.off_KB);
-  const int32_t* path = (const int32_t*)(B.slab + S.off_path);
+  const SprView V = make_view(B, S, blockIdx.x);
   int32_t* seg = (int32_t*)(B.slab + S.off_seg);
   const bool limited = S.limit != INT_MAX;
-  if (tid == 0) { int H0; s_C0 = c_down_start(f, S, xtab, Cend, &H0, Hend); s_carry = 0; }
+  const int C0 = S.C0;
+  if (tid == 0) s_carry = 0;
   __syncthreads();
-  const int C0 = s_C0;
-  for (int j0 = 0; j0 < S.path_len; j0 += 256) {
+  for (int j0 = 0; j0 < S.path_len; j0 += kSetupThreads) {
     const int j = j0 + tid;
     int cntA = 0, cntOwn = 0, cntSub = 0, cntUp = 0, sibpos = -1;
     if (j < S.path_len) {
-      const int a = path[j];
+      const int a = V.path[j];
       const int moff = f.mut_off[a], np = f.mut_off[a + 1] - moff;
       const int par = f.parent_pos[a];
       const bool is_root = a == S.root_pos;
       const double tNode = f.t[a], tPar = par >= 0 ? f.t[par] : 0.0;
-      int Cd = is_root ? 0 : Cend[par - S.node_base];
+      int Cd = (is_root || !limited) ? 0 : V.C(par - S.node_base);
       const int kA = (j == 0) ? S.k0 : np;
       for (int k = is_root ? np : 0; k <= np; ++k) {
         bool ok = true;
         if (limited) {
-          ok = scope_dist(S, Cend, path, j, true, Cd, C0) <= S.limit;
-          if (k < np) { int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc); Cd += dc; }
+          ok = scope_dist(V, j, true, Cd, C0) <= S.limit;
+          if (k < np) { int dh, dc; mut_dc(V.xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc); Cd += dc; }
         }
         if (ok && eval_region(f, S, a, k, np, moff, tPar, tNode).keep) {
           if (k == kA) ++cntA; else if (k < kA) ++cntUp; else ++cntOwn;
@@ -489,17 +530,17 @@ __global__ void __launch_bounds__(256) spr_segments_kernel(ForestDev f, SprBatch
       const int qa = a - S.node_base;
       if (j == 0) {
         sibpos = a + 1;
-        cntSub = KB[qa + f.subtree_size[a]] - KB[qa + 1];
+        cntSub = V.KB(qa + f.subtree_size[a]) - V.KB(qa + 1);
       } else {
         const int c1 = a + 1, c0 = a + 1 + f.subtree_size[a + 1];
-        sibpos = (path[j - 1] == c1) ? c0 : c1;
+        sibpos = (V.path[j - 1] == c1) ? c0 : c1;
         const int qs = sibpos - S.node_base;
-        cntSub = KB[qs + f.subtree_size[sibpos]] - KB[qs];
+        cntSub = V.KB(qs + f.subtree_size[sibpos]) - V.KB(qs);
       }
     }
     const int tot = cntA + cntOwn + cntSub + cntUp;
     int btot;
-    const int incl = block_scan_incl<int, 256>(tot, s_ws, &btot);
+    const int incl = block_scan_incl<int, kSetupThreads>(tot, s_ws, &btot);
     const int base = s_carry + incl - tot;
     if (j < S.path_len) {
       int32_t* sg = seg + (size_t)j * kSegStride;
@@ -514,16 +555,12 @@ __global__ void __launch_bounds__(256) spr_segments_kernel(ForestDev f, SprBatch
 }
 
 // ---- (4) emit regions in the reference's DFS order, with raw log-weights ------------------------------------------------------------------
-__device__ __forceinline__ double region_log_W(const ForestDev& f, const SprStudy& S, double t_min, double t_max, int m, double tS) {
-  const double fa = S.f, lam = S.lambda_X, mu = S.mu;
-  if (t_min != -DBL_MAX) {
-    const double t_prime = 0.5 * (t_min + t_max);
-    return log(fa * lam * (t_max - t_min)) + fa * (-lam * (S.t_X - t_prime) + m * log(mu * (S.t_X - t_prime) / 3));
-  }
-  // above-root region (core/spr_study.cpp:334-369)
-  const double s_min = fabs(S.t_X - tS);
-  const double t_early = fmin(S.t_X, tS);
-  const double s_max = s_min + 20.0 * (S.t_max_tip - t_early);
+// above-root region (core/spr_study.cpp:334-369): one region per study at most, kept out of line so that its lgamma /
+// incomplete-gamma code does not inflate the register budget of the common path
+__device__ __noinline__ double region_log_W_above_root(double fa, double lam, double mu, double t_X, double t_max_tip, int m, double tS) {
+  const double s_min = fabs(t_X - tS);
+  const double t_early = fmin(t_X, tS);
+  const double s_max = s_min + 20.0 * (t_max_tip - t_early);
   const double x_min = lam * fa * s_min, x_max = lam * fa * s_max;
   if (x_max < 0.01) {
     const double alpha = fa * m + 1;
@@ -533,24 +570,33 @@ __device__ __forceinline__ double region_log_W(const ForestDev& f, const SprStud
   return -0.6931471805599453 + fa * m * log(mu / (3 * lam * fa)) + lgamma(a) + log(dev_gamma_q(a, x_min) - dev_gamma_q(a, x_max));
 }
 
-__global__ void __launch_bounds__(kTile) spr_emit_kernel(ForestDev f, SprBatchDev B) {
-  __shared__ int s_C0, s_H0;
+__device__ __forceinline__ double region_log_W(const SprStudy& S, double t_min, double t_max, int m, double tS) {
+  const double fa = S.f, lam = S.lambda_X, mu = S.mu;
+  if (t_min != -DBL_MAX) {
+    const double t_prime = 0.5 * (t_min + t_max);
+    return log(fa * lam * (t_max - t_min)) + fa * (-lam * (S.t_X - t_prime) + m * log(mu * (S.t_X - t_prime) / 3));
+  }
+  return region_log_W_above_root(fa, lam, mu, S.t_X, S.t_max_tip, m, tS);
+}
+
+__global__ void __launch_bounds__(kTile, 3) spr_emit_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ SprStudy s_S;                 // the study record, read once (it lives in global memory)
   __shared__ double s_wmax[kTile / 32];
   const int study = blockIdx.y;
-  SprStudy& S = B.studies[study];
-  if ((int)blockIdx.x >= S.num_tiles || S.error) return;
+  {
+    const SprStudy& G = B.studies[study];
+    if ((int)blockIdx.x >= G.num_tiles || G.error) return;
+    const int* src = reinterpret_cast<const int*>(&G);
+    int* dst = reinterpret_cast<int*>(&s_S);
+    for (int i = threadIdx.x; i < (int)(sizeof(SprStudy) / sizeof(int)); i += kTile) dst[i] = src[i];
+  }
+  __syncthreads();
+  const SprStudy& S = s_S;
   const int tid = threadIdx.x;
-  const uint8_t* xtab = (const uint8_t*)(B.slab + S.off_xtab);
-  const int32_t* Hend = (const int32_t*)(B.slab + S.off_H);
-  const int32_t* Cend = (const int32_t*)(B.slab + S.off_C);
-  const int32_t* KB = (const int32_t*)(B.slab + S.off_KB);
-  const int32_t* path = (const int32_t*)(B.slab + S.off_path);
-  const int32_t* seg = (const int32_t*)(B.slab + S.off_seg);
+  const SprView V = make_view(B, S, study);
   dphy_candidate_region* out = (dphy_candidate_region*)(B.slab + S.off_regions);
   const bool limited = S.limit != INT_MAX;
-  if (tid == 0) { int H0; s_C0 = c_down_start(f, S, xtab, Cend, &H0, Hend); s_H0 = H0; }
-  __syncthreads();
-  const int C0 = s_C0, H0 = s_H0;
+  const int C0 = S.C0, H0 = S.H0;
   const int p = S.node_base + blockIdx.x * kTile + tid;
   double wmax = -CUDART_INF;
   bool any = false;
@@ -559,21 +605,21 @@ __global__ void __launch_bounds__(kTile) spr_emit_kernel(ForestDev f, SprBatchDe
     const int par = f.parent_pos[p];
     const bool is_root = p == S.root_pos;
     const double tNode = f.t[p], tPar = par >= 0 ? f.t[par] : 0.0;
-    const int j = classify(f, path, S.path_len, p);
-    const bool on_path = path[j] == p;
-    const int32_t* sg = seg + (size_t)j * kSegStride;
+    const int j = classify(V, p);
+    const bool on_path = V.path[j] == p;
+    const int32_t* sg = V.seg + (size_t)j * kSegStride;
     const int q = p - S.node_base;
-    int Hd = is_root ? 0 : Hend[par - S.node_base];
-    int Cd = (limited && !is_root) ? Cend[par - S.node_base] : 0;
+    int Hd = is_root ? 0 : V.H(par - S.node_base);
+    int Cd = (limited && !is_root) ? V.C(par - S.node_base) : 0;
     const int kA = (j == 0) ? S.k0 : np;
     int rank = 0, rank_up = 0, rank_own = 0;
-    const int hang_base = on_path ? 0 : sg[2] + (KB[q] - KB[sg[5] - S.node_base]);
+    const int hang_base = on_path ? 0 : sg[2] + (V.KB(q) - V.KB(sg[5] - S.node_base));
     for (int k = is_root ? np : 0; k <= np; ++k) {
       bool ok = true;
-      if (limited) ok = scope_dist(S, Cend, path, j, on_path, Cd, C0) <= S.limit;
+      if (limited) ok = scope_dist(V, j, on_path, Cd, C0) <= S.limit;
       const int Hk = Hd;
       if (k < np) {
-        int dh, dc; mut_dc(xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc);
+        int dh, dc; mut_dc(V.xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc);
         Hd += dh; Cd += dc;
       }
       if (!ok) continue;
@@ -585,12 +631,13 @@ __global__ void __launch_bounds__(kTile) spr_emit_kernel(ForestDev f, SprBatchDe
       else if (k > kA) idx = sg[1] + rank_own++;
       else idx = sg[3] + (sg[4] - 1 - rank_up++);
       const int m = S.init_min_muts + (Hk - H0);
-      const double lw = region_log_W(f, S, r.t_min, r.t_max, m, tNode);
+      const double lw = region_log_W(S, r.t_min, r.t_max, m, tNode);
       if (idx >= 0 && idx < S.region_cap) {
-        dphy_candidate_region o;
-        o.branch = r.branch; o.mut_idx = r.mut_idx; o.t_min = r.t_min; o.t_max = r.t_max;
-        o.min_muts = m; o.pad_ = 0; o.log_W_over_Wmax = lw; o.W_over_Wmax = 0.0;
-        out[idx] = o;
+        // 48-byte record written as three 16-byte stores
+        int4* o = reinterpret_cast<int4*>(out + idx);
+        o[0] = make_int4(r.branch, r.mut_idx, __double2loint(r.t_min), __double2hiint(r.t_min));
+        o[1] = make_int4(__double2loint(r.t_max), __double2hiint(r.t_max), m, 0);
+        o[2] = make_int4(__double2loint(lw), __double2hiint(lw), 0, 0);
       }
       wmax = any ? fmax(wmax, lw) : lw;   // std::max semantics of the reference's running maximum
       any = true;
@@ -604,7 +651,7 @@ __global__ void __launch_bounds__(kTile) spr_emit_kernel(ForestDev f, SprBatchDe
   if (warp == 0) {
     wm = lane < kTile / 32 ? s_wmax[lane] : -CUDART_INF;
     wm = warp_max(wm);
-    if (lane == 0 && wm > -CUDART_INF) atomicMax(&S.max_key, f64_order_key(wm));
+    if (lane == 0 && wm > -CUDART_INF) atomicMax(&B.studies[study].max_key, f64_order_key(wm));
   }
 }
 
@@ -746,6 +793,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     S.off_xkey = off; off = al(off + sizeof(uint32_t) * (size_t)L);
     S.off_path = off; off = al(off + sizeof(int32_t) * S.path_cap);
     S.off_xpath = off; off = al(off + sizeof(int32_t) * S.path_cap);
+    S.off_pae = off; off = al(off + sizeof(int2) * S.path_cap);
     S.off_H = off; off = al(off + sizeof(int32_t) * N);
     S.off_C = off; off = al(off + sizeof(int32_t) * N);
     S.off_KB = off; off = al(off + sizeof(int32_t) * (N + 1));
@@ -768,8 +816,8 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   const size_t slab_bytes = off;
   const size_t b_studies = 0;
   const size_t b_agg = al(b_studies + sizeof(SprStudy) * std::max(1, n));
-  const size_t b_flag = al(b_agg + sizeof(int32_t) * 3 * (size_t)max_tiles * std::max(1, n));
-  const size_t b_ticket = al(b_flag + sizeof(uint32_t) * (size_t)max_tiles * std::max(1, n));
+  const size_t b_flag = al(b_agg + sizeof(int32_t) * 3 * ((size_t)max_tiles + 1) * std::max(1, n));
+  const size_t b_ticket = al(b_flag + 256);
   const size_t b_slab = al(b_ticket + sizeof(uint32_t) * 4 * std::max(1, n));
   const size_t total = b_slab + slab_bytes;
   char* d = nullptr;
@@ -804,13 +852,20 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   }
   if (ce != cudaSuccess) { cudaFreeAsync(d, ctx->stream); delete b; return check_cuda(ctx, ce, "spr batch upload"); }
   const dim3 grid_tiles(max_tiles, n);
-  spr_setup_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
+  int max_nodes = 1;
+  for (int i = 0; i < n; ++i) max_nodes = std::max(max_nodes, fo->trees[reqs[i].tree].num_nodes);
+  spr_paths_kernel<<<dim3((max_nodes + kSetupThreads - 1) / kSetupThreads, n), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
+  spr_xtab_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
   spr_scan_kernel<0><<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev);
   bool any_limited = false;
   for (int i = 0; i < n; ++i) any_limited |= (b->host[i].limit != INT_MAX);
-  int launched = 2;
-  if (any_limited) { spr_scan_kernel<1><<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
-  spr_segments_kernel<<<n, 256, 0, ctx->stream>>>(fo->h, b->dev);
+  int launched = 3;
+  if (any_limited) {
+    spr_tile_prefix_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
+    spr_scan_kernel<1><<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+    launched += 2;
+  }
+  spr_segments_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
   spr_emit_kernel<<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev);
   spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ctx->stream>>>(b->dev);
   launched += 3;

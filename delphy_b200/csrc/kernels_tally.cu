@@ -209,9 +209,11 @@ __global__ void __launch_bounds__(1024) tally_sites_finalize_kernel(ForestDev f,
 static int scan_branch_lengths(dphy_ctx* ctx, dphy_forest* fo, int tree, double** PL_out) {
   const TreeDev& T = fo->trees[tree];
   double* PL = (double*)ctx->arena.alloc(sizeof(double) * T.num_nodes);
-  if (!PL) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (tally PL)");
+  // own scan workspace: d_tile_agg holds the log-G tile prefixes that the lambda_i getter still needs
+  double* agg = (double*)ctx->arena.alloc(sizeof(double) * T.num_tiles);
+  if (!PL || !agg) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (tally PL)");
   fo->epoch += 1; if (fo->epoch == 0) fo->epoch = 1;
-  tally_branch_len_scan_kernel<<<T.num_tiles, kTile, 0, ctx->stream>>>(fo->h, tree, PL, fo->d_tile_agg + T.first_tile,
+  tally_branch_len_scan_kernel<<<T.num_tiles, kTile, 0, ctx->stream>>>(fo->h, tree, PL, agg,
                                                                        fo->d_tile_flag + T.first_tile, fo->d_ticket + 2, fo->epoch);
   ctx->launches += 1;
   *PL_out = PL;

@@ -144,6 +144,13 @@ void* dphy_ctx_stream(dphy_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t dphy_ctx_launch_count(const dphy_ctx* ctx);
 
+/* Which kernels dphy_forest_eval_log_G uses.  AUTO: forests whose site tables all have uniform nu_l take the folded path
+ * (per-branch state-count vectors built at upload; the per-event lists are only walked for the mutation times);
+ * GENERAL: always the per-event path (the only one when there is site-rate heterogeneity).  Results agree to ~1e-13. */
+#define DPHY_LOG_G_PATH_AUTO 0
+#define DPHY_LOG_G_PATH_GENERAL 1
+int  dphy_ctx_set_log_G_path(dphy_ctx* ctx, int path);
+
 /* ---- sites / evo model ------------------------------------------------------------------------------- */
 int  dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** out);
 void dphy_sites_destroy(dphy_ctx* ctx, dphy_sites* sites);

@@ -15,9 +15,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["auto", "general"])
+def ctx(request):
+    """Every test runs twice: with the folded fast path enabled (taken whenever all site rates are uniform) and with the
+    general per-event kernels forced."""
     c = db.Context(0)
+    c.set_log_G_path(request.param)
     yield c
     c.close()
 
@@ -150,6 +153,45 @@ def test_set_evo_and_node_times(ctx, orc):
     _, br, _ = fo.log_G()
     assert br[0] == pytest.approx(orc.log_G_below_root(e, s), rel=RTOL)
     fo.close(); ds.close()
+
+
+def test_folded_and_general_paths_agree(orc):
+    """Same forest, both schedules: the folded path (per-branch state-count vectors) and the per-event path give the
+    same lambda_i / log G to ~1e-13, and the structure-only outputs (nsmn, num_muts) survive folded evaluations,
+    time tallies and evo changes in between."""
+    items = [synth(3, seed=21), synth(0, seed=22, num_tips=700, caterpillar=1), synth(0, seed=23, num_partitions=2, num_root_mutations=5)]
+    with db.Context(0) as c:
+        tables = [db.DeviceSites(c, it[1]) for it in items]
+        fo = db.Forest(c, [it[0] for it in items], tables, sites_index=np.arange(len(items)))
+        c.set_log_G_path("general")
+        fo.eval_log_G()
+        rp_g, br_g, _ = fo.log_G()
+        lam_g = [fo.lambda_i(k) for k in range(len(items))]
+        c.set_log_G_path("auto")
+        launches = c.launches
+        fo.eval_log_G()
+        assert c.launches - launches == 2            # folded tile kernel + per-tree fold
+        rp_f, br_f, _ = fo.log_G()
+        np.testing.assert_allclose(br_f, br_g, rtol=1e-12)
+        np.testing.assert_allclose(rp_f, rp_g, rtol=1e-13)
+        fo.Ttwiddle_beta_a(0); fo.Ttwiddle_l(1)      # scratch users must not disturb the lambda_i tile prefixes
+        for k, (emat, sites, _) in enumerate(items):
+            e, s = to_oracle(emat, sites)
+            np.testing.assert_allclose(fo.lambda_i(k), lam_g[k], rtol=1e-12)
+            np.testing.assert_array_equal(fo.num_sites_missing(k), orc.nsmn(e, s))
+            assert fo.tallies()[k]["num_muts"] == orc.num_muts(e, s)
+        # new mu / kappa-like change through set_evo, still uniform nu: folded again, vs the oracle
+        emat, sites, _ = items[0]
+        sites.mu = sites.mu * 0.6
+        tables[0].set_evo(mu=sites.mu)
+        fo.eval_log_G()
+        e, s = to_oracle(emat, sites)
+        lam = orc.lambda_i(e, s)
+        assert rel_err(fo.lambda_i(0), lam) <= RTOL
+        assert fo.log_G()[1][0] == pytest.approx(orc.log_G_below_root(e, s, lam), rel=RTOL)
+        fo.close()
+        for t in tables:
+            t.close()
 
 
 def test_error_behaviour(ctx):
