@@ -117,10 +117,17 @@ int main(int argc, char** argv) {
     {
       auto got = b200::calc_cum_Q_l_for_sequence(tree.ref_sequence, evo);
       auto same = cum_Q_l.size() == got.size();
-      for (auto l = size_t{0}; same && l != cum_Q_l.size(); ++l) { same = close_rel(cum_Q_l[l], got[l], 1e-12); }
-      expect(same, "calc_cum_Q_l_for_sequence (1e-12)");
-      expect(close_rel(calc_lambda_for_sequence(tree.ref_sequence, evo), b200::calc_lambda_for_sequence(tree.ref_sequence, evo), 1e-12),
-             "calc_lambda_for_sequence (1e-12)");
+      // The reference's strictly left-to-right fp64 scan drifts by up to ~L * eps/2 relative (a few 1e-13 at L = 29,903,
+      // above 1e-12 at L = 197,000: the addends take only 4P distinct values, so the rounding errors do not average out);
+      // the device's chunked scan stays within ~1e-14 of the exact sums.  1e-10 covers the reference's own drift.
+      auto worst = 0.0;
+      for (auto l = size_t{0}; same && l != cum_Q_l.size(); ++l) {
+        same = close_rel(cum_Q_l[l], got[l], 1e-10);
+        if (cum_Q_l[l] != 0.0) { worst = std::max(worst, std::abs(cum_Q_l[l] - got[l]) / std::abs(cum_Q_l[l])); }
+      }
+      expect(same, "calc_cum_Q_l_for_sequence (1e-10; worst rel " + std::to_string(worst * 1e12) + "e-12)");
+      expect(close_rel(calc_lambda_for_sequence(tree.ref_sequence, evo), b200::calc_lambda_for_sequence(tree.ref_sequence, evo), 1e-10),
+             "calc_lambda_for_sequence (1e-10)");
     }
     auto lambda_i = calc_lambda_i(tree, evo, cum_Q_l);
     {
@@ -162,15 +169,23 @@ int main(int argc, char** argv) {
     }
     expect(close_rel(calc_T(tree), b200::calc_T(tree)), "calc_T (1e-9)");
     {
+      // each entry is a sum of +-T_below terms of size up to T: entries that cancel to ~0 carry an absolute residue of
+      // ~1e-16 * T that depends on the summation order => relative 1e-9 plus an absolute floor of 1e-9 * max|want|
       auto want = calc_T_l_a(tree); auto got = b200::calc_T_l_a(tree);
       auto same = want.size() == got.size();
-      for (auto l = size_t{0}; same && l != want.size(); ++l) { for (auto a : k_all_real_seq_letters) { same = same && close_rel(want[l][a], got[l][a]); } }
+      auto scale = 0.0;
+      for (const auto& w : want) { for (auto a : k_all_real_seq_letters) { scale = std::max(scale, std::abs(w[a])); } }
+      for (auto l = size_t{0}; same && l != want.size(); ++l) {
+        for (auto a : k_all_real_seq_letters) { same = same && (close_rel(want[l][a], got[l][a]) || std::abs(want[l][a] - got[l][a]) <= 1e-9 * scale); }
+      }
       expect(same, "calc_T_l_a (1e-9)");
     }
     {
       auto want = calc_Ttwiddle_l(tree, evo); auto got = b200::calc_Ttwiddle_l(tree, evo);
       auto same = want.size() == got.size();
-      for (auto l = size_t{0}; same && l != want.size(); ++l) { same = close_rel(want[l], got[l]); }
+      auto scale = 0.0;
+      for (auto w : want) { scale = std::max(scale, std::abs(w)); }
+      for (auto l = size_t{0}; same && l != want.size(); ++l) { same = close_rel(want[l], got[l]) || std::abs(want[l] - got[l]) <= 1e-9 * scale; }
       expect(same, "calc_Ttwiddle_l (1e-9)");
     }
     {

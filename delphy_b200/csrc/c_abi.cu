@@ -569,6 +569,9 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   // rates are uniform take the folded fast path and leave them untouched
   st = launch_log_G_general(ctx, fo);
   if (st != DPHY_OK) { cudaStreamSynchronize(ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo; return st; }
+  fo->evaluated = true;         // that pass is a complete evaluation under the current evo model
+  fo->eval_version.resize(fo->sites.size());
+  for (size_t i = 0; i < fo->sites.size(); ++i) fo->eval_version[i] = fo->sites[i]->version;
   *out = fo;
   return DPHY_OK;
 }
@@ -625,12 +628,16 @@ int dphy_forest_eval_log_G(dphy_ctx* ctx, dphy_forest* fo) {
   if (!ctx || !fo) return DPHY_ERR_INVALID_ARGUMENT;
   cudaSetDevice(ctx->device);
   int st = launch_log_G(ctx, fo);
-  if (st == DPHY_OK) fo->evaluated = true;
+  if (st == DPHY_OK) {
+    fo->evaluated = true;
+    fo->eval_version.resize(fo->sites.size());
+    for (size_t i = 0; i < fo->sites.size(); ++i) fo->eval_version[i] = fo->sites[i]->version;
+  }
   return st;
 }
 
 static int fetch_tree_outputs(dphy_ctx* ctx, dphy_forest* fo, std::vector<double>& dout, std::vector<int32_t>* iout) {
-  if (!fo->evaluated) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
+  if (!fo->eval_current()) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
   const int T = fo->h.num_trees;
   dout.resize((size_t)T * 4);
   DPHY_CUDA(ctx, cudaMemcpyAsync(dout.data(), fo->d_tree_out, sizeof(double) * 4 * T, cudaMemcpyDeviceToHost, ctx->stream));
@@ -657,7 +664,7 @@ int dphy_forest_get_log_G(dphy_ctx* ctx, dphy_forest* fo, double* log_root_prior
 
 int dphy_forest_get_lambda_i(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, double* out) {
   if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
-  if (!fo->evaluated) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
+  if (!fo->eval_current()) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
   const TreeDev& T = fo->trees[tree];
   const size_t mark = ctx->arena.mark();
   double* tmp = (double*)ctx->arena.alloc(sizeof(double) * T.num_nodes);
@@ -671,7 +678,7 @@ int dphy_forest_get_lambda_i(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, doubl
 
 int dphy_forest_get_num_sites_missing(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t* out) {
   if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
-  if (!fo->evaluated) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
+  if (!fo->eval_current()) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
   const TreeDev& T = fo->trees[tree];
   const size_t mark = ctx->arena.mark();
   int32_t* tmp = (int32_t*)ctx->arena.alloc(sizeof(int32_t) * T.num_nodes);

@@ -229,6 +229,12 @@ struct dphy_forest {
   bool struct_valid = false;    // nsmn / num_muts tallies (structure-only outputs of the general log-G pass) are current
   uint32_t epoch = 0;           // look-back flag value of the current launch (flag == epoch means "published")
   std::vector<uint64_t> sites_version;
+  std::vector<uint64_t> eval_version;   // sites versions the last log-G evaluation used (a set_evo since then => stale)
+  bool eval_current() const {
+    if (!evaluated || eval_version.size() != sites.size()) return false;
+    for (size_t i = 0; i < sites.size(); ++i) if (eval_version[i] != sites[i]->version) return false;
+    return true;
+  }
 };
 
 namespace dphy {

@@ -10,7 +10,7 @@ if [[ $SEC == *s* ]]; then
   tail -3 $OUT/smoke.log
 fi
 if [[ $SEC == *t* ]]; then
-  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
+  timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
   tail -15 $OUT/pytest_gpu.log
 fi
 if [[ $SEC == *b* ]]; then
