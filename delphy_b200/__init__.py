@@ -137,6 +137,8 @@ def lib() -> C.CDLL:
     L.dphy_arena_stats.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.dphy_ctx_stream.argtypes = [vp]; L.dphy_ctx_stream.restype = vp
     L.dphy_ctx_launch_count.argtypes = [vp]; L.dphy_ctx_launch_count.restype = C.c_int64
+    L.dphy_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.dphy_host_free.argtypes = [vp, vp]; L.dphy_host_free.restype = None
     L.dphy_ctx_set_log_G_path.argtypes = [vp, C.c_int]
     L.dphy_sites_upload.argtypes = [vp, C.POINTER(SitesHost), C.POINTER(vp)]
     L.dphy_sites_destroy.argtypes = [vp, vp]
@@ -209,6 +211,11 @@ class HostEmat:
     @property
     def num_nodes(self):
         return int(self.parent.shape[0])
+
+    def pinned(self, ctx) -> "HostEmat":
+        """A copy whose arrays live in page-locked memory (dphy_host_alloc): dphy_forest_upload DMAs straight out of them."""
+        arrays = {k: ctx.host_array_like(getattr(self, k)) for k in self.FIELDS_I32 + self.FIELDS_U8 + self.FIELDS_F64}
+        return HostEmat(self.root, self.includes_run_root, **arrays)
 
     def as_struct(self) -> EmatHost:
         return EmatHost(self.num_nodes, self.root, self.includes_run_root, 0,
@@ -326,6 +333,7 @@ class Context:
 
     def __init__(self, device: int = 0):
         self._h = C.c_void_p()
+        self._host_blocks = []
         st = lib().dphy_ctx_create(device, C.byref(self._h))
         if st != DPHY_OK:
             raise DphyError(st, "dphy_ctx_create failed: a CUDA device is required (no CPU fallback)")
@@ -345,6 +353,17 @@ class Context:
     def launches(self) -> int:
         return int(lib().dphy_ctx_launch_count(self._h))
 
+    def host_array_like(self, a: np.ndarray) -> np.ndarray:
+        """Page-locked copy of `a` (freed with the context)."""
+        a = np.ascontiguousarray(a)
+        p = C.c_void_p()
+        self.check(lib().dphy_host_alloc(self._h, max(1, a.nbytes), C.byref(p)))
+        self._host_blocks.append(p)
+        buf = (C.c_char * max(1, a.nbytes)).from_address(p.value)
+        out = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape)
+        out[...] = a
+        return out
+
     def set_log_G_path(self, path: str = "auto"):
         """'auto': folded fast path when every site table has uniform nu_l; 'general': always the per-event kernels."""
         self.check(lib().dphy_ctx_set_log_G_path(self._h, {"auto": 0, "general": 1}[path]))
@@ -356,6 +375,9 @@ class Context:
 
     def close(self):
         if self._h:
+            for p in self._host_blocks:        # numpy views into these blocks must not be used after close()
+                lib().dphy_host_free(self._h, p)
+            self._host_blocks = []
             lib().dphy_ctx_destroy(self._h)
             self._h = C.c_void_p()
 

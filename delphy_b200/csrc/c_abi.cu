@@ -80,6 +80,21 @@ extern "C" {
 
 const char* dphy_version(void) { return "delphy_b200 0.1 (sm_100a)"; }
 
+int dphy_host_alloc(dphy_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return DPHY_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaHostAlloc");
+  }
+  return DPHY_OK;
+}
+void dphy_host_free(dphy_ctx* ctx, void* p) {
+  if (ctx) cudaSetDevice(ctx->device);
+  if (p) cudaFreeHost(p);
+}
+
 int dphy_ctx_create(int device, dphy_ctx** out) {
   if (!out) return DPHY_ERR_INVALID_ARGUMENT;
   *out = nullptr;
@@ -286,11 +301,34 @@ namespace {
 // overlap and the host never touches the data more than once.
 struct CopyJob { size_t dst_off; const void* src; size_t bytes; };
 
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char* d_base, size_t total) {
   if (total == 0) return DPHY_OK;
   constexpr size_t kChunk = (size_t)2 << 20;
   const size_t nchunks = (total + kChunk - 1) / kChunk;
   std::sort(jobs.begin(), jobs.end(), [](const CopyJob& a, const CopyJob& b) { return a.dst_off < b.dst_off; });
+  // Caller arrays that are already page-locked (dphy_host_alloc / cudaHostRegister) are DMA'd from where they lie: no host
+  // copy at all.  Only the bytes no job covers (the records written into the staging slab, alignment gaps) come from it.
+  {
+    bool all_pinned = !jobs.empty();
+    for (const CopyJob& j : jobs) if (!is_pinned_host(j.src)) { all_pinned = false; break; }
+    if (all_pinned) {
+      cudaError_t ce = cudaSuccess;
+      size_t cur = 0;
+      for (const CopyJob& j : jobs) {
+        if (ce == cudaSuccess && j.dst_off > cur) ce = cudaMemcpyAsync(d_base + cur, pinned + cur, j.dst_off - cur, cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_base + j.dst_off, j.src, j.bytes, cudaMemcpyHostToDevice, ctx->stream);
+        cur = std::max(cur, j.dst_off + j.bytes);
+      }
+      if (ce == cudaSuccess && cur < total) ce = cudaMemcpyAsync(d_base + cur, pinned + cur, total - cur, cudaMemcpyHostToDevice, ctx->stream);
+      return check_cuda(ctx, ce, "H2D direct upload");
+    }
+  }
   auto fill_chunk = [&](size_t c) {
     const size_t lo = c * kChunk, hi = std::min(total, lo + kChunk);
     // first job that may overlap [lo, hi)

@@ -47,6 +47,7 @@ struct LogGParams {
   int32_t* sd_n;         // [num_nodes] missing-site count of the straddlers (sparse)
   const int32_t* strad_list;   // device positions of the straddlers
   int32_t num_strad;
+  uint32_t* tree_done;   // [num_trees] folded path: tiles of the tree that have published their partials (self-resetting)
   int32_t debug_mask;    // profiling only (DPHY_DEBUG_MASK): 1 skip mutations, 2 intervals, 4 from-states, 8 closers
 };
 
@@ -685,6 +686,8 @@ struct FoldSmem {
   double clx[kLgTile + 2];
   double wsd[kNW * 2];
   double muq[kMaxPartitions * 4];
+  double carry;
+  int last;
 };
 
 __device__ __forceinline__ double block_scan_excl1(double& a, double* wsd) {   // returns the block total; a <- exclusive prefix
@@ -839,40 +842,45 @@ __global__ void __launch_bounds__(kLgThreads, 5) emat_log_G_folded_kernel(const 
       if (lane == 0) { P.tile_part[tile * 2 + 0] = a; P.tile_part[tile * 2 + 1] = b; }
     }
   }
-}
 
-// pass 2 of the folded path: one CTA per tree -- exclusive scan of the tile aggregates, log G fold, root prior from the root's
-// folded weights (ref_freq + bw[root] is exactly the state count vector of core/phylo_tree_calc.cpp:467-504).
-__global__ void __launch_bounds__(kTreeThreads) emat_log_G_folded_tree_kernel(const LogGParams P) {
-  __shared__ double s_wsd[kTreeThreads / 32];
-  __shared__ double s_carry;
-  const ForestDev& f = P.f;
-  const int tid = threadIdx.x;
-  const int tree = blockIdx.x;
-  const TreeDev T = f.trees[tree];
-  const SitesDev& S = f.sites[T.sites_id];
-  if (tid == 0) s_carry = 0.0;
+  // ---- pass 2, fused: the CTA that publishes the last tile of a tree folds the tree (no second launch, no spinning) -------------------
+  // Exclusive scan of the tile aggregates in tile order, log G = sum_tiles (A1 - prefix * A2), root prior from the root's folded
+  // weights (ref_freq + bw[root] is exactly the state-count vector of core/phylo_tree_calc.cpp:467-504).  The fold reads the
+  // partials in a fixed order whichever CTA happens to run it, so the result does not depend on the schedule.
+  const int tree = __ldg(f.ctile_tree + tile);
+  __threadfence();                         // my tile_agg / tile_part stores are visible device-wide before the ticket
   __syncthreads();
+  if (tid == 0) {
+    const TreeDev& T0 = f.trees[tree];
+    const uint32_t done = atomicAdd(P.tree_done + tree, 1u);
+    sm.last = done == (uint32_t)T0.num_ctiles - 1u;
+    if (sm.last) P.tree_done[tree] = 0u;   // re-arm for the next evaluation
+    sm.carry = 0.0;
+  }
+  __syncthreads();
+  if (!sm.last) return;
+  __threadfence();
+  const TreeDev T = f.trees[tree];
   double a1 = 0.0, a2 = 0.0;
-  for (int j0 = 0; j0 < T.num_ctiles; j0 += kTreeThreads) {
+  for (int j0 = 0; j0 < T.num_ctiles; j0 += kLgThreads) {
     const int j = T.first_ctile + j0 + tid;
     const bool ok = j0 + tid < T.num_ctiles;
-    const double v = ok ? P.tile_agg[j] : 0.0;
+    const double v = ok ? __ldcg(P.tile_agg + j) : 0.0;
     double tot;
-    const double incl = block_scan_incl<double, kTreeThreads>(v, s_wsd, &tot);
+    const double incl = block_scan_incl<double, kLgThreads>(v, sm.wsd, &tot);
     if (ok) {
-      const double pre = s_carry + (incl - v);          // exclusive prefix of this tile
+      const double pre = sm.carry + (incl - v);          // exclusive prefix of this tile
       P.tile_agg[j] = pre;
-      const double A1 = P.tile_part[j * 2 + 0], A2 = P.tile_part[j * 2 + 1];
-      a1 += A1 - pre * A2;                              // sum over the tile of -(lambda_local + pre) len + g
+      const double A1 = __ldcg(P.tile_part + j * 2 + 0), A2 = __ldcg(P.tile_part + j * 2 + 1);
+      a1 += A1 - pre * A2;                               // sum over the tile of -(lambda_local + pre) len + g
       a2 += A2;
     }
     __syncthreads();
-    if (tid == 0) s_carry += tot;
+    if (tid == 0) sm.carry += tot;
     __syncthreads();
   }
-  a1 = block_sum<double, kTreeThreads>(a1, s_wsd);
-  a2 = block_sum<double, kTreeThreads>(a2, s_wsd);
+  a1 = block_sum<double, kLgThreads>(a1, sm.wsd);
+  a2 = block_sum<double, kLgThreads>(a2, sm.wsd);
   if (tid == 0) {
     P.tree_out[tree * 4 + 1] = a1;
     P.tree_out[tree * 4 + 2] = a2;
@@ -980,9 +988,9 @@ static int launch_log_G_folded(dphy_ctx* ctx, dphy_forest* fo) {
   P.tile_agg = fo->d_tile_agg;
   P.tile_part = fo->d_tile_part;
   P.tree_out = fo->d_tree_out;
+  P.tree_done = fo->d_tree_done;
   emat_log_G_folded_kernel<<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
-  emat_log_G_folded_tree_kernel<<<fo->h.num_trees, kTreeThreads, 0, ctx->stream>>>(P);
-  ctx->launches += 2;
+  ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "emat_log_G folded kernels launch");
 }
 

@@ -244,6 +244,17 @@ __device__ __forceinline__ void node_dc(const ForestDev& f, const uint8_t* __res
   }
 }
 
+// remove_regions_in_Xs_future (core/spr_study.cpp:211-224) drops every region that starts at or after t_X.  Every region of
+// branch p starts at or after t[parent(p)], and so does everything below p: if t[parent(p)] >= t_X the branch and its whole
+// subtree -- a contiguous range of positions -- contribute nothing, so the kernels neither walk their mutation lists nor give
+// them output slots.  Exceptions: S and P (their regions are relabelled by account_for_Xs_detachment before the clip) and
+// the ancestors-or-self of the start node (H0 / C0 are read off that path).
+__device__ __forceinline__ bool branch_in_Xs_future(const ForestDev& f, const SprStudy& S, int p, int par) {
+  if (par < 0 || p == S.posS || p == S.posP) return false;
+  if (!(f.t[par] >= S.t_X)) return false;
+  return !(p <= S.pos0 && S.pos0 < p + f.subtree_size[p]);
+}
+
 // Per-study view used by the scan / segments / emit kernels.  The tree prefix sums H_end, C_end and the kept-region base KB
 // are stored two-level: a tile-local value per node plus one exclusive prefix per tile of kTile nodes (filled by
 // spr_tile_prefix), so that no kernel ever waits on another CTA and nothing is rewritten in place.
@@ -330,10 +341,13 @@ __device__ __forceinline__ int scope_dist(const SprView& V, int j, bool on_path,
 // number of kept regions on branch p (all filters).  `limited` => needs the scope test.
 __device__ int node_kept_count(const ForestDev& f, const SprStudy& S, const SprView& V, int p, bool limited, int C0) {
   if (S.posX >= 0 && p >= S.posX && p < S.posX + f.subtree_size[S.posX]) return 0;
-  const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
   const int par = f.parent_pos[p];
+  if (branch_in_Xs_future(f, S, p, par)) return 0;
+  const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
   const double tNode = f.t[p], tPar = par >= 0 ? f.t[par] : 0.0;
   const bool is_root = p == S.root_pos;
+  // an ordinary branch that ends before t_X keeps all of its np + 1 regions (t_min <= t_node < t_X)
+  if (!limited && !is_root && p != S.posS && p != S.posP && tPar < S.t_X && tNode < S.t_X) return np + 1;
   int j = 0; bool on_path = false; int Cd = 0;
   if (limited) {
     j = classify(V, p);
@@ -389,7 +403,8 @@ __global__ void __launch_bounds__(kTile) spr_scan_kernel(ForestDev f, SprBatchDe
 
   if (kPhase == 0) {
     int dh = 0, dc = 0;
-    if (active && p != S.root_pos) node_dc(f, V.xtab, p, dh, dc);   // the root's own list is never crossed by the walk
+    // the root's own list is never crossed by the walk; branches in X's future are never visited at all
+    if (active && p != S.root_pos && !branch_in_Xs_future(f, S, p, f.parent_pos[p])) node_dc(f, V.xtab, p, dh, dc);
     s_h[tid] = dh; s_c[tid] = dc; s_dh[tid] = dh; s_dc[tid] = dc;
     __syncthreads();
     {
@@ -400,6 +415,7 @@ __global__ void __launch_bounds__(kTile) spr_scan_kernel(ForestDev f, SprBatchDe
         const int a = f.post_node[node_base + j];
         int ah, ac;
         if (a >= tile_start) { ah = s_h[a - tile_start]; ac = s_c[a - tile_start]; }
+        else if (a == S.root_pos || branch_in_Xs_future(f, S, a, f.parent_pos[a])) { ah = 0; ac = 0; }
         else node_dc(f, V.xtab, a, ah, ac);
         const int qc = a + f.subtree_size[a] - tile_start;        // position right after a's subtree: inside this tile
         if (ah) atomicSub(&s_dh[qc], ah);
@@ -579,59 +595,166 @@ __device__ __forceinline__ double region_log_W(const SprStudy& S, double t_min, 
   return region_log_W_above_root(fa, lam, mu, S.t_X, S.t_max_tip, m, tS);
 }
 
-__global__ void __launch_bounds__(kTile, 3) spr_emit_kernel(ForestDev f, SprBatchDev B) {
-  __shared__ SprStudy s_S;                 // the study record, read once (it lives in global memory)
-  __shared__ double s_wmax[kTile / 32];
+// Two phases per tile of kTile nodes.  (A) one thread per node: the node's record (list range, H / C at its parent, times,
+// segment constants) goes to shared memory and the per-node candidate counts (np + 1 regions; 1 for the root) are scanned into
+// slot offsets; the tile's mutations -- one contiguous CSR range -- get their (dH, counted) pair flat, one per thread.
+// (B) one thread per SLOT (= candidate region), in rounds of kTile: the slot finds its node by binary search in the slot
+// offsets, so the expensive part of a region (keep rules, two fp64 logs, three 16-byte stores) runs with all lanes busy
+// no matter how the mutations are distributed over the nodes.  For regions off the start->root path the output index is
+//   seg[2] - KB(sibling) + (KB(tile) + rank of the kept region inside the tile)
+// i.e. one ballot-scan of the keep flags per round; consecutive kept slots write consecutive 48-byte records.
+constexpr int kEmitMutCap = 3072;          // per-tile mutations whose (dH, counted) pair is cached in shared memory
+
+struct EmitSmem {
+  SprStudy S;                              // the study record, read once (it lives in global memory)
+  double tPar[kTile], tNode[kTile];
+  int start[kTile + 1];                    // exclusive scan of the per-node candidate counts
+  int moff[kTile], np[kTile], Hpar[kTile], Cpar[kTile], hang[kTile], cls[kTile];   // cls = j << 1 | on_path
+  int wcnt[kTile / 32];
+  double wmax[kTile / 32];
+  int jb[2];
+  signed char dhc[kEmitMutCap];            // (dH + 1) | counted << 2
+};
+
+__device__ __forceinline__ void emit_mut_dc(const ForestDev& f, const EmitSmem& sm, const uint8_t* __restrict__ xtab, int m0, int i, int& dh, int& dc) {
+  const int rel = i - m0;
+  if (rel < kEmitMutCap) { const int v = sm.dhc[rel]; dh = (v & 3) - 1; dc = v >> 2; }
+  else mut_dc(xtab, f.mut_site[i], f.mut_code[i] & 15, dh, dc);
+}
+
+__global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ EmitSmem sm;
   const int study = blockIdx.y;
   {
     const SprStudy& G = B.studies[study];
     if ((int)blockIdx.x >= G.num_tiles || G.error) return;
     const int* src = reinterpret_cast<const int*>(&G);
-    int* dst = reinterpret_cast<int*>(&s_S);
+    int* dst = reinterpret_cast<int*>(&sm.S);
     for (int i = threadIdx.x; i < (int)(sizeof(SprStudy) / sizeof(int)); i += kTile) dst[i] = src[i];
   }
   __syncthreads();
-  const SprStudy& S = s_S;
-  const int tid = threadIdx.x;
+  const SprStudy& S = sm.S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SprView V = make_view(B, S, study);
   dphy_candidate_region* out = (dphy_candidate_region*)(B.slab + S.off_regions);
   const bool limited = S.limit != INT_MAX;
   const int C0 = S.C0, H0 = S.H0;
-  const int p = S.node_base + blockIdx.x * kTile + tid;
-  double wmax = -CUDART_INF;
-  bool any = false;
-  if (p < S.node_base + S.num_nodes && !(S.posX >= 0 && p >= S.posX && p < S.posX + f.subtree_size[S.posX])) {
+  const int kb_tile = V.agg[blockIdx.x * 3 + 2];      // kept regions before this tile (KBloc of the tile's first node is 0)
+  if (V.agg[(blockIdx.x + 1) * 3 + 2] == kb_tile) return;   // nothing kept in this tile (X's subtree, X's future, out of scope)
+  const int tile_start = S.node_base + blockIdx.x * kTile;
+  const int tile_end = min(tile_start + kTile, S.node_base + S.num_nodes);
+  const int p = tile_start + tid;
+  const int xs = S.posX, xe = S.posX >= 0 ? S.posX + f.subtree_size[S.posX] : -1;
+
+  // the deepest path node containing p is monotone in p on either side of the start node: bracket the search once per tile
+  if (tid < 2) sm.jb[tid] = classify(V, tid == 0 ? tile_start : tile_end - 1);
+  const int m0 = f.mut_off[tile_start], m1 = f.mut_off[tile_end];
+  for (int g = m0 + tid; g < min(m1, m0 + kEmitMutCap); g += kTile) {
+    int dh, dc; mut_dc(V.xtab, f.mut_site[g], f.mut_code[g] & 15, dh, dc);
+    sm.dhc[g - m0] = (signed char)((dh + 1) | (dc << 2));
+  }
+  __syncthreads();
+
+  // ---- (A) node records + slot offsets ------------------------------------------------------------------------------------------------
+  int cnt = 0;
+  const int par = p < tile_end ? f.parent_pos[p] : -1;
+  if (p < tile_end && !(xs >= 0 && p >= xs && p < xe) && !branch_in_Xs_future(f, S, p, par)) {
     const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
-    const int par = f.parent_pos[p];
     const bool is_root = p == S.root_pos;
-    const double tNode = f.t[p], tPar = par >= 0 ? f.t[par] : 0.0;
-    const int j = classify(V, p);
+    int lo = min(sm.jb[0], sm.jb[1]), hi = max(sm.jb[0], sm.jb[1]);
+    if (tile_start <= S.pos0 && S.pos0 < tile_end) lo = 0;      // the tile holds the start node: both sides of the bracket
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const int2 ae = __ldg(V.pae + mid);
+      if (p >= ae.x && p < ae.y) hi = mid; else lo = mid + 1;
+    }
+    const int j = lo;
     const bool on_path = V.path[j] == p;
     const int32_t* sg = V.seg + (size_t)j * kSegStride;
-    const int q = p - S.node_base;
-    int Hd = is_root ? 0 : V.H(par - S.node_base);
-    int Cd = (limited && !is_root) ? V.C(par - S.node_base) : 0;
-    const int kA = (j == 0) ? S.k0 : np;
-    int rank = 0, rank_up = 0, rank_own = 0;
-    const int hang_base = on_path ? 0 : sg[2] + (V.KB(q) - V.KB(sg[5] - S.node_base));
-    for (int k = is_root ? np : 0; k <= np; ++k) {
-      bool ok = true;
-      if (limited) ok = scope_dist(V, j, on_path, Cd, C0) <= S.limit;
-      const int Hk = Hd;
-      if (k < np) {
-        int dh, dc; mut_dc(V.xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc);
-        Hd += dh; Cd += dc;
+    sm.moff[tid] = moff; sm.np[tid] = np;
+    sm.tNode[tid] = f.t[p]; sm.tPar[tid] = par >= 0 ? f.t[par] : 0.0;
+    sm.Hpar[tid] = is_root ? 0 : V.H(par - S.node_base);
+    sm.Cpar[tid] = (limited && !is_root) ? V.C(par - S.node_base) : 0;
+    sm.hang[tid] = on_path ? 0 : sg[2] - V.KB(sg[5] - S.node_base);
+    sm.cls[tid] = (j << 1) | (on_path ? 1 : 0);
+    cnt = is_root ? 1 : np + 1;
+  }
+  {
+    int incl = warp_scan_incl(cnt, lane);
+    if (lane == 31) sm.wcnt[warp] = incl;
+    __syncthreads();
+    int pre = 0;
+#pragma unroll
+    for (int w = 0; w < kTile / 32; ++w) if (w < warp) pre += sm.wcnt[w];
+    sm.start[tid] = pre + incl - cnt;
+    if (tid == kTile - 1) sm.start[kTile] = pre + incl;
+    __syncthreads();
+  }
+  const int total = sm.start[kTile];
+
+  // ---- (B) one slot per thread ------------------------------------------------------------------------------------------------------------
+  double wmax = -CUDART_INF;
+  bool any = false;
+  int carry = 0;
+  for (int s0 = 0; s0 < total; s0 += kTile) {
+    const int s = s0 + tid;
+    bool keep = false;
+    int n = 0, k = 0, Hk = 0, j = 0;
+    bool on_path = false;
+    RegionEval r{};
+    if (s < total) {
+      int lo = 0, hi = kTile - 1;                     // last node with start <= s (nodes with no slot share their successor's start)
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (sm.start[mid] <= s) lo = mid; else hi = mid - 1;
       }
-      if (!ok) continue;
-      const RegionEval r = eval_region(f, S, p, k, np, moff, tPar, tNode);
-      if (!r.keep) continue;
+      n = lo;
+      const int pn = tile_start + n;
+      const int np = sm.np[n], moff = sm.moff[n];
+      const bool is_root = pn == S.root_pos;
+      k = is_root ? np : s - sm.start[n];
+      Hk = sm.Hpar[n];
+      int Ck = sm.Cpar[n];
+      const int ncross = is_root ? 0 : k;             // the root's own list is never crossed by the walk
+      for (int i = 0; i < ncross; ++i) { int dh, dc; emit_mut_dc(f, sm, V.xtab, m0, moff + i, dh, dc); Hk += dh; Ck += dc; }
+      j = sm.cls[n] >> 1; on_path = sm.cls[n] & 1;
+      bool ok = true;
+      if (limited) ok = scope_dist(V, j, on_path, Ck, C0) <= S.limit;
+      if (ok) { r = eval_region(f, S, pn, k, np, moff, sm.tPar[n], sm.tNode[n]); keep = r.keep; }
+    }
+    // rank of the kept slot inside the tile (ballot scan)
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) sm.wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int pre = 0, rtot = 0;
+#pragma unroll
+    for (int w = 0; w < kTile / 32; ++w) { const int c = sm.wcnt[w]; if (w < warp) pre += c; rtot += c; }
+    const int rank = carry + pre + __popc(bal & ((1u << lane) - 1u));
+    carry += rtot;
+    __syncthreads();                                  // wcnt is rewritten by the next round
+    if (keep) {
       int idx;
-      if (!on_path) idx = hang_base + rank++;
-      else if (k == kA) idx = sg[0];
-      else if (k > kA) idx = sg[1] + rank_own++;
-      else idx = sg[3] + (sg[4] - 1 - rank_up++);
+      if (!on_path) idx = sm.hang[n] + kb_tile + rank;
+      else {
+        // a node of the start->root path (at most depth-many per study): its regions go to the path segments
+        const int pn = tile_start + n, np = sm.np[n], moff = sm.moff[n];
+        const int32_t* sg = V.seg + (size_t)j * kSegStride;
+        const int kA = (j == 0) ? S.k0 : np;
+        if (k == kA) idx = sg[0];
+        else {
+          int before = 0, Ck = sm.Cpar[n];
+          const int kfirst = (pn == S.root_pos) ? np : 0;
+          for (int k2 = kfirst; k2 < k; ++k2) {
+            bool ok2 = true;
+            if (limited) ok2 = scope_dist(V, j, true, Ck, C0) <= S.limit;
+            if (k2 < np) { int dh, dc; emit_mut_dc(f, sm, V.xtab, m0, moff + k2, dh, dc); Ck += dc; }
+            if (ok2 && (k > kA ? k2 > kA : true) && eval_region(f, S, pn, k2, np, moff, sm.tPar[n], sm.tNode[n]).keep) ++before;
+          }
+          idx = k > kA ? sg[1] + before : sg[3] + (sg[4] - 1 - before);
+        }
+      }
       const int m = S.init_min_muts + (Hk - H0);
-      const double lw = region_log_W(S, r.t_min, r.t_max, m, tNode);
+      const double lw = region_log_W(S, r.t_min, r.t_max, m, sm.tNode[n]);
       if (idx >= 0 && idx < S.region_cap) {
         // 48-byte record written as three 16-byte stores
         int4* o = reinterpret_cast<int4*>(out + idx);
@@ -644,12 +767,11 @@ __global__ void __launch_bounds__(kTile, 3) spr_emit_kernel(ForestDev f, SprBatc
     }
   }
   // block max -> global max (ordered-integer atomicMax: exact, order independent)
-  const int lane = tid & 31, warp = tid >> 5;
   double wm = warp_max(wmax);
-  if (lane == 0) s_wmax[warp] = wm;
+  if (lane == 0) sm.wmax[warp] = wm;
   __syncthreads();
   if (warp == 0) {
-    wm = lane < kTile / 32 ? s_wmax[lane] : -CUDART_INF;
+    wm = lane < kTile / 32 ? sm.wmax[lane] : -CUDART_INF;
     wm = warp_max(wm);
     if (lane == 0 && wm > -CUDART_INF) atomicMax(&B.studies[study].max_key, f64_order_key(wm));
   }

@@ -144,6 +144,12 @@ void* dphy_ctx_stream(dphy_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t dphy_ctx_launch_count(const dphy_ctx* ctx);
 
+/* Page-locked host memory for the arrays of dphy_emat_host.  dphy_forest_upload DMAs straight out of buffers obtained
+ * here (or registered by the caller with cudaHostRegister); pageable buffers are staged through the ctx's own pinned slab by
+ * worker threads.  The analogue on the reference side is the arena a Phylo_tree's vectors live in (core/scratch_space.h). */
+int  dphy_host_alloc(dphy_ctx* ctx, size_t bytes, void** out);
+void dphy_host_free(dphy_ctx* ctx, void* p);
+
 /* Which kernels dphy_forest_eval_log_G uses.  AUTO: forests whose site tables all have uniform nu_l take the folded path
  * (per-branch state-count vectors built at upload; the per-event lists are only walked for the mutation times);
  * GENERAL: always the per-event path (the only one when there is site-rate heterogeneity).  Results agree to ~1e-13. */
