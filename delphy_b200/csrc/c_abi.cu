@@ -132,6 +132,11 @@ void dphy_ctx_destroy(dphy_ctx* ctx) {
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pinned_ev) cudaEventDestroy(ctx->pinned_ev);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaEventDestroy(ctx->ev_main); cudaEventDestroy(ctx->ev_topo); cudaEventDestroy(ctx->ev_lists);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -299,7 +304,7 @@ namespace {
 // Host -> device copy of many caller-owned (pageable) arrays: worker threads memcpy 2 MiB chunks into the pinned
 // staging slab while the main thread issues the H2D DMA of every finished chunk, so the memcpy and the PCIe transfer
 // overlap and the host never touches the data more than once.
-struct CopyJob { size_t dst_off; const void* src; size_t bytes; };
+struct CopyJob { size_t dst_off; const void* src; size_t bytes; int group; };   // group 0: topology (needed first), 1: the rest
 
 bool is_pinned_host(const void* p) {
   cudaPointerAttributes a{};
@@ -307,7 +312,19 @@ bool is_pinned_host(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char* d_base, size_t total) {
+int ensure_copy_stream(dphy_ctx* ctx) {
+  if (ctx->copy_stream) return DPHY_OK;
+  DPHY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
+  DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_topo, cudaEventDisableTiming));
+  DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_lists, cudaEventDisableTiming));
+  return DPHY_OK;
+}
+
+// *two_phase is set when the copies went to ctx->copy_stream: ev_topo fires once the group-0 arrays (and every byte no job
+// covers) have landed, ev_lists once everything has.
+int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char* d_base, size_t total, bool* two_phase) {
+  *two_phase = false;
   if (total == 0) return DPHY_OK;
   constexpr size_t kChunk = (size_t)2 << 20;
   const size_t nchunks = (total + kChunk - 1) / kChunk;
@@ -318,14 +335,25 @@ int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char*
     bool all_pinned = !jobs.empty();
     for (const CopyJob& j : jobs) if (!is_pinned_host(j.src)) { all_pinned = false; break; }
     if (all_pinned) {
-      cudaError_t ce = cudaSuccess;
+      int st = ensure_copy_stream(ctx);
+      if (st != DPHY_OK) return st;
+      cudaStream_t cs = ctx->copy_stream;
+      // the destination was allocated (stream-ordered) and partly cleared on the main stream
+      cudaError_t ce = cudaEventRecord(ctx->ev_main, ctx->stream);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, ctx->ev_main, 0);
       size_t cur = 0;
-      for (const CopyJob& j : jobs) {
-        if (ce == cudaSuccess && j.dst_off > cur) ce = cudaMemcpyAsync(d_base + cur, pinned + cur, j.dst_off - cur, cudaMemcpyHostToDevice, ctx->stream);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_base + j.dst_off, j.src, j.bytes, cudaMemcpyHostToDevice, ctx->stream);
+      for (const CopyJob& j : jobs) {      // gaps + topology
+        if (ce == cudaSuccess && j.dst_off > cur) ce = cudaMemcpyAsync(d_base + cur, pinned + cur, j.dst_off - cur, cudaMemcpyHostToDevice, cs);
+        if (ce == cudaSuccess && j.group == 0) ce = cudaMemcpyAsync(d_base + j.dst_off, j.src, j.bytes, cudaMemcpyHostToDevice, cs);
         cur = std::max(cur, j.dst_off + j.bytes);
       }
-      if (ce == cudaSuccess && cur < total) ce = cudaMemcpyAsync(d_base + cur, pinned + cur, total - cur, cudaMemcpyHostToDevice, ctx->stream);
+      if (ce == cudaSuccess && cur < total) ce = cudaMemcpyAsync(d_base + cur, pinned + cur, total - cur, cudaMemcpyHostToDevice, cs);
+      if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_topo, cs);
+      for (const CopyJob& j : jobs)        // the bulky per-node / per-event arrays
+        if (ce == cudaSuccess && j.group != 0) ce = cudaMemcpyAsync(d_base + j.dst_off, j.src, j.bytes, cudaMemcpyHostToDevice, cs);
+      if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_lists, cs);
+      *two_phase = ce == cudaSuccess;
+      if (ce != cudaSuccess) cudaStreamSynchronize(cs);   // nothing may still be writing when the caller frees the destination
       return check_cuda(ctx, ce, "H2D direct upload");
     }
   }
@@ -530,8 +558,8 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     R.miss_off = tmp.at<int32_t>(tbase, r.ioff); R.miss_start = tmp.at<int32_t>(tbase, r.is); R.miss_end = tmp.at<int32_t>(tbase, r.ie);
     R.fs_off = tmp.at<int32_t>(tbase, r.foff); R.fs_site = tmp.at<int32_t>(tbase, r.fsite); R.fs_from = tmp.at<uint8_t>(tbase, r.ffrom);
     R.root = e.root; R.num_nodes = n; R.num_muts = (int32_t)m; R.num_ivls = (int32_t)iv; R.num_fs = (int32_t)fs; R.pad = 0;
-    auto add = [&](int id, const void* src, size_t bytes) { if (bytes) jobs.push_back({tmp.blocks[id].off, src, bytes}); };
-    add(r.parent, e.parent, 4 * (size_t)n); add(r.c0, e.child0, 4 * (size_t)n); add(r.c1, e.child1, 4 * (size_t)n); add(r.t, e.t, 8 * (size_t)n);
+    auto add = [&](int id, const void* src, size_t bytes, int group = 1) { if (bytes) jobs.push_back({tmp.blocks[id].off, src, bytes, group}); };
+    add(r.parent, e.parent, 4 * (size_t)n, 0); add(r.c0, e.child0, 4 * (size_t)n, 0); add(r.c1, e.child1, 4 * (size_t)n, 0); add(r.t, e.t, 8 * (size_t)n);
     add(r.moff, e.mut_off, 4 * ((size_t)n + 1)); add(r.msite, e.mut_site, 4 * m); add(r.mfrom, e.mut_from, m); add(r.mto, e.mut_to, m); add(r.mt, e.mut_t, 8 * m);
     add(r.ioff, e.miss_off, 4 * ((size_t)n + 1)); add(r.is, e.miss_start, 4 * iv); add(r.ie, e.miss_end, 4 * iv);
     add(r.foff, e.fs_off, 4 * ((size_t)n + 1)); add(r.fsite, e.fs_site, 4 * fs); add(r.ffrom, e.fs_from, fs);
@@ -544,8 +572,9 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   if (ce != cudaSuccess) return fail(check_cuda(ctx, ce, "H2D forest header"));
   // the RawTreeDev records were written straight into the pinned slab above; everything in [0, raw_upload_bytes) not
   // covered by a job (those records, alignment gaps) is copied as it lies
-  st = staged_upload(ctx, hraw, jobs, tbase, raw_upload_bytes);
-  release_pinned_async(ctx);
+  bool two_phase = false;
+  st = staged_upload(ctx, hraw, jobs, tbase, raw_upload_bytes, &two_phase);
+  if (!two_phase) release_pinned_async(ctx);
   if (st != DPHY_OK) return fail(st);
 
   ForestDev& h = fo->h;
@@ -592,7 +621,19 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   P.fs_off = const_cast<int32_t*>(h.fs_off); P.fs_site = const_cast<int32_t*>(h.fs_site); P.fs_code = const_cast<uint8_t*>(h.fs_code);
   P.fsw = const_cast<int16_t*>(h.fsw); P.fsw_stride = fsw_stride;
   P.bw = const_cast<int32_t*>(h.bw);
-  st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes);
+  if (two_phase) {
+    // Euler-tour ranking as soon as the topology arrays have landed; the rest once the lists have
+    ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_topo, 0);
+    if (ce != cudaSuccess) return fail(check_cuda(ctx, ce, "wait topology upload"));
+    st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes, 0);
+    if (st != DPHY_OK) { cudaStreamSynchronize(ctx->copy_stream); return fail(st); }
+    ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_lists, 0);
+    if (ce != cudaSuccess) { cudaStreamSynchronize(ctx->copy_stream); return fail(check_cuda(ctx, ce, "wait list upload")); }
+    release_pinned_async(ctx);
+    st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes, 1);
+  } else {
+    st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes);
+  }
   if (st != DPHY_OK) return fail(st);
   std::vector<int32_t> status(4 + num_trees, 0);
   ce = cudaMemcpyAsync(status.data(), P.status, sizeof(int32_t) * status.size(), cudaMemcpyDeviceToHost, ctx->stream);

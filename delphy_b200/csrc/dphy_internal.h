@@ -46,7 +46,7 @@ struct SitesDev {
   const double* munu;        // [L]  mu_{beta(l)} * nu_l
   const double* cumQ;        // [L+1] calc_cum_Q_l_for_sequence
   const int32_t* ref_freq;   // [P*4] state frequencies of the reference sequence per partition
-  const int32_t* cref;       // [P*4][L+1] cref[(b*4+a)*(L+1)+l] = #{l' < l : partition(l') == b, ref[l'] == a}  (structure only)
+  const int32_t* cref;       // [L+1][P*4] cref[l*4P + b*4+a] = #{l' < l : partition(l') == b, ref[l'] == a}  (structure only; 16-byte aligned)
   double mu[kMaxPartitions];
   double pi[kMaxPartitions * 4];
   double q[kMaxPartitions * 16];     // q_ab
@@ -181,6 +181,10 @@ struct dphy_ctx {
   size_t pinned_bytes = 0;
   cudaEvent_t pinned_ev = nullptr;   // recorded after the last async copy out of `pinned`
   bool pinned_in_flight = false;
+  // second stream for direct (pinned-source) uploads: the list arrays are still in flight over PCIe while the main stream
+  // already ranks the Euler tour of the topology arrays that arrived first
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_topo = nullptr, ev_lists = nullptr;
   bool logg_attr_set = false;   // opt-in dynamic shared memory of the log-G tile kernel
   int logg_path = 0;            // DPHY_LOG_G_PATH_*: 0 auto (folded fast path when every site table has uniform nu), 1 general
 };
@@ -252,7 +256,8 @@ int gather_lambda_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, double* d
 int gather_nsmn_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* d_dst);
 int refresh_sites(dphy_ctx* ctx, dphy_forest* f);   // c_abi.cu
 // kernels_flatten.cu
-int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max_tree_nodes);
+// stage 0: Euler-tour ranking (needs parent / child0 / child1 only); stage 1: everything else; -1: both
+int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max_tree_nodes, int stage = -1);
 int launch_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count, uint32_t* d_status);
 // Pinned staging buffer of the ctx: acquire waits for the previous async copy out of it; release records an event.
 int acquire_pinned(dphy_ctx* ctx, size_t bytes, void** out);

@@ -179,93 +179,126 @@ __global__ void __launch_bounds__(kTile) flatten_scan_apply_kernel(FlattenParams
 }
 
 // ---- (3c) lists to device order: packed codes + range validation -------------------------------------------------------------------------
+// One CTA per tile of kTile device positions.  The destination ranges of a tile are contiguous (CSR in device order), so the
+// lists are copied FLAT -- one destination event per thread, its node found by binary search in the tile's offsets held in
+// shared memory -- which keeps every store coalesced and the gathers independent, however the events spread over the nodes.
+__device__ __forceinline__ int tile_owner(const int* s_dst, int e) {   // last n in [0, kTile) with s_dst[n] <= e
+  int lo = 0, hi = kTile - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (s_dst[mid] <= e) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(kTile) flatten_events_kernel(FlattenParams P) {
-  const int tile = blockIdx.x;
+  __shared__ int s_dst[3][kTile + 1];
+  __shared__ int s_src[3][kTile];
+  const int tile = blockIdx.x, tid = threadIdx.x;
   const int tree = P.tile_tree[tile];
   const TreeDev T = P.trees[tree];
   const RawTreeDev R = P.raw[tree];
   const SitesDev& S = P.sites[T.sites_id];
-  const int q = (tile - T.first_tile) * kTile + threadIdx.x;
-  if (q >= T.num_nodes) return;
-  const int p = T.node_base + q;
-  const int v = P.node_id[p];
+  const int q0 = (tile - T.first_tile) * kTile;
+  const int n_act = min(kTile, T.num_nodes - q0);
+  const int p0 = T.node_base + q0;
   const int L = S.L;
+  {
+    const int p = p0 + min(tid, n_act);          // inactive threads repeat the end offsets: they own no event
+    const int v = tid < n_act ? P.node_id[p] : 0;
+    s_dst[0][tid] = P.mut_off[p]; s_dst[1][tid] = P.miss_off[p]; s_dst[2][tid] = P.fs_off[p];
+    s_src[0][tid] = tid < n_act ? R.mut_off[v] : 0; s_src[1][tid] = tid < n_act ? R.miss_off[v] : 0; s_src[2][tid] = tid < n_act ? R.fs_off[v] : 0;
+    if (tid == 0) { s_dst[0][kTile] = P.mut_off[p0 + n_act]; s_dst[1][kTile] = P.miss_off[p0 + n_act]; s_dst[2][kTile] = P.fs_off[p0 + n_act]; }
+  }
+  __syncthreads();
   uint32_t err = 0;
-  {
-    const int src = R.mut_off[v], dst = P.mut_off[p], cnt = P.mut_off[p + 1] - dst;
-    for (int i = 0; i < cnt; ++i) {
-      int l = R.mut_site[src + i];
-      const int from = R.mut_from[src + i], to = R.mut_to[src + i];
-      if (l < 0 || l >= L) { err |= kFlattenErrMutSite; l = 0; }
-      if (from > 3 || to > 3) err |= kFlattenErrMutState;
-      P.mut_site[dst + i] = l;
-      P.mut_code[dst + i] = (uint8_t)(S.part[l] << 4 | (from & 3) << 2 | (to & 3));
-      P.mut_t[dst + i] = R.mut_t[src + i];
-    }
+  for (int e = s_dst[0][0] + tid; e < s_dst[0][kTile]; e += kTile) {
+    const int n = tile_owner(s_dst[0], e);
+    const int src = s_src[0][n] + (e - s_dst[0][n]);
+    int l = R.mut_site[src];
+    const int from = R.mut_from[src], to = R.mut_to[src];
+    if (l < 0 || l >= L) { err |= kFlattenErrMutSite; l = 0; }
+    if (from > 3 || to > 3) err |= kFlattenErrMutState;
+    P.mut_site[e] = l;
+    P.mut_code[e] = (uint8_t)(S.part[l] << 4 | (from & 3) << 2 | (to & 3));
+    P.mut_t[e] = R.mut_t[src];
   }
-  {
-    const int src = R.miss_off[v], dst = P.miss_off[p], cnt = P.miss_off[p + 1] - dst;
-    for (int i = 0; i < cnt; ++i) {
-      int s0 = R.miss_start[src + i], s1 = R.miss_end[src + i];
-      if (s0 < 0 || s1 > L || s0 >= s1) { err |= kFlattenErrMissation; s0 = 0; s1 = 1; }   // core/mutations.h:187-191
-      P.miss_se[dst + i] = make_int2(s0, s1);
-    }
+  for (int e = s_dst[1][0] + tid; e < s_dst[1][kTile]; e += kTile) {
+    const int n = tile_owner(s_dst[1], e);
+    const int src = s_src[1][n] + (e - s_dst[1][n]);
+    int s0 = R.miss_start[src], s1 = R.miss_end[src];
+    if (s0 < 0 || s1 > L || s0 >= s1) { err |= kFlattenErrMissation; s0 = 0; s1 = 1; }   // core/mutations.h:187-191
+    P.miss_se[e] = make_int2(s0, s1);
   }
-  {
-    const int src = R.fs_off[v], dst = P.fs_off[p], cnt = P.fs_off[p + 1] - dst;
-    int w[kMaxPartitions * 4];
-#pragma unroll
-    for (int k = 0; k < kMaxPartitions * 4; ++k) w[k] = 0;
-    for (int i = 0; i < cnt; ++i) {
-      int l = R.fs_site[src + i];
-      const int from = R.fs_from[src + i];
-      if (l < 0 || l >= L) { err |= kFlattenErrMissation; l = 0; }
-      if (from > 3) err |= kFlattenErrFsState;
-      const int pt = S.part[l], rf = S.ref[l];
-      P.fs_site[dst + i] = l;
-      P.fs_code[dst + i] = (uint8_t)(pt << 4 | rf << 2 | (from & 3));
-#pragma unroll
-      for (int k = 0; k < kMaxPartitions * 4; ++k) w[k] += (int)(k == pt * 4 + rf) - (int)(k == pt * 4 + (from & 3));
-    }
-#pragma unroll
-    for (int k = 0; k < kMaxPartitions * 4; ++k) if (k < P.fsw_stride) P.fsw[(size_t)p * P.fsw_stride + k] = (int16_t)w[k];
+  for (int e = s_dst[2][0] + tid; e < s_dst[2][kTile]; e += kTile) {
+    const int n = tile_owner(s_dst[2], e);
+    const int src = s_src[2][n] + (e - s_dst[2][n]);
+    int l = R.fs_site[src];
+    const int from = R.fs_from[src];
+    if (l < 0 || l >= L) { err |= kFlattenErrMissation; l = 0; }
+    if (from > 3) err |= kFlattenErrFsState;
+    P.fs_site[e] = l;
+    P.fs_code[e] = (uint8_t)(S.part[l] << 4 | S.ref[l] << 2 | (from & 3));
   }
   if (err) flag_error(P, err);
 }
 
-// ---- (3d) every per-branch list folded into one 4P-vector of state counts (see ForestDev::bw) --------------------------------------
+// ---- (3d) every per-branch list folded into one 4P-vector of state counts (see ForestDev::bw; fsw = the from-state part) -----------
 // Structure only: depends on the tree, its lists, the reference sequence and the partition map -- not on the evo model.
+// Flat over the tile's events again; an interval turns into 4P counts with two 16-byte look-ups per partition in the
+// interleaved cumulative table cref[l][4P]; per-node sums are integer shared-memory atomics (exact, order-free).
+constexpr int kBwRow = kMaxPartitions * 4 + 1;      // padded row: conflict-free when every thread walks its own row
 __global__ void __launch_bounds__(kTile) fold_branch_weights_kernel(FlattenParams P) {
-  const int tile = blockIdx.x;
+  __shared__ int s_w[kTile * kBwRow];
+  __shared__ int s_f[kTile * kBwRow];
+  __shared__ int s_dst[3][kTile + 1];
+  const int tile = blockIdx.x, tid = threadIdx.x;
   const int tree = P.tile_tree[tile];
   const TreeDev T = P.trees[tree];
   const SitesDev& S = P.sites[T.sites_id];
-  const int q = (tile - T.first_tile) * kTile + threadIdx.x;
-  if (q >= T.num_nodes) return;
-  const int p = T.node_base + q;
-  const int stride = P.fsw_stride;
-  const size_t Lp1 = (size_t)S.L + 1;
-  int w[kMaxPartitions * 4];
-#pragma unroll
-  for (int k = 0; k < kMaxPartitions * 4; ++k) w[k] = 0;
-  for (int i = P.mut_off[p]; i < P.mut_off[p + 1]; ++i) {
-    const int code = P.mut_code[i], pt = code >> 4, x = (code >> 2) & 3, y = code & 3;
-#pragma unroll
-    for (int k = 0; k < kMaxPartitions * 4; ++k) w[k] += (int)(k == pt * 4 + y) - (int)(k == pt * 4 + x);
+  const int q0 = (tile - T.first_tile) * kTile;
+  const int n_act = min(kTile, T.num_nodes - q0);
+  const int p0 = T.node_base + q0;
+  const int stride = P.fsw_stride, K = S.P * 4;
+  for (int i = tid; i < kTile * kBwRow; i += kTile) { s_w[i] = 0; s_f[i] = 0; }
+  {
+    const int p = p0 + min(tid, n_act);
+    s_dst[0][tid] = P.mut_off[p]; s_dst[1][tid] = P.miss_off[p]; s_dst[2][tid] = P.fs_off[p];
+    if (tid == 0) { s_dst[0][kTile] = P.mut_off[p0 + n_act]; s_dst[1][kTile] = P.miss_off[p0 + n_act]; s_dst[2][kTile] = P.fs_off[p0 + n_act]; }
   }
-  for (int i = P.miss_off[p]; i < P.miss_off[p + 1]; ++i) {
-    const int2 se = P.miss_se[i];
-#pragma unroll
-    for (int k = 0; k < kMaxPartitions * 4; ++k)
-      if (k < S.P * 4) w[k] -= __ldg(S.cref + k * Lp1 + se.y) - __ldg(S.cref + k * Lp1 + se.x);
+  __syncthreads();
+  for (int e = s_dst[0][0] + tid; e < s_dst[0][kTile]; e += kTile) {
+    const int n = tile_owner(s_dst[0], e);
+    const int code = P.mut_code[e], pt = code >> 4, x = (code >> 2) & 3, y = code & 3;
+    if (x != y) { atomicAdd(&s_w[n * kBwRow + pt * 4 + y], 1); atomicSub(&s_w[n * kBwRow + pt * 4 + x], 1); }
   }
-  for (int i = P.fs_off[p]; i < P.fs_off[p + 1]; ++i) {
-    const int code = P.fs_code[i], pt = code >> 4, rf = (code >> 2) & 3, fr = code & 3;
-#pragma unroll
-    for (int k = 0; k < kMaxPartitions * 4; ++k) w[k] += (int)(k == pt * 4 + rf) - (int)(k == pt * 4 + fr);
+  const int4* __restrict__ cref4 = reinterpret_cast<const int4*>(S.cref);
+  for (int e = s_dst[1][0] + tid; e < s_dst[1][kTile]; e += kTile) {
+    const int n = tile_owner(s_dst[1], e);
+    const int2 se = P.miss_se[e];
+    for (int b = 0; b < S.P; ++b) {
+      const int4 hi = __ldg(cref4 + (size_t)se.y * S.P + b), lo = __ldg(cref4 + (size_t)se.x * S.P + b);
+      int* w = &s_w[n * kBwRow + b * 4];
+      if (hi.x != lo.x) atomicSub(w + 0, hi.x - lo.x);
+      if (hi.y != lo.y) atomicSub(w + 1, hi.y - lo.y);
+      if (hi.z != lo.z) atomicSub(w + 2, hi.z - lo.z);
+      if (hi.w != lo.w) atomicSub(w + 3, hi.w - lo.w);
+    }
   }
-#pragma unroll
-  for (int k = 0; k < kMaxPartitions * 4; ++k) if (k < stride) P.bw[(size_t)p * stride + k] = w[k];
+  for (int e = s_dst[2][0] + tid; e < s_dst[2][kTile]; e += kTile) {
+    const int n = tile_owner(s_dst[2], e);
+    const int code = P.fs_code[e], pt = code >> 4, rf = (code >> 2) & 3, fr = code & 3;
+    if (rf != fr) { atomicAdd(&s_f[n * kBwRow + pt * 4 + rf], 1); atomicSub(&s_f[n * kBwRow + pt * 4 + fr], 1); }
+  }
+  __syncthreads();
+  if (tid < n_act) {
+    const int p = p0 + tid;
+    for (int k = 0; k < stride; ++k) {
+      const int fk = k < K ? s_f[tid * kBwRow + k] : 0;
+      P.fsw[(size_t)p * stride + k] = (int16_t)fk;
+      P.bw[(size_t)p * stride + k] = (k < K ? s_w[tid * kBwRow + k] : 0) + fk;
+    }
+  }
 }
 
 // ---- (4) log-G tile descriptors: event ranges, closer slice, staging size; fast / slow classification ---------------------------
@@ -306,14 +339,18 @@ int launch_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_
   return check_cuda(ctx, cudaGetLastError(), "set_node_times_kernel");
 }
 
-int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max_tree_nodes) {
+int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max_tree_nodes, int stage) {
   if (P.num_nodes == 0) return DPHY_OK;
   const int num_arcs = 2 * P.num_nodes;
-  flatten_arcs_init_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
   int rounds = 0;
   while ((1LL << rounds) < 2LL * max_tree_nodes) ++rounds;
-  for (int r = 0; r < rounds; ++r)
-    flatten_rank_round_kernel<<<(num_arcs + 255) / 256, 256, 0, ctx->stream>>>(P.arcs[r & 1], P.arcs[(r + 1) & 1], num_arcs);
+  if (stage != 1) {
+    flatten_arcs_init_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
+    for (int r = 0; r < rounds; ++r)
+      flatten_rank_round_kernel<<<(num_arcs + 255) / 256, 256, 0, ctx->stream>>>(P.arcs[r & 1], P.arcs[(r + 1) & 1], num_arcs);
+    ctx->launches += 1 + rounds;
+    if (stage == 0) return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch (topology)");
+  }
   flatten_nodes_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P, rounds & 1);
   const int nst = (P.num_nodes + kScanTile - 1) / kScanTile;
   flatten_scan_reduce_kernel<<<nst, kTile, 0, ctx->stream>>>(P);
@@ -322,7 +359,7 @@ int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max
   flatten_events_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
   fold_branch_weights_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
   flatten_ctiles_kernel<<<(P.num_ctiles + 255) / 256, 256, 0, ctx->stream>>>(P);
-  ctx->launches += 8 + rounds;
+  ctx->launches += 7;
   return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch");
 }
 

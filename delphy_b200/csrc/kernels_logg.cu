@@ -47,7 +47,6 @@ struct LogGParams {
   int32_t* sd_n;         // [num_nodes] missing-site count of the straddlers (sparse)
   const int32_t* strad_list;   // device positions of the straddlers
   int32_t num_strad;
-  uint32_t* tree_done;   // [num_trees] folded path: tiles of the tree that have published their partials (self-resetting)
   int32_t debug_mask;    // profiling only (DPHY_DEBUG_MASK): 1 skip mutations, 2 intervals, 4 from-states, 8 closers
 };
 
@@ -686,8 +685,6 @@ struct FoldSmem {
   double clx[kLgTile + 2];
   double wsd[kNW * 2];
   double muq[kMaxPartitions * 4];
-  double carry;
-  int last;
 };
 
 __device__ __forceinline__ double block_scan_excl1(double& a, double* wsd) {   // returns the block total; a <- exclusive prefix
@@ -724,7 +721,8 @@ __device__ __forceinline__ double folded_delta(const int32_t* __restrict__ bw, i
   return d;
 }
 
-__global__ void __launch_bounds__(kLgThreads, 5) emat_log_G_folded_kernel(const LogGParams P) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_folded_kernel(const __grid_constant__ LogGParams P) {
   __shared__ FoldSmem sm;
   const ForestDev& f = P.f;
   const int tid = threadIdx.x;
@@ -735,6 +733,11 @@ __global__ void __launch_bounds__(kLgThreads, 5) emat_log_G_folded_kernel(const 
   const SitesDev& S = f.sites[ct.w];
   const int stride = f.fsw_stride;
   if (tid < kMaxPartitions * 4) sm.muq[tid] = S.tab_muq[tid];
+  // the first chunk of the tile's closer slice does not depend on anything else: get it in flight together with the node records
+  const int32_t* __restrict__ post = f.post_node + node_base;
+  int pre_post[2] = {-1, -1};
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { const int j = cl.z + 2 * tid + u; if (j < cl.w) pre_post[u] = __ldg(post + j); }
   __syncthreads();
 
   // ---- node records: 2 consecutive positions per thread ------------------------------------------------------------------------------
@@ -790,7 +793,6 @@ __global__ void __launch_bounds__(kLgThreads, 5) emat_log_G_folded_kernel(const 
     const int cl0 = cl.z, cl1 = cl.w;
     const int q_first = tile_start - node_base;
     const int myc0 = act0 ? (q_first + q0) - dep[0] : cl0, myc1 = act1 ? (q_first + q0 + 1) - dep[1] : cl0;
-    const int32_t* __restrict__ post = f.post_node + node_base;
     double carry = 0.0;
     for (int c0 = cl0; c0 < cl1; c0 += kLgTile) {
       double a[2] = {0.0, 0.0};
@@ -798,7 +800,7 @@ __global__ void __launch_bounds__(kLgThreads, 5) emat_log_G_folded_kernel(const 
       for (int u = 0; u < 2; ++u) {
         const int j = c0 + 2 * tid + u;
         if (j < cl1) {
-          const int p = __ldg(post + j);
+          const int p = c0 == cl0 ? pre_post[u] : __ldg(post + j);
           const int qa = p - tile_start;
           a[u] = qa >= 0 ? sm.dl[qa] : folded_delta(f.bw, stride, sm.muq, p);   // straddler: opened in an earlier tile
         }
@@ -842,45 +844,40 @@ __global__ void __launch_bounds__(kLgThreads, 5) emat_log_G_folded_kernel(const 
       if (lane == 0) { P.tile_part[tile * 2 + 0] = a; P.tile_part[tile * 2 + 1] = b; }
     }
   }
+}
 
-  // ---- pass 2, fused: the CTA that publishes the last tile of a tree folds the tree (no second launch, no spinning) -------------------
-  // Exclusive scan of the tile aggregates in tile order, log G = sum_tiles (A1 - prefix * A2), root prior from the root's folded
-  // weights (ref_freq + bw[root] is exactly the state-count vector of core/phylo_tree_calc.cpp:467-504).  The fold reads the
-  // partials in a fixed order whichever CTA happens to run it, so the result does not depend on the schedule.
-  const int tree = __ldg(f.ctile_tree + tile);
-  __threadfence();                         // my tile_agg / tile_part stores are visible device-wide before the ticket
-  __syncthreads();
-  if (tid == 0) {
-    const TreeDev& T0 = f.trees[tree];
-    const uint32_t done = atomicAdd(P.tree_done + tree, 1u);
-    sm.last = done == (uint32_t)T0.num_ctiles - 1u;
-    if (sm.last) P.tree_done[tree] = 0u;   // re-arm for the next evaluation
-    sm.carry = 0.0;
-  }
-  __syncthreads();
-  if (!sm.last) return;
-  __threadfence();
+// pass 2 of the folded path: one CTA per tree -- exclusive scan of the tile aggregates, log G fold, root prior from the root's
+// folded weights (ref_freq + bw[root] is exactly the state count vector of core/phylo_tree_calc.cpp:467-504).
+__global__ void __launch_bounds__(kTreeThreads) emat_log_G_folded_tree_kernel(const LogGParams P) {
+  __shared__ double s_wsd[kTreeThreads / 32];
+  __shared__ double s_carry;
+  const ForestDev& f = P.f;
+  const int tid = threadIdx.x;
+  const int tree = blockIdx.x;
   const TreeDev T = f.trees[tree];
+  const SitesDev& S = f.sites[T.sites_id];
+  if (tid == 0) s_carry = 0.0;
+  __syncthreads();
   double a1 = 0.0, a2 = 0.0;
-  for (int j0 = 0; j0 < T.num_ctiles; j0 += kLgThreads) {
+  for (int j0 = 0; j0 < T.num_ctiles; j0 += kTreeThreads) {
     const int j = T.first_ctile + j0 + tid;
     const bool ok = j0 + tid < T.num_ctiles;
-    const double v = ok ? __ldcg(P.tile_agg + j) : 0.0;
+    const double v = ok ? P.tile_agg[j] : 0.0;
     double tot;
-    const double incl = block_scan_incl<double, kLgThreads>(v, sm.wsd, &tot);
+    const double incl = block_scan_incl<double, kTreeThreads>(v, s_wsd, &tot);
     if (ok) {
-      const double pre = sm.carry + (incl - v);          // exclusive prefix of this tile
+      const double pre = s_carry + (incl - v);          // exclusive prefix of this tile
       P.tile_agg[j] = pre;
-      const double A1 = __ldcg(P.tile_part + j * 2 + 0), A2 = __ldcg(P.tile_part + j * 2 + 1);
-      a1 += A1 - pre * A2;                               // sum over the tile of -(lambda_local + pre) len + g
+      const double A1 = P.tile_part[j * 2 + 0], A2 = P.tile_part[j * 2 + 1];
+      a1 += A1 - pre * A2;                              // sum over the tile of -(lambda_local + pre) len + g
       a2 += A2;
     }
     __syncthreads();
-    if (tid == 0) sm.carry += tot;
+    if (tid == 0) s_carry += tot;
     __syncthreads();
   }
-  a1 = block_sum<double, kLgThreads>(a1, sm.wsd);
-  a2 = block_sum<double, kLgThreads>(a2, sm.wsd);
+  a1 = block_sum<double, kTreeThreads>(a1, s_wsd);
+  a2 = block_sum<double, kTreeThreads>(a2, s_wsd);
   if (tid == 0) {
     P.tree_out[tree * 4 + 1] = a1;
     P.tree_out[tree * 4 + 2] = a2;
@@ -988,9 +985,17 @@ static int launch_log_G_folded(dphy_ctx* ctx, dphy_forest* fo) {
   P.tile_agg = fo->d_tile_agg;
   P.tile_part = fo->d_tile_part;
   P.tree_out = fo->d_tree_out;
-  P.tree_done = fo->d_tree_done;
-  emat_log_G_folded_kernel<<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
-  ctx->launches += 1;
+  // resident CTAs per SM: 6 (40 registers) by default -- measured fastest (the kernel is latency-bound); DPHY_FOLDED_OCC = 4 / 5 / 8
+  // selects the 64- / 48- / 32-register builds (tuning knob)
+  static const int occ = [] { const char* e = getenv("DPHY_FOLDED_OCC"); return e ? atoi(e) : 6; }();
+  if (occ == 4) emat_log_G_folded_kernel<4><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
+  else if (occ == 5) emat_log_G_folded_kernel<5><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
+  else if (occ == 8) emat_log_G_folded_kernel<8><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
+  else emat_log_G_folded_kernel<6><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
+  // one CTA per tree folds the tile partials (fusing this into the tile kernel with a last-CTA ticket was measured slower:
+  // every CTA then waits a device-wide atomic round trip before it can retire -- 102 vs 96 us per evaluation)
+  emat_log_G_folded_tree_kernel<<<fo->h.num_trees, kTreeThreads, 0, ctx->stream>>>(P);
+  ctx->launches += 2;
   return check_cuda(ctx, cudaGetLastError(), "emat_log_G folded kernels launch");
 }
 

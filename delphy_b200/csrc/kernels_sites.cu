@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(kScanThreads) sites_derive_kernel(
   }
 }
 
-// Cumulative reference-state counts per (partition, state): cref[(b*4+a)*(L+1) + l] = #{l' < l : beta(l') == b, ref[l'] == a}.
+// Cumulative reference-state counts per (partition, state), interleaved by site:
+// cref[l*(4P) + b*4+a] = #{l' < l : beta(l') == b, ref[l'] == a}  (one 16-byte look-up per partition and interval end).
 // Structure only (reference sequence + partition map), so it is built once per sites table.  One CTA per (b, a) row.
 // fold_branch_weights_kernel uses it to turn a missation interval into the 4P state counts of the sites it hides.
 __global__ void __launch_bounds__(kScanThreads) sites_ref_counts_kernel(int L, const uint8_t* __restrict__ ref,
@@ -91,11 +92,11 @@ __global__ void __launch_bounds__(kScanThreads) sites_ref_counts_kernel(int L, c
   int tot;
   const int incl = block_scan_incl<int, kScanThreads>(c, s_ws, &tot);
   int run = incl - c;
-  int32_t* out = cref + (size_t)k * (L + 1);
-  if (tid == 0) out[0] = 0;
+  const size_t K = gridDim.x;
+  if (tid == 0) cref[k] = 0;
   for (int l = l0; l < l1; ++l) {
     run += (part[l] * 4 + ref[l] == k);
-    out[l + 1] = run;
+    cref[(size_t)(l + 1) * K + k] = run;
   }
 }
 

@@ -36,7 +36,7 @@ struct SprStudy {
   double t_X, lambda_X, f, t_max_tip;
   // slab offsets in bytes
   int64_t off_xtab, off_xkey, off_path, off_xpath, off_H, off_C, off_KB, off_seg, off_regions, off_xd_site, off_xd_to, off_xm_start,
-      off_xm_end, off_part, off_pae;
+      off_xm_end, off_part, off_pae, off_lw;
   int32_t region_cap, path_cap;
   // ---- derived (spr_setup_kernel) ----
   int32_t node_base, num_nodes, num_tiles, L;
@@ -419,22 +419,26 @@ __global__ void __launch_bounds__(kTile) spr_scan_kernel(ForestDev f, SprBatchDe
         else node_dc(f, V.xtab, a, ah, ac);
         const int qc = a + f.subtree_size[a] - tile_start;        // position right after a's subtree: inside this tile
         if (ah) atomicSub(&s_dh[qc], ah);
-        if (ac) atomicSub(&s_dc[qc], ac);
+        if (limited && ac) atomicSub(&s_dc[qc], ac);   // C (counted-mutation depth) only feeds the scope test of bounded studies
       }
     }
     __syncthreads();
-    int toth, totc, totk = 0;
+    int toth, totc = 0, totk = 0;
     const int ih = block_scan_incl<int, kTile>(s_dh[tid], s_ws, &toth);
     __syncthreads();
-    const int ic = block_scan_incl<int, kTile>(s_dc[tid], s_ws, &totc);
-    __syncthreads();
+    int ic = 0;
+    if (limited) {
+      ic = block_scan_incl<int, kTile>(s_dc[tid], s_ws, &totc);
+      __syncthreads();
+    }
     int kc = 0, ik = 0;
     if (!limited) {
       if (active) kc = node_kept_count(f, S, V, p, false, 0);
       ik = block_scan_incl<int, kTile>(kc, s_ws, &totk);
     }
     if (active) {
-      Hloc[q] = ih; Cloc[q] = ic;
+      Hloc[q] = ih;
+      if (limited) Cloc[q] = ic;
       if (!limited) {
         KBloc[q] = ik - kc;
         if (q == N - 1) KBloc[N] = (N % kTile) ? ik : 0;      // KB(N): one past the end, same tile unless N is a tile multiple
@@ -486,7 +490,7 @@ __device__ void spr_tile_prefix(const ForestDev& f, SprBatchDev& B, SprStudy& S,
       const SprView V = make_view(B, S, study);
       const int par = f.parent_pos[S.pos0];
       const bool top = par < 0 || S.pos0 == S.root_pos;
-      int c = top ? 0 : V.C(par - S.node_base);
+      int c = (top || S.limit == INT_MAX) ? 0 : V.C(par - S.node_base);
       int h = top ? 0 : V.H(par - S.node_base);
       if (S.pos0 != S.root_pos) {
         const int mo = f.mut_off[S.pos0];
@@ -637,6 +641,7 @@ __global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatc
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SprView V = make_view(B, S, study);
   dphy_candidate_region* out = (dphy_candidate_region*)(B.slab + S.off_regions);
+  double* lw_out = (double*)(B.slab + S.off_lw);
   const bool limited = S.limit != INT_MAX;
   const int C0 = S.C0, H0 = S.H0;
   const int kb_tile = V.agg[blockIdx.x * 3 + 2];      // kept regions before this tile (KBloc of the tile's first node is 0)
@@ -756,11 +761,12 @@ __global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatc
       const int m = S.init_min_muts + (Hk - H0);
       const double lw = region_log_W(S, r.t_min, r.t_max, m, sm.tNode[n]);
       if (idx >= 0 && idx < S.region_cap) {
-        // 48-byte record written as three 16-byte stores
+        // the first 32 bytes of the 48-byte record as two 16-byte stores; the raw log-weight goes to a compact array so that
+        // the normalisation pass reads 8 bytes per region instead of the whole record, and fills the last 16 bytes itself
         int4* o = reinterpret_cast<int4*>(out + idx);
         o[0] = make_int4(r.branch, r.mut_idx, __double2loint(r.t_min), __double2hiint(r.t_min));
         o[1] = make_int4(__double2loint(r.t_max), __double2hiint(r.t_max), m, 0);
-        o[2] = make_int4(__double2loint(lw), __double2hiint(lw), 0, 0);
+        lw_out[idx] = lw;
       }
       wmax = any ? fmax(wmax, lw) : lw;   // std::max semantics of the reference's running maximum
       any = true;
@@ -791,11 +797,11 @@ __global__ void __launch_bounds__(256) spr_normalize_kernel(SprBatchDev B) {
   const int per = (n + kNormBlocks - 1) / kNormBlocks;
   const int i0 = min((int)blockIdx.x * per, n), i1 = min(i0 + per, n);
   double acc = 0.0;
+  const double* lw_raw = (const double*)(B.slab + S.off_lw);
   for (int i = i0 + threadIdx.x; i < i1; i += 256) {
-    const double lw = out[i].log_W_over_Wmax - lmax;
+    const double lw = lw_raw[i] - lmax;
     const double w = exp(lw);
-    out[i].log_W_over_Wmax = lw;
-    out[i].W_over_Wmax = w;
+    *reinterpret_cast<double2*>(&out[i].log_W_over_Wmax) = make_double2(lw, w);   // (log_W_over_Wmax, W_over_Wmax): one 16-byte store
     acc += w;
   }
   acc = block_sum<double, 256>(acc, s_ws);
@@ -926,6 +932,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     S.off_xm_start = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_missing));
     S.off_xm_end = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_missing));
     S.off_regions = off; off = al(off + sizeof(dphy_candidate_region) * (size_t)S.region_cap);
+    S.off_lw = off; off = al(off + sizeof(double) * (size_t)S.region_cap);     // raw log-weights between emit and normalise
     if (S.n_x_deltas) {
       copies.push_back({(size_t)S.off_xd_site, r.x_delta_site}); copy_bytes.push_back(sizeof(int32_t) * S.n_x_deltas);
       copies.push_back({(size_t)S.off_xd_to, r.x_delta_to}); copy_bytes.push_back(S.n_x_deltas);

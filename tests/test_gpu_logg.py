@@ -187,7 +187,7 @@ def test_folded_and_general_paths_agree(orc):
         c.set_log_G_path("auto")
         launches = c.launches
         fo.eval_log_G()
-        assert c.launches - launches == 1            # one launch: the last tile of each tree folds the tree
+        assert c.launches - launches == 2            # folded tile kernel + per-tree fold
         rp_f, br_f, _ = fo.log_G()
         np.testing.assert_allclose(br_f, br_g, rtol=1e-12)
         np.testing.assert_allclose(rp_f, rp_g, rtol=1e-13)
