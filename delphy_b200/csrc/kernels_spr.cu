@@ -36,7 +36,7 @@ struct SprStudy {
   double t_X, lambda_X, f, t_max_tip;
   // slab offsets in bytes
   int64_t off_xtab, off_xkey, off_path, off_xpath, off_H, off_C, off_KB, off_seg, off_regions, off_xd_site, off_xd_to, off_xm_start,
-      off_xm_end, off_part, off_pae, off_lw;
+      off_xm_end, off_part, off_pae, off_lw, off_tj;
   int32_t region_cap, path_cap;
   // ---- derived (spr_setup_kernel) ----
   int32_t node_base, num_nodes, num_tiles, L;
@@ -572,6 +572,13 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
     __syncthreads();
   }
   if (tid == 0) S.total_regions = s_carry;
+  // classify() of the first and the last node of every tile: the deepest path node containing p is monotone in p on either side
+  // of the start node, so these bracket the search of every node of the tile (spr_emit_kernel)
+  int2* tj = (int2*)(B.slab + S.off_tj);
+  for (int t = tid; t < S.num_tiles; t += kSetupThreads) {
+    const int first = S.node_base + t * kTile, last = min(first + kTile, S.node_base + S.num_nodes) - 1;
+    tj[t] = make_int2(classify(V, first), classify(V, last));
+  }
 }
 
 // ---- (4) emit regions in the reference's DFS order, with raw log-weights ------------------------------------------------------------------
@@ -607,17 +614,17 @@ __device__ __forceinline__ double region_log_W(const SprStudy& S, double t_min, 
 // no matter how the mutations are distributed over the nodes.  For regions off the start->root path the output index is
 //   seg[2] - KB(sibling) + (KB(tile) + rank of the kept region inside the tile)
 // i.e. one ballot-scan of the keep flags per round; consecutive kept slots write consecutive 48-byte records.
-constexpr int kEmitMutCap = 3072;          // per-tile mutations whose (dH, counted) pair is cached in shared memory
+constexpr int kEmitSub = 4;                    // kTile-tiles per CTA: the per-CTA chain of dependent loads is amortised over 4x the nodes
+constexpr int kEmitNodes = kTile * kEmitSub;
+constexpr int kEmitMutCap = 4096;              // per-CTA mutations whose (dH, counted) pair is cached in shared memory
 
 struct EmitSmem {
-  SprStudy S;                              // the study record, read once (it lives in global memory)
-  double tPar[kTile], tNode[kTile];
-  int start[kTile + 1];                    // exclusive scan of the per-node candidate counts
-  int moff[kTile], np[kTile], Hpar[kTile], Cpar[kTile], hang[kTile], cls[kTile];   // cls = j << 1 | on_path
+  SprStudy S;                                  // the study record, read once (it lives in global memory)
+  int start[kEmitNodes + 1];                   // exclusive scan of the per-node candidate counts
+  int moff[kEmitNodes], np[kEmitNodes], Hpar[kEmitNodes], Cpar[kEmitNodes], hang[kEmitNodes], cls[kEmitNodes];   // cls = j << 1 | on_path
   int wcnt[kTile / 32];
   double wmax[kTile / 32];
-  int jb[2];
-  signed char dhc[kEmitMutCap];            // (dH + 1) | counted << 2
+  signed char dhc[kEmitMutCap];                // (dH + 1) | counted << 2
 };
 
 __device__ __forceinline__ void emit_mut_dc(const ForestDev& f, const EmitSmem& sm, const uint8_t* __restrict__ xtab, int m0, int i, int& dh, int& dc) {
@@ -629,9 +636,10 @@ __device__ __forceinline__ void emit_mut_dc(const ForestDev& f, const EmitSmem& 
 __global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatchDev B) {
   __shared__ EmitSmem sm;
   const int study = blockIdx.y;
+  const int t0 = blockIdx.x * kEmitSub;        // first kTile-tile of this CTA
   {
     const SprStudy& G = B.studies[study];
-    if ((int)blockIdx.x >= G.num_tiles || G.error) return;
+    if (t0 >= G.num_tiles || G.error) return;
     const int* src = reinterpret_cast<const int*>(&G);
     int* dst = reinterpret_cast<int*>(&sm.S);
     for (int i = threadIdx.x; i < (int)(sizeof(SprStudy) / sizeof(int)); i += kTile) dst[i] = src[i];
@@ -644,58 +652,66 @@ __global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatc
   double* lw_out = (double*)(B.slab + S.off_lw);
   const bool limited = S.limit != INT_MAX;
   const int C0 = S.C0, H0 = S.H0;
-  const int kb_tile = V.agg[blockIdx.x * 3 + 2];      // kept regions before this tile (KBloc of the tile's first node is 0)
-  if (V.agg[(blockIdx.x + 1) * 3 + 2] == kb_tile) return;   // nothing kept in this tile (X's subtree, X's future, out of scope)
-  const int tile_start = S.node_base + blockIdx.x * kTile;
-  const int tile_end = min(tile_start + kTile, S.node_base + S.num_nodes);
-  const int p = tile_start + tid;
+  const int t1 = min(t0 + kEmitSub, S.num_tiles);
+  const int kb_first = V.agg[t0 * 3 + 2];       // kept regions before this CTA's nodes (KBloc of a tile's first node is 0)
+  if (V.agg[t1 * 3 + 2] == kb_first) return;    // nothing kept here (X's subtree, X's future, out of scope)
+  const int cta_start = S.node_base + t0 * kTile;
+  const int cta_end = min(cta_start + kEmitNodes, S.node_base + S.num_nodes);
   const int xs = S.posX, xe = S.posX >= 0 ? S.posX + f.subtree_size[S.posX] : -1;
-
-  // the deepest path node containing p is monotone in p on either side of the start node: bracket the search once per tile
-  if (tid < 2) sm.jb[tid] = classify(V, tid == 0 ? tile_start : tile_end - 1);
-  const int m0 = f.mut_off[tile_start], m1 = f.mut_off[tile_end];
+  const int2* tj = (const int2*)(B.slab + S.off_tj);
+  const int jb0 = __ldg(&tj[t0].x), jb1 = __ldg(&tj[t1 - 1].y);
+  const int m0 = f.mut_off[cta_start], m1 = f.mut_off[cta_end];
   for (int g = m0 + tid; g < min(m1, m0 + kEmitMutCap); g += kTile) {
     int dh, dc; mut_dc(V.xtab, f.mut_site[g], f.mut_code[g] & 15, dh, dc);
     sm.dhc[g - m0] = (signed char)((dh + 1) | (dc << 2));
   }
-  __syncthreads();
 
-  // ---- (A) node records + slot offsets ------------------------------------------------------------------------------------------------
-  int cnt = 0;
-  const int par = p < tile_end ? f.parent_pos[p] : -1;
-  if (p < tile_end && !(xs >= 0 && p >= xs && p < xe) && !branch_in_Xs_future(f, S, p, par)) {
-    const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
-    const bool is_root = p == S.root_pos;
-    int lo = min(sm.jb[0], sm.jb[1]), hi = max(sm.jb[0], sm.jb[1]);
-    if (tile_start <= S.pos0 && S.pos0 < tile_end) lo = 0;      // the tile holds the start node: both sides of the bracket
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      const int2 ae = __ldg(V.pae + mid);
-      if (p >= ae.x && p < ae.y) hi = mid; else lo = mid + 1;
+  // ---- (A) node records + slot offsets: thread tid owns the kEmitSub consecutive nodes tid * kEmitSub .. ------------------------------
+  int cnt[kEmitSub];
+  int par[kEmitSub];
+#pragma unroll
+  for (int u = 0; u < kEmitSub; ++u) { const int p = cta_start + tid * kEmitSub + u; par[u] = p < cta_end ? f.parent_pos[p] : -1; }
+#pragma unroll
+  for (int u = 0; u < kEmitSub; ++u) {
+    const int n = tid * kEmitSub + u, p = cta_start + n;
+    cnt[u] = 0;
+    if (p < cta_end && !(xs >= 0 && p >= xs && p < xe) && !branch_in_Xs_future(f, S, p, par[u])) {
+      const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
+      const bool is_root = p == S.root_pos;
+      int lo = min(jb0, jb1), hi = max(jb0, jb1);
+      if (cta_start <= S.pos0 && S.pos0 < cta_end) lo = 0;       // the CTA holds the start node: both sides of the bracket
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int2 ae = __ldg(V.pae + mid);
+        if (p >= ae.x && p < ae.y) hi = mid; else lo = mid + 1;
+      }
+      const int j = lo;
+      const bool on_path = V.path[j] == p;
+      const int32_t* sg = V.seg + (size_t)j * kSegStride;
+      sm.moff[n] = moff; sm.np[n] = np;
+      sm.Hpar[n] = is_root ? 0 : V.H(par[u] - S.node_base);
+      sm.Cpar[n] = (limited && !is_root) ? V.C(par[u] - S.node_base) : 0;
+      sm.hang[n] = on_path ? 0 : sg[2] - V.KB(sg[5] - S.node_base);
+      sm.cls[n] = (j << 1) | (on_path ? 1 : 0);
+      cnt[u] = is_root ? 1 : np + 1;
     }
-    const int j = lo;
-    const bool on_path = V.path[j] == p;
-    const int32_t* sg = V.seg + (size_t)j * kSegStride;
-    sm.moff[tid] = moff; sm.np[tid] = np;
-    sm.tNode[tid] = f.t[p]; sm.tPar[tid] = par >= 0 ? f.t[par] : 0.0;
-    sm.Hpar[tid] = is_root ? 0 : V.H(par - S.node_base);
-    sm.Cpar[tid] = (limited && !is_root) ? V.C(par - S.node_base) : 0;
-    sm.hang[tid] = on_path ? 0 : sg[2] - V.KB(sg[5] - S.node_base);
-    sm.cls[tid] = (j << 1) | (on_path ? 1 : 0);
-    cnt = is_root ? 1 : np + 1;
   }
   {
-    int incl = warp_scan_incl(cnt, lane);
+    int mine = 0;
+#pragma unroll
+    for (int u = 0; u < kEmitSub; ++u) mine += cnt[u];
+    const int incl = warp_scan_incl(mine, lane);
     if (lane == 31) sm.wcnt[warp] = incl;
     __syncthreads();
-    int pre = 0;
+    int run = incl - mine;
 #pragma unroll
-    for (int w = 0; w < kTile / 32; ++w) if (w < warp) pre += sm.wcnt[w];
-    sm.start[tid] = pre + incl - cnt;
-    if (tid == kTile - 1) sm.start[kTile] = pre + incl;
+    for (int w = 0; w < kTile / 32; ++w) if (w < warp) run += sm.wcnt[w];
+#pragma unroll
+    for (int u = 0; u < kEmitSub; ++u) { sm.start[tid * kEmitSub + u] = run; run += cnt[u]; }
+    if (tid == kTile - 1) sm.start[kEmitNodes] = run;
     __syncthreads();
   }
-  const int total = sm.start[kTile];
+  const int total = sm.start[kEmitNodes];
 
   // ---- (B) one slot per thread ------------------------------------------------------------------------------------------------------------
   double wmax = -CUDART_INF;
@@ -706,15 +722,16 @@ __global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatc
     bool keep = false;
     int n = 0, k = 0, Hk = 0, j = 0;
     bool on_path = false;
+    double tNode = 0.0, tPar = 0.0;
     RegionEval r{};
     if (s < total) {
-      int lo = 0, hi = kTile - 1;                     // last node with start <= s (nodes with no slot share their successor's start)
+      int lo = 0, hi = kEmitNodes - 1;                // last node with start <= s (nodes with no slot share their successor's start)
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         if (sm.start[mid] <= s) lo = mid; else hi = mid - 1;
       }
       n = lo;
-      const int pn = tile_start + n;
+      const int pn = cta_start + n;
       const int np = sm.np[n], moff = sm.moff[n];
       const bool is_root = pn == S.root_pos;
       k = is_root ? np : s - sm.start[n];
@@ -725,9 +742,13 @@ __global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatc
       j = sm.cls[n] >> 1; on_path = sm.cls[n] & 1;
       bool ok = true;
       if (limited) ok = scope_dist(V, j, on_path, Ck, C0) <= S.limit;
-      if (ok) { r = eval_region(f, S, pn, k, np, moff, sm.tPar[n], sm.tNode[n]); keep = r.keep; }
+      if (ok) {
+        const int pp = f.parent_pos[pn];
+        tNode = f.t[pn]; tPar = pp >= 0 ? f.t[pp] : 0.0;
+        r = eval_region(f, S, pn, k, np, moff, tPar, tNode); keep = r.keep;
+      }
     }
-    // rank of the kept slot inside the tile (ballot scan)
+    // rank of the kept slot inside the CTA's node range (ballot scan)
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) sm.wcnt[warp] = __popc(bal);
     __syncthreads();
@@ -739,10 +760,10 @@ __global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatc
     __syncthreads();                                  // wcnt is rewritten by the next round
     if (keep) {
       int idx;
-      if (!on_path) idx = sm.hang[n] + kb_tile + rank;
+      if (!on_path) idx = sm.hang[n] + kb_first + rank;
       else {
         // a node of the start->root path (at most depth-many per study): its regions go to the path segments
-        const int pn = tile_start + n, np = sm.np[n], moff = sm.moff[n];
+        const int pn = cta_start + n, np = sm.np[n], moff = sm.moff[n];
         const int32_t* sg = V.seg + (size_t)j * kSegStride;
         const int kA = (j == 0) ? S.k0 : np;
         if (k == kA) idx = sg[0];
@@ -753,13 +774,13 @@ __global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatc
             bool ok2 = true;
             if (limited) ok2 = scope_dist(V, j, true, Ck, C0) <= S.limit;
             if (k2 < np) { int dh, dc; emit_mut_dc(f, sm, V.xtab, m0, moff + k2, dh, dc); Ck += dc; }
-            if (ok2 && (k > kA ? k2 > kA : true) && eval_region(f, S, pn, k2, np, moff, sm.tPar[n], sm.tNode[n]).keep) ++before;
+            if (ok2 && (k > kA ? k2 > kA : true) && eval_region(f, S, pn, k2, np, moff, tPar, tNode).keep) ++before;
           }
           idx = k > kA ? sg[1] + before : sg[3] + (sg[4] - 1 - before);
         }
       }
       const int m = S.init_min_muts + (Hk - H0);
-      const double lw = region_log_W(S, r.t_min, r.t_max, m, sm.tNode[n]);
+      const double lw = region_log_W(S, r.t_min, r.t_max, m, tNode);
       if (idx >= 0 && idx < S.region_cap) {
         // the first 32 bytes of the 48-byte record as two 16-byte stores; the raw log-weight goes to a compact array so that
         // the normalisation pass reads 8 bytes per region instead of the whole record, and fills the last 16 bytes itself
@@ -927,6 +948,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     S.off_KB = off; off = al(off + sizeof(int32_t) * (N + 1));
     S.off_seg = off; off = al(off + sizeof(int32_t) * kSegStride * (size_t)S.path_cap);
     S.off_part = off; off = al(off + sizeof(double) * kNormBlocks);
+    S.off_tj = off; off = al(off + sizeof(int2) * (size_t)T.num_tiles);       // classify() of the first / last node of every tile
     S.off_xd_site = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_deltas));
     S.off_xd_to = off; off = al(off + std::max(1, S.n_x_deltas));
     S.off_xm_start = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_missing));
@@ -995,7 +1017,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     launched += 2;
   }
   spr_segments_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
-  spr_emit_kernel<<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+  spr_emit_kernel<<<dim3((max_tiles + kEmitSub - 1) / kEmitSub, n), kTile, 0, ctx->stream>>>(fo->h, b->dev);
   spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ctx->stream>>>(b->dev);
   launched += 3;
   ctx->launches += launched;
