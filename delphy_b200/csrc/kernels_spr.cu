@@ -110,13 +110,14 @@ __device__ __noinline__ double dev_gamma_q(double a, double x) {
 // posts (ordinal << 2 | to) with an atomicMax on a per-site key, ordinals coming from a block scan of the per-branch list
 // lengths in root->X order (spr_xtab_kernel, one CTA per study).
 constexpr int kSetupThreads = 1024;
+constexpr int kPathChunks = 8;     // chunks of kSetupThreads positions per CTA of spr_paths_kernel
 
 __global__ void __launch_bounds__(kSetupThreads) spr_paths_kernel(ForestDev f, SprBatchDev B) {
   __shared__ int s_v[4];   // pos0, posX, depth[pos0], depth[posX]
   SprStudy& S = B.studies[blockIdx.y];
   const int tid = threadIdx.x;
   const TreeDev T = f.trees[S.tree];
-  if ((long long)blockIdx.x * kSetupThreads >= T.num_nodes) return;
+  if ((long long)blockIdx.x * kSetupThreads * kPathChunks >= T.num_nodes) return;
   if (tid == 0) {
     const int pos0 = T.node_base + f.pos_of_node[T.node_base + S.start_branch];
     const int posX = S.X >= 0 ? T.node_base + f.pos_of_node[T.node_base + S.X] : -1;
@@ -146,8 +147,10 @@ __global__ void __launch_bounds__(kSetupThreads) spr_paths_kernel(ForestDev f, S
   __syncthreads();
   const int pos0 = s_v[0], posX = s_v[1];
   const int d0 = min(s_v[2] + 1, S.path_cap) - 1, dX = posX >= 0 ? min(s_v[3] + 1, S.path_cap) - 1 : -1;
-  const int p = T.node_base + blockIdx.x * kSetupThreads + tid;
-  if (p <= max(pos0, posX)) {
+  // each CTA sweeps kPathChunks chunks: the three dependent loads above are paid once per 8,192 positions
+  for (int ch = 0; ch < kPathChunks; ++ch) {
+  const int p = T.node_base + (blockIdx.x * kPathChunks + ch) * kSetupThreads + tid;
+  if (p < T.node_base + T.num_nodes && p <= max(pos0, posX)) {
     const int end = p + f.subtree_size[p];
     const bool a0 = p <= pos0 && end > pos0, aX = posX >= 0 && p <= posX && end > posX;
     if (a0 || aX) {
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_paths_kernel(ForestDev f, S
       }
       if (aX && dX - d >= 0) ((int32_t*)(B.slab + S.off_xpath))[dX - d] = p;
     }
+  }
   }
 }
 
@@ -375,85 +379,140 @@ __device__ int node_kept_count(const ForestDev& f, const SprStudy& S, const SprV
 // tile writes tile-local prefixes + its totals, and spr_tile_prefix turns the totals into per-tile exclusive prefixes.
 // phase 0: H and C for every study; unbounded studies also get their kept-count scan here.
 // phase 1: kept-count scan for bounded studies (needs the final C).
+// A CTA of kTile threads covers kScanSub consecutive tiles (thread tid owns the kScanSub consecutive nodes tid * kScanSub ..,
+// all inside one tile): the chain of dependent loads and the block-wide scans are paid once per 4 tiles, and the outputs keep
+// their tile granularity (CTA-wide prefix minus the prefix at the tile's first node).
+constexpr int kScanSub = 4;
+constexpr int kScanNodes = kTile * kScanSub;
+
+struct ScanSmem {
+  SprStudy S;
+  int h[kScanNodes], c[kScanNodes], dh[kScanNodes], dc[kScanNodes];
+  int ws[kTile / 32];
+  int bound[3][kScanSub + 1];      // CTA-wide inclusive prefix (H, C, kept) at the last node of each tile; [0] = 0
+};
+
+// CTA-wide inclusive scan of v[0..kScanSub) per thread (consecutive nodes); leaves the prefix at every tile end in bound[.]
+__device__ __forceinline__ void cta_scan_tiles(int (&v)[kScanSub], int* ws, int* bound) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int mine = 0;
+#pragma unroll
+  for (int u = 0; u < kScanSub; ++u) mine += v[u];
+  const int incl = warp_scan_incl(mine, lane);
+  __syncthreads();                 // ws / bound may still be read from the previous scan
+  if (lane == 31) ws[warp] = incl;
+  __syncthreads();
+  int run = incl - mine;
+#pragma unroll
+  for (int w = 0; w < kTile / 32; ++w) if (w < warp) run += ws[w];
+#pragma unroll
+  for (int u = 0; u < kScanSub; ++u) { run += v[u]; v[u] = run; }
+  if (tid == 0) bound[0] = 0;
+  if ((tid + 1) % (kTile / kScanSub) == 0) bound[(tid + 1) / (kTile / kScanSub)] = run;   // last node of a tile
+  __syncthreads();
+}
+
 template <int kPhase>
 __global__ void __launch_bounds__(kTile) spr_scan_kernel(ForestDev f, SprBatchDev B) {
-  __shared__ int s_h[kTile];
-  __shared__ int s_c[kTile];
-  __shared__ int s_dh[kTile];
-  __shared__ int s_dc[kTile];
-  __shared__ int s_ws[kTile / 32];
+  __shared__ ScanSmem sm;
   const int study = blockIdx.y;
-  const SprStudy& S = B.studies[study];
-  const int tile = blockIdx.x;
-  if (tile >= S.num_tiles || S.error) return;
+  const int t0 = blockIdx.x * kScanSub;          // first tile of this CTA
+  {
+    const SprStudy& G = B.studies[study];
+    if (t0 >= G.num_tiles || G.error) return;
+    if (kPhase == 1 && G.limit == INT_MAX) return;
+    const int* src = reinterpret_cast<const int*>(&G);
+    int* dst = reinterpret_cast<int*>(&sm.S);
+    for (int i = threadIdx.x; i < (int)(sizeof(SprStudy) / sizeof(int)); i += kTile) dst[i] = src[i];
+  }
+  __syncthreads();
+  const SprStudy& S = sm.S;
   const bool limited = S.limit != INT_MAX;
-  if (kPhase == 1 && !limited) return;
   const int tid = threadIdx.x;
   const SprView V = make_view(B, S, study);
   int32_t* Hloc = (int32_t*)(B.slab + S.off_H);
   int32_t* Cloc = (int32_t*)(B.slab + S.off_C);
   int32_t* KBloc = (int32_t*)(B.slab + S.off_KB);
-  int32_t* agg = B.tile_agg + ((size_t)study * (B.max_tiles + 1) + tile) * 3;
+  int32_t* agg = B.tile_agg + ((size_t)study * (B.max_tiles + 1) + t0) * 3;
   const int node_base = S.node_base, N = S.num_nodes;
-  const int tile_start = node_base + tile * kTile;
-  const int tile_end = min(tile_start + kTile, node_base + N);
-  const int p = tile_start + tid;
-  const bool active = p < tile_end;
-  const int q = p - node_base;
+  const int cta_start = node_base + t0 * kTile;
+  const int cta_end = min(cta_start + kScanNodes, node_base + N);
+  const int n0 = tid * kScanSub;                 // my first node (CTA-local); all mine lie in tile `sub` of the CTA
+  const int sub = n0 / kTile;
+  const int ntiles = min(kScanSub, S.num_tiles - t0);
 
   if (kPhase == 0) {
-    int dh = 0, dc = 0;
-    // the root's own list is never crossed by the walk; branches in X's future are never visited at all
-    if (active && p != S.root_pos && !branch_in_Xs_future(f, S, p, f.parent_pos[p])) node_dc(f, V.xtab, p, dh, dc);
-    s_h[tid] = dh; s_c[tid] = dc; s_dh[tid] = dh; s_dc[tid] = dc;
+    int par[kScanSub];
+#pragma unroll
+    for (int u = 0; u < kScanSub; ++u) { const int p = cta_start + n0 + u; par[u] = p < cta_end ? f.parent_pos[p] : -1; }
+#pragma unroll
+    for (int u = 0; u < kScanSub; ++u) {
+      const int p = cta_start + n0 + u;
+      int dh = 0, dc = 0;
+      // the root's own list is never crossed by the walk; branches in X's future are never visited at all
+      if (p < cta_end && p != S.root_pos && !branch_in_Xs_future(f, S, p, par[u])) node_dc(f, V.xtab, p, dh, dc);
+      sm.h[n0 + u] = dh; sm.c[n0 + u] = dc; sm.dh[n0 + u] = dh; sm.dc[n0 + u] = dc;
+    }
     __syncthreads();
     {
-      const int q_first = tile_start - node_base, q_last = tile_end - 1 - node_base;
-      const int c0 = q_first == 0 ? 0 : (q_first - 1) - f.depth[tile_start - 1];
-      const int c1 = q_last - f.depth[tile_end - 1];
+      const int q_first = cta_start - node_base, q_last = cta_end - 1 - node_base;
+      const int c0 = q_first == 0 ? 0 : (q_first - 1) - f.depth[cta_start - 1];
+      const int c1 = q_last - f.depth[cta_end - 1];
       for (int j = c0 + tid; j < c1; j += kTile) {
         const int a = f.post_node[node_base + j];
         int ah, ac;
-        if (a >= tile_start) { ah = s_h[a - tile_start]; ac = s_c[a - tile_start]; }
+        if (a >= cta_start) { ah = sm.h[a - cta_start]; ac = sm.c[a - cta_start]; }
         else if (a == S.root_pos || branch_in_Xs_future(f, S, a, f.parent_pos[a])) { ah = 0; ac = 0; }
         else node_dc(f, V.xtab, a, ah, ac);
-        const int qc = a + f.subtree_size[a] - tile_start;        // position right after a's subtree: inside this tile
-        if (ah) atomicSub(&s_dh[qc], ah);
-        if (limited && ac) atomicSub(&s_dc[qc], ac);   // C (counted-mutation depth) only feeds the scope test of bounded studies
+        const int qc = a + f.subtree_size[a] - cta_start;          // position right after a's subtree: inside this CTA's range
+        if (ah) atomicSub(&sm.dh[qc], ah);
+        if (limited && ac) atomicSub(&sm.dc[qc], ac);   // C (counted-mutation depth) only feeds the scope test of bounded studies
       }
     }
     __syncthreads();
-    int toth, totc = 0, totk = 0;
-    const int ih = block_scan_incl<int, kTile>(s_dh[tid], s_ws, &toth);
-    __syncthreads();
-    int ic = 0;
-    if (limited) {
-      ic = block_scan_incl<int, kTile>(s_dc[tid], s_ws, &totc);
-      __syncthreads();
-    }
-    int kc = 0, ik = 0;
+    int vh[kScanSub], vc[kScanSub], vk[kScanSub], kc[kScanSub];
+#pragma unroll
+    for (int u = 0; u < kScanSub; ++u) { vh[u] = sm.dh[n0 + u]; vc[u] = sm.dc[n0 + u]; vk[u] = 0; kc[u] = 0; }
+    cta_scan_tiles(vh, sm.ws, sm.bound[0]);
+    if (limited) cta_scan_tiles(vc, sm.ws, sm.bound[1]);
     if (!limited) {
-      if (active) kc = node_kept_count(f, S, V, p, false, 0);
-      ik = block_scan_incl<int, kTile>(kc, s_ws, &totk);
+#pragma unroll
+      for (int u = 0; u < kScanSub; ++u) { const int p = cta_start + n0 + u; if (p < cta_end) kc[u] = node_kept_count(f, S, V, p, false, 0); vk[u] = kc[u]; }
+      cta_scan_tiles(vk, sm.ws, sm.bound[2]);
     }
-    if (active) {
-      Hloc[q] = ih;
-      if (limited) Cloc[q] = ic;
-      if (!limited) {
-        KBloc[q] = ik - kc;
-        if (q == N - 1) KBloc[N] = (N % kTile) ? ik : 0;      // KB(N): one past the end, same tile unless N is a tile multiple
+#pragma unroll
+    for (int u = 0; u < kScanSub; ++u) {
+      const int p = cta_start + n0 + u, q = p - node_base;
+      if (p < cta_end) {
+        Hloc[q] = vh[u] - sm.bound[0][sub];
+        if (limited) Cloc[q] = vc[u] - sm.bound[1][sub];
+        else {
+          const int ik = vk[u] - sm.bound[2][sub];                  // tile-local inclusive
+          KBloc[q] = ik - kc[u];
+          if (q == N - 1) KBloc[N] = (N % kTile) ? ik : 0;          // KB(N): one past the end, same tile unless N is a tile multiple
+        }
       }
     }
-    if (tid == 0) { agg[0] = toth; agg[1] = totc; agg[2] = totk; }
-  } else {
-    int kc = 0, totk;
-    if (active) kc = node_kept_count(f, S, V, p, true, S.C0);
-    const int ik = block_scan_incl<int, kTile>(kc, s_ws, &totk);
-    if (active) {
-      KBloc[q] = ik - kc;
-      if (q == N - 1) KBloc[N] = (N % kTile) ? ik : 0;
+    if (tid < ntiles) {
+      agg[tid * 3 + 0] = sm.bound[0][tid + 1] - sm.bound[0][tid];
+      agg[tid * 3 + 1] = limited ? sm.bound[1][tid + 1] - sm.bound[1][tid] : 0;
+      agg[tid * 3 + 2] = limited ? 0 : sm.bound[2][tid + 1] - sm.bound[2][tid];
     }
-    if (tid == 0) agg[2] = totk;
+  } else {
+    int vk[kScanSub], kc[kScanSub];
+#pragma unroll
+    for (int u = 0; u < kScanSub; ++u) { const int p = cta_start + n0 + u; kc[u] = p < cta_end ? node_kept_count(f, S, V, p, true, S.C0) : 0; vk[u] = kc[u]; }
+    cta_scan_tiles(vk, sm.ws, sm.bound[2]);
+#pragma unroll
+    for (int u = 0; u < kScanSub; ++u) {
+      const int p = cta_start + n0 + u, q = p - node_base;
+      if (p < cta_end) {
+        const int ik = vk[u] - sm.bound[2][sub];
+        KBloc[q] = ik - kc[u];
+        if (q == N - 1) KBloc[N] = (N % kTile) ? ik : 0;
+      }
+    }
+    if (tid < ntiles) agg[tid * 3 + 2] = sm.bound[2][tid + 1] - sm.bound[2][tid];
   }
 }
 
@@ -1005,15 +1064,16 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   const dim3 grid_tiles(max_tiles, n);
   int max_nodes = 1;
   for (int i = 0; i < n; ++i) max_nodes = std::max(max_nodes, fo->trees[reqs[i].tree].num_nodes);
-  spr_paths_kernel<<<dim3((max_nodes + kSetupThreads - 1) / kSetupThreads, n), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
+  spr_paths_kernel<<<dim3((max_nodes + kSetupThreads * kPathChunks - 1) / (kSetupThreads * kPathChunks), n), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
   spr_xtab_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
-  spr_scan_kernel<0><<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+  const dim3 grid_scan((max_tiles + kScanSub - 1) / kScanSub, n);
+  spr_scan_kernel<0><<<grid_scan, kTile, 0, ctx->stream>>>(fo->h, b->dev);
   bool any_limited = false;
   for (int i = 0; i < n; ++i) any_limited |= (b->host[i].limit != INT_MAX);
   int launched = 3;
   if (any_limited) {
     spr_tile_prefix_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
-    spr_scan_kernel<1><<<grid_tiles, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+    spr_scan_kernel<1><<<grid_scan, kTile, 0, ctx->stream>>>(fo->h, b->dev);
     launched += 2;
   }
   spr_segments_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
