@@ -134,7 +134,8 @@ void dphy_ctx_destroy(dphy_ctx* ctx) {
   if (ctx->pinned_ev) cudaEventDestroy(ctx->pinned_ev);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
-    cudaEventDestroy(ctx->ev_main); cudaEventDestroy(ctx->ev_topo); cudaEventDestroy(ctx->ev_lists);
+    cudaEventDestroy(ctx->ev_main); cudaEventDestroy(ctx->ev_topo); cudaEventDestroy(ctx->ev_nodes); cudaEventDestroy(ctx->ev_lists);
+    cudaStreamSynchronize(ctx->copy_stream2); cudaEventDestroy(ctx->ev_copy2); cudaStreamDestroy(ctx->copy_stream2);
     cudaStreamDestroy(ctx->copy_stream);
   }
   cudaStreamDestroy(ctx->stream);
@@ -304,7 +305,7 @@ namespace {
 // Host -> device copy of many caller-owned (pageable) arrays: worker threads memcpy 2 MiB chunks into the pinned
 // staging slab while the main thread issues the H2D DMA of every finished chunk, so the memcpy and the PCIe transfer
 // overlap and the host never touches the data more than once.
-struct CopyJob { size_t dst_off; const void* src; size_t bytes; int group; };   // group 0: topology (needed first), 1: the rest
+struct CopyJob { size_t dst_off; const void* src; size_t bytes; int group; };   // group 0: topology (needed first), 1: node times + offsets, 2: lists
 
 bool is_pinned_host(const void* p) {
   cudaPointerAttributes a{};
@@ -315,8 +316,11 @@ bool is_pinned_host(const void* p) {
 int ensure_copy_stream(dphy_ctx* ctx) {
   if (ctx->copy_stream) return DPHY_OK;
   DPHY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  DPHY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
+  DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy2, cudaEventDisableTiming));
   DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
   DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_topo, cudaEventDisableTiming));
+  DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_nodes, cudaEventDisableTiming));
   DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_lists, cudaEventDisableTiming));
   return DPHY_OK;
 }
@@ -337,23 +341,30 @@ int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char*
     if (all_pinned) {
       int st = ensure_copy_stream(ctx);
       if (st != DPHY_OK) return st;
-      cudaStream_t cs = ctx->copy_stream;
-      // the destination was allocated (stream-ordered) and partly cleared on the main stream
-      cudaError_t ce = cudaEventRecord(ctx->ev_main, ctx->stream);
-      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, ctx->ev_main, 0);
-      size_t cur = 0;
-      for (const CopyJob& j : jobs) {      // gaps + topology
-        if (ce == cudaSuccess && j.dst_off > cur) ce = cudaMemcpyAsync(d_base + cur, pinned + cur, j.dst_off - cur, cudaMemcpyHostToDevice, cs);
-        if (ce == cudaSuccess && j.group == 0) ce = cudaMemcpyAsync(d_base + j.dst_off, j.src, j.bytes, cudaMemcpyHostToDevice, cs);
-        cur = std::max(cur, j.dst_off + j.bytes);
-      }
-      if (ce == cudaSuccess && cur < total) ce = cudaMemcpyAsync(d_base + cur, pinned + cur, total - cur, cudaMemcpyHostToDevice, cs);
-      if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_topo, cs);
-      for (const CopyJob& j : jobs)        // the bulky per-node / per-event arrays
-        if (ce == cudaSuccess && j.group != 0) ce = cudaMemcpyAsync(d_base + j.dst_off, j.src, j.bytes, cudaMemcpyHostToDevice, cs);
-      if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_lists, cs);
+      cudaStream_t cs = ctx->copy_stream, cs2 = ctx->copy_stream2;
+      // the destination was allocated stream-ordered on the main stream: ev_main was recorded right after that allocation (the
+      // slab memsets that follow it there touch other memory and need not delay the DMA)
+      cudaError_t ce = cudaStreamWaitEvent(cs, ctx->ev_main, 0);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs2, ctx->ev_main, 0);
+      int flip = 0;
+      auto copy = [&](char* dst, const void* src, size_t bytes) {
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (flip++ & 1) ? cs2 : cs);
+      };
+      auto close_group = [&](cudaEvent_t ev) {   // ev fires once both copy streams have drained what was issued so far
+        if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_copy2, cs2);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, ctx->ev_copy2, 0);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev, cs);
+      };
+      // (everything meaningful is covered by a job -- the per-tree records written into the staging slab are one -- so the
+      // alignment gaps between the destination blocks are not copied)
+      for (const CopyJob& j : jobs) if (j.group == 0) copy(d_base + j.dst_off, j.src, j.bytes);   // per-tree records + topology
+      close_group(ctx->ev_topo);
+      for (const CopyJob& j : jobs) if (j.group == 1) copy(d_base + j.dst_off, j.src, j.bytes);   // node times + CSR offsets
+      close_group(ctx->ev_nodes);
+      for (const CopyJob& j : jobs) if (j.group == 2) copy(d_base + j.dst_off, j.src, j.bytes);   // the bulky per-event arrays
+      close_group(ctx->ev_lists);
       *two_phase = ce == cudaSuccess;
-      if (ce != cudaSuccess) cudaStreamSynchronize(cs);   // nothing may still be writing when the caller frees the destination
+      if (ce != cudaSuccess) { cudaStreamSynchronize(cs); cudaStreamSynchronize(cs2); }   // nothing may still be writing when the caller frees the destination
       return check_cuda(ctx, ce, "H2D direct upload");
     }
   }
@@ -364,7 +375,8 @@ int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char*
     if (j > 0) --j;
     for (; j < jobs.size() && jobs[j].dst_off < hi; ++j) {
       const size_t a = std::max(lo, jobs[j].dst_off), b = std::min(hi, jobs[j].dst_off + jobs[j].bytes);
-      if (a < b) std::memcpy(pinned + a, static_cast<const char*>(jobs[j].src) + (a - jobs[j].dst_off), b - a);
+      const char* src = static_cast<const char*>(jobs[j].src) + (a - jobs[j].dst_off);
+      if (a < b && src != pinned + a) std::memcpy(pinned + a, src, b - a);   // (the per-tree records already lie in the slab)
     }
   };
   unsigned hw = std::thread::hardware_concurrency();
@@ -513,6 +525,10 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   }
   fo->allocs.push_back(dbase);
   fo->bytes = slab.total;
+  if (ensure_copy_stream(ctx) != DPHY_OK || cudaEventRecord(ctx->ev_main, ctx->stream) != cudaSuccess) {
+    cudaFreeAsync(tbase, ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo;
+    return set_error(ctx, DPHY_ERR_CUDA, "upload: copy stream / event");
+  }
   auto fail = [&](int st) { cudaFreeAsync(tbase, ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo; return st; };
 
   void* hbv = nullptr;
@@ -530,7 +546,8 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   auto* h_raw = tmp.at<RawTreeDev>(hraw, r_raw);
   for (int i = 0; i < num_sites_tables; ++i) { h_sites[i] = sites[i]->h; fo->sites_version[i] = sites[i]->version; }
   std::vector<CopyJob> jobs;
-  jobs.reserve((size_t)num_trees * 15);
+  jobs.reserve((size_t)num_trees * 15 + 1);
+  jobs.push_back({tmp.blocks[r_raw].off, h_raw, sizeof(RawTreeDev) * (size_t)num_trees, 0});   // written in place below
   int32_t base = 0, tile_pos = 0, ctile_pos = 0;
   for (int k = 0; k < num_trees; ++k) {
     const auto& e = trees[k];
@@ -558,11 +575,11 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     R.miss_off = tmp.at<int32_t>(tbase, r.ioff); R.miss_start = tmp.at<int32_t>(tbase, r.is); R.miss_end = tmp.at<int32_t>(tbase, r.ie);
     R.fs_off = tmp.at<int32_t>(tbase, r.foff); R.fs_site = tmp.at<int32_t>(tbase, r.fsite); R.fs_from = tmp.at<uint8_t>(tbase, r.ffrom);
     R.root = e.root; R.num_nodes = n; R.num_muts = (int32_t)m; R.num_ivls = (int32_t)iv; R.num_fs = (int32_t)fs; R.pad = 0;
-    auto add = [&](int id, const void* src, size_t bytes, int group = 1) { if (bytes) jobs.push_back({tmp.blocks[id].off, src, bytes, group}); };
-    add(r.parent, e.parent, 4 * (size_t)n, 0); add(r.c0, e.child0, 4 * (size_t)n, 0); add(r.c1, e.child1, 4 * (size_t)n, 0); add(r.t, e.t, 8 * (size_t)n);
-    add(r.moff, e.mut_off, 4 * ((size_t)n + 1)); add(r.msite, e.mut_site, 4 * m); add(r.mfrom, e.mut_from, m); add(r.mto, e.mut_to, m); add(r.mt, e.mut_t, 8 * m);
-    add(r.ioff, e.miss_off, 4 * ((size_t)n + 1)); add(r.is, e.miss_start, 4 * iv); add(r.ie, e.miss_end, 4 * iv);
-    add(r.foff, e.fs_off, 4 * ((size_t)n + 1)); add(r.fsite, e.fs_site, 4 * fs); add(r.ffrom, e.fs_from, fs);
+    auto add = [&](int id, const void* src, size_t bytes, int group = 2) { if (bytes) jobs.push_back({tmp.blocks[id].off, src, bytes, group}); };
+    add(r.parent, e.parent, 4 * (size_t)n, 0); add(r.c0, e.child0, 4 * (size_t)n, 0); add(r.c1, e.child1, 4 * (size_t)n, 0); add(r.t, e.t, 8 * (size_t)n, 1);
+    add(r.moff, e.mut_off, 4 * ((size_t)n + 1), 1); add(r.msite, e.mut_site, 4 * m); add(r.mfrom, e.mut_from, m); add(r.mto, e.mut_to, m); add(r.mt, e.mut_t, 8 * m);
+    add(r.ioff, e.miss_off, 4 * ((size_t)n + 1), 1); add(r.is, e.miss_start, 4 * iv); add(r.ie, e.miss_end, 4 * iv);
+    add(r.foff, e.fs_off, 4 * ((size_t)n + 1), 1); add(r.fsite, e.fs_site, 4 * fs); add(r.ffrom, e.fs_from, fs);
     base += n;
   }
 
@@ -626,11 +643,15 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_topo, 0);
     if (ce != cudaSuccess) return fail(check_cuda(ctx, ce, "wait topology upload"));
     st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes, 0);
-    if (st != DPHY_OK) { cudaStreamSynchronize(ctx->copy_stream); return fail(st); }
-    ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_lists, 0);
-    if (ce != cudaSuccess) { cudaStreamSynchronize(ctx->copy_stream); return fail(check_cuda(ctx, ce, "wait list upload")); }
-    release_pinned_async(ctx);
+    if (st != DPHY_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(st); }
+    ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_nodes, 0);
+    if (ce != cudaSuccess) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(check_cuda(ctx, ce, "wait node upload")); }
     st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes, 1);
+    if (st != DPHY_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(st); }
+    ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_lists, 0);
+    if (ce != cudaSuccess) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(check_cuda(ctx, ce, "wait list upload")); }
+    release_pinned_async(ctx);
+    st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes, 2);
   } else {
     st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes);
   }
@@ -644,9 +665,9 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   for (int k = 0; k < num_trees; ++k) fo->tree_max_depth[k] = status[4 + k];
   fo->num_strad = status[1]; fo->num_fast_ctiles = status[2]; fo->num_slow_ctiles = status[3];
   cudaFreeAsync(tbase, ctx->stream);
-  // structure-only outputs (nsmn, num_muts tallies) come from one general pass now; later evaluations of a forest whose site
-  // rates are uniform take the folded fast path and leave them untouched
-  st = launch_log_G_general(ctx, fo);
+  // first evaluation.  Forests whose site rates are uniform take the folded schedule; the structure-only outputs (nsmn, the
+  // num_muts tallies) then come from a general pass the first time a getter asks for them (ensure_struct_outputs)
+  st = launch_log_G(ctx, fo);
   if (st != DPHY_OK) { cudaStreamSynchronize(ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo; return st; }
   fo->evaluated = true;         // that pass is a complete evaluation under the current evo model
   fo->eval_version.resize(fo->sites.size());
@@ -715,7 +736,21 @@ int dphy_forest_eval_log_G(dphy_ctx* ctx, dphy_forest* fo) {
   return st;
 }
 
+// nsmn and the num_muts tallies depend on the tree alone and are produced by the general schedule only: run it once if the
+// forest has so far been evaluated by the folded schedule alone (it also re-derives everything else, consistently)
+static int ensure_struct_outputs(dphy_ctx* ctx, dphy_forest* fo) {
+  if (fo->struct_valid) return DPHY_OK;
+  int st = launch_log_G_general(ctx, fo);
+  if (st == DPHY_OK) {
+    fo->evaluated = true;
+    fo->eval_version.resize(fo->sites.size());
+    for (size_t i = 0; i < fo->sites.size(); ++i) fo->eval_version[i] = fo->sites[i]->version;
+  }
+  return st;
+}
+
 static int fetch_tree_outputs(dphy_ctx* ctx, dphy_forest* fo, std::vector<double>& dout, std::vector<int32_t>* iout) {
+  if (iout) { int st = ensure_struct_outputs(ctx, fo); if (st != DPHY_OK) return st; }
   if (!fo->eval_current()) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
   const int T = fo->h.num_trees;
   dout.resize((size_t)T * 4);
@@ -757,7 +792,7 @@ int dphy_forest_get_lambda_i(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, doubl
 
 int dphy_forest_get_num_sites_missing(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t* out) {
   if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
-  if (!fo->eval_current()) { int st = dphy_forest_eval_log_G(ctx, fo); if (st != DPHY_OK) return st; }
+  { int st = ensure_struct_outputs(ctx, fo); if (st != DPHY_OK) return st; }
   const TreeDev& T = fo->trees[tree];
   const size_t mark = ctx->arena.mark();
   int32_t* tmp = (int32_t*)ctx->arena.alloc(sizeof(int32_t) * T.num_nodes);

@@ -183,8 +183,9 @@ struct dphy_ctx {
   bool pinned_in_flight = false;
   // second stream for direct (pinned-source) uploads: the list arrays are still in flight over PCIe while the main stream
   // already ranks the Euler tour of the topology arrays that arrived first
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_main = nullptr, ev_topo = nullptr, ev_lists = nullptr;
+  cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr;   // two: consecutive DMAs alternate, hiding each other's set-up latency
+  cudaEvent_t ev_copy2 = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_topo = nullptr, ev_nodes = nullptr, ev_lists = nullptr;
   bool logg_attr_set = false;   // opt-in dynamic shared memory of the log-G tile kernel
   int logg_path = 0;            // DPHY_LOG_G_PATH_*: 0 auto (folded fast path when every site table has uniform nu), 1 general
 };
@@ -256,7 +257,8 @@ int gather_lambda_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, double* d
 int gather_nsmn_host_order(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* d_dst);
 int refresh_sites(dphy_ctx* ctx, dphy_forest* f);   // c_abi.cu
 // kernels_flatten.cu
-// stage 0: Euler-tour ranking (needs parent / child0 / child1 only); stage 1: everything else; -1: both
+// stage 0: Euler-tour ranking (needs parent / child0 / child1 only); stage 1: node records + CSR offset scans (needs t and the
+// three offset arrays); stage 2: list gathers, weight fold, tile descriptors (needs the lists); -1: all
 int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max_tree_nodes, int stage = -1);
 int launch_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count, uint32_t* d_status);
 // Pinned staging buffer of the ctx: acquire waits for the previous async copy out of it; release records an event.

@@ -344,22 +344,26 @@ int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max
   const int num_arcs = 2 * P.num_nodes;
   int rounds = 0;
   while ((1LL << rounds) < 2LL * max_tree_nodes) ++rounds;
-  if (stage != 1) {
+  if (stage < 0 || stage == 0) {
     flatten_arcs_init_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
     for (int r = 0; r < rounds; ++r)
       flatten_rank_round_kernel<<<(num_arcs + 255) / 256, 256, 0, ctx->stream>>>(P.arcs[r & 1], P.arcs[(r + 1) & 1], num_arcs);
     ctx->launches += 1 + rounds;
     if (stage == 0) return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch (topology)");
   }
-  flatten_nodes_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P, rounds & 1);
-  const int nst = (P.num_nodes + kScanTile - 1) / kScanTile;
-  flatten_scan_reduce_kernel<<<nst, kTile, 0, ctx->stream>>>(P);
-  flatten_scan_spine_kernel<<<1, 1024, 0, ctx->stream>>>(P, nst);
-  flatten_scan_apply_kernel<<<nst, kTile, 0, ctx->stream>>>(P);
+  if (stage < 0 || stage == 1) {
+    flatten_nodes_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P, rounds & 1);
+    const int nst = (P.num_nodes + kScanTile - 1) / kScanTile;
+    flatten_scan_reduce_kernel<<<nst, kTile, 0, ctx->stream>>>(P);
+    flatten_scan_spine_kernel<<<1, 1024, 0, ctx->stream>>>(P, nst);
+    flatten_scan_apply_kernel<<<nst, kTile, 0, ctx->stream>>>(P);
+    ctx->launches += 4;
+    if (stage == 1) return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch (node records)");
+  }
   flatten_events_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
   fold_branch_weights_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
   flatten_ctiles_kernel<<<(P.num_ctiles + 255) / 256, 256, 0, ctx->stream>>>(P);
-  ctx->launches += 7;
+  ctx->launches += 3;
   return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch");
 }
 

@@ -685,9 +685,7 @@ struct FoldSmem {
   double clx[kLgTile + 2];
   double wsd[kNW * 2];
   double muq[kMaxPartitions * 4];
-  double tab_md[kMaxPartitions * 16], tab_lq[kMaxPartitions * 16];   // per packed event code: mu nu (q_to - q_from), log(mu nu q_from,to)
 };
-constexpr int kFoldBatch = 2;   // mutations in flight per list per round
 
 __device__ __forceinline__ double block_scan_excl1(double& a, double* wsd) {   // returns the block total; a <- exclusive prefix
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -735,7 +733,6 @@ __global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_folded_kern
   const SitesDev& S = f.sites[ct.w];
   const int stride = f.fsw_stride;
   if (tid < kMaxPartitions * 4) sm.muq[tid] = S.tab_muq[tid];
-  if (tid < kMaxPartitions * 16) { sm.tab_md[tid] = S.tab_md[tid]; sm.tab_lq[tid] = S.tab_lq[tid]; }
   // the first chunk of the tile's closer slice does not depend on anything else: get it in flight together with the node records
   const int32_t* __restrict__ post = f.post_node + node_base;
   int pre_post[2] = {-1, -1};
@@ -763,44 +760,21 @@ __global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_folded_kern
       d[1] = folded_delta(f.bw, stride, sm.muq, p0 + 1);
     }
     // ---- mutations (list order): g_node = sum_m [d_m t_m + log(mu nu q_from,to)] - t_P sum_m d_m ---------------------------------------
-    // Both of my lists are walked together, kFoldBatch events each per round, every load of a round issued before its first use:
-    // the walk costs (longest list in the warp / kFoldBatch) memory round trips instead of one per event.  The sums still run
-    // in list order, so the result is the same as a plain loop's.
-    double tP[2] = {0.0, 0.0}, es[2] = {0.0, 0.0}, ds[2] = {0.0, 0.0};
-    int cnt[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      nonroot[k] = par[k] >= 0;      // the root's list ("mutations" above the root) is not part of log G
-      if (nonroot[k]) tP[k] = f.t[par[k]];
-      cnt[k] = nonroot[k] ? om[k + 1] - om[k] : 0;
-    }
-    const int cmax = max(cnt[0], cnt[1]);
-    for (int j = 0; j < cmax; j += kFoldBatch) {
-      int code[2][kFoldBatch]; double tm[2][kFoldBatch];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-#pragma unroll
-        for (int u = 0; u < kFoldBatch; ++u) {
-          const bool on = j + u < cnt[k];
-          code[k][u] = on ? (int)__ldg(f.mut_code + om[k] + j + u) & 63 : 0;
-          tm[k][u] = on ? __ldg(f.mut_t + om[k] + j + u) : 0.0;
+      if (par[k] >= 0) {       // the root's list ("mutations" above the root) is not part of log G
+        const double tP = f.t[par[k]];
+        double es = 0.0, ds = 0.0;
+        for (int i = om[k]; i < om[k + 1]; ++i) {
+          const int code = __ldg(f.mut_code + i) & 63;
+          const double dd = __ldg(S.tab_md + code);
+          es += dd * f.mut_t[i] + __ldg(S.tab_lq + code);
+          ds += dd;
         }
+        g[k] = es - tP * ds;
+        len[k] = tN[k] - tP;
+        nonroot[k] = true;
       }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-#pragma unroll
-        for (int u = 0; u < kFoldBatch; ++u) {
-          if (j + u < cnt[k]) {
-            const double dd = sm.tab_md[code[k][u]];
-            es[k] += dd * tm[k][u] + sm.tab_lq[code[k][u]];
-            ds[k] += dd;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (nonroot[k]) { g[k] = es[k] - tP[k] * ds[k]; len[k] = tN[k] - tP[k]; }
     }
   }
 
@@ -1029,9 +1003,9 @@ int launch_log_G(dphy_ctx* ctx, dphy_forest* fo) {
   if (fo->h.num_ctiles == 0) return DPHY_OK;
   bool all_uniform = true;
   for (const dphy_sites* s : fo->sites) all_uniform = all_uniform && s->h.nu_uniform;
-  // the folded path leaves nsmn and the num_muts tallies alone: they must have been produced by a general pass since the
-  // last structural change (dphy_forest_upload runs one)
-  if (ctx->logg_path == 0 && all_uniform && fo->struct_valid) return launch_log_G_folded(ctx, fo);
+  // the folded path leaves nsmn and the num_muts tallies alone: the getters that return those run a general pass on demand
+  // (fo->struct_valid says whether one has run since the upload)
+  if (ctx->logg_path == 0 && all_uniform) return launch_log_G_folded(ctx, fo);
   return launch_log_G_general(ctx, fo);
 }
 

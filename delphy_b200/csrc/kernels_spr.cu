@@ -442,15 +442,38 @@ __global__ void __launch_bounds__(kTile) spr_scan_kernel(ForestDev f, SprBatchDe
   const int ntiles = min(kScanSub, S.num_tiles - t0);
 
   if (kPhase == 0) {
-    int par[kScanSub];
+    int par[kScanSub], kc[kScanSub];
+    const int xs = S.posX, xe = S.posX >= 0 ? S.posX + f.subtree_size[S.posX] : -1;
 #pragma unroll
     for (int u = 0; u < kScanSub; ++u) { const int p = cta_start + n0 + u; par[u] = p < cta_end ? f.parent_pos[p] : -1; }
 #pragma unroll
     for (int u = 0; u < kScanSub; ++u) {
       const int p = cta_start + n0 + u;
       int dh = 0, dc = 0;
-      // the root's own list is never crossed by the walk; branches in X's future are never visited at all
-      if (p < cta_end && p != S.root_pos && !branch_in_Xs_future(f, S, p, par[u])) node_dc(f, V.xtab, p, dh, dc);
+      kc[u] = 0;
+      if (p < cta_end) {
+        // one pass per node: the X's-future test (branch_in_Xs_future, inlined so that t[parent] is loaded once), the potentials of
+        // its mutation list, and -- for unbounded studies -- its kept-region count
+        const int pr = par[u];
+        const bool is_root = pr < 0, special = p == S.posS || p == S.posP;
+        const double tPar = is_root ? 0.0 : f.t[pr];
+        const bool cut = !is_root && !special && tPar >= S.t_X && !(p <= S.pos0 && S.pos0 < p + f.subtree_size[p]);
+        if (!cut) {
+          const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
+          if (!is_root) {          // the root's own list is never crossed by the walk
+            for (int i = moff; i < moff + np; ++i) {
+              int h, c;
+              mut_dc(V.xtab, f.mut_site[i], f.mut_code[i] & 15, h, c);
+              dh += h; dc += c;
+            }
+          }
+          if (!limited && !(xs >= 0 && p >= xs && p < xe)) {
+            // an ordinary branch that ends before t_X keeps all of its np + 1 regions (t_min <= t_node < t_X)
+            if (!is_root && !special && tPar < S.t_X && f.t[p] < S.t_X) kc[u] = np + 1;
+            else kc[u] = node_kept_count(f, S, V, p, false, 0);
+          }
+        }
+      }
       sm.h[n0 + u] = dh; sm.c[n0 + u] = dc; sm.dh[n0 + u] = dh; sm.dc[n0 + u] = dc;
     }
     __syncthreads();
@@ -470,16 +493,12 @@ __global__ void __launch_bounds__(kTile) spr_scan_kernel(ForestDev f, SprBatchDe
       }
     }
     __syncthreads();
-    int vh[kScanSub], vc[kScanSub], vk[kScanSub], kc[kScanSub];
+    int vh[kScanSub], vc[kScanSub], vk[kScanSub];
 #pragma unroll
-    for (int u = 0; u < kScanSub; ++u) { vh[u] = sm.dh[n0 + u]; vc[u] = sm.dc[n0 + u]; vk[u] = 0; kc[u] = 0; }
+    for (int u = 0; u < kScanSub; ++u) { vh[u] = sm.dh[n0 + u]; vc[u] = sm.dc[n0 + u]; vk[u] = kc[u]; }
     cta_scan_tiles(vh, sm.ws, sm.bound[0]);
     if (limited) cta_scan_tiles(vc, sm.ws, sm.bound[1]);
-    if (!limited) {
-#pragma unroll
-      for (int u = 0; u < kScanSub; ++u) { const int p = cta_start + n0 + u; if (p < cta_end) kc[u] = node_kept_count(f, S, V, p, false, 0); vk[u] = kc[u]; }
-      cta_scan_tiles(vk, sm.ws, sm.bound[2]);
-    }
+    if (!limited) cta_scan_tiles(vk, sm.ws, sm.bound[2]);
 #pragma unroll
     for (int u = 0; u < kScanSub; ++u) {
       const int p = cta_start + n0 + u, q = p - node_base;

@@ -2,7 +2,7 @@
 # tests + folded occupancy sweep + bench (64 studies) + ncu full of the SPR emit / scan kernels and the folded log-G kernel
 TAG=${1:-q}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log; tail -8 $OUT/pytest_gpu.log
-for o in 5 6 8; do DPHY_FOLDED_OCC=$o timeout 300 python tools/logg_occ.py 16 4 2>&1 | tail -2 | head -1; done | tee $OUT/logg_occ.txt
+for o in 4 5 6; do DPHY_FOLDED_OCC=$o timeout 300 python tools/logg_occ.py 16 4 2>&1 | tail -2 | head -1; done | tee $OUT/logg_occ.txt
 timeout 600 python bench.py --no-cpu-baseline --spr-studies 64 > $OUT/bench64.json 2> $OUT/bench64.err; echo "bench exit $?"; tail -3 $OUT/bench64.err
 python - <<PY
 import json
