@@ -334,6 +334,7 @@ class Context:
     def __init__(self, device: int = 0):
         self._h = C.c_void_p()
         self._host_blocks = []
+        self.log_G_path = "auto"
         st = lib().dphy_ctx_create(device, C.byref(self._h))
         if st != DPHY_OK:
             raise DphyError(st, "dphy_ctx_create failed: a CUDA device is required (no CPU fallback)")
@@ -365,8 +366,10 @@ class Context:
         return out
 
     def set_log_G_path(self, path: str = "auto"):
-        """'auto': folded fast path when every site table has uniform nu_l; 'general': always the per-event kernels."""
-        self.check(lib().dphy_ctx_set_log_G_path(self._h, {"auto": 0, "general": 1}[path]))
+        """'auto': folded fast path when every site table has uniform nu_l; 'general': always the per-event kernels;
+        'general_stream': the per-event path through the TMA-staged persistent kernel (uniform nu_l only)."""
+        self.check(lib().dphy_ctx_set_log_G_path(self._h, {"auto": 0, "general": 1, "general_stream": 2}[path]))
+        self.log_G_path = path
 
     def arena_stats(self):
         cap, hw = C.c_size_t(), C.c_size_t()

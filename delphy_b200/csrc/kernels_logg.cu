@@ -721,7 +721,9 @@ __device__ __forceinline__ double folded_delta(const int32_t* __restrict__ bw, i
   return d;
 }
 
-template <int kMinBlocks>
+// kRec: node records come from the packed 48-byte FoldRec array (one partition): three 16-byte loads per node, the parent's time
+// included, instead of six scalar loads and a dependent gather.
+template <int kMinBlocks, bool kRec>
 __global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_folded_kernel(const __grid_constant__ LogGParams P) {
   __shared__ FoldSmem sm;
   const ForestDev& f = P.f;
@@ -738,43 +740,60 @@ __global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_folded_kern
   int pre_post[2] = {-1, -1};
 #pragma unroll
   for (int u = 0; u < 2; ++u) { const int j = cl.z + 2 * tid + u; if (j < cl.w) pre_post[u] = __ldg(post + j); }
-  __syncthreads();
-
   // ---- node records: 2 consecutive positions per thread ------------------------------------------------------------------------------
   const int q0 = 2 * tid, p0 = tile_start + q0;
   const bool act0 = q0 < n_act, act1 = q0 + 1 < n_act;
   int dep[2] = {0, 0};
   bool nonroot[2] = {false, false};
   double len[2] = {0.0, 0.0}, d[2] = {0.0, 0.0}, g[2] = {0.0, 0.0};
-  {
-    int par[2] = {-1, -1}, om[3] = {0, 0, 0};
-    double tN[2] = {0.0, 0.0};
+  int par[2] = {-1, -1}, moff[2] = {0, 0}, mcnt[2] = {0, 0};
+  double tN[2] = {0.0, 0.0}, tP[2] = {0.0, 0.0};
+  int4 rw[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+  if (kRec) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k == 0 ? act0 : act1) {
+        const int4* r = reinterpret_cast<const int4*>(f.frec + p0 + k);
+        const int4 a = __ldg(r), b = __ldg(r + 1);
+        rw[k] = __ldg(r + 2);
+        par[k] = a.x; dep[k] = a.y; moff[k] = a.z; mcnt[k] = a.w;
+        tN[k] = __hiloint2double(b.y, b.x); tP[k] = __hiloint2double(b.w, b.z);
+      }
+    }
+  }
+  __syncthreads();                           // muq is visible
+  if (kRec) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      d[k] = sm.muq[0] * (double)rw[k].x + sm.muq[1] * (double)rw[k].y + sm.muq[2] * (double)rw[k].z + sm.muq[3] * (double)rw[k].w;
+  } else {
     if (act0) {
       par[0] = __ldg(f.parent_pos + p0); dep[0] = __ldg(f.depth + p0); tN[0] = f.t[p0];
-      om[0] = __ldg(f.mut_off + p0); om[1] = __ldg(f.mut_off + p0 + 1); om[2] = om[1];
+      moff[0] = __ldg(f.mut_off + p0); mcnt[0] = __ldg(f.mut_off + p0 + 1) - moff[0];
       d[0] = folded_delta(f.bw, stride, sm.muq, p0);
     }
     if (act1) {
       par[1] = __ldg(f.parent_pos + p0 + 1); dep[1] = __ldg(f.depth + p0 + 1); tN[1] = f.t[p0 + 1];
-      om[2] = __ldg(f.mut_off + p0 + 2);
+      moff[1] = moff[0] + mcnt[0]; mcnt[1] = __ldg(f.mut_off + p0 + 2) - moff[1];
       d[1] = folded_delta(f.bw, stride, sm.muq, p0 + 1);
     }
-    // ---- mutations (list order): g_node = sum_m [d_m t_m + log(mu nu q_from,to)] - t_P sum_m d_m ---------------------------------------
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (par[k] >= 0) {       // the root's list ("mutations" above the root) is not part of log G
-        const double tP = f.t[par[k]];
-        double es = 0.0, ds = 0.0;
-        for (int i = om[k]; i < om[k + 1]; ++i) {
-          const int code = __ldg(f.mut_code + i) & 63;
-          const double dd = __ldg(S.tab_md + code);
-          es += dd * f.mut_t[i] + __ldg(S.tab_lq + code);
-          ds += dd;
-        }
-        g[k] = es - tP * ds;
-        len[k] = tN[k] - tP;
-        nonroot[k] = true;
+    for (int k = 0; k < 2; ++k) if (par[k] >= 0) tP[k] = f.t[par[k]];
+  }
+  // ---- mutations (list order): g_node = sum_m [d_m t_m + log(mu nu q_from,to)] - t_P sum_m d_m ---------------------------------------
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (par[k] >= 0) {       // the root's list ("mutations" above the root) is not part of log G
+      double es = 0.0, ds = 0.0;
+      for (int i = moff[k]; i < moff[k] + mcnt[k]; ++i) {
+        const int code = __ldg(f.mut_code + i) & 63;
+        const double dd = __ldg(S.tab_md + code);
+        es += dd * f.mut_t[i] + __ldg(S.tab_lq + code);
+        ds += dd;
       }
+      g[k] = es - tP[k] * ds;
+      len[k] = tN[k] - tP[k];
+      nonroot[k] = true;
     }
   }
 
@@ -951,11 +970,14 @@ int launch_log_G_general(dphy_ctx* ctx, dphy_forest* fo) {
     emat_log_G_straddler_kernel<<<(P.num_strad + 127) / 128, 128, 0, ctx->stream>>>(P);
     ctx->launches += 1;
   }
-  // the streaming kernel needs uniform site rates (it stages neither the event sites nor the munu gathers)
-  bool all_uniform = true;
-  for (const dphy_sites* s : fo->sites) all_uniform = all_uniform && s->h.nu_uniform;
-  if (P.debug_mask & 32) all_uniform = false;
-  if (all_uniform) {
+  // Default: the direct-from-global tile kernel for every tile.  The TMA-staged persistent kernel (DPHY_LOG_G_PATH_GENERAL_STREAM)
+  // needs uniform site rates (it stages neither the event sites nor the munu gathers) and was measured slower on B200
+  // (281 vs 216 us per 16 x 100k-tip evaluation): with ~2 events per node the per-node list walks of 8 resident CTAs/SM keep
+  // more loads in flight than two staged tiles per SM do.
+  bool use_stream = ctx->logg_path == DPHY_LOG_G_PATH_GENERAL_STREAM;
+  for (const dphy_sites* s : fo->sites) use_stream = use_stream && s->h.nu_uniform;
+  if (P.debug_mask & 32) use_stream = false;
+  if (use_stream) {
     if (fo->num_fast_ctiles > 0) {
       const int grid = std::min(fo->num_fast_ctiles, 2 * ctx->sm_count);
       emat_log_G_stream_kernel<<<grid, kLgThreads, kStreamSmemBytes, ctx->stream>>>(P, fo->num_fast_ctiles);
@@ -985,13 +1007,24 @@ static int launch_log_G_folded(dphy_ctx* ctx, dphy_forest* fo) {
   P.tile_agg = fo->d_tile_agg;
   P.tile_part = fo->d_tile_part;
   P.tree_out = fo->d_tree_out;
-  // resident CTAs per SM: 6 (40 registers) by default -- measured fastest (the kernel is latency-bound); DPHY_FOLDED_OCC = 4 / 5 / 8
-  // selects the 64- / 48- / 32-register builds (tuning knob)
+  // resident CTAs per SM: 6 (40 registers) by default -- measured fastest (the kernel is latency-bound); DPHY_FOLDED_OCC = 4 / 5
+  // selects the 64- / 48-register builds (tuning knob)
   static const int occ = [] { const char* e = getenv("DPHY_FOLDED_OCC"); return e ? atoi(e) : 6; }();
-  if (occ == 4) emat_log_G_folded_kernel<4><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
-  else if (occ == 5) emat_log_G_folded_kernel<5><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
-  else if (occ == 8) emat_log_G_folded_kernel<8><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
-  else emat_log_G_folded_kernel<6><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P);
+  // (a variant that gave each CTA two tiles -- 4 positions per thread, in-CTA closers across the pair -- was measured slower,
+  // 110 vs 92 us: its 64 registers halve the resident warps, and the kernel lives on warps in flight, not on bytes per CTA)
+  // packed node records (one partition) unless DPHY_FOLDED_REC=0
+  static const bool want_rec = [] { const char* e = getenv("DPHY_FOLDED_REC"); return !e || atoi(e) != 0; }();
+  const bool rec = want_rec && fo->h.frec != nullptr;
+  const int grid = fo->h.num_ctiles;
+  if (rec) {
+    if (occ == 4) emat_log_G_folded_kernel<4, true><<<grid, kLgThreads, 0, ctx->stream>>>(P);
+    else if (occ == 5) emat_log_G_folded_kernel<5, true><<<grid, kLgThreads, 0, ctx->stream>>>(P);
+    else emat_log_G_folded_kernel<6, true><<<grid, kLgThreads, 0, ctx->stream>>>(P);
+  } else {
+    if (occ == 4) emat_log_G_folded_kernel<4, false><<<grid, kLgThreads, 0, ctx->stream>>>(P);
+    else if (occ == 5) emat_log_G_folded_kernel<5, false><<<grid, kLgThreads, 0, ctx->stream>>>(P);
+    else emat_log_G_folded_kernel<6, false><<<grid, kLgThreads, 0, ctx->stream>>>(P);
+  }
   // one CTA per tree folds the tile partials (fusing this into the tile kernel with a last-CTA ticket was measured slower:
   // every CTA then waits a device-wide atomic round trip before it can retire -- 102 vs 96 us per evaluation)
   emat_log_G_folded_tree_kernel<<<fo->h.num_trees, kTreeThreads, 0, ctx->stream>>>(P);

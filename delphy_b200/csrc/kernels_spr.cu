@@ -23,6 +23,8 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstddef>
+#include <cstdlib>
 #include <cstring>
 #include <math_constants.h>
 #include <new>
@@ -36,7 +38,7 @@ struct SprStudy {
   double t_X, lambda_X, f, t_max_tip;
   // slab offsets in bytes
   int64_t off_xtab, off_xkey, off_path, off_xpath, off_H, off_C, off_KB, off_seg, off_regions, off_xd_site, off_xd_to, off_xm_start,
-      off_xm_end, off_part, off_pae, off_lw, off_tj;
+      off_xm_end, off_part, off_pae, off_lw, off_tj, off_nw;
   int32_t region_cap, path_cap;
   // ---- derived (spr_setup_kernel) ----
   int32_t node_base, num_nodes, num_tiles, L;
@@ -52,6 +54,13 @@ struct SprStudy {
   unsigned long long max_key;
   double log_Wmax, sum_W;
 };
+
+// Device-side form of a candidate region: the reference's 48-byte Candidate_region (core/spr_study.h:17-32) split into a 32-byte
+// head written by the emit kernel and a 16-byte (log_W_over_Wmax, W_over_Wmax) tail written by the normalisation kernel, each in
+// its own array, so that both kernels store whole 32-byte sectors (a 16-byte store into a 48-byte record costs a DRAM
+// read-modify-write: ncu showed 375 MB read for 78 MB of useful input).  dphy_spr_batch_get_regions interleaves them on the way out.
+struct alignas(32) RegionHead { int32_t branch, mut_idx; double t_min, t_max; int32_t min_muts, pad; };
+static_assert(sizeof(RegionHead) == 32, "RegionHead must be 32 bytes");
 
 constexpr int kSegStride = 6;     // ints per path node: baseA, baseOwnDown, baseSub, baseUp, cntUp, sibpos
 constexpr int kNormBlocks = 64;   // blocks per study in the normalisation pass (fixed => deterministic sum)
@@ -711,7 +720,8 @@ __device__ __forceinline__ void emit_mut_dc(const ForestDev& f, const EmitSmem& 
   else mut_dc(xtab, f.mut_site[i], f.mut_code[i] & 15, dh, dc);
 }
 
-__global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatchDev B) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kTile, kMinBlocks) spr_emit_kernel(ForestDev f, SprBatchDev B) {
   __shared__ EmitSmem sm;
   const int study = blockIdx.y;
   const int t0 = blockIdx.x * kEmitSub;        // first kTile-tile of this CTA
@@ -726,7 +736,7 @@ __global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatc
   const SprStudy& S = sm.S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SprView V = make_view(B, S, study);
-  dphy_candidate_region* out = (dphy_candidate_region*)(B.slab + S.off_regions);
+  RegionHead* out = (RegionHead*)(B.slab + S.off_regions);
   double* lw_out = (double*)(B.slab + S.off_lw);
   const bool limited = S.limit != INT_MAX;
   const int C0 = S.C0, H0 = S.H0;
@@ -860,8 +870,8 @@ __global__ void __launch_bounds__(kTile, 4) spr_emit_kernel(ForestDev f, SprBatc
       const int m = S.init_min_muts + (Hk - H0);
       const double lw = region_log_W(S, r.t_min, r.t_max, m, tNode);
       if (idx >= 0 && idx < S.region_cap) {
-        // the first 32 bytes of the 48-byte record as two 16-byte stores; the raw log-weight goes to a compact array so that
-        // the normalisation pass reads 8 bytes per region instead of the whole record, and fills the last 16 bytes itself
+        // the 32-byte head as two 16-byte stores; the raw log-weight goes to a compact array: the normalisation pass reads
+        // 8 bytes per region and writes the 16-byte tail array
         int4* o = reinterpret_cast<int4*>(out + idx);
         o[0] = make_int4(r.branch, r.mut_idx, __double2loint(r.t_min), __double2hiint(r.t_min));
         o[1] = make_int4(__double2loint(r.t_max), __double2hiint(r.t_max), m, 0);
@@ -890,7 +900,7 @@ __global__ void __launch_bounds__(256) spr_normalize_kernel(SprBatchDev B) {
   SprStudy& S = B.studies[study];
   if (S.error) return;
   const int n = min(S.total_regions, S.region_cap);
-  dphy_candidate_region* out = (dphy_candidate_region*)(B.slab + S.off_regions);
+  double2* nw = (double2*)(B.slab + S.off_nw);
   double* part = (double*)(B.slab + S.off_part);
   const double lmax = n > 0 ? f64_from_order_key(S.max_key) : 0.0;
   const int per = (n + kNormBlocks - 1) / kNormBlocks;
@@ -900,7 +910,7 @@ __global__ void __launch_bounds__(256) spr_normalize_kernel(SprBatchDev B) {
   for (int i = i0 + threadIdx.x; i < i1; i += 256) {
     const double lw = lw_raw[i] - lmax;
     const double w = exp(lw);
-    *reinterpret_cast<double2*>(&out[i].log_W_over_Wmax) = make_double2(lw, w);   // (log_W_over_Wmax, W_over_Wmax): one 16-byte store
+    nw[i] = make_double2(lw, w);   // (log_W_over_Wmax, W_over_Wmax): one 16-byte store, consecutive regions contiguous
     acc += w;
   }
   acc = block_sum<double, 256>(acc, s_ws);
@@ -928,13 +938,13 @@ __global__ void __launch_bounds__(1024) spr_pick_kernel(SprBatchDev B, const dou
   __shared__ double s_carry;
   const SprStudy& S = B.studies[blockIdx.x];
   const int n = min(S.total_regions, S.region_cap);
-  const dphy_candidate_region* reg = (const dphy_candidate_region*)(B.slab + S.off_regions);
+  const double2* nw = (const double2*)(B.slab + S.off_nw);
   const double r = r_in[blockIdx.x];
   if (threadIdx.x == 0) { s_found = INT_MAX; s_carry = 0.0; }
   __syncthreads();
   for (int i0 = 0; i0 < n; i0 += 1024) {
     const int i = i0 + threadIdx.x;
-    const double w = i < n ? reg[i].W_over_Wmax : 0.0;
+    const double w = i < n ? nw[i].y : 0.0;
     double tot;
     const double incl = block_scan_incl<double, 1024>(w, s_ws, &tot);
     // the reference scans "if (W_i >= r) pick i; else r -= W_i"  <=>  first i with r - sum_{j<i} W_j <= W_i
@@ -950,7 +960,7 @@ __global__ void __launch_bounds__(1024) spr_pick_kernel(SprBatchDev B, const dou
 __global__ void __launch_bounds__(256) spr_find_kernel(SprBatchDev B, int study, int branch, double t, int32_t* out_idx) {
   const SprStudy& S = B.studies[study];
   const int n = min(S.total_regions, S.region_cap);
-  const dphy_candidate_region* reg = (const dphy_candidate_region*)(B.slab + S.off_regions);
+  const RegionHead* reg = (const RegionHead*)(B.slab + S.off_regions);
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
     if (reg[i].branch == branch && reg[i].t_min < t && t <= reg[i].t_max) atomicMin(out_idx, i);
 }
@@ -1031,7 +1041,8 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     S.off_xd_to = off; off = al(off + std::max(1, S.n_x_deltas));
     S.off_xm_start = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_missing));
     S.off_xm_end = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_missing));
-    S.off_regions = off; off = al(off + sizeof(dphy_candidate_region) * (size_t)S.region_cap);
+    S.off_regions = off; off = al(off + sizeof(RegionHead) * (size_t)S.region_cap);
+    S.off_nw = off; off = al(off + sizeof(double2) * (size_t)S.region_cap);
     S.off_lw = off; off = al(off + sizeof(double) * (size_t)S.region_cap);     // raw log-weights between emit and normalise
     if (S.n_x_deltas) {
       copies.push_back({(size_t)S.off_xd_site, r.x_delta_site}); copy_bytes.push_back(sizeof(int32_t) * S.n_x_deltas);
@@ -1096,7 +1107,14 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     launched += 2;
   }
   spr_segments_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
-  spr_emit_kernel<<<dim3((max_tiles + kEmitSub - 1) / kEmitSub, n), kTile, 0, ctx->stream>>>(fo->h, b->dev);
+  {
+    // resident CTAs per SM (tuning knob DPHY_EMIT_OCC = 4 | 5 | 6; 64 / 48 / 40 registers)
+    static const int occ = [] { const char* e = getenv("DPHY_EMIT_OCC"); return e ? atoi(e) : 4; }();
+    const dim3 grid_emit((max_tiles + kEmitSub - 1) / kEmitSub, n);
+    if (occ == 5) spr_emit_kernel<5><<<grid_emit, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+    else if (occ == 6) spr_emit_kernel<6><<<grid_emit, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+    else spr_emit_kernel<4><<<grid_emit, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+  }
   spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ctx->stream>>>(b->dev);
   launched += 3;
   ctx->launches += launched;
@@ -1159,9 +1177,15 @@ int64_t dphy_spr_batch_get_regions(dphy_ctx* ctx, dphy_spr_batch* b, int32_t req
   for (int i = lo; i < hi; ++i) {
     const SprStudy& S = b->host[i];
     if (w + S.total_regions > cap) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: output capacity too small");
-    if (S.total_regions > 0)
-      DPHY_CUDA(ctx, cudaMemcpyAsync(out + w, b->dev.slab + S.off_regions, sizeof(dphy_candidate_region) * (size_t)S.total_regions,
-                                     cudaMemcpyDeviceToHost, ctx->stream));
+    if (S.total_regions > 0) {
+      // head and tail arrays -> the reference's 48-byte records, interleaved by two strided copies
+      char* dst = reinterpret_cast<char*>(out + w);
+      DPHY_CUDA(ctx, cudaMemcpy2DAsync(dst, sizeof(dphy_candidate_region), b->dev.slab + S.off_regions, sizeof(RegionHead), sizeof(RegionHead),
+                                       (size_t)S.total_regions, cudaMemcpyDeviceToHost, ctx->stream));
+      DPHY_CUDA(ctx, cudaMemcpy2DAsync(dst + offsetof(dphy_candidate_region, log_W_over_Wmax), sizeof(dphy_candidate_region),
+                                       b->dev.slab + S.off_nw, sizeof(double2), sizeof(double2), (size_t)S.total_regions,
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    }
     w += S.total_regions;
   }
   DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

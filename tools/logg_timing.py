@@ -5,6 +5,7 @@ import delphy_b200 as db
 chains = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 cfg = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 ctx = db.Context(0)
+ctx.set_log_G_path("general")   # the debug masks act on the general schedule
 ems, tabs = [], []
 for c in range(chains):
     e, s, info = db.synth_generate(db.synth_params(cfg, seed=20251017 + c))
