@@ -488,7 +488,6 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   const int b_foff = slab.reserve(sizeof(int32_t) * (N + 1)), b_fsite = slab.reserve(sizeof(int32_t) * F + 64), b_ffrom = slab.reserve(F + 64);
   const int b_fsw = slab.reserve(sizeof(int16_t) * (size_t)fsw_stride * N + 64);
   const int b_bw = slab.reserve(sizeof(int32_t) * (size_t)fsw_stride * N + 64);
-  const int b_frec = slab.reserve(fsw_stride == 4 ? sizeof(FoldRec) * (size_t)N : 16);
   // outputs + workspaces
   const int b_lambda = slab.reserve(sizeof(double) * N), b_nsmn = slab.reserve(sizeof(int32_t) * N);
   const int b_fastl = slab.reserve(sizeof(int32_t) * ctiles), b_slowl = slab.reserve(sizeof(int32_t) * ctiles);
@@ -611,7 +610,6 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   h.fs_off = slab.at<int32_t>(dbase, b_foff); h.fs_site = slab.at<int32_t>(dbase, b_fsite); h.fs_code = slab.at<uint8_t>(dbase, b_ffrom);
   h.fsw = slab.at<int16_t>(dbase, b_fsw); h.fsw_stride = fsw_stride; h.pad1 = 0;
   h.bw = slab.at<int32_t>(dbase, b_bw);
-  h.frec = fsw_stride == 4 ? slab.at<FoldRec>(dbase, b_frec) : nullptr;
   fo->d_lambda = slab.at<double>(dbase, b_lambda); fo->d_nsmn = slab.at<int32_t>(dbase, b_nsmn);
   fo->d_tree_out = slab.at<double>(dbase, b_tout); fo->d_tree_iout = slab.at<int32_t>(dbase, b_tiout);
   fo->d_tile_agg = slab.at<double>(dbase, b_tagg); fo->d_tile_iagg = slab.at<int32_t>(dbase, b_tiagg);
@@ -640,7 +638,6 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   P.fs_off = const_cast<int32_t*>(h.fs_off); P.fs_site = const_cast<int32_t*>(h.fs_site); P.fs_code = const_cast<uint8_t*>(h.fs_code);
   P.fsw = const_cast<int16_t*>(h.fsw); P.fsw_stride = fsw_stride;
   P.bw = const_cast<int32_t*>(h.bw);
-  P.frec = const_cast<FoldRec*>(h.frec);
   if (two_phase) {
     // Euler-tour ranking as soon as the topology arrays have landed; the rest once the lists have
     ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_topo, 0);

@@ -62,13 +62,6 @@ struct SitesDev {
 };
 
 // Per log-G tile descriptor: everything the streaming kernel needs to issue its bulk copies without touching memory first.
-struct alignas(16) FoldRec {
-  int32_t parent, depth, mut_off, mut_cnt;   // parent position (-1: root), depth, CSR range of the branch's mutations
-  double t, t_parent;                        // node time, parent's time (0 for a root)
-  int32_t bw[4];                             // folded state-count weights of the branch (see bw)
-};
-static_assert(sizeof(FoldRec) == 48, "FoldRec is three 16-byte words");
-
 struct alignas(16) CTileDesc {
   int32_t tile_start, n_act, node_base, sites_id;   // written by the host at upload
   int32_t m0, m1, i0, i1;                           // event ranges of the tile (CSR offsets at its first / past-last node)
@@ -133,10 +126,6 @@ struct ForestDev {
   // With uniform site rates the branch's delta-lambda (core/phylo_tree_calc.h:121-155) is  sum_k mu nu q_a(a) bw[k];
   // for the root, ref_freq + bw is the state count vector of calc_log_root_prior (core/phylo_tree_calc.cpp:467-504).
   const int32_t* bw;
-  // Packed per-node record of the folded log-G kernel (forests with one partition, fsw_stride == 4): everything the kernel
-  // needs about a node in three 16-byte loads, including the parent's time (no dependent gather).  Built at upload by
-  // fold_branch_weights_kernel, kept current by set_node_times_kernel.  nullptr when fsw_stride != 4.
-  const struct FoldRec* frec;
   // host-order lookup: device position of (tree, host node id) = pos_of_node[tree.node_base + id]
   const int32_t* pos_of_node;
 };
@@ -177,7 +166,6 @@ struct FlattenParams {
   int32_t* fs_off; int32_t* fs_site; uint8_t* fs_code;
   int16_t* fsw; int32_t fsw_stride;
   int32_t* bw;
-  FoldRec* frec;
 };
 
 }  // namespace dphy

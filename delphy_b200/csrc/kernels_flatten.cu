@@ -298,15 +298,6 @@ __global__ void __launch_bounds__(kTile) fold_branch_weights_kernel(FlattenParam
       P.fsw[(size_t)p * stride + k] = (int16_t)fk;
       P.bw[(size_t)p * stride + k] = (k < K ? s_w[tid * kBwRow + k] : 0) + fk;
     }
-    if (P.frec) {       // one partition: the folded log-G kernel's packed record
-      FoldRec r;
-      r.parent = P.parent_pos[p]; r.depth = P.depth[p];
-      r.mut_off = s_dst[0][tid]; r.mut_cnt = s_dst[0][tid + 1] - s_dst[0][tid];
-      r.t = P.t[p]; r.t_parent = r.parent >= 0 ? P.t[r.parent] : 0.0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) r.bw[k] = s_w[tid * kBwRow + k] + s_f[tid * kBwRow + k];
-      P.frec[p] = r;
-    }
   }
 }
 
@@ -332,28 +323,18 @@ __global__ void __launch_bounds__(256) flatten_ctiles_kernel(FlattenParams P) {
 }
 
 // Accepted displace moves (core/subrun.cpp:223-231,276-284): scatter new node times by host node index.
-__global__ void set_node_times_kernel(const int32_t* __restrict__ pos_of_node, double* __restrict__ t, FoldRec* __restrict__ frec,
-                                      const int32_t* __restrict__ subtree_size, int node_base, int num_nodes,
+__global__ void set_node_times_kernel(const int32_t* __restrict__ pos_of_node, double* __restrict__ t, int node_base, int num_nodes,
                                       const int32_t* __restrict__ nodes, const double* __restrict__ vals, int count, uint32_t* status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const int v = nodes[i];
   if (v < 0 || v >= num_nodes) { atomicOr(status, 1u); return; }
-  const int p = node_base + pos_of_node[node_base + v];
-  t[p] = vals[i];
-  if (frec) {           // the packed records carry the node's own time and, in its children's records, the parent's
-    frec[p].t = vals[i];
-    if (subtree_size[p] > 1) {
-      const int c1 = p + 1, c0 = p + 1 + subtree_size[p + 1];
-      frec[c1].t_parent = vals[i]; frec[c0].t_parent = vals[i];
-    }
-  }
+  t[node_base + pos_of_node[node_base + v]] = vals[i];
 }
 
 int launch_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count, uint32_t* d_status) {
   const TreeDev& T = fo->trees[tree];
-  set_node_times_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->h.t, const_cast<FoldRec*>(fo->h.frec), fo->h.subtree_size,
-                                                                    T.node_base, T.num_nodes, d_nodes, d_vals, count, d_status);
+  set_node_times_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->h.t, T.node_base, T.num_nodes, d_nodes, d_vals, count, d_status);
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "set_node_times_kernel");
 }

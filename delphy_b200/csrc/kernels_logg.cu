@@ -721,9 +721,7 @@ __device__ __forceinline__ double folded_delta(const int32_t* __restrict__ bw, i
   return d;
 }
 
-// kRec: node records come from the packed 48-byte FoldRec array (one partition): three 16-byte loads per node, the parent's time
-// included, instead of six scalar loads and a dependent gather.
-template <int kMinBlocks, bool kRec>
+template <int kMinBlocks>
 __global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_folded_kernel(const __grid_constant__ LogGParams P) {
   __shared__ FoldSmem sm;
   const ForestDev& f = P.f;
@@ -740,7 +738,11 @@ __global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_folded_kern
   int pre_post[2] = {-1, -1};
 #pragma unroll
   for (int u = 0; u < 2; ++u) { const int j = cl.z + 2 * tid + u; if (j < cl.w) pre_post[u] = __ldg(post + j); }
+  __syncthreads();
+
   // ---- node records: 2 consecutive positions per thread ------------------------------------------------------------------------------
+  // (a packed 48-byte per-node record -- parent, depth, list range, t, the parent's t and the weights in three 16-byte loads, no
+  // dependent gather -- was built and measured: 95-99 vs 92 us in stream; the scalar SoA loads below are not the limiter)
   const int q0 = 2 * tid, p0 = tile_start + q0;
   const bool act0 = q0 < n_act, act1 = q0 + 1 < n_act;
   int dep[2] = {0, 0};
@@ -748,38 +750,18 @@ __global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_folded_kern
   double len[2] = {0.0, 0.0}, d[2] = {0.0, 0.0}, g[2] = {0.0, 0.0};
   int par[2] = {-1, -1}, moff[2] = {0, 0}, mcnt[2] = {0, 0};
   double tN[2] = {0.0, 0.0}, tP[2] = {0.0, 0.0};
-  int4 rw[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
-  if (kRec) {
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k == 0 ? act0 : act1) {
-        const int4* r = reinterpret_cast<const int4*>(f.frec + p0 + k);
-        const int4 a = __ldg(r), b = __ldg(r + 1);
-        rw[k] = __ldg(r + 2);
-        par[k] = a.x; dep[k] = a.y; moff[k] = a.z; mcnt[k] = a.w;
-        tN[k] = __hiloint2double(b.y, b.x); tP[k] = __hiloint2double(b.w, b.z);
-      }
-    }
+  if (act0) {
+    par[0] = __ldg(f.parent_pos + p0); dep[0] = __ldg(f.depth + p0); tN[0] = f.t[p0];
+    moff[0] = __ldg(f.mut_off + p0); mcnt[0] = __ldg(f.mut_off + p0 + 1) - moff[0];
+    d[0] = folded_delta(f.bw, stride, sm.muq, p0);
   }
-  __syncthreads();                           // muq is visible
-  if (kRec) {
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-      d[k] = sm.muq[0] * (double)rw[k].x + sm.muq[1] * (double)rw[k].y + sm.muq[2] * (double)rw[k].z + sm.muq[3] * (double)rw[k].w;
-  } else {
-    if (act0) {
-      par[0] = __ldg(f.parent_pos + p0); dep[0] = __ldg(f.depth + p0); tN[0] = f.t[p0];
-      moff[0] = __ldg(f.mut_off + p0); mcnt[0] = __ldg(f.mut_off + p0 + 1) - moff[0];
-      d[0] = folded_delta(f.bw, stride, sm.muq, p0);
-    }
-    if (act1) {
-      par[1] = __ldg(f.parent_pos + p0 + 1); dep[1] = __ldg(f.depth + p0 + 1); tN[1] = f.t[p0 + 1];
-      moff[1] = moff[0] + mcnt[0]; mcnt[1] = __ldg(f.mut_off + p0 + 2) - moff[1];
-      d[1] = folded_delta(f.bw, stride, sm.muq, p0 + 1);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) if (par[k] >= 0) tP[k] = f.t[par[k]];
+  if (act1) {
+    par[1] = __ldg(f.parent_pos + p0 + 1); dep[1] = __ldg(f.depth + p0 + 1); tN[1] = f.t[p0 + 1];
+    moff[1] = moff[0] + mcnt[0]; mcnt[1] = __ldg(f.mut_off + p0 + 2) - moff[1];
+    d[1] = folded_delta(f.bw, stride, sm.muq, p0 + 1);
   }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) if (par[k] >= 0) tP[k] = f.t[par[k]];
   // ---- mutations (list order): g_node = sum_m [d_m t_m + log(mu nu q_from,to)] - t_P sum_m d_m ---------------------------------------
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
@@ -1012,18 +994,14 @@ static int launch_log_G_folded(dphy_ctx* ctx, dphy_forest* fo) {
   static const int occ = [] { const char* e = getenv("DPHY_FOLDED_OCC"); return e ? atoi(e) : 6; }();
   // (a variant that gave each CTA two tiles -- 4 positions per thread, in-CTA closers across the pair -- was measured slower,
   // 110 vs 92 us: its 64 registers halve the resident warps, and the kernel lives on warps in flight, not on bytes per CTA)
-  // packed node records (one partition) unless DPHY_FOLDED_REC=0
-  static const bool want_rec = [] { const char* e = getenv("DPHY_FOLDED_REC"); return !e || atoi(e) != 0; }();
-  const bool rec = want_rec && fo->h.frec != nullptr;
   const int grid = fo->h.num_ctiles;
-  if (rec) {
-    if (occ == 4) emat_log_G_folded_kernel<4, true><<<grid, kLgThreads, 0, ctx->stream>>>(P);
-    else if (occ == 5) emat_log_G_folded_kernel<5, true><<<grid, kLgThreads, 0, ctx->stream>>>(P);
-    else emat_log_G_folded_kernel<6, true><<<grid, kLgThreads, 0, ctx->stream>>>(P);
-  } else {
-    if (occ == 4) emat_log_G_folded_kernel<4, false><<<grid, kLgThreads, 0, ctx->stream>>>(P);
-    else if (occ == 5) emat_log_G_folded_kernel<5, false><<<grid, kLgThreads, 0, ctx->stream>>>(P);
-    else emat_log_G_folded_kernel<6, false><<<grid, kLgThreads, 0, ctx->stream>>>(P);
+  // profiling only: DPHY_FOLDED_REPEAT=n launches the tile kernel n times per evaluation (idempotent), to separate its in-stream
+  // duration (84 us) from launch gaps and the per-tree kernel (8 us); ncu's isolated, cache-flushed replay reports 59 us
+  static const int repeat = [] { const char* e = getenv("DPHY_FOLDED_REPEAT"); return e ? std::max(1, atoi(e)) : 1; }();
+  for (int rep = 0; rep < repeat; ++rep) {
+    if (occ == 4) emat_log_G_folded_kernel<4><<<grid, kLgThreads, 0, ctx->stream>>>(P);
+    else if (occ == 5) emat_log_G_folded_kernel<5><<<grid, kLgThreads, 0, ctx->stream>>>(P);
+    else emat_log_G_folded_kernel<6><<<grid, kLgThreads, 0, ctx->stream>>>(P);
   }
   // one CTA per tree folds the tile partials (fusing this into the tile kernel with a last-CTA ticket was measured slower:
   // every CTA then waits a device-wide atomic round trip before it can retire -- 102 vs 96 us per evaluation)
