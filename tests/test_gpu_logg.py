@@ -348,3 +348,33 @@ def test_streaming_and_direct_kernels_agree(ctx, orc, monkeypatch):
     fo.close()
     for t in tables:
         t.close()
+
+
+def test_pinned_direct_upload_matches_staged_upload(orc):
+    """dphy_forest_upload from page-locked caller arrays (DMA in place over two copy streams, flatten stages released by
+    events) gives bit-identical device state to the staged upload of pageable arrays -- several trees, two site tables."""
+    items = [synth(3, seed=31), synth(0, seed=32, num_tips=300), synth(1, seed=33), synth(0, seed=34, num_partitions=2)]
+    with db.Context(0) as c:
+        tables = [db.DeviceSites(c, it[1]) for it in items]
+        idx = np.arange(len(items))
+        fo_a = db.Forest(c, [it[0] for it in items], tables, sites_index=idx)
+        pinned = [it[0].pinned(c) for it in items]
+        fo_b = db.Forest(c, pinned, tables, sites_index=idx)
+        ra, rb = fo_a.log_G(), fo_b.log_G()
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y)
+        for k, (emat, sites, _) in enumerate(items):
+            assert np.array_equal(fo_a.lambda_i(k), fo_b.lambda_i(k))
+            assert np.array_equal(fo_a.num_sites_missing(k), fo_b.num_sites_missing(k))
+            e, s = to_oracle(emat, sites)
+            np.testing.assert_array_equal(fo_b.num_sites_missing(k), orc.nsmn(e, s))
+            assert fo_b.tallies()[k]["num_muts"] == orc.num_muts(e, s)
+        # a bad topology is still rejected on the direct path
+        bad = _copy_emat(items[1][0])
+        inner = int(next(v for v in range(bad.num_nodes) if bad.child0[v] >= 0 and v != bad.root))
+        bad.child0[inner] = bad.child1[inner]                      # same child twice
+        with pytest.raises(db.DphyError):
+            db.Forest(c, [bad.pinned(c)], [tables[1]])
+        fo_a.close(); fo_b.close()
+        for t in tables:
+            t.close()
