@@ -161,6 +161,7 @@ def lib() -> C.CDLL:
     L.dphy_forest_calc_num_muts_l.argtypes = [vp, vp, C.c_int32, i32p, i32p]
     L.dphy_forest_calc_Ttwiddle_beta_a.argtypes = [vp, vp, C.c_int32, f64p]
     L.dphy_forest_calc_Ttwiddle_l.argtypes = [vp, vp, C.c_int32, f64p, f64p]
+    L.dphy_forest_calc_site_tallies.argtypes = [vp, vp, C.c_int64, f64p, i32p]
     L.dphy_spr_study_batch.argtypes = [vp, vp, C.c_int32, C.POINTER(SprRequest), C.POINTER(vp)]
     L.dphy_spr_batch_destroy.argtypes = [vp, vp]
     L.dphy_spr_batch_get_summaries.argtypes = [vp, vp, C.POINTER(SprSummary)]
@@ -524,6 +525,14 @@ class Forest:
         self.ctx.check(lib().dphy_forest_calc_Ttwiddle_l(self.ctx._h, self._h, tree, _p(out_l, f64p),
                                                          _p(out_la, f64p) if want_T_l_a else None))
         return out_l, out_la
+
+    def site_tallies(self):
+        """(Ttwiddle_l, num_muts_l) of every tree in one call: two [num_trees, max L] arrays (rows padded with zeros)."""
+        ld = max(t.host.num_sites for t in self.sites_tables)
+        tw = np.zeros((self.num_trees, ld), np.float64)
+        nm = np.zeros((self.num_trees, ld), np.int32)
+        self.ctx.check(lib().dphy_forest_calc_site_tallies(self.ctx._h, self._h, ld, _p(tw, f64p), _p(nm, i32p)))
+        return tw, nm
 
     # -- SPR studies
     def spr_study_batch(self, requests):

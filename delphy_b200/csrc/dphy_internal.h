@@ -186,6 +186,8 @@ struct dphy_ctx {
   cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr;   // two: consecutive DMAs alternate, hiding each other's set-up latency
   cudaEvent_t ev_copy2 = nullptr;
   cudaEvent_t ev_main = nullptr, ev_topo = nullptr, ev_nodes = nullptr, ev_lists = nullptr;
+  struct DeferredCopy { void* dst; const void* src; size_t bytes; };
+  std::vector<DeferredCopy> deferred_d2h;   // device->host copies of a batched getter, issued once all its kernels are enqueued
   bool logg_attr_set = false;   // opt-in dynamic shared memory of the log-G tile kernel
   int logg_path = 0;            // DPHY_LOG_G_PATH_*: 0 auto (folded fast path when every site table has uniform nu), 1 general
 };

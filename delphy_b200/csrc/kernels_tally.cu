@@ -220,7 +220,9 @@ static int scan_branch_lengths(dphy_ctx* ctx, dphy_forest* fo, int tree, double*
   return check_cuda(ctx, cudaGetLastError(), "tally_branch_len_scan_kernel");
 }
 
-int tally_num_muts(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* out_beta_ab, int32_t* out_l, int32_t* out_l_ab) {
+// defer: leave the device->host copies enqueued and the arena scope open; the caller synchronizes the stream and releases the
+// arena once for a whole batch of trees (dphy_forest_calc_site_tallies)
+int tally_num_muts(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* out_beta_ab, int32_t* out_l, int32_t* out_l_ab, bool defer = false) {
   const TreeDev& T = fo->trees[tree];
   const dphy_sites* s = fo->sites[T.sites_id];
   int st = refresh_sites(ctx, fo);
@@ -242,14 +244,16 @@ int tally_num_muts(dphy_ctx* ctx, dphy_forest* fo, int tree, int32_t* out_beta_a
   ctx->launches += 1;
   st = check_cuda(ctx, cudaGetLastError(), "tally_events_kernel<false>");
   if (st == DPHY_OK && out_beta_ab) st = check_cuda(ctx, cudaMemcpyAsync(out_beta_ab, o.num_muts_beta_ab, sizeof(int32_t) * P * 16, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
-  if (st == DPHY_OK && out_l) st = check_cuda(ctx, cudaMemcpyAsync(out_l, o.num_muts_l, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (st == DPHY_OK && out_l && defer) ctx->deferred_d2h.push_back({out_l, o.num_muts_l, sizeof(int32_t) * (size_t)L});
+  else if (st == DPHY_OK && out_l) st = check_cuda(ctx, cudaMemcpyAsync(out_l, o.num_muts_l, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
   if (st == DPHY_OK && out_l_ab) st = check_cuda(ctx, cudaMemcpyAsync(out_l_ab, o.num_muts_l_ab, sizeof(int32_t) * (size_t)L * 16, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (defer && st == DPHY_OK) return st;
   if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "num_muts tallies");
   ctx->arena.release(mark);
   return st;
 }
 
-int tally_times(dphy_ctx* ctx, dphy_forest* fo, int tree, double* out_beta_a, double* out_l, double* out_l_a) {
+int tally_times(dphy_ctx* ctx, dphy_forest* fo, int tree, double* out_beta_a, double* out_l, double* out_l_a, bool defer = false) {
   const TreeDev& T = fo->trees[tree];
   const dphy_sites* s = fo->sites[T.sites_id];
   int st = refresh_sites(ctx, fo);
@@ -288,9 +292,11 @@ int tally_times(dphy_ctx* ctx, dphy_forest* fo, int tree, double* out_beta_a, do
     tally_sites_finalize_kernel<<<1, 1024, 0, ctx->stream>>>(fo->h, tree, PL, o.miss_diff, o.Ttw_l, o.T_l_a);
     ctx->launches += 1;
     st = check_cuda(ctx, cudaGetLastError(), "tally_sites_finalize_kernel");
-    if (st == DPHY_OK && out_l) st = check_cuda(ctx, cudaMemcpyAsync(out_l, o.Ttw_l, sizeof(double) * L, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+    if (st == DPHY_OK && out_l && defer) ctx->deferred_d2h.push_back({out_l, o.Ttw_l, sizeof(double) * (size_t)L});
+    else if (st == DPHY_OK && out_l) st = check_cuda(ctx, cudaMemcpyAsync(out_l, o.Ttw_l, sizeof(double) * L, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
     if (st == DPHY_OK && out_l_a) st = check_cuda(ctx, cudaMemcpyAsync(out_l_a, o.T_l_a, sizeof(double) * (size_t)L * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
   }
+  if (defer && st == DPHY_OK) return st;
   if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "time tallies");
   ctx->arena.release(mark);
   return st;
@@ -318,6 +324,40 @@ int dphy_forest_calc_Ttwiddle_beta_a(dphy_ctx* ctx, dphy_forest* fo, int32_t tre
   if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;
   cudaSetDevice(ctx->device);
   return tally_times(ctx, fo, tree, out, nullptr, nullptr);
+}
+
+int dphy_forest_calc_site_tallies(dphy_ctx* ctx, dphy_forest* fo, int64_t ld, double* out_Ttwiddle_l, int32_t* out_num_muts_l) {
+  if (!ctx || !fo || (!out_Ttwiddle_l && !out_num_muts_l) || ld <= 0) return DPHY_ERR_INVALID_ARGUMENT;
+  for (const TreeDev& T : fo->trees)
+    if (fo->sites[T.sites_id]->L > ld) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "site tallies: row stride smaller than a tree's number of sites");
+  cudaSetDevice(ctx->device);
+  const size_t mark = ctx->arena.mark();
+  int st = DPHY_OK;
+  ctx->deferred_d2h.clear();
+  // a device->host copy into pageable memory blocks the host, so the copies are issued after every tree's kernels are enqueued
+  auto drain = [&]() {
+    int r = DPHY_OK;
+    for (const auto& c : ctx->deferred_d2h)
+      if (r == DPHY_OK) r = check_cuda(ctx, cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->stream), "site tallies D2H");
+    ctx->deferred_d2h.clear();
+    const int r2 = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "site tallies");
+    ctx->arena.release(mark);
+    return r != DPHY_OK ? r : r2;
+  };
+  // every tree's kernels are enqueued back to back; one synchronization per arena-full of trees
+  for (int k = 0; k < fo->h.num_trees && st == DPHY_OK; ++k) {
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      st = DPHY_OK;
+      if (out_Ttwiddle_l) st = tally_times(ctx, fo, k, nullptr, out_Ttwiddle_l + (size_t)k * ld, nullptr, true);
+      if (st == DPHY_OK && out_num_muts_l) st = tally_num_muts(ctx, fo, k, nullptr, out_num_muts_l + (size_t)k * ld, nullptr, true);
+      if (st != DPHY_ERR_OUT_OF_MEMORY || attempt == 1) break;
+      // arena full: drain what is in flight, reopen the scope, retry this tree once
+      st = drain();
+      if (st != DPHY_OK) break;
+    }
+  }
+  const int st2 = drain();
+  return st != DPHY_OK ? st : st2;
 }
 
 int dphy_forest_calc_Ttwiddle_l(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, double* out_l, double* out_l_a) {

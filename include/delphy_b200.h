@@ -213,6 +213,12 @@ int  dphy_forest_calc_num_muts_l(dphy_ctx* ctx, dphy_forest* forest, int32_t tre
 int  dphy_forest_calc_Ttwiddle_beta_a(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, double* out);
 /* calc_Ttwiddle_l (:176-222) -> out_l[L];  calc_T_l_a (:130-174) -> out_l_a[L*4] (either may be NULL) */
 int  dphy_forest_calc_Ttwiddle_l(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, double* out_l, double* out_l_a);
+/* The per-site inputs of the reference's global Gibbs moves for EVERY tree of the forest in one call (what Run gathers from
+ * its subruns each cycle for gibbs_sample_all_nus / alpha_moves, core/run.cpp:1105-1235): row k of out_Ttwiddle_l is
+ * calc_Ttwiddle_l of tree k (core/phylo_tree_calc.cpp:176-222), row k of out_num_muts_l its calc_num_muts_l (:612-622).
+ * Rows are `ld` elements apart (ld >= every tree's number of sites); either output may be NULL.  All trees' kernels and copies
+ * are enqueued back to back with one synchronization at the end. */
+int  dphy_forest_calc_site_tallies(dphy_ctx* ctx, dphy_forest* forest, int64_t ld, double* out_Ttwiddle_l, int32_t* out_num_muts_l);
 
 /* ---- SPR regraft study -------------------------------------------------------------------------------- */
 /* Runs a batch of SPR studies (Spr_study_builder::seed_fill_from + Spr_study ctor) in one pass over the forest.

@@ -378,3 +378,24 @@ def test_pinned_direct_upload_matches_staged_upload(orc):
         fo_a.close(); fo_b.close()
         for t in tables:
             t.close()
+
+
+def test_site_tallies_of_a_whole_forest(ctx, orc):
+    """dphy_forest_calc_site_tallies: the per-site Gibbs inputs (calc_Ttwiddle_l, calc_num_muts_l) of every tree in one call
+    == the per-tree getters == the oracle; trees with different numbers of sites share the padded output."""
+    items = [synth(1, seed=41), synth(0, seed=42, num_tips=300, site_rate_heterogeneity=1), synth(0, seed=43, num_partitions=2),
+             synth(0, seed=44, num_tips=64, num_sites=500)]
+    tables = [db.DeviceSites(ctx, it[1]) for it in items]
+    fo = db.Forest(ctx, [it[0] for it in items], tables, sites_index=np.arange(len(items)))
+    tw, nm = fo.site_tallies()
+    for k, (emat, sites, _) in enumerate(items):
+        L = sites.num_sites
+        e, s = to_oracle(emat, sites)
+        np.testing.assert_array_equal(nm[k, :L], orc.num_muts_l(e, s))
+        assert not nm[k, L:].any() and not tw[k, L:].any()
+        want = orc.Ttwiddle_l(e, s)
+        np.testing.assert_allclose(tw[k, :L], want, rtol=RTOL, atol=1e-9 * np.abs(want).max())
+        np.testing.assert_allclose(tw[k, :L], fo.Ttwiddle_l(k, want_T_l_a=False)[0], rtol=1e-12, atol=1e-12 * np.abs(want).max())
+    fo.close()
+    for t in tables:
+        t.close()
