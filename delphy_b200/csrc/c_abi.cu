@@ -136,6 +136,7 @@ void dphy_ctx_destroy(dphy_ctx* ctx) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaEventDestroy(ctx->ev_main); cudaEventDestroy(ctx->ev_topo); cudaEventDestroy(ctx->ev_nodes); cudaEventDestroy(ctx->ev_lists);
     cudaStreamSynchronize(ctx->copy_stream2); cudaEventDestroy(ctx->ev_copy2); cudaStreamDestroy(ctx->copy_stream2);
+    for (cudaEvent_t e : ctx->ev_tree) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->copy_stream);
   }
   cudaStreamDestroy(ctx->stream);
@@ -305,7 +306,7 @@ namespace {
 // Host -> device copy of many caller-owned (pageable) arrays: worker threads memcpy 2 MiB chunks into the pinned
 // staging slab while the main thread issues the H2D DMA of every finished chunk, so the memcpy and the PCIe transfer
 // overlap and the host never touches the data more than once.
-struct CopyJob { size_t dst_off; const void* src; size_t bytes; int group; };   // group 0: topology (needed first), 1: node times + offsets, 2: lists
+struct CopyJob { size_t dst_off; const void* src; size_t bytes; int group; int tree; };   // group 0: topology (needed first), 1: node times + offsets, 2: lists
 
 bool is_pinned_host(const void* p) {
   cudaPointerAttributes a{};
@@ -361,7 +362,17 @@ int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char*
       close_group(ctx->ev_topo);
       for (const CopyJob& j : jobs) if (j.group == 1) copy(d_base + j.dst_off, j.src, j.bytes);   // node times + CSR offsets
       close_group(ctx->ev_nodes);
-      for (const CopyJob& j : jobs) if (j.group == 2) copy(d_base + j.dst_off, j.src, j.bytes);   // the bulky per-event arrays
+      // the bulky per-event arrays, tree by tree (the jobs are sorted by destination, i.e. tree-major): each tree gets its own event
+      int cur_tree = -1;
+      for (const CopyJob& j : jobs) {
+        if (j.group != 2) continue;
+        if (j.tree != cur_tree) {
+          if (cur_tree >= 0) close_group(ctx->ev_tree[cur_tree]);
+          cur_tree = j.tree;
+        }
+        copy(d_base + j.dst_off, j.src, j.bytes);
+      }
+      if (cur_tree >= 0) close_group(ctx->ev_tree[cur_tree]);
       close_group(ctx->ev_lists);
       *two_phase = ce == cudaSuccess;
       if (ce != cudaSuccess) { cudaStreamSynchronize(cs); cudaStreamSynchronize(cs2); }   // nothing may still be writing when the caller frees the destination
@@ -547,7 +558,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   for (int i = 0; i < num_sites_tables; ++i) { h_sites[i] = sites[i]->h; fo->sites_version[i] = sites[i]->version; }
   std::vector<CopyJob> jobs;
   jobs.reserve((size_t)num_trees * 15 + 1);
-  jobs.push_back({tmp.blocks[r_raw].off, h_raw, sizeof(RawTreeDev) * (size_t)num_trees, 0});   // written in place below
+  jobs.push_back({tmp.blocks[r_raw].off, h_raw, sizeof(RawTreeDev) * (size_t)num_trees, 0, -1});   // written in place below
   int32_t base = 0, tile_pos = 0, ctile_pos = 0;
   for (int k = 0; k < num_trees; ++k) {
     const auto& e = trees[k];
@@ -575,7 +586,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     R.miss_off = tmp.at<int32_t>(tbase, r.ioff); R.miss_start = tmp.at<int32_t>(tbase, r.is); R.miss_end = tmp.at<int32_t>(tbase, r.ie);
     R.fs_off = tmp.at<int32_t>(tbase, r.foff); R.fs_site = tmp.at<int32_t>(tbase, r.fsite); R.fs_from = tmp.at<uint8_t>(tbase, r.ffrom);
     R.root = e.root; R.num_nodes = n; R.num_muts = (int32_t)m; R.num_ivls = (int32_t)iv; R.num_fs = (int32_t)fs; R.pad = 0;
-    auto add = [&](int id, const void* src, size_t bytes, int group = 2) { if (bytes) jobs.push_back({tmp.blocks[id].off, src, bytes, group}); };
+    auto add = [&](int id, const void* src, size_t bytes, int group = 2) { if (bytes) jobs.push_back({tmp.blocks[id].off, src, bytes, group, k}); };
     add(r.parent, e.parent, 4 * (size_t)n, 0); add(r.c0, e.child0, 4 * (size_t)n, 0); add(r.c1, e.child1, 4 * (size_t)n, 0); add(r.t, e.t, 8 * (size_t)n, 1);
     add(r.moff, e.mut_off, 4 * ((size_t)n + 1), 1); add(r.msite, e.mut_site, 4 * m); add(r.mfrom, e.mut_from, m); add(r.mto, e.mut_to, m); add(r.mt, e.mut_t, 8 * m);
     add(r.ioff, e.miss_off, 4 * ((size_t)n + 1), 1); add(r.is, e.miss_start, 4 * iv); add(r.ie, e.miss_end, 4 * iv);
@@ -589,6 +600,13 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   if (ce != cudaSuccess) return fail(check_cuda(ctx, ce, "H2D forest header"));
   // the RawTreeDev records were written straight into the pinned slab above; everything in [0, raw_upload_bytes) not
   // covered by a job (those records, alignment gaps) is copied as it lies
+  while ((int)ctx->ev_tree.size() < num_trees) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(set_error(ctx, DPHY_ERR_CUDA, "cudaEventCreate"));
+    ctx->ev_tree.push_back(e);
+  }
+  std::vector<char> tree_has_lists(num_trees, 0);
+  for (const CopyJob& j : jobs) if (j.group == 2 && j.tree >= 0) tree_has_lists[j.tree] = 1;
   bool two_phase = false;
   st = staged_upload(ctx, hraw, jobs, tbase, raw_upload_bytes, &two_phase);
   if (!two_phase) release_pinned_async(ctx);
@@ -648,10 +666,21 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     if (ce != cudaSuccess) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(check_cuda(ctx, ce, "wait node upload")); }
     st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes, 1);
     if (st != DPHY_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(st); }
-    ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_lists, 0);
-    if (ce != cudaSuccess) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(check_cuda(ctx, ce, "wait list upload")); }
+    // lists: each tree is gathered and folded as soon as its own arrays have landed, while the next trees' are still in flight
+    for (int k = 0; k < num_trees && st == DPHY_OK; ++k) {
+      if (tree_has_lists[k]) {
+        ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_tree[k], 0);
+        if (ce != cudaSuccess) { st = check_cuda(ctx, ce, "wait list upload"); break; }
+      }
+      st = launch_flatten_lists(ctx, P, fo->trees[k].first_tile, fo->trees[k].num_tiles);
+    }
+    if (st == DPHY_OK) {
+      ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_lists, 0);
+      if (ce != cudaSuccess) st = check_cuda(ctx, ce, "wait list upload");
+    }
+    if (st != DPHY_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(st); }
     release_pinned_async(ctx);
-    st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes, 2);
+    st = launch_flatten_ctiles(ctx, P);
   } else {
     st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes);
   }

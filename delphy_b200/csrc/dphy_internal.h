@@ -150,6 +150,7 @@ enum : uint32_t {
 };
 
 struct FlattenParams {
+  int32_t tile_base = 0;       // first tile of a per-tree launch of the list kernels (flatten_events / fold_branch_weights)
   const TreeDev* trees; const SitesDev* sites; const int32_t* tile_tree; const RawTreeDev* raw;
   int4* arcs[2];               // ping-pong Euler-tour arcs: (succ, #enter arcs to the end, #arcs to the end, -)
   int32_t* scan_tiles;         // [ceil(num_nodes / 1024) * 3]
@@ -185,6 +186,7 @@ struct dphy_ctx {
   // already ranks the Euler tour of the topology arrays that arrived first
   cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr;   // two: consecutive DMAs alternate, hiding each other's set-up latency
   cudaEvent_t ev_copy2 = nullptr;
+  std::vector<cudaEvent_t> ev_tree;   // per-tree "lists have landed" events of a direct upload (grown on demand)
   cudaEvent_t ev_main = nullptr, ev_topo = nullptr, ev_nodes = nullptr, ev_lists = nullptr;
   struct DeferredCopy { void* dst; const void* src; size_t bytes; };
   std::vector<DeferredCopy> deferred_d2h;   // device->host copies of a batched getter, issued once all its kernels are enqueued
@@ -262,6 +264,9 @@ int refresh_sites(dphy_ctx* ctx, dphy_forest* f);   // c_abi.cu
 // stage 0: Euler-tour ranking (needs parent / child0 / child1 only); stage 1: node records + CSR offset scans (needs t and the
 // three offset arrays); stage 2: list gathers, weight fold, tile descriptors (needs the lists); -1: all
 int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max_tree_nodes, int stage = -1);
+// stage 2 split per tree (direct uploads: each tree's lists are gathered as soon as its own arrays have landed)
+int launch_flatten_lists(dphy_ctx* ctx, FlattenParams P, int first_tile, int num_tiles);
+int launch_flatten_ctiles(dphy_ctx* ctx, const FlattenParams& P);
 int launch_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count, uint32_t* d_status);
 // Pinned staging buffer of the ctx: acquire waits for the previous async copy out of it; release records an event.
 int acquire_pinned(dphy_ctx* ctx, size_t bytes, void** out);

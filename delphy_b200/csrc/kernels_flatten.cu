@@ -194,7 +194,7 @@ __device__ __forceinline__ int tile_owner(const int* s_dst, int e) {   // last n
 __global__ void __launch_bounds__(kTile) flatten_events_kernel(FlattenParams P) {
   __shared__ int s_dst[3][kTile + 1];
   __shared__ int s_src[3][kTile];
-  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int tile = blockIdx.x + P.tile_base, tid = threadIdx.x;
   const int tree = P.tile_tree[tile];
   const TreeDev T = P.trees[tree];
   const RawTreeDev R = P.raw[tree];
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kTile) fold_branch_weights_kernel(FlattenParam
   __shared__ int s_w[kTile * kBwRow];
   __shared__ int s_f[kTile * kBwRow];
   __shared__ int s_dst[3][kTile + 1];
-  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int tile = blockIdx.x + P.tile_base, tid = threadIdx.x;
   const int tree = P.tile_tree[tile];
   const TreeDev T = P.trees[tree];
   const SitesDev& S = P.sites[T.sites_id];
@@ -365,6 +365,21 @@ int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max
   flatten_ctiles_kernel<<<(P.num_ctiles + 255) / 256, 256, 0, ctx->stream>>>(P);
   ctx->launches += 3;
   return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch");
+}
+
+int launch_flatten_lists(dphy_ctx* ctx, FlattenParams P, int first_tile, int num_tiles) {
+  if (num_tiles <= 0) return DPHY_OK;
+  P.tile_base = first_tile;
+  flatten_events_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
+  fold_branch_weights_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
+  ctx->launches += 2;
+  return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch (lists)");
+}
+
+int launch_flatten_ctiles(dphy_ctx* ctx, const FlattenParams& P) {
+  flatten_ctiles_kernel<<<(P.num_ctiles + 255) / 256, 256, 0, ctx->stream>>>(P);
+  ctx->launches += 1;
+  return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch (tile descriptors)");
 }
 
 }  // namespace dphy
