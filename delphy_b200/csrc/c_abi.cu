@@ -135,9 +135,11 @@ void dphy_ctx_destroy(dphy_ctx* ctx) {
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaEventDestroy(ctx->ev_main); cudaEventDestroy(ctx->ev_topo); cudaEventDestroy(ctx->ev_nodes); cudaEventDestroy(ctx->ev_lists);
-    cudaStreamSynchronize(ctx->copy_stream2); cudaEventDestroy(ctx->ev_copy2); cudaStreamDestroy(ctx->copy_stream2);
     for (cudaEvent_t e : ctx->ev_tree) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < dphy_ctx::kCopyStreams; ++i) {
+      if (ctx->copy_streams[i]) { cudaStreamSynchronize(ctx->copy_streams[i]); cudaStreamDestroy(ctx->copy_streams[i]); }
+      if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    }
   }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -314,11 +316,17 @@ bool is_pinned_host(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+void sync_copy_streams(dphy_ctx* ctx) {
+  for (int i = 0; i < dphy_ctx::kCopyStreams; ++i) if (ctx->copy_streams[i]) cudaStreamSynchronize(ctx->copy_streams[i]);
+}
+
 int ensure_copy_stream(dphy_ctx* ctx) {
   if (ctx->copy_stream) return DPHY_OK;
-  DPHY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  DPHY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
-  DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy2, cudaEventDisableTiming));
+  for (int i = 0; i < dphy_ctx::kCopyStreams; ++i) {
+    DPHY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_streams[i], cudaStreamNonBlocking));
+    DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+  }
+  ctx->copy_stream = ctx->copy_streams[0];
   DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
   DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_topo, cudaEventDisableTiming));
   DPHY_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_nodes, cudaEventDisableTiming));
@@ -342,18 +350,21 @@ int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char*
     if (all_pinned) {
       int st = ensure_copy_stream(ctx);
       if (st != DPHY_OK) return st;
-      cudaStream_t cs = ctx->copy_stream, cs2 = ctx->copy_stream2;
+      constexpr int kS = dphy_ctx::kCopyStreams;
+      cudaStream_t cs = ctx->copy_stream;
       // the destination was allocated stream-ordered on the main stream: ev_main was recorded right after that allocation (the
       // slab memsets that follow it there touch other memory and need not delay the DMA)
-      cudaError_t ce = cudaStreamWaitEvent(cs, ctx->ev_main, 0);
-      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs2, ctx->ev_main, 0);
+      cudaError_t ce = cudaSuccess;
+      for (int i = 0; i < kS; ++i) if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_streams[i], ctx->ev_main, 0);
       int flip = 0;
       auto copy = [&](char* dst, const void* src, size_t bytes) {
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (flip++ & 1) ? cs2 : cs);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_streams[flip++ % kS]);
       };
-      auto close_group = [&](cudaEvent_t ev) {   // ev fires once both copy streams have drained what was issued so far
-        if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_copy2, cs2);
-        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, ctx->ev_copy2, 0);
+      auto close_group = [&](cudaEvent_t ev) {   // ev fires once every copy stream has drained what was issued so far
+        for (int i = 1; i < kS; ++i) {
+          if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_copy[i], ctx->copy_streams[i]);
+          if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, ctx->ev_copy[i], 0);
+        }
         if (ce == cudaSuccess) ce = cudaEventRecord(ev, cs);
       };
       // (everything meaningful is covered by a job -- the per-tree records written into the staging slab are one -- so the
@@ -375,7 +386,7 @@ int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char*
       if (cur_tree >= 0) close_group(ctx->ev_tree[cur_tree]);
       close_group(ctx->ev_lists);
       *two_phase = ce == cudaSuccess;
-      if (ce != cudaSuccess) { cudaStreamSynchronize(cs); cudaStreamSynchronize(cs2); }   // nothing may still be writing when the caller frees the destination
+      if (ce != cudaSuccess) for (int i = 0; i < kS; ++i) cudaStreamSynchronize(ctx->copy_streams[i]);   // nothing may still be writing when the caller frees the destination
       return check_cuda(ctx, ce, "H2D direct upload");
     }
   }
@@ -661,11 +672,11 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_topo, 0);
     if (ce != cudaSuccess) return fail(check_cuda(ctx, ce, "wait topology upload"));
     st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes, 0);
-    if (st != DPHY_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(st); }
+    if (st != DPHY_OK) { sync_copy_streams(ctx); return fail(st); }
     ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_nodes, 0);
-    if (ce != cudaSuccess) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(check_cuda(ctx, ce, "wait node upload")); }
+    if (ce != cudaSuccess) { sync_copy_streams(ctx); return fail(check_cuda(ctx, ce, "wait node upload")); }
     st = launch_flatten(ctx, P, (int)tiles, max_tree_nodes, 1);
-    if (st != DPHY_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(st); }
+    if (st != DPHY_OK) { sync_copy_streams(ctx); return fail(st); }
     // lists: each tree is gathered and folded as soon as its own arrays have landed, while the next trees' are still in flight
     for (int k = 0; k < num_trees && st == DPHY_OK; ++k) {
       if (tree_has_lists[k]) {
@@ -678,7 +689,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
       ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_lists, 0);
       if (ce != cudaSuccess) st = check_cuda(ctx, ce, "wait list upload");
     }
-    if (st != DPHY_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return fail(st); }
+    if (st != DPHY_OK) { sync_copy_streams(ctx); return fail(st); }
     release_pinned_async(ctx);
     st = launch_flatten_ctiles(ctx, P);
   } else {

@@ -184,8 +184,10 @@ struct dphy_ctx {
   bool pinned_in_flight = false;
   // second stream for direct (pinned-source) uploads: the list arrays are still in flight over PCIe while the main stream
   // already ranks the Euler tour of the topology arrays that arrived first
-  cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr;   // two: consecutive DMAs alternate, hiding each other's set-up latency
-  cudaEvent_t ev_copy2 = nullptr;
+  static constexpr int kCopyStreams = 2;   // consecutive DMAs alternate over these, hiding each other's set-up latency (4 measured no better)
+  cudaStream_t copy_stream = nullptr;       // == copy_streams[0]: the one the group events are recorded on
+  cudaStream_t copy_streams[kCopyStreams] = {};
+  cudaEvent_t ev_copy[kCopyStreams] = {};
   std::vector<cudaEvent_t> ev_tree;   // per-tree "lists have landed" events of a direct upload (grown on demand)
   cudaEvent_t ev_main = nullptr, ev_topo = nullptr, ev_nodes = nullptr, ev_lists = nullptr;
   struct DeferredCopy { void* dst; const void* src; size_t bytes; };
