@@ -101,6 +101,7 @@ def test_root_prior_zero_pi(ctx, orc):
     (0, dict(caterpillar=1, num_tips=700)),
     (0, dict(num_tips=2, num_sites=50, missing_len_max=20.0)),
     (0, dict(num_tips=257, missing_mean_intervals_per_tip=0.0, end_gaps=0)),
+    (0, dict(num_tips=2500, muts_per_tip=24.0, missing_mean_intervals_per_tip=12.0)),   # long per-branch lists
     (1, {}),
     (2, {}),
     (3, {}),

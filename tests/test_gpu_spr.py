@@ -98,6 +98,7 @@ def test_detached_new_sequence(ctx, orc):
     (0, {}, 40),
     (0, dict(num_root_mutations=6, num_partitions=2, site_rate_heterogeneity=1), 40),
     (0, dict(caterpillar=1, num_tips=400), 30),
+    (0, dict(num_tips=2500, muts_per_tip=24.0), 10),   # ~12 mutations per branch: more than the emit kernel caches per CTA, many slot rounds
     (1, {}, 48),
     (2, {}, 32),
     (3, {}, 12),
