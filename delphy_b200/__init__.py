@@ -419,7 +419,9 @@ class DeviceSites:
             h.pi_a = np.ascontiguousarray(pi_a, np.float64).reshape(-1, 4)
         if q_ab is not None:
             h.q_ab = np.ascontiguousarray(q_ab, np.float64).reshape(-1, 4, 4)
-        self.ctx.check(lib().dphy_sites_set_evo(self.ctx._h, self._h, _p(h.nu_l, f64p), _p(h.mu, f64p), _p(h.pi_a, f64p), _p(h.q_ab, f64p)))
+        # nu_l is passed only when it changed: the cumulative-nu tables are then left alone
+        self.ctx.check(lib().dphy_sites_set_evo(self.ctx._h, self._h, _p(h.nu_l, f64p) if nu_l is not None else None,
+                                                _p(h.mu, f64p), _p(h.pi_a, f64p), _p(h.q_ab, f64p)))
 
     def state_frequencies(self):
         out = np.zeros((self.host.num_partitions, 4), np.int32)

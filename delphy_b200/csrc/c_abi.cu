@@ -285,9 +285,9 @@ int dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* s, const double* nu_l, const d
   }
   fill_tables(s);
   s->version += 1;
-  st = launch_sites_derive(ctx, s);
-  if (st != DPHY_OK) return st;
-  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sites set_evo");
+  // asynchronous: everything that consumes the tables is ordered after this on the ctx's stream, and the forests pick up the
+  // new host-side constants (mu, q, the 64-entry event tables) through the version bump
+  return launch_sites_derive(ctx, s, /*with_nu_tables=*/nu_l != nullptr);
 }
 
 int dphy_calc_state_frequencies_per_partition(dphy_ctx* ctx, dphy_sites* s, int32_t* out) {

@@ -254,7 +254,7 @@ int check_cuda(dphy_ctx* ctx, cudaError_t e, const char* what);
 #define DPHY_CUDA(ctx, expr) do { int st__ = dphy::check_cuda((ctx), (expr), #expr); if (st__ != DPHY_OK) return st__; } while (0)
 
 // kernels_sites.cu
-int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s);
+int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s, bool with_nu_tables = true);
 int launch_sites_ref_counts(dphy_ctx* ctx, dphy_sites* s);
 // kernels_logg.cu
 int launch_log_G(dphy_ctx* ctx, dphy_forest* f);            // picks the path (ctx->logg_path, site tables, struct_valid)

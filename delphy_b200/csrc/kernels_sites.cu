@@ -9,72 +9,125 @@
 #include "dphy_internal.h"
 #include "device_utils.cuh"
 
+#include <cooperative_groups.h>
+
 namespace dphy {
 
 constexpr int kScanThreads = 1024;
 
-// One CTA; each thread owns a contiguous chunk of sites (sequential left-to-right inside the chunk like the
-// reference's loop), chunk totals are combined by a block scan.  L <= a few 1e5, so this is a ~10 us kernel.
-__global__ void __launch_bounds__(kScanThreads) sites_derive_kernel(
+// A thread-block cluster of kClusterCtas CTAs sweeps the sites in rounds: CTA r of the cluster takes slab round * kClusterCtas + r
+// (kScanThreads * kSitesPerThread consecutive sites; thread tid owns kSitesPerThread consecutive sites, so every load of a warp is
+// one contiguous run, summed left to right), scans it, and publishes the slab total into the shared memory of EVERY CTA of the
+// cluster (distributed shared memory); after one cluster barrier each CTA adds the totals of the lower ranks and the running
+// carry.  L = 29,903 is one round of 8 slabs.  (The reference's scan is strictly sequential; see DESIGN.md section 2.3 for why the
+// comparison uses 1e-10.)
+namespace cg = cooperative_groups;
+constexpr int kSitesPerThread = 4;
+constexpr int kClusterCtas = 8;
+struct EvoArgs { double mu[kMaxPartitions]; double q[kMaxPartitions * 16]; };   // passed by value: no staging copies
+
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kScanThreads) sites_derive_kernel(
     int L, int P, const uint8_t* __restrict__ ref, const uint8_t* __restrict__ part, const double* __restrict__ nu,
-    const double* __restrict__ mu, const double* __restrict__ q, double* __restrict__ munu, double* __restrict__ cumQ,
+    const __grid_constant__ EvoArgs evo, double* __restrict__ munu, double* __restrict__ cumQ,
     int32_t* __restrict__ ref_freq, double* __restrict__ cum_nu_ba) {
   __shared__ double s_q[kMaxPartitions * 16];
   __shared__ double s_mu[kMaxPartitions];
   __shared__ double s_ws[kScanThreads / 32];
   __shared__ int s_freq[kMaxPartitions * 4];
+  __shared__ double s_tot[2][kClusterCtas];      // slab totals of the current exchange, written by every CTA of the cluster
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x;
-  if (tid < P * 16) s_q[tid] = q[tid];
-  if (tid < P) s_mu[tid] = mu[tid];
+  const int K = P * 4;
+  if (tid < P * 16) s_q[tid] = evo.q[tid];
+  if (tid < P) s_mu[tid] = evo.mu[tid];
   if (tid < kMaxPartitions * 4) s_freq[tid] = 0;
+  if (rank == 0 && tid == 0) cumQ[0] = 0.0;
+  if (rank == 0 && cum_nu_ba != nullptr && tid < K) cum_nu_ba[(size_t)tid * (L + 1)] = 0.0;
   __syncthreads();
-  const int chunk = (L + kScanThreads - 1) / kScanThreads;
-  const int l0 = min(tid * chunk, L), l1 = min(l0 + chunk, L);
-
-  // pass 1: chunk totals of Q_l = mu nu q_a(ref)
-  double tot = 0.0;
   int cnt[kMaxPartitions * 4];
 #pragma unroll
   for (int i = 0; i < kMaxPartitions * 4; ++i) cnt[i] = 0;
-  for (int l = l0; l < l1; ++l) {
-    const int pt = part[l], a = ref[l];
-    const double mn = s_mu[pt] * nu[l];
-    munu[l] = mn;
-    tot += mn * (-s_q[pt * 16 + a * 5]);
+  constexpr int kSlab = kScanThreads * kSitesPerThread;
+  const int num_slabs = (L + kSlab - 1) / kSlab;
+  const int rounds = (num_slabs + kClusterCtas - 1) / kClusterCtas;
+  int xchg = 0;                                  // exchanges so far (parity selects the s_tot buffer)
+  double carry = 0.0;                            // sum of every slab of the earlier rounds (identical in all CTAs)
+  double carry_k[kMaxPartitions * 4];
 #pragma unroll
-    for (int i = 0; i < kMaxPartitions * 4; ++i) cnt[i] += (i == pt * 4 + a);
-  }
-  double btot;
-  const double incl = block_scan_incl<double, kScanThreads>(tot, s_ws, &btot);
-  double run = incl - tot;   // exclusive prefix of this chunk
-  if (tid == 0) cumQ[0] = 0.0;
-  for (int l = l0; l < l1; ++l) {
-    const int pt = part[l], a = ref[l];
-    run += s_mu[pt] * nu[l] * (-s_q[pt * 16 + a * 5]);
-    cumQ[l + 1] = run;
-  }
-#pragma unroll
-  for (int i = 0; i < kMaxPartitions * 4; ++i) if (cnt[i]) atomicAdd(&s_freq[i], cnt[i]);
-  __syncthreads();
-  if (tid < P * 4) ref_freq[tid] = s_freq[tid];
+  for (int i = 0; i < kMaxPartitions * 4; ++i) carry_k[i] = 0.0;
 
-  // cumulative nu per (partition, state): cum_nu_ba[(b*4+a)*(L+1) + l] = sum_{l' < l, beta(l')=b, ref[l']=a} nu_l'
-  if (cum_nu_ba != nullptr) {
-    for (int k = 0; k < P * 4; ++k) {
-      __syncthreads();
-      double t = 0.0;
-      for (int l = l0; l < l1; ++l) if (part[l] * 4 + ref[l] == k) t += nu[l];
-      double bt;
-      const double inc = block_scan_incl<double, kScanThreads>(t, s_ws, &bt);
-      double r = inc - t;
-      double* out = cum_nu_ba + (size_t)k * (L + 1);
-      if (tid == 0) out[0] = 0.0;
-      for (int l = l0; l < l1; ++l) {
-        if (part[l] * 4 + ref[l] == k) r += nu[l];
-        out[l + 1] = r;
+  // one exchange: block scan of `t`, totals to every CTA, cluster barrier; returns the exclusive prefix of this thread's first
+  // site within the round (lower ranks + own lower threads) and the round's grand total
+  auto exchange = [&](double t, double& round_total) -> double {
+    double bt;
+    __syncthreads();                             // s_ws may still be read from the previous scan
+    const double incl = block_scan_incl<double, kScanThreads>(t, s_ws, &bt);
+    const int par = xchg & 1; ++xchg;
+    if (tid < kClusterCtas) *cluster.map_shared_rank(&s_tot[par][rank], tid) = bt;     // my total into CTA tid's buffer
+    cluster.sync();
+    double lower = 0.0, all = 0.0;
+#pragma unroll
+    for (int r = 0; r < kClusterCtas; ++r) { const double x = s_tot[par][r]; if (r < rank) lower += x; all += x; }
+    round_total = all;
+    return lower + (incl - t);
+  };
+
+  for (int round = 0; round < rounds; ++round) {
+    const int l0 = (round * kClusterCtas + rank) * kSlab + tid * kSitesPerThread;
+    double v[kSitesPerThread], nuv[kSitesPerThread];
+    int key[kSitesPerThread];
+    double tot = 0.0;
+#pragma unroll
+    for (int u = 0; u < kSitesPerThread; ++u) {
+      const int l = l0 + u;
+      v[u] = 0.0; nuv[u] = 0.0; key[u] = -1;
+      if (l < L) {
+        const int pt = part[l], a = ref[l];
+        nuv[u] = nu[l]; key[u] = pt * 4 + a;
+        const double mn = s_mu[pt] * nuv[u];
+        munu[l] = mn;
+        v[u] = mn * (-s_q[pt * 16 + a * 5]);
+#pragma unroll
+        for (int i = 0; i < kMaxPartitions * 4; ++i) cnt[i] += (i == key[u]);
+      }
+      tot += v[u];
+    }
+    double all;
+    double run = carry + exchange(tot, all);     // exclusive prefix of my first site
+    carry += all;
+#pragma unroll
+    for (int u = 0; u < kSitesPerThread; ++u) {
+      run += v[u];
+      if (l0 + u < L) cumQ[l0 + u + 1] = run;
+    }
+    // cumulative nu per (partition, state): cum_nu_ba[(b*4+a)*(L+1) + l] = sum_{l' < l, beta(l')=b, ref[l']=a} nu_l'  (same sweep;
+    // depends on nu_l alone, so it is skipped when only mu / pi / q changed)
+    if (cum_nu_ba != nullptr) {
+#pragma unroll
+      for (int k = 0; k < kMaxPartitions * 4; ++k) {
+        if (k < K) {
+          double t = 0.0;
+#pragma unroll
+          for (int u = 0; u < kSitesPerThread; ++u) t += key[u] == k ? nuv[u] : 0.0;
+          double allk;
+          double r = carry_k[k] + exchange(t, allk);
+          carry_k[k] += allk;
+          double* out = cum_nu_ba + (size_t)k * (L + 1);
+#pragma unroll
+          for (int u = 0; u < kSitesPerThread; ++u) {
+            if (key[u] == k) r += nuv[u];
+            if (l0 + u < L) out[l0 + u + 1] = r;
+          }
+        }
       }
     }
   }
+  // reference-state counts: every CTA adds its own into rank 0's shared memory
+#pragma unroll
+  for (int i = 0; i < kMaxPartitions * 4; ++i) if (cnt[i]) atomicAdd(cluster.map_shared_rank(&s_freq[i], 0), cnt[i]);
+  cluster.sync();
+  if (rank == 0 && tid < P * 4) ref_freq[tid] = s_freq[tid];
 }
 
 // Cumulative reference-state counts per (partition, state), interleaved by site:
@@ -106,22 +159,15 @@ int launch_sites_ref_counts(dphy_ctx* ctx, dphy_sites* s) {
   return check_cuda(ctx, cudaGetLastError(), "sites_ref_counts_kernel launch");
 }
 
-int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s) {
-  // mu and q live in the SitesDev host mirror; stage them through the arena
-  size_t mark = ctx->arena.mark();
-  double* d_mu = (double*)ctx->arena.alloc(sizeof(double) * kMaxPartitions);
-  double* d_q = (double*)ctx->arena.alloc(sizeof(double) * kMaxPartitions * 16);
-  if (!d_mu || !d_q) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted in sites_derive");
-  DPHY_CUDA(ctx, cudaMemcpyAsync(d_mu, s->h.mu, sizeof(double) * kMaxPartitions, cudaMemcpyHostToDevice, ctx->stream));
-  DPHY_CUDA(ctx, cudaMemcpyAsync(d_q, s->h.q, sizeof(double) * kMaxPartitions * 16, cudaMemcpyHostToDevice, ctx->stream));
-  sites_derive_kernel<<<1, kScanThreads, 0, ctx->stream>>>(s->L, s->P, s->d_ref, s->d_part, s->d_nu, d_mu, d_q, s->d_munu,
-                                                           s->d_cumQ, s->d_ref_freq, s->d_cum_nu_ba);
+// with_nu_tables: also rebuild the cumulative-nu tables (they depend on nu_l alone: skipped when only mu / pi / q changed)
+int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s, bool with_nu_tables) {
+  EvoArgs evo;
+  for (int i = 0; i < kMaxPartitions; ++i) evo.mu[i] = s->h.mu[i];
+  for (int i = 0; i < kMaxPartitions * 16; ++i) evo.q[i] = s->h.q[i];
+  sites_derive_kernel<<<kClusterCtas, kScanThreads, 0, ctx->stream>>>(s->L, s->P, s->d_ref, s->d_part, s->d_nu, evo, s->d_munu,
+                                                           s->d_cumQ, s->d_ref_freq, with_nu_tables ? s->d_cum_nu_ba : nullptr);
   ctx->launches += 1;
-  int st = check_cuda(ctx, cudaGetLastError(), "sites_derive_kernel launch");
-  // the staging copies were enqueued before the kernel on the same stream; the arena slots may be reused by later
-  // stream-ordered work only, so releasing the mark here is safe.
-  ctx->arena.release(mark);
-  return st;
+  return check_cuda(ctx, cudaGetLastError(), "sites_derive_kernel launch");
 }
 
 }  // namespace dphy

@@ -161,7 +161,8 @@ int  dphy_ctx_set_log_G_path(dphy_ctx* ctx, int path);
 /* ---- sites / evo model ------------------------------------------------------------------------------- */
 int  dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** out);
 void dphy_sites_destroy(dphy_ctx* ctx, dphy_sites* sites);
-/* Subrun::set_evo (core/subrun.h:29-30): new mu/pi/q/nu_l; recomputes cum_Q_l on the device. */
+/* Subrun::set_evo (core/subrun.h:29-30): new mu/pi/q/nu_l; recomputes cum_Q_l on the device.  nu_l == NULL keeps the current site
+ * rates (the cumulative-nu tables are then not rebuilt).  Asynchronous: consumers are ordered after it on the ctx's stream. */
 int  dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* sites, const double* nu_l, const double* mu,
                         const double* pi_a, const double* q_ab);
 /* calc_state_frequencies_per_partition_of (core/phylo_tree_calc.cpp:95-106) -> out[P*4] */
