@@ -330,6 +330,32 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     logg_ms_max, spr_ms_max, gen_ms_max = [float(x) for x in t.tolist()]
 
+    # ---- the reference's global-move cycle: new mu on every chain's site table, re-evaluate every chain, read log G back --------
+    # (what Run does after a global move, core/run.cpp:437-453; every evaluation here follows a real model change)
+    mc_steps = max(3, min(args.steps, 20))
+    mus = [t.host.mu.copy() for t in tables]
+    def model_change_cycle(i):
+        for k, t in enumerate(tables):
+            t.set_evo(mu=mus[k] * (1.0 + 1e-3 * ((i % 7) + 1)))
+        forest.eval_log_G()
+        return forest.log_G()
+    for i in range(2):
+        model_change_cycle(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(mc_steps):
+        mc_out = model_change_cycle(i)
+    torch.cuda.synchronize()
+    mc_s = time.perf_counter() - t0
+    for k, t in enumerate(tables):
+        t.set_evo(mu=mus[k])
+    forest.eval_log_G()
+    assert np.allclose(forest.log_G()[2], lg, rtol=1e-12), "restoring the model does not restore log G"
+    tm = torch.tensor([mc_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    mc_s = float(tm.item())
+
     # ---- e2e: host buffers -> C ABI -> host scalars, copies inside the timed region ------------------------------
     n_e2e = min(args.e2e_chains, args.chains)
     # the caller's EMAT arrays live in page-locked host memory (dphy_host_alloc), as the contract's e2e leg asks: the upload
@@ -385,6 +411,8 @@ def main():
             "loglik_general_schedule": {"value": args.chains * world / (gen_ms_max * 1e-3), "unit": UNIT, "launch_ms": gen_ms_max,
                                         "achieved": alg_bytes / (gen_ms_max * 1e-3) / 1e9, "frac": alg_bytes / (gen_ms_max * 1e-3) / 1e9 / peak,
                                         "note": "every mutation / missation / from-state list re-read per evaluation (also refreshes nsmn and the num_muts tallies)"},
+            "model_change_cycle": {"value": args.chains * mc_steps * world / mc_s, "unit": UNIT, "ms_per_cycle": mc_s / mc_steps * 1e3,
+                                   "note": "dphy_sites_set_evo(new mu) on every chain's site table + evaluation of every chain + log G read back, wall clock"},
             "spr_candidates_per_s": (spr_regions * world / (spr_ms_max * 1e-3)) if spr_ms else None,
             "spr_regions_per_batch": spr_regions, "spr_ms_per_batch": spr_ms_max if spr_ms else None,
             "e2e": {"value": n_e2e * e2e_steps * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
