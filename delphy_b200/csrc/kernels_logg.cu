@@ -245,7 +245,8 @@ __device__ __forceinline__ void tile_back_half(const LogGParams& P, LogGSmem& sm
 constexpr int kIvlBatch = 4;   // missation intervals in flight per node per round
 constexpr int kMutBatch = 2;   // mutations in flight per node per round
 
-__global__ void __launch_bounds__(kLgThreads, 4) emat_log_G_tile_kernel(const LogGParams P, const int32_t* __restrict__ tile_list) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_tile_kernel(const LogGParams P, const int32_t* __restrict__ tile_list) {
   __shared__ LogGSmem sm;
   const ForestDev& f = P.f;
   const int tid = threadIdx.x;
@@ -966,11 +967,16 @@ int launch_log_G_general(dphy_ctx* ctx, dphy_forest* fo) {
       ctx->launches += 1;
     }
     if (fo->num_slow_ctiles > 0) {
-      emat_log_G_tile_kernel<<<fo->num_slow_ctiles, kLgThreads, 0, ctx->stream>>>(P, fo->h.slow_ctiles);
+      emat_log_G_tile_kernel<4><<<fo->num_slow_ctiles, kLgThreads, 0, ctx->stream>>>(P, fo->h.slow_ctiles);
       ctx->launches += 1;
     }
   } else {
-    emat_log_G_tile_kernel<<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);
+    // resident CTAs per SM (tuning knob DPHY_TILE_OCC = 3 | 4 | 5 | 6)
+    static const int tocc = [] { const char* e = getenv("DPHY_TILE_OCC"); return e ? atoi(e) : 4; }();
+    if (tocc == 3) emat_log_G_tile_kernel<3><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);
+    else if (tocc == 5) emat_log_G_tile_kernel<5><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);
+    else if (tocc == 6) emat_log_G_tile_kernel<6><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);
+    else emat_log_G_tile_kernel<4><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);
     ctx->launches += 1;
   }
   emat_log_G_tree_kernel<<<fo->h.num_trees, kTreeThreads, 0, ctx->stream>>>(P);

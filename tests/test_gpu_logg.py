@@ -400,3 +400,24 @@ def test_site_tallies_of_a_whole_forest(ctx, orc):
     fo.close()
     for t in tables:
         t.close()
+
+
+def test_set_evo_rebuilds_the_nu_tables_only_when_nu_changes(ctx, orc):
+    """dphy_sites_set_evo(nu_l = NULL) keeps the cumulative-nu tables (Ttwiddle_beta_a still right under the new mu);
+    with a new nu_l they are rebuilt (site-rate heterogeneity switched on after the upload)."""
+    emat, sites, _ = synth(0, seed=51, num_tips=500, num_partitions=2)
+    ds = db.DeviceSites(ctx, sites); fo = db.Forest(ctx, [emat], [ds])
+    sites.mu = sites.mu * 0.5
+    ds.set_evo(mu=sites.mu)                               # nu_l untouched
+    e, s = to_oracle(emat, sites)
+    want = orc.Ttwiddle_beta_a(e, s)
+    np.testing.assert_allclose(fo.Ttwiddle_beta_a(0), want, rtol=RTOL, atol=1e-9 * np.abs(want).max())
+    assert fo.log_G()[1][0] == pytest.approx(orc.log_G_below_root(e, s), rel=RTOL)
+    sites.nu_l = np.random.default_rng(3).gamma(0.5, 2.0, size=sites.num_sites)
+    ds.set_evo(nu_l=sites.nu_l)
+    e, s = to_oracle(emat, sites)
+    want = orc.Ttwiddle_beta_a(e, s)
+    np.testing.assert_allclose(fo.Ttwiddle_beta_a(0), want, rtol=RTOL, atol=1e-9 * np.abs(want).max())
+    assert fo.log_G()[1][0] == pytest.approx(orc.log_G_below_root(e, s), rel=RTOL)
+    assert rel_err(ds.cum_Q_l()[1:], orc.cum_Q_l(s)[1:]) <= 1e-10
+    fo.close(); ds.close()
