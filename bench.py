@@ -184,8 +184,31 @@ def pick_spr_nodes(emat, n, seed=1234):
     return cand[:n]
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner at communicator
+    creation), so file descriptor 1 is pointed at stderr for the whole run and the line goes to a private duplicate of the
+    original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -216,7 +239,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": last["kind"], "sample": last["sample"],
                                  "spr": last.get("spr")},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit_line(line)
         return 0
 
     import torch
@@ -225,9 +248,6 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION (an explicit INFO is kept)
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = db.Context(local_rank)
@@ -427,7 +447,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_run(emats[0], host_sites[0], args.cpu_seconds, host_cores(), infos[0]["t_max_tip"],
                                                     spr_xs if spr_reqs is not None else None)
-        print(json.dumps(line))
+        emit_line(line)
     forest.close()
     for tb in tables:
         tb.close()
