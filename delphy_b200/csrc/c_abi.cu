@@ -447,6 +447,7 @@ int flatten_status_to_error(dphy_ctx* ctx, uint32_t bits) {
   if (bits & kFlattenErrMissation) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "Missation out of range");
   if (bits & kFlattenErrMutState) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "mutation state not in ACGT");
   if (bits & kFlattenErrFsState) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "missation from-state not in ACGT");
+  if (bits & kFlattenErrTimes) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "a node is earlier than its parent");
   return DPHY_OK;
 }
 
@@ -759,7 +760,8 @@ int dphy_forest_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int
   if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "set_node_times");
   ctx->arena.release(mark);
   fo->evaluated = false;
-  if (st == DPHY_OK && status) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "node out of range");
+  if (st == DPHY_OK && (status & 1u)) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "node out of range");
+  if (st == DPHY_OK && (status & 2u)) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "a displaced node is no longer between its parent and its children");
   return st;
 }
 

@@ -147,6 +147,7 @@ enum : uint32_t {
   kFlattenErrMutState = 8u,    // mutation from/to not in ACGT
   kFlattenErrMissation = 16u,  // missation interval / from-state site out of range (core/mutations.h:187-191)
   kFlattenErrFsState = 32u,    // missation from-state not in ACGT
+  kFlattenErrTimes = 64u,      // a node is earlier than its parent (the reference's integrity CHECK, core/phylo_tree.cpp:131)
 };
 
 struct FlattenParams {

@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(kTile) flatten_nodes_kernel(FlattenParams P, i
   P.post_node[T.node_base + post] = p;
   const int par = R.parent[v];
   P.parent_pos[p] = par < 0 ? -1 : T.node_base + (n - arcs[2 * (T.node_base + par)].y);
+  // times never decrease away from the root (core/phylo_tree.cpp:131): the SPR kernels prune whole subtrees on that invariant
+  if (par >= 0 && R.t[v] < R.t[par]) flag_error(P, kFlattenErrTimes);
   int cm = R.mut_off[v + 1] - R.mut_off[v], ci = R.miss_off[v + 1] - R.miss_off[v], cf = R.fs_off[v + 1] - R.fs_off[v];
   if (cm < 0 || ci < 0 || cf < 0 || R.mut_off[v] < 0 || R.miss_off[v] < 0 || R.fs_off[v] < 0 ||
       R.mut_off[v + 1] > R.num_muts || R.miss_off[v + 1] > R.num_ivls || R.fs_off[v + 1] > R.num_fs) {
@@ -332,10 +334,30 @@ __global__ void set_node_times_kernel(const int32_t* __restrict__ pos_of_node, d
   t[node_base + pos_of_node[node_base + v]] = vals[i];
 }
 
+// After the scatter: every displaced node must still lie between its parent and its children (status bit 1).
+__global__ void check_node_times_kernel(const int32_t* __restrict__ pos_of_node, const double* __restrict__ t, const int32_t* __restrict__ parent_pos,
+                                        const int32_t* __restrict__ subtree_size, int node_base, int num_nodes,
+                                        const int32_t* __restrict__ nodes, int count, uint32_t* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int v = nodes[i];
+  if (v < 0 || v >= num_nodes) return;
+  const int p = node_base + pos_of_node[node_base + v];
+  const int par = parent_pos[p];
+  bool bad = par >= 0 && t[p] < t[par];
+  if (subtree_size[p] > 1) {
+    const int c1 = p + 1, c0 = p + 1 + subtree_size[p + 1];
+    bad = bad || t[c1] < t[p] || t[c0] < t[p];
+  }
+  if (bad) atomicOr(status, 2u);
+}
+
 int launch_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count, uint32_t* d_status) {
   const TreeDev& T = fo->trees[tree];
   set_node_times_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->h.t, T.node_base, T.num_nodes, d_nodes, d_vals, count, d_status);
-  ctx->launches += 1;
+  check_node_times_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(fo->h.pos_of_node, fo->h.t, fo->h.parent_pos, fo->h.subtree_size,
+                                                                        T.node_base, T.num_nodes, d_nodes, count, d_status);
+  ctx->launches += 2;
   return check_cuda(ctx, cudaGetLastError(), "set_node_times_kernel");
 }
 

@@ -180,7 +180,10 @@ int64_t dphy_forest_num_nodes(const dphy_forest* forest);
 int64_t dphy_forest_device_bytes(const dphy_forest* forest);
 /* algorithmic bytes of one log-G evaluation over the whole forest (SURVEY.md section 8d formula) */
 int64_t dphy_forest_log_G_algorithmic_bytes(const dphy_forest* forest);
-/* Update node times in place (accepted inner_node/tip displace moves, core/subrun.cpp:223-231,276-284). */
+/* Update node times in place (accepted inner_node/tip displace moves, core/subrun.cpp:223-231,276-284).  Times must not
+ * decrease away from the root (the reference's integrity CHECK, core/phylo_tree.cpp:131; the SPR kernels prune subtrees on it):
+ * DPHY_ERR_INVALID_ARGUMENT if a displaced node ends up earlier than its parent or later than a child (the times are then
+ * already changed -- set them again); dphy_forest_upload rejects such trees outright. */
 int  dphy_forest_set_node_times(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, int32_t count,
                                 const int32_t* nodes, const double* t);
 

@@ -276,6 +276,11 @@ def test_flatten_rejects_bad_topology(ctx):
         with pytest.raises(db.DphyError):
             db.Forest(ctx, [bad], [ds])
 
+    bad = _copy_emat(emat); bad.t[tip] = bad.t[int(bad.parent[tip])] - 1e-6       # a tip earlier than its parent
+    with pytest.raises(db.DphyError) as ei:
+        db.Forest(ctx, [bad], [ds])
+    assert ei.value.status == db.ERR_INVALID_ARGUMENT
+
     bad = _copy_emat(emat); bad.mut_off[3] = bad.mut_off[emat.num_nodes] + 7      # offsets not monotone
     with pytest.raises(db.DphyError):
         db.Forest(ctx, [bad], [ds])
