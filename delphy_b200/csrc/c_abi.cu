@@ -402,14 +402,50 @@ int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char*
     }
   };
   unsigned hw = std::thread::hardware_concurrency();
-  const size_t nthreads = std::min<size_t>({nchunks, hw ? hw : 1u, (size_t)8});
-  cudaError_t ce = cudaSuccess;
+  const size_t nthreads = std::min<size_t>({nchunks, hw ? hw : 1u, (size_t)16});
+  // The chunk DMAs go to the copy stream; the same stage events as on the direct path are recorded as soon as the chunk that
+  // completes a group (or a tree's lists) has been issued -- the destination layout is group-major for exactly this.
+  {
+    int st = ensure_copy_stream(ctx);
+    if (st != DPHY_OK) return st;
+  }
+  cudaStream_t cs = ctx->copy_stream;
+  struct Milestone { size_t end; cudaEvent_t ev; };
+  std::vector<Milestone> marks;
+  {
+    size_t topo_end = 0, nodes_end = 0;
+    std::vector<size_t> tree_end(ctx->ev_tree.size(), 0);
+    for (const CopyJob& j : jobs) {
+      const size_t e = j.dst_off + j.bytes;
+      if (j.group == 0) topo_end = std::max(topo_end, e);
+      if (j.group <= 1) nodes_end = std::max(nodes_end, e);
+      if (j.group == 2 && j.tree >= 0 && (size_t)j.tree < tree_end.size()) tree_end[j.tree] = std::max(tree_end[j.tree], e);
+    }
+    nodes_end = std::max(nodes_end, topo_end);
+    marks.push_back({topo_end, ctx->ev_topo});
+    marks.push_back({nodes_end, ctx->ev_nodes});
+    for (size_t k = 0; k < tree_end.size(); ++k) if (tree_end[k]) marks.push_back({std::max(tree_end[k], nodes_end), ctx->ev_tree[k]});
+    std::stable_sort(marks.begin(), marks.end(), [](const Milestone& a, const Milestone& b) { return a.end < b.end; });
+  }
+  size_t next_mark = 0;
+  cudaError_t ce = cudaStreamWaitEvent(cs, ctx->ev_main, 0);
+  auto issue_chunk = [&](size_t c) {
+    const size_t lo = c * kChunk, hi = std::min(total, lo + kChunk);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_base + lo, pinned + lo, hi - lo, cudaMemcpyHostToDevice, cs);
+    while (ce == cudaSuccess && next_mark < marks.size() && marks[next_mark].end <= hi) ce = cudaEventRecord(marks[next_mark++].ev, cs);
+  };
+  auto finish = [&]() {
+    while (ce == cudaSuccess && next_mark < marks.size()) ce = cudaEventRecord(marks[next_mark++].ev, cs);
+    if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_lists, cs);
+    *two_phase = ce == cudaSuccess;
+    if (ce != cudaSuccess) sync_copy_streams(ctx);
+  };
   if (nthreads <= 1) {
     for (size_t c = 0; c < nchunks && ce == cudaSuccess; ++c) {
       fill_chunk(c);
-      const size_t lo = c * kChunk, hi = std::min(total, lo + kChunk);
-      ce = cudaMemcpyAsync(d_base + lo, pinned + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream);
+      issue_chunk(c);
     }
+    finish();
   } else {
     std::vector<std::atomic<int>> done(nchunks);
     for (auto& d : done) d.store(0, std::memory_order_relaxed);
@@ -430,12 +466,10 @@ int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char*
         const size_t h = next.fetch_add(1, std::memory_order_relaxed);
         if (h < nchunks) { fill_chunk(h); done[h].store(1, std::memory_order_release); } else std::this_thread::yield();
       }
-      if (ce == cudaSuccess) {
-        const size_t lo = c * kChunk, hi = std::min(total, lo + kChunk);
-        ce = cudaMemcpyAsync(d_base + lo, pinned + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream);
-      }
+      issue_chunk(c);
     }
     for (auto& th : pool) th.join();
+    finish();
   }
   return check_cuda(ctx, ce, "H2D staged upload");
 }
@@ -526,14 +560,25 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   const int r_raw = tmp.reserve(sizeof(RawTreeDev) * num_trees);
   struct RawIds { int parent, c0, c1, t, moff, msite, mfrom, mto, mt, ioff, is, ie, foff, fsite, ffrom; };
   std::vector<RawIds> rid(num_trees);
+  // group-major: every tree's topology arrays first, then the node times + CSR offsets, then the lists tree by tree -- the order
+  // in which the flatten stages need them, so that a staged (in destination order) upload releases the stages early too
+  for (int k = 0; k < num_trees; ++k) {
+    const size_t n = trees[k].num_nodes;
+    RawIds& r = rid[k];
+    r.parent = tmp.reserve(4 * n); r.c0 = tmp.reserve(4 * n); r.c1 = tmp.reserve(4 * n);
+  }
+  for (int k = 0; k < num_trees; ++k) {
+    const size_t n = trees[k].num_nodes;
+    RawIds& r = rid[k];
+    r.t = tmp.reserve(8 * n); r.moff = tmp.reserve(4 * (n + 1)); r.ioff = tmp.reserve(4 * (n + 1)); r.foff = tmp.reserve(4 * (n + 1));
+  }
   for (int k = 0; k < num_trees; ++k) {
     const auto& e = trees[k];
     const size_t n = e.num_nodes, m = e.mut_off[n], iv = e.miss_off[n], fs = e.fs_off[n];
     RawIds& r = rid[k];
-    r.parent = tmp.reserve(4 * n); r.c0 = tmp.reserve(4 * n); r.c1 = tmp.reserve(4 * n); r.t = tmp.reserve(8 * n);
-    r.moff = tmp.reserve(4 * (n + 1)); r.msite = tmp.reserve(4 * m); r.mfrom = tmp.reserve(m); r.mto = tmp.reserve(m); r.mt = tmp.reserve(8 * m);
-    r.ioff = tmp.reserve(4 * (n + 1)); r.is = tmp.reserve(4 * iv); r.ie = tmp.reserve(4 * iv);
-    r.foff = tmp.reserve(4 * (n + 1)); r.fsite = tmp.reserve(4 * fs); r.ffrom = tmp.reserve(fs);
+    r.msite = tmp.reserve(4 * m); r.mfrom = tmp.reserve(m); r.mto = tmp.reserve(m); r.mt = tmp.reserve(8 * m);
+    r.is = tmp.reserve(4 * iv); r.ie = tmp.reserve(4 * iv);
+    r.fsite = tmp.reserve(4 * fs); r.ffrom = tmp.reserve(fs);
   }
   const size_t raw_upload_bytes = tmp.total;
   const int w_arcs0 = tmp.reserve(sizeof(int4) * 2 * N), w_arcs1 = tmp.reserve(sizeof(int4) * 2 * N);
