@@ -133,12 +133,13 @@ __global__ void __launch_bounds__(128) emat_log_G_straddler_kernel(const LogGPar
 // ---- pass 1 --------------------------------------------------------------------------------------------------------------------
 // kLgTile consecutive device positions of one tree per tile; thread tid owns the two consecutive positions 2 tid and
 // 2 tid + 1.  Two kernels share the back half (scan of the deltas, closers, outputs):
-//   * emat_log_G_stream_kernel: persistent CTAs; the tile's node records, event lists and closer slice -- all contiguous
-//     ranges thanks to the DFS/CSR layout -- are staged in shared memory by 1-D bulk async copies (TMA engine,
-//     mbarrier-tracked, two stages deep) while the previous tile is being computed, so HBM streams continuously;
-//     per-node sums come from flat prefix scans over the staged events (no variable-length per-node loop).
-//   * emat_log_G_tile_kernel: one CTA per tile straight from global memory (thread-per-node list walks); handles tiles
-//     whose staging would not fit kStageBytes and forests with per-site rate heterogeneity.
+//   * emat_log_G_tile_kernel (the default): one CTA per tile straight from global memory, thread-per-node list walks with
+//     batched, predicated loads; any site-rate model.
+//   * emat_log_G_stream_kernel (DPHY_LOG_G_PATH_GENERAL_STREAM; uniform site rates only): persistent CTAs; the tile's node
+//     records, event lists and closer slice -- all contiguous ranges thanks to the DFS/CSR layout -- are staged in shared
+//     memory by 1-D bulk async copies (TMA engine, mbarrier-tracked, two stages deep) while the previous tile is being
+//     computed; per-node sums come from flat prefix scans over the staged events.  Measured slower than the direct kernel on
+//     B200 (281 vs 216 us per 16 x 100k-tip evaluation); tiles whose staging would not fit kStageBytes go to the direct kernel.
 struct NodeRegs {
   int par[2], dep[2], om[3];
   double tN[2], tP[2];
