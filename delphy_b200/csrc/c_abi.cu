@@ -5,6 +5,9 @@
 
 #include <algorithm>
 #include <atomic>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <thread>
 #include <cmath>
 #include <cstdio>
@@ -310,6 +313,29 @@ namespace {
 // overlap and the host never touches the data more than once.
 struct CopyJob { size_t dst_off; const void* src; size_t bytes; int group; int tree; };   // group 0: topology (needed first), 1: node times + offsets, 2: lists
 
+// Host copy into the pinned staging slab with non-temporal stores: the destination is read next by the DMA engine, not by this
+// core, so it should neither be fetched for ownership nor displace the source from the cache (plain memcpy below 16 bytes or
+// on non-SSE2 hosts).
+void stream_copy(char* dst, const char* src, size_t n) {
+#if defined(__SSE2__)
+  if (n >= 256) {
+    const size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (head) { std::memcpy(dst, src, head); dst += head; src += head; n -= head; }
+    const size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; ++i) {
+      const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 0), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 1);
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 2), d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 3);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 0, a); _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 1, b);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 2, c); _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 3, d);
+      src += 64; dst += 64;
+    }
+    n -= blocks * 64;
+    _mm_sfence();
+  }
+#endif
+  if (n) std::memcpy(dst, src, n);
+}
+
 bool is_pinned_host(const void* p) {
   cudaPointerAttributes a{};
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -398,7 +424,7 @@ int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char*
     for (; j < jobs.size() && jobs[j].dst_off < hi; ++j) {
       const size_t a = std::max(lo, jobs[j].dst_off), b = std::min(hi, jobs[j].dst_off + jobs[j].bytes);
       const char* src = static_cast<const char*>(jobs[j].src) + (a - jobs[j].dst_off);
-      if (a < b && src != pinned + a) std::memcpy(pinned + a, src, b - a);   // (the per-tree records already lie in the slab)
+      if (a < b && src != pinned + a) stream_copy(pinned + a, src, b - a);   // (the per-tree records already lie in the slab)
     }
   };
   unsigned hw = std::thread::hardware_concurrency();
