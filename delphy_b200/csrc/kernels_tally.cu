@@ -180,28 +180,42 @@ __global__ void tally_beta_a_finalize_kernel(ForestDev f, int tree, const double
 }
 
 // Per-site finalize: scan the +-T_below_miss difference array over sites, then add the no-mutation baseline
-// (T_total - missing time) * [state == ref].  One CTA, chunk per thread (L is at most a few 1e5).
+// (T_total - missing time) * [state == ref].  One CTA sweeping coalesced slabs with a running carry (L is at most a few 1e5).
 __global__ void __launch_bounds__(1024) tally_sites_finalize_kernel(ForestDev f, int tree, const double* __restrict__ PL,
                                                                     const double* __restrict__ miss_diff,
                                                                     double* __restrict__ Ttw_l, double* __restrict__ T_l_a) {
   __shared__ double s_ws[32];
+  __shared__ double s_carry;
   const TreeDev T = f.trees[tree];
   const SitesDev& S = f.sites[T.sites_id];
   const int L = S.L, tid = threadIdx.x;
   const double Ttot = PL[T.num_nodes - 1];
-  const int chunk = (L + 1023) / 1024;
-  const int l0 = min(tid * chunk, L), l1 = min(l0 + chunk, L);
-  double tot = 0.0;
-  for (int l = l0; l < l1; ++l) tot += miss_diff[l];
-  double bt;
-  const double incl = block_scan_incl<double, 1024>(tot, s_ws, &bt);
-  double run = incl - tot;
-  for (int l = l0; l < l1; ++l) {
-    run += miss_diff[l];
-    const double base = Ttot - run;       // time during which site l is present with the reference state (before mutations)
-    const int a = S.ref[l], pt = S.part[l];
-    if (Ttw_l) Ttw_l[l] += (-S.q[pt * 16 + a * 5]) * base;
-    if (T_l_a) T_l_a[(size_t)l * 4 + a] += base;
+  if (tid == 0) s_carry = 0.0;
+  __syncthreads();
+  // slabs of 4,096 sites, 4 consecutive sites per thread: every load / store of a warp is one contiguous run
+  constexpr int kPer = 4;
+  for (int base = 0; base < L; base += 1024 * kPer) {
+    const int l0 = base + tid * kPer;
+    double v[kPer], tot = 0.0;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) { v[u] = l0 + u < L ? miss_diff[l0 + u] : 0.0; tot += v[u]; }
+    double bt;
+    const double incl = block_scan_incl<double, 1024>(tot, s_ws, &bt);
+    double run = s_carry + (incl - tot);
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int l = l0 + u;
+      run += v[u];
+      if (l < L) {
+        const double basev = Ttot - run;    // time during which site l is present with the reference state (before mutations)
+        const int a = S.ref[l], pt = S.part[l];
+        if (Ttw_l) Ttw_l[l] += (-S.q[pt * 16 + a * 5]) * basev;
+        if (T_l_a) T_l_a[(size_t)l * 4 + a] += basev;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_carry += bt;
+    __syncthreads();
   }
 }
 
