@@ -63,6 +63,15 @@ __global__ void __launch_bounds__(kTile) tally_branch_len_scan_kernel(ForestDev 
   if (p < T.node_base + T.num_nodes) PL[p - T.node_base] = s_prefix + incl;
 }
 
+// atomicAdd(base + idx, v) with the lanes of the warp that hit the same address combined first: interval end points pile up on a
+// few sites (every tip's 5' / 3' end gap starts at site 0 / ends at site L), and same-address atomics serialise in L2.
+__device__ __forceinline__ void warp_agg_atomic_add(double* base, int idx, double v) {
+  const unsigned peers = __match_any_sync(__activemask(), idx);
+  double sum = 0.0;
+  for (unsigned rem = peers; rem; rem &= rem - 1) sum += __shfl_sync(peers, v, __ffs(rem) - 1);   // ascending lanes: fixed order
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(base + idx, sum);
+}
+
 struct TallyOut {
   int32_t* num_muts_beta_ab;  // [P*16] or null
   int32_t* num_muts_l;        // [L] or null
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(kTile) tally_events_kernel(ForestDev f, int tr
             }
           }
         }
-        if (out.miss_diff) { atomicAdd(out.miss_diff + s, Tbmiss); atomicAdd(out.miss_diff + e, -Tbmiss); }
+        if (out.miss_diff) { warp_agg_atomic_add(out.miss_diff, s, Tbmiss); warp_agg_atomic_add(out.miss_diff, e, -Tbmiss); }
       }
       for (int i = f.fs_off[p]; i < f.fs_off[p + 1]; ++i) {
         const int l = f.fs_site[i], code = f.fs_code[i], from = code & 3, rf = (code >> 2) & 3, pt = code >> 4;
