@@ -17,6 +17,8 @@
 #include "dphy_internal.h"
 #include "device_utils.cuh"
 
+#include <cstring>
+
 namespace dphy {
 
 // ---- inclusive scan of branch lengths over one tree's device positions --------------------------------------------
@@ -358,12 +360,24 @@ int dphy_forest_calc_site_tallies(dphy_ctx* ctx, dphy_forest* fo, int64_t ld, do
   int st = DPHY_OK;
   ctx->deferred_d2h.clear();
   // a device->host copy into pageable memory blocks the host, so the copies are issued after every tree's kernels are enqueued
+  // the results come back through the ctx's pinned slab in one go (a device->host copy straight into pageable memory blocks the
+  // host for every row), then are copied out to the caller's rows
   auto drain = [&]() {
-    int r = DPHY_OK;
-    for (const auto& c : ctx->deferred_d2h)
-      if (r == DPHY_OK) r = check_cuda(ctx, cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->stream), "site tallies D2H");
-    ctx->deferred_d2h.clear();
+    size_t total = 0;
+    for (const auto& c : ctx->deferred_d2h) total += (c.bytes + 255) & ~(size_t)255;
+    void* hb = nullptr;
+    int r = total ? acquire_pinned(ctx, total, &hb) : DPHY_OK;
+    size_t off = 0;
+    for (const auto& c : ctx->deferred_d2h) {
+      if (r == DPHY_OK) r = check_cuda(ctx, cudaMemcpyAsync(static_cast<char*>(hb) + off, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->stream), "site tallies D2H");
+      off += (c.bytes + 255) & ~(size_t)255;
+    }
     const int r2 = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "site tallies");
+    if (r == DPHY_OK && r2 == DPHY_OK) {
+      off = 0;
+      for (const auto& c : ctx->deferred_d2h) { std::memcpy(c.dst, static_cast<char*>(hb) + off, c.bytes); off += (c.bytes + 255) & ~(size_t)255; }
+    }
+    ctx->deferred_d2h.clear();
     ctx->arena.release(mark);
     return r != DPHY_OK ? r : r2;
   };
