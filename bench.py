@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=4, help="synthetic shape: 1..5 == BASELINE.json configs[0..4]")
     ap.add_argument("--chains", type=int, default=16, help="independent EMATs per GPU (forest must exceed L2)")
-    ap.add_argument("--spr-studies", type=int, default=64, help="full SPR studies per step (0 disables)")
+    ap.add_argument("--spr-studies", type=int, default=128, help="full SPR studies per step (0 disables)")
     ap.add_argument("--e2e-chains", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
