@@ -1,16 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- EMAT log-lik evals/s + SPR candidates scored/s on B200 (BASELINE.json metric).
 
-One "step" = one pass of the hot path over one batch: a full log-G evaluation (calc_lambda_i + calc_log_root_prior
-+ calc_log_G_below_root) of every EMAT of a forest of `--chains` independent synthetic
-100k-tip x 29,903-site EMATs (BASELINE.json configs[3] shape; the forest is larger than the 126 MB L2 so the
-timed kernels stream from HBM), followed by a batch of full (unbounded) SPR regraft studies on one of them.
+One "step" = one log-G evaluation (calc_lambda_i + calc_log_root_prior + calc_log_G_below_root)
+of every EMAT of a forest of `--chains` independent synthetic 100k-tip x 29,903-site EMATs (BASELINE.json configs[3]
+shape; the forest is larger than the 126 MB L2 so the timed kernels stream from HBM).  K steps are enqueued back to
+back between two CUDA events.  The metric's second figure -- SPR candidates scored/s -- is timed the same way right
+after (K batches of `--spr-studies` full, unbounded regraft studies), and so is the general log-G schedule.
 
-  value         = log-lik evals/s, inputs resident in HBM (whole job, all ranks)
-  spr_*         = SPR candidate regions scored/s, same step
-  e2e           = the same log-lik metric through the C ABI with HOST buffers (upload + eval + download per step)
-  roofline      = algorithmic bytes of the log-G kernel / its CUDA-event duration vs the measured HBM peak
-  cpu_baseline  = the reference's own CPU code (oracle/_ref, compiled from /root/reference) on the box's host cores
+  value               = log-lik evals/s, inputs resident in HBM (whole job, all ranks)
+  spr_*               = SPR candidate regions scored/s
+  model_change_cycle  = evals/s when every evaluation follows a model change (set_evo on every table + eval + read-back)
+  e2e                 = the same log-lik metric through the C ABI with HOST buffers (upload + eval + download per step)
+  roofline            = algorithmic bytes of the log-G evaluation / its CUDA-event duration vs the measured HBM peak
+  cpu_baseline        = the reference's own CPU code (oracle/_ref, compiled from /root/reference) on the box's host cores
 
 Multi-GPU (torchrun): each rank owns its own forest of chains (weak scaling; the path shards over independent
 EMATs with no data-path collective -- SURVEY.md section 8e); NCCL is used for the barrier and the max-over-ranks time.
