@@ -67,11 +67,18 @@ class SprRequest(C.Structure):
         ("tree", C.c_int32), ("X", C.c_int32), ("t_X", C.c_double),
         ("start_branch", C.c_int32), ("start_mut_idx", C.c_int32),
         ("init_min_muts", C.c_int32), ("max_muts_from_start", C.c_int32),
-        ("can_change_root", C.c_int32), ("reserved", C.c_int32),
+        ("can_change_root", C.c_int32), ("x_state_mode", C.c_int32),
         ("lambda_X", C.c_double), ("annealing_factor", C.c_double), ("t_max_tip", C.c_double),
         ("n_x_deltas", C.c_int32), ("x_delta_site", i32p), ("x_delta_to", u8p),
         ("n_x_missing", C.c_int32), ("x_missing_start", i32p), ("x_missing_end", i32p),
     ]
+
+
+class SprWeightParams(C.Structure):
+    _fields_ = [("lambda_X", C.c_double), ("annealing_factor", C.c_double), ("t_max_tip", C.c_double)]
+
+
+SPR_X_FROM_TREE, SPR_X_REL_REF, SPR_X_REL_START = 0, 1, 2
 
 
 class SprSummary(C.Structure):
@@ -168,6 +175,12 @@ def lib() -> C.CDLL:
     L.dphy_spr_batch_total_regions.argtypes = [vp, vp]; L.dphy_spr_batch_total_regions.restype = C.c_int64
     L.dphy_spr_batch_get_regions.argtypes = [vp, vp, C.c_int32, C.POINTER(CandidateRegion), C.c_int64]
     L.dphy_spr_batch_get_regions.restype = C.c_int64
+    L.dphy_spr_batch_set_weights.argtypes = [vp, vp, C.POINTER(SprWeightParams)]
+    L.dphy_spr_batch_get_region_weights.argtypes = [vp, vp, C.c_int32, C.POINTER(CandidateRegion), C.c_int64]
+    L.dphy_spr_batch_get_region_weights.restype = C.c_int64
+    L.dphy_spr_batch_log_alpha_in_region.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_double, f64p]
+    L.dphy_gamma_q.argtypes = [vp, C.c_int32, f64p, f64p, f64p]
+    L.dphy_gamma_q_inv.argtypes = [vp, C.c_int32, f64p, f64p, f64p]
     L.dphy_spr_batch_pick_nexus_regions.argtypes = [vp, vp, f64p, i32p]
     L.dphy_spr_batch_find_region.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_double, i32p]
     L.dphy_partition_generate_stencil.argtypes = [C.POINTER(EmatHost), C.c_int32, C.c_uint64, i32p, i32p]
@@ -392,6 +405,18 @@ class Context:
         self.close()
 
     # -- one-shot host-buffer call (what the C++ adapter does for Subrun::calc_cur_log_G)
+    def gamma_q(self, a, x):
+        a = np.ascontiguousarray(a, np.float64); x = np.ascontiguousarray(x, np.float64)
+        out = np.zeros(len(a), np.float64)
+        self.check(lib().dphy_gamma_q(self._h, len(a), _p(a, f64p), _p(x, f64p), _p(out, f64p)))
+        return out
+
+    def gamma_q_inv(self, a, q):
+        a = np.ascontiguousarray(a, np.float64); q = np.ascontiguousarray(q, np.float64)
+        out = np.zeros(len(a), np.float64)
+        self.check(lib().dphy_gamma_q_inv(self._h, len(a), _p(a, f64p), _p(q, f64p), _p(out, f64p)))
+        return out
+
     def log_G_host(self, emat: HostEmat, sites: HostSites, want_lambda=False):
         rp, br = C.c_double(), C.c_double()
         lam = np.zeros(emat.num_nodes, np.float64) if want_lambda else None
@@ -548,8 +573,10 @@ class Forest:
 
 def spr_request(tree, X, t_X, start_branch, start_mut_idx, init_min_muts, lambda_X, t_max_tip,
                 max_muts_from_start=INT32_MAX, can_change_root=True, annealing_factor=0.8,
-                x_deltas=None, x_missing=None):
+                x_deltas=None, x_missing=None, x_state_mode=SPR_X_FROM_TREE):
+    """x_deltas: [(site, to_state)], x_missing: (starts, ends); read only when x_state_mode != SPR_X_FROM_TREE or X == -1."""
     r = SprRequest()
+    r.x_state_mode = x_state_mode
     r.tree, r.X, r.t_X = tree, X, t_X
     r.start_branch, r.start_mut_idx, r.init_min_muts = start_branch, start_mut_idx, init_min_muts
     r.max_muts_from_start, r.can_change_root = max_muts_from_start, int(can_change_root)
@@ -585,6 +612,12 @@ class SprBatch:
     def total_regions(self):
         return int(lib().dphy_spr_batch_total_regions(self.ctx._h, self._h))
 
+    def total_regions_checked(self):
+        n = self.total_regions()
+        if n < 0:
+            self.ctx.check(n)
+        return n
+
     def regions(self, request=-1):
         n = self.total_regions() if request < 0 else self.summaries()[request].num_regions
         out = np.zeros(max(n, 1), REGION_DTYPE)
@@ -602,6 +635,24 @@ class SprBatch:
     def find_region(self, request, branch, t):
         out = C.c_int32(-2)
         self.ctx.check(lib().dphy_spr_batch_find_region(self.ctx._h, self._h, request, branch, t, C.byref(out)))
+        return out.value
+
+    def set_weights(self, params):
+        """params: [(lambda_X, annealing_factor, t_max_tip)] per request -- the Spr_study constructor on enumerated regions."""
+        n = len(self.requests)
+        arr = (SprWeightParams * max(n, 1))(*[SprWeightParams(*p) for p in params])
+        self.ctx.check(lib().dphy_spr_batch_set_weights(self.ctx._h, self._h, arr))
+
+    def region_weights(self, request, regions):
+        """Fills only the weight fields of `regions` (a REGION_DTYPE array from regions())."""
+        got = lib().dphy_spr_batch_get_region_weights(self.ctx._h, self._h, request, _p(regions, C.POINTER(CandidateRegion)), len(regions))
+        if got < 0:
+            self.ctx.check(int(got))
+        return regions
+
+    def log_alpha_in_region(self, request, region_idx, t):
+        out = C.c_double(0.0)
+        self.ctx.check(lib().dphy_spr_batch_log_alpha_in_region(self.ctx._h, self._h, request, region_idx, t, C.byref(out)))
         return out.value
 
     def close(self):

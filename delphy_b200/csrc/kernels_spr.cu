@@ -34,7 +34,8 @@ namespace dphy {
 
 struct SprStudy {
   // ---- inputs (host) ----
-  int32_t tree, X, start_branch, start_mut_idx, init_min_muts, limit, can_change_root, n_x_deltas, n_x_missing, pad0;
+  int32_t tree, X, start_branch, start_mut_idx, init_min_muts, limit, can_change_root, n_x_deltas, n_x_missing;
+  int32_t x_mode;          // DPHY_SPR_X_*: where X's state and missing set come from
   double t_X, lambda_X, f, t_max_tip;
   // slab offsets in bytes
   int64_t off_xtab, off_xkey, off_path, off_xpath, off_H, off_C, off_KB, off_seg, off_regions, off_xd_site, off_xd_to, off_xm_start,
@@ -182,15 +183,22 @@ __global__ void __launch_bounds__(kSetupThreads) spr_xtab_kernel(ForestDev f, Sp
   const TreeDev T = f.trees[S.tree];
   const SitesDev& Si = f.sites[T.sites_id];
   const int L = Si.L;
-  const int xpath_len = S.xpath_len, X = S.X;
+  const int X = S.X;
   uint8_t* xtab = (uint8_t*)(B.slab + S.off_xtab);
   uint32_t* xkey = (uint32_t*)(B.slab + S.off_xkey);
-  const int32_t* xpath = (const int32_t*)(B.slab + S.off_xpath);
   for (int l = tid; l < L; l += kSetupThreads) { xtab[l] = Si.ref[l]; xkey[l] = 0u; }
   if (tid == 0) s_carry = 0;
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  if (X >= 0) {
+  // The state table is the reference sequence overlaid with the LAST mutation per site along a root-ward path, then with the
+  // caller's deltas.  Which path:  FROM_TREE -> root..X (view_of_sequence_at(X));  REL_START -> root..start region (the state the
+  // builder's cur_to_X_deltas are relative to, core/spr_study.cpp:9-24), start branch truncated to its first k0 mutations;
+  // REL_REF -> none (deltas are relative to the reference sequence).
+  const bool from_tree = S.x_mode == DPHY_SPR_X_FROM_TREE && X >= 0;
+  const bool rel_start = S.x_mode == DPHY_SPR_X_REL_START;
+  const int32_t* xpath = from_tree ? (const int32_t*)(B.slab + S.off_xpath) : (const int32_t*)(B.slab + S.off_path);
+  const int xpath_len = from_tree ? S.xpath_len : (rel_start ? S.path_len : 0);
+  if (from_tree) {
     // missing_at_X = union of the missation intervals on the X->root path (disjoint along a path by invariant):
     // one warp per path node, lanes stride over the sites of each interval
     for (int jj = warp; jj < xpath_len; jj += kSetupThreads / 32) {
@@ -200,29 +208,34 @@ __global__ void __launch_bounds__(kSetupThreads) spr_xtab_kernel(ForestDev f, Sp
         for (int l = se.x + lane; l < se.y; l += 32) xtab[l] |= 4;
       }
     }
-    // X's sequence: last mutation per site on the root->X path
-    for (int j0 = 0; j0 < xpath_len; j0 += kSetupThreads) {
-      const int j = j0 + tid;                                   // j counts from the ROOT end of the path
-      const int a = j < xpath_len ? xpath[xpath_len - 1 - j] : -1;
-      const int mo = a >= 0 ? f.mut_off[a] : 0, cnt = a >= 0 ? f.mut_off[a + 1] - mo : 0;
-      int tot;
-      const int incl = block_scan_incl<int, kSetupThreads>(cnt, s_ws, &tot);
-      const int base = s_carry + incl - cnt;
-      if (base + cnt >= (1 << 29)) S.error = 4;
-      for (int i = 0; i < cnt; ++i)
-        atomicMax(xkey + f.mut_site[mo + i], ((uint32_t)(base + i + 1) << 2) | (uint32_t)(f.mut_code[mo + i] & 3));
-      __syncthreads();
-      if (tid == 0) s_carry += tot;
-      __syncthreads();
-    }
   } else {
     const int32_t* ms = (const int32_t*)(B.slab + S.off_xm_start);
     const int32_t* me = (const int32_t*)(B.slab + S.off_xm_end);
     for (int i = warp; i < S.n_x_missing; i += kSetupThreads / 32)
       for (int l = ms[i] + lane; l < me[i]; l += 32) xtab[l] |= 4;
+  }
+  // last mutation per site on the path: every path mutation posts (ordinal << 2 | to) with an atomicMax on a per-site key
+  for (int j0 = 0; j0 < xpath_len; j0 += kSetupThreads) {
+    const int j = j0 + tid;                                   // j counts from the ROOT end of the path
+    const int a = j < xpath_len ? xpath[xpath_len - 1 - j] : -1;
+    const int mo = a >= 0 ? f.mut_off[a] : 0;
+    int cnt = a >= 0 ? f.mut_off[a + 1] - mo : 0;
+    if (rel_start && j == xpath_len - 1 && a != S.root_pos) cnt = min(cnt, S.start_mut_idx);   // region (start, k0): k0 mutations crossed
+    int tot;
+    const int incl = block_scan_incl<int, kSetupThreads>(cnt, s_ws, &tot);
+    const int base = s_carry + incl - cnt;
+    if (base + cnt >= (1 << 28)) S.error = 4;
+    for (int i = 0; i < cnt; ++i)
+      atomicMax(xkey + f.mut_site[mo + i], ((uint32_t)(base + i + 1) << 2) | (uint32_t)(f.mut_code[mo + i] & 3));
+    __syncthreads();
+    if (tid == 0) s_carry += tot;
+    __syncthreads();
+  }
+  if (!from_tree) {
     const int32_t* ds = (const int32_t*)(B.slab + S.off_xd_site);
     const uint8_t* dt = (const uint8_t*)(B.slab + S.off_xd_to);
-    for (int i = tid; i < S.n_x_deltas; i += kSetupThreads) atomicMax(xkey + ds[i], ((uint32_t)(i + 1) << 2) | (uint32_t)(dt[i] & 3));
+    const int base = s_carry;
+    for (int i = tid; i < S.n_x_deltas; i += kSetupThreads) atomicMax(xkey + ds[i], ((uint32_t)(base + i + 1) << 2) | (uint32_t)(dt[i] & 3));
   }
   __syncthreads();
   int cnt = 0;
@@ -710,7 +723,6 @@ struct EmitSmem {
   int start[kEmitNodes + 1];                   // exclusive scan of the per-node candidate counts
   int moff[kEmitNodes], np[kEmitNodes], Hpar[kEmitNodes], Cpar[kEmitNodes], hang[kEmitNodes], cls[kEmitNodes];   // cls = j << 1 | on_path
   int wcnt[kTile / 32];
-  double wmax[kTile / 32];
   signed char dhc[kEmitMutCap];                // (dH + 1) | counted << 2
 };
 
@@ -737,7 +749,6 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) spr_emit_kernel(ForestDev f
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SprView V = make_view(B, S, study);
   RegionHead* out = (RegionHead*)(B.slab + S.off_regions);
-  double* lw_out = (double*)(B.slab + S.off_lw);
   const bool limited = S.limit != INT_MAX;
   const int C0 = S.C0, H0 = S.H0;
   const int t1 = min(t0 + kEmitSub, S.num_tiles);
@@ -802,8 +813,6 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) spr_emit_kernel(ForestDev f
   const int total = sm.start[kEmitNodes];
 
   // ---- (B) one slot per thread ------------------------------------------------------------------------------------------------------------
-  double wmax = -CUDART_INF;
-  bool any = false;
   int carry = 0;
   for (int s0 = 0; s0 < total; s0 += kTile) {
     const int s = s0 + tid;
@@ -868,28 +877,61 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) spr_emit_kernel(ForestDev f
         }
       }
       const int m = S.init_min_muts + (Hk - H0);
-      const double lw = region_log_W(S, r.t_min, r.t_max, m, tNode);
       if (idx >= 0 && idx < S.region_cap) {
-        // the 32-byte head as two 16-byte stores; the raw log-weight goes to a compact array: the normalisation pass reads
-        // 8 bytes per region and writes the 16-byte tail array
+        // the 32-byte head as two 16-byte stores (one whole sector); the weights are a separate streaming pass over the heads
+        // (spr_weights_kernel), as they are a separate step in the reference (the Spr_study constructor, core/spr_study.cpp:226-385)
         int4* o = reinterpret_cast<int4*>(out + idx);
         o[0] = make_int4(r.branch, r.mut_idx, __double2loint(r.t_min), __double2hiint(r.t_min));
         o[1] = make_int4(__double2loint(r.t_max), __double2hiint(r.t_max), m, 0);
-        lw_out[idx] = lw;
       }
-      wmax = any ? fmax(wmax, lw) : lw;   // std::max semantics of the reference's running maximum
-      any = true;
     }
   }
-  // block max -> global max (ordered-integer atomicMax: exact, order independent)
+}
+
+// ---- (4b) raw log-weights of the emitted regions + their maximum (Spr_study::Spr_study, core/spr_study.cpp:306-376) ----------------------
+// Flat over regions: each thread reads one 32-byte head, writes one 8-byte raw log-weight; block maximum -> one ordered-integer
+// atomicMax per CTA (exact, order independent).  The above-root region needs t_S = t[region.branch]: one gather per study at most.
+constexpr int kWeightBlocks = 128;
+__global__ void __launch_bounds__(256) spr_weights_kernel(ForestDev f, SprBatchDev B) {
+  __shared__ double s_ws[8];
+  const int study = blockIdx.y;
+  const SprStudy& S = B.studies[study];
+  if (S.error || !(S.lambda_X > 0.0)) return;
+  const int n = min(S.total_regions, S.region_cap);
+  const int4* heads = (const int4*)(B.slab + S.off_regions);
+  double* lw_out = (double*)(B.slab + S.off_lw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double wmax = -CUDART_INF;
+  bool any = false;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += kWeightBlocks * 256) {
+    const int4 a = __ldg(heads + 2 * (size_t)i), b = __ldg(heads + 2 * (size_t)i + 1);
+    const double t_min = __hiloint2double(a.w, a.z), t_max = __hiloint2double(b.y, b.x);
+    const int m = b.z;
+    double tS = 0.0;
+    if (t_min == -DBL_MAX) tS = f.t[S.node_base + f.pos_of_node[S.node_base + a.x]];
+    const double lw = region_log_W(S, t_min, t_max, m, tS);
+    lw_out[i] = lw;
+    wmax = any ? fmax(wmax, lw) : lw;   // std::max semantics of the reference's running maximum
+    any = true;
+  }
   double wm = warp_max(wmax);
-  if (lane == 0) sm.wmax[warp] = wm;
+  if (lane == 0) s_ws[warp] = wm;
   __syncthreads();
   if (warp == 0) {
-    wm = lane < kTile / 32 ? sm.wmax[lane] : -CUDART_INF;
+    wm = lane < 8 ? s_ws[lane] : -CUDART_INF;
     wm = warp_max(wm);
     if (lane == 0 && wm > -CUDART_INF) atomicMax(&B.studies[study].max_key, f64_order_key(wm));
   }
+}
+
+// new (lambda_X, f, t_max_tip) for studies whose regions are already enumerated: dphy_spr_batch_set_weights
+__global__ void spr_set_weight_params_kernel(ForestDev f, SprBatchDev B, const double* __restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.num_studies) return;
+  SprStudy& S = B.studies[i];
+  S.lambda_X = wp[3 * i]; S.f = wp[3 * i + 1]; S.t_max_tip = wp[3 * i + 2];
+  S.mu = S.lambda_X / (double)(S.L - S.num_missing);
+  S.max_key = 0ULL; S.log_Wmax = 0.0; S.sum_W = 0.0;
 }
 
 // ---- (5) normalise: log_W_over_Wmax -= log_Wmax; W = exp(.); sum in a fixed order ------------------------------------------------------------
@@ -898,7 +940,7 @@ __global__ void __launch_bounds__(256) spr_normalize_kernel(SprBatchDev B) {
   __shared__ int s_last;
   const int study = blockIdx.y;
   SprStudy& S = B.studies[study];
-  if (S.error) return;
+  if (S.error || !(S.lambda_X > 0.0)) return;
   const int n = min(S.total_regions, S.region_cap);
   double2* nw = (double2*)(B.slab + S.off_nw);
   double* part = (double*)(B.slab + S.off_part);
@@ -965,6 +1007,58 @@ __global__ void __launch_bounds__(256) spr_find_kernel(SprBatchDev B, int study,
     if (reg[i].branch == branch && reg[i].t_min < t && t <= reg[i].t_max) atomicMin(out_idx, i);
 }
 
+// ---- Spr_study::log_alpha_in_region (core/spr_study.cpp:486-549): one region, one thread ------------------------------------------------------
+__global__ void spr_log_alpha_kernel(ForestDev f, SprBatchDev B, int study, int idx, double t, double* out) {
+  const SprStudy& S = B.studies[study];
+  const RegionHead rg = ((const RegionHead*)(B.slab + S.off_regions))[idx];
+  const double2 nw = ((const double2*)(B.slab + S.off_nw))[idx];
+  const double log_p_region = nw.x - log(S.sum_W);
+  if (rg.t_min != -DBL_MAX) { *out = log_p_region - log(rg.t_max - rg.t_min); return; }
+  const double fa = S.f, lam = S.lambda_X;
+  const int m = rg.min_muts;
+  const double tS = f.t[S.node_base + f.pos_of_node[S.node_base + rg.branch]];
+  const double s_min = fabs(S.t_X - tS);
+  const double t_early = fmin(S.t_X, tS);
+  const double s_max = s_min + 20.0 * (S.t_max_tip - t_early);
+  const double x_min = lam * fa * s_min, x_max = lam * fa * s_max;
+  const double sv = S.t_X - t + tS - t;
+  if (sv > s_max + 1e-6) { *out = -CUDART_INF; return; }
+  if (x_max < 0.01) {
+    const double alpha = fa * m + 1;
+    *out = log_p_region + 0.6931471805599453 + log(alpha) + (alpha - 1) * log(sv) + -alpha * log(s_max) + -log1p(-pow(s_min / s_max, alpha));
+    return;
+  }
+  const double a = fa * m + 1;
+  *out = log_p_region + 0.6931471805599453 + log(lam * fa) + fa * m * log(lam * fa * sv) + -lam * fa * sv + -lgamma(a)
+         - log(dev_gamma_q(a, x_min) - dev_gamma_q(a, x_max));
+}
+
+// x with Q(a, x) = q: bracket by doubling, then Newton steps safeguarded by bisection (dQ/dx = -x^(a-1) e^-x / Gamma(a))
+__device__ double dev_gamma_q_inv(double a, double q) {
+  if (q <= 0.0) return CUDART_INF;
+  if (q >= 1.0) return 0.0;
+  double lo = 0.0, hi = a > 1.0 ? a : 1.0;
+  while (dev_gamma_q(a, hi) > q) { lo = hi; hi *= 2.0; if (hi > 1e300) return CUDART_INF; }
+  double x = 0.5 * (lo + hi);
+  for (int it = 0; it < 400; ++it) {
+    const double fv = dev_gamma_q(a, x) - q;
+    if (fv > 0.0) lo = x; else hi = x;
+    const double dq = -exp((a - 1.0) * log(x) - x - lgamma(a));
+    double xn = (dq != 0.0 && isfinite(dq)) ? x - fv / dq : 0.5 * (lo + hi);
+    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    if (fabs(xn - x) <= 4e-16 * fabs(x)) { x = xn; break; }
+    x = xn;
+  }
+  return x;
+}
+
+// which: 0 -> out[i] = Q(a[i], x[i]);  1 -> out[i] = x with Q(a[i], x) = x_or_q[i]
+__global__ void gamma_q_kernel(int which, int n, const double* __restrict__ a, const double* __restrict__ x_or_q, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = which == 0 ? dev_gamma_q(a[i], x_or_q[i]) : dev_gamma_q_inv(a[i], x_or_q[i]);
+}
+
 }  // namespace dphy
 
 using namespace dphy;
@@ -976,6 +1070,9 @@ struct dphy_spr_batch {
   int32_t num = 0;
   std::vector<SprStudy> host;     // filled by get_summaries
   bool fetched = false;
+  bool weighted = false;          // spr_weights_kernel + spr_normalize_kernel have run for the current (lambda_X, f, t_max_tip)
+  int status = DPHY_OK;           // sticky: the first per-study error found by spr_fetch, returned by every accessor
+  std::string status_msg;
   dphy_forest* forest = nullptr;
 };
 
@@ -1010,11 +1107,17 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     if (r.X == T.root_id) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: X must not be the root (CHECK_NE(X, tree->root))"); }
     if (r.start_branch < 0 || r.start_branch >= T.num_nodes) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: start branch out of range"); }
     if (r.start_branch == r.X) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: start region is on branch X"); }
-    if (!(r.lambda_X > 0.0)) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: lambda_X must be > 0"); }
+    if (!(r.lambda_X >= 0.0)) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: lambda_X must be >= 0 (0: enumerate only)"); }
+    if (r.x_state_mode < DPHY_SPR_X_FROM_TREE || r.x_state_mode > DPHY_SPR_X_REL_START) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: unknown x_state_mode"); }
+    if ((r.x_state_mode != DPHY_SPR_X_FROM_TREE || r.X < 0) && ((r.n_x_deltas > 0 && (!r.x_delta_site || !r.x_delta_to)) || (r.n_x_missing > 0 && (!r.x_missing_start || !r.x_missing_end)) || r.n_x_deltas < 0 || r.n_x_missing < 0)) {
+      delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: explicit X state without its arrays");
+    }
     S.tree = r.tree; S.X = r.X; S.start_branch = r.start_branch; S.start_mut_idx = r.start_mut_idx;
     S.init_min_muts = r.init_min_muts; S.limit = r.max_muts_from_start; S.can_change_root = r.can_change_root != 0;
     S.t_X = r.t_X; S.lambda_X = r.lambda_X; S.f = r.annealing_factor; S.t_max_tip = r.t_max_tip;
-    S.n_x_deltas = r.X < 0 ? r.n_x_deltas : 0; S.n_x_missing = r.X < 0 ? r.n_x_missing : 0;
+    S.x_mode = (r.X < 0 && r.x_state_mode == DPHY_SPR_X_FROM_TREE) ? DPHY_SPR_X_REL_REF : r.x_state_mode;   // a detached X has no state in the tree
+    const bool explicit_x = S.x_mode != DPHY_SPR_X_FROM_TREE;
+    S.n_x_deltas = explicit_x ? r.n_x_deltas : 0; S.n_x_missing = explicit_x ? r.n_x_missing : 0;
     for (int k = 0; k < S.n_x_deltas; ++k)
       if (r.x_delta_site[k] < 0 || r.x_delta_site[k] >= L || r.x_delta_to[k] > 3) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: X delta out of range"); }
     for (int k = 0; k < S.n_x_missing; ++k)
@@ -1115,8 +1218,15 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     else if (occ == 6) spr_emit_kernel<6><<<grid_emit, kTile, 0, ctx->stream>>>(fo->h, b->dev);
     else spr_emit_kernel<4><<<grid_emit, kTile, 0, ctx->stream>>>(fo->h, b->dev);
   }
-  spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ctx->stream>>>(b->dev);
-  launched += 3;
+  launched += 2;
+  bool any_weighted = false;
+  for (int i = 0; i < n; ++i) any_weighted |= b->host[i].lambda_X > 0.0;
+  if (any_weighted) {
+    spr_weights_kernel<<<dim3(kWeightBlocks, n), 256, 0, ctx->stream>>>(fo->h, b->dev);
+    spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ctx->stream>>>(b->dev);
+    launched += 2;
+    b->weighted = true;
+  }
   ctx->launches += launched;
   st = check_cuda(ctx, cudaGetLastError(), "spr kernels launch");
   if (st != DPHY_OK) { cudaFreeAsync(d, ctx->stream); delete b; return st; }
@@ -1131,16 +1241,24 @@ void dphy_spr_batch_destroy(dphy_ctx* ctx, dphy_spr_batch* b) {
 }
 
 static int spr_fetch(dphy_ctx* ctx, dphy_spr_batch* b) {
+  if (b->status != DPHY_OK) return set_error(ctx, b->status, b->status_msg);
   if (b->fetched || b->num == 0) return DPHY_OK;
   DPHY_CUDA(ctx, cudaMemcpyAsync(b->host.data(), b->dev.studies, sizeof(SprStudy) * b->num, cudaMemcpyDeviceToHost, ctx->stream));
   DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   b->fetched = true;
   for (int i = 0; i < b->num; ++i) {
-    if (b->host[i].error == 1) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: X has no parent");
-    if (b->host[i].error == 2) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: start_mut_idx out of range for the start branch");
-    if (b->host[i].error == 3) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: start region lies inside X's subtree");
-    if (b->host[i].error == 4) return set_error(ctx, DPHY_ERR_INTERNAL, "spr: more than 2^29 mutations on the root->X path");
-    if (b->host[i].total_regions > b->host[i].region_cap) return set_error(ctx, DPHY_ERR_INTERNAL, "spr: region capacity exceeded");
+    const char* what = nullptr; int st = DPHY_OK;
+    if (b->host[i].error == 1) { st = DPHY_ERR_INVALID_ARGUMENT; what = "X has no parent"; }
+    else if (b->host[i].error == 2) { st = DPHY_ERR_OUT_OF_RANGE; what = "start_mut_idx out of range for the start branch"; }
+    else if (b->host[i].error == 3) { st = DPHY_ERR_INVALID_ARGUMENT; what = "start region lies inside X's subtree"; }
+    else if (b->host[i].error == 4) { st = DPHY_ERR_INTERNAL; what = "more than 2^28 mutations on the root path"; }
+    else if (b->host[i].total_regions > b->host[i].region_cap) { st = DPHY_ERR_INTERNAL; what = "region capacity exceeded"; }
+    if (st != DPHY_OK) {
+      // sticky: every later accessor of this batch (getters, pick, find) reports the same failure, naming the request
+      b->status = st;
+      b->status_msg = "spr: request " + std::to_string(i) + ": " + what;
+      return set_error(ctx, b->status, b->status_msg);
+    }
   }
   return DPHY_OK;
 }
@@ -1182,10 +1300,66 @@ int64_t dphy_spr_batch_get_regions(dphy_ctx* ctx, dphy_spr_batch* b, int32_t req
       char* dst = reinterpret_cast<char*>(out + w);
       DPHY_CUDA(ctx, cudaMemcpy2DAsync(dst, sizeof(dphy_candidate_region), b->dev.slab + S.off_regions, sizeof(RegionHead), sizeof(RegionHead),
                                        (size_t)S.total_regions, cudaMemcpyDeviceToHost, ctx->stream));
-      DPHY_CUDA(ctx, cudaMemcpy2DAsync(dst + offsetof(dphy_candidate_region, log_W_over_Wmax), sizeof(dphy_candidate_region),
+      if (b->weighted && S.lambda_X > 0.0) {
+        DPHY_CUDA(ctx, cudaMemcpy2DAsync(dst + offsetof(dphy_candidate_region, log_W_over_Wmax), sizeof(dphy_candidate_region),
+                                         b->dev.slab + S.off_nw, sizeof(double2), sizeof(double2), (size_t)S.total_regions,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+      } else {
+        // enumerate-only study: the reference's builder leaves both weights at 0.0 (core/spr_study.h:26-27)
+        for (int64_t k = 0; k < S.total_regions; ++k) { out[w + k].log_W_over_Wmax = 0.0; out[w + k].W_over_Wmax = 0.0; }
+      }
+    }
+    w += S.total_regions;
+  }
+  DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return w;
+}
+
+int dphy_spr_batch_set_weights(dphy_ctx* ctx, dphy_spr_batch* b, const dphy_spr_weight_params* params) {
+  if (!ctx || !b || (!params && b->num > 0)) return DPHY_ERR_INVALID_ARGUMENT;
+  if (b->status != DPHY_OK) return set_error(ctx, b->status, b->status_msg);
+  if (b->num == 0) return DPHY_OK;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < b->num; ++i)
+    if (!(params[i].lambda_X > 0.0)) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: lambda_X must be > 0");
+  void* hbv = nullptr;
+  int st = acquire_pinned(ctx, sizeof(double) * 3 * b->num, &hbv);
+  if (st != DPHY_OK) return st;
+  double* hb = (double*)hbv;
+  for (int i = 0; i < b->num; ++i) { hb[3 * i] = params[i].lambda_X; hb[3 * i + 1] = params[i].annealing_factor; hb[3 * i + 2] = params[i].t_max_tip; }
+  const size_t mark = ctx->arena.mark();
+  double* d_wp = (double*)ctx->arena.alloc(sizeof(double) * 3 * b->num);
+  if (!d_wp) { release_pinned_async(ctx); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (spr weights)"); }
+  cudaError_t ce = cudaMemcpyAsync(d_wp, hb, sizeof(double) * 3 * b->num, cudaMemcpyHostToDevice, ctx->stream);
+  release_pinned_async(ctx);
+  if (ce == cudaSuccess) {
+    spr_set_weight_params_kernel<<<(b->num + 127) / 128, 128, 0, ctx->stream>>>(b->forest->h, b->dev, d_wp);
+    spr_weights_kernel<<<dim3(kWeightBlocks, b->num), 256, 0, ctx->stream>>>(b->forest->h, b->dev);
+    spr_normalize_kernel<<<dim3(kNormBlocks, b->num), 256, 0, ctx->stream>>>(b->dev);
+    ctx->launches += 3;
+    ce = cudaGetLastError();
+  }
+  ctx->arena.release(mark);
+  if (ce != cudaSuccess) return check_cuda(ctx, ce, "spr set_weights");
+  b->weighted = true;
+  b->fetched = false;       // summaries (mu, log_Wmax, sum_W) changed
+  return DPHY_OK;
+}
+
+int64_t dphy_spr_batch_get_region_weights(dphy_ctx* ctx, dphy_spr_batch* b, int32_t request, dphy_candidate_region* out, int64_t cap) {
+  if (!ctx || !b || (!out && cap > 0) || request >= b->num) return DPHY_ERR_INVALID_ARGUMENT;
+  int st = spr_fetch(ctx, b);
+  if (st != DPHY_OK) return st;
+  if (!b->weighted) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: this batch has no weights (lambda_X == 0 and dphy_spr_batch_set_weights not called)");
+  int64_t w = 0;
+  const int lo = request < 0 ? 0 : request, hi = request < 0 ? b->num : request + 1;
+  for (int i = lo; i < hi; ++i) {
+    const SprStudy& S = b->host[i];
+    if (w + S.total_regions > cap) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: output capacity too small");
+    if (S.total_regions > 0)
+      DPHY_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(out + w) + offsetof(dphy_candidate_region, log_W_over_Wmax), sizeof(dphy_candidate_region),
                                        b->dev.slab + S.off_nw, sizeof(double2), sizeof(double2), (size_t)S.total_regions,
                                        cudaMemcpyDeviceToHost, ctx->stream));
-    }
     w += S.total_regions;
   }
   DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1195,6 +1369,8 @@ int64_t dphy_spr_batch_get_regions(dphy_ctx* ctx, dphy_spr_batch* b, int32_t req
 int dphy_spr_batch_pick_nexus_regions(dphy_ctx* ctx, dphy_spr_batch* b, const double* r, int32_t* out_idx) {
   if (!ctx || !b || !r || !out_idx) return DPHY_ERR_INVALID_ARGUMENT;
   if (b->num == 0) return DPHY_OK;
+  { const int st0 = spr_fetch(ctx, b); if (st0 != DPHY_OK) return st0; }
+  if (!b->weighted) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: this batch has no weights");
   const size_t mark = ctx->arena.mark();
   double* d_r = (double*)ctx->arena.alloc(sizeof(double) * b->num);
   int32_t* d_o = (int32_t*)ctx->arena.alloc(sizeof(int32_t) * b->num);
@@ -1211,6 +1387,7 @@ int dphy_spr_batch_pick_nexus_regions(dphy_ctx* ctx, dphy_spr_batch* b, const do
 
 int dphy_spr_batch_find_region(dphy_ctx* ctx, dphy_spr_batch* b, int32_t request, int32_t branch, double t, int32_t* out_idx) {
   if (!ctx || !b || !out_idx || request < 0 || request >= b->num) return DPHY_ERR_INVALID_ARGUMENT;
+  { const int st0 = spr_fetch(ctx, b); if (st0 != DPHY_OK) return st0; }
   const size_t mark = ctx->arena.mark();
   int32_t* d_o = (int32_t*)ctx->arena.alloc(sizeof(int32_t));
   if (!d_o) { ctx->arena.release(mark); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (spr find)"); }
@@ -1226,5 +1403,50 @@ int dphy_spr_batch_find_region(dphy_ctx* ctx, dphy_spr_batch* b, int32_t request
   *out_idx = res == INT_MAX ? -1 : res;
   return st;
 }
+
+int dphy_spr_batch_log_alpha_in_region(dphy_ctx* ctx, dphy_spr_batch* b, int32_t request, int32_t region_idx, double t, double* out) {
+  if (!ctx || !b || !out || request < 0 || request >= b->num) return DPHY_ERR_INVALID_ARGUMENT;
+  { const int st0 = spr_fetch(ctx, b); if (st0 != DPHY_OK) return st0; }
+  if (!b->weighted) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: this batch has no weights");
+  if (region_idx < 0 || region_idx >= b->host[request].total_regions) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: region index out of range");
+  cudaSetDevice(ctx->device);
+  const size_t mark = ctx->arena.mark();
+  double* d_o = (double*)ctx->arena.alloc(sizeof(double));
+  if (!d_o) { ctx->arena.release(mark); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (spr log_alpha)"); }
+  spr_log_alpha_kernel<<<1, 1, 0, ctx->stream>>>(b->forest->h, b->dev, request, region_idx, t, d_o);
+  ctx->launches += 1;
+  int st = check_cuda(ctx, cudaGetLastError(), "spr_log_alpha_kernel");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(out, d_o, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "spr log_alpha");
+  ctx->arena.release(mark);
+  return st;
+}
+
+static int gamma_q_call(dphy_ctx* ctx, int which, int32_t n, const double* a, const double* v, double* out) {
+  if (!ctx || n < 0 || (n > 0 && (!a || !v || !out))) return DPHY_ERR_INVALID_ARGUMENT;
+  if (n == 0) return DPHY_OK;
+  for (int i = 0; i < n; ++i) {
+    if (!(a[i] > 0.0)) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "gamma_q: a must be > 0");
+    if (which == 0 ? !(v[i] >= 0.0) : !(v[i] >= 0.0 && v[i] <= 1.0)) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, which == 0 ? "gamma_q: x must be >= 0" : "gamma_q_inv: q must be in [0, 1]");
+  }
+  cudaSetDevice(ctx->device);
+  const size_t mark = ctx->arena.mark();
+  double* d = (double*)ctx->arena.alloc(sizeof(double) * 3 * (size_t)n);
+  if (!d) { ctx->arena.release(mark); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (gamma_q)"); }
+  int st = check_cuda(ctx, cudaMemcpyAsync(d, a, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(d + n, v, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+  if (st == DPHY_OK) {
+    gamma_q_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(which, n, d, d + n, d + 2 * (size_t)n);
+    ctx->launches += 1;
+    st = check_cuda(ctx, cudaGetLastError(), "gamma_q_kernel");
+  }
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(out, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gamma_q");
+  ctx->arena.release(mark);
+  return st;
+}
+
+int dphy_gamma_q(dphy_ctx* ctx, int32_t n, const double* a, const double* x, double* out) { return gamma_q_call(ctx, 0, n, a, x, out); }
+int dphy_gamma_q_inv(dphy_ctx* ctx, int32_t n, const double* a, const double* q, double* out) { return gamma_q_call(ctx, 1, n, a, q, out); }
 
 }  // extern "C"

@@ -90,10 +90,24 @@ typedef struct dphy_candidate_region {
 
 /* Inputs of one SPR study == Spr_study_builder{tree, X, t_X, missing_at_X} + .max_muts_from_start +
  * .seed_fill_from(branch, mut_idx, deltas, can_change_root) + Spr_study{builder, lambda_X, f, t_X, t_max_tip}
- * (core/spr_study.h:69-205).  missing_at_X and X's sequence are reconstructed on the device from the EMAT
- * (reconstruct_missing_sites_at / view_of_sequence_at, core/phylo_tree_calc.cpp:19-56), unless X == -1
- * (k_no_node, the build_usher_like_tree mode, core/phylo_tree.cpp:918-932), in which case the caller passes
- * X's sequence as deltas from the reference sequence plus its missing intervals. */
+ * (core/spr_study.h:69-205).
+ *
+ * Where X's sequence and missing set come from (x_state_mode):
+ *   DPHY_SPR_X_FROM_TREE  X >= 0 is attached and the EMAT is self-consistent: both are reconstructed on the device
+ *                         (reconstruct_missing_sites_at / view_of_sequence_at, core/phylo_tree_calc.cpp:19-56);
+ *   DPHY_SPR_X_REL_REF    the caller passes X's sequence as deltas from the REFERENCE sequence plus its missing intervals
+ *                         (a sequence that is not in the tree: X == -1 == k_no_node, build_usher_like_tree,
+ *                         core/phylo_tree.cpp:918-932);
+ *   DPHY_SPR_X_REL_START  exactly the builder's own inputs: x_delta_* is the Site_deltas `init_to_X_deltas` handed to
+ *                         seed_fill_from -- deltas from the state at the START REGION (start_branch, start_mut_idx) to X --
+ *                         and x_missing_* is `missing_at_X` (core/spr_study.cpp:9-24, core/subrun.cpp:543-554).  Nothing about X is
+ *                         read from the tree, so this is the mode for studies on a tree mid-move (after Spr_move::peel_graft /
+ *                         move, core/subrun.cpp:539-599) and it works for X >= 0 and X == -1 alike.
+ * lambda_X == 0 enumerates the regions only (the builder without the Spr_study constructor): weights stay 0 until
+ * dphy_spr_batch_set_weights. */
+#define DPHY_SPR_X_FROM_TREE 0
+#define DPHY_SPR_X_REL_REF 1
+#define DPHY_SPR_X_REL_START 2
 typedef struct dphy_spr_request {
   int32_t tree;                 /* index of the EMAT inside the forest */
   int32_t X;                    /* node being pruned (host node index), or -1 */
@@ -103,14 +117,21 @@ typedef struct dphy_spr_request {
   int32_t init_min_muts;        /* == ssize(init_to_X_deltas) */
   int32_t max_muts_from_start;  /* INT32_MAX == unbounded */
   int32_t can_change_root;
-  int32_t reserved;
-  double  lambda_X;
+  int32_t x_state_mode;         /* DPHY_SPR_X_* */
+  double  lambda_X;             /* > 0, or 0 for "enumerate only" */
   double  annealing_factor;
   double  t_max_tip;
-  /* only read when X == -1: */
-  int32_t n_x_deltas;  const int32_t* x_delta_site;  const uint8_t* x_delta_to;     /* X's state where != ref */
+  /* only read when x_state_mode != DPHY_SPR_X_FROM_TREE: */
+  int32_t n_x_deltas;  const int32_t* x_delta_site;  const uint8_t* x_delta_to;
   int32_t n_x_missing; const int32_t* x_missing_start; const int32_t* x_missing_end;
 } dphy_spr_request;
+
+/* Inputs of the Spr_study constructor for a study whose regions are already enumerated (core/spr_study.cpp:226-239). */
+typedef struct dphy_spr_weight_params {
+  double lambda_X;
+  double annealing_factor;
+  double t_max_tip;
+} dphy_spr_weight_params;
 
 /* Outputs of Spr_study::Spr_study (core/spr_study.cpp:226-385). */
 typedef struct dphy_spr_summary {
@@ -244,6 +265,22 @@ int  dphy_spr_batch_pick_nexus_regions(dphy_ctx* ctx, dphy_spr_batch* batch, con
 /* Spr_study::find_region (core/spr_study.cpp:474-484) for study `request` */
 int  dphy_spr_batch_find_region(dphy_ctx* ctx, dphy_spr_batch* batch, int32_t request, int32_t branch, double t,
                                 int32_t* out_region_idx);
+/* The Spr_study constructor on its own (core/spr_study.cpp:226-385): (re)computes log_W_over_Wmax / W_over_Wmax, log_Wmax and
+ * sum_W_over_Wmax of every study of the batch from its enumerated regions with params[num_requests].  Asynchronous. */
+int  dphy_spr_batch_set_weights(dphy_ctx* ctx, dphy_spr_batch* batch, const dphy_spr_weight_params* params);
+/* writes ONLY the (log_W_over_Wmax, W_over_Wmax) fields of out[0..count) (records already filled by dphy_spr_batch_get_regions
+ * keep their other fields); returns count or <0 */
+int64_t dphy_spr_batch_get_region_weights(dphy_ctx* ctx, dphy_spr_batch* batch, int32_t request,
+                                          dphy_candidate_region* out, int64_t cap);
+/* Spr_study::log_alpha_in_region (core/spr_study.cpp:486-549): log proposal density of attaching at time t in region_idx. */
+int  dphy_spr_batch_log_alpha_in_region(dphy_ctx* ctx, dphy_spr_batch* batch, int32_t request, int32_t region_idx, double t,
+                                        double* out);
+/* Regularized upper incomplete gamma Q(a,x) and its inverse in x, fp64, evaluated on the device for n argument pairs: the two
+ * special functions behind the above-root region (safe_gamma_q / safe_gamma_q_inv, core/safe_gamma_math.h:46-83, which the
+ * reference takes from Boost.Math).  Spr_study::pick_time_in_region (core/spr_study.cpp:424-471) draws its uniform on the host
+ * between Q(a, x_max) and Q(a, x_min) and inverts here. */
+int  dphy_gamma_q(dphy_ctx* ctx, int32_t n, const double* a, const double* x, double* out);
+int  dphy_gamma_q_inv(dphy_ctx* ctx, int32_t n, const double* a, const double* q, double* out);
 
 /* ---- tree partitioning (one or more parts per GPU) ------------------------------------------------------------- */
 /* generate_random_partition_stencil (core/tree_partitioning.h:139-194): up to num_parts-1 cut points. */

@@ -197,3 +197,164 @@ def test_studies_on_every_tree_of_a_forest(ctx, orc):
     batch.close(); fo.close()
     for t in tables:
         t.close()
+
+
+def _state_at_region(emat, sites, branch, k):
+    """Sequence at region (branch, k): the reference overlaid with the mutations from the root down to the k-th of `branch`."""
+    path = []
+    v = branch
+    while v >= 0:
+        path.append(v)
+        v = int(emat.parent[v])
+    state = sites.ref.copy()
+    for v in reversed(path):
+        m0, m1 = int(emat.mut_off[v]), int(emat.mut_off[v + 1])
+        if v == branch and v != emat.root:
+            m1 = m0 + k
+        for i in range(m0, m1):
+            state[emat.mut_site[i]] = emat.mut_to[i]
+    return state
+
+
+@pytest.mark.parametrize("cfg,ov", [(0, {}), (0, dict(num_root_mutations=5, num_partitions=2)), (1, {})])
+@pytest.mark.parametrize("limit", [INF, 2])
+def test_builder_inputs_taken_as_given(ctx, orc, cfg, ov, limit):
+    """DPHY_SPR_X_REL_START: X's state = state at the start region + the caller's deltas, missing_at_X = the caller's intervals;
+    nothing about X is read from the tree (the contract of Spr_study_builder::seed_fill_from, core/spr_study.cpp:9-24, which
+    Subrun::spr1_move uses on a tree mid-move, core/subrun.cpp:539-599).  Checked for (a) inputs consistent with the tree, where
+    the result must also equal the FROM_TREE mode, (b) deltas / missing sets the tree knows nothing about, (c) start regions in
+    the middle of a branch and away from X's sibling, (d) a detached X."""
+    emat, sites, info = synth(cfg, **ov)
+    e, s = to_oracle(emat, sites)
+    ds = db.DeviceSites(ctx, sites)
+    fo = db.Forest(ctx, [emat], [ds])
+    lam = fo.lambda_i(0)
+    rng = np.random.default_rng(5 + cfg)
+    L = sites.num_sites
+    nodes = [int(v) for v in rng.permutation(emat.num_nodes) if v != emat.root]
+    reqs, wants = [], []
+
+    def add(X, t_X, start, k0, deltas, missing, ccr, lam_X):
+        reqs.append(db.spr_request(0, X, t_X, start, k0, len(deltas), lam_X, info["t_max_tip"], limit, ccr, 0.8,
+                                   x_deltas=[(l, to) for (l, fr, to) in deltas], x_missing=missing,
+                                   x_state_mode=db.SPR_X_REL_START))
+        wants.append(orc.spr_study(e, s, X, t_X, missing, start, k0, deltas, limit, ccr, weights=(lam_X, 0.8, info["t_max_tip"])))
+
+    for X in nodes[:12]:
+        P = int(emat.parent[X])
+        S = int(emat.child1[P]) if int(emat.child0[P]) == X else int(emat.child0[P])
+        miss = orc.missing_sites_at(e, s, X)
+        missing_mask = np.zeros(L, bool)
+        for a, b in zip(*miss):
+            missing_mask[a:b] = True
+        # (a) consistent inputs: deltas P -> X at sites not missing at X
+        dl = [(l, fr, to) for l, (fr, to) in db.net_branch_deltas(emat, X).items() if not missing_mask[l]]
+        add(X, float(emat.t[X]), S, 0, dl, miss, True, float(lam[X]))
+        # (b) deltas and missing set unrelated to what the tree says about X
+        st0 = _state_at_region(emat, sites, S, 0)
+        sites_b = rng.choice(L, size=7, replace=False)
+        dl_b = [(int(l), int(st0[l]), int((st0[l] + 1 + rng.integers(3)) % 4)) for l in sites_b]
+        a0 = int(rng.integers(0, L - 200))
+        miss_b = ([a0, min(L - 50, a0 + 300)], [a0 + 120, min(L, a0 + 420)])
+        mm = np.zeros(L, bool)
+        for a, b in zip(*miss_b):
+            mm[a:b] = True
+        dl_b = [d for d in dl_b if not mm[d[0]]]
+        add(X, float(emat.t[X]), S, 0, dl_b, miss_b, bool(rng.integers(2)), float(lam[X]))
+    # (c) start regions in the middle of a branch, anywhere outside X's subtree
+    with_muts = [v for v in nodes if emat.mut_off[v + 1] - emat.mut_off[v] >= 2][:6]
+    for B in with_muts:
+        X = next(v for v in nodes if v != B and not _is_ancestor(emat, v, B) and int(emat.parent[v]) != emat.root)
+        k0 = int(rng.integers(1, emat.mut_off[B + 1] - emat.mut_off[B] + 1))
+        stB = _state_at_region(emat, sites, B, k0)
+        sites_c = rng.choice(L, size=3, replace=False)
+        dl_c = [(int(l), int(stB[l]), int((stB[l] + 1) % 4)) for l in sites_c]
+        add(X, float(emat.t[X]), B, k0, dl_c, ([], []), True, float(lam[X]))
+    # (d) a sequence that is not in the tree, seeded from the root region
+    nroot = int(emat.mut_off[emat.root + 1] - emat.mut_off[emat.root])
+    st_root = _state_at_region(emat, sites, emat.root, nroot)
+    dl_d = [(int(l), int(st_root[l]), int((st_root[l] + 2) % 4)) for l in rng.choice(L, size=4, replace=False)]
+    add(-1, info["t_max_tip"], emat.root, nroot, dl_d, ([10], [60]), True, 0.7)
+
+    batch = fo.spr_study_batch(reqs)
+    summ = batch.summaries()
+    for i, (want, ws) in enumerate(wants):
+        _cmp_regions(batch.regions(i), want)
+        if len(want):
+            assert summ[i].sum_W_over_Wmax == pytest.approx(ws.sum_W_over_Wmax, rel=1e-9)
+            assert summ[i].num_missing_at_X == ws.num_missing_at_X
+    # (a) again through the tree-derived mode
+    xs = nodes[:12]
+    b2 = fo.spr_study_batch(db.spr_requests_for_attached(emat, 0, xs, lam, info["t_max_tip"], limit, True))
+    for j in range(len(xs)):
+        _cmp_regions(b2.regions(j), batch.regions(2 * j), weights=True)
+    b2.close(); batch.close(); fo.close(); ds.close()
+
+
+def _is_ancestor(emat, a, v):
+    """True if a is v or an ancestor of v."""
+    while v >= 0:
+        if v == a:
+            return True
+        v = int(emat.parent[v])
+    return False
+
+
+def test_enumerate_then_weigh(ctx, orc):
+    """The reference's two steps as two calls: Spr_study_builder::seed_fill_from (lambda_X == 0: regions, zero weights), then the
+    Spr_study constructor (dphy_spr_batch_set_weights) -- also re-weighing with other parameters -- and log_alpha_in_region."""
+    import ctypes as C
+    from oracle_lib import OrcRegion
+    emat, sites, info = synth(1)
+    e, s = to_oracle(emat, sites)
+    ds = db.DeviceSites(ctx, sites); fo = db.Forest(ctx, [emat], [ds])
+    lam = fo.lambda_i(0)
+    xs = [int(v) for v in np.random.default_rng(3).permutation(emat.num_nodes) if v != emat.root][:10]
+    xs += [int(emat.child0[emat.root]), int(emat.child1[emat.root])]     # above-root regions with a real incomplete-gamma factor
+    reqs = db.spr_requests_for_attached(emat, 0, xs, np.zeros_like(lam), info["t_max_tip"])
+    batch = fo.spr_study_batch(reqs)
+    plain = [batch.regions(i) for i in range(len(xs))]
+    for i, X in enumerate(xs):
+        want, _ = orc.spr_study_from_attached(e, s, X, lam, INF, True, 0.8, info["t_max_tip"])
+        _cmp_regions(plain[i], want, weights=False)
+        assert not plain[i]["W_over_Wmax"].any() and not plain[i]["log_W_over_Wmax"].any()
+    with pytest.raises(db.DphyError):
+        batch.pick_nexus_regions(np.zeros(len(xs)))
+    for f, scale in ((0.8, 1.0), (0.6, 2.5)):
+        batch.set_weights([(float(lam[X]) * scale, f, info["t_max_tip"]) for X in xs])
+        summ = batch.summaries()
+        for i, X in enumerate(xs):
+            want, ws = orc.spr_study_from_attached(e, s, X, lam * scale, INF, True, f, info["t_max_tip"])
+            got = batch.region_weights(i, plain[i].copy())
+            _cmp_regions(got, want)
+            assert summ[i].sum_W_over_Wmax == pytest.approx(ws.sum_W_over_Wmax, rel=1e-9)
+            assert summ[i].log_Wmax == pytest.approx(ws.log_Wmax, rel=1e-9, abs=1e-9)
+            assert summ[i].mu == pytest.approx(ws.mu, rel=1e-12)
+            # log_alpha_in_region at a few regions (incl. the above-root one when there is one)
+            idxs = {0, len(want) // 2, len(want) - 1} | {int(k) for k in np.nonzero(want["t_min"] == -DBL_MAX)[0]}
+            for k in idxs:
+                r = want[k]
+                t = r["t_max"] - 0.37 * ((r["t_max"] - r["t_min"]) if r["t_min"] != -DBL_MAX else 0.05)
+                la_ref = orc.lib.orc_spr_log_alpha_in_region(C.byref(e.as_struct()), want.ctypes.data_as(C.POINTER(OrcRegion)), len(want), int(k),
+                                                             float(t), float(lam[X]) * scale, f, float(emat.t[X]), info["t_max_tip"],
+                                                             ws.sum_W_over_Wmax)
+                la = batch.log_alpha_in_region(i, int(k), float(t))
+                assert la == pytest.approx(la_ref, rel=1e-9, abs=1e-9), (X, k)
+    batch.close(); fo.close(); ds.close()
+
+
+def test_errors_are_sticky_and_name_the_request(ctx):
+    emat, sites, info = synth(0)
+    ds = db.DeviceSites(ctx, sites); fo = db.Forest(ctx, [emat], [ds])
+    lam = fo.lambda_i(0)
+    X = int(next(v for v in range(emat.num_nodes) if v != emat.root and emat.parent[v] != emat.root and emat.child0[v] >= 0))
+    good = db.spr_requests_for_attached(emat, 0, [X], lam, info["t_max_tip"])[0]
+    inside = int(emat.child0[X])                               # start region inside X's subtree
+    bad = db.spr_request(0, X, float(emat.t[X]), inside, 0, 0, float(lam[X]), info["t_max_tip"])
+    batch = fo.spr_study_batch([good, bad])
+    for call in (batch.summaries, batch.total_regions_checked, lambda: batch.regions(0), lambda: batch.pick_nexus_regions([0.1, 0.1]),
+                 lambda: batch.find_region(0, 1, 0.0), batch.summaries):
+        with pytest.raises(db.DphyError) as ei:
+            call()
+        assert "request 1" in str(ei.value)
+    batch.close(); fo.close(); ds.close()
