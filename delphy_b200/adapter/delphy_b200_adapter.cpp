@@ -2,6 +2,8 @@
 // See delphy_b200_adapter.h.  Nothing here computes: it flattens, calls include/delphy_b200.h, and re-shapes results.
 #include "delphy_b200_adapter.h"
 
+#include <atomic>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -12,7 +14,16 @@ namespace delphy::b200 {
 namespace {
 
 thread_local dphy_ctx* tl_ctx = nullptr;
-thread_local int tl_device = 0;
+thread_local int tl_device = -1;   // -1: not chosen yet
+
+// Host threads are spread round-robin over the first DPHY_DEVICES CUDA devices (default 1): with one Subrun per worker thread
+// (core/run.cpp:682-693) that places the partition parts on the GPUs of the box.
+auto next_device() -> int {
+  static std::atomic<int> counter{0};
+  const char* e = std::getenv("DPHY_DEVICES");
+  const int n = e != nullptr ? std::max(1, std::atoi(e)) : 1;
+  return counter.fetch_add(1) % n;
+}
 
 struct Ctx_reaper {   // destroys the thread's ctx at thread exit
   ~Ctx_reaper() { if (tl_ctx) { dphy_ctx_destroy(tl_ctx); tl_ctx = nullptr; } }
@@ -39,6 +50,7 @@ auto set_thread_device(int device) -> void { tl_device = device; }
 auto thread_ctx() -> dphy_ctx* {
   if (tl_ctx == nullptr) {
     (void)&tl_reaper;
+    if (tl_device < 0) { tl_device = next_device(); }
     auto st = dphy_ctx_create(tl_device, &tl_ctx);
     if (st != DPHY_OK) {
       tl_ctx = nullptr;

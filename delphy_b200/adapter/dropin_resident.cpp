@@ -1,0 +1,246 @@
+// dropin_resident.cpp -- see dropin_resident.h.
+#include "dropin_resident.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+
+#include "delphy_b200_adapter.h"   // thread_ctx()
+
+namespace delphy::b200 {
+
+auto throw_on_error(dphy_ctx* ctx, int status, const char* what) -> void {
+  if (status == DPHY_OK) { return; }
+  auto msg = std::string{what} + ": " + dphy_last_error(ctx);
+  switch (status) {
+    case DPHY_ERR_OUT_OF_RANGE: throw std::out_of_range(msg);
+    case DPHY_ERR_INVALID_ARGUMENT: throw std::invalid_argument(msg);
+    default: throw std::runtime_error(msg);
+  }
+}
+
+template <typename T>
+auto Pinned_array<T>::ensure(dphy_ctx* c, size_t n) -> T* {
+  if (n + 1 > capacity) {      // + 1: a non-null pointer even for empty lists
+    release();
+    ctx = c;
+    auto want = std::max<size_t>(n + 1, capacity + capacity / 2);
+    void* p = nullptr;
+    throw_on_error(c, dphy_host_alloc(c, want * sizeof(T), &p), "dphy_host_alloc");
+    data = static_cast<T*>(p);
+    capacity = want;
+  }
+  return data;
+}
+
+template <typename T>
+auto Pinned_array<T>::release() -> void {
+  if (data != nullptr) { dphy_host_free(ctx, data); data = nullptr; capacity = 0; }
+}
+
+template struct Pinned_array<int32_t>;
+template struct Pinned_array<uint8_t>;
+template struct Pinned_array<double>;
+
+auto Pinned_flat_emat::view(bool includes_run_root) const -> dphy_emat_host {
+  auto e = dphy_emat_host{};
+  e.num_nodes = num_nodes;
+  e.root = root;
+  e.includes_run_root = includes_run_root ? 1 : 0;
+  e.parent = parent.data; e.child0 = child0.data; e.child1 = child1.data; e.t = t.data;
+  e.mut_off = mut_off.data; e.mut_site = mut_site.data; e.mut_from = mut_from.data; e.mut_to = mut_to.data; e.mut_t = mut_t.data;
+  e.miss_off = miss_off.data; e.miss_start = miss_start.data; e.miss_end = miss_end.data;
+  e.fs_off = fs_off.data; e.fs_site = fs_site.data; e.fs_from = fs_from.data;
+  return e;
+}
+
+auto Pinned_flat_emat::release() -> void {
+  parent.release(); child0.release(); child1.release(); mut_off.release(); mut_site.release(); miss_off.release();
+  miss_start.release(); miss_end.release(); fs_off.release(); fs_site.release(); mut_from.release(); mut_to.release();
+  fs_from.release(); t.release(); mut_t.release();
+}
+
+namespace {
+
+// run fn(lo, hi) over [0, n) on up to `threads` host threads (the calling thread takes the first chunk)
+template <typename F>
+auto parallel_ranges(size_t n, int threads, F&& fn) -> void {
+  if (threads <= 1 || n < 16384) { fn(size_t{0}, n); return; }
+  const auto chunk = (n + threads - 1) / threads;
+  auto pool = std::vector<std::thread>{};
+  pool.reserve(threads - 1);
+  for (auto k = 1; k < threads; ++k) {
+    const auto lo = std::min(n, k * chunk), hi = std::min(n, lo + chunk);
+    if (lo < hi) { pool.emplace_back([&fn, lo, hi] { fn(lo, hi); }); }
+  }
+  fn(size_t{0}, std::min(n, chunk));
+  for (auto& th : pool) { th.join(); }
+}
+
+auto flatten_threads() -> int {
+  static const int n = [] {
+    const char* e = std::getenv("DPHY_FLATTEN_THREADS");
+    if (e != nullptr) { return std::max(1, std::atoi(e)); }
+    return static_cast<int>(std::clamp(std::thread::hardware_concurrency() / 2, 1u, 8u));
+  }();
+  return n;
+}
+
+}  // namespace
+
+auto flatten_into(dphy_ctx* ctx, const Phylo_tree& tree, Pinned_flat_emat& out) -> void {
+  const auto n = static_cast<size_t>(std::ssize(tree));
+  out.num_nodes = static_cast<int32_t>(n);
+  out.root = tree.root;
+  auto* parent = out.parent.ensure(ctx, n); auto* child0 = out.child0.ensure(ctx, n); auto* child1 = out.child1.ensure(ctx, n);
+  auto* t = out.t.ensure(ctx, n);
+  auto* mut_off = out.mut_off.ensure(ctx, n + 1); auto* miss_off = out.miss_off.ensure(ctx, n + 1); auto* fs_off = out.fs_off.ensure(ctx, n + 1);
+  const auto threads = flatten_threads();
+
+  // pass 1: node scalars + list sizes (written into the offset arrays, shifted by one)
+  mut_off[0] = 0; miss_off[0] = 0; fs_off[0] = 0;
+  parallel_ranges(n, threads, [&](size_t lo, size_t hi) {
+    for (auto v = lo; v != hi; ++v) {
+      const auto& node = tree.nodes[v];
+      parent[v] = node.parent;
+      if (node.is_tip()) { child0[v] = -1; child1[v] = -1; }
+      else { child0[v] = node.children[0]; child1[v] = node.children[1]; }
+      t[v] = node.t;
+      mut_off[v + 1] = static_cast<int32_t>(node.mutations.size());
+      miss_off[v + 1] = static_cast<int32_t>(node.missations.intervals.num_intervals());
+      fs_off[v + 1] = static_cast<int32_t>(node.missations.from_states.size());
+    }
+  });
+  for (auto v = size_t{0}; v != n; ++v) { mut_off[v + 1] += mut_off[v]; miss_off[v + 1] += miss_off[v]; fs_off[v + 1] += fs_off[v]; }
+  out.num_muts = mut_off[n]; out.num_ivls = miss_off[n]; out.num_fs = fs_off[n];
+
+  auto* mut_site = out.mut_site.ensure(ctx, out.num_muts); auto* mut_from = out.mut_from.ensure(ctx, out.num_muts);
+  auto* mut_to = out.mut_to.ensure(ctx, out.num_muts); auto* mut_t = out.mut_t.ensure(ctx, out.num_muts);
+  auto* miss_start = out.miss_start.ensure(ctx, out.num_ivls); auto* miss_end = out.miss_end.ensure(ctx, out.num_ivls);
+  auto* fs_site = out.fs_site.ensure(ctx, out.num_fs); auto* fs_from = out.fs_from.ensure(ctx, out.num_fs);
+
+  // pass 2: every thread copies the lists of its own node range to their final places
+  parallel_ranges(n, threads, [&](size_t lo, size_t hi) {
+    for (auto v = lo; v != hi; ++v) {
+      const auto& node = tree.nodes[v];
+      auto m = static_cast<size_t>(mut_off[v]);
+      for (const auto& mut : node.mutations) {
+        mut_site[m] = mut.site; mut_from[m] = static_cast<uint8_t>(mut.from); mut_to[m] = static_cast<uint8_t>(mut.to); mut_t[m] = mut.t;
+        ++m;
+      }
+      auto i = static_cast<size_t>(miss_off[v]);
+      for (const auto& [start, end] : node.missations.intervals) { miss_start[i] = start; miss_end[i] = end; ++i; }
+      auto f = static_cast<size_t>(fs_off[v]);
+      for (const auto& [site, from] : node.missations.from_states) { fs_site[f] = site; fs_from[f] = static_cast<uint8_t>(from); ++f; }
+    }
+  });
+}
+
+// ---- Resident ------------------------------------------------------------------------------------------------------------------------------------
+Resident::Resident() : ctx_{thread_ctx()} {}
+
+Resident::~Resident() {
+  // thread_local: runs before the adapter's ctx reaper (constructed earlier, by thread_ctx() above)
+  drop_forest();
+  if (sites_ != nullptr) { dphy_sites_destroy(ctx_, sites_); sites_ = nullptr; }
+  flat_.release();
+}
+
+auto Resident::get() -> Resident& {
+  thread_local Resident instance;
+  return instance;
+}
+
+auto Resident::drop_forest() -> void {
+  if (forest_ != nullptr) { dphy_forest_destroy(ctx_, forest_); forest_ = nullptr; }
+}
+
+auto Resident::sync_sites(const Real_sequence& seq, const Global_evo_model* evo) -> dphy_sites* {
+  const auto L = static_cast<size_t>(std::ssize(seq));
+  static_assert(sizeof(Real_seq_letter) == 1);
+  const auto* seq_bytes = reinterpret_cast<const uint8_t*>(seq.data());
+  const auto same_seq = sites_ != nullptr && ref_.size() == L && (L == 0 || std::memcmp(ref_.data(), seq_bytes, L) == 0);
+  if (evo == nullptr && same_seq) { return sites_; }
+
+  // the model the table should hold
+  auto P = size_t{1};
+  auto mu = std::vector<double>{}, pi = std::vector<double>{}, q = std::vector<double>{};
+  const int32_t* part = nullptr;
+  const double* nu = nullptr;
+  auto neutral_part = std::vector<int32_t>{};
+  auto neutral_nu = std::vector<double>{};
+  if (evo != nullptr) {
+    if (evo->partition_for_site.size() != L || evo->nu_l.size() != L) {
+      throw std::invalid_argument("delphy_b200: evo model and reference sequence disagree on the number of sites");
+    }
+    P = static_cast<size_t>(evo->num_partitions());
+    mu.resize(P); pi.resize(P * 4); q.resize(P * 16);
+    for (auto p = size_t{0}; p != P; ++p) {
+      const auto& model = evo->partition_evo_model[p];
+      mu[p] = model.mu;
+      for (auto a = 0; a != 4; ++a) {
+        pi[p * 4 + a] = model.pi_a[static_cast<Real_seq_letter>(a)];
+        for (auto b = 0; b != 4; ++b) { q[p * 16 + a * 4 + b] = model.q_ab[static_cast<Real_seq_letter>(a)][static_cast<Real_seq_letter>(b)]; }
+      }
+    }
+    static_assert(sizeof(Partition_index) == sizeof(int32_t));
+    part = reinterpret_cast<const int32_t*>(evo->partition_for_site.data());
+    nu = evo->nu_l.data();
+  } else {
+    // no model given and nothing usable resident: a neutral one (the caller reads only structure: counts, missing sites, regions)
+    mu = {1.0}; pi = {0.25, 0.25, 0.25, 0.25};
+    q.assign(16, 1.0 / 3.0);
+    for (auto a = 0; a != 4; ++a) { q[a * 4 + a] = -1.0; }
+    neutral_part.assign(L, 0); neutral_nu.assign(L, 1.0);
+    part = neutral_part.data(); nu = neutral_nu.data();
+  }
+
+  const auto same_structure = same_seq && mu_.size() == P && (L == 0 || std::memcmp(part_.data(), part, L * sizeof(int32_t)) == 0);
+  if (same_structure) {
+    const auto same_nu = L == 0 || std::memcmp(nu_.data(), nu, L * sizeof(double)) == 0;
+    const auto same_model = mu_ == mu && pi_ == pi && q_ == q;
+    if (same_nu && same_model) { return sites_; }
+    // Subrun::set_evo (core/subrun.h:29-30): same sequence, new parameters
+    throw_on_error(ctx_, dphy_sites_set_evo(ctx_, sites_, same_nu ? nullptr : nu, mu.data(), pi.data(), q.data()), "dphy_sites_set_evo");
+    if (!same_nu) { nu_.assign(nu, nu + L); }
+    mu_ = std::move(mu); pi_ = std::move(pi); q_ = std::move(q);
+    return sites_;
+  }
+
+  drop_forest();     // a forest refers to its sites table
+  if (sites_ != nullptr) { dphy_sites_destroy(ctx_, sites_); sites_ = nullptr; }
+  ref_.assign(seq_bytes, seq_bytes + L);
+  part_.assign(part, part + L);
+  nu_.assign(nu, nu + L);
+  mu_ = std::move(mu); pi_ = std::move(pi); q_ = std::move(q);
+  auto hs = dphy_sites_host{};
+  hs.num_sites = static_cast<int32_t>(L); hs.num_partitions = static_cast<int32_t>(P);
+  hs.ref = ref_.data(); hs.partition_for_site = part_.data(); hs.nu_l = nu_.data();
+  hs.mu = mu_.data(); hs.pi_a = pi_.data(); hs.q_ab = q_.data();
+  throw_on_error(ctx_, dphy_sites_upload(ctx_, &hs, &sites_), "dphy_sites_upload");
+  return sites_;
+}
+
+auto Resident::sync_tree(const Phylo_tree& tree, const Global_evo_model* evo) -> dphy_forest* {
+  using clock = std::chrono::steady_clock;
+  sync_sites(tree.ref_sequence, evo);
+  // the previous upload DMAs straight out of flat_: it must have landed before the buffers are rewritten
+  throw_on_error(ctx_, dphy_ctx_synchronize(ctx_), "dphy_ctx_synchronize");
+  const auto t0 = clock::now();
+  flatten_into(ctx_, tree, flat_);
+  const auto t1 = clock::now();
+  drop_forest();
+  auto he = flat_.view(true);     // both pieces of log G are computed; callers pick (Subrun::calc_cur_log_G, core/subrun.cpp:58-68)
+  auto zero = int32_t{0};
+  throw_on_error(ctx_, dphy_forest_upload(ctx_, 1, &he, &zero, 1, &sites_, &forest_), "dphy_forest_upload");
+  const auto t2 = clock::now();
+  ++uploads;
+  flatten_seconds += std::chrono::duration<double>(t1 - t0).count();
+  upload_seconds += std::chrono::duration<double>(t2 - t1).count();
+  return forest_;
+}
+
+}  // namespace delphy::b200
