@@ -15,6 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdelphy_b200.so")
+SYNTH_LIB_PATH = os.path.join(_HERE, "libdphy_synth.so")   # input generator only: no product code, no CUDA
 
 i32p = C.POINTER(C.c_int32)
 u8p = C.POINTER(C.c_uint8)
@@ -125,6 +126,23 @@ def build(force: bool = False) -> str:
 
 
 _LIB = None
+_SYNTH_LIB = None
+
+
+def synth_lib() -> C.CDLL:
+    """libdphy_synth.so: the synthetic-input generator (its own shared object, so that generating inputs loads no product code)."""
+    global _SYNTH_LIB
+    if _SYNTH_LIB is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise FileNotFoundError(f"{SYNTH_LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(SYNTH_LIB_PATH)
+        L.dphy_synth_default_params.argtypes = [C.POINTER(SynthParams), C.c_int32]
+        L.dphy_synth_default_params.restype = None
+        L.dphy_synth_generate.argtypes = [C.POINTER(SynthParams), C.POINTER(C.POINTER(SynthEmat))]
+        L.dphy_synth_free.argtypes = [C.POINTER(SynthEmat)]
+        L.dphy_synth_free.restype = None
+        _SYNTH_LIB = L
+    return _SYNTH_LIB
 
 
 def lib() -> C.CDLL:
@@ -175,6 +193,8 @@ def lib() -> C.CDLL:
     L.dphy_spr_batch_total_regions.argtypes = [vp, vp]; L.dphy_spr_batch_total_regions.restype = C.c_int64
     L.dphy_spr_batch_get_regions.argtypes = [vp, vp, C.c_int32, C.POINTER(CandidateRegion), C.c_int64]
     L.dphy_spr_batch_get_regions.restype = C.c_int64
+    L.dphy_sites_update.argtypes = [vp, vp, C.POINTER(SitesHost)]
+    L.dphy_forest_cycle_tallies_device.argtypes = [vp, vp, vp, C.c_int32]
     L.dphy_spr_batch_set_weights.argtypes = [vp, vp, C.POINTER(SprWeightParams)]
     L.dphy_spr_batch_get_region_weights.argtypes = [vp, vp, C.c_int32, C.POINTER(CandidateRegion), C.c_int64]
     L.dphy_spr_batch_get_region_weights.restype = C.c_int64
@@ -189,9 +209,8 @@ def lib() -> C.CDLL:
     L.dphy_partition_part.argtypes = [vp, C.c_int32]; L.dphy_partition_part.restype = C.POINTER(EmatHost)
     L.dphy_partition_orig_index.argtypes = [vp, C.c_int32]; L.dphy_partition_orig_index.restype = i32p
     L.dphy_partition_free.argtypes = [vp]
-    L.dphy_synth_default_params.argtypes = [C.POINTER(SynthParams), C.c_int32]
-    L.dphy_synth_generate.argtypes = [C.POINTER(SynthParams), C.POINTER(C.POINTER(SynthEmat))]
-    L.dphy_synth_free.argtypes = [C.POINTER(SynthEmat)]
+    L.dphy_partition_reassemble.argtypes = [vp, C.POINTER(EmatHost), C.c_int32, C.POINTER(EmatHost)]
+    L.dphy_partition_reassemble.restype = C.POINTER(EmatHost)
     _LIB = L
     return L
 
@@ -299,9 +318,50 @@ def partition_emat(emat: HostEmat, sites: HostSites, num_parts: int, seed: int =
         L.dphy_partition_free(h)
 
 
+class Partition:
+    """A tree cut into parts that can be edited independently and merged back (Run::repartition / Run::reassemble,
+    core/run.cpp:110-256).  parts[i] are HostEmat copies; origs[i] = orig_tree_index of every node of part i."""
+
+    def __init__(self, emat: HostEmat, sites: HostSites, num_parts: int = 0, seed: int = 1, cut_points=None):
+        L = lib()
+        self.emat = emat
+        es, ss = emat.as_struct(), sites.as_struct()
+        if cut_points is None:
+            cuts = np.zeros(max(num_parts, 1), np.int32)
+            ncut = C.c_int32(0)
+            st = L.dphy_partition_generate_stencil(C.byref(es), num_parts, seed, _p(cuts, i32p), C.byref(ncut))
+            if st != DPHY_OK:
+                raise DphyError(st, "dphy_partition_generate_stencil")
+            cut_points = cuts[:ncut.value].copy()
+        self.cut_points = np.ascontiguousarray(cut_points, np.int32)
+        self._h = C.c_void_p()
+        st = L.dphy_partition_split(C.byref(es), C.byref(ss), len(self.cut_points), _p(self.cut_points, i32p), C.byref(self._h))
+        if st != DPHY_OK:
+            raise DphyError(st, "dphy_partition_split")
+        self.parts, self.origs = [], []
+        for i in range(L.dphy_partition_num_parts(self._h)):
+            pe = L.dphy_partition_part(self._h, i).contents
+            self.parts.append(_emat_from_struct(pe))
+            self.origs.append(_np_from(L.dphy_partition_orig_index(self._h, i), pe.num_nodes, np.int32))
+
+    def reassemble(self, parts=None) -> HostEmat:
+        parts = self.parts if parts is None else parts
+        arr = (EmatHost * len(parts))(*[p.as_struct() for p in parts])
+        es = self.emat.as_struct()
+        r = lib().dphy_partition_reassemble(self._h, C.byref(es), len(parts), arr)
+        if not r:
+            raise DphyError(ERR_INVALID_ARGUMENT, "dphy_partition_reassemble: parts do not match the split")
+        return _emat_from_struct(r.contents)
+
+    def close(self):
+        if self._h:
+            lib().dphy_partition_free(self._h)
+            self._h = C.c_void_p()
+
+
 def synth_params(config: int = 0, **overrides) -> SynthParams:
     p = SynthParams()
-    lib().dphy_synth_default_params(C.byref(p), config)
+    synth_lib().dphy_synth_default_params(C.byref(p), config)
     for k, v in overrides.items():
         if k == "pi":
             for i in range(4):
@@ -313,7 +373,7 @@ def synth_params(config: int = 0, **overrides) -> SynthParams:
 
 def synth_generate(params: SynthParams):
     """Returns (HostEmat, HostSites, info dict) -- numpy copies of a synthetic EMAT."""
-    L = lib()
+    L = synth_lib()
     out = C.POINTER(SynthEmat)()
     st = L.dphy_synth_generate(C.byref(params), C.byref(out))
     if st != DPHY_OK:
@@ -429,7 +489,9 @@ class Context:
 class DeviceSites:
     def __init__(self, ctx: Context, sites: HostSites):
         self.ctx = ctx
-        self.host = sites
+        # a private mirror of what the device table holds: set_evo / update must not write through to the caller's object
+        self.host = HostSites(sites.ref.copy(), sites.partition_for_site.copy(), sites.nu_l.copy(), sites.mu.copy(),
+                              sites.pi_a.copy(), sites.q_ab.copy())
         self._h = C.c_void_p()
         ss = sites.as_struct()
         ctx.check(lib().dphy_sites_upload(ctx._h, C.byref(ss), C.byref(self._h)))
@@ -447,6 +509,13 @@ class DeviceSites:
         # nu_l is passed only when it changed: the cumulative-nu tables are then left alone
         self.ctx.check(lib().dphy_sites_set_evo(self.ctx._h, self._h, _p(h.nu_l, f64p) if nu_l is not None else None,
                                                 _p(h.mu, f64p), _p(h.pi_a, f64p), _p(h.q_ab, f64p)))
+
+    def update(self, sites: HostSites):
+        """New reference sequence / partitioning / model in place (same L and P): dphy_sites_update."""
+        hs = sites.as_struct()
+        self.ctx.check(lib().dphy_sites_update(self.ctx._h, self._h, C.byref(hs)))
+        self.host = HostSites(sites.ref.copy(), sites.partition_for_site.copy(), sites.nu_l.copy(), sites.mu.copy(),
+                              sites.pi_a.copy(), sites.q_ab.copy())
 
     def state_frequencies(self):
         out = np.zeros((self.host.num_partitions, 4), np.int32)
@@ -552,6 +621,11 @@ class Forest:
         self.ctx.check(lib().dphy_forest_calc_Ttwiddle_l(self.ctx._h, self._h, tree, _p(out_l, f64p),
                                                          _p(out_la, f64p) if want_T_l_a else None))
         return out_l, out_la
+
+    def cycle_tallies_device(self, device_ptr: int, cap: int):
+        """Packs the forest's additive per-cycle tallies into device memory at `device_ptr` (>= 19 + 4P doubles), asynchronously
+        on the ctx stream: [log_G, T, num_muts, num_muts_ab[16], Ttwiddle_beta_a[4P]] summed over the forest's trees."""
+        self.ctx.check(lib().dphy_forest_cycle_tallies_device(self.ctx._h, self._h, C.c_void_p(device_ptr), cap))
 
     def site_tallies(self):
         """(Ttwiddle_l, num_muts_l) of every tree in one call: two [num_trees, max L] arrays (rows padded with zeros)."""

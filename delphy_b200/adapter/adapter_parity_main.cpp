@@ -20,6 +20,7 @@
 #include "spr_study.h"
 
 #include "delphy_b200_adapter.h"
+#include "dphy_synth.h"
 
 using namespace delphy;
 

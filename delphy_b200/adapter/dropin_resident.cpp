@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -144,6 +146,11 @@ Resident::Resident() : ctx_{thread_ctx()} {}
 
 Resident::~Resident() {
   // thread_local: runs before the adapter's ctx reaper (constructed earlier, by thread_ctx() above)
+  if (const char* e = std::getenv("DPHY_DROPIN_STATS"); e != nullptr && std::atoi(e) != 0) {
+    std::fprintf(stderr, "[delphy_b200 drop-in] thread stats: %lld tree uploads (flatten %.3f s, upload+device flatten %.3f s), "
+                 "sites: %lld uploads, %lld set_evo, %lld reused (%.3f s)\n", (long long)uploads, flatten_seconds, upload_seconds,
+                 (long long)sites_uploads, (long long)set_evos, (long long)sites_reused, sites_seconds);
+  }
   drop_forest();
   if (sites_ != nullptr) { dphy_sites_destroy(ctx_, sites_); sites_ = nullptr; }
   flat_.release();
@@ -159,11 +166,15 @@ auto Resident::drop_forest() -> void {
 }
 
 auto Resident::sync_sites(const Real_sequence& seq, const Global_evo_model* evo) -> dphy_sites* {
+  struct Timer {
+    double& acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~Timer() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+  } timer{sites_seconds};
   const auto L = static_cast<size_t>(std::ssize(seq));
   static_assert(sizeof(Real_seq_letter) == 1);
   const auto* seq_bytes = reinterpret_cast<const uint8_t*>(seq.data());
   const auto same_seq = sites_ != nullptr && ref_.size() == L && (L == 0 || std::memcmp(ref_.data(), seq_bytes, L) == 0);
-  if (evo == nullptr && same_seq) { return sites_; }
+  if (evo == nullptr && same_seq) { ++sites_reused; return sites_; }
 
   // the model the table should hold
   auto P = size_t{1};
@@ -202,7 +213,8 @@ auto Resident::sync_sites(const Real_sequence& seq, const Global_evo_model* evo)
   if (same_structure) {
     const auto same_nu = L == 0 || std::memcmp(nu_.data(), nu, L * sizeof(double)) == 0;
     const auto same_model = mu_ == mu && pi_ == pi && q_ == q;
-    if (same_nu && same_model) { return sites_; }
+    if (same_nu && same_model) { ++sites_reused; return sites_; }
+    ++set_evos;
     // Subrun::set_evo (core/subrun.h:29-30): same sequence, new parameters
     throw_on_error(ctx_, dphy_sites_set_evo(ctx_, sites_, same_nu ? nullptr : nu, mu.data(), pi.data(), q.data()), "dphy_sites_set_evo");
     if (!same_nu) { nu_.assign(nu, nu + L); }
@@ -210,8 +222,9 @@ auto Resident::sync_sites(const Real_sequence& seq, const Global_evo_model* evo)
     return sites_;
   }
 
-  drop_forest();     // a forest refers to its sites table
-  if (sites_ != nullptr) { dphy_sites_destroy(ctx_, sites_); sites_ = nullptr; }
+  ++sites_uploads;
+  drop_forest();     // a forest refers to its sites table (and its folded weights to the reference sequence)
+  const auto same_shape = sites_ != nullptr && ref_.size() == L && mu_.size() == P;
   ref_.assign(seq_bytes, seq_bytes + L);
   part_.assign(part, part + L);
   nu_.assign(nu, nu + L);
@@ -220,6 +233,12 @@ auto Resident::sync_sites(const Real_sequence& seq, const Global_evo_model* evo)
   hs.num_sites = static_cast<int32_t>(L); hs.num_partitions = static_cast<int32_t>(P);
   hs.ref = ref_.data(); hs.partition_for_site = part_.data(); hs.nu_l = nu_.data();
   hs.mu = mu_.data(); hs.pi_a = pi_.data(); hs.q_ab = q_.data();
+  if (same_shape) {
+    // Run::normalize_root re-references the sequence every cycle (core/run.cpp:258-265): same table, new contents
+    throw_on_error(ctx_, dphy_sites_update(ctx_, sites_, &hs), "dphy_sites_update");
+    return sites_;
+  }
+  if (sites_ != nullptr) { dphy_sites_destroy(ctx_, sites_); sites_ = nullptr; }
   throw_on_error(ctx_, dphy_sites_upload(ctx_, &hs, &sites_), "dphy_sites_upload");
   return sites_;
 }

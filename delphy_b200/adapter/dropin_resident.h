@@ -62,8 +62,8 @@ class Resident {
   auto num_nodes() const -> int { return flat_.num_nodes; }
 
   // counters (bench / tests): how many trees were shipped and how long the host-side flatten took in total
-  int64_t uploads = 0;
-  double flatten_seconds = 0.0, upload_seconds = 0.0;
+  int64_t uploads = 0, sites_uploads = 0, set_evos = 0, sites_reused = 0;
+  double flatten_seconds = 0.0, upload_seconds = 0.0, sites_seconds = 0.0;
 
  private:
   Resident();

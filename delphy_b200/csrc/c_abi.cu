@@ -200,17 +200,65 @@ static void fill_tables(dphy_sites* s) {
   }
 }
 
-static int fill_evo(dphy_ctx* ctx, dphy_sites* s, const double* mu, const double* pi_a, const double* q_ab) {
+// Validate first, commit second: a rejected model must leave the host mirror untouched (no half-updated tables).
+static int validate_evo(dphy_ctx* ctx, int P, int L, const double* nu_l, const double* mu, const double* pi_a, const double* q_ab) {
+  for (int b = 0; b < P; ++b) {
+    if (!(mu[b] >= 0.0) || !std::isfinite(mu[b])) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "mu must be finite and >= 0");
+    for (int a = 0; a < 4; ++a) {
+      if (!(pi_a[b * 4 + a] >= 0.0) || !std::isfinite(pi_a[b * 4 + a])) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "pi_a must be finite and >= 0");
+      for (int c = 0; c < 4; ++c) {
+        const double q = q_ab[b * 16 + a * 4 + c];
+        if (!std::isfinite(q) || (a != c && q < 0.0) || (a == c && q > 0.0)) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "q_ab must be a finite rate matrix (off-diagonal >= 0, diagonal <= 0)");
+      }
+    }
+  }
+  if (nu_l) for (int l = 0; l < L; ++l) if (!(nu_l[l] >= 0.0) || !std::isfinite(nu_l[l])) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "nu_l must be finite and >= 0");
+  return DPHY_OK;
+}
+
+static void fill_evo(dphy_sites* s, const double* mu, const double* pi_a, const double* q_ab) {
   for (int b = 0; b < s->P; ++b) {
     s->h.mu[b] = mu[b];
-    if (!(mu[b] >= 0.0)) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "mu must be >= 0");
     for (int a = 0; a < 4; ++a) {
       s->h.pi[b * 4 + a] = pi_a[b * 4 + a];
       s->h.log_pi[b * 4 + a] = pi_a[b * 4 + a] != 0.0 ? std::log(pi_a[b * 4 + a]) : 0.0;
       for (int c = 0; c < 4; ++c) s->h.q[b * 16 + a * 4 + c] = q_ab[b * 16 + a * 4 + c];
     }
   }
+}
+
+static int validate_sequence(dphy_ctx* ctx, const dphy_sites_host* host) {
+  const int L = host->num_sites, P = host->num_partitions;
+  for (int l = 0; l < L; ++l) {
+    if (host->ref[l] > 3) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "ref_sequence holds a non-ACGT state");
+    if (host->partition_for_site[l] < 0 || host->partition_for_site[l] >= P)
+      return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "partition_for_site out of range");
+  }
   return DPHY_OK;
+}
+
+// stage ref / partition / nu through the pinned slab and re-derive every table (stream-ordered)
+static int upload_sequence_and_derive(dphy_ctx* ctx, dphy_sites* s, const dphy_sites_host* host) {
+  const int L = s->L;
+  const size_t off_part = (L + 255) / 256 * 256, off_nu = 2 * off_part, total = off_nu + sizeof(double) * (size_t)L;
+  void* hbv = nullptr;
+  int st = acquire_pinned(ctx, total, &hbv);
+  if (st != DPHY_OK) return st;
+  char* hb = static_cast<char*>(hbv);
+  std::memcpy(hb, host->ref, L);
+  uint8_t* hp = reinterpret_cast<uint8_t*>(hb + off_part);
+  for (int l = 0; l < L; ++l) hp[l] = (uint8_t)host->partition_for_site[l];
+  std::memcpy(hb + off_nu, host->nu_l, sizeof(double) * L);
+  set_nu_uniform(s, host->nu_l);
+  fill_tables(s);
+  cudaError_t e = cudaMemcpyAsync(s->d_ref, hb, L, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_part, hb + off_part, L, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_nu, hb + off_nu, sizeof(double) * L, cudaMemcpyHostToDevice, ctx->stream);
+  release_pinned_async(ctx);
+  if (e != cudaSuccess) return check_cuda(ctx, e, "H2D sites");
+  st = launch_sites_derive(ctx, s);
+  if (st == DPHY_OK) st = launch_sites_ref_counts(ctx, s);
+  return st;
 }
 
 int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** out) {
@@ -219,64 +267,62 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
   const int L = host->num_sites, P = host->num_partitions;
   if (L <= 0) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "num_sites must be > 0");
   if (P <= 0 || P > kMaxPartitions) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "num_partitions must be in [1,4]");
-  for (int l = 0; l < L; ++l) {
-    if (host->ref[l] > 3) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "ref_sequence holds a non-ACGT state");
-    if (host->partition_for_site[l] < 0 || host->partition_for_site[l] >= P)
-      return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "partition_for_site out of range");
-  }
+  int st = validate_sequence(ctx, host);
+  if (st == DPHY_OK) st = validate_evo(ctx, P, L, host->nu_l, host->mu, host->pi_a, host->q_ab);
+  if (st != DPHY_OK) return st;
   auto* s = new (std::nothrow) dphy_sites();
   if (!s) return DPHY_ERR_OUT_OF_MEMORY;
   s->L = L; s->P = P;
-  int st = fill_evo(ctx, s, host->mu, host->pi_a, host->q_ab);
-  if (st != DPHY_OK) { delete s; return st; }
+  fill_evo(s, host->mu, host->pi_a, host->q_ab);
   cudaSetDevice(ctx->device);
   Slab slab;
   const int b_ref = slab.reserve(L), b_part = slab.reserve(L), b_nu = slab.reserve(sizeof(double) * L);
-  const size_t upload_bytes = slab.total;
   const int b_munu = slab.reserve(sizeof(double) * L), b_cumQ = slab.reserve(sizeof(double) * (L + 1));
   const int b_freq = slab.reserve(sizeof(int32_t) * kMaxPartitions * 4);
   const int b_cnu = slab.reserve(sizeof(double) * (size_t)P * 4 * (L + 1));
   const int b_cref = slab.reserve(sizeof(int32_t) * (size_t)P * 4 * (L + 1));
   char* dbase = nullptr;
-  if (cudaMalloc((void**)&dbase, slab.total) != cudaSuccess) { delete s; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMalloc(sites)"); }
+  // stream-ordered pool allocation: no device-wide synchronization, and a freed table's block is reused by the next one
+  if (cudaMallocAsync((void**)&dbase, slab.total, ctx->stream) != cudaSuccess) { delete s; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(sites)"); }
   s->bytes = slab.total;
-  void* hbv = nullptr;
-  st = acquire_pinned(ctx, upload_bytes, &hbv);
-  if (st != DPHY_OK) { cudaFree(dbase); delete s; return st; }
-  char* hb = static_cast<char*>(hbv);
-  std::memcpy(slab.at<uint8_t>(hb, b_ref), host->ref, L);
-  uint8_t* hp = slab.at<uint8_t>(hb, b_part);
-  for (int l = 0; l < L; ++l) hp[l] = (uint8_t)host->partition_for_site[l];
-  std::memcpy(slab.at<double>(hb, b_nu), host->nu_l, sizeof(double) * L);
-  set_nu_uniform(s, host->nu_l);
-  fill_tables(s);
   s->d_ref = slab.at<uint8_t>(dbase, b_ref); s->d_part = slab.at<uint8_t>(dbase, b_part); s->d_nu = slab.at<double>(dbase, b_nu);
   s->d_munu = slab.at<double>(dbase, b_munu); s->d_cumQ = slab.at<double>(dbase, b_cumQ);
   s->d_ref_freq = slab.at<int32_t>(dbase, b_freq); s->d_cum_nu_ba = slab.at<double>(dbase, b_cnu);
   s->d_cref = slab.at<int32_t>(dbase, b_cref);
   s->h.L = L; s->h.P = P; s->h.ref = s->d_ref; s->h.part = s->d_part; s->h.nu = s->d_nu; s->h.munu = s->d_munu;
   s->h.cumQ = s->d_cumQ; s->h.ref_freq = s->d_ref_freq; s->h.cref = s->d_cref;
-  cudaError_t e = cudaMemcpyAsync(dbase, hb, upload_bytes, cudaMemcpyHostToDevice, ctx->stream);
-  if (e != cudaSuccess) { cudaFree(dbase); delete s; return check_cuda(ctx, e, "H2D sites"); }
-  release_pinned_async(ctx);
-  st = launch_sites_derive(ctx, s);
-  if (st == DPHY_OK) st = launch_sites_ref_counts(ctx, s);
-  if (st != DPHY_OK) { cudaStreamSynchronize(ctx->stream); cudaFree(dbase); delete s; return st; }
+  st = upload_sequence_and_derive(ctx, s, host);
+  if (st != DPHY_OK) { cudaFreeAsync(dbase, ctx->stream); delete s; return st; }
   *out = s;
   return DPHY_OK;
 }
 
+int dphy_sites_update(dphy_ctx* ctx, dphy_sites* s, const dphy_sites_host* host) {
+  if (!ctx || !s || !host) return DPHY_ERR_INVALID_ARGUMENT;
+  if (host->num_sites != s->L || host->num_partitions != s->P) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "sites update: number of sites / partitions differs from the table's");
+  int st = validate_sequence(ctx, host);
+  if (st == DPHY_OK) st = validate_evo(ctx, s->P, s->L, host->nu_l, host->mu, host->pi_a, host->q_ab);
+  if (st != DPHY_OK) return st;
+  cudaSetDevice(ctx->device);
+  fill_evo(s, host->mu, host->pi_a, host->q_ab);
+  s->version += 1;
+  return upload_sequence_and_derive(ctx, s, host);
+}
+
 void dphy_sites_destroy(dphy_ctx* ctx, dphy_sites* s) {
   if (!s) return;
-  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  if (s->d_ref) cudaFree(s->d_ref);   // base of the slab
+  if (s->d_ref) {   // base of the slab
+    if (ctx) { cudaSetDevice(ctx->device); cudaFreeAsync(s->d_ref, ctx->stream); }   // stream-ordered: after the last kernel that reads it
+    else cudaFree(s->d_ref);
+  }
   delete s;
 }
 
 int dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* s, const double* nu_l, const double* mu, const double* pi_a, const double* q_ab) {
   if (!ctx || !s || !mu || !pi_a || !q_ab) return DPHY_ERR_INVALID_ARGUMENT;
-  int st = fill_evo(ctx, s, mu, pi_a, q_ab);
+  int st = validate_evo(ctx, s->P, s->L, nu_l, mu, pi_a, q_ab);
   if (st != DPHY_OK) return st;
+  fill_evo(s, mu, pi_a, q_ab);
   if (nu_l) {
     void* hbv = nullptr;
     st = acquire_pinned(ctx, sizeof(double) * s->L, &hbv);

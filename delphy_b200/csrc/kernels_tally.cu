@@ -17,6 +17,7 @@
 #include "dphy_internal.h"
 #include "device_utils.cuh"
 
+#include <algorithm>
 #include <cstring>
 
 namespace dphy {
@@ -327,11 +328,70 @@ int tally_times(dphy_ctx* ctx, dphy_forest* fo, int tree, double* out_beta_a, do
   return st;
 }
 
+// Sum over the trees of a forest (fixed order) of the additive per-cycle quantities, packed as doubles for ONE all-reduce:
+//   out[0] = sum log_G, [1] = sum T, [2] = sum num_muts, [3..19) = sum num_muts_ab, [19 .. 19 + 4 maxP) = sum Ttwiddle_beta_a
+__global__ void pack_cycle_tallies_kernel(ForestDev f, const double* __restrict__ tree_out, const int32_t* __restrict__ tree_iout,
+                                          const double* __restrict__ beta_a /* [num_trees][16] */, int maxP4, double* __restrict__ out) {
+  const int k = threadIdx.x;
+  if (k >= 19 + maxP4) return;
+  double v = 0.0;
+  for (int t = 0; t < f.num_trees; ++t) {
+    if (k == 0) v += (f.trees[t].includes_run_root ? tree_out[t * 4 + 0] : 0.0) + tree_out[t * 4 + 1];
+    else if (k == 1) v += tree_out[t * 4 + 2];
+    else if (k == 2) v += (double)tree_iout[t * 20 + 0];
+    else if (k < 19) v += (double)tree_iout[t * 20 + 2 + (k - 3)];
+    else if (k - 19 < f.sites[f.trees[t].sites_id].P * 4) v += beta_a[t * 16 + (k - 19)];
+  }
+  out[k] = v;
+}
+
 }  // namespace dphy
 
 using namespace dphy;
 
 extern "C" {
+
+int dphy_forest_cycle_tallies_device(dphy_ctx* ctx, dphy_forest* fo, double* d_out, int32_t cap) {
+  if (!ctx || !fo || !d_out) return DPHY_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  int maxP = 1;
+  for (const dphy_sites* s : fo->sites) maxP = std::max(maxP, (int)s->P);
+  if (cap < 19 + 4 * maxP) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "cycle tallies: output shorter than 19 + 4 P doubles");
+  int st = refresh_sites(ctx, fo);
+  if (st != DPHY_OK) return st;
+  // log G under the current model + the structure-only counts (general schedule once per upload)
+  if (!fo->struct_valid) st = launch_log_G_general(ctx, fo);
+  else if (!fo->eval_current()) st = launch_log_G(ctx, fo);
+  if (st != DPHY_OK) return st;
+  fo->evaluated = true;
+  fo->eval_version.resize(fo->sites.size());
+  for (size_t i = 0; i < fo->sites.size(); ++i) fo->eval_version[i] = fo->sites[i]->version;
+  const size_t mark = ctx->arena.mark();
+  const int nt = fo->h.num_trees;
+  double* d_beta = (double*)ctx->arena.alloc(sizeof(double) * 16 * (size_t)std::max(nt, 1));
+  if (!d_beta) { ctx->arena.release(mark); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (cycle tallies)"); }
+  for (int k = 0; k < nt && st == DPHY_OK; ++k) {
+    const TreeDev& T = fo->trees[k];
+    const dphy_sites* s = fo->sites[T.sites_id];
+    double* PL = nullptr;
+    st = scan_branch_lengths(ctx, fo, k, &PL);
+    if (st != DPHY_OK) break;
+    TallyOut o{};
+    o.beta_a_part = (double*)ctx->arena.alloc(sizeof(double) * 16 * T.num_tiles);
+    if (!o.beta_a_part) { st = set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (cycle tallies)"); break; }
+    tally_events_kernel<true><<<T.num_tiles, kTile, 0, ctx->stream>>>(fo->h, k, PL, s->d_cum_nu_ba, o);
+    tally_beta_a_finalize_kernel<<<1, 32, 0, ctx->stream>>>(fo->h, k, PL, s->d_cum_nu_ba, o.beta_a_part, T.num_tiles, d_beta + 16 * (size_t)k);
+    ctx->launches += 2;
+  }
+  if (st == DPHY_OK) {
+    pack_cycle_tallies_kernel<<<1, 64, 0, ctx->stream>>>(fo->h, fo->d_tree_out, fo->d_tree_iout, d_beta, 4 * maxP, d_out);
+    ctx->launches += 1;
+    st = check_cuda(ctx, cudaGetLastError(), "cycle tallies kernels");
+  }
+  // stream-ordered: the arena scope is reused only by later work on the same stream
+  ctx->arena.release(mark);
+  return st;
+}
 
 int dphy_forest_calc_num_muts_beta_ab(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t* out) {
   if (!ctx || !fo || !out || tree < 0 || tree >= fo->h.num_trees) return DPHY_ERR_INVALID_ARGUMENT;

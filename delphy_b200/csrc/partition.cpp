@@ -34,52 +34,92 @@ struct PartOwner {
 struct dphy_partition {
   std::vector<PartOwner*> parts;
   std::vector<int32_t> part_of_node;   // original node -> part index (cut points belong to the part they root)
-  ~dphy_partition() { for (auto* p : parts) delete p; }
+  PartOwner* merged = nullptr;         // result of the last dphy_partition_reassemble
+  ~dphy_partition() { for (auto* p : parts) delete p; delete merged; }
 };
 
-extern "C" {
+// The reference draws its "bit of randomness" as std::bernoulli_distribution{0.5}(bitgen) with bitgen an absl::BitGenRef over the
+// run's std::mt19937 (core/run.h:20, core/tree.h:338, core/tree_partitioning.h:172).  Restated from the published pieces so that
+// the same seed yields the same cut points as the reference: MT19937 (Matsumoto & Nishimura 1998; 32-bit outputs); BitGenRef
+// composes a 64-bit value from two outputs, first one high (absl FastUniformBits, power-of-two range); libstdc++'s bernoulli
+// compares generate_canonical<double, 53> = double(u64) / 2^64 (conversion rounds to nearest) with p.
+namespace {
+struct Mt19937 {
+  uint32_t mt[624];
+  int idx = 624;
+  explicit Mt19937(uint32_t seed) {
+    mt[0] = seed;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+  }
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int i = 0; i < 624; ++i) {
+        const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+  }
+  bool bernoulli_half() {
+    const uint64_t hi = next(), lo = next();
+    const uint64_t u = (hi << 32) + lo;
+    return static_cast<double>(u) / 18446744073709551616.0 < 0.5;
+  }
+};
 
-int dphy_partition_generate_stencil(const dphy_emat_host* e, int32_t num_parts, uint64_t seed, int32_t* cut_points,
-                                    int32_t* num_cut_points) {
+// randomized_post_order_traversal (core/tree.h:320-365) as a pull iterator: the reference's generator is lazy, so its coin flips
+// interleave with the ones the stencil loop makes between two pulls
+struct RandomizedPostOrder {
+  const dphy_emat_host* e;
+  Mt19937* rng;
+  std::vector<std::pair<int32_t, int32_t>> stack;   // (node, children_so_far), -1 == not expanded yet
+  RandomizedPostOrder(const dphy_emat_host* e_, Mt19937* r) : e(e_), rng(r) { stack.push_back({e->root, -1}); }
+  // next node for which children_so_far == number of children, or -1 when the traversal is over
+  int32_t next() {
+    while (!stack.empty()) {
+      auto [node, so_far] = stack.back();
+      stack.pop_back();
+      const bool tip = e->child0[node] < 0;
+      const int nchild = tip ? 0 : 2;
+      if (so_far != -1) {
+        if (so_far == nchild) return node;
+        continue;
+      }
+      stack.push_back({node, nchild});
+      if (!tip) {
+        const int32_t c0 = e->child0[node], c1 = e->child1[node];
+        if (rng->bernoulli_half()) { stack.push_back({c0, -1}); stack.push_back({node, 1}); stack.push_back({c1, -1}); stack.push_back({node, 0}); }
+        else { stack.push_back({c1, -1}); stack.push_back({node, 1}); stack.push_back({c0, -1}); stack.push_back({node, 0}); }
+      }
+    }
+    return -1;
+  }
+};
+}  // namespace
+
+extern "C" int dphy_partition_generate_stencil(const dphy_emat_host* e, int32_t num_parts, uint64_t seed, int32_t* cut_points,
+                                               int32_t* num_cut_points) {
   if (!e || !cut_points || !num_cut_points || num_parts < 1) return DPHY_ERR_INVALID_ARGUMENT;
   const int n = e->num_nodes;
   *num_cut_points = 0;
-  if (num_parts == 1 || n < 3) return DPHY_OK;
-  // splitmix64 stream for the "bit of randomness" of the reference (child visiting order + 50% veto)
-  auto next = [&seed]() {
-    seed += 0x9E3779B97F4A7C15ULL;
-    uint64_t z = seed;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
-  };
-  // randomized post-order (core/tree.h:320-357)
-  std::vector<int32_t> post; post.reserve(n);
-  {
-    std::vector<int32_t> st{e->root};
-    std::vector<int32_t> pre; pre.reserve(n);
-    while (!st.empty()) {
-      int v = st.back(); st.pop_back(); pre.push_back(v);
-      if (e->child0[v] >= 0) {
-        if (next() & 1) { st.push_back(e->child0[v]); st.push_back(e->child1[v]); }
-        else { st.push_back(e->child1[v]); st.push_back(e->child0[v]); }
-      }
-    }
-    post.assign(pre.rbegin(), pre.rend());   // reverse pre-order visits children before parents
-  }
+  Mt19937 rng((uint32_t)seed);
+  RandomizedPostOrder order(e, &rng);
   std::vector<int32_t> desc(n, 0);
   long branches_left = n, parts_left = num_parts;
   int ncut = 0;
-  for (int v : post) {
-    if (v == e->root) break;
-    if (ncut == num_parts - 1) break;
+  for (int32_t v = order.next(); v >= 0; v = order.next()) {
+    if (v == e->root) break;                  // the root never goes explicitly into the stencil
+    if (ncut == num_parts - 1) break;         // the last part implicitly starts at the root
     desc[v] = 1;
     if (e->child0[v] >= 0) desc[v] += desc[e->child0[v]] + desc[e->child1[v]];
     const long min_size = std::max(10L, branches_left / (parts_left + 1));
     if (desc[v] >= min_size) {
       bool allowed = true;
-      if (branches_left - (desc[v] - 1) < min_size) allowed = false;
-      if (allowed && (next() & 1)) allowed = false;
+      if (branches_left - (desc[v] - 1) < min_size) allowed = false;       // the remaining stump would be too small
+      if (allowed && rng.bernoulli_half()) allowed = false;                  // "a bit of randomness"
       if (allowed) {
         branches_left -= desc[v] - 1;
         cut_points[ncut++] = v;
@@ -91,6 +131,8 @@ int dphy_partition_generate_stencil(const dphy_emat_host* e, int32_t num_parts, 
   *num_cut_points = ncut;
   return DPHY_OK;
 }
+
+extern "C" {
 
 int dphy_partition_split(const dphy_emat_host* e, const dphy_sites_host* s, int32_t num_cut_points, const int32_t* cut_points,
                          dphy_partition** out) {
@@ -112,18 +154,23 @@ int dphy_partition_split(const dphy_emat_host* e, const dphy_sites_host* s, int3
     auto* po = new PartOwner();
     P->parts.push_back(po);
     // ---- topology: DFS from the cut point, stopping at tips and at other cut points ------------------------------------
-    std::vector<std::pair<int32_t, int32_t>> st{{subroot, -1}};   // (orig node, parent dst)
+    // node numbering exactly as details::make_partition_part (core/tree_partitioning.h:88-135): the part root is 0; a node's two
+    // children get consecutive indices when the node is popped from the work stack (left pushed first, so right is popped first)
+    auto add_node = [&](int32_t pd) {
+      po->orig.push_back(-1); po->parent.push_back(pd); po->child0.push_back(-1); po->child1.push_back(-1); po->t.push_back(0.0);
+      return (int32_t)po->orig.size() - 1;
+    };
+    std::vector<std::pair<int32_t, int32_t>> st{{subroot, add_node(-1)}};   // (orig node, dst node)
     while (!st.empty()) {
-      auto [v, pd] = st.back(); st.pop_back();
-      const int d = (int)po->orig.size();
-      po->orig.push_back(v); po->parent.push_back(pd); po->child0.push_back(-1); po->child1.push_back(-1);
-      po->t.push_back(e->t[v]);
-      if (pd >= 0) { if (po->child0[pd] < 0) po->child0[pd] = d; else po->child1[pd] = d; }
+      auto [v, d] = st.back(); st.pop_back();
+      po->orig[d] = v; po->t[d] = e->t[v];
       P->part_of_node[v] = (int)pi;
       const bool frozen_tip = is_cut[v] && v != subroot;
       if (e->child0[v] >= 0 && !frozen_tip) {
-        st.push_back({e->child1[v], d});   // pushed first => visited second => becomes children[1]
-        st.push_back({e->child0[v], d});
+        const int32_t dl = add_node(d), dr = add_node(d);
+        po->child0[d] = dl; po->child1[d] = dr;
+        st.push_back({e->child0[v], dl});
+        st.push_back({e->child1[v], dr});
       }
     }
     const int pn = (int)po->orig.size();
@@ -194,5 +241,62 @@ const int32_t* dphy_partition_orig_index(const dphy_partition* p, int32_t i) {
   return (p && i >= 0 && i < (int32_t)p->parts.size()) ? p->parts[i]->orig.data() : nullptr;
 }
 void dphy_partition_free(dphy_partition* p) { delete p; }
+
+// reassemble_tree / Run::reassemble (core/tree_partitioning.cpp:55-83, core/run.cpp:195-256): transpose every part's node times,
+// lists and topology back onto the whole tree through orig_tree_index.  `parts` are the (possibly edited) parts in the order of
+// dphy_partition_part(p, i) -- same node counts as the split produced, any topology / lists / times.  The part that holds the
+// run root also sets the tree's root and the root's lists.  The result is a freshly built EMAT owned by `p`.
+const dphy_emat_host* dphy_partition_reassemble(dphy_partition* P, const dphy_emat_host* whole, int32_t num_parts, const dphy_emat_host* parts) {
+  if (!P || !whole || !parts || num_parts != (int32_t)P->parts.size()) return nullptr;
+  const int n = whole->num_nodes;
+  struct NodeLists { const dphy_emat_host* src; int32_t v; };
+  std::vector<int32_t> parent(whole->parent, whole->parent + n), child0(whole->child0, whole->child0 + n), child1(whole->child1, whole->child1 + n);
+  std::vector<double> t(whole->t, whole->t + n);
+  std::vector<NodeLists> lists(n);
+  for (int v = 0; v < n; ++v) lists[v] = {whole, v};
+  int32_t root = whole->root;
+  for (int32_t i = 0; i < num_parts; ++i) {
+    const dphy_emat_host& sub = parts[i];
+    const std::vector<int32_t>& orig = P->parts[i]->orig;
+    if (sub.num_nodes != (int32_t)orig.size()) return nullptr;
+    for (int32_t sv = 0; sv < sub.num_nodes; ++sv) {
+      const int32_t v = orig[sv];
+      t[v] = sub.t[sv];
+      if (sv != sub.root) lists[v] = {&sub, sv};
+      if (sub.child0[sv] >= 0) {     // inner node OF THE PART (cut points that are sub-tips keep their own children)
+        const int32_t l = orig[sub.child0[sv]], r = orig[sub.child1[sv]];
+        child0[v] = l; child1[v] = r; parent[l] = v; parent[r] = v;
+      }
+    }
+    if (sub.includes_run_root) {
+      root = orig[sub.root];
+      parent[root] = -1;
+      lists[root] = {&sub, sub.root};
+    }
+  }
+  auto* po = new PartOwner();
+  po->parent = std::move(parent); po->child0 = std::move(child0); po->child1 = std::move(child1); po->t = std::move(t);
+  po->mut_off.assign(n + 1, 0); po->miss_off.assign(n + 1, 0); po->fs_off.assign(n + 1, 0);
+  for (int v = 0; v < n; ++v) {
+    const dphy_emat_host& e = *lists[v].src; const int32_t u = lists[v].v;
+    for (int k = e.mut_off[u]; k < e.mut_off[u + 1]; ++k) {
+      po->mut_site.push_back(e.mut_site[k]); po->mut_from.push_back(e.mut_from[k]); po->mut_to.push_back(e.mut_to[k]); po->mut_t.push_back(e.mut_t[k]);
+    }
+    for (int k = e.miss_off[u]; k < e.miss_off[u + 1]; ++k) { po->miss_start.push_back(e.miss_start[k]); po->miss_end.push_back(e.miss_end[k]); }
+    for (int k = e.fs_off[u]; k < e.fs_off[u + 1]; ++k) { po->fs_site.push_back(e.fs_site[k]); po->fs_from.push_back(e.fs_from[k]); }
+    po->mut_off[v + 1] = (int32_t)po->mut_site.size(); po->miss_off[v + 1] = (int32_t)po->miss_start.size(); po->fs_off[v + 1] = (int32_t)po->fs_site.size();
+  }
+  auto nz = [](auto& x) { if (x.empty()) x.reserve(1); };
+  nz(po->mut_site); nz(po->mut_from); nz(po->mut_to); nz(po->mut_t); nz(po->miss_start); nz(po->miss_end); nz(po->fs_site); nz(po->fs_from);
+  auto& w = po->view;
+  w.num_nodes = n; w.root = root; w.includes_run_root = whole->includes_run_root; w.reserved = 0;
+  w.parent = po->parent.data(); w.child0 = po->child0.data(); w.child1 = po->child1.data(); w.t = po->t.data();
+  w.mut_off = po->mut_off.data(); w.mut_site = po->mut_site.data(); w.mut_from = po->mut_from.data(); w.mut_to = po->mut_to.data();
+  w.mut_t = po->mut_t.data(); w.miss_off = po->miss_off.data(); w.miss_start = po->miss_start.data(); w.miss_end = po->miss_end.data();
+  w.fs_off = po->fs_off.data(); w.fs_site = po->fs_site.data(); w.fs_from = po->fs_from.data();
+  delete P->merged;
+  P->merged = po;
+  return &po->view;
+}
 
 }  // extern "C"

@@ -7,7 +7,7 @@
 // where the state differs from the reference sequence).  Shapes/distributions follow SURVEY.md section 8(d):
 // coalescent tree under exponential growth with heterochronous tips, HKY mutations dropped as a Poisson process,
 // per-tip gap intervals (LogUniform lengths + 5'/3' end gaps) factored upward with interval algebra.
-#include "delphy_b200.h"
+#include "dphy_synth.h"
 
 #include <algorithm>
 #include <cfloat>

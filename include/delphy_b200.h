@@ -180,12 +180,19 @@ void dphy_host_free(dphy_ctx* ctx, void* p);
 int  dphy_ctx_set_log_G_path(dphy_ctx* ctx, int path);
 
 /* ---- sites / evo model ------------------------------------------------------------------------------- */
+/* Lifetime: a forest keeps pointers to the sites tables it was uploaded against; destroy the forests first.  Inputs are validated
+ * before anything is committed (ref in ACGT, partitions in range, mu / pi / nu finite and >= 0, q_ab a finite rate matrix). */
 int  dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** out);
 void dphy_sites_destroy(dphy_ctx* ctx, dphy_sites* sites);
 /* Subrun::set_evo (core/subrun.h:29-30): new mu/pi/q/nu_l; recomputes cum_Q_l on the device.  nu_l == NULL keeps the current site
  * rates (the cumulative-nu tables are then not rebuilt).  Asynchronous: consumers are ordered after it on the ctx's stream. */
 int  dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* sites, const double* nu_l, const double* mu,
                         const double* pi_a, const double* q_ab);
+/* Replace the reference sequence, the site partitioning and the whole model of an existing table in place (same number of sites
+ * and partitions): what Run::normalize_root -> rereference_to_root_sequence does to every subrun's tables once per cycle
+ * (core/run.cpp:258-265, core/phylo_tree.cpp:299-312).  No allocation; every derived table is rebuilt on the device.
+ * Forests uploaded against the old sequence keep their folded weights and must be re-uploaded. */
+int  dphy_sites_update(dphy_ctx* ctx, dphy_sites* sites, const dphy_sites_host* host);
 /* calc_state_frequencies_per_partition_of (core/phylo_tree_calc.cpp:95-106) -> out[P*4] */
 int  dphy_calc_state_frequencies_per_partition(dphy_ctx* ctx, dphy_sites* sites, int32_t* out);
 /* calc_cum_Q_l_for_sequence (core/phylo_tree_calc.cpp:379-388) -> out[L+1] */
@@ -245,6 +252,14 @@ int  dphy_forest_calc_Ttwiddle_l(dphy_ctx* ctx, dphy_forest* forest, int32_t tre
  * are enqueued back to back with one synchronization at the end. */
 int  dphy_forest_calc_site_tallies(dphy_ctx* ctx, dphy_forest* forest, int64_t ld, double* out_Ttwiddle_l, int32_t* out_num_muts_l);
 
+/* The quantities the reference sums over its subruns once per cycle (Run::check_global_and_local_totals_match and the inputs of
+ * the global moves, core/run.cpp:340-357,437-453), summed over the trees of this forest and packed as doubles in DEVICE memory
+ * so that ranks holding different partition parts combine them with ONE all-reduce (NCCL over NVLink):
+ *   d_out[0] = sum log_G   [1] = sum T   [2] = sum num_muts   [3..19) = sum num_muts_ab   [19 .. 19+4P) = sum Ttwiddle_beta_a
+ * cap >= 19 + 4 P (DPHY_CYCLE_TALLIES_LEN).  Asynchronous on the ctx stream; no host round trip. */
+#define DPHY_CYCLE_TALLIES_LEN(P) (19 + 4 * (P))
+int  dphy_forest_cycle_tallies_device(dphy_ctx* ctx, dphy_forest* forest, double* d_out, int32_t cap);
+
 /* ---- SPR regraft study -------------------------------------------------------------------------------- */
 /* Runs a batch of SPR studies (Spr_study_builder::seed_fill_from + Spr_study ctor) in one pass over the forest.
  * Regions of study i are emitted in the reference's DFS order (core/spr_study.cpp:26-128) at
@@ -283,7 +298,9 @@ int  dphy_gamma_q(dphy_ctx* ctx, int32_t n, const double* a, const double* x, do
 int  dphy_gamma_q_inv(dphy_ctx* ctx, int32_t n, const double* a, const double* q, double* out);
 
 /* ---- tree partitioning (one or more parts per GPU) ------------------------------------------------------------- */
-/* generate_random_partition_stencil (core/tree_partitioning.h:139-194): up to num_parts-1 cut points. */
+/* generate_random_partition_stencil (core/tree_partitioning.h:139-194): up to num_parts-1 cut points.  The coin flips are the
+ * reference's: std::bernoulli_distribution{0.5} drawn from std::mt19937{(uint32_t)seed} through absl::BitGenRef, interleaved with
+ * the lazy randomized post-order traversal (core/tree.h:320-365), so the same seed gives the reference's cut points. */
 typedef struct dphy_partition dphy_partition;
 int  dphy_partition_generate_stencil(const dphy_emat_host* tree, int32_t num_parts, uint64_t seed, int32_t* cut_points,
                                      int32_t* num_cut_points);
@@ -295,42 +312,13 @@ int32_t dphy_partition_num_parts(const dphy_partition* p);
 const dphy_emat_host* dphy_partition_part(const dphy_partition* p, int32_t i);
 /* orig_tree_index of every node of part i (core/tree_partitioning.h:20-34) */
 const int32_t* dphy_partition_orig_index(const dphy_partition* p, int32_t i);
+/* reassemble_tree / Run::reassemble (core/tree_partitioning.cpp:55-83, core/run.cpp:195-256): the whole tree with every part's
+ * times, lists and topology transposed back through orig_tree_index.  parts[i] corresponds to dphy_partition_part(p, i) (same
+ * node count; contents may have been edited by local moves).  The result is owned by `p` (valid until the next reassemble or
+ * dphy_partition_free); NULL on a shape mismatch. */
+const dphy_emat_host* dphy_partition_reassemble(dphy_partition* p, const dphy_emat_host* whole, int32_t num_parts,
+                                                const dphy_emat_host* parts);
 void dphy_partition_free(dphy_partition* p);
-
-/* ---- synthetic EMATs (bench / tests input generator) -------------------------------- */
-typedef struct dphy_synth_params {
-  int32_t num_tips;
-  int32_t num_sites;
-  uint64_t seed;
-  double  muts_per_tip;          /* target M / n (SURVEY: ~1.5) */
-  double  tip_date_span_years;   /* tips uniform over this span */
-  double  growth_rate;           /* exponential-growth coalescent g (1/yr) */
-  double  n0_years;              /* N(0) in years */
-  double  kappa;                 /* HKY transition/transversion ratio */
-  double  pi[4];                 /* stationary frequencies */
-  int32_t site_rate_heterogeneity; /* 0: nu_l == 1;  1: nu_l ~ Gamma(alpha, alpha) */
-  double  gamma_alpha;
-  int32_t num_partitions;        /* 1, or 2 (mpox-hack-like split, core/run.cpp:359-435) */
-  double  missing_mean_intervals_per_tip;   /* Geometric mean; 0 disables missing data */
-  double  missing_len_min, missing_len_max; /* LogUniform interval length */
-  int32_t end_gaps;              /* add 5'/3' end gaps */
-  int32_t num_root_mutations;    /* root "mutations" at t=-DBL_MAX (as partition parts have, core/run.cpp:148-154) */
-  int32_t caterpillar;           /* 1: ladder topology (the reference's random initial tree, core/phylo_tree.cpp) */
-} dphy_synth_params;
-
-typedef struct dphy_synth_emat {     /* owns its arrays; free with dphy_synth_free */
-  dphy_emat_host emat;
-  dphy_sites_host sites;
-  double mu_used;
-  double t_max_tip;
-  int64_t num_mutations, num_intervals, num_from_states, num_missing_sites;
-  int32_t max_depth;
-  void* owner_;
-} dphy_synth_emat;
-
-void dphy_synth_default_params(dphy_synth_params* p, int32_t config /* 1..5 == BASELINE.json configs[0..4] */);
-int  dphy_synth_generate(const dphy_synth_params* p, dphy_synth_emat** out);
-void dphy_synth_free(dphy_synth_emat* s);
 
 const char* dphy_version(void);
 

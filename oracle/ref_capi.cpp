@@ -16,6 +16,8 @@
 #include "spr_study.h"
 #include "site_deltas.h"
 #include "evo_model.h"
+#include "tree_partitioning.h"
+#include <random>
 
 #include "emat_oracle.h"
 
@@ -324,6 +326,39 @@ double ref_bench_spr(const orc_emat* e, const orc_sites* s, const int32_t* xs, i
   for (auto c : counts) { total += c; }
   if (out_regions) { *out_regions = total; }
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- tree partitioning: the reference's own stencil and parts (core/tree_partitioning.h:139-239) ------------------------------
+// generate_random_partition_stencil with bitgen = std::mt19937{seed}, the generator type Run holds (core/run.h:20).
+int32_t ref_partition_stencil(const orc_emat* e, const orc_sites* s, int32_t num_parts, uint32_t seed, int32_t* out_cuts, int32_t cap) {
+  auto scope = Local_arena_scope{};
+  auto tree = make_tree(e, s);
+  auto bitgen = std::mt19937{seed};
+  auto stencil = generate_random_partition_stencil(tree, num_parts, bitgen);
+  if ((int32_t)stencil.size() > cap) return -1;
+  for (auto i = 0; i != std::ssize(stencil); ++i) out_cuts[i] = stencil[i].cut_point;
+  return (int32_t)stencil.size();
+}
+
+// partition_tree: topology + orig_tree_index of part `part_index`; returns its node count (-1 if cap is too small)
+int32_t ref_partition_part(const orc_emat* e, const orc_sites* s, const int32_t* cuts, int32_t n_cuts, int32_t part_index,
+                           int32_t* orig, int32_t* parent, int32_t* child0, int32_t* child1, int32_t cap, int32_t* root_part_index) {
+  auto scope = Local_arena_scope{};
+  auto tree = make_tree(e, s);
+  auto stencil = std::vector<Partition_part_info>{};
+  for (auto i = 0; i != n_cuts; ++i) stencil.push_back({cuts[i]});
+  auto partition = partition_tree(tree, stencil);
+  if (root_part_index) *root_part_index = partition.root_part_index();
+  if (part_index < 0 || part_index >= std::ssize(partition.parts())) return -2;
+  const auto& part = partition.parts()[part_index];
+  if (std::ssize(part) > cap) return -1;
+  for (auto v = 0; v != std::ssize(part); ++v) {
+    orig[v] = part.at(v).orig_tree_index();
+    parent[v] = part.at(v).parent;
+    if (part.at(v).is_tip()) { child0[v] = -1; child1[v] = -1; }
+    else { child0[v] = part.at(v).children[0]; child1[v] = part.at(v).children[1]; }
+  }
+  return (int32_t)std::ssize(part);
 }
 
 }  // extern "C"

@@ -12,8 +12,8 @@ import delphy_b200 as db
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "delphy_b200.h")).read()
+def _declared_symbols(header="delphy_b200.h"):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(dphy_[a-zA-Z0-9_]+)\s*\(", hdr)))
 
@@ -25,6 +25,17 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/delphy_b200.h but not exported"
     assert db.lib().dphy_version().decode().startswith("delphy_b200")
+
+
+def test_input_generator_is_a_separate_library():
+    """include/dphy_synth.h -> libdphy_synth.so: the product library exports none of it, and the generator links no CUDA."""
+    synth = C.CDLL(db.SYNTH_LIB_PATH)
+    names = _declared_symbols("dphy_synth.h")
+    assert names == ["dphy_synth_default_params", "dphy_synth_free", "dphy_synth_generate"]
+    prod = C.CDLL(db.LIB_PATH)
+    for n in names:
+        assert hasattr(synth, n)
+        assert not hasattr(prod, n)
 
 
 def test_no_cpu_fallback():
