@@ -1,21 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- EMAT log-lik evals/s + SPR candidates scored/s on B200 (BASELINE.json metric).
+"""bench.py -- EMAT log-lik evals/s + SPR candidates scored/s + MCMC steps/s on B200 (BASELINE.json metric).
 
-One "step" = one log-G evaluation (calc_lambda_i + calc_log_root_prior + calc_log_G_below_root)
-of every EMAT of a forest of `--chains` independent synthetic 100k-tip x 29,903-site EMATs (BASELINE.json configs[3]
-shape; the forest is larger than the 126 MB L2 so the timed kernels stream from HBM).  K steps are enqueued back to
-back between two CUDA events.  The metric's second figure -- SPR candidates scored/s -- is timed the same way right
-after (K batches of `--spr-studies` full, unbounded regraft studies), and so is the general log-G schedule.
+Workload at N = 1: a forest of `--chains` independent synthetic 100k-tip x 29,903-site EMATs (BASELINE.json configs[3] shape,
+the shape the target is quoted on; 16 chains so that the forest exceeds the 126 MB L2 and the timed kernels stream from HBM).
+One "step" = `--evals-per-step` log-G evaluations (calc_lambda_i + calc_log_root_prior + calc_log_G_below_root, SURVEY.md
+section 8d) of every EMAT of the forest; K steps are enqueued back to back between two CUDA events on the launching stream.
 
   value               = log-lik evals/s, inputs resident in HBM (whole job, all ranks)
-  spr_*               = SPR candidate regions scored/s
-  model_change_cycle  = evals/s when every evaluation follows a model change (set_evo on every table + eval + read-back)
-  e2e                 = the same log-lik metric through the C ABI with HOST buffers (upload + eval + download per step)
-  roofline            = algorithmic bytes of the log-G evaluation / its CUDA-event duration vs the measured HBM peak
+  roofline            = algorithmic bytes of one evaluation / its CUDA-event duration vs the measured HBM peak
+                        (+ achieved_dram_frac: the DRAM bytes ncu measured for the same launch, same duration)
+  spr_candidates_per_s, roofline_spr   = full SPR regraft studies (the metric's second figure), timed the same way
+  loglik_general_schedule              = the per-event schedule (the one site-rate heterogeneity needs)
+  configs             = the same two figures for BASELINE.json configs[1], [2], [4] (parity-test shapes; secondary)
+  model_change_cycle  = evals/s when every evaluation follows a model change (set_evo + eval + read-back)
+  partitioned         = ONE 100k-tip tree cut into parts spread over the ranks: per cycle new mu -> every part re-evaluated ->
+                        packed tallies -> ONE NCCL all-reduce (strong scaling)
+  e2e                 = the log-lik metric through the C ABI with HOST buffers (upload + eval + download per step)
+  mcmc                = MCMC steps/s of the reference's own CLI with the hot path substituted at link time
+                        (delphy_b200/adapter/_build/delphy_b200_cli); `--impl reference` runs the stock build of the same sources
   cpu_baseline        = the reference's own CPU code (oracle/_ref, compiled from /root/reference) on the box's host cores
 
-Multi-GPU (torchrun): each rank owns its own forest of chains (weak scaling; the path shards over independent
-EMATs with no data-path collective -- SURVEY.md section 8e); NCCL is used for the barrier and the max-over-ranks time.
+`--impl reference` times the reference's CPU implementation (oracle/_ref) on the same workload and prints the same keys; it
+loads no product code (inputs come from libdphy_synth.so).
+
+Multi-GPU (torchrun): the headline shards independent EMATs over ranks with no data-path collective (weak scaling); the
+`partitioned` section is the one place with a real exchange.
 """
 from __future__ import annotations
 
@@ -32,29 +41,43 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "EMAT log-lik evals/s (+ spr_candidates_per_s)"
+METRIC = "EMAT log-lik evals/s (+ spr_candidates_per_s, mcmc steps/s)"
 UNIT = "evals/s"
+SHAPES = {1: "200-tip x 29,903-site", 2: "1,600-tip x 18,959-site (nu_l on, missations)", 3: "10k-tip x 29,903-site",
+          4: "100k-tip x 29,903-site", 5: "50k-tip x 197,000-site (heavy missing, 2 partitions)"}
+SECONDARY = {2: 256, 3: 64, 5: 8}        # config -> chains per GPU (forest > L2 where the shape allows it)
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=4, help="synthetic shape: 1..5 == BASELINE.json configs[0..4]")
     ap.add_argument("--chains", type=int, default=16, help="independent EMATs per GPU (forest must exceed L2)")
-    ap.add_argument("--spr-studies", type=int, default=128, help="full SPR studies per step (0 disables)")
+    ap.add_argument("--evals-per-step", type=int, default=32, help="log-G evaluations of the whole forest per step (timed region >= 50 ms)")
+    ap.add_argument("--spr-studies", type=int, default=128, help="full SPR studies per batch (0 disables)")
+    ap.add_argument("--spr-batches-per-step", type=int, default=4)
     ap.add_argument("--e2e-chains", type=int, default=16)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline budget per figure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs 2/3/5 figures")
+    ap.add_argument("--no-partitioned", action="store_true")
+    ap.add_argument("--no-mcmc", action="store_true")
+    ap.add_argument("--parts-per-gpu", type=int, default=2)
+    ap.add_argument("--mcmc-tips", type=int, default=10000, help="tips of the second MCMC alignment (config 3 shape)")
+    ap.add_argument("--mcmc-steps", type=int, default=200000)
+    ap.add_argument("--mcmc-threads-per-gpu", type=int, default=2)
     return ap.parse_args()
 
 
-def workload_name(cfg, chains):
-    shapes = {1: "200-tip x 29,903-site", 2: "1,600-tip x 18,959-site (nu_l on)", 3: "10k-tip x 29,903-site",
-              4: "100k-tip x 29,903-site", 5: "50k-tip x 197,000-site (heavy missing)"}
-    return f"synthetic {shapes.get(cfg, 'small')} EMAT x {chains} independent chains per GPU"
+def config_block(args):
+    """Identical for both arms: names the workload, nothing implementation specific."""
+    return {"workload": f"synthetic {SHAPES.get(args.config, 'small')} EMAT x {args.chains} independent chains per GPU",
+            "chains_per_gpu": args.chains, "evals_per_step": args.evals_per_step,
+            "step": f"{args.evals_per_step} log-G evaluations (lambda_i + root prior + log G below root) of every EMAT of the forest",
+            "spr_studies_per_batch": args.spr_studies, "l2": "inputs larger than L2 (forest > 126 MB)"}
 
 
 def measured_peak():
@@ -71,12 +94,13 @@ def measured_traffic(kernel, cfg, chains):
     """DRAM bytes (read + write) per launch of `kernel` from the committed ncu --set full capture of this workload
     (profiles/traffic.json), or None when no capture matches."""
     try:
+        best = None
         for row in json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))):
             if row["kernel"] == kernel and row["config"] == cfg and row["chains"] == chains:
-                return row["dram_bytes_per_launch"]
+                best = row["dram_bytes_per_launch"]
+        return best
     except Exception:
-        pass
-    return None
+        return None
 
 
 class ClockSampler:
@@ -91,7 +115,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -105,7 +129,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -135,55 +159,114 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_baseline_run(emat, sites, budget_s, threads, t_max_tip, spr_xs=None):
-    """Times the reference's own CPU functions (oracle/_ref) -- or the oracle port if _ref is absent -- on a bounded
-    sample of the same workload.  bench.py is one of the three places allowed to execute oracle/."""
+# ---- the reference's own CPU code (oracle/_ref), or the oracle port when it is absent ------------------------------------------
+def _oracle_modules():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import ctypes as C
     import oracle_lib as ol
     from helpers import to_oracle
+    return ol, to_oracle
+
+
+def cpu_log_G(emat, sites, budget_s, threads):
+    """calc_lambda_i + calc_log_root_prior + calc_log_G_below_root on `threads` replicas of one tree, one per thread."""
+    import ctypes as C
+    ol, to_oracle = _oracle_modules()
     e, s = to_oracle(emat, sites)
     es, ss = e.as_struct(), s.as_struct()
-    out = {}
-    if ol.ref_available():
-        lib = ol.ref()
-        kind = "reference"
-        lg = C.c_double()
-        t1 = lib.ref_bench_log_G(C.byref(es), C.byref(ss), 2, threads, C.byref(lg))      # calibration
-        per = max(t1 / 2, 1e-6)
-        reps = max(2, int(budget_s / per))
-        t = lib.ref_bench_log_G(C.byref(es), C.byref(ss), reps, threads, C.byref(lg))
-        out.update(value=threads * reps / t, unit=UNIT, cores=threads, kind=kind, log_G=lg.value,
-                   sample=f"{reps} evals/thread x {threads} threads of one {emat.num_nodes}-node EMAT "
-                          f"(calc_lambda_i + calc_log_root_prior + calc_log_G_below_root), {t:.1f} s")
-        if spr_xs is not None and len(spr_xs):
-            xs = np.ascontiguousarray(spr_xs, np.int32)
-            nreg = C.c_int64()
-            t0 = lib.ref_bench_spr(C.byref(es), C.byref(ss), xs.ctypes.data_as(ol.i32p), min(len(xs), threads), threads, 0.8,
-                                   t_max_tip, C.byref(nreg))
-            per_x = max(t0 / max(1, min(len(xs), threads)) * threads, 1e-6) / threads
-            n_x = int(max(threads, min(len(xs), budget_s / max(per_x, 1e-9) * 1.0)))
-            n_x = min(n_x, len(xs))
-            t = lib.ref_bench_spr(C.byref(es), C.byref(ss), xs.ctypes.data_as(ol.i32p), n_x, threads, 0.8, t_max_tip, C.byref(nreg))
-            out["spr"] = dict(value=nreg.value / t, unit="candidates/s", cores=threads, kind=kind,
-                              sample=f"{n_x} full SPR studies (reconstruct_missing_sites_at + seed_fill_from + Spr_study), "
-                                     f"{nreg.value} regions, {t:.1f} s")
-    else:
+    if not ol.ref_available():
         o = ol.Oracle("oracle")
-        kind = "port"
         cq = o.cum_Q_l(s)
         t0 = time.perf_counter(); n = 0
         while time.perf_counter() - t0 < budget_s or n < 2:
             lam = o.lambda_i(e, s, cq); o.log_root_prior(e, s); o.log_G_below_root(e, s, lam); n += 1
         t = time.perf_counter() - t0
-        out.update(value=n / t, unit=UNIT, cores=1, kind=kind, sample=f"{n} evals of one {emat.num_nodes}-node EMAT, 1 thread, {t:.1f} s")
-    return out
+        return dict(value=n / t, unit=UNIT, cores=1, kind="port", seconds=t, sample=f"{n} evals of one {emat.num_nodes}-node EMAT, 1 thread, {t:.1f} s")
+    lib = ol.ref()
+    lg = C.c_double()
+    t1 = lib.ref_bench_log_G(C.byref(es), C.byref(ss), 2, threads, C.byref(lg))      # calibration
+    reps = max(2, int(budget_s / max(t1 / 2, 1e-6)))
+    t = lib.ref_bench_log_G(C.byref(es), C.byref(ss), reps, threads, C.byref(lg))
+    return dict(value=threads * reps / t, unit=UNIT, cores=threads, kind="reference", log_G=lg.value, seconds=t,
+                sample=f"{reps} evals/thread x {threads} threads of one {emat.num_nodes}-node EMAT "
+                       f"(calc_lambda_i + calc_log_root_prior + calc_log_G_below_root), {t:.1f} s")
+
+
+def cpu_log_G_partitioned(db, emat, sites, budget_s, threads):
+    """The reference's own multithreaded scheme (core/run.cpp:682-693): the tree cut into `threads` parts, one per worker thread."""
+    import ctypes as C
+    ol, to_oracle = _oracle_modules()
+    if not ol.ref_available():
+        return None
+    lib = ol.ref()
+    part = db.Partition(emat, sites, threads, seed=20251017, host_only=True)
+    pes = [to_oracle(p, sites)[0] for p in part.parts]
+    _, s = to_oracle(emat, sites)
+    structs = [pe.as_struct() for pe in pes]
+    arr = (C.POINTER(type(structs[0])) * len(structs))(*[C.pointer(x) for x in structs])
+    ss = s.as_struct()
+    lib.ref_bench_log_G_parts.restype = C.c_double
+    lg = C.c_double()
+    t1 = lib.ref_bench_log_G_parts(arr, len(structs), C.byref(ss), 2, C.byref(lg))
+    reps = max(2, int(budget_s / max(t1 / 2, 1e-6)))
+    t = lib.ref_bench_log_G_parts(arr, len(structs), C.byref(ss), reps, C.byref(lg))
+    n_parts = len(structs)
+    part.close()
+    return dict(value=reps / t, unit="whole-tree evals/s", cores=n_parts, kind="reference", log_G=lg.value, seconds=t,
+                sample=f"one {emat.num_nodes}-node EMAT cut into {n_parts} parts (generate_random_partition_stencil), one part per thread, "
+                       f"{reps} evaluations of every part, {t:.1f} s")
+
+
+def cpu_spr(emat, sites, xs, budget_s, threads, t_max_tip):
+    import ctypes as C
+    ol, to_oracle = _oracle_modules()
+    if not ol.ref_available() or xs is None or len(xs) == 0:
+        return None
+    lib = ol.ref()
+    e, s = to_oracle(emat, sites)
+    es, ss = e.as_struct(), s.as_struct()
+    xs = np.ascontiguousarray(xs, np.int32)
+    nreg = C.c_int64()
+    n0 = min(len(xs), threads)
+    t0 = lib.ref_bench_spr(C.byref(es), C.byref(ss), xs.ctypes.data_as(ol.i32p), n0, threads, 0.8, t_max_tip, C.byref(nreg))
+    n_x = int(min(len(xs), max(threads, budget_s / max(t0, 1e-9) * n0)))
+    t = lib.ref_bench_spr(C.byref(es), C.byref(ss), xs.ctypes.data_as(ol.i32p), n_x, threads, 0.8, t_max_tip, C.byref(nreg))
+    return dict(value=nreg.value / t, unit="candidates/s", cores=threads, kind="reference", seconds=t,
+                sample=f"{n_x} full SPR studies (reconstruct_missing_sites_at + seed_fill_from + Spr_study), {nreg.value} regions, {t:.1f} s")
 
 
 def pick_spr_nodes(emat, n, seed=1234):
     rng = np.random.default_rng(seed)
     cand = np.array([v for v in rng.permutation(emat.num_nodes)[: 8 * n + 8] if v != emat.root and emat.parent[v] != emat.root], np.int32)
     return cand[:n]
+
+
+# ---- MCMC through the reference's own CLI (stock build or link-time drop-in) ------------------------------------------------------
+def mcmc_figures(db, args, which, n_gpus):
+    """steps/s of the reference's CLI on two synthetic alignments: configs[0] (200 tips, 1 M steps -- the reference's own
+    CPU-runnable case) and a config-3-shaped one (`--mcmc-tips` tips).  `which`: "dropin" | "stock"."""
+    from delphy_b200 import mcmc
+    from delphy_b200.maple import write_maple
+    binary = mcmc.DROPIN_CLI if which == "dropin" else mcmc.STOCK_CLI
+    if not os.path.exists(binary):
+        return {"unavailable": f"{os.path.relpath(binary, ROOT)} not built (needs the reference checkout at build time)"}
+    tmp = os.path.join("/tmp", f"dphy_bench_{os.getpid()}")
+    os.makedirs(tmp, exist_ok=True)
+    threads = max(1, args.mcmc_threads_per_gpu * n_gpus)
+    out = {"binary": os.path.relpath(binary, ROOT), "host_threads": threads, "n_gpus": n_gpus if which == "dropin" else 0}
+    cases = [("cfg1_200_tips", db.synth_params(1), 1000000), (f"cfg3_{args.mcmc_tips}_tips", db.synth_params(3, num_tips=args.mcmc_tips), args.mcmc_steps)]
+    for name, params, steps in cases:
+        emat, sites, info = db.synth_generate(params)
+        path = os.path.join(tmp, name + ".maple")
+        write_maple(emat, sites, path, info["t_max_tip"])
+        r = mcmc.run_cli(binary, path, steps, threads=threads, seed=20251017, log_every=max(1, steps // 10),
+                         env={"DPHY_DEVICES": n_gpus, "DPHY_DROPIN_STATS": 1}, timeout=900)
+        last = r["samples"][-1] if r["samples"] else {}
+        out[name] = {"steps_per_s": r["steps_per_s"], "steps": steps, "mcmc_seconds": r["mcmc_s"], "init_seconds": r["init_s"],
+                     "returncode": r["returncode"], "final": {k: last.get(k) for k in ("log_G", "num_muts", "t_MRCA", "mu", "n0")},
+                     "tips": (emat.num_nodes + 1) // 2}
+        if r["returncode"] != 0:
+            out[name]["stderr_tail"] = r["stderr_tail"][-4:]
+    return out
 
 
 _REAL_STDOUT = None
@@ -208,6 +291,38 @@ def emit_line(obj):
         os.write(_REAL_STDOUT, data)
 
 
+def reference_arm(db, args, rank):
+    """The reference's own CPU implementation of the path on all host threads; rank 0 only.  Loads libdphy_synth.so (inputs)
+    and oracle/_ref -- no product code."""
+    if rank != 0:
+        return 0
+    threads = host_cores()
+    emat, sites, info = db.synth_generate(db.synth_params(args.config))
+    spr_xs = pick_spr_nodes(emat, max(args.spr_studies, threads)) if args.spr_studies > 0 else None
+    # a step = a bounded sample of the workload: as many evaluations as fit the per-step budget, measured, not assumed
+    per_step = max(0.25, min(args.cpu_seconds, 100.0 / max(1, args.steps + args.warmup)))
+    vals, secs, last = [], [], None
+    for i in range(args.warmup + args.steps):
+        r = cpu_log_G(emat, sites, per_step, threads)
+        if i >= args.warmup:
+            vals.append(r["value"]); secs.append(r["seconds"])
+        last = r
+    v = float(np.mean(vals))
+    spr = cpu_spr(emat, sites, spr_xs, args.cpu_seconds, threads, info["t_max_tip"]) if spr_xs is not None else None
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_block(args),
+            "spr_candidates_per_s": spr["value"] if spr else None,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": last["kind"], "sample": last["sample"], "spr": spr},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_partitioned:
+        line["partitioned"] = cpu_log_G_partitioned(db, emat, sites, args.cpu_seconds, threads)
+    if not args.no_mcmc:
+        line["mcmc"] = mcmc_figures(db, args, "stock", args.gpus)
+    emit_line(line)
+    return 0
+
+
 def main():
     args = parse_args()
     claim_stdout()
@@ -218,144 +333,118 @@ def main():
     import delphy_b200 as db
 
     if args.impl == "reference":
-        # the reference's own CPU implementation of the path, all host threads, rank 0 only
-        if rank != 0:
-            return 0
-        threads = host_cores()
-        emat, sites, info = db.synth_generate(db.synth_params(args.config))
-        spr_xs = pick_spr_nodes(emat, max(args.spr_studies, threads)) if args.spr_studies > 0 else None
-        per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
-        vals, sprs = [], []
-        last = None
-        for i in range(args.warmup + args.steps):
-            r = cpu_baseline_run(emat, sites, per_step, threads, info["t_max_tip"], spr_xs)
-            if i >= args.warmup:
-                vals.append(r["value"]); sprs.append(r.get("spr", {}).get("value", 0.0))
-            last = r
-        v = float(np.mean(vals))
-        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.config, args.chains), "host_threads": threads},
-                "spr_candidates_per_s": float(np.mean(sprs)) if sprs else None,
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": last["kind"], "sample": last["sample"],
-                                 "spr": last.get("spr")},
-                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        emit_line(line)
-        return 0
+        return reference_arm(db, args, rank)
 
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = db.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
-
-    # ---- synthetic inputs: `chains` distinct EMATs per rank (different seeds) --------------------------------------
-    emats, tables, infos = [], [], []
-    base_seed = 20251017 + 1000 * rank
-    for c in range(args.chains):
-        e, s, info = db.synth_generate(db.synth_params(args.config, seed=base_seed + c))
-        emats.append(e); infos.append(info)
-        tables.append(db.DeviceSites(ctx, s))
-    host_sites = [t.host for t in tables]
-    forest = db.Forest(ctx, emats, tables, sites_index=np.arange(args.chains))
-    alg_bytes = forest.log_G_algorithmic_bytes
-
-    # SPR requests: full studies of random attached nodes of chain 0 (seeded as Subrun::spr1_move does)
-    spr_reqs = None
-    spr_xs = pick_spr_nodes(emats[0], args.spr_studies) if args.spr_studies > 0 else np.zeros(0, np.int32)
-    if args.spr_studies > 0 and hasattr(db, "spr_requests_for_attached"):
-        forest.eval_log_G()
-        lam0 = forest.lambda_i(0)
-        spr_reqs = db.spr_requests_for_attached(emats[0], 0, spr_xs, lam0, infos[0]["t_max_tip"])
+    peak, peak_src = measured_peak()
+    R = max(1, args.evals_per_step)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def make_forest(cfg, chains):
+        emats, tables, infos = [], [], []
+        base_seed = 20251017 + 1000 * rank + 100000 * cfg
+        for c in range(chains):
+            e, s, info = db.synth_generate(db.synth_params(cfg, seed=base_seed + c))
+            emats.append(e); infos.append(info)
+            tables.append(db.DeviceSites(ctx, s))
+        return emats, tables, infos, db.Forest(ctx, emats, tables, sites_index=np.arange(chains))
+
+    def time_evals(forest, steps, reps):
+        """ms per step of `reps` evaluations of the forest each, K steps back to back between two events on the launching stream."""
+        a, b = ev(), ev()
+        barrier()
+        a.record(stream)
+        h0 = time.perf_counter()
+        for _ in range(steps * reps):
+            forest.eval_log_G()
+        host_ms = (time.perf_counter() - h0) * 1e3 / steps
+        b.record(stream)
+        barrier()
+        return a.elapsed_time(b) / steps, host_ms
+
+    # ---- headline workload --------------------------------------------------------------------------------------------------------------
+    emats, tables, infos, forest = make_forest(args.config, args.chains)
+    host_sites = [t.host for t in tables]
+    alg_bytes = forest.log_G_algorithmic_bytes
+    spr_reqs = None
+    spr_xs = pick_spr_nodes(emats[0], args.spr_studies) if args.spr_studies > 0 else np.zeros(0, np.int32)
+    if args.spr_studies > 0:
+        forest.eval_log_G()
+        spr_reqs = db.spr_requests_for_attached(emats[0], 0, spr_xs, forest.lambda_i(0), infos[0]["t_max_tip"])
+
     def spr_batch():
         b = forest.spr_study_batch(spr_reqs)
         b.close()                    # stream-ordered free: the memory is reused by the next batch
 
     for _ in range(max(args.warmup, 3)):
-        forest.eval_log_G()
+        for _ in range(R):
+            forest.eval_log_G()
         if spr_reqs is not None:
             spr_batch()
-    barrier()
 
-    # ---- timed region ------------------------------------------------------------------------------------------------
-    # A step = one log-G evaluation of every EMAT of the forest (the metric's unit).  The K steps are enqueued back to back
-    # between two events on the launching stream, so the interval is device time, not launch latency.  The SPR sweep
-    # (the metric's second figure) is timed the same way right after, K batches of `--spr-studies` full studies, and so is
-    # the general (per-event) log-G schedule, which re-reads every list instead of the per-branch folded weights.
-    def ev():
-        return torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launches
-    e0, e1, e2, e3 = ev(), ev(), ev(), ev()
-    barrier()
-    e0.record(stream)
-    h0 = time.perf_counter()
-    for i in range(args.steps):
-        forest.eval_log_G()
-    host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps    # CPU cost of enqueuing one step (must stay below ms_per_step)
-    e1.record(stream)
-    barrier()
+    logg_ms, host_enqueue_ms = time_evals(forest, args.steps, R)
     launches = ctx.launches - launches0
-    logg_ms = e0.elapsed_time(e1) / args.steps
     _, _, lg = forest.log_G()        # checksum of the timed work: log G of every chain
 
-    spr_ms = None
-    spr_regions = 0
-    spr_launches = 0
+    spr_ms, spr_regions, spr_launches = None, 0, 0
     if spr_reqs is not None:
+        SB = max(1, args.spr_batches_per_step)
         l0 = ctx.launches
+        a, b = ev(), ev()
         barrier()
-        e2.record(stream)
-        for i in range(args.steps):
+        a.record(stream)
+        for _ in range(args.steps * SB):
             spr_batch()
-        e3.record(stream)
+        b.record(stream)
         barrier()
-        spr_ms = e2.elapsed_time(e3) / args.steps
+        spr_ms = a.elapsed_time(b) / (args.steps * SB)        # per batch
         spr_launches = ctx.launches - l0
-        b = forest.spr_study_batch(spr_reqs)
-        spr_regions = b.total_regions()
-        b.close()
+        bt = forest.spr_study_batch(spr_reqs)
+        spr_regions = bt.total_regions()
+        bt.close()
 
     # the general schedule (every mutation / missation / from-state list re-read per evaluation)
     ctx.set_log_G_path("general")
     for _ in range(3):
         forest.eval_log_G()
-    g0, g1 = ev(), ev()
-    barrier()
-    g0.record(stream)
-    for i in range(args.steps):
-        forest.eval_log_G()
-    g1.record(stream)
-    barrier()
-    gen_ms = g0.elapsed_time(g1) / args.steps
+    gen_ms, _ = time_evals(forest, args.steps, R)
     _, _, lg_gen = forest.log_G()
     ctx.set_log_G_path("auto")
     assert np.allclose(lg_gen, lg, rtol=1e-11), "folded and general log-G schedules disagree"
     clocks = sampler.stop() if rank == 0 else None
-
-    t = torch.tensor([logg_ms, spr_ms or 0.0, gen_ms], device=f"cuda:{local_rank}", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    logg_ms_max, spr_ms_max, gen_ms_max = [float(x) for x in t.tolist()]
+    logg_ms_max, spr_ms_max, gen_ms_max = max_over_ranks([logg_ms, spr_ms or 0.0, gen_ms])
 
     # ---- the reference's global-move cycle: new mu on every chain's site table, re-evaluate every chain, read log G back --------
-    # (what Run does after a global move, core/run.cpp:437-453; every evaluation here follows a real model change)
     mc_steps = max(3, min(args.steps, 20))
     mus = [t.host.mu.copy() for t in tables]
+
     def model_change_cycle(i):
         for k, t in enumerate(tables):
             t.set_evo(mu=mus[k] * (1.0 + 1e-3 * ((i % 7) + 1)))
@@ -366,28 +455,20 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for i in range(mc_steps):
-        mc_out = model_change_cycle(i)
+        model_change_cycle(i)
     torch.cuda.synchronize()
     mc_s = time.perf_counter() - t0
     for k, t in enumerate(tables):
         t.set_evo(mu=mus[k])
     forest.eval_log_G()
     assert np.allclose(forest.log_G()[2], lg, rtol=1e-12), "restoring the model does not restore log G"
-    tm = torch.tensor([mc_s], device=f"cuda:{local_rank}", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    mc_s = float(tm.item())
+    (mc_s,) = max_over_ranks([mc_s])
 
     # ---- e2e: host buffers -> C ABI -> host scalars, copies inside the timed region ------------------------------
     n_e2e = min(args.e2e_chains, args.chains)
-    # the caller's EMAT arrays live in page-locked host memory (dphy_host_alloc), as the contract's e2e leg asks: the upload
-    # DMAs them from where they lie
-    e2e_emats = [e.pinned(ctx) for e in emats[:n_e2e]]
+    e2e_emats = [e.pinned(ctx) for e in emats[:n_e2e]]        # page-locked caller arrays (dphy_host_alloc): DMA'd from where they lie
     e2e_steps = max(3, min(args.steps, 10))
-    h2d = 0
-    for e in e2e_emats:
-        for k in db.HostEmat.FIELDS_I32 + db.HostEmat.FIELDS_U8 + db.HostEmat.FIELDS_F64:
-            h2d += getattr(e, k).nbytes
+    h2d = sum(getattr(e, k).nbytes for e in e2e_emats for k in db.HostEmat.FIELDS_I32 + db.HostEmat.FIELDS_U8 + db.HostEmat.FIELDS_F64)
     d2h = n_e2e * 3 * 8
 
     def e2e_step():
@@ -403,35 +484,107 @@ def main():
     for _ in range(e2e_steps):
         e2e_out = e2e_step()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    (e2e_s,) = max_over_ranks([time.perf_counter() - t0])
     assert np.allclose(e2e_out[2], lg[:n_e2e], rtol=1e-12)
+    del e2e_emats
+    forest_bytes = forest.device_bytes
+    nodes0, info0 = emats[0].num_nodes, infos[0]
+    whole_emat, whole_sites = emats[0], host_sites[0]
+    forest.close()
+    for tb in tables[1:]:
+        tb.close()
+
+    # ---- secondary shapes: BASELINE.json configs[1], [2], [4] ------------------------------------------------------------------------------------
+    secondary = {}
+    if not args.no_secondary:
+        for cfg, chains in SECONDARY.items():
+            if cfg == args.config:
+                continue
+            se, st, si, sf = make_forest(cfg, chains)
+            for _ in range(3):
+                sf.eval_log_G()
+            reps = 8
+            ms, _ = time_evals(sf, max(3, args.steps // 2), reps)
+            (ms,) = max_over_ranks([ms])
+            ab = sf.log_G_algorithmic_bytes
+            uniform = bool(np.all(st[0].host.nu_l == st[0].host.nu_l[0]))
+            entry = {"workload": f"synthetic {SHAPES[cfg]} EMAT x {chains} chains per GPU", "value": chains * reps * world / (ms * 1e-3), "unit": UNIT,
+                     "ms_per_eval": ms / reps, "schedule": "folded (uniform nu)" if uniform else "general (site-rate heterogeneity)",
+                     "forest_device_bytes": sf.device_bytes, "l2": "larger than L2" if sf.device_bytes > 130e6 else "fits in L2",
+                     "roofline": {"bound": "hbm", "achieved": ab / (ms / reps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": ab / (ms / reps * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": ab,
+                                  "traffic": measured_traffic("emat_log_G_folded_kernel" if uniform else "emat_log_G_tile_kernel", cfg, chains)}}
+            if spr_reqs is not None:
+                sf.eval_log_G()
+                xs2 = pick_spr_nodes(se[0], min(args.spr_studies, 64))
+                rq = db.spr_requests_for_attached(se[0], 0, xs2, sf.lambda_i(0), si[0]["t_max_tip"])
+                for _ in range(2):
+                    sf.spr_study_batch(rq).close()
+                a, b = ev(), ev()
+                nb = max(4, args.steps)
+                barrier(); a.record(stream)
+                for _ in range(nb):
+                    sf.spr_study_batch(rq).close()
+                b.record(stream); barrier()
+                (sms,) = max_over_ranks([a.elapsed_time(b) / nb])
+                bt = sf.spr_study_batch(rq); nreg = bt.total_regions(); bt.close()
+                entry["spr_candidates_per_s"] = nreg * world / (sms * 1e-3)
+                entry["spr_roofline_frac"] = nreg * 60 / (sms * 1e-3) / 1e9 / peak
+            secondary[str(cfg)] = entry
+            sf.close()
+            for tb in st:
+                tb.close()
+
+    # ---- one tree, parts spread over the ranks, one all-reduce per cycle -----------------------------------------------------------------
+    partitioned = None
+    if not args.no_partitioned:
+        from delphy_b200 import partitioned as pp
+        # every rank cuts the SAME tree (same seed) and keeps the parts i % world == rank
+        pe, ps, pinfo = db.synth_generate(db.synth_params(args.config, seed=20251017))
+        pt = pp.PartitionedTree(ctx, pe, ps, world, rank, parts_per_rank=args.parts_per_gpu, dist=dist if world > 1 else None,
+                                torch=torch, device=dev)
+        pt.cycle(1.0)
+        got = pt.totals()
+        want = pp.whole_tree_totals(ctx, pe, ps, torch, dev, 1.0)
+        pp.check_totals(got, want)                 # Run::check_global_and_local_totals_match (core/run.cpp:340-357)
+        psteps = max(20, args.steps * 4)
+        cyc_ms, cyc_host_ms = pp.timed_cycles(pt, psteps, torch, reduce=True, barrier=barrier)
+        nored_ms, _ = pp.timed_cycles(pt, psteps, torch, reduce=False, barrier=barrier)
+        cyc_ms, nored_ms = max_over_ranks([cyc_ms, nored_ms])
+        t0 = time.perf_counter()
+        merged = pt.partition.reassemble()
+        reasm_ms = (time.perf_counter() - t0) * 1e3
+        assert merged.root == pe.root and np.array_equal(merged.parent, pe.parent) and np.array_equal(merged.mut_t, pe.mut_t)
+        partitioned = {"workload": f"ONE synthetic {SHAPES[args.config]} EMAT cut into {pt.num_parts} parts, parts i % {world} on rank i",
+                       "parallelism": "partition parts", "scaling": "strong", "parts": pt.num_parts, "parts_on_rank0": len(pt.mine),
+                       "cycle": "set_evo(new mu) + log G / T / num_muts / num_muts_ab / Ttwiddle_beta_a of every local part + ONE all-reduce of 23 doubles",
+                       "value": 1e3 / cyc_ms, "unit": "whole-tree cycles/s", "ms_per_cycle": cyc_ms, "ms_per_cycle_without_allreduce": nored_ms,
+                       "allreduce_ms": max(0.0, cyc_ms - nored_ms), "collective": "NCCL all_reduce(sum), 23 x f64" if world > 1 else "none (1 rank)",
+                       "host_enqueue_ms_per_cycle": cyc_host_ms, "totals_match_whole_tree": True, "log_G": float(got[0]),
+                       "reassemble_ms_host": reasm_ms}
+        pt.close()
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        value = args.chains * world / (logg_ms_max * 1e-3)
-        achieved = alg_bytes / (logg_ms_max * 1e-3) / 1e9
+        value = args.chains * R * world / (logg_ms_max * 1e-3)
+        eval_ms = logg_ms_max / R
+        achieved = alg_bytes / (eval_ms * 1e-3) / 1e9
         traffic = measured_traffic("emat_log_G_folded_kernel", args.config, args.chains)
+        cfg = config_block(args)
+        cfg.update({"nodes_per_chain": nodes0, "mutations_per_chain": info0["num_mutations"], "missation_intervals_per_chain": info0["num_intervals"],
+                    "max_depth": info0["max_depth"], "forest_device_bytes": forest_bytes, "parallelism": f"chains x{world}"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": logg_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, args.chains), "chains_per_gpu": args.chains,
-                       "step": "one log-G evaluation (lambda_i + root prior + log G below root) of every EMAT of the forest",
-                       "nodes_per_chain": emats[0].num_nodes, "mutations_per_chain": infos[0]["num_mutations"],
-                       "missation_intervals_per_chain": infos[0]["num_intervals"], "max_depth": infos[0]["max_depth"],
-                       "forest_device_bytes": forest.device_bytes, "l2": "inputs larger than L2 (forest > 126 MB)" if forest.device_bytes > 130e6 else "forest fits in L2",
-                       "spr_studies_per_batch": int(args.spr_studies if spr_reqs is not None else 0), "parallelism": f"chains x{world}"},
+            "dtype": "f64", "data": "synthetic", "config": cfg,
             "roofline": {"kernel": "emat_log_G_folded_kernel (+ emat_log_G_folded_tree_kernel)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": logg_ms_max,
-                         "note": "algorithmic bytes = SURVEY 8(d) per-event figure; this schedule reads per-branch folded weights "
-                                 "instead of the missation / from-state lists, so its DRAM traffic is below the algorithmic bytes"},
-            "loglik_general_schedule": {"value": args.chains * world / (gen_ms_max * 1e-3), "unit": UNIT, "launch_ms": gen_ms_max,
-                                        "achieved": alg_bytes / (gen_ms_max * 1e-3) / 1e9, "frac": alg_bytes / (gen_ms_max * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": eval_ms,
+                         "achieved_dram_frac": (traffic / (eval_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "note": "algorithmic bytes = SURVEY 8(d) per-event figure; this schedule reads per-branch folded weights instead of the "
+                                 "missation / from-state lists, so its DRAM traffic (traffic, achieved_dram_frac) is below the algorithmic bytes"},
+            "loglik_general_schedule": {"value": args.chains * R * world / (gen_ms_max * 1e-3), "unit": UNIT, "launch_ms": gen_ms_max / R,
+                                        "achieved": alg_bytes / (gen_ms_max / R * 1e-3) / 1e9, "frac": alg_bytes / (gen_ms_max / R * 1e-3) / 1e9 / peak,
+                                        "traffic": measured_traffic("emat_log_G_tile_kernel", args.config, args.chains),
                                         "note": "every mutation / missation / from-state list re-read per evaluation (also refreshes nsmn and the num_muts tallies)"},
             "model_change_cycle": {"value": args.chains * mc_steps * world / mc_s, "unit": UNIT, "ms_per_cycle": mc_s / mc_steps * 1e3,
                                    "note": "dphy_sites_set_evo(new mu) on every chain's site table + evaluation of every chain + log G read back, wall clock"},
@@ -439,21 +592,36 @@ def main():
             "spr_regions_per_batch": spr_regions, "spr_ms_per_batch": spr_ms_max if spr_ms else None,
             "e2e": {"value": n_e2e * e2e_steps * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "chains_per_step": n_e2e, "steps": e2e_steps},
-            "host_enqueue_ms_per_step": host_enqueue_ms, "gpu_launches": int(launches), "gpu_launches_spr": int(spr_launches), "clocks": clocks, "log_G_checksum": float(np.sum(lg)),
+            "host_enqueue_ms_per_step": host_enqueue_ms, "gpu_launches": int(launches), "gpu_launches_spr": int(spr_launches), "clocks": clocks,
+            "log_G_checksum": float(np.sum(lg)),
         }
         if spr_ms:
             spr_alg = spr_regions * 60
             line["roofline_spr"] = {"bound": "hbm", "achieved": spr_alg / (spr_ms_max * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": spr_alg / (spr_ms_max * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_candidate": 60,
                                     "launch_ms": spr_ms_max}
+        if secondary:
+            line["configs"] = secondary
+        if partitioned:
+            line["partitioned"] = partitioned
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_run(emats[0], host_sites[0], args.cpu_seconds, host_cores(), infos[0]["t_max_tip"],
-                                                    spr_xs if spr_reqs is not None else None)
-        emit_line(line)
-    forest.close()
-    for tb in tables:
-        tb.close()
+            threads = host_cores()
+            cb = cpu_log_G(whole_emat, whole_sites, args.cpu_seconds, threads)
+            cb["spr"] = cpu_spr(whole_emat, whole_sites, spr_xs if spr_reqs is not None else None, args.cpu_seconds, threads, info0["t_max_tip"])
+            if not args.no_partitioned:
+                cb["partitioned"] = cpu_log_G_partitioned(db, whole_emat, whole_sites, args.cpu_seconds / 2, threads)
+            line["cpu_baseline"] = cb
+    tables[0].close()
     ctx.close()
+    # MCMC steps/s through the reference's own driver with the hot path substituted at link time: one process (the driver's own
+    # thread pool, one Subrun per thread, threads spread round-robin over the N GPUs), run by rank 0 while the other ranks wait
+    if not args.no_mcmc:
+        if rank == 0:
+            line["mcmc"] = mcmc_figures(db, args, "dropin", world)
+        if world > 1:
+            dist.barrier()
+    if rank == 0:
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -129,6 +129,18 @@ _LIB = None
 _SYNTH_LIB = None
 
 
+def _bind_partition(L):
+    vp = C.c_void_p
+    L.dphy_partition_generate_stencil.argtypes = [C.POINTER(EmatHost), C.c_int32, C.c_uint64, i32p, i32p]
+    L.dphy_partition_split.argtypes = [C.POINTER(EmatHost), C.POINTER(SitesHost), C.c_int32, i32p, C.POINTER(vp)]
+    L.dphy_partition_num_parts.argtypes = [vp]; L.dphy_partition_num_parts.restype = C.c_int32
+    L.dphy_partition_part.argtypes = [vp, C.c_int32]; L.dphy_partition_part.restype = C.POINTER(EmatHost)
+    L.dphy_partition_orig_index.argtypes = [vp, C.c_int32]; L.dphy_partition_orig_index.restype = i32p
+    L.dphy_partition_free.argtypes = [vp]; L.dphy_partition_free.restype = None
+    L.dphy_partition_reassemble.argtypes = [vp, C.POINTER(EmatHost), C.c_int32, C.POINTER(EmatHost)]
+    L.dphy_partition_reassemble.restype = C.POINTER(EmatHost)
+
+
 def synth_lib() -> C.CDLL:
     """libdphy_synth.so: the synthetic-input generator (its own shared object, so that generating inputs loads no product code)."""
     global _SYNTH_LIB
@@ -141,6 +153,7 @@ def synth_lib() -> C.CDLL:
         L.dphy_synth_generate.argtypes = [C.POINTER(SynthParams), C.POINTER(C.POINTER(SynthEmat))]
         L.dphy_synth_free.argtypes = [C.POINTER(SynthEmat)]
         L.dphy_synth_free.restype = None
+        _bind_partition(L)
         _SYNTH_LIB = L
     return _SYNTH_LIB
 
@@ -203,14 +216,7 @@ def lib() -> C.CDLL:
     L.dphy_gamma_q_inv.argtypes = [vp, C.c_int32, f64p, f64p, f64p]
     L.dphy_spr_batch_pick_nexus_regions.argtypes = [vp, vp, f64p, i32p]
     L.dphy_spr_batch_find_region.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_double, i32p]
-    L.dphy_partition_generate_stencil.argtypes = [C.POINTER(EmatHost), C.c_int32, C.c_uint64, i32p, i32p]
-    L.dphy_partition_split.argtypes = [C.POINTER(EmatHost), C.POINTER(SitesHost), C.c_int32, i32p, C.POINTER(vp)]
-    L.dphy_partition_num_parts.argtypes = [vp]; L.dphy_partition_num_parts.restype = C.c_int32
-    L.dphy_partition_part.argtypes = [vp, C.c_int32]; L.dphy_partition_part.restype = C.POINTER(EmatHost)
-    L.dphy_partition_orig_index.argtypes = [vp, C.c_int32]; L.dphy_partition_orig_index.restype = i32p
-    L.dphy_partition_free.argtypes = [vp]
-    L.dphy_partition_reassemble.argtypes = [vp, C.POINTER(EmatHost), C.c_int32, C.POINTER(EmatHost)]
-    L.dphy_partition_reassemble.restype = C.POINTER(EmatHost)
+    _bind_partition(L)
     _LIB = L
     return L
 
@@ -322,8 +328,10 @@ class Partition:
     """A tree cut into parts that can be edited independently and merged back (Run::repartition / Run::reassemble,
     core/run.cpp:110-256).  parts[i] are HostEmat copies; origs[i] = orig_tree_index of every node of part i."""
 
-    def __init__(self, emat: HostEmat, sites: HostSites, num_parts: int = 0, seed: int = 1, cut_points=None):
-        L = lib()
+    def __init__(self, emat: HostEmat, sites: HostSites, num_parts: int = 0, seed: int = 1, cut_points=None, host_only=False):
+        # host_only: use the copy of the (host-only) tree cutter inside libdphy_synth.so, so that no product library is loaded
+        L = synth_lib() if host_only else lib()
+        self._L = L
         self.emat = emat
         es, ss = emat.as_struct(), sites.as_struct()
         if cut_points is None:
@@ -348,14 +356,14 @@ class Partition:
         parts = self.parts if parts is None else parts
         arr = (EmatHost * len(parts))(*[p.as_struct() for p in parts])
         es = self.emat.as_struct()
-        r = lib().dphy_partition_reassemble(self._h, C.byref(es), len(parts), arr)
+        r = self._L.dphy_partition_reassemble(self._h, C.byref(es), len(parts), arr)
         if not r:
             raise DphyError(ERR_INVALID_ARGUMENT, "dphy_partition_reassemble: parts do not match the split")
         return _emat_from_struct(r.contents)
 
     def close(self):
         if self._h:
-            lib().dphy_partition_free(self._h)
+            self._L.dphy_partition_free(self._h)
             self._h = C.c_void_p()
 
 

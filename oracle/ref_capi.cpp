@@ -361,4 +361,33 @@ int32_t ref_partition_part(const orc_emat* e, const orc_sites* s, const int32_t*
   return (int32_t)std::ssize(part);
 }
 
+// The reference's own multithreaded scheme (core/run.cpp:682-693): the tree cut into parts, one part per worker thread, each
+// thread evaluating its part's log G (Subrun::calc_cur_log_G: calc_lambda_i + [root prior] + calc_log_G_below_root) `reps` times.
+// The parts are passed in already cut (Run::repartition's per-part Phylo_trees).  Returns seconds; *out_log_G = sum over parts.
+double ref_bench_log_G_parts(const orc_emat* const* parts, int32_t n_parts, const orc_sites* s, int32_t reps, double* out_log_G) {
+  auto evo = make_evo(s);
+  auto trees = std::vector<Phylo_tree>{};
+  for (auto i = 0; i != n_parts; ++i) { trees.push_back(make_tree(parts[i], s)); }
+  auto cq = calc_cum_Q_l_for_sequence(trees[0].ref_sequence, evo);
+  auto freqs = calc_state_frequencies_per_partition_of(trees[0].ref_sequence, evo);
+  auto results = std::vector<double>(n_parts, 0.0);
+  auto work = [&](int tid) {
+    auto acc = 0.0;
+    for (auto r = 0; r != reps; ++r) {
+      auto lambda_i = calc_lambda_i(trees[tid], evo, cq);
+      acc = (parts[tid]->includes_run_root ? calc_log_root_prior(trees[tid], evo, freqs) : 0.0)
+          + calc_log_G_below_root(trees[tid], evo, lambda_i, freqs);
+    }
+    results[tid] = acc;
+  };
+  auto t0 = std::chrono::steady_clock::now();
+  auto threads = std::vector<std::thread>{};
+  for (auto i = 1; i < n_parts; ++i) { threads.emplace_back(work, i); }
+  work(0);
+  for (auto& th : threads) { th.join(); }
+  auto t1 = std::chrono::steady_clock::now();
+  if (out_log_G) { *out_log_G = 0.0; for (auto v : results) { *out_log_G += v; } }
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
 }  // extern "C"

@@ -15,7 +15,7 @@ def _run(env_extra=None):
     env = dict(os.environ)
     env.update(env_extra or {})
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "1", "--steps", "1",
-                           "--warmup", "0", "--cpu-seconds", "0.3", "--spr-studies", "2"],
+                           "--warmup", "0", "--cpu-seconds", "0.3", "--spr-studies", "2", "--mcmc-tips", "300", "--mcmc-steps", "20000"],
                           capture_output=True, text=True, timeout=300, env=env)
 
 
@@ -29,7 +29,15 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["ms_per_step"] > 0
+    # the reference's own multithreaded scheme (tree cut into one part per thread) and its own CLI's MCMC throughput
+    assert d["partitioned"]["kind"] == "reference" and d["partitioned"]["value"] > 0
+    stock = os.path.join(ROOT, "oracle", "_ref", "delphy")
+    if os.path.exists(stock):
+        for case in ("cfg1_200_tips", "cfg3_300_tips"):
+            assert d["mcmc"][case]["returncode"] == 0 and d["mcmc"][case]["steps_per_s"] > 0
+    # the reference arm loads no product code: its inputs come from libdphy_synth.so
+    assert "libdelphy_b200" not in r.stderr
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref not built (needs the reference checkout)")

@@ -36,6 +36,8 @@ def test_input_generator_is_a_separate_library():
     for n in names:
         assert hasattr(synth, n)
         assert not hasattr(prod, n)
+    # it carries its own copy of the host-only tree cutter (input preparation for the reference arm's partitioned CPU baseline)
+    assert hasattr(synth, "dphy_partition_split") and not hasattr(synth, "dphy_ctx_create")
 
 
 def test_no_cpu_fallback():
