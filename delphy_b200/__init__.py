@@ -82,6 +82,29 @@ class SprWeightParams(C.Structure):
 SPR_X_FROM_TREE, SPR_X_REL_REF, SPR_X_REL_START = 0, 1, 2
 
 
+class NodeRow(C.Structure):
+    _fields_ = [
+        ("tree", C.c_int32), ("node", C.c_int32), ("parent", C.c_int32), ("child0", C.c_int32), ("child1", C.c_int32),
+        ("n_muts", C.c_int32), ("n_miss", C.c_int32), ("n_fs", C.c_int32), ("t", C.c_double),
+        ("mut_site", i32p), ("mut_from", u8p), ("mut_to", u8p), ("mut_t", f64p),
+        ("miss_start", i32p), ("miss_end", i32p), ("fs_site", i32p), ("fs_from", u8p),
+    ]
+
+
+def node_row(tree: int, emat: "HostEmat", v: int) -> NodeRow:
+    """The row of node v as `emat` (already edited on the host) has it."""
+    m0, m1 = int(emat.mut_off[v]), int(emat.mut_off[v + 1])
+    i0, i1 = int(emat.miss_off[v]), int(emat.miss_off[v + 1])
+    f0, f1 = int(emat.fs_off[v]), int(emat.fs_off[v + 1])
+    keep = [np.ascontiguousarray(a) for a in (emat.mut_site[m0:m1], emat.mut_from[m0:m1], emat.mut_to[m0:m1], emat.mut_t[m0:m1],
+                                              emat.miss_start[i0:i1], emat.miss_end[i0:i1], emat.fs_site[f0:f1], emat.fs_from[f0:f1])]
+    r = NodeRow(tree, v, int(emat.parent[v]), int(emat.child0[v]), int(emat.child1[v]), m1 - m0, i1 - i0, f1 - f0, float(emat.t[v]),
+                _p(keep[0], i32p), _p(keep[1], u8p), _p(keep[2], u8p), _p(keep[3], f64p), _p(keep[4], i32p), _p(keep[5], i32p),
+                _p(keep[6], i32p), _p(keep[7], u8p))
+    r._keep = keep
+    return r
+
+
 class SprSummary(C.Structure):
     _fields_ = [
         ("mu", C.c_double), ("log_Wmax", C.c_double), ("sum_W_over_Wmax", C.c_double),
@@ -206,6 +229,7 @@ def lib() -> C.CDLL:
     L.dphy_spr_batch_total_regions.argtypes = [vp, vp]; L.dphy_spr_batch_total_regions.restype = C.c_int64
     L.dphy_spr_batch_get_regions.argtypes = [vp, vp, C.c_int32, C.POINTER(CandidateRegion), C.c_int64]
     L.dphy_spr_batch_get_regions.restype = C.c_int64
+    L.dphy_forest_apply_rows.argtypes = [vp, vp, C.c_int32, C.POINTER(NodeRow), i32p]
     L.dphy_sites_update.argtypes = [vp, vp, C.POINTER(SitesHost)]
     L.dphy_forest_cycle_tallies_device.argtypes = [vp, vp, vp, C.c_int32]
     L.dphy_spr_batch_set_weights.argtypes = [vp, vp, C.POINTER(SprWeightParams)]
@@ -595,6 +619,13 @@ class Forest:
     def set_node_times(self, tree, nodes, t):
         nodes = np.ascontiguousarray(nodes, np.int32); t = np.ascontiguousarray(t, np.float64)
         self.ctx.check(lib().dphy_forest_set_node_times(self.ctx._h, self._h, tree, len(nodes), _p(nodes, i32p), _p(t, f64p)))
+
+    def apply_rows(self, rows, new_roots=None):
+        """dphy_forest_apply_rows: replace the given NodeRow rows (and optionally every tree's root) on the device."""
+        n = len(rows)
+        arr = (NodeRow * max(n, 1))(*rows)
+        nr = None if new_roots is None else np.ascontiguousarray(new_roots, np.int32)
+        self.ctx.check(lib().dphy_forest_apply_rows(self.ctx._h, self._h, n, arr, _p(nr, i32p) if nr is not None else None))
 
     def tallies(self):
         out = (Tallies * self.num_trees)()

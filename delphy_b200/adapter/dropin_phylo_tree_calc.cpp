@@ -30,7 +30,8 @@ struct Shipped {       // the calling thread's device copy of (tree, evo) after 
   Resident& r;
   dphy_ctx* ctx;
   dphy_forest* forest;
-  Shipped(const Phylo_tree& tree, const Global_evo_model* evo) : r{Resident::get()}, ctx{r.ctx()}, forest{r.sync_tree(tree, evo)} {}
+  Shipped(const Phylo_tree& tree, const Global_evo_model* evo, const char* who = __builtin_FUNCTION())
+      : r{Resident::get()}, ctx{r.ctx()}, forest{r.sync_tree(tree, evo)} { b200::count_call(who); }
   auto tallies() -> dphy_tallies {
     auto t = dphy_tallies{};
     throw_on_error(ctx, dphy_forest_calc_tallies(ctx, forest, &t), "dphy_forest_calc_tallies");

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -22,6 +24,26 @@ auto throw_on_error(dphy_ctx* ctx, int status, const char* what) -> void {
     case DPHY_ERR_INVALID_ARGUMENT: throw std::invalid_argument(msg);
     default: throw std::runtime_error(msg);
   }
+}
+
+namespace {
+struct Call_counters {
+  std::mutex mu;
+  std::map<std::string, long long> counts;
+  ~Call_counters() {
+    if (const char* e = std::getenv("DPHY_DROPIN_STATS"); e != nullptr && std::atoi(e) != 0) {
+      for (const auto& [name, n] : counts) { std::fprintf(stderr, "[delphy_b200 drop-in] calls: %-48s %lld\n", name.c_str(), n); }
+    }
+  }
+};
+Call_counters g_calls;
+}  // namespace
+
+auto count_call(const char* name) -> void {
+  static const bool on = [] { const char* e = std::getenv("DPHY_DROPIN_STATS"); return e != nullptr && std::atoi(e) != 0; }();
+  if (!on) { return; }
+  auto lock = std::lock_guard<std::mutex>{g_calls.mu};
+  ++g_calls.counts[name];
 }
 
 template <typename T>
@@ -70,7 +92,7 @@ namespace {
 // run fn(lo, hi) over [0, n) on up to `threads` host threads (the calling thread takes the first chunk)
 template <typename F>
 auto parallel_ranges(size_t n, int threads, F&& fn) -> void {
-  if (threads <= 1 || n < 16384) { fn(size_t{0}, n); return; }
+  if (threads <= 1 || n < 65536) { fn(size_t{0}, n); return; }   // thread start-up costs more than flattening a small tree
   const auto chunk = (n + threads - 1) / threads;
   auto pool = std::vector<std::thread>{};
   pool.reserve(threads - 1);
@@ -139,6 +161,57 @@ auto flatten_into(dphy_ctx* ctx, const Phylo_tree& tree, Pinned_flat_emat& out) 
       for (const auto& [site, from] : node.missations.from_states) { fs_site[f] = site; fs_from[f] = static_cast<uint8_t>(from); ++f; }
     }
   });
+}
+
+auto flatten_reachable_into(dphy_ctx* ctx, const Phylo_tree& tree, Pinned_flat_emat& out, std::vector<int32_t>& to_orig,
+                            std::vector<int32_t>& of_orig) -> void {
+  const auto n_all = static_cast<size_t>(std::ssize(tree));
+  to_orig.clear();
+  of_orig.assign(n_all, -1);
+  if (tree.root != k_no_node) {
+    auto stack = std::vector<Node_index>{tree.root};
+    while (not stack.empty()) {
+      const auto v = stack.back();
+      stack.pop_back();
+      of_orig[v] = static_cast<int32_t>(to_orig.size());
+      to_orig.push_back(v);
+      if (not tree.at(v).is_tip()) { stack.push_back(tree.at(v).children[1]); stack.push_back(tree.at(v).children[0]); }
+    }
+  }
+  const auto n = to_orig.size();
+  out.num_nodes = static_cast<int32_t>(n);
+  out.root = n != 0 ? 0 : -1;
+  auto* parent = out.parent.ensure(ctx, n); auto* child0 = out.child0.ensure(ctx, n); auto* child1 = out.child1.ensure(ctx, n);
+  auto* t = out.t.ensure(ctx, n);
+  auto* mut_off = out.mut_off.ensure(ctx, n + 1); auto* miss_off = out.miss_off.ensure(ctx, n + 1); auto* fs_off = out.fs_off.ensure(ctx, n + 1);
+  mut_off[0] = 0; miss_off[0] = 0; fs_off[0] = 0;
+  for (auto i = size_t{0}; i != n; ++i) {
+    const auto& node = tree.nodes[to_orig[i]];
+    mut_off[i + 1] = mut_off[i] + static_cast<int32_t>(node.mutations.size());
+    miss_off[i + 1] = miss_off[i] + static_cast<int32_t>(node.missations.intervals.num_intervals());
+    fs_off[i + 1] = fs_off[i] + static_cast<int32_t>(node.missations.from_states.size());
+  }
+  out.num_muts = mut_off[n]; out.num_ivls = miss_off[n]; out.num_fs = fs_off[n];
+  auto* mut_site = out.mut_site.ensure(ctx, out.num_muts); auto* mut_from = out.mut_from.ensure(ctx, out.num_muts);
+  auto* mut_to = out.mut_to.ensure(ctx, out.num_muts); auto* mut_t = out.mut_t.ensure(ctx, out.num_muts);
+  auto* miss_start = out.miss_start.ensure(ctx, out.num_ivls); auto* miss_end = out.miss_end.ensure(ctx, out.num_ivls);
+  auto* fs_site = out.fs_site.ensure(ctx, out.num_fs); auto* fs_from = out.fs_from.ensure(ctx, out.num_fs);
+  for (auto i = size_t{0}; i != n; ++i) {
+    const auto& node = tree.nodes[to_orig[i]];
+    parent[i] = static_cast<size_t>(i) == 0 ? -1 : of_orig[node.parent];
+    if (node.is_tip()) { child0[i] = -1; child1[i] = -1; }
+    else { child0[i] = of_orig[node.children[0]]; child1[i] = of_orig[node.children[1]]; }
+    t[i] = node.t;
+    auto m = static_cast<size_t>(mut_off[i]);
+    for (const auto& mut : node.mutations) {
+      mut_site[m] = mut.site; mut_from[m] = static_cast<uint8_t>(mut.from); mut_to[m] = static_cast<uint8_t>(mut.to); mut_t[m] = mut.t;
+      ++m;
+    }
+    auto iv = static_cast<size_t>(miss_off[i]);
+    for (const auto& [start, end] : node.missations.intervals) { miss_start[iv] = start; miss_end[iv] = end; ++iv; }
+    auto f = static_cast<size_t>(fs_off[i]);
+    for (const auto& [site, from] : node.missations.from_states) { fs_site[f] = site; fs_from[f] = static_cast<uint8_t>(from); ++f; }
+  }
 }
 
 // ---- Resident ------------------------------------------------------------------------------------------------------------------------------------
@@ -253,6 +326,24 @@ auto Resident::sync_tree(const Phylo_tree& tree, const Global_evo_model* evo) ->
   const auto t1 = clock::now();
   drop_forest();
   auto he = flat_.view(true);     // both pieces of log G are computed; callers pick (Subrun::calc_cur_log_G, core/subrun.cpp:58-68)
+  auto zero = int32_t{0};
+  throw_on_error(ctx_, dphy_forest_upload(ctx_, 1, &he, &zero, 1, &sites_, &forest_), "dphy_forest_upload");
+  const auto t2 = clock::now();
+  ++uploads;
+  flatten_seconds += std::chrono::duration<double>(t1 - t0).count();
+  upload_seconds += std::chrono::duration<double>(t2 - t1).count();
+  return forest_;
+}
+
+auto Resident::sync_reachable_tree(const Phylo_tree& tree) -> dphy_forest* {
+  using clock = std::chrono::steady_clock;
+  sync_sites(tree.ref_sequence, nullptr);
+  throw_on_error(ctx_, dphy_ctx_synchronize(ctx_), "dphy_ctx_synchronize");
+  const auto t0 = clock::now();
+  flatten_reachable_into(ctx_, tree, flat_, to_orig_, of_orig_);
+  const auto t1 = clock::now();
+  drop_forest();
+  auto he = flat_.view(true);
   auto zero = int32_t{0};
   throw_on_error(ctx_, dphy_forest_upload(ctx_, 1, &he, &zero, 1, &sites_, &forest_), "dphy_forest_upload");
   const auto t2 = clock::now();

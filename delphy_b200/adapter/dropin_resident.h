@@ -44,6 +44,11 @@ struct Pinned_flat_emat {
 // Phylo_tree -> SoA + CSR (include/delphy_b200.h, dphy_emat_host), in two passes over the nodes split across host threads:
 // list sizes -> offsets (one sequential prefix sum over N), then every thread copies its own node range.
 auto flatten_into(dphy_ctx* ctx, const Phylo_tree& tree, Pinned_flat_emat& out) -> void;
+// The same for the part of `tree` reachable from its root, renumbered in DFS order: build_usher_like_tree studies a tree whose
+// node vector already holds every future tip, most of them not attached yet (core/phylo_tree.cpp:905-932).  to_orig[i] is the
+// tree's index of compact node i; of_orig[v] the compact index of node v (-1: not attached).
+auto flatten_reachable_into(dphy_ctx* ctx, const Phylo_tree& tree, Pinned_flat_emat& out, std::vector<int32_t>& to_orig,
+                            std::vector<int32_t>& of_orig) -> void;
 
 class Resident {
  public:
@@ -56,6 +61,10 @@ class Resident {
   auto sync_sites(const Real_sequence& seq, const Global_evo_model* evo) -> dphy_sites*;
   // Ship `tree` (always) against the synced sites table; the previous forest of this thread is dropped.
   auto sync_tree(const Phylo_tree& tree, const Global_evo_model* evo) -> dphy_forest*;
+  // Ship only the nodes reachable from the root (see flatten_reachable_into); node indices on the device are compact ones.
+  auto sync_reachable_tree(const Phylo_tree& tree) -> dphy_forest*;
+  auto to_orig() const -> const std::vector<int32_t>& { return to_orig_; }
+  auto of_orig() const -> const std::vector<int32_t>& { return of_orig_; }
 
   auto num_sites() const -> int { return static_cast<int>(ref_.size()); }
   auto num_partitions() const -> int { return static_cast<int>(mu_.size()); }
@@ -72,11 +81,15 @@ class Resident {
   dphy_sites* sites_ = nullptr;
   dphy_forest* forest_ = nullptr;
   Pinned_flat_emat flat_;
+  std::vector<int32_t> to_orig_, of_orig_;
   // host shadow of what the sites table holds
   std::vector<uint8_t> ref_;
   std::vector<int32_t> part_;
   std::vector<double> nu_, mu_, pi_, q_;
 };
+
+// Process-wide call counters of the substituted entry points, printed at exit when DPHY_DROPIN_STATS=1.
+auto count_call(const char* name) -> void;
 
 // status -> the exception the reference would have thrown (std::out_of_range / std::invalid_argument; CHECK -> runtime_error)
 auto throw_on_error(dphy_ctx* ctx, int status, const char* what) -> void;

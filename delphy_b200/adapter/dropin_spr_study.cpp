@@ -100,15 +100,21 @@ auto Spr_study_builder::seed_fill_from(Branch_index init_branch, int init_mut_id
 
   if (max_muts_from_start != std::numeric_limits<int>::max() && not bounded_on_device()) {
     pending().drop();                      // a stale record must never match this builder's address
+    b200::count_call("Spr_study_builder::seed_fill_from (bounded, host)");
     as_ref(*this).seed_fill_from(init_branch, init_mut_idx, std::move(init_to_X_deltas), can_change_root);
     return;
   }
 
   auto& p = pending();
   p.drop();
+  b200::count_call(max_muts_from_start == std::numeric_limits<int>::max() ? "Spr_study_builder::seed_fill_from (full, device)"
+                                                                           : "Spr_study_builder::seed_fill_from (bounded, device)");
   auto& r = Resident::get();
   auto* ctx = r.ctx();
-  auto* forest = r.sync_tree(*tree, nullptr);
+  // a sequence that is not in the tree yet (build_usher_like_tree): the node vector also holds the tips still to be attached,
+  // so only the part hanging from the root is shipped, under compact node indices
+  const auto compact = X == k_no_node;
+  auto* forest = compact ? r.sync_reachable_tree(*tree) : r.sync_tree(*tree, nullptr);
   auto verify_deltas = Site_deltas{};
   if (verify_enabled()) { verify_deltas = init_to_X_deltas; }
 
@@ -122,7 +128,7 @@ auto Spr_study_builder::seed_fill_from(Branch_index init_branch, int init_mut_id
   req.tree = 0;
   req.X = X;
   req.t_X = t_X;
-  req.start_branch = init_branch;
+  req.start_branch = compact ? r.of_orig().at(init_branch) : init_branch;
   req.start_mut_idx = init_mut_idx;
   req.init_min_muts = static_cast<int32_t>(std::ssize(init_to_X_deltas));
   req.max_muts_from_start = max_muts_from_start;
@@ -150,6 +156,7 @@ auto Spr_study_builder::seed_fill_from(Branch_index init_branch, int init_mut_id
     if (st == DPHY_ERR_INVALID_ARGUMENT) { throw std::invalid_argument(msg); }
     throw std::runtime_error(msg);
   }
+  if (compact) { for (auto& region : result) { region.branch = r.to_orig().at(region.branch); } }
   p.builder = this;
   cur_to_X_deltas = std::move(init_to_X_deltas);
 

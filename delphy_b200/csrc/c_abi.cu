@@ -382,10 +382,11 @@ void stream_copy(char* dst, const char* src, size_t n) {
   if (n) std::memcpy(dst, src, n);
 }
 
+// page-locked host memory or device memory: the copy engine can read it where it lies
 bool is_pinned_host(const void* p) {
   cudaPointerAttributes a{};
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeHost;
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice;
 }
 
 void sync_copy_streams(dphy_ctx* ctx) {
@@ -430,7 +431,7 @@ int staged_upload(dphy_ctx* ctx, char* pinned, std::vector<CopyJob>& jobs, char*
       for (int i = 0; i < kS; ++i) if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_streams[i], ctx->ev_main, 0);
       int flip = 0;
       auto copy = [&](char* dst, const void* src, size_t bytes) {
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_streams[flip++ % kS]);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->copy_streams[flip++ % kS]);
       };
       auto close_group = [&](cudaEvent_t ev) {   // ev fires once every copy stream has drained what was issued so far
         for (int i = 1; i < kS; ++i) {
@@ -559,11 +560,15 @@ int flatten_status_to_error(dphy_ctx* ctx, uint32_t bits) {
 
 }  // namespace
 
-int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* trees, const int32_t* sites_index,
-                       int32_t num_sites_tables, dphy_sites* const* sites, dphy_forest** out) {
+static int forest_upload_impl(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* trees, const TreeTotals* totals, const int32_t* sites_index,
+                              int32_t num_sites_tables, dphy_sites* const* sites, dphy_forest** out) {
   if (!ctx || !out || num_trees < 0 || (num_trees > 0 && (!trees || !sites)) || num_sites_tables <= 0) return DPHY_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   cudaSetDevice(ctx->device);
+  auto tot_m = [&](int k) -> int64_t { return totals ? totals[k].m : trees[k].mut_off[trees[k].num_nodes]; };
+  auto tot_iv = [&](int k) -> int64_t { return totals ? totals[k].iv : trees[k].miss_off[trees[k].num_nodes]; };
+  auto tot_fs = [&](int k) -> int64_t { return totals ? totals[k].fs : trees[k].fs_off[trees[k].num_nodes]; };
+  auto tot_root_m = [&](int k) -> int64_t { return totals ? totals[k].root_m : trees[k].mut_off[trees[k].root + 1] - trees[k].mut_off[trees[k].root]; };
   int64_t N = 0, M = 0, I = 0, F = 0, tiles = 0, ctiles = 0, Mnr = 0;
   int max_tree_nodes = 0;
   for (int k = 0; k < num_trees; ++k) {
@@ -573,10 +578,10 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     const int si = sites_index ? sites_index[k] : 0;
     if (si < 0 || si >= num_sites_tables) return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "sites_index out of range");
     const int n = e.num_nodes;
-    if (e.mut_off[n] < 0 || e.miss_off[n] < 0 || e.fs_off[n] < 0 || e.mut_off[e.root + 1] < e.mut_off[e.root])
+    if (tot_m(k) < 0 || tot_iv(k) < 0 || tot_fs(k) < 0 || tot_root_m(k) < 0)
       return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "CSR offsets are not monotone");
-    N += n; M += e.mut_off[n]; I += e.miss_off[n]; F += e.fs_off[n];
-    Mnr += e.mut_off[n] - (e.mut_off[e.root + 1] - e.mut_off[e.root]);
+    N += n; M += tot_m(k); I += tot_iv(k); F += tot_fs(k);
+    Mnr += tot_m(k) - tot_root_m(k);
     tiles += (n + kTile - 1) / kTile;
     ctiles += (n + kLgTile - 1) / kLgTile;
     max_tree_nodes = std::max(max_tree_nodes, n);
@@ -645,31 +650,36 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
     r.t = tmp.reserve(8 * n); r.moff = tmp.reserve(4 * (n + 1)); r.ioff = tmp.reserve(4 * (n + 1)); r.foff = tmp.reserve(4 * (n + 1));
   }
   for (int k = 0; k < num_trees; ++k) {
-    const auto& e = trees[k];
-    const size_t n = e.num_nodes, m = e.mut_off[n], iv = e.miss_off[n], fs = e.fs_off[n];
+    const size_t m = tot_m(k), iv = tot_iv(k), fs = tot_fs(k);
     RawIds& r = rid[k];
     r.msite = tmp.reserve(4 * m); r.mfrom = tmp.reserve(m); r.mto = tmp.reserve(m); r.mt = tmp.reserve(8 * m);
     r.is = tmp.reserve(4 * iv); r.ie = tmp.reserve(4 * iv);
     r.fsite = tmp.reserve(4 * fs); r.ffrom = tmp.reserve(fs);
   }
   const size_t raw_upload_bytes = tmp.total;
-  const int w_arcs0 = tmp.reserve(sizeof(int4) * 2 * N), w_arcs1 = tmp.reserve(sizeof(int4) * 2 * N);
+  // the raw (host-order) arrays stay resident next to the flattened forest: dphy_forest_apply_rows patches them on the device and
+  // re-flattens from there, so an edited tree never crosses PCIe again.  The flatten workspaces live in their own block, freed below.
+  Slab work;
+  const int w_arcs0 = work.reserve(sizeof(int4) * 2 * N), w_arcs1 = work.reserve(sizeof(int4) * 2 * N);
   const int64_t scan_tiles = (N + 1023) / 1024;
-  const int w_scan = tmp.reserve(sizeof(int32_t) * 3 * scan_tiles);
-  const int w_status = tmp.reserve(sizeof(uint32_t) * 4 + sizeof(int32_t) * num_trees);
+  const int w_scan = work.reserve(sizeof(int32_t) * 3 * scan_tiles);
+  const int w_status = work.reserve(sizeof(uint32_t) * 4 + sizeof(int32_t) * num_trees);
 
-  char* dbase = nullptr; char* tbase = nullptr;
+  char* dbase = nullptr; char* tbase = nullptr; char* wbase = nullptr;
   if (cudaMallocAsync((void**)&dbase, slab.total, ctx->stream) != cudaSuccess) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(forest)"); }
   if (cudaMallocAsync((void**)&tbase, tmp.total, ctx->stream) != cudaSuccess) {
-    cudaFreeAsync(dbase, ctx->stream); delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(forest staging)");
+    cudaFreeAsync(dbase, ctx->stream); delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(forest raw arrays)");
+  }
+  if (cudaMallocAsync((void**)&wbase, work.total, ctx->stream) != cudaSuccess) {
+    cudaFreeAsync(tbase, ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(forest workspace)");
   }
   fo->allocs.push_back(dbase);
   fo->bytes = slab.total;
   if (ensure_copy_stream(ctx) != DPHY_OK || cudaEventRecord(ctx->ev_main, ctx->stream) != cudaSuccess) {
-    cudaFreeAsync(tbase, ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo;
+    cudaFreeAsync(wbase, ctx->stream); cudaFreeAsync(tbase, ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo;
     return set_error(ctx, DPHY_ERR_CUDA, "upload: copy stream / event");
   }
-  auto fail = [&](int st) { cudaFreeAsync(tbase, ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo; return st; };
+  auto fail = [&](int st) { cudaFreeAsync(wbase, ctx->stream); cudaFreeAsync(tbase, ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo; return st; };
 
   void* hbv = nullptr;
   int st = acquire_pinned(ctx, header_bytes + raw_upload_bytes, &hbv);
@@ -692,7 +702,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   for (int k = 0; k < num_trees; ++k) {
     const auto& e = trees[k];
     const int n = e.num_nodes;
-    const size_t m = e.mut_off[n], iv = e.miss_off[n], fs = e.fs_off[n];
+    const size_t m = tot_m(k), iv = tot_iv(k), fs = tot_fs(k);
     TreeDev& T = fo->trees[k];
     T.node_base = base; T.num_nodes = n; T.sites_id = sites_index ? sites_index[k] : 0; T.first_tile = tile_pos;
     T.num_tiles = (n + kTile - 1) / kTile; T.includes_run_root = e.includes_run_root; T.root_id = e.root; T.pad = 0;
@@ -725,7 +735,7 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
 
   cudaError_t ce = cudaMemcpyAsync(dbase, hb, header_bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (ce == cudaSuccess) ce = cudaMemsetAsync(dbase + header_bytes, 0, slab.total - header_bytes, ctx->stream);
-  if (ce == cudaSuccess) ce = cudaMemsetAsync(tbase + tmp.blocks[w_status].off, 0, tmp.blocks[w_status].bytes, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(wbase + work.blocks[w_status].off, 0, work.blocks[w_status].bytes, ctx->stream);
   if (ce != cudaSuccess) return fail(check_cuda(ctx, ce, "H2D forest header"));
   // the RawTreeDev records were written straight into the pinned slab above; everything in [0, raw_upload_bytes) not
   // covered by a job (those records, alignment gaps) is copied as it lies
@@ -768,9 +778,9 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   // ---- device side: Euler tour + list ranking -> DFS order; CSR offsets; lists ------------------------------------------
   FlattenParams P{};
   P.trees = h.trees; P.sites = h.sites; P.tile_tree = h.tile_tree; P.raw = tmp.at<RawTreeDev>(tbase, r_raw);
-  P.arcs[0] = tmp.at<int4>(tbase, w_arcs0); P.arcs[1] = tmp.at<int4>(tbase, w_arcs1);
-  P.scan_tiles = tmp.at<int32_t>(tbase, w_scan);
-  P.status = tmp.at<uint32_t>(tbase, w_status); P.max_depth = reinterpret_cast<int32_t*>(P.status + 4);
+  P.arcs[0] = work.at<int4>(wbase, w_arcs0); P.arcs[1] = work.at<int4>(wbase, w_arcs1);
+  P.scan_tiles = work.at<int32_t>(wbase, w_scan);
+  P.status = work.at<uint32_t>(wbase, w_status); P.max_depth = reinterpret_cast<int32_t*>(P.status + 4);
   P.strad_list = fo->d_strad_list;
   P.ctiles = const_cast<CTileDesc*>(h.ctiles); P.fast_ctiles = const_cast<int32_t*>(h.fast_ctiles);
   P.slow_ctiles = const_cast<int32_t*>(h.slow_ctiles); P.num_ctiles = (int32_t)ctiles;
@@ -822,17 +832,45 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
   if (st != DPHY_OK) return fail(st);
   for (int k = 0; k < num_trees; ++k) fo->tree_max_depth[k] = status[4 + k];
   fo->num_strad = status[1]; fo->num_fast_ctiles = status[2]; fo->num_slow_ctiles = status[3];
-  cudaFreeAsync(tbase, ctx->stream);
+  cudaFreeAsync(wbase, ctx->stream);
+  fo->allocs.push_back(tbase);                       // the raw arrays stay (freed with the forest)
+  fo->bytes += tmp.total;
+  fo->raw.assign(h_raw, h_raw + num_trees);          // device pointers of every tree's host-order arrays
+  fo->sites_index.resize(num_trees);
+  for (int k = 0; k < num_trees; ++k) fo->sites_index[k] = sites_index ? sites_index[k] : 0;
   // first evaluation.  Forests whose site rates are uniform take the folded schedule; the structure-only outputs (nsmn, the
   // num_muts tallies) then come from a general pass the first time a getter asks for them (ensure_struct_outputs)
   st = launch_log_G(ctx, fo);
-  if (st != DPHY_OK) { cudaStreamSynchronize(ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo; return st; }
+  if (st != DPHY_OK) { cudaStreamSynchronize(ctx->stream); cudaFreeAsync(tbase, ctx->stream); cudaFreeAsync(dbase, ctx->stream); delete fo; return st; }
   fo->evaluated = true;         // that pass is a complete evaluation under the current evo model
   fo->eval_version.resize(fo->sites.size());
   for (size_t i = 0; i < fo->sites.size(); ++i) fo->eval_version[i] = fo->sites[i]->version;
   *out = fo;
   return DPHY_OK;
 }
+
+int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* trees, const int32_t* sites_index,
+                       int32_t num_sites_tables, dphy_sites* const* sites, dphy_forest** out) {
+  return forest_upload_impl(ctx, num_trees, trees, nullptr, sites_index, num_sites_tables, sites, out);
+}
+
+}  // extern "C"
+
+// Re-flatten `fo` from device-resident host-order arrays (dphy_forest_apply_rows): a fresh forest is built by the upload path with
+// device sources, then swapped into the caller's handle; the old contents are released stream-ordered.  On failure `fo` is untouched.
+int dphy::rebuild_forest_from_device(dphy_ctx* ctx, dphy_forest* fo, const dphy_emat_host* trees, const TreeTotals* totals) {
+  dphy_forest* fresh = nullptr;
+  const std::vector<dphy_sites*> sites = fo->sites;
+  const std::vector<int32_t> si = fo->sites_index;
+  int st = forest_upload_impl(ctx, fo->h.num_trees, trees, totals, si.data(), (int32_t)sites.size(), sites.data(), &fresh);
+  if (st != DPHY_OK) return st;
+  fresh->cnt_mut = std::move(fo->cnt_mut); fresh->cnt_miss = std::move(fo->cnt_miss); fresh->cnt_fs = std::move(fo->cnt_fs);
+  std::swap(*fo, *fresh);
+  dphy_forest_destroy(ctx, fresh);
+  return DPHY_OK;
+}
+
+extern "C" {
 
 void dphy_forest_destroy(dphy_ctx* ctx, dphy_forest* fo) {
   if (!fo) return;
@@ -873,6 +911,7 @@ int dphy_forest_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int
   if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(d_vals, t, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream), "H2D");
   if (st == DPHY_OK) st = check_cuda(ctx, cudaMemsetAsync(d_status, 0, sizeof(uint32_t), ctx->stream), "memset");
   if (st == DPHY_OK) st = launch_set_node_times(ctx, fo, tree, d_nodes, d_vals, count, d_status);
+  if (st == DPHY_OK) st = launch_raw_set_node_times(ctx, fo, tree, d_nodes, d_vals, count);   // the resident host-order copy follows
   if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(&status, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream), "D2H");
   if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "set_node_times");
   ctx->arena.release(mark);

@@ -220,6 +220,11 @@ struct dphy_forest {
   std::vector<int64_t> tree_muts;     // mutations per tree (incl. the root's list)
   std::vector<int64_t> tree_fs;       // from-state overrides per tree
   std::vector<int32_t> tree_max_depth;
+  // host-order arrays of every tree, resident on the device (what dphy_forest_apply_rows patches and re-flattens from)
+  std::vector<dphy::RawTreeDev> raw;
+  std::vector<int32_t> sites_index;
+  // per-node list lengths in host order, mirrored on the host the first time rows are applied: [tree] -> {mut, miss, fs} counts
+  std::vector<std::vector<int32_t>> cnt_mut, cnt_miss, cnt_fs;
   // outputs of the last eval (device)
   double* d_lambda = nullptr;   // [num_nodes] device order
   int32_t* d_nsmn = nullptr;    // [num_nodes]
@@ -250,6 +255,10 @@ struct dphy_forest {
 };
 
 namespace dphy {
+// List totals of one tree whose arrays are NOT host-readable (device-resident sources of dphy_forest_apply_rows).
+struct TreeTotals { int64_t m, iv, fs, root_m; };
+int rebuild_forest_from_device(dphy_ctx* ctx, dphy_forest* fo, const dphy_emat_host* trees, const TreeTotals* totals);   // c_abi.cu
+int launch_raw_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count);   // kernels_delta.cu
 int set_error(dphy_ctx* ctx, int status, const std::string& msg);
 int check_cuda(dphy_ctx* ctx, cudaError_t e, const char* what);
 #define DPHY_CUDA(ctx, expr) do { int st__ = dphy::check_cuda((ctx), (expr), #expr); if (st__ != DPHY_OK) return st__; } while (0)

@@ -215,6 +215,27 @@ int64_t dphy_forest_log_G_algorithmic_bytes(const dphy_forest* forest);
 int  dphy_forest_set_node_times(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, int32_t count,
                                 const int32_t* nodes, const double* t);
 
+/* ---- incremental edits (device-resident) --------------------------------------------------------------
+ * One changed node of one tree: its new links, time and lists (the whole row).  What the reference's in-place edits change:
+ * a branch-reform move = one row (core/subrun.cpp:316-319); an SPR move = the rows of X, P, G, the old and the new sibling and its
+ * old parent, plus the nodes of the hot path whose lists peel_graft / apply_graft rewrite (core/spr_move.cpp:838-1156). */
+typedef struct dphy_node_row {
+  int32_t tree;                 /* index of the EMAT inside the forest */
+  int32_t node;                 /* host node index */
+  int32_t parent, child0, child1;   /* -1 == k_no_node */
+  int32_t n_muts, n_miss, n_fs;
+  double  t;
+  const int32_t* mut_site; const uint8_t* mut_from; const uint8_t* mut_to; const double* mut_t;
+  const int32_t* miss_start; const int32_t* miss_end;
+  const int32_t* fs_site; const uint8_t* fs_from;
+} dphy_node_row;
+/* Replace `count` rows and (new_roots != NULL) set every tree's root (new_roots[num_trees]).  Only the rows cross PCIe: the
+ * host-order arrays of every tree stay resident on the device, the edited trees' arrays are rebuilt there and the forest is
+ * re-flattened from them with the validation of an upload (DPHY_ERR_INVALID_ARGUMENT for a broken topology / times, the forest
+ * is then unchanged).  Results are those of a fresh dphy_forest_upload of the edited trees.  SPR batches made before the call
+ * refer to the old forest and must be destroyed first. */
+int  dphy_forest_apply_rows(dphy_ctx* ctx, dphy_forest* forest, int32_t count, const dphy_node_row* rows, const int32_t* new_roots);
+
 /* ---- log G ------------------------------------------------------------------------------------------- */
 /* One launch evaluates, for EVERY tree of the forest: calc_lambda_i (core/phylo_tree_calc.cpp:420-436),
  * calc_num_sites_missing_at_every_node (:67-76), calc_log_root_prior (:467-504) and calc_log_G_below_root

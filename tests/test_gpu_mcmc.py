@@ -67,3 +67,21 @@ def test_posterior_summaries_agree_with_the_stock_build(maple_cfg1):
         assert abs(a["mean"] - b["mean"]) <= 4.0 * err + 1e-12, (key, a, b)
     # and the truth the alignment was simulated with is recovered: mu = 1.39e-3 /site/yr, tips span 2020-07..2021-01
     assert 1.0 < runs["dropin"]["mu"]["mean"] < 2.2
+
+
+def test_usher_like_initial_tree_through_the_drop_in(tmp_path):
+    """build_usher_like_tree (core/phylo_tree.cpp:796-1047): one full-tree SPR study of a sequence that is not in the tree
+    (X == k_no_node) per tip, over the tree built so far -- every one of them on the device in the substituted build, each re-run
+    by the reference's builder (DPHY_DROPIN_VERIFY).  The resulting initial trees must coincide with the stock build's."""
+    _need_binaries()
+    emat, sites, info = db.synth_generate(db.synth_params(3, num_tips=600))
+    path = str(tmp_path / "t600.maple")
+    write_maple(emat, sites, path, info["t_max_tip"])
+    args = ["--v0-init", "old-usher-like"]
+    a = mcmc.run_cli(mcmc.DROPIN_CLI, path, 2000, threads=1, seed=9, log_every=1000, extra_args=args, env=dict(DPHY_DROPIN_VERIFY=1), timeout=900)
+    b = mcmc.run_cli(mcmc.STOCK_CLI, path, 2000, threads=1, seed=9, log_every=1000, extra_args=args, timeout=900)
+    assert a["returncode"] == 0, "\n".join(a["stderr_tail"])
+    assert b["returncode"] == 0, "\n".join(b["stderr_tail"])
+    s0a, s0b = a["samples"][0], b["samples"][0]
+    assert s0a["step"] == 0 and s0a["num_muts"] == s0b["num_muts"]
+    assert s0a["log_G"] == pytest.approx(s0b["log_G"], abs=0.02) and s0a["T"] == pytest.approx(s0b["T"], abs=0.02)
