@@ -54,6 +54,10 @@ struct SprStudy {
   int32_t total_regions, pad1;
   unsigned long long max_key;
   double log_Wmax, sum_W;
+  // ---- layout of the tree prefix sums H / KB (and of their per-tile aggregates) ----
+  // per-study path: one int per node (h_stride 1), tiles of kTile nodes (tile_shift 8);
+  // grouped path (spr_gscan / spr_gemit, 32 studies of one tree side by side): [node][32] (h_stride 32), chunks of 32 nodes (tile_shift 5)
+  int32_t h_stride, tile_shift, num_htiles, weights_fused;
 };
 
 // Device-side form of a candidate region: the reference's 48-byte Candidate_region (core/spr_study.h:17-32) split into a 32-byte
@@ -290,9 +294,10 @@ struct SprView {
   const int32_t* agg;          // [num_tiles + 1][3]
   const int32_t* path; const int2* pae; const int32_t* seg;
   int node_base, path_len;
-  __device__ __forceinline__ int H(int q) const { return Hloc[q] + agg[(q / kTile) * 3 + 0]; }
-  __device__ __forceinline__ int C(int q) const { return Cloc[q] + agg[(q / kTile) * 3 + 1]; }
-  __device__ __forceinline__ int KB(int q) const { return KBloc[q] + agg[(q / kTile) * 3 + 2]; }
+  int stride, shift;           // SprStudy::h_stride / tile_shift
+  __device__ __forceinline__ int H(int q) const { return Hloc[(size_t)q * stride] + agg[(q >> shift) * 3 + 0]; }
+  __device__ __forceinline__ int C(int q) const { return Cloc[(size_t)q * stride] + agg[(q >> shift) * 3 + 1]; }
+  __device__ __forceinline__ int KB(int q) const { return KBloc[(size_t)q * stride] + agg[(q >> shift) * 3 + 2]; }
 };
 
 __device__ __forceinline__ SprView make_view(const SprBatchDev& B, const SprStudy& S, int study) {
@@ -306,6 +311,7 @@ __device__ __forceinline__ SprView make_view(const SprBatchDev& B, const SprStud
   V.pae = (const int2*)(B.slab + S.off_pae);
   V.seg = (const int32_t*)(B.slab + S.off_seg);
   V.node_base = S.node_base; V.path_len = S.path_len;
+  V.stride = S.h_stride; V.shift = S.tile_shift;
   return V;
 }
 
@@ -441,7 +447,7 @@ __global__ void __launch_bounds__(kTile) spr_scan_kernel(ForestDev f, SprBatchDe
   const int t0 = blockIdx.x * kScanSub;          // first tile of this CTA
   {
     const SprStudy& G = B.studies[study];
-    if (t0 >= G.num_tiles || G.error) return;
+    if (t0 >= G.num_tiles || G.error || G.h_stride != 1) return;     // grouped studies are scanned by spr_gscan_kernel
     if (kPhase == 1 && G.limit == INT_MAX) return;
     const int* src = reinterpret_cast<const int*>(&G);
     int* dst = reinterpret_cast<int*>(&sm.S);
@@ -566,7 +572,7 @@ __device__ void spr_tile_prefix(const ForestDev& f, SprBatchDev& B, SprStudy& S,
   __syncthreads();
   if (todo == 0) return;
   int32_t* agg = B.tile_agg + (size_t)study * (B.max_tiles + 1) * 3;
-  const int nt = S.num_tiles;
+  const int nt = S.num_htiles;
   for (int comp = 0; comp < 3; ++comp) {
     if (!((comp < 2 ? 1 : 2) & todo)) continue;
     if (tid == 0) *s_carry = 0;
@@ -610,6 +616,51 @@ __global__ void __launch_bounds__(kSetupThreads) spr_tile_prefix_kernel(ForestDe
   SprStudy& S = B.studies[blockIdx.x];
   if (S.error) return;
   spr_tile_prefix(f, B, S, blockIdx.x, S.limit != INT_MAX ? 1 : 3, s_ws, &s_carry);
+}
+
+// ---- per-node emission under the general rules (grouped path: the root, P, S and the nodes of the start->root path) ------------------------
+struct GLane {            // what a study carries through the grouped emit
+  RegionHead* out;
+  const int2* pae; const int32_t* seg;
+  const int32_t* agg;
+  int region_cap, path_len, H0, init_min_muts;
+  double tX;
+};
+
+__device__ __forceinline__ void g_store_region(const GLane& L, int idx, int branch, int mut_idx, double t_min, double t_max, int m) {
+  if (idx >= 0 && idx < L.region_cap) {
+    // one 256-bit store per record (STG.256): in the grouped emit each lane writes into its own study's array, so every store
+    // instruction of the warp touches 32 different lines -- halving the instructions halves the LSU wavefronts
+    const unsigned long long w0 = (unsigned long long)(unsigned)branch | ((unsigned long long)(unsigned)mut_idx << 32);
+    const unsigned long long w3 = (unsigned long long)(unsigned)m;
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(L.out + idx), "l"(w0), "l"(__double_as_longlong(t_min)),
+                 "l"(__double_as_longlong(t_max)), "l"(w3) : "memory");
+  }
+}
+
+// Same arithmetic as the per-study emit kernel (eval_region + the segment bases), walking the node's regions in order.
+// sg = the segment record of path index j = classify(p).
+__device__ void g_emit_node_general(const ForestDev& f, const SprStudy& S, const SprView& V, const GLane& L, int p, const int32_t* sg, int j, bool on_path) {
+  const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
+  const int par = f.parent_pos[p];
+  const bool is_root = p == S.root_pos;
+  const double tNode = f.t[p], tPar = par >= 0 ? f.t[par] : 0.0;
+  int Hk = is_root ? 0 : V.H(par - S.node_base);
+  const int kA = (j == 0) ? S.k0 : np;
+  int n_up = 0, n_own = 0, rank = 0;
+  const int base_off = on_path ? 0 : sg[2] - V.KB(sg[5] - S.node_base) + V.KB(p - S.node_base);
+  for (int k = is_root ? np : 0; k <= np; ++k) {
+    const RegionEval r = eval_region(f, S, p, k, np, moff, tPar, tNode);
+    if (r.keep) {
+      int idx;
+      if (!on_path) idx = base_off + rank++;
+      else if (k == kA) idx = sg[0];
+      else if (k > kA) idx = sg[1] + n_own++;
+      else idx = sg[3] + (sg[4] - 1 - n_up++);
+      g_store_region(L, idx, r.branch, r.mut_idx, r.t_min, r.t_max, L.init_min_muts + (Hk - L.H0));
+    }
+    if (k < np && !is_root) { int dh, dc; mut_dc(V.xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc); Hk += dh; }
+  }
 }
 
 // ---- (3) segment bases along the start->root path ---------------------------------------------------------------------------------------
@@ -666,19 +717,67 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
       int32_t* sg = seg + (size_t)j * kSegStride;
       sg[0] = base; sg[1] = base + cntA; sg[2] = base + cntA + cntOwn; sg[3] = base + cntA + cntOwn + cntSub;
       sg[4] = cntUp; sg[5] = sibpos;
+      if (S.h_stride != 1) {
+        // grouped studies: the path nodes' own regions are written here, one thread per path node (spr_gemit_kernel skips them)
+        GLane L;
+        L.out = (RegionHead*)(B.slab + S.off_regions); L.pae = V.pae; L.seg = V.seg; L.agg = V.agg;
+        L.region_cap = S.region_cap; L.path_len = S.path_len; L.H0 = S.H0; L.init_min_muts = S.init_min_muts; L.tX = S.t_X;
+        g_emit_node_general(f, S, V, L, V.path[j], sg, j, true);
+      }
     }
     __syncthreads();
     if (tid == 0) s_carry += btot;
     __syncthreads();
   }
   if (tid == 0) S.total_regions = s_carry;
+  if (S.h_stride != 1 && tid < 2) {
+    // ... and so are S and P when they are not on the path (their regions are relabelled by account_for_Xs_detachment)
+    const int p = tid == 0 ? S.posS : S.posP;
+    if (p >= 0 && !(tid == 1 && S.posP == S.posS)) {
+      const int j = classify(V, p);
+      if (V.path[j] != p) {
+        GLane L;
+        L.out = (RegionHead*)(B.slab + S.off_regions); L.pae = V.pae; L.seg = V.seg; L.agg = V.agg;
+        L.region_cap = S.region_cap; L.path_len = S.path_len; L.H0 = S.H0; L.init_min_muts = S.init_min_muts; L.tX = S.t_X;
+        g_emit_node_general(f, S, V, L, p, seg + (size_t)j * kSegStride, j, false);
+      }
+    }
+  }
   // classify() of the first and the last node of every tile: the deepest path node containing p is monotone in p on either side
   // of the start node, so these bracket the search of every node of the tile (spr_emit_kernel)
   int2* tj = (int2*)(B.slab + S.off_tj);
+  if (S.h_stride == 1)
   for (int t = tid; t < S.num_tiles; t += kSetupThreads) {
     const int first = S.node_base + t * kTile, last = min(first + kTile, S.node_base + S.num_nodes) - 1;
     tj[t] = make_int2(classify(V, first), classify(V, last));
   }
+}
+
+// ---- fp64 log for the region weights -----------------------------------------------------------------------------------------------------
+// Two logs per candidate region are most of the arithmetic of the weight pass (the library routine is ~100 instructions).  The
+// weights are compared at 1e-9 relative (BASELINE.json north_star), so a 128-entry table of (1/c, log c) over the mantissa's top
+// 7 bits + a degree-6 polynomial of r = m/c - 1 (|r| <= 2^-8, truncation 2^-56) + a two-part ln 2 is ample: absolute error
+// < 5e-16 on [1e-12, 1e3], ~1e-15 relative to a weight exponent of O(10).  Zero, denormal, infinite, NaN and negative arguments go to
+// the library routine, so -inf for an empty region is preserved (core/spr_study.cpp:318).
+constexpr int kLogTabBits = 7;
+__device__ __forceinline__ void fill_log_table(double2* tab) {
+  for (int i = threadIdx.x; i < (1 << kLogTabBits); i += blockDim.x) {
+    const double c = 1.0 + (i + 0.5) / (double)(1 << kLogTabBits);
+    tab[i] = make_double2(1.0 / c, log(c));
+  }
+}
+__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
+  const long long b = __double_as_longlong(x);
+  const int hi = (int)(b >> 32);
+  const int ex = (hi >> 20) & 0x7ff;
+  if (ex == 0 || ex == 0x7ff || hi < 0) return log(x);
+  const double2 tc = tab[(hi >> (20 - kLogTabBits)) & ((1 << kLogTabBits) - 1)];
+  const double m = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double r = fma(m, tc.x, -1.0);
+  double p = fma(r, -1.0 / 6.0, 0.2);
+  p = fma(r, p, -0.25); p = fma(r, p, 1.0 / 3.0); p = fma(r, p, -0.5); p = fma(r, p, 1.0);
+  const double e = (double)(ex - 1023);
+  return fma(e, 6.93147180369123816490e-01, fma(e, 1.90821492927058770002e-10, fma(r, p, tc.y)));
 }
 
 // ---- (4) emit regions in the reference's DFS order, with raw log-weights ------------------------------------------------------------------
@@ -739,7 +838,7 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) spr_emit_kernel(ForestDev f
   const int t0 = blockIdx.x * kEmitSub;        // first kTile-tile of this CTA
   {
     const SprStudy& G = B.studies[study];
-    if (t0 >= G.num_tiles || G.error) return;
+    if (t0 >= G.num_tiles || G.error || G.h_stride != 1) return;     // grouped studies are emitted by spr_gemit_kernel
     const int* src = reinterpret_cast<const int*>(&G);
     int* dst = reinterpret_cast<int*>(&sm.S);
     for (int i = threadIdx.x; i < (int)(sizeof(SprStudy) / sizeof(int)); i += kTile) dst[i] = src[i];
@@ -894,9 +993,12 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) spr_emit_kernel(ForestDev f
 constexpr int kWeightBlocks = 128;
 __global__ void __launch_bounds__(256) spr_weights_kernel(ForestDev f, SprBatchDev B) {
   __shared__ double s_ws[8];
+  __shared__ double2 s_log[1 << kLogTabBits];
+  fill_log_table(s_log);
+  __syncthreads();
   const int study = blockIdx.y;
   const SprStudy& S = B.studies[study];
-  if (S.error || !(S.lambda_X > 0.0)) return;
+  if (S.error || !(S.lambda_X > 0.0) || S.weights_fused) return;
   const int n = min(S.total_regions, S.region_cap);
   const int4* heads = (const int4*)(B.slab + S.off_regions);
   double* lw_out = (double*)(B.slab + S.off_lw);
@@ -907,9 +1009,14 @@ __global__ void __launch_bounds__(256) spr_weights_kernel(ForestDev f, SprBatchD
     const int4 a = __ldg(heads + 2 * (size_t)i), b = __ldg(heads + 2 * (size_t)i + 1);
     const double t_min = __hiloint2double(a.w, a.z), t_max = __hiloint2double(b.y, b.x);
     const int m = b.z;
-    double tS = 0.0;
-    if (t_min == -DBL_MAX) tS = f.t[S.node_base + f.pos_of_node[S.node_base + a.x]];
-    const double lw = region_log_W(S, t_min, t_max, m, tS);
+    double lw;
+    if (t_min != -DBL_MAX) {
+      // core/spr_study.cpp:313-318
+      const double fa = S.f, lam = S.lambda_X, t_prime = 0.5 * (t_min + t_max);
+      lw = fast_log(fa * lam * (t_max - t_min), s_log) + fa * (-lam * (S.t_X - t_prime) + m * fast_log(S.mu * (S.t_X - t_prime) / 3, s_log));
+    } else {
+      lw = region_log_W_above_root(S.f, S.lambda_X, S.mu, S.t_X, S.t_max_tip, m, f.t[S.node_base + f.pos_of_node[S.node_base + a.x]]);
+    }
     lw_out[i] = lw;
     wmax = any ? fmax(wmax, lw) : lw;   // std::max semantics of the reference's running maximum
     any = true;
@@ -932,6 +1039,7 @@ __global__ void spr_set_weight_params_kernel(ForestDev f, SprBatchDev B, const d
   S.lambda_X = wp[3 * i]; S.f = wp[3 * i + 1]; S.t_max_tip = wp[3 * i + 2];
   S.mu = S.lambda_X / (double)(S.L - S.num_missing);
   S.max_key = 0ULL; S.log_Wmax = 0.0; S.sum_W = 0.0;
+  S.weights_fused = 0;      // the weights pass over the stored heads does it this time
 }
 
 // ---- (5) normalise: log_W_over_Wmax -= log_Wmax; W = exp(.); sum in a fixed order ------------------------------------------------------------
@@ -972,6 +1080,8 @@ __global__ void __launch_bounds__(256) spr_normalize_kernel(SprBatchDev B) {
     B.ticket[study * 4 + 2] = 0u;
   }
 }
+
+#include "kernels_spr_group.cuh"
 
 // ---- pick_nexus_region / find_region ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) spr_pick_kernel(SprBatchDev B, const double* __restrict__ r_in, int32_t* __restrict__ out_idx) {
@@ -1070,6 +1180,7 @@ struct dphy_spr_batch {
   int32_t num = 0;
   std::vector<SprStudy> host;     // filled by get_summaries
   bool fetched = false;
+  SprGroupDev* d_groups = nullptr; int32_t num_groups = 0, group_chunks = 0;
   bool weighted = false;          // spr_weights_kernel + spr_normalize_kernel have run for the current (lambda_X, f, t_max_tip)
   int status = DPHY_OK;           // sticky: the first per-study error found by spr_fetch, returned by every accessor
   std::string status_msg;
@@ -1092,10 +1203,45 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   if (!b) return DPHY_ERR_OUT_OF_MEMORY;
   b->num = n; b->forest = fo;
   b->host.resize(n);
-  int max_tiles = 1;
+  int max_tiles = 1, max_tiles256 = 0;
   size_t off = 0;
   std::vector<std::pair<size_t, const void*>> copies;   // (slab offset, host ptr) with sizes below
   std::vector<size_t> copy_bytes;
+  // ---- grouping: full (unbounded) studies of the same tree go 32 at a time through the lanes-are-studies kernels ----------------
+  // (DPHY_SPR_GROUPED=0 disables)
+  constexpr int kMinGroup = 24;     // a group costs the same for 1 or 32 lanes: below ~24 studies the per-study kernels are cheaper
+  static const bool use_groups = [] { const char* e = getenv("DPHY_SPR_GROUPED"); return !(e && atoi(e) == 0); }();
+  std::vector<int> group_of(n, -1), lane_of(n, 0);
+  std::vector<SprGroupDev> groups;
+  if (use_groups) {
+    std::vector<std::vector<int>> by_tree(fo->h.num_trees);
+    for (int i = 0; i < n; ++i)
+      if (reqs[i].tree >= 0 && reqs[i].tree < fo->h.num_trees && reqs[i].max_muts_from_start == INT_MAX) by_tree[reqs[i].tree].push_back(i);
+    std::vector<int64_t> mut_base(fo->h.num_trees + 1, 0);
+    for (int k = 0; k < fo->h.num_trees; ++k) mut_base[k + 1] = mut_base[k] + fo->tree_muts[k];
+    for (int k = 0; k < fo->h.num_trees; ++k) {
+      const auto& v = by_tree[k];
+      for (size_t g0 = 0; g0 < v.size(); g0 += kGroup) {
+        if ((int)(v.size() - g0) < kMinGroup) break;       // a thin remainder goes study by study
+        SprGroupDev G;
+        std::memset(&G, 0, sizeof(G));
+        const TreeDev& T = fo->trees[k];
+        G.tree = k; G.node_base = T.node_base; G.num_nodes = T.num_nodes; G.L = fo->sites[T.sites_id]->L;
+        G.mut_base = (int32_t)mut_base[k]; G.num_chunks = (T.num_nodes + kGChunk - 1) / kGChunk;
+        G.num = (int32_t)std::min<size_t>(kGroup, v.size() - g0);
+        for (int l = 0; l < G.num; ++l) { G.study[l] = v[g0 + l]; group_of[v[g0 + l]] = (int)groups.size(); lane_of[v[g0 + l]] = l; }
+        G.off_xT = off; off = al(off + (size_t)G.L * kGroup);
+        G.off_dhT = off; off = al(off + (size_t)std::max<int64_t>(1, fo->tree_muts[k]) * kGroup);
+        G.off_dhP = off; off = al(off + sizeof(unsigned long long) * ((size_t)fo->tree_muts[k] / 32 + 4) * kGroup);
+        G.off_H = off; off = al(off + sizeof(int32_t) * (size_t)T.num_nodes * kGroup);
+        G.off_KB = off; off = al(off + sizeof(int32_t) * ((size_t)T.num_nodes + 1) * kGroup);
+        groups.push_back(G);
+      }
+    }
+  }
+  // (raw log-weights inside the grouped emit were measured slower than the dense weights pass over the stored heads: the two logs
+  // per region then run at the emit's ~45 % lane utilisation and low occupancy, 1.26 ms vs 0.68 + 0.23 ms per 128 studies)
+  const bool fuse_weights = false;
   for (int i = 0; i < n; ++i) {
     const dphy_spr_request& r = reqs[i];
     SprStudy& S = b->host[i];
@@ -1122,8 +1268,13 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
       if (r.x_delta_site[k] < 0 || r.x_delta_site[k] >= L || r.x_delta_to[k] > 3) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: X delta out of range"); }
     for (int k = 0; k < S.n_x_missing; ++k)
       if (r.x_missing_start[k] < 0 || r.x_missing_end[k] > L || r.x_missing_start[k] >= r.x_missing_end[k]) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: X missing interval out of range"); }
-    max_tiles = std::max(max_tiles, T.num_tiles);
     const int N = T.num_nodes;
+    const bool grouped = group_of[i] >= 0;
+    S.h_stride = grouped ? kGroup : 1; S.tile_shift = grouped ? 5 : 8;
+    S.num_htiles = grouped ? (N + kGChunk - 1) / kGChunk : T.num_tiles;
+    S.weights_fused = (grouped && fuse_weights) ? 1 : 0;
+    max_tiles = std::max(max_tiles, S.num_htiles);
+    if (!grouped) max_tiles256 = std::max(max_tiles256, T.num_tiles);
     // exact upper bound on regions: every non-root node has n+1 regions, the root has 1
     const int64_t cap64 = (int64_t)N + fo->tree_muts[r.tree] + 1;
     if (cap64 > INT_MAX) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: region capacity overflow"); }
@@ -1134,9 +1285,14 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     S.off_path = off; off = al(off + sizeof(int32_t) * S.path_cap);
     S.off_xpath = off; off = al(off + sizeof(int32_t) * S.path_cap);
     S.off_pae = off; off = al(off + sizeof(int2) * S.path_cap);
-    S.off_H = off; off = al(off + sizeof(int32_t) * N);
-    S.off_C = off; off = al(off + sizeof(int32_t) * N);
-    S.off_KB = off; off = al(off + sizeof(int32_t) * (N + 1));
+    if (grouped) {
+      const SprGroupDev& G = groups[group_of[i]];
+      S.off_H = G.off_H + (int64_t)sizeof(int32_t) * lane_of[i]; S.off_C = S.off_H; S.off_KB = G.off_KB + (int64_t)sizeof(int32_t) * lane_of[i];
+    } else {
+      S.off_H = off; off = al(off + sizeof(int32_t) * N);
+      S.off_C = off; off = al(off + sizeof(int32_t) * N);
+      S.off_KB = off; off = al(off + sizeof(int32_t) * (N + 1));
+    }
     S.off_seg = off; off = al(off + sizeof(int32_t) * kSegStride * (size_t)S.path_cap);
     S.off_part = off; off = al(off + sizeof(double) * kNormBlocks);
     S.off_tj = off; off = al(off + sizeof(int2) * (size_t)T.num_tiles);       // classify() of the first / last node of every tile
@@ -1161,7 +1317,8 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   const size_t b_agg = al(b_studies + sizeof(SprStudy) * std::max(1, n));
   const size_t b_flag = al(b_agg + sizeof(int32_t) * 3 * ((size_t)max_tiles + 1) * std::max(1, n));
   const size_t b_ticket = al(b_flag + 256);
-  const size_t b_slab = al(b_ticket + sizeof(uint32_t) * 4 * std::max(1, n));
+  const size_t b_groups = al(b_ticket + sizeof(uint32_t) * 4 * std::max(1, n));
+  const size_t b_slab = al(b_groups + sizeof(SprGroupDev) * std::max<size_t>(1, groups.size()));
   const size_t total = b_slab + slab_bytes;
   char* d = nullptr;
   cudaError_t ce = cudaMallocAsync((void**)&d, total, ctx->stream);
@@ -1173,10 +1330,12 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   b->dev.ticket = (uint32_t*)(d + b_ticket);
   b->dev.slab = d + b_slab;
   b->dev.num_studies = n; b->dev.max_tiles = max_tiles; b->dev.epoch = 1;
+  { static const bool dry = [] { const char* e = getenv("DPHY_SPR_DRY"); return e && atoi(e) != 0; }(); if (dry) b->dev.epoch = 777u; }
+  b->d_groups = (SprGroupDev*)(d + b_groups); b->num_groups = (int32_t)groups.size();
   if (n == 0) { *out = b; return DPHY_OK; }
   // flags + tickets start at zero; studies + X overlays uploaded through the pinned staging buffer
-  ce = cudaMemsetAsync(d + b_flag, 0, b_slab - b_flag, ctx->stream);
-  size_t stage = sizeof(SprStudy) * n;
+  ce = cudaMemsetAsync(d + b_flag, 0, b_groups - b_flag, ctx->stream);
+  size_t stage = sizeof(SprStudy) * n + al(sizeof(SprGroupDev) * groups.size());
   for (size_t cb : copy_bytes) stage += al(cb);
   if (ce == cudaSuccess) {
     void* hbv = nullptr;
@@ -1186,6 +1345,11 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     std::memcpy(hb, b->host.data(), sizeof(SprStudy) * n);
     ce = cudaMemcpyAsync(b->dev.studies, hb, sizeof(SprStudy) * n, cudaMemcpyHostToDevice, ctx->stream);
     size_t so = sizeof(SprStudy) * n;
+    if (!groups.empty() && ce == cudaSuccess) {
+      std::memcpy(hb + so, groups.data(), sizeof(SprGroupDev) * groups.size());
+      ce = cudaMemcpyAsync(b->d_groups, hb + so, sizeof(SprGroupDev) * groups.size(), cudaMemcpyHostToDevice, ctx->stream);
+      so += al(sizeof(SprGroupDev) * groups.size());
+    }
     for (size_t k = 0; k < copies.size() && ce == cudaSuccess; ++k) {
       std::memcpy(hb + so, copies[k].second, copy_bytes[k]);
       ce = cudaMemcpyAsync(b->dev.slab + copies[k].first, hb + so, copy_bytes[k], cudaMemcpyHostToDevice, ctx->stream);
@@ -1194,37 +1358,55 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     release_pinned_async(ctx);
   }
   if (ce != cudaSuccess) { cudaFreeAsync(d, ctx->stream); delete b; return check_cuda(ctx, ce, "spr batch upload"); }
-  const dim3 grid_tiles(max_tiles, n);
-  int max_nodes = 1;
+  int max_nodes = 1, group_chunks = 0, group_L = 1;
   for (int i = 0; i < n; ++i) max_nodes = std::max(max_nodes, fo->trees[reqs[i].tree].num_nodes);
+  for (const SprGroupDev& G : groups) { group_chunks = std::max(group_chunks, G.num_chunks); group_L = std::max(group_L, G.L); }
+  const int ng = (int)groups.size();
+  const bool any_single = max_tiles256 > 0;        // studies on the per-study path
   spr_paths_kernel<<<dim3((max_nodes + kSetupThreads * kPathChunks - 1) / (kSetupThreads * kPathChunks), n), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
   spr_xtab_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
-  const dim3 grid_scan((max_tiles + kScanSub - 1) / kScanSub, n);
-  spr_scan_kernel<0><<<grid_scan, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+  int launched = 2;
+  const dim3 grid_scan((std::max(max_tiles256, 1) + kScanSub - 1) / kScanSub, n);
+  if (any_single) { spr_scan_kernel<0><<<grid_scan, kTile, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
+  const dim3 grid_group((group_chunks + kGWarps - 1) / kGWarps, std::max(ng, 1));
+  if (ng > 0) {
+    for (const SprGroupDev& G : groups)      // the packed potentials are OR-ed together by the chunks that share a word
+      cudaMemsetAsync(b->dev.slab + G.off_dhP, 0, sizeof(unsigned long long) * ((size_t)fo->tree_muts[G.tree] / 32 + 4) * kGroup, ctx->stream);
+    spr_xT_kernel<<<dim3((group_L + 255) / 256, ng), 256, 0, ctx->stream>>>(b->dev, b->d_groups);
+    spr_gscan_kernel<<<grid_group, kGWarps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    launched += 2;
+  }
   bool any_limited = false;
   for (int i = 0; i < n; ++i) any_limited |= (b->host[i].limit != INT_MAX);
-  int launched = 3;
   if (any_limited) {
     spr_tile_prefix_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
     spr_scan_kernel<1><<<grid_scan, kTile, 0, ctx->stream>>>(fo->h, b->dev);
     launched += 2;
   }
   spr_segments_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
-  {
+  ++launched;
+  if (any_single) {
     // resident CTAs per SM (tuning knob DPHY_EMIT_OCC = 4 | 5 | 6; 64 / 48 / 40 registers)
     static const int occ = [] { const char* e = getenv("DPHY_EMIT_OCC"); return e ? atoi(e) : 4; }();
-    const dim3 grid_emit((max_tiles + kEmitSub - 1) / kEmitSub, n);
+    const dim3 grid_emit((max_tiles256 + kEmitSub - 1) / kEmitSub, n);
     if (occ == 5) spr_emit_kernel<5><<<grid_emit, kTile, 0, ctx->stream>>>(fo->h, b->dev);
     else if (occ == 6) spr_emit_kernel<6><<<grid_emit, kTile, 0, ctx->stream>>>(fo->h, b->dev);
     else spr_emit_kernel<4><<<grid_emit, kTile, 0, ctx->stream>>>(fo->h, b->dev);
+    ++launched;
   }
-  launched += 2;
-  bool any_weighted = false;
-  for (int i = 0; i < n; ++i) any_weighted |= b->host[i].lambda_X > 0.0;
+  if (ng > 0) {
+    spr_gemit_kernel<<<grid_group, kGWarps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    ++launched;
+  }
+  bool any_weighted = false, any_unfused = false;
+  for (int i = 0; i < n; ++i) {
+    any_weighted |= b->host[i].lambda_X > 0.0;
+    any_unfused |= b->host[i].lambda_X > 0.0 && !b->host[i].weights_fused;
+  }
   if (any_weighted) {
-    spr_weights_kernel<<<dim3(kWeightBlocks, n), 256, 0, ctx->stream>>>(fo->h, b->dev);
+    if (any_unfused) { spr_weights_kernel<<<dim3(kWeightBlocks, n), 256, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
     spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ctx->stream>>>(b->dev);
-    launched += 2;
+    ++launched;
     b->weighted = true;
   }
   ctx->launches += launched;
@@ -1252,6 +1434,7 @@ static int spr_fetch(dphy_ctx* ctx, dphy_spr_batch* b) {
     else if (b->host[i].error == 2) { st = DPHY_ERR_OUT_OF_RANGE; what = "start_mut_idx out of range for the start branch"; }
     else if (b->host[i].error == 3) { st = DPHY_ERR_INVALID_ARGUMENT; what = "start region lies inside X's subtree"; }
     else if (b->host[i].error == 4) { st = DPHY_ERR_INTERNAL; what = "more than 2^28 mutations on the root path"; }
+    else if (b->host[i].error == 5) { st = DPHY_ERR_INTERNAL; what = "more than 65535 candidate regions on 32 consecutive branches (set DPHY_SPR_GROUPED=0)"; }
     else if (b->host[i].total_regions > b->host[i].region_cap) { st = DPHY_ERR_INTERNAL; what = "region capacity exceeded"; }
     if (st != DPHY_OK) {
       // sticky: every later accessor of this batch (getters, pick, find) reports the same failure, naming the request
