@@ -68,7 +68,7 @@ def parse_args():
     ap.add_argument("--parts-per-gpu", type=int, default=2)
     ap.add_argument("--mcmc-tips", type=int, default=10000, help="tips of the second MCMC alignment (config 3 shape)")
     ap.add_argument("--mcmc-steps", type=int, default=200000)
-    ap.add_argument("--mcmc-threads-per-gpu", type=int, default=2)
+    ap.add_argument("--mcmc-threads-per-gpu", type=int, default=1)
     return ap.parse_args()
 
 

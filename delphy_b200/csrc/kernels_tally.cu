@@ -66,13 +66,27 @@ __global__ void __launch_bounds__(kTile) tally_branch_len_scan_kernel(ForestDev 
   if (p < T.node_base + T.num_nodes) PL[p - T.node_base] = s_prefix + incl;
 }
 
-// atomicAdd(base + idx, v) with the lanes of the warp that hit the same address combined first: interval end points pile up on a
-// few sites (every tip's 5' / 3' end gap starts at site 0 / ends at site L), and same-address atomics serialise in L2.
-__device__ __forceinline__ void warp_agg_atomic_add(double* base, int idx, double v) {
+// Order-independent fp64 accumulation.  The per-site tallies scatter ~(M + I + F) terms into L bins from all over the tree; fp64
+// atomicAdd would make the sums depend on the arrival order (not reproducible run to run, which a replayed Gibbs move would see).
+// Each term is split into its integer part and its fraction rounded to 2^-44, and both are accumulated with INTEGER atomics, which
+// commute exactly: the result is the exact sum of the rounded terms, whatever the order.  Error <= 2^-45 (3e-14, absolute) per term.
+__device__ __forceinline__ void fx_add(long long* __restrict__ acc2, double v) {
+  const double hi = trunc(v);
+  const long long ih = (long long)hi;
+  const long long il = __double2ll_rn((v - hi) * 17592186044416.0);        // 2^44
+  if (ih) atomicAdd(reinterpret_cast<unsigned long long*>(acc2), (unsigned long long)ih);
+  if (il) atomicAdd(reinterpret_cast<unsigned long long*>(acc2 + 1), (unsigned long long)il);
+}
+__device__ __forceinline__ double fx_get(const long long* __restrict__ acc2) {
+  return (double)acc2[0] + (double)acc2[1] * 5.6843418860808015e-14;        // 2^-44
+}
+// the lanes of a warp that hit the same bin combine first (interval end points pile up on a few sites: every tip's 5' / 3' end gap
+// starts at site 0 / ends at site L, and same-address atomics serialise in L2); ascending lanes, so the partial sum is reproducible
+__device__ __forceinline__ void warp_agg_fx_add(long long* base2, int idx, double v) {
   const unsigned peers = __match_any_sync(__activemask(), idx);
   double sum = 0.0;
-  for (unsigned rem = peers; rem; rem &= rem - 1) sum += __shfl_sync(peers, v, __ffs(rem) - 1);   // ascending lanes: fixed order
-  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(base + idx, sum);
+  for (unsigned rem = peers; rem; rem &= rem - 1) sum += __shfl_sync(peers, v, __ffs(rem) - 1);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) fx_add(base2 + 2 * (size_t)idx, sum);
 }
 
 struct TallyOut {
@@ -80,9 +94,9 @@ struct TallyOut {
   int32_t* num_muts_l;        // [L] or null
   int32_t* num_muts_l_ab;     // [L*16] or null
   double* beta_a_part;        // [num_tiles * 16] per-tile partials of Ttwiddle_beta_a, or null
-  double* Ttw_l;              // [L] or null (atomic scatter)
-  double* T_l_a;              // [L*4] or null
-  double* miss_diff;          // [L+1] difference array of T_below_miss (needed when Ttw_l or T_l_a)
+  long long* Ttw_l;           // [L][2] fixed-point accumulators (fx_add) or null
+  long long* T_l_a;           // [L*4][2] or null
+  long long* miss_diff;       // [L+1][2] difference array of T_below_miss (needed when Ttw_l or T_l_a)
 };
 
 // One thread per node of the tree.  kTime: evaluate the time tallies (needs PL).
@@ -132,8 +146,8 @@ __global__ void __launch_bounds__(kTile) tally_events_kernel(ForestDev f, int tr
             if (k == pt * 4 + to) acc[k] += w;
           }
         }
-        if (out.Ttw_l) atomicAdd(out.Ttw_l + l, ((-S.q[pt * 16 + to * 5]) - (-S.q[pt * 16 + from * 5])) * Tbm);
-        if (out.T_l_a) { atomicAdd(out.T_l_a + (size_t)l * 4 + from, -Tbm); atomicAdd(out.T_l_a + (size_t)l * 4 + to, Tbm); }
+        if (out.Ttw_l) fx_add(out.Ttw_l + 2 * (size_t)l, ((-S.q[pt * 16 + to * 5]) - (-S.q[pt * 16 + from * 5])) * Tbm);
+        if (out.T_l_a) { fx_add(out.T_l_a + 2 * ((size_t)l * 4 + from), -Tbm); fx_add(out.T_l_a + 2 * ((size_t)l * 4 + to), Tbm); }
       }
     }
     if (kTime) {
@@ -149,7 +163,7 @@ __global__ void __launch_bounds__(kTile) tally_events_kernel(ForestDev f, int tr
             }
           }
         }
-        if (out.miss_diff) { warp_agg_atomic_add(out.miss_diff, s, Tbmiss); warp_agg_atomic_add(out.miss_diff, e, -Tbmiss); }
+        if (out.miss_diff) { warp_agg_fx_add(out.miss_diff, s, Tbmiss); warp_agg_fx_add(out.miss_diff, e, -Tbmiss); }
       }
       for (int i = f.fs_off[p]; i < f.fs_off[p + 1]; ++i) {
         const int l = f.fs_site[i], code = f.fs_code[i], from = code & 3, rf = (code >> 2) & 3, pt = code >> 4;
@@ -161,8 +175,8 @@ __global__ void __launch_bounds__(kTile) tally_events_kernel(ForestDev f, int tr
             if (k == pt * 4 + from) acc[k] -= w;    // apply the correct from-state
           }
         }
-        if (out.Ttw_l) atomicAdd(out.Ttw_l + l, ((-S.q[pt * 16 + rf * 5]) - (-S.q[pt * 16 + from * 5])) * Tbmiss);
-        if (out.T_l_a) { atomicAdd(out.T_l_a + (size_t)l * 4 + rf, Tbmiss); atomicAdd(out.T_l_a + (size_t)l * 4 + from, -Tbmiss); }
+        if (out.Ttw_l) fx_add(out.Ttw_l + 2 * (size_t)l, ((-S.q[pt * 16 + rf * 5]) - (-S.q[pt * 16 + from * 5])) * Tbmiss);
+        if (out.T_l_a) { fx_add(out.T_l_a + 2 * ((size_t)l * 4 + rf), Tbmiss); fx_add(out.T_l_a + 2 * ((size_t)l * 4 + from), -Tbmiss); }
       }
     }
   }
@@ -194,7 +208,8 @@ __global__ void tally_beta_a_finalize_kernel(ForestDev f, int tree, const double
 // Per-site finalize: scan the +-T_below_miss difference array over sites, then add the no-mutation baseline
 // (T_total - missing time) * [state == ref].  One CTA sweeping coalesced slabs with a running carry (L is at most a few 1e5).
 __global__ void __launch_bounds__(1024) tally_sites_finalize_kernel(ForestDev f, int tree, const double* __restrict__ PL,
-                                                                    const double* __restrict__ miss_diff,
+                                                                    const long long* __restrict__ miss_diff,
+                                                                    const long long* __restrict__ Ttw_fx, const long long* __restrict__ T_l_a_fx,
                                                                     double* __restrict__ Ttw_l, double* __restrict__ T_l_a) {
   __shared__ double s_ws[32];
   __shared__ double s_carry;
@@ -210,7 +225,7 @@ __global__ void __launch_bounds__(1024) tally_sites_finalize_kernel(ForestDev f,
     const int l0 = base + tid * kPer;
     double v[kPer], tot = 0.0;
 #pragma unroll
-    for (int u = 0; u < kPer; ++u) { v[u] = l0 + u < L ? miss_diff[l0 + u] : 0.0; tot += v[u]; }
+    for (int u = 0; u < kPer; ++u) { v[u] = l0 + u < L ? fx_get(miss_diff + 2 * (size_t)(l0 + u)) : 0.0; tot += v[u]; }
     double bt;
     const double incl = block_scan_incl<double, 1024>(tot, s_ws, &bt);
     double run = s_carry + (incl - tot);
@@ -221,8 +236,11 @@ __global__ void __launch_bounds__(1024) tally_sites_finalize_kernel(ForestDev f,
       if (l < L) {
         const double basev = Ttot - run;    // time during which site l is present with the reference state (before mutations)
         const int a = S.ref[l], pt = S.part[l];
-        if (Ttw_l) Ttw_l[l] += (-S.q[pt * 16 + a * 5]) * basev;
-        if (T_l_a) T_l_a[(size_t)l * 4 + a] += basev;
+        if (Ttw_l) Ttw_l[l] = fx_get(Ttw_fx + 2 * (size_t)l) + (-S.q[pt * 16 + a * 5]) * basev;
+        if (T_l_a) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) T_l_a[(size_t)l * 4 + b] = fx_get(T_l_a_fx + 2 * ((size_t)l * 4 + b)) + (b == a ? basev : 0.0);
+        }
       }
     }
     __syncthreads();
@@ -291,20 +309,21 @@ int tally_times(dphy_ctx* ctx, dphy_forest* fo, int tree, double* out_beta_a, do
   if (st != DPHY_OK) { ctx->arena.release(mark); return st; }
   TallyOut o{};
   double* d_beta_a = nullptr;
+  double* d_Ttw = nullptr; double* d_Tla = nullptr;      // the doubles handed back (the scatter itself runs on fixed-point bins)
   if (out_beta_a) {
     o.beta_a_part = (double*)ctx->arena.alloc(sizeof(double) * 16 * T.num_tiles);
     d_beta_a = (double*)ctx->arena.alloc(sizeof(double) * 16);
   }
-  if (out_l) o.Ttw_l = (double*)ctx->arena.alloc(sizeof(double) * L);
-  if (out_l_a) o.T_l_a = (double*)ctx->arena.alloc(sizeof(double) * (size_t)L * 4);
-  if (out_l || out_l_a) o.miss_diff = (double*)ctx->arena.alloc(sizeof(double) * (L + 1));
-  if ((out_beta_a && (!o.beta_a_part || !d_beta_a)) || (out_l && !o.Ttw_l) || (out_l_a && !o.T_l_a) || ((out_l || out_l_a) && !o.miss_diff)) {
+  if (out_l) { o.Ttw_l = (long long*)ctx->arena.alloc(sizeof(long long) * 2 * L); d_Ttw = (double*)ctx->arena.alloc(sizeof(double) * L); }
+  if (out_l_a) { o.T_l_a = (long long*)ctx->arena.alloc(sizeof(long long) * 2 * (size_t)L * 4); d_Tla = (double*)ctx->arena.alloc(sizeof(double) * (size_t)L * 4); }
+  if (out_l || out_l_a) o.miss_diff = (long long*)ctx->arena.alloc(sizeof(long long) * 2 * (L + 1));
+  if ((out_beta_a && (!o.beta_a_part || !d_beta_a)) || (out_l && (!o.Ttw_l || !d_Ttw)) || (out_l_a && (!o.T_l_a || !d_Tla)) || ((out_l || out_l_a) && !o.miss_diff)) {
     ctx->arena.release(mark);
     return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (time tallies)");
   }
-  if (o.Ttw_l) DPHY_CUDA(ctx, cudaMemsetAsync(o.Ttw_l, 0, sizeof(double) * L, ctx->stream));
-  if (o.T_l_a) DPHY_CUDA(ctx, cudaMemsetAsync(o.T_l_a, 0, sizeof(double) * (size_t)L * 4, ctx->stream));
-  if (o.miss_diff) DPHY_CUDA(ctx, cudaMemsetAsync(o.miss_diff, 0, sizeof(double) * (L + 1), ctx->stream));
+  if (o.Ttw_l) DPHY_CUDA(ctx, cudaMemsetAsync(o.Ttw_l, 0, sizeof(long long) * 2 * L, ctx->stream));
+  if (o.T_l_a) DPHY_CUDA(ctx, cudaMemsetAsync(o.T_l_a, 0, sizeof(long long) * 2 * (size_t)L * 4, ctx->stream));
+  if (o.miss_diff) DPHY_CUDA(ctx, cudaMemsetAsync(o.miss_diff, 0, sizeof(long long) * 2 * (L + 1), ctx->stream));
   tally_events_kernel<true><<<T.num_tiles, kTile, 0, ctx->stream>>>(fo->h, tree, PL, s->d_cum_nu_ba, o);
   ctx->launches += 1;
   st = check_cuda(ctx, cudaGetLastError(), "tally_events_kernel<true>");
@@ -315,12 +334,12 @@ int tally_times(dphy_ctx* ctx, dphy_forest* fo, int tree, double* out_beta_a, do
     if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(out_beta_a, d_beta_a, sizeof(double) * P * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
   }
   if (st == DPHY_OK && (out_l || out_l_a)) {
-    tally_sites_finalize_kernel<<<1, 1024, 0, ctx->stream>>>(fo->h, tree, PL, o.miss_diff, o.Ttw_l, o.T_l_a);
+    tally_sites_finalize_kernel<<<1, 1024, 0, ctx->stream>>>(fo->h, tree, PL, o.miss_diff, o.Ttw_l, o.T_l_a, d_Ttw, d_Tla);
     ctx->launches += 1;
     st = check_cuda(ctx, cudaGetLastError(), "tally_sites_finalize_kernel");
-    if (st == DPHY_OK && out_l && defer) ctx->deferred_d2h.push_back({out_l, o.Ttw_l, sizeof(double) * (size_t)L});
-    else if (st == DPHY_OK && out_l) st = check_cuda(ctx, cudaMemcpyAsync(out_l, o.Ttw_l, sizeof(double) * L, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
-    if (st == DPHY_OK && out_l_a) st = check_cuda(ctx, cudaMemcpyAsync(out_l_a, o.T_l_a, sizeof(double) * (size_t)L * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+    if (st == DPHY_OK && out_l && defer) ctx->deferred_d2h.push_back({out_l, d_Ttw, sizeof(double) * (size_t)L});
+    else if (st == DPHY_OK && out_l) st = check_cuda(ctx, cudaMemcpyAsync(out_l, d_Ttw, sizeof(double) * L, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+    if (st == DPHY_OK && out_l_a) st = check_cuda(ctx, cudaMemcpyAsync(out_l_a, d_Tla, sizeof(double) * (size_t)L * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
   }
   if (defer && st == DPHY_OK) return st;
   if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "time tallies");

@@ -426,3 +426,23 @@ def test_set_evo_rebuilds_the_nu_tables_only_when_nu_changes(ctx, orc):
     assert fo.log_G()[1][0] == pytest.approx(orc.log_G_below_root(e, s), rel=RTOL)
     assert rel_err(ds.cum_Q_l()[1:], orc.cum_Q_l(s)[1:]) <= 1e-10
     fo.close(); ds.close()
+
+
+def test_site_tallies_are_bit_reproducible(ctx):
+    """calc_Ttwiddle_l / calc_T_l_a scatter O(M + I + F) terms into per-site bins from all over the tree.  The bins are fixed-point
+    integers (order-independent), so repeated evaluations -- and evaluations of the same tree at another position of another forest,
+    where every block and atomic lands at a different time -- give the same bits."""
+    emat, sites, info = synth(2)
+    other, osites, _ = synth(1)
+    ds = db.DeviceSites(ctx, sites); dso = db.DeviceSites(ctx, osites)
+    fo = db.Forest(ctx, [emat], [ds])
+    first = fo.Ttwiddle_l(0, want_T_l_a=True)
+    for _ in range(6):
+        again = fo.Ttwiddle_l(0, want_T_l_a=True)
+        assert np.array_equal(again[0], first[0]) and np.array_equal(again[1], first[1])
+    fo2 = db.Forest(ctx, [other, emat], [dso, ds], sites_index=[0, 1])
+    moved = fo2.Ttwiddle_l(1, want_T_l_a=True)
+    assert np.array_equal(moved[0], first[0]) and np.array_equal(moved[1], first[1])
+    st = fo.site_tallies()
+    assert np.array_equal(st[0][0], first[0])
+    fo.close(); fo2.close(); ds.close(); dso.close()
