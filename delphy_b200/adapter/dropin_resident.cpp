@@ -214,6 +214,22 @@ auto flatten_reachable_into(dphy_ctx* ctx, const Phylo_tree& tree, Pinned_flat_e
   }
 }
 
+namespace {
+template <typename T>
+auto same_array(const Pinned_array<T>& a, const Pinned_array<T>& b, size_t n) -> bool {
+  return n == 0 || std::memcmp(a.data, b.data, n * sizeof(T)) == 0;
+}
+auto same_flat(const Pinned_flat_emat& a, const Pinned_flat_emat& b) -> bool {
+  if (a.num_nodes != b.num_nodes || a.root != b.root || a.num_muts != b.num_muts || a.num_ivls != b.num_ivls || a.num_fs != b.num_fs) { return false; }
+  const auto n = static_cast<size_t>(a.num_nodes), m = static_cast<size_t>(a.num_muts), iv = static_cast<size_t>(a.num_ivls), fs = static_cast<size_t>(a.num_fs);
+  return same_array(a.t, b.t, n) && same_array(a.parent, b.parent, n) && same_array(a.child0, b.child0, n) && same_array(a.child1, b.child1, n) &&
+         same_array(a.mut_off, b.mut_off, n + 1) && same_array(a.mut_t, b.mut_t, m) && same_array(a.mut_site, b.mut_site, m) &&
+         same_array(a.mut_from, b.mut_from, m) && same_array(a.mut_to, b.mut_to, m) &&
+         same_array(a.miss_off, b.miss_off, n + 1) && same_array(a.miss_start, b.miss_start, iv) && same_array(a.miss_end, b.miss_end, iv) &&
+         same_array(a.fs_off, b.fs_off, n + 1) && same_array(a.fs_site, b.fs_site, fs) && same_array(a.fs_from, b.fs_from, fs);
+}
+}  // namespace
+
 // ---- Resident ------------------------------------------------------------------------------------------------------------------------------------
 Resident::Resident() : ctx_{thread_ctx()} {}
 
@@ -221,12 +237,12 @@ Resident::~Resident() {
   // thread_local: runs before the adapter's ctx reaper (constructed earlier, by thread_ctx() above)
   if (const char* e = std::getenv("DPHY_DROPIN_STATS"); e != nullptr && std::atoi(e) != 0) {
     std::fprintf(stderr, "[delphy_b200 drop-in] thread stats: %lld tree uploads (flatten %.3f s, upload+device flatten %.3f s), "
-                 "sites: %lld uploads, %lld set_evo, %lld reused (%.3f s)\n", (long long)uploads, flatten_seconds, upload_seconds,
-                 (long long)sites_uploads, (long long)set_evos, (long long)sites_reused, sites_seconds);
+                 "sites: %lld uploads, %lld set_evo, %lld reused (%.3f s); %lld calls answered by the resident forest\n", (long long)uploads, flatten_seconds, upload_seconds,
+                 (long long)sites_uploads, (long long)set_evos, (long long)sites_reused, sites_seconds, (long long)uploads_skipped);
   }
   drop_forest();
   if (sites_ != nullptr) { dphy_sites_destroy(ctx_, sites_); sites_ = nullptr; }
-  flat_.release();
+  flat_.release(); prev_.release();
 }
 
 auto Resident::get() -> Resident& {
@@ -319,13 +335,23 @@ auto Resident::sync_sites(const Real_sequence& seq, const Global_evo_model* evo)
 auto Resident::sync_tree(const Phylo_tree& tree, const Global_evo_model* evo) -> dphy_forest* {
   using clock = std::chrono::steady_clock;
   sync_sites(tree.ref_sequence, evo);
-  // the previous upload DMAs straight out of flat_: it must have landed before the buffers are rewritten
-  throw_on_error(ctx_, dphy_ctx_synchronize(ctx_), "dphy_ctx_synchronize");
+  // (flat_ is never a DMA source: uploads go out of prev_, which is only rewritten by the swap below after a synchronize)
   const auto t0 = clock::now();
   flatten_into(ctx_, tree, flat_);
+  // The driver recomputes in bursts on an unchanged tree (Run::recalc_derived_quantities makes five hot calls in a row, and every
+  // pop-model proposal of a global move revalidates everything, core/run.cpp:302-314,760-779): if the flattened arrays equal the
+  // ones the resident forest was built from, that forest -- already evaluated -- answers the call as it is.
+  if (prev_valid_ && forest_ != nullptr && same_flat(flat_, prev_)) {
+    ++uploads_skipped;
+    flatten_seconds += std::chrono::duration<double>(clock::now() - t0).count();
+    return forest_;
+  }
   const auto t1 = clock::now();
+  throw_on_error(ctx_, dphy_ctx_synchronize(ctx_), "dphy_ctx_synchronize");    // the previous upload has left prev_
   drop_forest();
-  auto he = flat_.view(true);     // both pieces of log G are computed; callers pick (Subrun::calc_cur_log_G, core/subrun.cpp:58-68)
+  std::swap(flat_, prev_);        // prev_ now holds the arrays being uploaded (DMA'd in place: they stay untouched until the next upload)
+  prev_valid_ = true;
+  auto he = prev_.view(true);     // both pieces of log G are computed; callers pick (Subrun::calc_cur_log_G, core/subrun.cpp:58-68)
   auto zero = int32_t{0};
   throw_on_error(ctx_, dphy_forest_upload(ctx_, 1, &he, &zero, 1, &sites_, &forest_), "dphy_forest_upload");
   const auto t2 = clock::now();
@@ -343,7 +369,9 @@ auto Resident::sync_reachable_tree(const Phylo_tree& tree) -> dphy_forest* {
   flatten_reachable_into(ctx_, tree, flat_, to_orig_, of_orig_);
   const auto t1 = clock::now();
   drop_forest();
-  auto he = flat_.view(true);
+  std::swap(flat_, prev_);
+  prev_valid_ = false;            // compact node indices: never reused for a whole-tree call
+  auto he = prev_.view(true);
   auto zero = int32_t{0};
   throw_on_error(ctx_, dphy_forest_upload(ctx_, 1, &he, &zero, 1, &sites_, &forest_), "dphy_forest_upload");
   const auto t2 = clock::now();

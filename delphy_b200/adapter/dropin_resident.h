@@ -71,7 +71,7 @@ class Resident {
   auto num_nodes() const -> int { return flat_.num_nodes; }
 
   // counters (bench / tests): how many trees were shipped and how long the host-side flatten took in total
-  int64_t uploads = 0, sites_uploads = 0, set_evos = 0, sites_reused = 0;
+  int64_t uploads = 0, uploads_skipped = 0, sites_uploads = 0, set_evos = 0, sites_reused = 0;
   double flatten_seconds = 0.0, upload_seconds = 0.0, sites_seconds = 0.0;
 
  private:
@@ -80,7 +80,8 @@ class Resident {
   dphy_ctx* ctx_ = nullptr;
   dphy_sites* sites_ = nullptr;
   dphy_forest* forest_ = nullptr;
-  Pinned_flat_emat flat_;
+  Pinned_flat_emat flat_, prev_;         // the tree being shipped / the tree the resident forest was built from
+  bool prev_valid_ = false;
   std::vector<int32_t> to_orig_, of_orig_;
   // host shadow of what the sites table holds
   std::vector<uint8_t> ref_;
