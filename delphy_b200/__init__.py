@@ -472,9 +472,8 @@ class Context:
         return out
 
     def set_log_G_path(self, path: str = "auto"):
-        """'auto': folded fast path when every site table has uniform nu_l; 'general': always the per-event kernels;
-        'general_stream': the per-event path through the TMA-staged persistent kernel (uniform nu_l only)."""
-        self.check(lib().dphy_ctx_set_log_G_path(self._h, {"auto": 0, "general": 1, "general_stream": 2}[path]))
+        """'auto': folded fast path when every site table has uniform nu_l; 'general': always the per-event kernels."""
+        self.check(lib().dphy_ctx_set_log_G_path(self._h, {"auto": 0, "general": 1}[path]))
         self.log_G_path = path
 
     def arena_stats(self):

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -89,19 +91,75 @@ auto Pinned_flat_emat::release() -> void {
 
 namespace {
 
-// run fn(lo, hi) over [0, n) on up to `threads` host threads (the calling thread takes the first chunk)
+// A small persistent pool for the flatten passes: starting threads per call costs more than flattening a 20k-node tree.
+// One flatten at a time may use it (try_lock); a concurrent caller -- another Subrun's thread -- simply runs its passes alone.
+class Flatten_pool {
+ public:
+  explicit Flatten_pool(int workers) {
+    for (auto k = 0; k < workers; ++k) { threads_.emplace_back([this, k] { worker(k); }); }
+  }
+  ~Flatten_pool() {
+    { auto lock = std::unique_lock<std::mutex>{mu_}; stop_ = true; ++epoch_; }
+    cv_.notify_all();
+    for (auto& th : threads_) { th.join(); }
+  }
+  auto workers() const -> int { return static_cast<int>(threads_.size()); }
+  // fn(part) for part = 1 .. workers() on the pool; part 0 runs on the caller; returns when all are done
+  auto run(const std::function<void(int)>& fn) -> void {
+    { auto lock = std::unique_lock<std::mutex>{mu_}; fn_ = &fn; pending_ = workers(); ++epoch_; }
+    cv_.notify_all();
+    fn(0);
+    auto lock = std::unique_lock<std::mutex>{mu_};
+    done_.wait(lock, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+  std::mutex user;      // held by the flatten that owns the pool
+ private:
+  auto worker(int k) -> void {
+    auto seen = uint64_t{0};
+    for (;;) {
+      const std::function<void(int)>* fn = nullptr;
+      {
+        auto lock = std::unique_lock<std::mutex>{mu_};
+        cv_.wait(lock, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_) { return; }
+        fn = fn_;
+      }
+      if (fn != nullptr) { (*fn)(k + 1); }
+      { auto lock = std::unique_lock<std::mutex>{mu_}; if (--pending_ == 0) { done_.notify_one(); } }
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
+auto flatten_threads() -> int;
+
+auto flatten_pool() -> Flatten_pool& {
+  static Flatten_pool pool{std::max(0, flatten_threads() - 1)};
+  return pool;
+}
+
+// run fn(lo, hi) over [0, n) split into equal ranges over the pool (the calling thread takes the first range)
 template <typename F>
 auto parallel_ranges(size_t n, int threads, F&& fn) -> void {
-  if (threads <= 1 || n < 65536) { fn(size_t{0}, n); return; }   // thread start-up costs more than flattening a small tree
-  const auto chunk = (n + threads - 1) / threads;
-  auto pool = std::vector<std::thread>{};
-  pool.reserve(threads - 1);
-  for (auto k = 1; k < threads; ++k) {
-    const auto lo = std::min(n, k * chunk), hi = std::min(n, lo + chunk);
-    if (lo < hi) { pool.emplace_back([&fn, lo, hi] { fn(lo, hi); }); }
-  }
-  fn(size_t{0}, std::min(n, chunk));
-  for (auto& th : pool) { th.join(); }
+  if (threads <= 1 || n < 8192) { fn(size_t{0}, n); return; }
+  auto& pool = flatten_pool();
+  auto own = std::unique_lock<std::mutex>{pool.user, std::try_to_lock};
+  if (!own.owns_lock() || pool.workers() == 0) { fn(size_t{0}, n); return; }
+  const auto parts = static_cast<size_t>(pool.workers() + 1);
+  const auto chunk = (n + parts - 1) / parts;
+  const auto body = std::function<void(int)>{[&](int part) {
+    const auto lo = std::min(n, static_cast<size_t>(part) * chunk), hi = std::min(n, lo + chunk);
+    if (lo < hi) { fn(lo, hi); }
+  }};
+  pool.run(body);
 }
 
 auto flatten_threads() -> int {

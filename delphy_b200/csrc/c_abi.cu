@@ -164,7 +164,7 @@ int dphy_arena_stats(const dphy_ctx* ctx, size_t* capacity, size_t* high_water) 
 }
 
 int dphy_ctx_set_log_G_path(dphy_ctx* ctx, int path) {
-  if (!ctx || (path != DPHY_LOG_G_PATH_AUTO && path != DPHY_LOG_G_PATH_GENERAL && path != DPHY_LOG_G_PATH_GENERAL_STREAM)) return DPHY_ERR_INVALID_ARGUMENT;
+  if (!ctx || (path != DPHY_LOG_G_PATH_AUTO && path != DPHY_LOG_G_PATH_GENERAL)) return DPHY_ERR_INVALID_ARGUMENT;
   ctx->logg_path = path;
   return DPHY_OK;
 }

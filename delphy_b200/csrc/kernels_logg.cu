@@ -132,14 +132,8 @@ __global__ void __launch_bounds__(128) emat_log_G_straddler_kernel(const LogGPar
 
 // ---- pass 1 --------------------------------------------------------------------------------------------------------------------
 // kLgTile consecutive device positions of one tree per tile; thread tid owns the two consecutive positions 2 tid and
-// 2 tid + 1.  Two kernels share the back half (scan of the deltas, closers, outputs):
-//   * emat_log_G_tile_kernel (the default): one CTA per tile straight from global memory, thread-per-node list walks with
-//     batched, predicated loads; any site-rate model.
-//   * emat_log_G_stream_kernel (DPHY_LOG_G_PATH_GENERAL_STREAM; uniform site rates only): persistent CTAs; the tile's node
-//     records, event lists and closer slice -- all contiguous ranges thanks to the DFS/CSR layout -- are staged in shared
-//     memory by 1-D bulk async copies (TMA engine, mbarrier-tracked, two stages deep) while the previous tile is being
-//     computed; per-node sums come from flat prefix scans over the staged events.  Measured slower than the direct kernel on
-//     B200 (281 vs 216 us per 16 x 100k-tip evaluation); tiles whose staging would not fit kStageBytes go to the direct kernel.
+// 2 tid + 1.  emat_log_G_tile_kernel: one CTA per tile straight from global memory, thread-per-node list walks with batched,
+// predicated loads; any site-rate model.
 struct NodeRegs {
   int par[2], dep[2], om[3];
   double tN[2], tP[2];
@@ -354,232 +348,6 @@ __global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_tile_kernel
   }
   tile_back_half<false>(P, sm, R, tile, tile_start, n_act, node_base, cl.z, (P.debug_mask & 8) ? cl.z : cl.w,
                         f.post_node + node_base, __ldg(cumQ + S.L));
-}
-
-// ---- pass 1, streaming variant ---------------------------------------------------------------------------------------------------------
-constexpr int kStages = 2;
-constexpr int kWorkBytes = 20 * 1024;          // per-interval site counts of the tile being computed (4 B each)
-
-struct StageMap {
-  CTileDesc d;
-  uint32_t o_par, o_dep, o_t, o_om, o_oi, o_fsw, o_mc, o_mt, o_ise, o_post, tile, pad;
-};
-
-struct StreamSmem {
-  LogGSmem lg;
-  unsigned long long bar[kStages];
-  StageMap map[kStages];
-  alignas(16) CTileDesc next_desc;   // descriptor of the tile that will refill the current stage (prefetched with cp.async)
-};
-constexpr size_t kStreamSmemBytes = ((sizeof(StreamSmem) + 127) / 128) * 128 + kWorkBytes + (size_t)kStages * kStageBytes;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// One thread: plan the 10 bulk copies of a tile (16-byte aligned on both ends), arm the stage's mbarrier, issue them.
-__device__ __forceinline__ void issue_tile(const ForestDev& f, StreamSmem& sm, char* stage_base, int stage, int tile, const CTileDesc& d) {
-  StageMap& M = sm.map[stage];
-  M.d = d; M.tile = (uint32_t)tile;
-  const void* src[10]; uint32_t dst[10], bytes[10];
-  uint32_t cur = 0;
-  auto plan = [&](int k, const void* base, size_t first_byte, size_t nbytes, uint32_t& off_out) {
-    const uintptr_t s0 = (uintptr_t)base + first_byte, a0 = s0 & ~(uintptr_t)15;
-    const uint32_t lead = (uint32_t)(s0 - a0);
-    bytes[k] = nbytes ? (uint32_t)((lead + nbytes + 15) & ~(size_t)15) : 0u;
-    src[k] = (const void*)a0; dst[k] = cur; off_out = cur + lead; cur += bytes[k];
-  };
-  const size_t p0 = (size_t)d.tile_start, n = (size_t)d.n_act;
-  plan(0, f.parent_pos, 4 * p0, 4 * n, M.o_par);
-  plan(1, f.depth, 4 * p0, 4 * n, M.o_dep);
-  plan(2, f.t, 8 * p0, 8 * n, M.o_t);
-  plan(3, f.mut_off, 4 * p0, 4 * (n + 1), M.o_om);
-  plan(4, f.miss_off, 4 * p0, 4 * (n + 1), M.o_oi);
-  plan(5, f.fsw, 2 * (size_t)f.fsw_stride * p0, 2 * (size_t)f.fsw_stride * n, M.o_fsw);
-  plan(6, f.mut_code, (size_t)d.m0, (size_t)(d.m1 - d.m0), M.o_mc);
-  plan(7, f.mut_t, 8 * (size_t)d.m0, 8 * (size_t)(d.m1 - d.m0), M.o_mt);
-  plan(8, f.miss_se, 8 * (size_t)d.i0, 8 * (size_t)(d.i1 - d.i0), M.o_ise);
-  plan(9, f.post_node, 4 * (size_t)(d.node_base + d.cl0), 4 * (size_t)(d.cl1 - d.cl0), M.o_post);
-  fence_proxy_async();                     // the stage was last read through the generic proxy
-  mbar_arrive_expect_tx(&sm.bar[stage], cur);
-#pragma unroll
-  for (int k = 0; k < 10; ++k) if (bytes[k]) bulk_g2s(stage_base + dst[k], src[k], bytes[k], &sm.bar[stage]);
-}
-
-__global__ void __launch_bounds__(kLgThreads, 2) emat_log_G_stream_kernel(const LogGParams P, int num_tiles) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smem_raw);
-  int* s_n = reinterpret_cast<int*>(smem_raw + ((sizeof(StreamSmem) + 127) / 128) * 128);
-  char* stages = reinterpret_cast<char*>(s_n) + kWorkBytes;
-  const ForestDev& f = P.f;
-  const int tid = threadIdx.x;
-  const int my_count = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(&sm.bar[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  int next_tile = -1;           // (thread 0) tile that refills the stage consumed in the current iteration
-  if (tid == 0) {
-    for (int s = 0; s < kStages && s < my_count; ++s) {
-      const int t = f.fast_ctiles[blockIdx.x + s * gridDim.x];
-      issue_tile(f, sm, stages + (size_t)s * kStageBytes, s, t, f.ctiles[t]);
-    }
-    if (kStages < my_count) next_tile = f.fast_ctiles[blockIdx.x + kStages * gridDim.x];
-  }
-  const int stride = f.fsw_stride;
-
-  for (int it = 0; it < my_count; ++it) {
-    const int stage = it % kStages;
-    const uint32_t parity = (uint32_t)(it / kStages) & 1u;
-    // the issuing thread prefetches the descriptor of the tile that will refill this stage (asynchronously, into smem)
-    // and looks up the one after it, so that neither load is exposed when the stage is released
-    const int refill = next_tile;
-    if (tid == 0) {
-      if (refill >= 0) {
-        const char* src = reinterpret_cast<const char*>(f.ctiles + refill);
-        const uint32_t dst = smem_u32(&sm.next_desc);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * k), "l"(src + 16 * k) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-      next_tile = it + kStages + 1 < my_count ? f.fast_ctiles[blockIdx.x + (it + kStages + 1) * gridDim.x] : -1;
-    }
-    if (tid < 64) sm.lg.ab[tid] = 0;
-    __syncthreads();
-    mbar_wait(&sm.bar[stage], parity);
-
-    const StageMap& M = sm.map[stage];
-    char* sb = stages + (size_t)stage * kStageBytes;
-    const int tile = (int)M.tile;
-    const int tile_start = M.d.tile_start, n_act = M.d.n_act, node_base = M.d.node_base;
-    const SitesDev& S = f.sites[M.d.sites_id];
-    const double* __restrict__ cumQ = S.cumQ;
-    const int* s_par = reinterpret_cast<const int*>(sb + M.o_par);
-    const int* s_dep = reinterpret_cast<const int*>(sb + M.o_dep);
-    const double* s_t = reinterpret_cast<const double*>(sb + M.o_t);
-    const int* s_om = reinterpret_cast<const int*>(sb + M.o_om);
-    const int* s_oi = reinterpret_cast<const int*>(sb + M.o_oi);
-    const int16_t* s_fsw = reinterpret_cast<const int16_t*>(sb + M.o_fsw);
-    const uint8_t* s_mc = reinterpret_cast<const uint8_t*>(sb + M.o_mc);
-    const double* s_mt = reinterpret_cast<const double*>(sb + M.o_mt);
-    int2* s_ise = reinterpret_cast<int2*>(sb + M.o_ise);
-    const int32_t* s_post = reinterpret_cast<const int32_t*>(sb + M.o_post);
-    const int m0 = M.d.m0, i0 = M.d.i0;
-    const int ni = (P.debug_mask & 2) ? 0 : M.d.i1 - i0;
-    const int cl0 = M.d.cl0, cl1 = (P.debug_mask & 8) ? cl0 : M.d.cl1;
-
-    // ---- (A) flat over the staged missation intervals: resolve the two cumQ gathers (the only global reads of the tile's
-    //      event work), in place: (start, end) -> cumQ[end] - cumQ[start]; the site counts go to the work buffer ----------------
-    {
-      double* s_a = reinterpret_cast<double*>(s_ise);
-      for (int i = tid; i < ni; i += 4 * kLgThreads) {
-        int2 se[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) se[u] = i + u * kLgThreads < ni ? s_ise[i + u * kLgThreads] : make_int2(0, 0);
-        double a[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) a[u] = __ldg(cumQ + se[u].y) - __ldg(cumQ + se[u].x);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (i + u * kLgThreads < ni) { s_a[i + u * kLgThreads] = a[u]; s_n[i + u * kLgThreads] = se[u].y - se[u].x; }
-        }
-      }
-    }
-
-    // ---- node records (from the stage) ---------------------------------------------------------------------------------------------
-    NodeRegs R;
-    const int q0 = 2 * tid;
-    const bool act0 = q0 < n_act, act1 = q0 + 1 < n_act;
-    int oi[3] = {i0, i0, i0};
-#pragma unroll
-    for (int k = 0; k < 2; ++k) { R.par[k] = -1; R.dep[k] = 0; R.tN[k] = 0.0; R.tP[k] = 0.0; R.dm[k] = 0.0; R.es[k] = 0.0; R.dmi[k] = 0.0; R.nmiss[k] = 0; }
-    R.om[0] = R.om[1] = R.om[2] = m0;
-    if (act0) {
-      R.par[0] = s_par[q0]; R.dep[0] = s_dep[q0]; R.tN[0] = s_t[q0];
-      R.om[0] = s_om[q0]; oi[0] = s_oi[q0];
-      R.om[1] = s_om[q0 + 1]; oi[1] = s_oi[q0 + 1];
-      R.om[2] = R.om[1]; oi[2] = oi[1];
-    }
-    if (act1) {
-      R.par[1] = s_par[q0 + 1]; R.dep[1] = s_dep[q0 + 1]; R.tN[1] = s_t[q0 + 1];
-      R.om[2] = s_om[q0 + 2]; oi[2] = s_oi[q0 + 2];
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (R.par[k] >= 0) {
-        const int qp = R.par[k] - tile_start;
-        R.tP[k] = qp >= 0 ? s_t[qp] : __ldg(f.t + R.par[k]);   // the parent is usually in the same tile
-      }
-    }
-    // mutations: d_i = mu nu (q_to - q_from);  e_i = d_i * t_i + log(mu nu q_from,to)   [g_node = sum e_i - t_P * sum d_i]
-    if (!(P.debug_mask & 1)) {
-      const int c0 = R.om[1] - R.om[0], c1 = R.om[2] - R.om[1];
-      const int b0 = R.om[0] - m0, b1 = R.om[1] - m0;
-      const int cmax = max(c0, c1);
-      for (int j = 0; j < cmax; ++j) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (j < (k == 0 ? c0 : c1)) {
-            const int i = (k == 0 ? b0 : b1) + j;
-            const int code = s_mc[i] & 63;
-            const double dd = __ldg(S.tab_md + code);
-            R.dm[k] += dd;
-            if (R.par[k] >= 0) {     // the root's list ("mutations" above the root) is not part of log G nor of the counts
-              R.es[k] += dd * s_mt[i] + __ldg(S.tab_lq + code);
-              atomicAdd(&sm.lg.ab[(tid & 3) * 16 + (code & 15)], 1);
-            }
-          }
-        }
-      }
-    }
-    // from-state overrides, folded per branch at upload: delta -= mu nu sum_a q_a (#from == a) - (#ref == a)
-    if (!(P.debug_mask & 4)) {
-      for (int k2 = 0; k2 < stride; ++k2) {
-        const double mq = __ldg(S.tab_muq + k2);
-        if (act0) R.dmi[0] += mq * (double)s_fsw[(size_t)q0 * stride + k2];
-        if (act1) R.dmi[1] += mq * (double)s_fsw[(size_t)(q0 + 1) * stride + k2];
-      }
-    }
-    __syncthreads();                       // (A) is complete
-    // missation intervals of my two branches
-    {
-      const double* s_a = reinterpret_cast<const double*>(s_ise);
-      const int c0 = ni ? oi[1] - oi[0] : 0, c1 = ni ? oi[2] - oi[1] : 0;
-      const int b0 = oi[0] - i0, b1 = oi[1] - i0;
-      const int cmax = max(c0, c1);
-      for (int j = 0; j < cmax; ++j) {
-        if (j < c0) { R.dmi[0] -= s_a[b0 + j]; R.nmiss[0] += s_n[b0 + j]; }
-        if (j < c1) { R.dmi[1] -= s_a[b1 + j]; R.nmiss[1] += s_n[b1 + j]; }
-      }
-    }
-
-    tile_back_half<true>(P, sm.lg, R, tile, tile_start, n_act, node_base, cl0, cl1, s_post - cl0, __ldg(cumQ + S.L));
-
-    __syncthreads();                       // everybody is done with the stage (and with lg.ab)
-    if (tid == 0 && refill >= 0) {
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      issue_tile(f, sm, stages + (size_t)stage * kStageBytes, stage, refill, sm.next_desc);
-    }
-  }
 }
 
 // ---- pass 2: one CTA per tree -- exclusive scan of the tile aggregates (tile order), log G fold, tallies, root prior -----
@@ -931,10 +699,6 @@ int launch_log_G_general(dphy_ctx* ctx, dphy_forest* fo) {
   if (fo->h.num_ctiles == 0) return DPHY_OK;
   int st = refresh_sites(ctx, fo);
   if (st != DPHY_OK) return st;
-  if (!ctx->logg_attr_set) {
-    DPHY_CUDA(ctx, cudaFuncSetAttribute(emat_log_G_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmemBytes));
-    ctx->logg_attr_set = true;
-  }
   LogGParams P;
   P.f = fo->h;
   P.lambda_out = fo->d_lambda;
@@ -954,24 +718,11 @@ int launch_log_G_general(dphy_ctx* ctx, dphy_forest* fo) {
     emat_log_G_straddler_kernel<<<(P.num_strad + 127) / 128, 128, 0, ctx->stream>>>(P);
     ctx->launches += 1;
   }
-  // Default: the direct-from-global tile kernel for every tile.  The TMA-staged persistent kernel (DPHY_LOG_G_PATH_GENERAL_STREAM)
-  // needs uniform site rates (it stages neither the event sites nor the munu gathers) and was measured slower on B200
-  // (281 vs 216 us per 16 x 100k-tip evaluation): with ~2 events per node the per-node list walks of 8 resident CTAs/SM keep
-  // more loads in flight than two staged tiles per SM do.
-  bool use_stream = ctx->logg_path == DPHY_LOG_G_PATH_GENERAL_STREAM;
-  for (const dphy_sites* s : fo->sites) use_stream = use_stream && s->h.nu_uniform;
-  if (P.debug_mask & 32) use_stream = false;
-  if (use_stream) {
-    if (fo->num_fast_ctiles > 0) {
-      const int grid = std::min(fo->num_fast_ctiles, 2 * ctx->sm_count);
-      emat_log_G_stream_kernel<<<grid, kLgThreads, kStreamSmemBytes, ctx->stream>>>(P, fo->num_fast_ctiles);
-      ctx->launches += 1;
-    }
-    if (fo->num_slow_ctiles > 0) {
-      emat_log_G_tile_kernel<4><<<fo->num_slow_ctiles, kLgThreads, 0, ctx->stream>>>(P, fo->h.slow_ctiles);
-      ctx->launches += 1;
-    }
-  } else {
+  // The direct-from-global tile kernel: every thread walks the short lists of its own two nodes.  (A TMA-staged persistent variant
+  // -- node records / event lists / closer slice brought to shared memory by cp.async.bulk under an mbarrier, two stages deep -- was
+  // built and measured in round 1: 281 vs 216 us per 16 x 100k-tip evaluation.  With ~2 events per node, 8 resident CTAs/SM walking
+  // lists keep more loads in flight than two staged tiles per SM; it was removed.)
+  {
     // resident CTAs per SM (tuning knob DPHY_TILE_OCC = 3 | 4 | 5 | 6)
     static const int tocc = [] { const char* e = getenv("DPHY_TILE_OCC"); return e ? atoi(e) : 4; }();
     if (tocc == 3) emat_log_G_tile_kernel<3><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);

@@ -176,7 +176,6 @@ void dphy_host_free(dphy_ctx* ctx, void* p);
  * GENERAL: always the per-event path (the only one when there is site-rate heterogeneity).  Results agree to ~1e-13. */
 #define DPHY_LOG_G_PATH_AUTO 0
 #define DPHY_LOG_G_PATH_GENERAL 1
-#define DPHY_LOG_G_PATH_GENERAL_STREAM 2   /* general path through the TMA-staged persistent kernel (uniform nu only; measured slower) */
 int  dphy_ctx_set_log_G_path(dphy_ctx* ctx, int path);
 
 /* ---- sites / evo model ------------------------------------------------------------------------------- */

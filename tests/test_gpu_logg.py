@@ -328,34 +328,6 @@ def test_upload_order_independence(ctx, orc):
     fo.close(); ds.close()
 
 
-def test_streaming_and_direct_kernels_agree(ctx, orc, monkeypatch):
-    """The TMA-staged streaming kernel and the direct-from-global tile kernel are two schedules of the same sums."""
-    items = [synth(3, seed=5), synth(0, seed=6, num_tips=700, caterpillar=1), synth(1, seed=7)]
-    tables = [db.DeviceSites(ctx, it[1]) for it in items]
-    fo = db.Forest(ctx, [it[0] for it in items], tables, sites_index=np.arange(len(items)))
-    orig_path = ctx.log_G_path
-    ctx.set_log_G_path("general_stream")                 # TMA-staged persistent kernel (+ direct kernel for oversized tiles)
-    fo.eval_log_G()
-    rp, br, _ = fo.log_G()
-    lam = [fo.lambda_i(k) for k in range(len(items))]
-    ns = [fo.num_sites_missing(k) for k in range(len(items))]
-    tl = fo.tallies()
-    ctx.set_log_G_path("general")                        # the direct kernel for every tile
-    fo.eval_log_G()
-    rp2, br2, _ = fo.log_G()
-    tl2 = fo.tallies()
-    np.testing.assert_allclose(br2, br, rtol=1e-12)
-    assert np.array_equal(rp2, rp)
-    for k in range(len(items)):
-        np.testing.assert_allclose(fo.lambda_i(k), lam[k], rtol=1e-11)
-        np.testing.assert_array_equal(fo.num_sites_missing(k), ns[k])
-        assert tl2[k]["num_muts"] == tl[k]["num_muts"] and np.array_equal(tl2[k]["num_muts_ab"], tl[k]["num_muts_ab"])
-    ctx.set_log_G_path(orig_path)
-    fo.close()
-    for t in tables:
-        t.close()
-
-
 def test_pinned_direct_upload_matches_staged_upload(orc):
     """dphy_forest_upload from page-locked caller arrays (DMA in place over two copy streams, flatten stages released by
     events) gives bit-identical device state to the staged upload of pageable arrays -- several trees, two site tables."""
