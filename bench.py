@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--spr-studies", type=int, default=128, help="full SPR studies per batch (0 disables)")
     ap.add_argument("--spr-batches-per-step", type=int, default=4)
     ap.add_argument("--e2e-chains", type=int, default=16)
+    ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (one context each) that take the e2e steps in turn")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline budget per figure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the configs 2/3/5 figures")
@@ -464,6 +465,43 @@ def main():
     assert np.allclose(forest.log_G()[2], lg, rtol=1e-12), "restoring the model does not restore log G"
     (mc_s,) = max_over_ranks([mc_s])
 
+    # ---- edit + eval: per step one branch reform per chain (the mutation times of one branch redrawn,
+    # core/subrun.cpp:316-319) shipped as rows -> dphy_forest_apply_rows -> evaluation -> log G read back.  Only the rows cross PCIe.
+    edit_rng = np.random.default_rng(99 + rank)
+    edit_steps = max(3, min(args.steps, 10))
+    edit_nodes = []
+    for e in emats:
+        has = np.nonzero((np.diff(e.mut_off) > 0) & (e.parent >= 0))[0]
+        edit_nodes.append(has[edit_rng.integers(len(has), size=edit_steps + 2)])
+
+    def edit_step(i):
+        rows, nbytes = [], 0
+        for k, e in enumerate(emats):
+            v = int(edit_nodes[k][i]); m0, m1 = int(e.mut_off[v]), int(e.mut_off[v + 1])
+            lo, hi = e.t[e.parent[v]], e.t[v]
+            e.mut_t[m0:m1] = np.sort(lo + (hi - lo) * edit_rng.random(m1 - m0))
+            r = db.node_row(k, e, v)
+            rows.append(r)
+            nbytes += C_sizeof_row + 14 * r.n_muts + 8 * r.n_miss + 5 * r.n_fs
+        forest.apply_rows(rows)
+        forest.eval_log_G()
+        return forest.log_G(), nbytes
+    import ctypes as _C
+    C_sizeof_row = _C.sizeof(db.NodeRow)
+    for i in range(2):
+        edit_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(edit_steps):
+        edit_out, edit_bytes = edit_step(2 + i)
+    torch.cuda.synchronize()
+    (edit_s,) = max_over_ranks([time.perf_counter() - t0])
+    fresh = db.Forest(ctx, emats, tables, sites_index=np.arange(args.chains))     # the edited trees, uploaded afresh
+    fresh.eval_log_G()
+    assert np.allclose(fresh.log_G()[2], edit_out[2], rtol=1e-12), "edited forest differs from a fresh upload"
+    fresh.close()
+    lg_timed, lg = lg, edit_out[2]          # the e2e leg below uploads the edited trees
+
     # ---- e2e: host buffers -> C ABI -> host scalars, copies inside the timed region ------------------------------
     n_e2e = min(args.e2e_chains, args.chains)
     e2e_emats = [e.pinned(ctx) for e in emats[:n_e2e]]        # page-locked caller arrays (dphy_host_alloc): DMA'd from where they lie
@@ -471,21 +509,53 @@ def main():
     h2d = sum(getattr(e, k).nbytes for e in e2e_emats for k in db.HostEmat.FIELDS_I32 + db.HostEmat.FIELDS_U8 + db.HostEmat.FIELDS_F64)
     d2h = n_e2e * 3 * 8
 
-    def e2e_step():
-        fo = db.Forest(ctx, e2e_emats, tables[:n_e2e], sites_index=np.arange(n_e2e))
+    # `--e2e-threads` host threads, each with its own context (stream, arena, pinned slab -- the per-thread handles the reference's
+    # threading model asks for, SURVEY.md section 8b "Threading"), take the steps in turn: while one thread's forest is being
+    # flattened / evaluated / read back, the other thread's arrays are crossing PCIe.  Every step still uploads all its inputs.
+    n_thr = max(1, args.e2e_threads)
+    e2e_ctxs = [ctx] + [db.Context(local_rank) for _ in range(n_thr - 1)]
+    e2e_tables = [tables[:n_e2e]] + [[db.DeviceSites(c, host_sites[k]) for k in range(n_e2e)] for c in e2e_ctxs[1:]]
+
+    def e2e_step(w=0):
+        fo = db.Forest(e2e_ctxs[w], e2e_emats, e2e_tables[w], sites_index=np.arange(n_e2e))
         fo.eval_log_G()
         out = fo.log_G()
         fo.close()
         return out
-    for _ in range(2):
-        e2e_step()
+
+    def e2e_run(total_steps):
+        """total_steps steps shared by the worker threads (a common counter); returns the last result of every thread"""
+        lock, nxt, outs = threading.Lock(), [0], [None] * n_thr
+
+        def worker(w):
+            torch.cuda.set_device(local_rank)
+            while True:
+                with lock:
+                    if nxt[0] >= total_steps:
+                        return
+                    nxt[0] += 1
+                outs[w] = e2e_step(w)
+        ths = [threading.Thread(target=worker, args=(w,)) for w in range(1, n_thr)]
+        for t in ths:
+            t.start()
+        worker(0)
+        for t in ths:
+            t.join()
+        for c in e2e_ctxs:
+            c.synchronize()
+        return [o for o in outs if o is not None]
+    e2e_run(2 * n_thr)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_out = e2e_step()
+    e2e_outs = e2e_run(e2e_steps)
     torch.cuda.synchronize()
     (e2e_s,) = max_over_ranks([time.perf_counter() - t0])
-    assert np.allclose(e2e_out[2], lg[:n_e2e], rtol=1e-12)
+    for e2e_out in e2e_outs:
+        assert np.allclose(e2e_out[2], lg[:n_e2e], rtol=1e-12)
+    for c, tb in zip(e2e_ctxs[1:], e2e_tables[1:]):
+        for t in tb:
+            t.close()
+        c.close()
     del e2e_emats
     forest_bytes = forest.device_bytes
     nodes0, info0 = emats[0].num_nodes, infos[0]
@@ -591,9 +661,14 @@ def main():
             "spr_candidates_per_s": (spr_regions * world / (spr_ms_max * 1e-3)) if spr_ms else None,
             "spr_regions_per_batch": spr_regions, "spr_ms_per_batch": spr_ms_max if spr_ms else None,
             "e2e": {"value": n_e2e * e2e_steps * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "chains_per_step": n_e2e, "steps": e2e_steps},
+                    "chains_per_step": n_e2e, "steps": e2e_steps, "host_threads": n_thr,
+                    "note": "per step: page-locked host arrays of every chain -> dphy_forest_upload (DMA + device-side flatten) -> evaluation -> log G read back"},
+            "e2e_edit": {"value": args.chains * edit_steps * world / edit_s, "unit": UNIT, "h2d_bytes_per_step": int(edit_bytes), "d2h_bytes_per_step": int(args.chains * 3 * 8),
+                         "ms_per_step": edit_s / edit_steps * 1e3, "chains_per_step": args.chains,
+                         "note": "per step: one branch reform per chain shipped as rows (dphy_forest_apply_rows: resident host-order arrays patched and "
+                                 "re-flattened on the device) + evaluation of every chain + log G read back; checked against a fresh upload of the edited trees"},
             "host_enqueue_ms_per_step": host_enqueue_ms, "gpu_launches": int(launches), "gpu_launches_spr": int(spr_launches), "clocks": clocks,
-            "log_G_checksum": float(np.sum(lg)),
+            "log_G_checksum": float(np.sum(lg_timed)),
         }
         if spr_ms:
             spr_alg = spr_regions * 60

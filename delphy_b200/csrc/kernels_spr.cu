@@ -991,7 +991,12 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) spr_emit_kernel(ForestDev f
 // Flat over regions: each thread reads one 32-byte head, writes one 8-byte raw log-weight; block maximum -> one ordered-integer
 // atomicMax per CTA (exact, order independent).  The above-root region needs t_S = t[region.branch]: one gather per study at most.
 constexpr int kWeightBlocks = 128;
-__global__ void __launch_bounds__(256) spr_weights_kernel(ForestDev f, SprBatchDev B) {
+__device__ __forceinline__ void ld_head_256(const RegionHead* p, unsigned long long& w0, double& t_min, double& t_max, unsigned long long& w3) {
+  long long a, b;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(w0), "=l"(a), "=l"(b), "=l"(w3) : "l"(p));
+  t_min = __longlong_as_double(a); t_max = __longlong_as_double(b);
+}
+__global__ void __launch_bounds__(256, 4) spr_weights_kernel(ForestDev f, SprBatchDev B) {
   __shared__ double s_ws[8];
   __shared__ double2 s_log[1 << kLogTabBits];
   fill_log_table(s_log);
@@ -1000,26 +1005,45 @@ __global__ void __launch_bounds__(256) spr_weights_kernel(ForestDev f, SprBatchD
   const SprStudy& S = B.studies[study];
   if (S.error || !(S.lambda_X > 0.0) || S.weights_fused) return;
   const int n = min(S.total_regions, S.region_cap);
-  const int4* heads = (const int4*)(B.slab + S.off_regions);
-  double* lw_out = (double*)(B.slab + S.off_lw);
+  const RegionHead* __restrict__ heads = (const RegionHead*)(B.slab + S.off_regions);
+  double* __restrict__ lw_out = (double*)(B.slab + S.off_lw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the study's constants in registers: the stores below could alias the study record as far as the compiler knows
+  const double fa = S.f, lam = S.lambda_X, tX = S.t_X, mu = S.mu, falam = fa * lam;
   double wmax = -CUDART_INF;
   bool any = false;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += kWeightBlocks * 256) {
-    const int4 a = __ldg(heads + 2 * (size_t)i), b = __ldg(heads + 2 * (size_t)i + 1);
-    const double t_min = __hiloint2double(a.w, a.z), t_max = __hiloint2double(b.y, b.x);
-    const int m = b.z;
-    double lw;
+  int root_i = -1, root_m = 0, root_branch = 0;      // the above-root region (one per study at most) is finished after the loop
+  auto one = [&](int i, unsigned long long w0, double t_min, double t_max, unsigned long long w3) {
+    const int m = (int)(unsigned)w3;
     if (t_min != -DBL_MAX) {
       // core/spr_study.cpp:313-318
-      const double fa = S.f, lam = S.lambda_X, t_prime = 0.5 * (t_min + t_max);
-      lw = fast_log(fa * lam * (t_max - t_min), s_log) + fa * (-lam * (S.t_X - t_prime) + m * fast_log(S.mu * (S.t_X - t_prime) / 3, s_log));
+      const double t_prime = 0.5 * (t_min + t_max);
+      const double lw = fast_log(falam * (t_max - t_min), s_log) + fa * (-lam * (tX - t_prime) + m * fast_log(mu * (tX - t_prime) / 3, s_log));
+      lw_out[i] = lw;
+      wmax = any ? fmax(wmax, lw) : lw;   // std::max semantics of the reference's running maximum
+      any = true;
     } else {
-      lw = region_log_W_above_root(S.f, S.lambda_X, S.mu, S.t_X, S.t_max_tip, m, f.t[S.node_base + f.pos_of_node[S.node_base + a.x]]);
+      root_i = i; root_m = m; root_branch = (int)(unsigned)w0;
     }
-    lw_out[i] = lw;
-    wmax = any ? fmax(wmax, lw) : lw;   // std::max semantics of the reference's running maximum
-    any = true;
+  };
+  // two regions per thread per round: both 32-byte heads are in flight before the first logarithm starts
+  int i = blockIdx.x * 256 + threadIdx.x;
+  for (; i + kWeightBlocks * 256 < n; i += 2 * kWeightBlocks * 256) {
+    unsigned long long a0, a3, b0, b3; double a1, a2, b1, b2;
+    ld_head_256(heads + i, a0, a1, a2, a3);
+    ld_head_256(heads + i + kWeightBlocks * 256, b0, b1, b2, b3);
+    one(i, a0, a1, a2, a3);
+    one(i + kWeightBlocks * 256, b0, b1, b2, b3);
+  }
+  if (i < n) {
+    unsigned long long a0, a3; double a1, a2;
+    ld_head_256(heads + i, a0, a1, a2, a3);
+    one(i, a0, a1, a2, a3);
+  }
+  if (root_i >= 0) {
+    const double lw = region_log_W_above_root(fa, lam, mu, tX, S.t_max_tip, root_m, f.t[S.node_base + f.pos_of_node[S.node_base + root_branch]]);
+    lw_out[root_i] = lw;
+    wmax = any ? fmax(wmax, lw) : lw;
   }
   double wm = warp_max(wmax);
   if (lane == 0) s_ws[warp] = wm;
@@ -1050,18 +1074,42 @@ __global__ void __launch_bounds__(256) spr_normalize_kernel(SprBatchDev B) {
   SprStudy& S = B.studies[study];
   if (S.error || !(S.lambda_X > 0.0)) return;
   const int n = min(S.total_regions, S.region_cap);
-  double2* nw = (double2*)(B.slab + S.off_nw);
+  double2* __restrict__ nw = (double2*)(B.slab + S.off_nw);
   double* part = (double*)(B.slab + S.off_part);
   const double lmax = n > 0 ? f64_from_order_key(S.max_key) : 0.0;
-  const int per = (n + kNormBlocks - 1) / kNormBlocks;
+  const int per = (((n + kNormBlocks - 1) / kNormBlocks) + 1) & ~1;      // even: every block starts on a 16-byte boundary of lw_raw
   const int i0 = min((int)blockIdx.x * per, n), i1 = min(i0 + per, n);
   double acc = 0.0;
-  const double* lw_raw = (const double*)(B.slab + S.off_lw);
-  for (int i = i0 + threadIdx.x; i < i1; i += 256) {
-    const double lw = lw_raw[i] - lmax;
-    const double w = exp(lw);
-    nw[i] = make_double2(lw, w);   // (log_W_over_Wmax, W_over_Wmax): one 16-byte store, consecutive regions contiguous
-    acc += w;
+  const double* __restrict__ lw_raw = (const double*)(B.slab + S.off_lw);
+  // a pair of regions per thread and four pairs in flight per round: 16-byte loads, 32-byte (whole-sector) stores; the summation
+  // order is fixed by (n, grid), so sum_W is bit-reproducible
+  constexpr int kU = 4;
+  for (int b0 = i0; b0 < i1; b0 += 2 * 256 * kU) {
+    double2 v[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int i = b0 + 2 * (u * 256 + (int)threadIdx.x);
+      v[u] = make_double2(0.0, 0.0);
+      if (i + 1 < i1) v[u] = __ldcs(reinterpret_cast<const double2*>(lw_raw + i));
+      else if (i < i1) v[u].x = __ldcs(lw_raw + i);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int i = b0 + 2 * (u * 256 + (int)threadIdx.x);
+      if (i < i1) {
+        const double la = v[u].x - lmax, wa = exp(la);
+        acc += wa;
+        if (i + 1 < i1) {
+          const double lb = v[u].y - lmax, wb = exp(lb);
+          acc += wb;
+          // (log_W_over_Wmax, W_over_Wmax) of two consecutive regions: one 32-byte store
+          asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(nw + i), "l"(__double_as_longlong(la)), "l"(__double_as_longlong(wa)),
+                       "l"(__double_as_longlong(lb)), "l"(__double_as_longlong(wb)) : "memory");
+        } else {
+          nw[i] = make_double2(la, wa);
+        }
+      }
+    }
   }
   acc = block_sum<double, 256>(acc, s_ws);
   if (threadIdx.x == 0) {
