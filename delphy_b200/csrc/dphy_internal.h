@@ -242,6 +242,8 @@ struct dphy_forest {
   int32_t* d_tile_ipart = nullptr;  // [num_tiles * 17]
   uint32_t* d_tree_done = nullptr;  // [num_trees] tiles finished (for last-tile reduction)
   uint32_t* d_ticket = nullptr;     // [1] dynamic tile ticket
+  // study-independent tables of the event-scan SPR path (kernels_spr_group2.cuh), built by the first grouped batch on this forest
+  int32_t* d_spr_eopen = nullptr; int32_t* d_spr_tnode = nullptr; int32_t* d_spr_ev = nullptr;
   bool evaluated = false;
   bool struct_valid = false;    // nsmn / num_muts tallies (structure-only outputs of the general log-G pass) are current
   uint32_t epoch = 0;           // look-back flag value of the current launch (flag == epoch means "published")

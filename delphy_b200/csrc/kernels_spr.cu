@@ -20,6 +20,8 @@
 #include "dphy_internal.h"
 #include "device_utils.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -58,6 +60,9 @@ struct SprStudy {
   // per-study path: one int per node (h_stride 1), tiles of kTile nodes (tile_shift 8);
   // grouped path (spr_gscan / spr_gemit, 32 studies of one tree side by side): [node][32] (h_stride 32), chunks of 32 nodes (tile_shift 5)
   int32_t h_stride, tile_shift, num_htiles, weights_fused;
+  // event-scan grouped path (kernels_spr_group2.cuh): lane of the study inside its group and the group's tables (0 => not used)
+  int32_t g2, g2_lane, g2_mut_base, g2_num_templates;
+  int64_t off_g2S, off_g2aggS, off_g2mask, off_g2aggK, off_g2cbase, off_hang;
 };
 
 // Device-side form of a candidate region: the reference's 48-byte Candidate_region (core/spr_study.h:17-32) split into a 32-byte
@@ -78,6 +83,11 @@ struct SprBatchDev {
   uint32_t* ticket;       // [S][4]
   int32_t num_studies, max_tiles;
   uint32_t epoch;
+  // study-independent tables of the forest for the event-scan path (built once per forest, dphy_forest::d_spr_*)
+  const int32_t* g2_eopen;     // [num_nodes]  tree-local index of the event at which the node opens
+  const int32_t* g2_tnode;     // [num_nodes + total mutations]  device position of the node of every region template
+  const int32_t* g2_ev;        // [2 * total mutations]  tree-local mutation index | exit << 31, in event order
+  const int32_t* g2_mut_off;   // == ForestDev::mut_off
 };
 
 __device__ __forceinline__ unsigned long long f64_order_key(double d) {
@@ -139,6 +149,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_paths_kernel(ForestDev f, S
     if (blockIdx.x == 0) {
       S.node_base = T.node_base; S.num_nodes = T.num_nodes; S.num_tiles = T.num_tiles; S.L = f.sites[T.sites_id].L;
       S.root_pos = T.node_base; S.error = 0; S.scanned = 0; S.C0 = 0; S.H0 = 0;
+      S.num_missing = 0;
       S.total_regions = 0; S.max_key = 0ULL; S.log_Wmax = 0.0; S.sum_W = 0.0;
       int posP = -1, posS = -1, nP = 0, nS = 0, Proot = 0;
       if (posX >= 0) {
@@ -179,18 +190,22 @@ __global__ void __launch_bounds__(kSetupThreads) spr_paths_kernel(ForestDev f, S
   }
 }
 
+constexpr int kXtabSlices = 2;     // CTAs per study: each owns a contiguous slice of the sites
 __global__ void __launch_bounds__(kSetupThreads) spr_xtab_kernel(ForestDev f, SprBatchDev B) {
   __shared__ int s_ws[kSetupThreads / 32];
   __shared__ int s_carry;
-  SprStudy& S = B.studies[blockIdx.x];
+  SprStudy& S = B.studies[blockIdx.y];
   const int tid = threadIdx.x;
   const TreeDev T = f.trees[S.tree];
   const SitesDev& Si = f.sites[T.sites_id];
   const int L = Si.L;
   const int X = S.X;
+  // this CTA's sites: [l0, l1), a multiple of 128 long so that no two CTAs share a line of xtab / xkey
+  const int per = ((L + kXtabSlices - 1) / kXtabSlices + 127) & ~127;
+  const int l0 = min((int)blockIdx.x * per, L), l1 = min(l0 + per, L);
   uint8_t* xtab = (uint8_t*)(B.slab + S.off_xtab);
   uint32_t* xkey = (uint32_t*)(B.slab + S.off_xkey);
-  for (int l = tid; l < L; l += kSetupThreads) { xtab[l] = Si.ref[l]; xkey[l] = 0u; }
+  for (int l = l0 + tid; l < l1; l += kSetupThreads) { xtab[l] = Si.ref[l]; xkey[l] = 0u; }
   if (tid == 0) s_carry = 0;
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
@@ -204,21 +219,22 @@ __global__ void __launch_bounds__(kSetupThreads) spr_xtab_kernel(ForestDev f, Sp
   const int xpath_len = from_tree ? S.xpath_len : (rel_start ? S.path_len : 0);
   if (from_tree) {
     // missing_at_X = union of the missation intervals on the X->root path (disjoint along a path by invariant):
-    // one warp per path node, lanes stride over the sites of each interval
+    // one warp per path node, lanes stride over the sites of each interval that fall into this CTA's slice
     for (int jj = warp; jj < xpath_len; jj += kSetupThreads / 32) {
       const int a = xpath[jj];
       for (int i = f.miss_off[a]; i < f.miss_off[a + 1]; ++i) {
         const int2 se = f.miss_se[i];
-        for (int l = se.x + lane; l < se.y; l += 32) xtab[l] |= 4;
+        for (int l = max(se.x, l0) + lane; l < min(se.y, l1); l += 32) xtab[l] |= 4;
       }
     }
   } else {
     const int32_t* ms = (const int32_t*)(B.slab + S.off_xm_start);
     const int32_t* me = (const int32_t*)(B.slab + S.off_xm_end);
     for (int i = warp; i < S.n_x_missing; i += kSetupThreads / 32)
-      for (int l = ms[i] + lane; l < me[i]; l += 32) xtab[l] |= 4;
+      for (int l = max(ms[i], l0) + lane; l < min(me[i], l1); l += 32) xtab[l] |= 4;
   }
   // last mutation per site on the path: every path mutation posts (ordinal << 2 | to) with an atomicMax on a per-site key
+  // (every CTA walks the whole path -- it is short -- and posts the mutations of its own sites)
   for (int j0 = 0; j0 < xpath_len; j0 += kSetupThreads) {
     const int j = j0 + tid;                                   // j counts from the ROOT end of the path
     const int a = j < xpath_len ? xpath[xpath_len - 1 - j] : -1;
@@ -229,8 +245,10 @@ __global__ void __launch_bounds__(kSetupThreads) spr_xtab_kernel(ForestDev f, Sp
     const int incl = block_scan_incl<int, kSetupThreads>(cnt, s_ws, &tot);
     const int base = s_carry + incl - cnt;
     if (base + cnt >= (1 << 28)) S.error = 4;
-    for (int i = 0; i < cnt; ++i)
-      atomicMax(xkey + f.mut_site[mo + i], ((uint32_t)(base + i + 1) << 2) | (uint32_t)(f.mut_code[mo + i] & 3));
+    for (int i = 0; i < cnt; ++i) {
+      const int site = f.mut_site[mo + i];
+      if (site >= l0 && site < l1) atomicMax(xkey + site, ((uint32_t)(base + i + 1) << 2) | (uint32_t)(f.mut_code[mo + i] & 3));
+    }
     __syncthreads();
     if (tid == 0) s_carry += tot;
     __syncthreads();
@@ -239,21 +257,21 @@ __global__ void __launch_bounds__(kSetupThreads) spr_xtab_kernel(ForestDev f, Sp
     const int32_t* ds = (const int32_t*)(B.slab + S.off_xd_site);
     const uint8_t* dt = (const uint8_t*)(B.slab + S.off_xd_to);
     const int base = s_carry;
-    for (int i = tid; i < S.n_x_deltas; i += kSetupThreads) atomicMax(xkey + ds[i], ((uint32_t)(base + i + 1) << 2) | (uint32_t)(dt[i] & 3));
+    for (int i = tid; i < S.n_x_deltas; i += kSetupThreads) {
+      const int site = ds[i];
+      if (site >= l0 && site < l1) atomicMax(xkey + site, ((uint32_t)(base + i + 1) << 2) | (uint32_t)(dt[i] & 3));
+    }
   }
   __syncthreads();
   int cnt = 0;
-  for (int l = tid; l < L; l += kSetupThreads) {
-    const uint32_t k = xkey[l];
+  for (int l = l0 + tid; l < l1; l += kSetupThreads) {
+    const uint32_t k = __ldcg(xkey + l);
     uint8_t x = xtab[l];
     if (k) { x = (uint8_t)((x & 4) | (k & 3)); xtab[l] = x; }
     cnt += (x >> 2) & 1;
   }
   cnt = block_sum<int, kSetupThreads>(cnt, s_ws);
-  if (tid == 0) {
-    S.num_missing = cnt;
-    S.mu = S.lambda_X / (double)(L - cnt);   // Spr_study::mu, core/spr_study.cpp:239
-  }
+  if (tid == 0 && cnt) atomicAdd(&S.num_missing, cnt);      // zeroed by spr_paths_kernel; Spr_study::mu is set by spr_segments_kernel
 }
 
 // ---- shared device helpers ----------------------------------------------------------------------------------------------------
@@ -295,9 +313,30 @@ struct SprView {
   const int32_t* path; const int2* pae; const int32_t* seg;
   int node_base, path_len;
   int stride, shift;           // SprStudy::h_stride / tile_shift
-  __device__ __forceinline__ int H(int q) const { return Hloc[(size_t)q * stride] + agg[(q >> shift) * 3 + 0]; }
+  // event-scan grouped path: H and KB come from the group's event-prefix rows / keep masks (kernels_spr_group2.cuh)
+  int g2, g2_lane, g2_mut_base, g2_num_templates;
+  const int8_t* g2S; const int32_t* g2aggS; const uint32_t* g2mask; const int32_t* g2aggK;
+  const int32_t* g2_eopen; const int32_t* g2_mut_off;
+  // H_end(q): potential at the bottom of branch q == prefix of the signed events before event eopen(q) + np(q)
+  __device__ __forceinline__ int H(int q) const {
+    if (g2) {
+      const int p = node_base + q;
+      const int e = g2_eopen[p] + (g2_mut_off[p + 1] - g2_mut_off[p]);
+      return (int)g2S[(size_t)e * 32 + g2_lane] + g2aggS[(size_t)(e >> 7) * 32 + g2_lane];
+    }
+    return Hloc[(size_t)q * stride] + agg[(q >> shift) * 3 + 0];
+  }
   __device__ __forceinline__ int C(int q) const { return Cloc[(size_t)q * stride] + agg[(q >> shift) * 3 + 1]; }
-  __device__ __forceinline__ int KB(int q) const { return KBloc[(size_t)q * stride] + agg[(q >> shift) * 3 + 2]; }
+  // KB(q): kept regions of the positions before q (q == num_nodes allowed)
+  __device__ __forceinline__ int KB(int q) const {
+    if (g2) {
+      const int p = node_base + q;
+      const int tq = q + (g2_mut_off[p] - g2_mut_base);          // template index of region (q, 0); == num_templates for q == N
+      const size_t w = (size_t)(tq >> 5) * 32 + g2_lane;
+      return g2aggK[w] + __popc(g2mask[w] & ((1u << (tq & 31)) - 1u));
+    }
+    return KBloc[(size_t)q * stride] + agg[(q >> shift) * 3 + 2];
+  }
 };
 
 __device__ __forceinline__ SprView make_view(const SprBatchDev& B, const SprStudy& S, int study) {
@@ -312,6 +351,10 @@ __device__ __forceinline__ SprView make_view(const SprBatchDev& B, const SprStud
   V.seg = (const int32_t*)(B.slab + S.off_seg);
   V.node_base = S.node_base; V.path_len = S.path_len;
   V.stride = S.h_stride; V.shift = S.tile_shift;
+  V.g2 = S.g2; V.g2_lane = S.g2_lane; V.g2_mut_base = S.g2_mut_base; V.g2_num_templates = S.g2_num_templates;
+  V.g2S = (const int8_t*)(B.slab + S.off_g2S); V.g2aggS = (const int32_t*)(B.slab + S.off_g2aggS);
+  V.g2mask = (const uint32_t*)(B.slab + S.off_g2mask); V.g2aggK = (const int32_t*)(B.slab + S.off_g2aggK);
+  V.g2_eopen = B.g2_eopen; V.g2_mut_off = B.g2_mut_off;
   return V;
 }
 
@@ -669,7 +712,25 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
   __shared__ int s_carry;
   SprStudy& S = B.studies[blockIdx.x];
   if (S.error) return;
-  spr_tile_prefix(f, B, S, blockIdx.x, 3, s_ws, &s_carry);
+  if (threadIdx.x == 0) S.mu = S.lambda_X / (double)(S.L - S.num_missing);   // Spr_study::mu, core/spr_study.cpp:239
+  if (S.g2) {
+    // event-scan path: the chunk prefixes are already final (spr_g2_prefix_kernel); only the start region's potential is missing
+    if (threadIdx.x == 0) {
+      const SprView V0 = make_view(B, S, blockIdx.x);
+      const int par = f.parent_pos[S.pos0];
+      const bool top = par < 0 || S.pos0 == S.root_pos;
+      int h = top ? 0 : V0.H(par - S.node_base);
+      if (S.pos0 != S.root_pos) {
+        const int mo = f.mut_off[S.pos0];
+        for (int i = 0; i < S.k0; ++i) { int dh, dc; mut_dc(V0.xtab, f.mut_site[mo + i], f.mut_code[mo + i] & 15, dh, dc); h += dh; }
+      }
+      S.C0 = 0; S.H0 = h; S.scanned = 3;
+      __threadfence_block();
+    }
+    __syncthreads();
+  } else {
+    spr_tile_prefix(f, B, S, blockIdx.x, 3, s_ws, &s_carry);
+  }
   const int tid = threadIdx.x;
   const SprView V = make_view(B, S, blockIdx.x);
   int32_t* seg = (int32_t*)(B.slab + S.off_seg);
@@ -717,6 +778,8 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
       int32_t* sg = seg + (size_t)j * kSegStride;
       sg[0] = base; sg[1] = base + cntA; sg[2] = base + cntA + cntOwn; sg[3] = base + cntA + cntOwn + cntSub;
       sg[4] = cntUp; sg[5] = sibpos;
+      // output offset of the regions hanging off path node j, relative to the kept-region prefix KB (spr_g2_bases_kernel / emit)
+      if (S.g2) ((int32_t*)(B.slab + S.off_hang))[j] = sg[2] - V.KB(sibpos - S.node_base);
       if (S.h_stride != 1) {
         // grouped studies: the path nodes' own regions are written here, one thread per path node (spr_gemit_kernel skips them)
         GLane L;
@@ -1130,6 +1193,7 @@ __global__ void __launch_bounds__(256) spr_normalize_kernel(SprBatchDev B) {
 }
 
 #include "kernels_spr_group.cuh"
+#include "kernels_spr_group2.cuh"
 
 // ---- pick_nexus_region / find_region ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) spr_pick_kernel(SprBatchDev B, const double* __restrict__ r_in, int32_t* __restrict__ out_idx) {
@@ -1237,6 +1301,29 @@ struct dphy_spr_batch {
 
 namespace {
 size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+// the study-independent tables of the event-scan path: built by the first grouped batch on a forest, freed with it
+int ensure_spr_tables(dphy_ctx* ctx, dphy_forest* fo) {
+  if (fo->d_spr_eopen) return DPHY_OK;
+  const size_t N = (size_t)fo->h.num_nodes, M = (size_t)fo->total_muts;
+  const size_t b_eopen = 0, b_tnode = al(sizeof(int32_t) * N), b_ev = b_tnode + al(sizeof(int32_t) * (N + M + 1));
+  const size_t b_pm = b_ev + al(sizeof(int32_t) * (2 * M + 1)), total = b_pm + al(sizeof(int32_t) * N);
+  char* d = nullptr;
+  if (cudaMallocAsync((void**)&d, total, ctx->stream) != cudaSuccess) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(spr tables)");
+  int max_nodes = 1;
+  for (const TreeDev& T : fo->trees) max_nodes = std::max(max_nodes, T.num_nodes);
+  int32_t* pm = (int32_t*)(d + b_pm);
+  spr_tab_pm_kernel<<<fo->h.num_trees, 1024, 0, ctx->stream>>>(fo->h, pm);
+  spr_tab_fill_kernel<<<dim3((max_nodes + 255) / 256, fo->h.num_trees), 256, 0, ctx->stream>>>(fo->h, pm, (int32_t*)(d + b_eopen), (int32_t*)(d + b_tnode),
+                                                                                             (int32_t*)(d + b_ev));
+  ctx->launches += 2;
+  const int st = check_cuda(ctx, cudaGetLastError(), "spr table kernels launch");
+  if (st != DPHY_OK) { cudaFreeAsync(d, ctx->stream); return st; }
+  fo->allocs.push_back(d);
+  fo->bytes += total;
+  fo->d_spr_eopen = (int32_t*)(d + b_eopen); fo->d_spr_tnode = (int32_t*)(d + b_tnode); fo->d_spr_ev = (int32_t*)(d + b_ev);
+  return DPHY_OK;
+}
 }
 
 extern "C" {
@@ -1258,7 +1345,11 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   // ---- grouping: full (unbounded) studies of the same tree go 32 at a time through the lanes-are-studies kernels ----------------
   // (DPHY_SPR_GROUPED=0 disables)
   constexpr int kMinGroup = 24;     // a group costs the same for 1 or 32 lanes: below ~24 studies the per-study kernels are cheaper
-  static const bool use_groups = [] { const char* e = getenv("DPHY_SPR_GROUPED"); return !(e && atoi(e) == 0); }();
+  // DPHY_SPR_GROUPED: 0 = every study on the per-study kernels, 1 = lanes-are-studies scan / emit over nodes (kernels_spr_group.cuh),
+  // 2 (default) = event scan + template emit (kernels_spr_group2.cuh)
+  static const int group_mode = [] { const char* e = getenv("DPHY_SPR_GROUPED"); return e ? atoi(e) : 2; }();
+  const bool use_groups = group_mode != 0;
+  const bool g2 = group_mode == 2;
   std::vector<int> group_of(n, -1), lane_of(n, 0);
   std::vector<SprGroupDev> groups;
   if (use_groups) {
@@ -1279,10 +1370,23 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
         G.num = (int32_t)std::min<size_t>(kGroup, v.size() - g0);
         for (int l = 0; l < G.num; ++l) { G.study[l] = v[g0 + l]; group_of[v[g0 + l]] = (int)groups.size(); lane_of[v[g0 + l]] = l; }
         G.off_xT = off; off = al(off + (size_t)G.L * kGroup);
-        G.off_dhT = off; off = al(off + (size_t)std::max<int64_t>(1, fo->tree_muts[k]) * kGroup);
-        G.off_dhP = off; off = al(off + sizeof(unsigned long long) * ((size_t)fo->tree_muts[k] / 32 + 4) * kGroup);
-        G.off_H = off; off = al(off + sizeof(int32_t) * (size_t)T.num_nodes * kGroup);
-        G.off_KB = off; off = al(off + sizeof(int32_t) * ((size_t)T.num_nodes + 1) * kGroup);
+        if (g2) {
+          const int64_t M = fo->tree_muts[k];
+          if (2 * M + 1 + kEvChunk > INT_MAX || (int64_t)T.num_nodes + M + 64 > INT_MAX) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: tree too large"); }
+          G.num_muts = (int32_t)M; G.num_templates = (int32_t)(T.num_nodes + M);
+          G.num_ev_chunks = (int32_t)(2 * M / kEvChunk + 1);           // rows 0 .. 2M
+          G.num_t_chunks = (G.num_templates + 31) / 32;                // + one empty chunk, so that KB(N) always has a row
+          G.off_S = off; off = al(off + (size_t)G.num_ev_chunks * kEvChunk * kGroup);
+          G.off_aggS = off; off = al(off + sizeof(int32_t) * ((size_t)G.num_ev_chunks + 1) * kGroup);
+          G.off_mask = off; off = al(off + sizeof(uint32_t) * ((size_t)G.num_t_chunks + 1) * kGroup);
+          G.off_aggK = off; off = al(off + sizeof(int32_t) * ((size_t)G.num_t_chunks + 2) * kGroup);
+          G.off_cbase = off; off = al(off + sizeof(int2) * ((size_t)G.num_t_chunks + 1) * kGroup);
+        } else {
+          G.off_dhT = off; off = al(off + (size_t)std::max<int64_t>(1, fo->tree_muts[k]) * kGroup);
+          G.off_dhP = off; off = al(off + sizeof(unsigned long long) * ((size_t)fo->tree_muts[k] / 32 + 4) * kGroup);
+          G.off_H = off; off = al(off + sizeof(int32_t) * (size_t)T.num_nodes * kGroup);
+          G.off_KB = off; off = al(off + sizeof(int32_t) * ((size_t)T.num_nodes + 1) * kGroup);
+        }
         groups.push_back(G);
       }
     }
@@ -1319,7 +1423,12 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     const int N = T.num_nodes;
     const bool grouped = group_of[i] >= 0;
     S.h_stride = grouped ? kGroup : 1; S.tile_shift = grouped ? 5 : 8;
-    S.num_htiles = grouped ? (N + kGChunk - 1) / kGChunk : T.num_tiles;
+    S.num_htiles = grouped ? (g2 ? 1 : (N + kGChunk - 1) / kGChunk) : T.num_tiles;
+    if (grouped && g2) {
+      const SprGroupDev& G = groups[group_of[i]];
+      S.g2 = 1; S.g2_lane = lane_of[i]; S.g2_mut_base = G.mut_base; S.g2_num_templates = G.num_templates;
+      S.off_g2S = G.off_S; S.off_g2aggS = G.off_aggS; S.off_g2mask = G.off_mask; S.off_g2aggK = G.off_aggK; S.off_g2cbase = G.off_cbase;
+    }
     S.weights_fused = (grouped && fuse_weights) ? 1 : 0;
     max_tiles = std::max(max_tiles, S.num_htiles);
     if (!grouped) max_tiles256 = std::max(max_tiles256, T.num_tiles);
@@ -1333,7 +1442,9 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     S.off_path = off; off = al(off + sizeof(int32_t) * S.path_cap);
     S.off_xpath = off; off = al(off + sizeof(int32_t) * S.path_cap);
     S.off_pae = off; off = al(off + sizeof(int2) * S.path_cap);
-    if (grouped) {
+    if (grouped && g2) {
+      S.off_H = 0; S.off_C = 0; S.off_KB = 0;          // unused: H and KB are read off the group's event rows / keep masks
+    } else if (grouped) {
       const SprGroupDev& G = groups[group_of[i]];
       S.off_H = G.off_H + (int64_t)sizeof(int32_t) * lane_of[i]; S.off_C = S.off_H; S.off_KB = G.off_KB + (int64_t)sizeof(int32_t) * lane_of[i];
     } else {
@@ -1342,6 +1453,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
       S.off_KB = off; off = al(off + sizeof(int32_t) * (N + 1));
     }
     S.off_seg = off; off = al(off + sizeof(int32_t) * kSegStride * (size_t)S.path_cap);
+    S.off_hang = off; if (grouped && g2) off = al(off + sizeof(int32_t) * (size_t)S.path_cap);
     S.off_part = off; off = al(off + sizeof(double) * kNormBlocks);
     S.off_tj = off; off = al(off + sizeof(int2) * (size_t)T.num_tiles);       // classify() of the first / last node of every tile
     S.off_xd_site = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_deltas));
@@ -1378,6 +1490,12 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   b->dev.ticket = (uint32_t*)(d + b_ticket);
   b->dev.slab = d + b_slab;
   b->dev.num_studies = n; b->dev.max_tiles = max_tiles; b->dev.epoch = 1;
+  b->dev.g2_eopen = nullptr; b->dev.g2_tnode = nullptr; b->dev.g2_ev = nullptr; b->dev.g2_mut_off = fo->h.mut_off;
+  if (g2 && !groups.empty()) {
+    st = ensure_spr_tables(ctx, fo);
+    if (st != DPHY_OK) { cudaFreeAsync(d, ctx->stream); delete b; return st; }
+    b->dev.g2_eopen = fo->d_spr_eopen; b->dev.g2_tnode = fo->d_spr_tnode; b->dev.g2_ev = fo->d_spr_ev;
+  }
   { static const bool dry = [] { const char* e = getenv("DPHY_SPR_DRY"); return e && atoi(e) != 0; }(); if (dry) b->dev.epoch = 777u; }
   b->d_groups = (SprGroupDev*)(d + b_groups); b->num_groups = (int32_t)groups.size();
   if (n == 0) { *out = b; return DPHY_OK; }
@@ -1412,12 +1530,21 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   const int ng = (int)groups.size();
   const bool any_single = max_tiles256 > 0;        // studies on the per-study path
   spr_paths_kernel<<<dim3((max_nodes + kSetupThreads * kPathChunks - 1) / (kSetupThreads * kPathChunks), n), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
-  spr_xtab_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
+  spr_xtab_kernel<<<dim3(kXtabSlices, n), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
   int launched = 2;
   const dim3 grid_scan((std::max(max_tiles256, 1) + kScanSub - 1) / kScanSub, n);
   if (any_single) { spr_scan_kernel<0><<<grid_scan, kTile, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
   const dim3 grid_group((group_chunks + kGWarps - 1) / kGWarps, std::max(ng, 1));
-  if (ng > 0) {
+  int g2_ev_chunks = 0, g2_t_chunks = 0;
+  for (const SprGroupDev& G : groups) { g2_ev_chunks = std::max(g2_ev_chunks, G.num_ev_chunks); g2_t_chunks = std::max(g2_t_chunks, G.num_t_chunks + 1); }
+  const dim3 grid_g2t((g2_t_chunks + kG2Warps - 1) / kG2Warps, std::max(ng, 1));
+  if (ng > 0 && g2) {
+    spr_xT_kernel<<<dim3((group_L + 255) / 256, ng), 256, 0, ctx->stream>>>(b->dev, b->d_groups);
+    spr_g2_scan_kernel<<<dim3((g2_ev_chunks + kG2Warps - 1) / kG2Warps, ng), kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    spr_g2_emit_kernel<true><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    spr_g2_prefix_kernel<<<dim3(kPfxCtas, ng, 2), 1024, 0, ctx->stream>>>(b->dev, b->d_groups);
+    launched += 4;
+  } else if (ng > 0) {
     for (const SprGroupDev& G : groups)      // the packed potentials are OR-ed together by the chunks that share a word
       cudaMemsetAsync(b->dev.slab + G.off_dhP, 0, sizeof(unsigned long long) * ((size_t)fo->tree_muts[G.tree] / 32 + 4) * kGroup, ctx->stream);
     spr_xT_kernel<<<dim3((group_L + 255) / 256, ng), 256, 0, ctx->stream>>>(b->dev, b->d_groups);
@@ -1442,7 +1569,11 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     else spr_emit_kernel<4><<<grid_emit, kTile, 0, ctx->stream>>>(fo->h, b->dev);
     ++launched;
   }
-  if (ng > 0) {
+  if (ng > 0 && g2) {
+    spr_g2_bases_kernel<<<dim3((g2_t_chunks + 255) / 256, kGroup, ng), 256, 0, ctx->stream>>>(b->dev, b->d_groups);
+    spr_g2_emit_kernel<false><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    launched += 2;
+  } else if (ng > 0) {
     spr_gemit_kernel<<<grid_group, kGWarps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
     ++launched;
   }

@@ -32,6 +32,13 @@ struct SprGroupDev {
   int64_t off_dhT;              // i8  [M_tree][32] potential of every mutation of the tree for every study
   int64_t off_dhP;              // u64 [M_tree / 32 + 4][32] the same, 2 bits each (dh + 1): 32 consecutive mutations per word
   int64_t off_H, off_KB;        // i32 [N][32], i32 [N + 1][32]
+  // event-scan path (kernels_spr_group2.cuh)
+  int32_t num_muts, num_templates, num_ev_chunks, num_t_chunks;   // M of the tree; N + M; chunks of 128 events / 32 templates
+  int64_t off_S;                // i8  [num_ev_chunks * 128][32]  chunk-local prefix of the signed potentials before every event
+  int64_t off_aggS;             // i32 [num_ev_chunks + 1][32]    chunk totals, then their exclusive prefixes
+  int64_t off_mask;             // u32 [num_t_chunks + 1][32]     keep flags of the 32 templates of a chunk, per study
+  int64_t off_aggK;             // i32 [num_t_chunks + 2][32]     kept regions per chunk, then their exclusive prefixes
+  int64_t off_cbase;            // int2 [num_t_chunks + 1][32]    (output index of the chunk's first kept region, path index j | straddles << 30)
 };
 
 __global__ void __launch_bounds__(256) spr_xT_kernel(SprBatchDev B, const SprGroupDev* __restrict__ groups) {
