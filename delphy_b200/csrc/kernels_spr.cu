@@ -62,7 +62,8 @@ struct SprStudy {
   int32_t h_stride, tile_shift, num_htiles, weights_fused;
   // event-scan grouped path (kernels_spr_group2.cuh): lane of the study inside its group and the group's tables (0 => not used)
   int32_t g2, g2_lane, g2_mut_base, g2_num_templates;
-  int64_t off_g2S, off_g2aggS, off_g2mask, off_g2aggK, off_g2cbase, off_hang;
+  int64_t off_g2S, off_g2aggS, off_g2mask, off_g2aggK, off_g2cbase, off_hang, off_hmix;
+  int32_t hmix_cap, pad3;
 };
 
 // Device-side form of a candidate region: the reference's 48-byte Candidate_region (core/spr_study.h:17-32) split into a 32-byte
@@ -668,6 +669,7 @@ struct GLane {            // what a study carries through the grouped emit
   const int32_t* agg;
   int region_cap, path_len, H0, init_min_muts;
   double tX;
+  double* lw; unsigned long long* max_key;      // fused weights: raw log-weights of the study, its running maximum (ordered key)
 };
 
 __device__ __forceinline__ void g_store_region(const GLane& L, int idx, int branch, int mut_idx, double t_min, double t_max, int m) {
@@ -681,8 +683,11 @@ __device__ __forceinline__ void g_store_region(const GLane& L, int idx, int bran
   }
 }
 
+__device__ __noinline__ double region_log_W_above_root(double fa, double lam, double mu, double t_X, double t_max_tip, int m, double tS);
+
 // Same arithmetic as the per-study emit kernel (eval_region + the segment bases), walking the node's regions in order.
-// sg = the segment record of path index j = classify(p).
+// sg = the segment record of path index j = classify(p).  When the study's weights are fused into the emit (event-scan path), the
+// raw log-weight of each of these few regions is written here as well (core/spr_study.cpp:306-376).
 __device__ void g_emit_node_general(const ForestDev& f, const SprStudy& S, const SprView& V, const GLane& L, int p, const int32_t* sg, int j, bool on_path) {
   const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
   const int par = f.parent_pos[p];
@@ -691,6 +696,7 @@ __device__ void g_emit_node_general(const ForestDev& f, const SprStudy& S, const
   int Hk = is_root ? 0 : V.H(par - S.node_base);
   const int kA = (j == 0) ? S.k0 : np;
   int n_up = 0, n_own = 0, rank = 0;
+  unsigned long long best = 0ULL;       // fused weights: largest raw log-weight of this node's regions, as an ordered key
   const int base_off = on_path ? 0 : sg[2] - V.KB(sg[5] - S.node_base) + V.KB(p - S.node_base);
   for (int k = is_root ? np : 0; k <= np; ++k) {
     const RegionEval r = eval_region(f, S, p, k, np, moff, tPar, tNode);
@@ -700,10 +706,23 @@ __device__ void g_emit_node_general(const ForestDev& f, const SprStudy& S, const
       else if (k == kA) idx = sg[0];
       else if (k > kA) idx = sg[1] + n_own++;
       else idx = sg[3] + (sg[4] - 1 - n_up++);
-      g_store_region(L, idx, r.branch, r.mut_idx, r.t_min, r.t_max, L.init_min_muts + (Hk - L.H0));
+      const int m = L.init_min_muts + (Hk - L.H0);
+      g_store_region(L, idx, r.branch, r.mut_idx, r.t_min, r.t_max, m);
+      if (S.weights_fused && idx >= 0 && idx < L.region_cap) {
+        double lw;
+        if (r.t_min != -DBL_MAX) {
+          const double t_prime = 0.5 * (r.t_min + r.t_max);
+          lw = log(S.f * S.lambda_X * (r.t_max - r.t_min)) + S.f * (-S.lambda_X * (S.t_X - t_prime) + m * log(S.mu * (S.t_X - t_prime) / 3));
+        } else {
+          lw = region_log_W_above_root(S.f, S.lambda_X, S.mu, S.t_X, S.t_max_tip, m, f.t[S.node_base + f.pos_of_node[S.node_base + r.branch]]);
+        }
+        L.lw[idx] = lw;
+        if (lw == lw) { const unsigned long long key = f64_order_key(lw); if (key > best) best = key; }
+      }
     }
     if (k < np && !is_root) { int dh, dc; mut_dc(V.xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc); Hk += dh; }
   }
+  if (best != 0ULL) atomicMax(L.max_key, best);
 }
 
 // ---- (3) segment bases along the start->root path ---------------------------------------------------------------------------------------
@@ -785,6 +804,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
         GLane L;
         L.out = (RegionHead*)(B.slab + S.off_regions); L.pae = V.pae; L.seg = V.seg; L.agg = V.agg;
         L.region_cap = S.region_cap; L.path_len = S.path_len; L.H0 = S.H0; L.init_min_muts = S.init_min_muts; L.tX = S.t_X;
+        L.lw = (double*)(B.slab + S.off_lw); L.max_key = &S.max_key;
         g_emit_node_general(f, S, V, L, V.path[j], sg, j, true);
       }
     }
@@ -802,6 +822,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
         GLane L;
         L.out = (RegionHead*)(B.slab + S.off_regions); L.pae = V.pae; L.seg = V.seg; L.agg = V.agg;
         L.region_cap = S.region_cap; L.path_len = S.path_len; L.H0 = S.H0; L.init_min_muts = S.init_min_muts; L.tX = S.t_X;
+        L.lw = (double*)(B.slab + S.off_lw); L.max_key = &S.max_key;
         g_emit_node_general(f, S, V, L, p, seg + (size_t)j * kSegStride, j, false);
       }
     }
@@ -1381,6 +1402,10 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
           G.off_mask = off; off = al(off + sizeof(uint32_t) * ((size_t)G.num_t_chunks + 1) * kGroup);
           G.off_aggK = off; off = al(off + sizeof(int32_t) * ((size_t)G.num_t_chunks + 2) * kGroup);
           G.off_cbase = off; off = al(off + sizeof(int2) * ((size_t)G.num_t_chunks + 1) * kGroup);
+          G.off_consts = off; off = al(off + 32 * kGroup);
+          G.off_outs = off; off = al(off + 64 * kGroup);
+          if (g0 == 0) { G.trec_owner = 1; G.off_trec = off; off = al(off + 48 * (size_t)G.num_templates); }
+          else { G.trec_owner = 0; G.off_trec = groups[groups.size() - g0 / kGroup].off_trec; }
         } else {
           G.off_dhT = off; off = al(off + (size_t)std::max<int64_t>(1, fo->tree_muts[k]) * kGroup);
           G.off_dhP = off; off = al(off + sizeof(unsigned long long) * ((size_t)fo->tree_muts[k] / 32 + 4) * kGroup);
@@ -1393,7 +1418,9 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   }
   // (raw log-weights inside the grouped emit were measured slower than the dense weights pass over the stored heads: the two logs
   // per region then run at the emit's ~45 % lane utilisation and low occupancy, 1.26 ms vs 0.68 + 0.23 ms per 128 studies)
-  const bool fuse_weights = false;
+  // The event-scan emit computes the raw log-weights itself (DPHY_SPR_FUSE_WEIGHTS=0: dense pass over the stored heads instead)
+  static const bool fuse_env = [] { const char* e = getenv("DPHY_SPR_FUSE_WEIGHTS"); return !(e && atoi(e) == 0); }();
+  const bool fuse_weights = g2 && fuse_env;
   for (int i = 0; i < n; ++i) {
     const dphy_spr_request& r = reqs[i];
     SprStudy& S = b->host[i];
@@ -1429,7 +1456,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
       S.g2 = 1; S.g2_lane = lane_of[i]; S.g2_mut_base = G.mut_base; S.g2_num_templates = G.num_templates;
       S.off_g2S = G.off_S; S.off_g2aggS = G.off_aggS; S.off_g2mask = G.off_mask; S.off_g2aggK = G.off_aggK; S.off_g2cbase = G.off_cbase;
     }
-    S.weights_fused = (grouped && fuse_weights) ? 1 : 0;
+    S.weights_fused = (grouped && fuse_weights && r.lambda_X > 0.0) ? 1 : 0;
     max_tiles = std::max(max_tiles, S.num_htiles);
     if (!grouped) max_tiles256 = std::max(max_tiles256, T.num_tiles);
     // exact upper bound on regions: every non-root node has n+1 regions, the root has 1
@@ -1454,6 +1481,9 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     }
     S.off_seg = off; off = al(off + sizeof(int32_t) * kSegStride * (size_t)S.path_cap);
     S.off_hang = off; if (grouped && g2) off = al(off + sizeof(int32_t) * (size_t)S.path_cap);
+    // chunks that straddle a segment boundary of the study: at most two per path node
+    S.hmix_cap = (grouped && g2) ? 2 * S.path_cap + 2 : 0;
+    S.off_hmix = off; off = al(off + sizeof(int32_t) * 32 * (size_t)S.hmix_cap);
     S.off_part = off; off = al(off + sizeof(double) * kNormBlocks);
     S.off_tj = off; off = al(off + sizeof(int2) * (size_t)T.num_tiles);       // classify() of the first / last node of every tile
     S.off_xd_site = off; off = al(off + sizeof(int32_t) * std::max(1, S.n_x_deltas));
@@ -1535,13 +1565,19 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   const dim3 grid_scan((std::max(max_tiles256, 1) + kScanSub - 1) / kScanSub, n);
   if (any_single) { spr_scan_kernel<0><<<grid_scan, kTile, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
   const dim3 grid_group((group_chunks + kGWarps - 1) / kGWarps, std::max(ng, 1));
-  int g2_ev_chunks = 0, g2_t_chunks = 0;
-  for (const SprGroupDev& G : groups) { g2_ev_chunks = std::max(g2_ev_chunks, G.num_ev_chunks); g2_t_chunks = std::max(g2_t_chunks, G.num_t_chunks + 1); }
+  int g2_ev_chunks = 0, g2_t_chunks = 0, g2_templates = 1;
+  for (const SprGroupDev& G : groups) {
+    g2_ev_chunks = std::max(g2_ev_chunks, G.num_ev_chunks); g2_t_chunks = std::max(g2_t_chunks, G.num_t_chunks + 1);
+    g2_templates = std::max(g2_templates, G.num_templates);
+  }
   const dim3 grid_g2t((g2_t_chunks + kG2Warps - 1) / kG2Warps, std::max(ng, 1));
   if (ng > 0 && g2) {
     spr_xT_kernel<<<dim3((group_L + 255) / 256, ng), 256, 0, ctx->stream>>>(b->dev, b->d_groups);
+    spr_g2_consts_kernel<<<ng, kGroup, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    spr_g2_templ_kernel<<<dim3((g2_templates + 255) / 256, ng), 256, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    launched += 2;
     spr_g2_scan_kernel<<<dim3((g2_ev_chunks + kG2Warps - 1) / kG2Warps, ng), kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
-    spr_g2_emit_kernel<true><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    spr_g2_emit_kernel<0><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
     spr_g2_prefix_kernel<<<dim3(kPfxCtas, ng, 2), 1024, 0, ctx->stream>>>(b->dev, b->d_groups);
     launched += 4;
   } else if (ng > 0) {
@@ -1571,7 +1607,8 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   }
   if (ng > 0 && g2) {
     spr_g2_bases_kernel<<<dim3((g2_t_chunks + 255) / 256, kGroup, ng), 256, 0, ctx->stream>>>(b->dev, b->d_groups);
-    spr_g2_emit_kernel<false><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    if (fuse_weights) spr_g2_emit_kernel<2><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    else spr_g2_emit_kernel<1><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
     launched += 2;
   } else if (ng > 0) {
     spr_gemit_kernel<<<grid_group, kGWarps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);

@@ -38,7 +38,10 @@ struct SprGroupDev {
   int64_t off_aggS;             // i32 [num_ev_chunks + 1][32]    chunk totals, then their exclusive prefixes
   int64_t off_mask;             // u32 [num_t_chunks + 1][32]     keep flags of the 32 templates of a chunk, per study
   int64_t off_aggK;             // i32 [num_t_chunks + 2][32]     kept regions per chunk, then their exclusive prefixes
-  int64_t off_cbase;            // int2 [num_t_chunks + 1][32]    (output index of the chunk's first kept region, path index j | straddles << 30)
+  int64_t off_cbase;            // int2 [num_t_chunks + 1][32]    (output offset of the chunk's kept regions, 0) or (row in the study's hmix, 1)
+  int64_t off_trec;             // G2Templ [num_templates]        study-independent template records (shared by the groups of a tree)
+  int64_t off_consts, off_outs; // G2Const [32], G2Out [32]
+  int32_t trec_owner, pad2;     // this group writes the tree's template records
 };
 
 __global__ void __launch_bounds__(256) spr_xT_kernel(SprBatchDev B, const SprGroupDev* __restrict__ groups) {

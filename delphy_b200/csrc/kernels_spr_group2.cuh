@@ -160,165 +160,300 @@ __global__ void __cluster_dims__(kPfxCtas, 1, 1) __launch_bounds__(1024) spr_g2_
 }
 
 // ---- keep masks (kCount) / emit over templates ---------------------------------------------------------------------------------------------
-struct G2Study {            // what the template loop needs of a study: 3 broadcast 16-byte shared loads per (chunk, study)
-  double tX; int qX, xe;    // X's subtree = [qX, xe) in tree-local positions (empty when X is detached)
-  int qS, qP, q0, cap;      // S, P, the start node; region capacity
-  int base, mH; unsigned out_lo, out_hi;   // hang + kept regions before the chunk; init_min_muts - H0; the study's head array
+// What a template is, independent of the study: written once per batch and tree (spr_g2_templ_kernel), so that the two template
+// kernels start from one 48-byte record per lane instead of a three-level chain of gathers through the node arrays.
+struct alignas(16) G2Templ {
+  double t_min, t_max;            // (t_min, t_max] of region (q, k) before any clipping; the root's t_min is unused
+  int idn, k, q, qend;            // host node id, mutation index, tree-local position, end of the node's subtree
+  int e, nonroot, moff, np;       // event-prefix row of the region; parent exists; the node's list (global offset, length)
 };
+// What the template loop needs of a study: constants of the batch (spr_g2_consts_kernel, after the X tables) ...
+struct alignas(16) G2Const {
+  double tX; int qX, xe;          // X's subtree = [qX, xe) in tree-local positions (empty when X is detached); tX = -DBL_MAX: dead lane
+  int qS, qP, q0, cap;            // S, P, the start node; region capacity
+};
+// ... and what is known once the segments are laid out (spr_g2_bases_kernel)
+struct alignas(16) G2Out {
+  int mH, fused; unsigned long long out;     // init_min_muts - H0; weights computed by the emit; the study's head array
+  double logfl, fa, lam, mu3;                // log(f lambda_X), f, lambda_X, mu / 3   (Spr_study::Spr_study, core/spr_study.cpp:239,313-318)
+  long long lw_minus_out, pad;               // raw log-weight array relative to the head array, in bytes
+};
+struct alignas(16) G2Study { G2Const c; int base, mH; unsigned out_lo, out_hi; };
+struct alignas(16) G2Weight { double logfl, fa, lam, mu3; long long lw_minus_out; int fused, pad; };
+static_assert(sizeof(G2Templ) == 48 && sizeof(G2Const) == 32 && sizeof(G2Out) == 64 && sizeof(G2Study) == 48, "record sizes are part of the slab layout");
+
+__global__ void __launch_bounds__(256) spr_g2_templ_kernel(ForestDev f, SprBatchDev B, const SprGroupDev* __restrict__ groups) {
+  const SprGroupDev& G = groups[blockIdx.y];
+  if (!G.trec_owner) return;                       // one group per tree writes the records; the others share them
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= G.num_templates) return;
+  const int nb = G.node_base, mb = G.mut_base;
+  const int p = __ldg(B.g2_tnode + (size_t)nb + mb + r);
+  const int q = p - nb;
+  const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
+  const int k = r - (q + (moff - mb));
+  const int par = f.parent_pos[p];
+  G2Templ T;
+  T.nonroot = par >= 0;
+  const double tn = f.t[p], tp = T.nonroot ? f.t[par] : 0.0;
+  T.t_min = k == 0 ? tp : f.mut_t[moff + k - 1];
+  T.t_max = k >= np ? tn : f.mut_t[moff + k];
+  T.idn = f.node_id[p]; T.k = k; T.q = q; T.qend = q + f.subtree_size[p];
+  T.e = B.g2_eopen[p] + k; T.moff = moff; T.np = np;
+  ((G2Templ*)(B.slab + G.off_trec))[r] = T;
+}
+
+__global__ void spr_g2_consts_kernel(ForestDev f, SprBatchDev B, const SprGroupDev* __restrict__ groups) {
+  const SprGroupDev& G = groups[blockIdx.x];
+  const int lane = threadIdx.x;
+  const int nb = G.node_base;
+  G2Const c;
+  c.tX = -DBL_MAX; c.qX = -1; c.xe = -1; c.qS = -1; c.qP = -1; c.q0 = 0; c.cap = 0;
+  if (lane < G.num) {
+    const SprStudy& S = B.studies[G.study[lane]];
+    if (!S.error) {
+      c.tX = S.t_X;
+      if (S.posX >= 0) { c.qX = S.posX - nb; c.xe = S.posX - nb + f.subtree_size[S.posX]; c.qS = S.posS - nb; c.qP = S.posP - nb; }
+      c.q0 = S.pos0 - nb; c.cap = S.region_cap;
+    }
+  }
+  ((G2Const*)(B.slab + G.off_consts))[lane] = c;
+}
 
 // ---- per (chunk, study): where the chunk's kept regions go -------------------------------------------------------------------------------
 // The regions of an off-path node go to  hang[j] + KB(node) + rank,  j = the deepest node of the study's start->root path that
 // contains the node.  j is constant over long runs of positions, so it is found ONCE per (template chunk, study) here -- one thread
 // each, the binary search over the study's nested path ranges running out of L1 (every thread of a CTA searches the same study) --
 // instead of in the emit kernel's prologue, where ten dependent loads per warp were its critical path.  A chunk whose positions
-// straddle a segment boundary of the study is flagged; its lanes step from j on their own (g2_lane_hang).
-__global__ void __launch_bounds__(256) spr_g2_bases_kernel(SprBatchDev B, const SprGroupDev* __restrict__ groups) {
-  const SprGroupDev& G = groups[blockIdx.z];
-  const int s = blockIdx.y;
-  const int tc = blockIdx.x * 256 + threadIdx.x;
-  if (s >= G.num || tc > G.num_t_chunks) return;
-  const SprStudy& S = B.studies[G.study[s]];
-  int2* out = (int2*)(B.slab + G.off_cbase) + (size_t)tc * kGroup + s;
-  const uint32_t mask = ((const uint32_t*)(B.slab + G.off_mask))[(size_t)tc * kGroup + s];
-  if (S.error || mask == 0u) { *out = make_int2(0, 0); return; }
-  const int nb = G.node_base, NT = G.num_templates;
-  const int32_t* tn = B.g2_tnode + (size_t)nb + G.mut_base;
-  const int pfirst = __ldg(tn + tc * 32), plast = __ldg(tn + min(tc * 32 + 31, NT - 1));
-  const int2* __restrict__ pae = (const int2*)(B.slab + S.off_pae);
-  int lo = 0, hi = S.path_len - 1;
+// straddle a segment boundary of the study (at most two per path node) gets a row of per-template offsets instead, filled by the
+// whole warp, one lane per template.
+__device__ __forceinline__ int g2_classify(const int2* __restrict__ pae, int path_len, int p, int lo = 0, int hi = -1) {
+  if (hi < 0) hi = path_len - 1;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     const int2 ae = __ldg(pae + mid);
-    if (pfirst >= ae.x && pfirst < ae.y) hi = mid; else lo = mid + 1;
+    if (p >= ae.x && p < ae.y) hi = mid; else lo = mid + 1;
   }
-  const int j = lo;
-  const int2 cur = __ldg(pae + j);
-  const int dnx = j > 0 ? __ldg(pae + j - 1).x : INT_MAX;
-  const bool mixed = (plast >= cur.y) || (dnx > pfirst && dnx <= plast);
-  const int base = ((const int32_t*)(B.slab + S.off_hang))[j] + ((const int32_t*)(B.slab + G.off_aggK))[(size_t)tc * kGroup + s];
-  *out = make_int2(base, j | (mixed ? (1 << 30) : 0));
+  return lo;
 }
 
-// slow path of a (chunk, study) pair that straddles a segment boundary of the study: the lane's own segment, stepped from the
-// chunk's first node (the deepest path node containing p is monotone in p on either side of the start node)
-__device__ __noinline__ int g2_lane_hang(const SprBatchDev& B, int sidx, int j, int p) {
-  const SprStudy& S = B.studies[sidx];
+__global__ void __launch_bounds__(256) spr_g2_bases_kernel(SprBatchDev B, const SprGroupDev* __restrict__ groups) {
+  const unsigned full = 0xffffffffu;
+  const SprGroupDev& G = groups[blockIdx.z];
+  const int s = blockIdx.y, lane = threadIdx.x & 31;
+  const int tc = blockIdx.x * 256 + threadIdx.x;
+  if (s >= G.num) return;
+  const int sidx = G.study[s];
+  SprStudy& S = B.studies[sidx];
+  if (S.error) return;
+  const int nb = G.node_base, NT = G.num_templates;
+  const G2Templ* __restrict__ trec = (const G2Templ*)(B.slab + G.off_trec);
   const int2* __restrict__ pae = (const int2*)(B.slab + S.off_pae);
-  const int last = S.path_len - 1;
-  while (j < last && p >= __ldg(pae + j).y) ++j;
-  while (j > 0) { const int2 d = __ldg(pae + j - 1); if (p >= d.x && p < d.y) --j; else break; }
-  return ((const int32_t*)(B.slab + S.off_hang))[j];
+  const int32_t* __restrict__ hang = (const int32_t*)(B.slab + S.off_hang);
+  const int path_len = S.path_len;
+  if (tc == 0) {
+    G2Out o; o.mH = S.init_min_muts - S.H0; o.fused = S.weights_fused; o.out = (unsigned long long)(B.slab + S.off_regions);
+    o.logfl = log(S.f * S.lambda_X); o.fa = S.f; o.lam = S.lambda_X; o.mu3 = S.mu / 3;
+    o.lw_minus_out = (long long)(S.off_lw - S.off_regions); o.pad = 0;
+    ((G2Out*)(B.slab + G.off_outs))[s] = o;
+  }
+  bool mixed = false;
+  int j = 0, jlo = 0, jhi = 0;        // straddling chunks: every template's path index lies in [jlo, jhi]
+  if (tc <= G.num_t_chunks) {
+    int2* out = (int2*)(B.slab + G.off_cbase) + (size_t)tc * kGroup + s;
+    const uint32_t mask = ((const uint32_t*)(B.slab + G.off_mask))[(size_t)tc * kGroup + s];
+    if (mask == 0u) *out = make_int2(0, 0);
+    else {
+      const int pfirst = nb + trec[tc * 32].q, plast = nb + trec[min(tc * 32 + 31, NT - 1)].q;
+      j = g2_classify(pae, path_len, pfirst);
+      const int2 cur = __ldg(pae + j);
+      const int dnx = j > 0 ? __ldg(pae + j - 1).x : INT_MAX;
+      mixed = (plast >= cur.y) || (dnx > pfirst && dnx <= plast);
+      if (!mixed) *out = make_int2(hang[j] + ((const int32_t*)(B.slab + G.off_aggK))[(size_t)tc * kGroup + s], 0);
+      else {
+        // the path index is monotone in the position on either side of the start node (0 inside its subtree)
+        const int jl = g2_classify(pae, path_len, plast);
+        jlo = (S.pos0 >= pfirst && S.pos0 <= plast) ? 0 : min(j, jl);
+        jhi = max(j, jl);
+      }
+    }
+  }
+  // straddling chunks: a row of 32 per-template offsets each, rows handed out by a per-study counter
+  unsigned todo = __ballot_sync(full, mixed);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int tcs = __shfl_sync(full, tc, src), lo_s = __shfl_sync(full, jlo, src), hi_s = __shfl_sync(full, jhi, src);
+    int row = 0;
+    if (lane == src) row = (int)atomicAdd(B.ticket + sidx * 4 + 3, 1u);
+    row = __shfl_sync(full, row, src);
+    if (row >= S.hmix_cap) { if (lane == src) S.error = 6; continue; }
+    const int r = tcs * 32 + lane;
+    int h = 0;
+    if (r < NT) h = hang[g2_classify(pae, path_len, nb + trec[r].q, lo_s, hi_s)];
+    ((int32_t*)(B.slab + S.off_hmix))[(size_t)row * 32 + lane] = h + ((const int32_t*)(B.slab + G.off_aggK))[(size_t)tcs * kGroup + s];
+    if (lane == src) ((int2*)(B.slab + G.off_cbase))[(size_t)tcs * kGroup + s] = make_int2(row, 1);
+  }
 }
 
-__device__ __noinline__ bool g2_special_keep(const ForestDev& f, const SprBatchDev& B, int sidx, int p, int k, int np, int moff, double tp, double tn) {
-  return eval_region(f, B.studies[sidx], p, k, np, moff, tp, tn).keep;
+__device__ __noinline__ bool g2_special_keep(const ForestDev& f, const SprBatchDev& B, int sidx, int p, int k, int np, int moff) {
+  const int par = f.parent_pos[p];
+  return eval_region(f, B.studies[sidx], p, k, np, moff, par >= 0 ? f.t[par] : 0.0, f.t[p]).keep;
 }
 
-template <bool kCount>
+// kMode 0: keep masks + counts;  1: emit the 32-byte heads;  2: emit + raw log-weights (and their per-study maximum)
+template <int kMode>
 __global__ void __launch_bounds__(kG2Warps * 32) spr_g2_emit_kernel(ForestDev f, SprBatchDev B, const SprGroupDev* __restrict__ groups) {
+  constexpr bool kCount = kMode == 0, kFuse = kMode == 2;
   __shared__ G2Study s_st[kG2Warps][kGroup];
+  __shared__ G2Weight s_wt[kFuse ? kG2Warps : 1][kFuse ? kGroup : 1];
+  __shared__ double2 s_log[kFuse ? (1 << kLogTabBits) : 1];
+  if (kFuse) { fill_log_table(s_log); __syncthreads(); }
   const unsigned full = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SprGroupDev& G = groups[blockIdx.y];
   const int tc = blockIdx.x * kG2Warps + warp;
   if (tc > G.num_t_chunks) return;                    // chunk num_t_chunks exists (empty): KB(N) reads its row
-  const int nb = G.node_base, mb = G.mut_base, NT = G.num_templates;
+  const int nb = G.node_base, NT = G.num_templates;
   uint32_t* maskp = (uint32_t*)(B.slab + G.off_mask) + (size_t)tc * kGroup;
   int32_t* aggKp = (int32_t*)(B.slab + G.off_aggK) + (size_t)tc * kGroup;
 
-  // ---- the lane's template -----------------------------------------------------------------------------------------------------------------
+  // ---- the lane's study (everything one level deep) -----------------------------------------------------------------------------------
+  G2Study st;
+  st.c = ((const G2Const*)(B.slab + G.off_consts))[lane];
+  st.base = 0; st.mH = 0; st.out_lo = 0u; st.out_hi = 0u;
+  uint32_t mymask = 0u;
+  int2 cb = make_int2(0, 0);
+  bool fused_lane = false;                                // (kFuse) the lane's study gets its weights here
+  unsigned long long mykey = 0ULL;                        // (kFuse) running maximum of the lane's study, as an ordered key
+  if (!kCount) {
+    mymask = maskp[lane];
+    cb = ((const int2*)(B.slab + G.off_cbase))[(size_t)tc * kGroup + lane];
+    const G2Out* op = (const G2Out*)(B.slab + G.off_outs) + lane;
+    const int4 o0 = *reinterpret_cast<const int4*>(op);
+    st.base = cb.x; st.mH = o0.x; st.out_lo = (unsigned)o0.z; st.out_hi = (unsigned)o0.w;
+    if (kFuse) {
+      G2Weight w; w.logfl = op->logfl; w.fa = op->fa; w.lam = op->lam; w.mu3 = op->mu3; w.lw_minus_out = op->lw_minus_out; w.fused = o0.y; w.pad = 0;
+      s_wt[warp][lane] = w;
+      fused_lane = o0.y != 0;
+    }
+    if (st.c.tX == -DBL_MAX) mymask = 0u;
+  }
+  // ---- the lane's template ---------------------------------------------------------------------------------------------------------------
   const int r = tc * 32 + lane;
   const bool valid = r < NT;
-  const int p = valid ? __ldg(B.g2_tnode + (size_t)nb + mb + r) : nb;
-  const int q = p - nb;
-  const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
-  const int k = r - (q + (moff - mb));
-  const int par = f.parent_pos[p];
-  const bool nonroot = par >= 0;
-  const double tn = f.t[p], tp = nonroot ? f.t[par] : 0.0;
-  const double t_min = (k == 0 || !valid) ? tp : f.mut_t[moff + k - 1];
-  const double t_max = (k >= np || !valid) ? tn : f.mut_t[moff + k];
-
-  // ---- the lane's study ---------------------------------------------------------------------------------------------------------------------
-  const bool active = lane < G.num;
-  const int sidx = G.study[active ? lane : 0];
-  const SprStudy& S = B.studies[sidx];
-  const bool ok = active && !S.error;
-  uint32_t mymask = 0u;
-  int jst = 0;                  // classify() of the chunk's first node
-  bool mixed = false;
-  {
-    G2Study st;
-    st.tX = ok ? S.t_X : -DBL_MAX;             // nothing starts before -DBL_MAX: an inactive lane keeps nothing
-    const int posX = S.posX;
-    st.qX = posX >= 0 ? posX - nb : -1; st.xe = posX >= 0 ? posX - nb + f.subtree_size[posX] : -1;
-    st.qS = S.posS >= 0 ? S.posS - nb : -1; st.qP = S.posP >= 0 ? S.posP - nb : -1; st.q0 = S.pos0 - nb; st.cap = S.region_cap;
-    st.base = 0; st.mH = 0; st.out_lo = 0u; st.out_hi = 0u;
-    if (!kCount) {
-      mymask = maskp[lane];
-      if (ok && mymask != 0u) {
-        const int2 cb = ((const int2*)(B.slab + G.off_cbase))[(size_t)tc * kGroup + lane];
-        st.base = cb.x; jst = cb.y & 0x3fffffff; mixed = (cb.y >> 30) & 1;
-        st.mH = S.init_min_muts - S.H0;
-        const unsigned long long o = (unsigned long long)(B.slab + S.off_regions);
-        st.out_lo = (unsigned)o; st.out_hi = (unsigned)(o >> 32);
-      } else mymask = 0u;
-    }
-    s_st[warp][lane] = st;
+  G2Templ T;
+  T.t_min = DBL_MAX; T.t_max = DBL_MAX; T.idn = 0; T.k = 0; T.q = -2; T.qend = -2; T.e = 0; T.nonroot = 0; T.moff = 0; T.np = 0;
+  if (valid) {
+    const uint4* tp = reinterpret_cast<const uint4*>((const G2Templ*)(B.slab + G.off_trec) + r);
+    const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+    T.t_min = __hiloint2double(a.y, a.x); T.t_max = __hiloint2double(a.w, a.z);
+    T.idn = b.x; T.k = b.y; T.q = b.z; T.qend = b.w; T.e = c.x; T.nonroot = c.y; T.moff = c.z; T.np = c.w;
   }
-  __syncwarp();
   if (!kCount && !__any_sync(full, mymask != 0u)) return;
+  const bool nonroot = T.nonroot != 0;
+  const int q = T.q;
 
-  int cnt_mine = 0;
-  const int qend = q + f.subtree_size[p];
-  const int idn = f.node_id[p];
-  // chunk-local potentials of the lane's template for the 32 studies: one 32-byte row
+  // chunk-local potentials of the lane's template for the 32 studies: one 32-byte row; the chunk prefixes of the event chunk of the
+  // warp's first template are folded into the study constants, the (few) lanes in a later event chunk add the difference
   uint4 row0 = make_uint4(0u, 0u, 0u, 0u), row1 = row0;
-  const int32_t* aggrow = nullptr;
+  const int32_t* aggrow = nullptr; const int32_t* aggrow0 = nullptr;
+  bool uniform = true;
+  unsigned deadmask = 0u, specmask = 0u;      // (kCount) studies that keep nothing here / that have S, P or the root in this chunk
   if (!kCount) {
-    const int e = valid ? B.g2_eopen[p] + k : 0;
-    const uint4* rp = reinterpret_cast<const uint4*>(B.slab + G.off_S + (size_t)e * kGroup);
+    const uint4* rp = reinterpret_cast<const uint4*>(B.slab + G.off_S + (size_t)T.e * kGroup);
     row0 = __ldg(rp); row1 = __ldg(rp + 1);
-    aggrow = (const int32_t*)(B.slab + G.off_aggS) + (size_t)(e >> 7) * kGroup;
+    const int ec = T.e >> 7, ec0 = __shfl_sync(full, ec, 0);
+    aggrow = (const int32_t*)(B.slab + G.off_aggS) + (size_t)ec * kGroup;
+    aggrow0 = (const int32_t*)(B.slab + G.off_aggS) + (size_t)ec0 * kGroup;
+    uniform = __all_sync(full, !valid || ec == ec0);
+    st.mH += aggrow0[lane];
+  } else {
+    // studies that can keep nothing of this chunk: everything here starts at or after t_X, or lies inside X's subtree -- unless one of
+    // the chunk's nodes follows the general rules (S, P, the root)
+    double tmin_w = (valid && nonroot) ? T.t_min : DBL_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmin_w = fmin(tmin_w, __shfl_xor_sync(full, tmin_w, o));
+    const int qfirst = __shfl_sync(full, q, 0), qlast = __shfl_sync(full, q, max(0, min(31, NT - 1 - tc * 32)));
+    const bool has_special = (st.c.qS >= qfirst && st.c.qS <= qlast) || (st.c.qP >= qfirst && st.c.qP <= qlast) || qfirst == 0;
+    const bool dead = st.c.tX == -DBL_MAX || (!has_special && (st.c.tX <= tmin_w || (qfirst >= st.c.qX && qlast < st.c.xe)));
+    deadmask = __ballot_sync(full, dead);
+    specmask = __ballot_sync(full, has_special && st.c.tX != -DBL_MAX);
+    if (NT <= tc * 32) { deadmask = full; specmask = 0u; }      // the empty chunk past the last template
   }
+  s_st[warp][lane] = st;
+  __syncwarp();
+  int cnt_mine = 0;
   const unsigned lt = (1u << lane) - 1u;
+  // log(t_max - t_min) of the unclipped region: shared by every study that does not clip it
+  double logdt = 0.0;
+  if (kFuse) logdt = fast_log(T.t_max - T.t_min, s_log);
 
 #pragma unroll
   for (int s = 0; s < kGroup; ++s) {
-    const G2Study& st = s_st[warp][s];
+    const G2Study& ss = s_st[warp][s];
     if (kCount) {
-      const double tX = st.tX;
-      bool keep = valid && nonroot && t_min < tX && !(q >= st.qX && q < st.xe);
-      if (valid && (q == st.qS || q == st.qP || !nonroot)) {
-        // S, P (relabelled by account_for_Xs_detachment) and the root follow the general rules, as in node_kept_count
-        keep = false;
-        if (tX != -DBL_MAX && (nonroot || k == np)) keep = g2_special_keep(f, B, G.study[s], p, k, np, moff, tp, tn);
-      }
+      if ((deadmask >> s) & 1u) continue;
+      // (studies with S, P or the root in this chunk are redone under the general rules after the loop)
+      const bool keep = valid && nonroot && T.t_min < ss.c.tX && !(q >= ss.c.qX && q < ss.c.xe);
       const unsigned bal = __ballot_sync(full, keep);
       if (lane == s) { mymask = bal; cnt_mine = __popc(bal); }
     } else {
       const unsigned bal = __shfl_sync(full, mymask, s);
       if (bal == 0u) continue;
-      const bool special = q == st.qS || q == st.qP || !nonroot || (q <= st.q0 && st.q0 < qend);
+      const bool special = q == ss.c.qS || q == ss.c.qP || !nonroot || (q <= ss.c.q0 && ss.c.q0 < T.qend);
       const bool emit = ((bal >> lane) & 1u) && !special;
-      int base = st.base;
-      if (__shfl_sync(full, (int)mixed, s)) {
-        const int js = __shfl_sync(full, jst, s);
-        if (emit) base = g2_lane_hang(B, G.study[s], js, p) + aggKp[s];
+      int base = ss.base;
+      if (__shfl_sync(full, cb.y, s)) {
+        // a chunk that straddles a segment boundary of this study: per-template offsets (spr_g2_bases_kernel); base is the row
+        const SprStudy& S = B.studies[G.study[s]];
+        base = ((const int32_t*)(B.slab + S.off_hmix))[(size_t)base * 32 + lane];
       }
       const int idx = base + __popc(bal & lt);
-      if (emit && idx >= 0 && idx < st.cap) {
+      unsigned long long key = 0ULL;
+      if (emit && idx >= 0 && idx < ss.c.cap) {
         const unsigned w = s < 16 ? (s < 8 ? (s < 4 ? row0.x : row0.y) : (s < 12 ? row0.z : row0.w))
                                   : (s < 24 ? (s < 20 ? row1.x : row1.y) : (s < 28 ? row1.z : row1.w));
         const int hloc = (int)(w << (24 - 8 * (s & 3))) >> 24;                // sign-extended byte s of the row
-        const int m = st.mH + hloc + __ldg(aggrow + s);
-        const double tmx = t_max > st.tX ? st.tX : t_max;
-        char* o = (char*)(((unsigned long long)st.out_hi << 32) | st.out_lo) + (size_t)idx * sizeof(RegionHead);
-        const unsigned long long w0 = (unsigned long long)(unsigned)idn | ((unsigned long long)(unsigned)k << 32);
-        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o), "l"(w0), "l"(__double_as_longlong(t_min)),
+        int m = ss.mH + hloc;
+        if (!uniform) m += __ldg(aggrow + s) - __ldg(aggrow0 + s);
+        const double tmx = T.t_max > ss.c.tX ? ss.c.tX : T.t_max;
+        char* o = (char*)(((unsigned long long)ss.out_hi << 32) | ss.out_lo) + (size_t)idx * sizeof(RegionHead);
+        const unsigned long long w0 = (unsigned long long)(unsigned)T.idn | ((unsigned long long)(unsigned)T.k << 32);
+        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o), "l"(w0), "l"(__double_as_longlong(T.t_min)),
                      "l"(__double_as_longlong(tmx)), "l"((unsigned long long)(unsigned)m) : "memory");
+        if (kFuse && s_wt[warp][s].fused) {
+          // raw log-weight (core/spr_study.cpp:313-318): log(f lam dt) + f (-lam (t_X - t') + m log(mu (t_X - t') / 3)), t' = mid-point
+          const G2Weight& w8 = s_wt[warp][s];
+          const double x = ss.c.tX - 0.5 * (T.t_min + tmx);
+          const double ldt = T.t_max > ss.c.tX ? fast_log(ss.c.tX - T.t_min, s_log) : logdt;
+          const double lw = (w8.logfl + ldt) + w8.fa * (-(w8.lam * x) + m * fast_log(w8.mu3 * x, s_log));
+          *reinterpret_cast<double*>(o - (size_t)idx * sizeof(RegionHead) + w8.lw_minus_out + (size_t)idx * sizeof(double)) = lw;
+          key = f64_order_key(lw);
+        }
+      }
+      if (kFuse) {
+        // warp maximum of the ordered keys (two 32-bit REDUX steps), kept by the lane that owns study s
+        const unsigned hi = (unsigned)(key >> 32), mh = __reduce_max_sync(full, hi);
+        const unsigned ml = __reduce_max_sync(full, hi == mh ? (unsigned)key : 0u);
+        if (lane == s) { const unsigned long long k2 = ((unsigned long long)mh << 32) | ml; if (k2 > mykey) mykey = k2; }
       }
     }
   }
-  if (kCount) { maskp[lane] = mymask; aggKp[lane] = cnt_mine; }
+  if (kCount) {
+    // S, P (relabelled by account_for_Xs_detachment) and the root follow the general rules, as in node_kept_count
+    for (unsigned sm = specmask; sm; sm &= sm - 1u) {
+      const int s = __ffs(sm) - 1;
+      const G2Const c = s_st[warp][s].c;
+      bool keep = valid && nonroot && T.t_min < c.tX && !(q >= c.qX && q < c.xe);
+      if (valid && (q == c.qS || q == c.qP || !nonroot)) {
+        keep = false;
+        if (nonroot || T.k == T.np) keep = g2_special_keep(f, B, G.study[s], nb + q, T.k, T.np, T.moff);
+      }
+      const unsigned bal = __ballot_sync(full, keep);
+      if (lane == s) { mymask = bal; cnt_mine = __popc(bal); }
+    }
+    maskp[lane] = mymask; aggKp[lane] = cnt_mine;
+  }
+  if (kFuse && fused_lane && mykey != 0ULL) atomicMax(&B.studies[G.study[lane]].max_key, mykey);
 }
