@@ -137,16 +137,24 @@ __device__ __noinline__ double dev_gamma_q(double a, double x) {
 constexpr int kSetupThreads = 1024;
 constexpr int kPathChunks = 8;     // chunks of kSetupThreads positions per CTA of spr_paths_kernel
 
+constexpr int kPathStudies = 8;    // studies per CTA of spr_paths_kernel: studies of the same tree share every subtree_size load
 __global__ void __launch_bounds__(kSetupThreads) spr_paths_kernel(ForestDev f, SprBatchDev B) {
-  __shared__ int s_v[4];   // pos0, posX, depth[pos0], depth[posX]
-  SprStudy& S = B.studies[blockIdx.y];
+  __shared__ int s_pos0[kPathStudies], s_posX[kPathStudies], s_d0[kPathStudies], s_dX[kPathStudies];
+  __shared__ int s_nb[kPathStudies], s_N[kPathStudies], s_tree[kPathStudies];
+  __shared__ long long s_path[kPathStudies], s_pae[kPathStudies], s_xpath[kPathStudies];
   const int tid = threadIdx.x;
-  const TreeDev T = f.trees[S.tree];
-  if ((long long)blockIdx.x * kSetupThreads * kPathChunks >= T.num_nodes) return;
-  if (tid == 0) {
+  const int sb = blockIdx.y * kPathStudies;
+  const int ns = min(kPathStudies, B.num_studies - sb);
+  if (tid < ns) {
+    SprStudy& S = B.studies[sb + tid];
+    const TreeDev T = f.trees[S.tree];
     const int pos0 = T.node_base + f.pos_of_node[T.node_base + S.start_branch];
     const int posX = S.X >= 0 ? T.node_base + f.pos_of_node[T.node_base + S.X] : -1;
-    s_v[0] = pos0; s_v[1] = posX; s_v[2] = f.depth[pos0]; s_v[3] = posX >= 0 ? f.depth[posX] : -1;
+    const int dep0 = f.depth[pos0], depX = posX >= 0 ? f.depth[posX] : -1;
+    s_pos0[tid] = pos0; s_posX[tid] = posX;
+    s_d0[tid] = min(dep0 + 1, S.path_cap) - 1; s_dX[tid] = posX >= 0 ? min(depX + 1, S.path_cap) - 1 : -1;
+    s_nb[tid] = T.node_base; s_N[tid] = T.num_nodes; s_tree[tid] = S.tree;
+    s_path[tid] = S.off_path; s_pae[tid] = S.off_pae; s_xpath[tid] = S.off_xpath;
     if (blockIdx.x == 0) {
       S.node_base = T.node_base; S.num_nodes = T.num_nodes; S.num_tiles = T.num_tiles; S.L = f.sites[T.sites_id].L;
       S.root_pos = T.node_base; S.error = 0; S.scanned = 0; S.C0 = 0; S.H0 = 0;
@@ -166,28 +174,32 @@ __global__ void __launch_bounds__(kSetupThreads) spr_paths_kernel(ForestDev f, S
       S.pos0 = pos0; S.k0 = S.start_mut_idx; S.n0 = f.mut_off[pos0 + 1] - f.mut_off[pos0];
       if (S.k0 < 0 || S.k0 > S.n0 || (pos0 == T.node_base && S.k0 != S.n0)) S.error = 2;
       if (posX >= 0 && pos0 >= posX && pos0 < posX + f.subtree_size[posX]) S.error = 3;   // start inside X's subtree
-      S.path_len = min(s_v[2] + 1, S.path_cap);
-      S.xpath_len = posX >= 0 ? min(s_v[3] + 1, S.path_cap) : 0;
+      S.path_len = min(dep0 + 1, S.path_cap);
+      S.xpath_len = posX >= 0 ? min(depX + 1, S.path_cap) : 0;
     }
   }
   __syncthreads();
-  const int pos0 = s_v[0], posX = s_v[1];
-  const int d0 = min(s_v[2] + 1, S.path_cap) - 1, dX = posX >= 0 ? min(s_v[3] + 1, S.path_cap) - 1 : -1;
-  // each CTA sweeps kPathChunks chunks: the three dependent loads above are paid once per 8,192 positions
+  // each CTA sweeps kPathChunks chunks of positions for its studies: the dependent loads above are paid once per 8,192 positions
   for (int ch = 0; ch < kPathChunks; ++ch) {
-  const int p = T.node_base + (blockIdx.x * kPathChunks + ch) * kSetupThreads + tid;
-  if (p < T.node_base + T.num_nodes && p <= max(pos0, posX)) {
-    const int end = p + f.subtree_size[p];
-    const bool a0 = p <= pos0 && end > pos0, aX = posX >= 0 && p <= posX && end > posX;
-    if (a0 || aX) {
-      const int d = f.depth[p];
-      if (a0 && d0 - d >= 0) {
-        ((int32_t*)(B.slab + S.off_path))[d0 - d] = p;
-        ((int2*)(B.slab + S.off_pae))[d0 - d] = make_int2(p, end);     // classify() searches these nested [start, end) ranges
+    const int q = (blockIdx.x * kPathChunks + ch) * kSetupThreads + tid;      // tree-local position
+    int size = 0, dep = -1, cur_tree = -1;
+    for (int k = 0; k < ns; ++k) {
+      const int pos0 = s_pos0[k], posX = s_posX[k];
+      const int p = s_nb[k] + q;
+      if (q >= s_N[k] || p > max(pos0, posX)) continue;
+      if (s_tree[k] != cur_tree) { size = f.subtree_size[p]; dep = -1; cur_tree = s_tree[k]; }
+      const int end = p + size;
+      const bool a0 = p <= pos0 && end > pos0, aX = posX >= 0 && p <= posX && end > posX;
+      if (a0 || aX) {
+        if (dep < 0) dep = f.depth[p];
+        const int d0 = s_d0[k], dX = s_dX[k];
+        if (a0 && d0 - dep >= 0) {
+          ((int32_t*)(B.slab + s_path[k]))[d0 - dep] = p;
+          ((int2*)(B.slab + s_pae[k]))[d0 - dep] = make_int2(p, end);     // classify() searches these nested [start, end) ranges
+        }
+        if (aX && dX - dep >= 0) ((int32_t*)(B.slab + s_xpath[k]))[dX - dep] = p;
       }
-      if (aX && dX - d >= 0) ((int32_t*)(B.slab + S.off_xpath))[dX - d] = p;
     }
-  }
   }
 }
 
@@ -1559,7 +1571,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   for (const SprGroupDev& G : groups) { group_chunks = std::max(group_chunks, G.num_chunks); group_L = std::max(group_L, G.L); }
   const int ng = (int)groups.size();
   const bool any_single = max_tiles256 > 0;        // studies on the per-study path
-  spr_paths_kernel<<<dim3((max_nodes + kSetupThreads * kPathChunks - 1) / (kSetupThreads * kPathChunks), n), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
+  spr_paths_kernel<<<dim3((max_nodes + kSetupThreads * kPathChunks - 1) / (kSetupThreads * kPathChunks), (n + kPathStudies - 1) / kPathStudies), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
   spr_xtab_kernel<<<dim3(kXtabSlices, n), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
   int launched = 2;
   const dim3 grid_scan((std::max(max_tiles256, 1) + kScanSub - 1) / kScanSub, n);
@@ -1606,7 +1618,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     ++launched;
   }
   if (ng > 0 && g2) {
-    spr_g2_bases_kernel<<<dim3((g2_t_chunks + 255) / 256, kGroup, ng), 256, 0, ctx->stream>>>(b->dev, b->d_groups);
+    spr_g2_bases_kernel<<<dim3(kGroup, ng, kBasesSlices), kBasesThreads, 0, ctx->stream>>>(b->dev, b->d_groups);
     if (fuse_weights) spr_g2_emit_kernel<2><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
     else spr_g2_emit_kernel<1><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
     launched += 2;

@@ -237,62 +237,91 @@ __device__ __forceinline__ int g2_classify(const int2* __restrict__ pae, int pat
   return lo;
 }
 
-__global__ void __launch_bounds__(256) spr_g2_bases_kernel(SprBatchDev B, const SprGroupDev* __restrict__ groups) {
-  const unsigned full = 0xffffffffu;
-  const SprGroupDev& G = groups[blockIdx.z];
-  const int s = blockIdx.y, lane = threadIdx.x & 31;
-  const int tc = blockIdx.x * 256 + threadIdx.x;
+constexpr int kBasesPathSmem = 2048;      // path nodes whose ranges / offsets are staged in shared memory (deeper paths are read in place)
+constexpr int kBasesThreads = 256, kBasesSlices = 16;
+__global__ void __launch_bounds__(kBasesThreads) spr_g2_bases_kernel(SprBatchDev B, const SprGroupDev* __restrict__ groups) {
+  __shared__ int2 s_pae[kBasesPathSmem];
+  __shared__ int s_hang[kBasesPathSmem];
+  const SprGroupDev& G = groups[blockIdx.y];
+  const int s = blockIdx.x;
   if (s >= G.num) return;
   const int sidx = G.study[s];
   SprStudy& S = B.studies[sidx];
   if (S.error) return;
   const int nb = G.node_base, NT = G.num_templates;
   const G2Templ* __restrict__ trec = (const G2Templ*)(B.slab + G.off_trec);
-  const int2* __restrict__ pae = (const int2*)(B.slab + S.off_pae);
-  const int32_t* __restrict__ hang = (const int32_t*)(B.slab + S.off_hang);
   const int path_len = S.path_len;
-  if (tc == 0) {
+  const int2* pae = (const int2*)(B.slab + S.off_pae);
+  const int32_t* hang = (const int32_t*)(B.slab + S.off_hang);
+  if (path_len <= kBasesPathSmem) {
+    for (int i = threadIdx.x; i < path_len; i += kBasesThreads) { s_pae[i] = pae[i]; s_hang[i] = hang[i]; }
+    pae = s_pae; hang = s_hang;
+  }
+  if (threadIdx.x == 0 && blockIdx.z == 0) {
     G2Out o; o.mH = S.init_min_muts - S.H0; o.fused = S.weights_fused; o.out = (unsigned long long)(B.slab + S.off_regions);
     o.logfl = log(S.f * S.lambda_X); o.fa = S.f; o.lam = S.lambda_X; o.mu3 = S.mu / 3;
     o.lw_minus_out = (long long)(S.off_lw - S.off_regions); o.pad = 0;
     ((G2Out*)(B.slab + G.off_outs))[s] = o;
   }
-  bool mixed = false;
-  int j = 0, jlo = 0, jhi = 0;        // straddling chunks: every template's path index lies in [jlo, jhi]
-  if (tc <= G.num_t_chunks) {
-    int2* out = (int2*)(B.slab + G.off_cbase) + (size_t)tc * kGroup + s;
-    const uint32_t mask = ((const uint32_t*)(B.slab + G.off_mask))[(size_t)tc * kGroup + s];
-    if (mask == 0u) *out = make_int2(0, 0);
-    else {
-      const int pfirst = nb + trec[tc * 32].q, plast = nb + trec[min(tc * 32 + 31, NT - 1)].q;
-      j = g2_classify(pae, path_len, pfirst);
-      const int2 cur = __ldg(pae + j);
-      const int dnx = j > 0 ? __ldg(pae + j - 1).x : INT_MAX;
-      mixed = (plast >= cur.y) || (dnx > pfirst && dnx <= plast);
-      if (!mixed) *out = make_int2(hang[j] + ((const int32_t*)(B.slab + G.off_aggK))[(size_t)tc * kGroup + s], 0);
+  __syncthreads();
+  const uint32_t* __restrict__ maskcol = (const uint32_t*)(B.slab + G.off_mask) + s;
+  const int32_t* __restrict__ aggKcol = (const int32_t*)(B.slab + G.off_aggK) + s;
+  int2* cbase = (int2*)(B.slab + G.off_cbase) + s;
+  int32_t* hmix = (int32_t*)(B.slab + S.off_hmix);
+  const int pos0 = S.pos0;
+  auto classify = [&](int p, int lo, int hi) {
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const int2 ae = pae[mid];
+      if (p >= ae.x && p < ae.y) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  };
+  // the study's chunks are split over gridDim.z CTAs; a warp takes 32 consecutive chunks per round
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int per = ((G.num_t_chunks + 1 + (int)gridDim.z - 1) / (int)gridDim.z + 31) & ~31;
+  const int c0 = (int)blockIdx.z * per, c1 = min(c0 + per, G.num_t_chunks + 1);
+  for (int tb = c0 + (int)(threadIdx.x & ~31u); tb < c1; tb += kBasesThreads) {
+    const int tc = tb + lane;
+    bool mixed = false;
+    int jlo = 0, jhi = 0, kb = 0;
+    if (tc < c1) {
+      const uint32_t mask = maskcol[(size_t)tc * kGroup];
+      if (mask == 0u) cbase[(size_t)tc * kGroup] = make_int2(0, 0);
       else {
-        // the path index is monotone in the position on either side of the start node (0 inside its subtree)
-        const int jl = g2_classify(pae, path_len, plast);
-        jlo = (S.pos0 >= pfirst && S.pos0 <= plast) ? 0 : min(j, jl);
-        jhi = max(j, jl);
+        kb = aggKcol[(size_t)tc * kGroup];
+        const int pfirst = nb + trec[tc * 32].q, plast = nb + trec[min(tc * 32 + 31, NT - 1)].q;
+        const int j = classify(pfirst, 0, path_len - 1);
+        const int2 cur = pae[j];
+        const int dnx = j > 0 ? pae[j - 1].x : INT_MAX;
+        mixed = (plast >= cur.y) || (dnx > pfirst && dnx <= plast);
+        if (!mixed) cbase[(size_t)tc * kGroup] = make_int2(hang[j] + kb, 0);
+        else {
+          // the path index is monotone in the position on either side of the start node (and 0 inside its subtree): this brackets
+          // the search of every template of the chunk
+          const int jl = classify(plast, 0, path_len - 1);
+          jlo = (pos0 >= pfirst && pos0 <= plast) ? 0 : min(j, jl);
+          jhi = max(j, jl);
+        }
       }
     }
-  }
-  // straddling chunks: a row of 32 per-template offsets each, rows handed out by a per-study counter
-  unsigned todo = __ballot_sync(full, mixed);
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int tcs = __shfl_sync(full, tc, src), lo_s = __shfl_sync(full, jlo, src), hi_s = __shfl_sync(full, jhi, src);
-    int row = 0;
-    if (lane == src) row = (int)atomicAdd(B.ticket + sidx * 4 + 3, 1u);
-    row = __shfl_sync(full, row, src);
-    if (row >= S.hmix_cap) { if (lane == src) S.error = 6; continue; }
-    const int r = tcs * 32 + lane;
-    int h = 0;
-    if (r < NT) h = hang[g2_classify(pae, path_len, nb + trec[r].q, lo_s, hi_s)];
-    ((int32_t*)(B.slab + S.off_hmix))[(size_t)row * 32 + lane] = h + ((const int32_t*)(B.slab + G.off_aggK))[(size_t)tcs * kGroup + s];
-    if (lane == src) ((int2*)(B.slab + G.off_cbase))[(size_t)tcs * kGroup + s] = make_int2(row, 1);
+    // chunks that straddle a segment boundary of the study: a row of 32 per-template offsets each, one lane per template
+    unsigned todo = __ballot_sync(full, mixed);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int tcs = tb + src, lo_s = __shfl_sync(full, jlo, src), hi_s = __shfl_sync(full, jhi, src), kb_s = __shfl_sync(full, kb, src);
+      int row = 0;
+      if (lane == src) row = (int)atomicAdd(B.ticket + sidx * 4 + 3, 1u);
+      row = __shfl_sync(full, row, src);
+      if (row >= S.hmix_cap) { if (lane == src) S.error = 6; continue; }
+      const int r = tcs * 32 + lane;
+      int h = 0;
+      if (r < NT) h = hang[classify(nb + trec[r].q, lo_s, hi_s)];
+      hmix[(size_t)row * 32 + lane] = h + kb_s;
+      if (lane == src) cbase[(size_t)tcs * kGroup] = make_int2(row, 1);
+    }
   }
 }
 
@@ -356,13 +385,17 @@ __global__ void __launch_bounds__(kG2Warps * 32) spr_g2_emit_kernel(ForestDev f,
 
   // chunk-local potentials of the lane's template for the 32 studies: one 32-byte row; the chunk prefixes of the event chunk of the
   // warp's first template are folded into the study constants, the (few) lanes in a later event chunk add the difference
-  uint4 row0 = make_uint4(0u, 0u, 0u, 0u), row1 = row0;
+  // (kept in shared memory, 36-byte pitch: the study loop is not fully unrolled -- 32 copies of its body, two logarithms each, do not
+  // fit the instruction cache: ncu showed "no instruction" as the top stall -- so the byte of study s is a dynamic index)
+  __shared__ uint32_t s_row[kCount ? 1 : kG2Warps][kCount ? 1 : 32][9];
   const int32_t* aggrow = nullptr; const int32_t* aggrow0 = nullptr;
   bool uniform = true;
   unsigned deadmask = 0u, specmask = 0u;      // (kCount) studies that keep nothing here / that have S, P or the root in this chunk
   if (!kCount) {
     const uint4* rp = reinterpret_cast<const uint4*>(B.slab + G.off_S + (size_t)T.e * kGroup);
-    row0 = __ldg(rp); row1 = __ldg(rp + 1);
+    const uint4 row0 = __ldg(rp), row1 = __ldg(rp + 1);
+    uint32_t* rw = s_row[warp][lane];
+    rw[0] = row0.x; rw[1] = row0.y; rw[2] = row0.z; rw[3] = row0.w; rw[4] = row1.x; rw[5] = row1.y; rw[6] = row1.z; rw[7] = row1.w;
     const int ec = T.e >> 7, ec0 = __shfl_sync(full, ec, 0);
     aggrow = (const int32_t*)(B.slab + G.off_aggS) + (size_t)ec * kGroup;
     aggrow0 = (const int32_t*)(B.slab + G.off_aggS) + (size_t)ec0 * kGroup;
@@ -375,7 +408,9 @@ __global__ void __launch_bounds__(kG2Warps * 32) spr_g2_emit_kernel(ForestDev f,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmin_w = fmin(tmin_w, __shfl_xor_sync(full, tmin_w, o));
     const int qfirst = __shfl_sync(full, q, 0), qlast = __shfl_sync(full, q, max(0, min(31, NT - 1 - tc * 32)));
-    const bool has_special = (st.c.qS >= qfirst && st.c.qS <= qlast) || (st.c.qP >= qfirst && st.c.qP <= qlast) || qfirst == 0;
+    // ... or X's subtree starts or ends inside the chunk (the main loop below only compares times)
+    const bool has_special = (st.c.qS >= qfirst && st.c.qS <= qlast) || (st.c.qP >= qfirst && st.c.qP <= qlast) || qfirst == 0 ||
+                             (st.c.qX > qfirst && st.c.qX <= qlast) || (st.c.xe > qfirst && st.c.xe <= qlast);
     const bool dead = st.c.tX == -DBL_MAX || (!has_special && (st.c.tX <= tmin_w || (qfirst >= st.c.qX && qlast < st.c.xe)));
     deadmask = __ballot_sync(full, dead);
     specmask = __ballot_sync(full, has_special && st.c.tX != -DBL_MAX);
@@ -385,17 +420,19 @@ __global__ void __launch_bounds__(kG2Warps * 32) spr_g2_emit_kernel(ForestDev f,
   __syncwarp();
   int cnt_mine = 0;
   const unsigned lt = (1u << lane) - 1u;
+  const bool live = valid && nonroot;
   // log(t_max - t_min) of the unclipped region: shared by every study that does not clip it
   double logdt = 0.0;
   if (kFuse) logdt = fast_log(T.t_max - T.t_min, s_log);
 
-#pragma unroll
+#pragma unroll 4
   for (int s = 0; s < kGroup; ++s) {
     const G2Study& ss = s_st[warp][s];
     if (kCount) {
       if ((deadmask >> s) & 1u) continue;
-      // (studies with S, P or the root in this chunk are redone under the general rules after the loop)
-      const bool keep = valid && nonroot && T.t_min < ss.c.tX && !(q >= ss.c.qX && q < ss.c.xe);
+      // (studies with S, P, the root or an end of X's subtree in this chunk are redone under the general rules after the loop; a chunk
+      // wholly inside X's subtree is dead)
+      const bool keep = live && T.t_min < ss.c.tX;
       const unsigned bal = __ballot_sync(full, keep);
       if (lane == s) { mymask = bal; cnt_mine = __popc(bal); }
     } else {
@@ -412,9 +449,7 @@ __global__ void __launch_bounds__(kG2Warps * 32) spr_g2_emit_kernel(ForestDev f,
       const int idx = base + __popc(bal & lt);
       unsigned long long key = 0ULL;
       if (emit && idx >= 0 && idx < ss.c.cap) {
-        const unsigned w = s < 16 ? (s < 8 ? (s < 4 ? row0.x : row0.y) : (s < 12 ? row0.z : row0.w))
-                                  : (s < 24 ? (s < 20 ? row1.x : row1.y) : (s < 28 ? row1.z : row1.w));
-        const int hloc = (int)(w << (24 - 8 * (s & 3))) >> 24;                // sign-extended byte s of the row
+        const int hloc = reinterpret_cast<const int8_t*>(s_row[kCount ? 0 : warp][kCount ? 0 : lane])[s];   // chunk-local prefix, study s
         int m = ss.mH + hloc;
         if (!uniform) m += __ldg(aggrow + s) - __ldg(aggrow0 + s);
         const double tmx = T.t_max > ss.c.tX ? ss.c.tX : T.t_max;
