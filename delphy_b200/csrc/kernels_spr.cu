@@ -1414,10 +1414,17 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
           G.off_mask = off; off = al(off + sizeof(uint32_t) * ((size_t)G.num_t_chunks + 1) * kGroup);
           G.off_aggK = off; off = al(off + sizeof(int32_t) * ((size_t)G.num_t_chunks + 2) * kGroup);
           G.off_cbase = off; off = al(off + sizeof(int2) * ((size_t)G.num_t_chunks + 1) * kGroup);
-          G.off_consts = off; off = al(off + 32 * kGroup);
+          G.off_consts = off; off = al(off + 32 * kGroup + sizeof(int32_t) * kGroup);      // G2Const [32] + root_keep [32]
           G.off_outs = off; off = al(off + 64 * kGroup);
-          if (g0 == 0) { G.trec_owner = 1; G.off_trec = off; off = al(off + 48 * (size_t)G.num_templates); }
-          else { G.trec_owner = 0; G.off_trec = groups[groups.size() - g0 / kGroup].off_trec; }
+          if (g0 == 0) {
+            G.trec_owner = 1; G.off_trec = off; off = al(off + 48 * (size_t)G.num_templates);
+            G.off_csort = off; off = al(off + sizeof(double) * 32 * ((size_t)G.num_t_chunks + 1));
+            G.off_cpm = off; off = al(off + sizeof(uint32_t) * 32 * ((size_t)G.num_t_chunks + 1));
+            G.off_cq = off; off = al(off + sizeof(int2) * ((size_t)G.num_t_chunks + 1));
+          } else {
+            const SprGroupDev& G0 = groups[groups.size() - g0 / kGroup];
+            G.trec_owner = 0; G.off_trec = G0.off_trec; G.off_csort = G0.off_csort; G.off_cpm = G0.off_cpm; G.off_cq = G0.off_cq;
+          }
         } else {
           G.off_dhT = off; off = al(off + (size_t)std::max<int64_t>(1, fo->tree_muts[k]) * kGroup);
           G.off_dhP = off; off = al(off + sizeof(unsigned long long) * ((size_t)fo->tree_muts[k] / 32 + 4) * kGroup);
@@ -1586,10 +1593,10 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   if (ng > 0 && g2) {
     spr_xT_kernel<<<dim3((group_L + 255) / 256, ng), 256, 0, ctx->stream>>>(b->dev, b->d_groups);
     spr_g2_consts_kernel<<<ng, kGroup, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
-    spr_g2_templ_kernel<<<dim3((g2_templates + 255) / 256, ng), 256, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    spr_g2_templ_kernel<<<dim3((g2_t_chunks * 32 + 255) / 256, ng), 256, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
     launched += 2;
     spr_g2_scan_kernel<<<dim3((g2_ev_chunks + kG2Warps - 1) / kG2Warps, ng), kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
-    spr_g2_emit_kernel<0><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    spr_g2_count_kernel<<<dim3((g2_t_chunks + kCountWarps * kCountPerWarp - 1) / (kCountWarps * kCountPerWarp), ng), kCountWarps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
     spr_g2_prefix_kernel<<<dim3(kPfxCtas, ng, 2), 1024, 0, ctx->stream>>>(b->dev, b->d_groups);
     launched += 4;
   } else if (ng > 0) {

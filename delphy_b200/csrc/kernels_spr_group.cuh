@@ -41,6 +41,7 @@ struct SprGroupDev {
   int64_t off_cbase;            // int2 [num_t_chunks + 1][32]    (output offset of the chunk's kept regions, 0) or (row in the study's hmix, 1)
   int64_t off_trec;             // G2Templ [num_templates]        study-independent template records (shared by the groups of a tree)
   int64_t off_consts, off_outs; // G2Const [32], G2Out [32]
+  int64_t off_csort, off_cpm, off_cq;   // per chunk (shared like off_trec): double [..][32] sorted start times, u32 [..][32] running OR of their lane bits, int2 first / last position
   int32_t trec_owner, pad2;     // this group writes the tree's template records
 };
 

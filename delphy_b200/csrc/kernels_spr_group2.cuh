@@ -182,25 +182,58 @@ struct alignas(16) G2Study { G2Const c; int base, mH; unsigned out_lo, out_hi; }
 struct alignas(16) G2Weight { double logfl, fa, lam, mu3; long long lw_minus_out; int fused, pad; };
 static_assert(sizeof(G2Templ) == 48 && sizeof(G2Const) == 32 && sizeof(G2Out) == 64 && sizeof(G2Study) == 48, "record sizes are part of the slab layout");
 
+// Besides the records, per chunk of 32 templates (study-independent as well): the start times of its live templates SORTED
+// (csort), the running OR of their lane bits in that order (cpm) and the chunk's first / last position (cq).  A region is kept iff it
+// starts before t_X, so the keep mask of (chunk, study) is cpm[#{sorted starts < t_X} - 1]: the count kernel finds it with a
+// five-step binary search per study, all 32 studies at once, instead of 32 x 32 comparisons.
 __global__ void __launch_bounds__(256) spr_g2_templ_kernel(ForestDev f, SprBatchDev B, const SprGroupDev* __restrict__ groups) {
+  const unsigned full = 0xffffffffu;
   const SprGroupDev& G = groups[blockIdx.y];
   if (!G.trec_owner) return;                       // one group per tree writes the records; the others share them
   const int r = blockIdx.x * 256 + threadIdx.x;
-  if (r >= G.num_templates) return;
+  const int tc = r >> 5, lane = threadIdx.x & 31;
+  if (tc > G.num_t_chunks) return;                 // (whole warps)
   const int nb = G.node_base, mb = G.mut_base;
-  const int p = __ldg(B.g2_tnode + (size_t)nb + mb + r);
-  const int q = p - nb;
-  const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
-  const int k = r - (q + (moff - mb));
-  const int par = f.parent_pos[p];
+  const bool valid = r < G.num_templates;
   G2Templ T;
-  T.nonroot = par >= 0;
-  const double tn = f.t[p], tp = T.nonroot ? f.t[par] : 0.0;
-  T.t_min = k == 0 ? tp : f.mut_t[moff + k - 1];
-  T.t_max = k >= np ? tn : f.mut_t[moff + k];
-  T.idn = f.node_id[p]; T.k = k; T.q = q; T.qend = q + f.subtree_size[p];
-  T.e = B.g2_eopen[p] + k; T.moff = moff; T.np = np;
-  ((G2Templ*)(B.slab + G.off_trec))[r] = T;
+  T.t_min = DBL_MAX; T.t_max = DBL_MAX; T.idn = 0; T.k = 0; T.q = -3; T.qend = -3; T.e = 0; T.nonroot = 0; T.moff = 0; T.np = 0;
+  if (valid) {
+    const int p = __ldg(B.g2_tnode + (size_t)nb + mb + r);
+    const int q = p - nb;
+    const int moff = f.mut_off[p], np = f.mut_off[p + 1] - moff;
+    const int k = r - (q + (moff - mb));
+    const int par = f.parent_pos[p];
+    T.nonroot = par >= 0;
+    const double tn = f.t[p], tp = T.nonroot ? f.t[par] : 0.0;
+    T.t_min = k == 0 ? tp : f.mut_t[moff + k - 1];
+    T.t_max = k >= np ? tn : f.mut_t[moff + k];
+    T.idn = f.node_id[p]; T.k = k; T.q = q; T.qend = q + f.subtree_size[p];
+    T.e = B.g2_eopen[p] + k; T.moff = moff; T.np = np;
+    ((G2Templ*)(B.slab + G.off_trec))[r] = T;
+  }
+  // bitonic sort of (start time, lane) over the warp; templates that can never be kept by the time rule (the root's, the padding of
+  // the last chunk) sort last with the key DBL_MAX and contribute no bit
+  double key = (valid && T.nonroot) ? T.t_min : DBL_MAX;
+  int idx = lane;
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const double ok = __shfl_xor_sync(full, key, j);
+      const int oi = __shfl_xor_sync(full, idx, j);
+      const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+      const bool other_less = ok < key || (ok == key && oi < idx);
+      if (keep_min == other_less) { key = ok; idx = oi; }
+    }
+  }
+  unsigned pm = key != DBL_MAX ? (1u << idx) : 0u;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(full, pm, o); if (lane >= o) pm |= u; }
+  ((double*)(B.slab + G.off_csort))[(size_t)tc * 32 + lane] = key;
+  ((uint32_t*)(B.slab + G.off_cpm))[(size_t)tc * 32 + lane] = pm;
+  const int nv = min(32, G.num_templates - tc * 32);
+  const int qfirst = __shfl_sync(full, T.q, 0), qlast = __shfl_sync(full, T.q, max(nv - 1, 0));
+  if (lane == 0) ((int2*)(B.slab + G.off_cq))[tc] = nv > 0 ? make_int2(qfirst, qlast) : make_int2(-3, -3);
 }
 
 __global__ void spr_g2_consts_kernel(ForestDev f, SprBatchDev B, const SprGroupDev* __restrict__ groups) {
@@ -218,6 +251,10 @@ __global__ void spr_g2_consts_kernel(ForestDev f, SprBatchDev B, const SprGroupD
     }
   }
   ((G2Const*)(B.slab + G.off_consts))[lane] = c;
+  // the root has ONE region, (root, np), kept iff the root may change and the root is not P (eval_region); it starts at -DBL_MAX
+  int rk = 0;
+  if (lane < G.num) { const SprStudy& S = B.studies[G.study[lane]]; rk = (!S.error && S.can_change_root && S.posP != S.root_pos) ? 1 : 0; }
+  ((int32_t*)(B.slab + G.off_consts + 32 * kGroup))[lane] = rk;
 }
 
 // ---- per (chunk, study): where the chunk's kept regions go -------------------------------------------------------------------------------
@@ -282,16 +319,21 @@ __global__ void __launch_bounds__(kBasesThreads) spr_g2_bases_kernel(SprBatchDev
   const int lane = threadIdx.x & 31;
   const int per = ((G.num_t_chunks + 1 + (int)gridDim.z - 1) / (int)gridDim.z + 31) & ~31;
   const int c0 = (int)blockIdx.z * per, c1 = min(c0 + per, G.num_t_chunks + 1);
-  for (int tb = c0 + (int)(threadIdx.x & ~31u); tb < c1; tb += kBasesThreads) {
-    const int tc = tb + lane;
+  // (consecutive chunks go to different warps: straddling chunks cluster along the path, and each costs its warp a serial step)
+  constexpr int kW = kBasesThreads / 32;
+  const int wrp = threadIdx.x >> 5;
+  for (int tb = c0; tb < c1; tb += kBasesThreads) {
+    const int tc = tb + lane * kW + wrp;
     bool mixed = false;
     int jlo = 0, jhi = 0, kb = 0;
     if (tc < c1) {
+      // (all four loads issued together: the chunk's first / last position come from the study-independent chunk records)
       const uint32_t mask = maskcol[(size_t)tc * kGroup];
+      kb = aggKcol[(size_t)tc * kGroup];
+      const int2 qfl = ((const int2*)(B.slab + G.off_cq))[tc];
       if (mask == 0u) cbase[(size_t)tc * kGroup] = make_int2(0, 0);
       else {
-        kb = aggKcol[(size_t)tc * kGroup];
-        const int pfirst = nb + trec[tc * 32].q, plast = nb + trec[min(tc * 32 + 31, NT - 1)].q;
+        const int pfirst = nb + qfl.x, plast = nb + qfl.y;
         const int j = classify(pfirst, 0, path_len - 1);
         const int2 cur = pae[j];
         const int dnx = j > 0 ? pae[j - 1].x : INT_MAX;
@@ -306,21 +348,24 @@ __global__ void __launch_bounds__(kBasesThreads) spr_g2_bases_kernel(SprBatchDev
         }
       }
     }
-    // chunks that straddle a segment boundary of the study: a row of 32 per-template offsets each, one lane per template
+    // chunks that straddle a segment boundary of the study: a row of 32 per-template offsets each, one lane per template; the
+    // warp reserves its rows with one atomic
     unsigned todo = __ballot_sync(full, mixed);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int tcs = tb + src, lo_s = __shfl_sync(full, jlo, src), hi_s = __shfl_sync(full, jhi, src), kb_s = __shfl_sync(full, kb, src);
-      int row = 0;
-      if (lane == src) row = (int)atomicAdd(B.ticket + sidx * 4 + 3, 1u);
-      row = __shfl_sync(full, row, src);
-      if (row >= S.hmix_cap) { if (lane == src) S.error = 6; continue; }
-      const int r = tcs * 32 + lane;
-      int h = 0;
-      if (r < NT) h = hang[classify(nb + trec[r].q, lo_s, hi_s)];
-      hmix[(size_t)row * 32 + lane] = h + kb_s;
-      if (lane == src) cbase[(size_t)tcs * kGroup] = make_int2(row, 1);
+    if (todo) {
+      int row0 = 0;
+      if (lane == 0) row0 = (int)atomicAdd(B.ticket + sidx * 4 + 3, (unsigned)__popc(todo));
+      row0 = __shfl_sync(full, row0, 0);
+      if (row0 + __popc(todo) > S.hmix_cap) { if (lane == 0) S.error = 6; todo = 0u; }
+      for (int nrow = 0; todo; todo &= todo - 1, ++nrow) {
+        const int src = __ffs(todo) - 1;
+        const int tcs = tb + src * kW + wrp, lo_s = __shfl_sync(full, jlo, src), hi_s = __shfl_sync(full, jhi, src), kb_s = __shfl_sync(full, kb, src);
+        const int row = row0 + nrow;
+        const int r = tcs * 32 + lane;
+        int h = 0;
+        if (r < NT) h = hang[classify(nb + trec[r].q, lo_s, hi_s)];
+        hmix[(size_t)row * 32 + lane] = h + kb_s;
+        if (lane == src) cbase[(size_t)tcs * kGroup] = make_int2(row, 1);
+      }
     }
   }
 }
@@ -330,44 +375,104 @@ __device__ __noinline__ bool g2_special_keep(const ForestDev& f, const SprBatchD
   return eval_region(f, B.studies[sidx], p, k, np, moff, par >= 0 ? f.t[par] : 0.0, f.t[p]).keep;
 }
 
-// kMode 0: keep masks + counts;  1: emit the 32-byte heads;  2: emit + raw log-weights (and their per-study maximum)
+// ---- keep masks + kept counts of every (template chunk, study): lanes = studies -----------------------------------------------------------
+constexpr int kCountWarps = 8, kCountPerWarp = 8;     // chunks per CTA = 64: the per-chunk work is ~100 instructions, CTA launch would dominate
+__global__ void __launch_bounds__(kCountWarps * 32) spr_g2_count_kernel(ForestDev f, SprBatchDev B, const SprGroupDev* __restrict__ groups) {
+  const unsigned full = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const SprGroupDev& G = groups[blockIdx.y];
+  const int nb = G.node_base, NT = G.num_templates;
+  const G2Const c = ((const G2Const*)(B.slab + G.off_consts))[lane];
+  const int r_root = f.mut_off[nb + 1] - f.mut_off[nb];          // template index of the root's one region, (root, np)
+#pragma unroll 2
+  for (int it = 0; it < kCountPerWarp; ++it) {
+  const int tc = (blockIdx.x * kCountWarps + warp) * kCountPerWarp + it;
+  if (tc > G.num_t_chunks) return;                    // chunk num_t_chunks exists (empty): KB(N) reads its row
+  const double sorted = ((const double*)(B.slab + G.off_csort))[(size_t)tc * 32 + lane];
+  const unsigned pm = ((const uint32_t*)(B.slab + G.off_cpm))[(size_t)tc * 32 + lane];
+  const int2 qfl = ((const int2*)(B.slab + G.off_cq))[tc];
+  // number of the chunk's sorted start times before this lane's t_X (binary lifting over the warp's registers)
+  int n = 0;
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) { const double v = __shfl_sync(full, sorted, n + step - 1); if (v < c.tX) n += step; }
+  { const double v = __shfl_sync(full, sorted, 31); if (n == 31 && v < c.tX) n = 32; }
+  const unsigned pmn = __shfl_sync(full, pm, max(n - 1, 0));
+  uint32_t mymask = n > 0 ? pmn : 0u;
+  const int qfirst = qfl.x, qlast = qfl.y;
+  if (qfirst >= c.qX && qlast < c.xe) mymask = 0u;          // the whole chunk lies inside X's subtree
+  if (tc == (r_root >> 5)) mymask |= (uint32_t)((const int32_t*)(B.slab + G.off_consts + 32 * kGroup))[lane] << (r_root & 31);
+  // S and P (relabelled by account_for_Xs_detachment) follow the general rules, as in node_kept_count; a chunk that holds one of
+  // them for some study, or an end of that study's X subtree, is redone for that study template by template
+  const bool has_special = c.tX != -DBL_MAX && qfirst >= 0 &&
+                           ((c.qS >= qfirst && c.qS <= qlast) || (c.qP >= qfirst && c.qP <= qlast) ||
+                            (c.qX > qfirst && c.qX <= qlast) || (c.xe > qfirst && c.xe <= qlast));
+  unsigned specmask = __ballot_sync(full, has_special);
+  if (specmask) {
+    const int r = tc * 32 + lane;
+    const bool valid = r < NT;
+    G2Templ T;
+    T.t_min = DBL_MAX; T.k = 0; T.q = -3; T.nonroot = 0; T.moff = 0; T.np = 0;
+    if (valid) {
+      const uint4* tp = reinterpret_cast<const uint4*>((const G2Templ*)(B.slab + G.off_trec) + r);
+      const uint4 a = __ldg(tp), b = __ldg(tp + 1), cc = __ldg(tp + 2);
+      T.t_min = __hiloint2double(a.y, a.x); T.k = b.y; T.q = b.z; T.nonroot = cc.y; T.moff = cc.z; T.np = cc.w;
+    }
+    const bool nonroot = T.nonroot != 0;
+    const int q = T.q;
+    for (; specmask; specmask &= specmask - 1u) {
+      const int s = __ffs(specmask) - 1;
+      const double tX = __shfl_sync(full, c.tX, s);
+      const int qX = __shfl_sync(full, c.qX, s), xe = __shfl_sync(full, c.xe, s), qS = __shfl_sync(full, c.qS, s), qP = __shfl_sync(full, c.qP, s);
+      bool keep = valid && nonroot && T.t_min < tX && !(q >= qX && q < xe);
+      if (valid && (q == qS || q == qP || !nonroot)) {
+        keep = false;
+        if (nonroot || T.k == T.np) keep = g2_special_keep(f, B, G.study[s], nb + q, T.k, T.np, T.moff);
+      }
+      const unsigned bal = __ballot_sync(full, keep);
+      if (lane == s) mymask = bal;
+    }
+  }
+  ((uint32_t*)(B.slab + G.off_mask))[(size_t)tc * kGroup + lane] = mymask;
+  ((int32_t*)(B.slab + G.off_aggK))[(size_t)tc * kGroup + lane] = __popc(mymask);
+  }
+}
+
+// ---- emit: lanes = templates, loop over the studies ------------------------------------------------------------------------------------------
+// kMode 1: the 32-byte heads;  2: heads + raw log-weights (and their per-study maximum)
 template <int kMode>
 __global__ void __launch_bounds__(kG2Warps * 32) spr_g2_emit_kernel(ForestDev f, SprBatchDev B, const SprGroupDev* __restrict__ groups) {
-  constexpr bool kCount = kMode == 0, kFuse = kMode == 2;
+  constexpr bool kFuse = kMode == 2;
   __shared__ G2Study s_st[kG2Warps][kGroup];
   __shared__ G2Weight s_wt[kFuse ? kG2Warps : 1][kFuse ? kGroup : 1];
   __shared__ double2 s_log[kFuse ? (1 << kLogTabBits) : 1];
+  // chunk-local potentials of the lane's template for the 32 studies: one 32-byte row, kept in shared memory (36-byte pitch) because
+  // the study loop is not fully unrolled -- 32 copies of its body, two logarithms each, do not fit the instruction cache: ncu showed
+  // "no instruction" as the top stall -- so the byte of study s is a dynamic index
+  __shared__ uint32_t s_row[kG2Warps][32][9];
   if (kFuse) { fill_log_table(s_log); __syncthreads(); }
   const unsigned full = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SprGroupDev& G = groups[blockIdx.y];
   const int tc = blockIdx.x * kG2Warps + warp;
-  if (tc > G.num_t_chunks) return;                    // chunk num_t_chunks exists (empty): KB(N) reads its row
-  const int nb = G.node_base, NT = G.num_templates;
-  uint32_t* maskp = (uint32_t*)(B.slab + G.off_mask) + (size_t)tc * kGroup;
-  int32_t* aggKp = (int32_t*)(B.slab + G.off_aggK) + (size_t)tc * kGroup;
+  if (tc >= G.num_t_chunks) return;
+  const int NT = G.num_templates;
 
   // ---- the lane's study (everything one level deep) -----------------------------------------------------------------------------------
   G2Study st;
   st.c = ((const G2Const*)(B.slab + G.off_consts))[lane];
-  st.base = 0; st.mH = 0; st.out_lo = 0u; st.out_hi = 0u;
-  uint32_t mymask = 0u;
-  int2 cb = make_int2(0, 0);
+  uint32_t mymask = ((const uint32_t*)(B.slab + G.off_mask))[(size_t)tc * kGroup + lane];
+  const int2 cb = ((const int2*)(B.slab + G.off_cbase))[(size_t)tc * kGroup + lane];
+  const G2Out* op = (const G2Out*)(B.slab + G.off_outs) + lane;
+  const int4 o0 = *reinterpret_cast<const int4*>(op);
+  st.base = cb.x; st.mH = o0.x; st.out_lo = (unsigned)o0.z; st.out_hi = (unsigned)o0.w;
   bool fused_lane = false;                                // (kFuse) the lane's study gets its weights here
   unsigned long long mykey = 0ULL;                        // (kFuse) running maximum of the lane's study, as an ordered key
-  if (!kCount) {
-    mymask = maskp[lane];
-    cb = ((const int2*)(B.slab + G.off_cbase))[(size_t)tc * kGroup + lane];
-    const G2Out* op = (const G2Out*)(B.slab + G.off_outs) + lane;
-    const int4 o0 = *reinterpret_cast<const int4*>(op);
-    st.base = cb.x; st.mH = o0.x; st.out_lo = (unsigned)o0.z; st.out_hi = (unsigned)o0.w;
-    if (kFuse) {
-      G2Weight w; w.logfl = op->logfl; w.fa = op->fa; w.lam = op->lam; w.mu3 = op->mu3; w.lw_minus_out = op->lw_minus_out; w.fused = o0.y; w.pad = 0;
-      s_wt[warp][lane] = w;
-      fused_lane = o0.y != 0;
-    }
-    if (st.c.tX == -DBL_MAX) mymask = 0u;
+  if (kFuse) {
+    G2Weight w; w.logfl = op->logfl; w.fa = op->fa; w.lam = op->lam; w.mu3 = op->mu3; w.lw_minus_out = op->lw_minus_out; w.fused = o0.y; w.pad = 0;
+    s_wt[warp][lane] = w;
+    fused_lane = o0.y != 0;
   }
+  if (st.c.tX == -DBL_MAX) mymask = 0u;
   // ---- the lane's template ---------------------------------------------------------------------------------------------------------------
   const int r = tc * 32 + lane;
   const bool valid = r < NT;
@@ -379,116 +484,69 @@ __global__ void __launch_bounds__(kG2Warps * 32) spr_g2_emit_kernel(ForestDev f,
     T.t_min = __hiloint2double(a.y, a.x); T.t_max = __hiloint2double(a.w, a.z);
     T.idn = b.x; T.k = b.y; T.q = b.z; T.qend = b.w; T.e = c.x; T.nonroot = c.y; T.moff = c.z; T.np = c.w;
   }
-  if (!kCount && !__any_sync(full, mymask != 0u)) return;
+  if (!__any_sync(full, mymask != 0u)) return;
   const bool nonroot = T.nonroot != 0;
   const int q = T.q;
-
-  // chunk-local potentials of the lane's template for the 32 studies: one 32-byte row; the chunk prefixes of the event chunk of the
-  // warp's first template are folded into the study constants, the (few) lanes in a later event chunk add the difference
-  // (kept in shared memory, 36-byte pitch: the study loop is not fully unrolled -- 32 copies of its body, two logarithms each, do not
-  // fit the instruction cache: ncu showed "no instruction" as the top stall -- so the byte of study s is a dynamic index)
-  __shared__ uint32_t s_row[kCount ? 1 : kG2Warps][kCount ? 1 : 32][9];
-  const int32_t* aggrow = nullptr; const int32_t* aggrow0 = nullptr;
-  bool uniform = true;
-  unsigned deadmask = 0u, specmask = 0u;      // (kCount) studies that keep nothing here / that have S, P or the root in this chunk
-  if (!kCount) {
-    const uint4* rp = reinterpret_cast<const uint4*>(B.slab + G.off_S + (size_t)T.e * kGroup);
+  // the chunk prefixes of the event chunk of the warp's first template are folded into the study constants, the (few) lanes in a
+  // later event chunk add the difference
+  const uint4* rp = reinterpret_cast<const uint4*>(B.slab + G.off_S + (size_t)T.e * kGroup);
+  {
     const uint4 row0 = __ldg(rp), row1 = __ldg(rp + 1);
     uint32_t* rw = s_row[warp][lane];
     rw[0] = row0.x; rw[1] = row0.y; rw[2] = row0.z; rw[3] = row0.w; rw[4] = row1.x; rw[5] = row1.y; rw[6] = row1.z; rw[7] = row1.w;
-    const int ec = T.e >> 7, ec0 = __shfl_sync(full, ec, 0);
-    aggrow = (const int32_t*)(B.slab + G.off_aggS) + (size_t)ec * kGroup;
-    aggrow0 = (const int32_t*)(B.slab + G.off_aggS) + (size_t)ec0 * kGroup;
-    uniform = __all_sync(full, !valid || ec == ec0);
-    st.mH += aggrow0[lane];
-  } else {
-    // studies that can keep nothing of this chunk: everything here starts at or after t_X, or lies inside X's subtree -- unless one of
-    // the chunk's nodes follows the general rules (S, P, the root)
-    double tmin_w = (valid && nonroot) ? T.t_min : DBL_MAX;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tmin_w = fmin(tmin_w, __shfl_xor_sync(full, tmin_w, o));
-    const int qfirst = __shfl_sync(full, q, 0), qlast = __shfl_sync(full, q, max(0, min(31, NT - 1 - tc * 32)));
-    // ... or X's subtree starts or ends inside the chunk (the main loop below only compares times)
-    const bool has_special = (st.c.qS >= qfirst && st.c.qS <= qlast) || (st.c.qP >= qfirst && st.c.qP <= qlast) || qfirst == 0 ||
-                             (st.c.qX > qfirst && st.c.qX <= qlast) || (st.c.xe > qfirst && st.c.xe <= qlast);
-    const bool dead = st.c.tX == -DBL_MAX || (!has_special && (st.c.tX <= tmin_w || (qfirst >= st.c.qX && qlast < st.c.xe)));
-    deadmask = __ballot_sync(full, dead);
-    specmask = __ballot_sync(full, has_special && st.c.tX != -DBL_MAX);
-    if (NT <= tc * 32) { deadmask = full; specmask = 0u; }      // the empty chunk past the last template
   }
+  const int ec = T.e >> 7, ec0 = __shfl_sync(full, ec, 0);
+  const int32_t* aggrow = (const int32_t*)(B.slab + G.off_aggS) + (size_t)ec * kGroup;
+  const int32_t* aggrow0 = (const int32_t*)(B.slab + G.off_aggS) + (size_t)ec0 * kGroup;
+  const bool uniform = __all_sync(full, !valid || ec == ec0);
+  st.mH += aggrow0[lane];
   s_st[warp][lane] = st;
   __syncwarp();
-  int cnt_mine = 0;
   const unsigned lt = (1u << lane) - 1u;
-  const bool live = valid && nonroot;
   // log(t_max - t_min) of the unclipped region: shared by every study that does not clip it
   double logdt = 0.0;
   if (kFuse) logdt = fast_log(T.t_max - T.t_min, s_log);
+  const int8_t* myrow = reinterpret_cast<const int8_t*>(s_row[warp][lane]);
 
 #pragma unroll 4
   for (int s = 0; s < kGroup; ++s) {
+    const unsigned bal = __shfl_sync(full, mymask, s);
+    if (bal == 0u) continue;
     const G2Study& ss = s_st[warp][s];
-    if (kCount) {
-      if ((deadmask >> s) & 1u) continue;
-      // (studies with S, P, the root or an end of X's subtree in this chunk are redone under the general rules after the loop; a chunk
-      // wholly inside X's subtree is dead)
-      const bool keep = live && T.t_min < ss.c.tX;
-      const unsigned bal = __ballot_sync(full, keep);
-      if (lane == s) { mymask = bal; cnt_mine = __popc(bal); }
-    } else {
-      const unsigned bal = __shfl_sync(full, mymask, s);
-      if (bal == 0u) continue;
-      const bool special = q == ss.c.qS || q == ss.c.qP || !nonroot || (q <= ss.c.q0 && ss.c.q0 < T.qend);
-      const bool emit = ((bal >> lane) & 1u) && !special;
-      int base = ss.base;
-      if (__shfl_sync(full, cb.y, s)) {
-        // a chunk that straddles a segment boundary of this study: per-template offsets (spr_g2_bases_kernel); base is the row
-        const SprStudy& S = B.studies[G.study[s]];
-        base = ((const int32_t*)(B.slab + S.off_hmix))[(size_t)base * 32 + lane];
-      }
-      const int idx = base + __popc(bal & lt);
-      unsigned long long key = 0ULL;
-      if (emit && idx >= 0 && idx < ss.c.cap) {
-        const int hloc = reinterpret_cast<const int8_t*>(s_row[kCount ? 0 : warp][kCount ? 0 : lane])[s];   // chunk-local prefix, study s
-        int m = ss.mH + hloc;
-        if (!uniform) m += __ldg(aggrow + s) - __ldg(aggrow0 + s);
-        const double tmx = T.t_max > ss.c.tX ? ss.c.tX : T.t_max;
-        char* o = (char*)(((unsigned long long)ss.out_hi << 32) | ss.out_lo) + (size_t)idx * sizeof(RegionHead);
-        const unsigned long long w0 = (unsigned long long)(unsigned)T.idn | ((unsigned long long)(unsigned)T.k << 32);
-        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o), "l"(w0), "l"(__double_as_longlong(T.t_min)),
-                     "l"(__double_as_longlong(tmx)), "l"((unsigned long long)(unsigned)m) : "memory");
-        if (kFuse && s_wt[warp][s].fused) {
-          // raw log-weight (core/spr_study.cpp:313-318): log(f lam dt) + f (-lam (t_X - t') + m log(mu (t_X - t') / 3)), t' = mid-point
-          const G2Weight& w8 = s_wt[warp][s];
-          const double x = ss.c.tX - 0.5 * (T.t_min + tmx);
-          const double ldt = T.t_max > ss.c.tX ? fast_log(ss.c.tX - T.t_min, s_log) : logdt;
-          const double lw = (w8.logfl + ldt) + w8.fa * (-(w8.lam * x) + m * fast_log(w8.mu3 * x, s_log));
-          *reinterpret_cast<double*>(o - (size_t)idx * sizeof(RegionHead) + w8.lw_minus_out + (size_t)idx * sizeof(double)) = lw;
-          key = f64_order_key(lw);
-        }
-      }
-      if (kFuse) {
-        // warp maximum of the ordered keys (two 32-bit REDUX steps), kept by the lane that owns study s
-        const unsigned hi = (unsigned)(key >> 32), mh = __reduce_max_sync(full, hi);
-        const unsigned ml = __reduce_max_sync(full, hi == mh ? (unsigned)key : 0u);
-        if (lane == s) { const unsigned long long k2 = ((unsigned long long)mh << 32) | ml; if (k2 > mykey) mykey = k2; }
+    const bool special = q == ss.c.qS || q == ss.c.qP || !nonroot || (q <= ss.c.q0 && ss.c.q0 < T.qend);
+    const bool emit = ((bal >> lane) & 1u) && !special;
+    int base = ss.base;
+    if (__shfl_sync(full, cb.y, s)) {
+      // a chunk that straddles a segment boundary of this study: per-template offsets (spr_g2_bases_kernel); base is the row
+      const SprStudy& S = B.studies[G.study[s]];
+      base = ((const int32_t*)(B.slab + S.off_hmix))[(size_t)base * 32 + lane];
+    }
+    const int idx = base + __popc(bal & lt);
+    unsigned long long key = 0ULL;
+    if (emit && idx >= 0 && idx < ss.c.cap) {
+      int m = ss.mH + myrow[s];                             // chunk-local prefix of study s + everything folded into mH
+      if (!uniform) m += __ldg(aggrow + s) - __ldg(aggrow0 + s);
+      const double tmx = T.t_max > ss.c.tX ? ss.c.tX : T.t_max;
+      char* o = (char*)(((unsigned long long)ss.out_hi << 32) | ss.out_lo) + (size_t)idx * sizeof(RegionHead);
+      const unsigned long long w0 = (unsigned long long)(unsigned)T.idn | ((unsigned long long)(unsigned)T.k << 32);
+      asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o), "l"(w0), "l"(__double_as_longlong(T.t_min)),
+                   "l"(__double_as_longlong(tmx)), "l"((unsigned long long)(unsigned)m) : "memory");
+      if (kFuse && s_wt[warp][s].fused) {
+        // raw log-weight (core/spr_study.cpp:313-318): log(f lam dt) + f (-lam (t_X - t') + m log(mu (t_X - t') / 3)), t' = mid-point
+        const G2Weight& w8 = s_wt[warp][s];
+        const double x = ss.c.tX - 0.5 * (T.t_min + tmx);
+        const double ldt = T.t_max > ss.c.tX ? fast_log(ss.c.tX - T.t_min, s_log) : logdt;
+        const double lw = (w8.logfl + ldt) + w8.fa * (-(w8.lam * x) + m * fast_log(w8.mu3 * x, s_log));
+        *reinterpret_cast<double*>(o - (size_t)idx * sizeof(RegionHead) + w8.lw_minus_out + (size_t)idx * sizeof(double)) = lw;
+        key = f64_order_key(lw);
       }
     }
-  }
-  if (kCount) {
-    // S, P (relabelled by account_for_Xs_detachment) and the root follow the general rules, as in node_kept_count
-    for (unsigned sm = specmask; sm; sm &= sm - 1u) {
-      const int s = __ffs(sm) - 1;
-      const G2Const c = s_st[warp][s].c;
-      bool keep = valid && nonroot && T.t_min < c.tX && !(q >= c.qX && q < c.xe);
-      if (valid && (q == c.qS || q == c.qP || !nonroot)) {
-        keep = false;
-        if (nonroot || T.k == T.np) keep = g2_special_keep(f, B, G.study[s], nb + q, T.k, T.np, T.moff);
-      }
-      const unsigned bal = __ballot_sync(full, keep);
-      if (lane == s) { mymask = bal; cnt_mine = __popc(bal); }
+    if (kFuse) {
+      // warp maximum of the ordered keys (two 32-bit REDUX steps), kept by the lane that owns study s
+      const unsigned hi = (unsigned)(key >> 32), mh = __reduce_max_sync(full, hi);
+      const unsigned ml = __reduce_max_sync(full, hi == mh ? (unsigned)key : 0u);
+      if (lane == s) { const unsigned long long k2 = ((unsigned long long)mh << 32) | ml; if (k2 > mykey) mykey = k2; }
     }
-    maskp[lane] = mymask; aggKp[lane] = cnt_mine;
   }
   if (kFuse && fused_lane && mykey != 0ULL) atomicMax(&B.studies[G.study[lane]].max_key, mykey);
 }
