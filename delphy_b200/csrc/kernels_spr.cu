@@ -744,6 +744,13 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
   SprStudy& S = B.studies[blockIdx.x];
   if (S.error) return;
   if (threadIdx.x == 0) S.mu = S.lambda_X / (double)(S.L - S.num_missing);   // Spr_study::mu, core/spr_study.cpp:239
+  // the path index of S and P (a ten-step search of dependent loads) is found now, by two threads of another warp, rather than at the
+  // end of the kernel where it would sit on the critical path
+  __shared__ int s_jsp[2];
+  if (S.h_stride != 1 && (threadIdx.x == 32 || threadIdx.x == 33)) {
+    const int p = threadIdx.x == 32 ? S.posS : S.posP;
+    s_jsp[threadIdx.x - 32] = p >= 0 ? classify(make_view(B, S, blockIdx.x), p) : 0;
+  }
   if (S.g2) {
     // event-scan path: the chunk prefixes are already final (spr_g2_prefix_kernel); only the start region's potential is missing
     if (threadIdx.x == 0) {
@@ -829,7 +836,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
     // ... and so are S and P when they are not on the path (their regions are relabelled by account_for_Xs_detachment)
     const int p = tid == 0 ? S.posS : S.posP;
     if (p >= 0 && !(tid == 1 && S.posP == S.posS)) {
-      const int j = classify(V, p);
+      const int j = s_jsp[tid];
       if (V.path[j] != p) {
         GLane L;
         L.out = (RegionHead*)(B.slab + S.off_regions); L.pae = V.pae; L.seg = V.seg; L.agg = V.agg;
@@ -1340,15 +1347,18 @@ int ensure_spr_tables(dphy_ctx* ctx, dphy_forest* fo) {
   if (fo->d_spr_eopen) return DPHY_OK;
   const size_t N = (size_t)fo->h.num_nodes, M = (size_t)fo->total_muts;
   const size_t b_eopen = 0, b_tnode = al(sizeof(int32_t) * N), b_ev = b_tnode + al(sizeof(int32_t) * (N + M + 1));
-  const size_t b_pm = b_ev + al(sizeof(int32_t) * (2 * M + 1)), total = b_pm + al(sizeof(int32_t) * N);
-  char* d = nullptr;
-  if (cudaMallocAsync((void**)&d, total, ctx->stream) != cudaSuccess) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(spr tables)");
   int max_nodes = 1;
   for (const TreeDev& T : fo->trees) max_nodes = std::max(max_nodes, T.num_nodes);
+  const int max_tiles = (max_nodes + kPmTile - 1) / kPmTile;
+  const size_t b_pm = b_ev + al(sizeof(int32_t) * (2 * M + 1)), b_tt = b_pm + al(sizeof(int32_t) * N);
+  const size_t total = b_tt + al(sizeof(int32_t) * (size_t)max_tiles * fo->h.num_trees);
+  char* d = nullptr;
+  if (cudaMallocAsync((void**)&d, total, ctx->stream) != cudaSuccess) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(spr tables)");
   int32_t* pm = (int32_t*)(d + b_pm);
-  spr_tab_pm_kernel<<<fo->h.num_trees, 1024, 0, ctx->stream>>>(fo->h, pm);
-  spr_tab_fill_kernel<<<dim3((max_nodes + 255) / 256, fo->h.num_trees), 256, 0, ctx->stream>>>(fo->h, pm, (int32_t*)(d + b_eopen), (int32_t*)(d + b_tnode),
-                                                                                             (int32_t*)(d + b_ev));
+  int32_t* tt = (int32_t*)(d + b_tt);
+  spr_tab_pm_kernel<<<dim3(max_tiles, fo->h.num_trees), 1024, 0, ctx->stream>>>(fo->h, pm, tt, max_tiles);
+  spr_tab_fill_kernel<<<dim3((max_nodes + 255) / 256, fo->h.num_trees), 256, 0, ctx->stream>>>(fo->h, pm, tt, max_tiles, (int32_t*)(d + b_eopen),
+                                                                                             (int32_t*)(d + b_tnode), (int32_t*)(d + b_ev));
   ctx->launches += 2;
   const int st = check_cuda(ctx, cudaGetLastError(), "spr table kernels launch");
   if (st != DPHY_OK) { cudaFreeAsync(d, ctx->stream); return st; }

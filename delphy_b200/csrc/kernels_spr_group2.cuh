@@ -26,41 +26,38 @@ constexpr int kEvChunk = 128;      // events per warp of the scan (int8 chunk-lo
 constexpr int kG2Warps = 4;
 
 // ---- study-independent tables -----------------------------------------------------------------------------------------------------------
-// PM[j] = number of mutations of the first j nodes of the tree's post-order list: one CTA per tree, 8 elements per thread per round
-__global__ void __launch_bounds__(1024) spr_tab_pm_kernel(ForestDev f, int32_t* __restrict__ PM) {
+// PM[j] = number of mutations of the first j nodes of the tree's post-order list.  Two levels: every CTA scans one tile of 8,192
+// entries (tile-local exclusive prefix + the tile total); the consumer adds the totals of the tiles before (a few dozen per tree).
+constexpr int kPmTile = 1024 * 8;
+__global__ void __launch_bounds__(1024) spr_tab_pm_kernel(ForestDev f, int32_t* __restrict__ PM, int32_t* __restrict__ tile_tot, int max_tiles) {
   __shared__ int s_ws[32];
-  __shared__ int s_carry;
-  const TreeDev T = f.trees[blockIdx.x];
+  const TreeDev T = f.trees[blockIdx.y];
   const int nb = T.node_base, N = T.num_nodes;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (int j0 = 0; j0 < N; j0 += 1024 * 8) {
-    int v[8], mine = 0;
+  const int j0 = blockIdx.x * kPmTile;
+  if (j0 >= N) return;
+  int v[8], mine = 0;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + (int)threadIdx.x * 8 + u;
-      v[u] = 0;
-      if (j < N) { const int a = f.post_node[nb + j]; v[u] = f.mut_off[a + 1] - f.mut_off[a]; }
-      mine += v[u];
-    }
-    int tot;
-    const int incl = block_scan_incl<int, 1024>(mine, s_ws, &tot);
-    int run = s_carry + incl - mine;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + (int)threadIdx.x * 8 + u;
-      if (j < N) PM[nb + j] = run;
-      run += v[u];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry += tot;
-    __syncthreads();
+  for (int u = 0; u < 8; ++u) {
+    const int j = j0 + (int)threadIdx.x * 8 + u;
+    v[u] = 0;
+    if (j < N) { const int a = f.post_node[nb + j]; v[u] = f.mut_off[a + 1] - f.mut_off[a]; }
+    mine += v[u];
   }
+  int tot;
+  const int incl = block_scan_incl<int, 1024>(mine, s_ws, &tot);
+  int run = incl - mine;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int j = j0 + (int)threadIdx.x * 8 + u;
+    if (j < N) PM[nb + j] = run;
+    run += v[u];
+  }
+  if (threadIdx.x == 0) tile_tot[(size_t)blockIdx.y * max_tiles + blockIdx.x] = tot;
 }
 
 // eopen, tnode and the event list: one thread per node (grid.y = tree)
-__global__ void __launch_bounds__(256) spr_tab_fill_kernel(ForestDev f, const int32_t* __restrict__ PM, int32_t* __restrict__ eopen,
-                                                           int32_t* __restrict__ tnode, int32_t* __restrict__ ev) {
+__global__ void __launch_bounds__(256) spr_tab_fill_kernel(ForestDev f, const int32_t* __restrict__ PM, const int32_t* __restrict__ tile_tot, int max_tiles,
+                                                           int32_t* __restrict__ eopen, int32_t* __restrict__ tnode, int32_t* __restrict__ ev) {
   const TreeDev T = f.trees[blockIdx.y];
   const int nb = T.node_base, N = T.num_nodes;
   const int q = blockIdx.x * 256 + threadIdx.x;
@@ -69,13 +66,19 @@ __global__ void __launch_bounds__(256) spr_tab_fill_kernel(ForestDev f, const in
   const int mb = f.mut_off[nb];
   const int moff = f.mut_off[p] - mb, np = f.mut_off[p + 1] - f.mut_off[p];
   const int dep = f.depth[p], size = f.subtree_size[p];
-  const int eo = moff + PM[nb + q - dep];
+  const int32_t* tt = tile_tot + (size_t)blockIdx.y * max_tiles;
+  auto pm_at = [&](int j) {                      // PM[j] = tile-local prefix + totals of the tiles before
+    int s = PM[nb + j];
+    for (int t = 0; t < j / kPmTile; ++t) s += __ldg(tt + t);
+    return s;
+  };
+  const int eo = moff + pm_at(q - dep);
   eopen[p] = eo;
   int32_t* tn = tnode + (size_t)nb + mb + q + moff;          // global template base of the tree = nb + mb
   for (int k = 0; k <= np; ++k) tn[k] = p;
   if (np > 0) {
     int32_t* evt = ev + 2 * (size_t)mb;
-    const int xo = (f.mut_off[p + size] - mb) + PM[nb + q + size - 1 - dep];   // post-order index of q = q + size - 1 - depth
+    const int xo = (f.mut_off[p + size] - mb) + pm_at(q + size - 1 - dep);     // post-order index of q = q + size - 1 - depth
     for (int k = 0; k < np; ++k) { evt[eo + k] = moff + k; evt[xo + k] = (moff + k) | (int)0x80000000; }
   }
 }
