@@ -60,16 +60,28 @@ __global__ void __launch_bounds__(1024) delta_offsets_kernel(RawTreeDev old, Raw
   const int n = old.num_nodes;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
-  for (int v0 = 0; v0 < n; v0 += 1024) {
-    const int v = v0 + threadIdx.x;
-    int cnt = 0;
-    if (v < n) {
-      const int r = row_of[v];
-      cnt = r < 0 ? old_off[v + 1] - old_off[v] : (kind == 0 ? rows[r].n_muts : (kind == 1 ? rows[r].n_miss : rows[r].n_fs));
+  // eight consecutive nodes per thread and round: 25 rounds of (gather, block scan) for a 100k-tip tree instead of 196
+  for (int v0 = 0; v0 < n; v0 += 1024 * 8) {
+    int cnt[8], mine = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int v = v0 + (int)threadIdx.x * 8 + u;
+      cnt[u] = 0;
+      if (v < n) {
+        const int r = row_of[v];
+        cnt[u] = r < 0 ? old_off[v + 1] - old_off[v] : (kind == 0 ? rows[r].n_muts : (kind == 1 ? rows[r].n_miss : rows[r].n_fs));
+      }
+      mine += cnt[u];
     }
     int tot;
-    const int incl = block_scan_incl<int, 1024>(cnt, s_ws, &tot);
-    if (v < n) new_off[v] = s_carry + incl - cnt;
+    const int incl = block_scan_incl<int, 1024>(mine, s_ws, &tot);
+    int run = s_carry + incl - mine;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int v = v0 + (int)threadIdx.x * 8 + u;
+      if (v < n) new_off[v] = run;
+      run += cnt[u];
+    }
     __syncthreads();
     if (threadIdx.x == 0) s_carry += tot;
     __syncthreads();

@@ -58,7 +58,7 @@ struct SprStudy {
   double log_Wmax, sum_W;
   // ---- layout of the tree prefix sums H / KB (and of their per-tile aggregates) ----
   // per-study path: one int per node (h_stride 1), tiles of kTile nodes (tile_shift 8);
-  // grouped path (spr_gscan / spr_gemit, 32 studies of one tree side by side): [node][32] (h_stride 32), chunks of 32 nodes (tile_shift 5)
+  // grouped studies (h_stride 32) read H / KB off their group's event rows / keep masks instead (g2 fields below)
   int32_t h_stride, tile_shift, num_htiles, weights_fused;
   // event-scan grouped path (kernels_spr_group2.cuh): lane of the study inside its group and the group's tables (0 => not used)
   int32_t g2, g2_lane, g2_mut_base, g2_num_templates;
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(kTile) spr_scan_kernel(ForestDev f, SprBatchDe
   const int t0 = blockIdx.x * kScanSub;          // first tile of this CTA
   {
     const SprStudy& G = B.studies[study];
-    if (t0 >= G.num_tiles || G.error || G.h_stride != 1) return;     // grouped studies are scanned by spr_gscan_kernel
+    if (t0 >= G.num_tiles || G.error || G.h_stride != 1) return;     // grouped studies are scanned by spr_g2_scan_kernel
     if (kPhase == 1 && G.limit == INT_MAX) return;
     const int* src = reinterpret_cast<const int*>(&G);
     int* dst = reinterpret_cast<int*>(&sm.S);
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
       // output offset of the regions hanging off path node j, relative to the kept-region prefix KB (spr_g2_bases_kernel / emit)
       if (S.g2) ((int32_t*)(B.slab + S.off_hang))[j] = sg[2] - V.KB(sibpos - S.node_base);
       if (S.h_stride != 1) {
-        // grouped studies: the path nodes' own regions are written here, one thread per path node (spr_gemit_kernel skips them)
+        // grouped studies: the path nodes' own regions are written here, one thread per path node (spr_g2_emit_kernel skips them)
         GLane L;
         L.out = (RegionHead*)(B.slab + S.off_regions); L.pae = V.pae; L.seg = V.seg; L.agg = V.agg;
         L.region_cap = S.region_cap; L.path_len = S.path_len; L.H0 = S.H0; L.init_min_muts = S.init_min_muts; L.tX = S.t_X;
@@ -899,15 +899,6 @@ __device__ __noinline__ double region_log_W_above_root(double fa, double lam, do
   return -0.6931471805599453 + fa * m * log(mu / (3 * lam * fa)) + lgamma(a) + log(dev_gamma_q(a, x_min) - dev_gamma_q(a, x_max));
 }
 
-__device__ __forceinline__ double region_log_W(const SprStudy& S, double t_min, double t_max, int m, double tS) {
-  const double fa = S.f, lam = S.lambda_X, mu = S.mu;
-  if (t_min != -DBL_MAX) {
-    const double t_prime = 0.5 * (t_min + t_max);
-    return log(fa * lam * (t_max - t_min)) + fa * (-lam * (S.t_X - t_prime) + m * log(mu * (S.t_X - t_prime) / 3));
-  }
-  return region_log_W_above_root(fa, lam, mu, S.t_X, S.t_max_tip, m, tS);
-}
-
 // Two phases per tile of kTile nodes.  (A) one thread per node: the node's record (list range, H / C at its parent, times,
 // segment constants) goes to shared memory and the per-node candidate counts (np + 1 regions; 1 for the root) are scanned into
 // slot offsets; the tile's mutations -- one contiguous CSR range -- get their (dH, counted) pair flat, one per thread.
@@ -941,7 +932,7 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) spr_emit_kernel(ForestDev f
   const int t0 = blockIdx.x * kEmitSub;        // first kTile-tile of this CTA
   {
     const SprStudy& G = B.studies[study];
-    if (t0 >= G.num_tiles || G.error || G.h_stride != 1) return;     // grouped studies are emitted by spr_gemit_kernel
+    if (t0 >= G.num_tiles || G.error || G.h_stride != 1) return;     // grouped studies are emitted by spr_g2_emit_kernel
     const int* src = reinterpret_cast<const int*>(&G);
     int* dst = reinterpret_cast<int*>(&sm.S);
     for (int i = threadIdx.x; i < (int)(sizeof(SprStudy) / sizeof(int)); i += kTile) dst[i] = src[i];
@@ -1332,7 +1323,7 @@ struct dphy_spr_batch {
   int32_t num = 0;
   std::vector<SprStudy> host;     // filled by get_summaries
   bool fetched = false;
-  SprGroupDev* d_groups = nullptr; int32_t num_groups = 0, group_chunks = 0;
+  SprGroupDev* d_groups = nullptr; int32_t num_groups = 0;
   bool weighted = false;          // spr_weights_kernel + spr_normalize_kernel have run for the current (lambda_X, f, t_max_tip)
   int status = DPHY_OK;           // sticky: the first per-study error found by spr_fetch, returned by every accessor
   std::string status_msg;
@@ -1388,11 +1379,9 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   // ---- grouping: full (unbounded) studies of the same tree go 32 at a time through the lanes-are-studies kernels ----------------
   // (DPHY_SPR_GROUPED=0 disables)
   constexpr int kMinGroup = 24;     // a group costs the same for 1 or 32 lanes: below ~24 studies the per-study kernels are cheaper
-  // DPHY_SPR_GROUPED: 0 = every study on the per-study kernels, 1 = lanes-are-studies scan / emit over nodes (kernels_spr_group.cuh),
-  // 2 (default) = event scan + template emit (kernels_spr_group2.cuh)
-  static const int group_mode = [] { const char* e = getenv("DPHY_SPR_GROUPED"); return e ? atoi(e) : 2; }();
-  const bool use_groups = group_mode != 0;
-  const bool g2 = group_mode == 2;
+  // DPHY_SPR_GROUPED=0: every study on the per-study kernels
+  static const bool use_groups = [] { const char* e = getenv("DPHY_SPR_GROUPED"); return !(e && atoi(e) == 0); }();
+  const bool g2 = use_groups;
   std::vector<int> group_of(n, -1), lane_of(n, 0);
   std::vector<SprGroupDev> groups;
   if (use_groups) {
@@ -1409,11 +1398,11 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
         std::memset(&G, 0, sizeof(G));
         const TreeDev& T = fo->trees[k];
         G.tree = k; G.node_base = T.node_base; G.num_nodes = T.num_nodes; G.L = fo->sites[T.sites_id]->L;
-        G.mut_base = (int32_t)mut_base[k]; G.num_chunks = (T.num_nodes + kGChunk - 1) / kGChunk;
+        G.mut_base = (int32_t)mut_base[k];
         G.num = (int32_t)std::min<size_t>(kGroup, v.size() - g0);
         for (int l = 0; l < G.num; ++l) { G.study[l] = v[g0 + l]; group_of[v[g0 + l]] = (int)groups.size(); lane_of[v[g0 + l]] = l; }
         G.off_xT = off; off = al(off + (size_t)G.L * kGroup);
-        if (g2) {
+        {
           const int64_t M = fo->tree_muts[k];
           if (2 * M + 1 + kEvChunk > INT_MAX || (int64_t)T.num_nodes + M + 64 > INT_MAX) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: tree too large"); }
           G.num_muts = (int32_t)M; G.num_templates = (int32_t)(T.num_nodes + M);
@@ -1435,11 +1424,6 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
             const SprGroupDev& G0 = groups[groups.size() - g0 / kGroup];
             G.trec_owner = 0; G.off_trec = G0.off_trec; G.off_csort = G0.off_csort; G.off_cpm = G0.off_cpm; G.off_cq = G0.off_cq;
           }
-        } else {
-          G.off_dhT = off; off = al(off + (size_t)std::max<int64_t>(1, fo->tree_muts[k]) * kGroup);
-          G.off_dhP = off; off = al(off + sizeof(unsigned long long) * ((size_t)fo->tree_muts[k] / 32 + 4) * kGroup);
-          G.off_H = off; off = al(off + sizeof(int32_t) * (size_t)T.num_nodes * kGroup);
-          G.off_KB = off; off = al(off + sizeof(int32_t) * ((size_t)T.num_nodes + 1) * kGroup);
         }
         groups.push_back(G);
       }
@@ -1479,7 +1463,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     const int N = T.num_nodes;
     const bool grouped = group_of[i] >= 0;
     S.h_stride = grouped ? kGroup : 1; S.tile_shift = grouped ? 5 : 8;
-    S.num_htiles = grouped ? (g2 ? 1 : (N + kGChunk - 1) / kGChunk) : T.num_tiles;
+    S.num_htiles = grouped ? 1 : T.num_tiles;
     if (grouped && g2) {
       const SprGroupDev& G = groups[group_of[i]];
       S.g2 = 1; S.g2_lane = lane_of[i]; S.g2_mut_base = G.mut_base; S.g2_num_templates = G.num_templates;
@@ -1500,9 +1484,6 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     S.off_pae = off; off = al(off + sizeof(int2) * S.path_cap);
     if (grouped && g2) {
       S.off_H = 0; S.off_C = 0; S.off_KB = 0;          // unused: H and KB are read off the group's event rows / keep masks
-    } else if (grouped) {
-      const SprGroupDev& G = groups[group_of[i]];
-      S.off_H = G.off_H + (int64_t)sizeof(int32_t) * lane_of[i]; S.off_C = S.off_H; S.off_KB = G.off_KB + (int64_t)sizeof(int32_t) * lane_of[i];
     } else {
       S.off_H = off; off = al(off + sizeof(int32_t) * N);
       S.off_C = off; off = al(off + sizeof(int32_t) * N);
@@ -1583,9 +1564,9 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     release_pinned_async(ctx);
   }
   if (ce != cudaSuccess) { cudaFreeAsync(d, ctx->stream); delete b; return check_cuda(ctx, ce, "spr batch upload"); }
-  int max_nodes = 1, group_chunks = 0, group_L = 1;
+  int max_nodes = 1, group_L = 1;
   for (int i = 0; i < n; ++i) max_nodes = std::max(max_nodes, fo->trees[reqs[i].tree].num_nodes);
-  for (const SprGroupDev& G : groups) { group_chunks = std::max(group_chunks, G.num_chunks); group_L = std::max(group_L, G.L); }
+  for (const SprGroupDev& G : groups) group_L = std::max(group_L, G.L);
   const int ng = (int)groups.size();
   const bool any_single = max_tiles256 > 0;        // studies on the per-study path
   spr_paths_kernel<<<dim3((max_nodes + kSetupThreads * kPathChunks - 1) / (kSetupThreads * kPathChunks), (n + kPathStudies - 1) / kPathStudies), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
@@ -1593,7 +1574,6 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   int launched = 2;
   const dim3 grid_scan((std::max(max_tiles256, 1) + kScanSub - 1) / kScanSub, n);
   if (any_single) { spr_scan_kernel<0><<<grid_scan, kTile, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
-  const dim3 grid_group((group_chunks + kGWarps - 1) / kGWarps, std::max(ng, 1));
   int g2_ev_chunks = 0, g2_t_chunks = 0, g2_templates = 1;
   for (const SprGroupDev& G : groups) {
     g2_ev_chunks = std::max(g2_ev_chunks, G.num_ev_chunks); g2_t_chunks = std::max(g2_t_chunks, G.num_t_chunks + 1);
@@ -1609,12 +1589,6 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     spr_g2_count_kernel<<<dim3((g2_t_chunks + kCountWarps * kCountPerWarp - 1) / (kCountWarps * kCountPerWarp), ng), kCountWarps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
     spr_g2_prefix_kernel<<<dim3(kPfxCtas, ng, 2), 1024, 0, ctx->stream>>>(b->dev, b->d_groups);
     launched += 4;
-  } else if (ng > 0) {
-    for (const SprGroupDev& G : groups)      // the packed potentials are OR-ed together by the chunks that share a word
-      cudaMemsetAsync(b->dev.slab + G.off_dhP, 0, sizeof(unsigned long long) * ((size_t)fo->tree_muts[G.tree] / 32 + 4) * kGroup, ctx->stream);
-    spr_xT_kernel<<<dim3((group_L + 255) / 256, ng), 256, 0, ctx->stream>>>(b->dev, b->d_groups);
-    spr_gscan_kernel<<<grid_group, kGWarps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
-    launched += 2;
   }
   bool any_limited = false;
   for (int i = 0; i < n; ++i) any_limited |= (b->host[i].limit != INT_MAX);
@@ -1639,9 +1613,6 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     if (fuse_weights) spr_g2_emit_kernel<2><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
     else spr_g2_emit_kernel<1><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
     launched += 2;
-  } else if (ng > 0) {
-    spr_gemit_kernel<<<grid_group, kGWarps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
-    ++launched;
   }
   bool any_weighted = false, any_unfused = false;
   for (int i = 0; i < n; ++i) {

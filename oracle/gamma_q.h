@@ -7,11 +7,13 @@
  * core/safe_gamma_math.h:46-83.  Boost's implementation cannot be compiled here, so this header
  * restates the published algorithm (power series for x < a+1, Legendre continued fraction evaluated
  * with the modified Lentz method otherwise; Abramowitz & Stegun 6.5.29 / 6.5.31).
- * PARITY UNPINNED for the values of Q(a,x): the reference's own tests at this boundary
+ * Pinning: Boost's own output is unavailable here, and the reference's tests at this boundary
  * (tests/safe_gamma_math_tests.cpp:35-63) compare Boost against itself plus three trivial absolutes,
- * which this implementation reproduces (Q(271.4,6601)=0, Q(1000,100)=1, Q(a,0)=1); tests/ also
- * cross-check it against scipy.special.gammaincc.  It only ever affects the single above-root
- * candidate region of an SPR study.
+ * which this implementation reproduces (Q(271.4,6601)=0, Q(1000,100)=1, Q(a,0)=1).  The VALUES are
+ * pinned on the function's definition instead: tests/test_gamma_q.py checks this header (and the
+ * device code) at 1e-13 against a committed table of 40-digit mpmath values over the (a, x) range
+ * Spr_study reaches (tests/golden/make_gamma_q_table.py -> tests/golden/gamma_q_table.json).
+ * It only ever affects the single above-root candidate region of an SPR study.
  */
 #ifndef DPHY_ORACLE_GAMMA_Q_H_
 #define DPHY_ORACLE_GAMMA_Q_H_

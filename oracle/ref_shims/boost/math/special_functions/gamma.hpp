@@ -1,6 +1,6 @@
 // Stand-in for <boost/math/special_functions/gamma.hpp> (Boost 1.84 is not present under
 // /root/reference).  TEST INFRASTRUCTURE ONLY.  gamma_q / gamma_q_inv forward to the oracle's fp64
-// restatement in oracle/gamma_q.h (parity unpinned for these values; see that header).
+// restatement in oracle/gamma_q.h (values pinned on a 40-digit mpmath table, not on Boost's binary; see that header).
 #ifndef DPHY_ORACLE_SHIM_BOOST_MATH_GAMMA_HPP_
 #define DPHY_ORACLE_SHIM_BOOST_MATH_GAMMA_HPP_
 #include "gamma_q.h"

@@ -199,6 +199,36 @@ def test_studies_on_every_tree_of_a_forest(ctx, orc):
         t.close()
 
 
+def test_grouped_studies_on_several_trees_of_a_forest(ctx, orc):
+    """Full studies in numbers that take the grouped (event-scan) kernels, on several trees of one forest in ONE batch: 70 studies
+    of tree 0 (two groups sharing the tree's template records + a thin remainder on the per-study kernels), 40 of tree 1 and 33 of
+    tree 2 (one group each, different site tables), interleaved in the request list; weights and picks included."""
+    items = [synth(0, seed=41, num_tips=300), synth(0, seed=42, num_tips=150, num_root_mutations=4), synth(1, seed=43)]
+    tables = [db.DeviceSites(ctx, it[1]) for it in items]
+    fo = db.Forest(ctx, [it[0] for it in items], tables, sites_index=np.arange(len(items)))
+    per_tree = []
+    for k, (emat, sites, info) in enumerate(items):
+        lam = fo.lambda_i(k)
+        nx = (70, 40, 33)[k]
+        xs = [int(v) for v in np.random.default_rng(100 + k).permutation(emat.num_nodes) if v != emat.root][:nx - 2]
+        xs += [int(emat.child0[emat.root]), int(emat.child1[emat.root])]
+        rq = db.spr_requests_for_attached(emat, k, xs, lam, info["t_max_tip"], INF, k != 1)
+        per_tree.append([(r, k, X, lam) for r, X in zip(rq, xs)])
+    order = [t for trio in zip(*[pt[:33] for pt in per_tree]) for t in trio] + per_tree[0][33:] + per_tree[1][33:]
+    batch = fo.spr_study_batch([o[0] for o in order])
+    summ = batch.summaries()
+    for i, (_, k, X, lam) in enumerate(order):
+        e, s = to_oracle(items[k][0], items[k][1])
+        want, ws = orc.spr_study_from_attached(e, s, X, lam, INF, k != 1, 0.8, items[k][2]["t_max_tip"])
+        _cmp_regions(batch.regions(i), want)
+        if len(want):
+            assert summ[i].sum_W_over_Wmax == pytest.approx(ws.sum_W_over_Wmax, rel=1e-9)
+            assert summ[i].log_Wmax == pytest.approx(ws.log_Wmax, rel=1e-9, abs=1e-9)
+    batch.close(); fo.close()
+    for t in tables:
+        t.close()
+
+
 def _state_at_region(emat, sites, branch, k):
     """Sequence at region (branch, k): the reference overlaid with the mutations from the root down to the k-th of `branch`."""
     path = []
