@@ -135,69 +135,121 @@ __device__ __noinline__ double dev_gamma_q(double a, double x) {
 // posts (ordinal << 2 | to) with an atomicMax on a per-site key, ordinals coming from a block scan of the per-branch list
 // lengths in root->X order (spr_xtab_kernel, one CTA per study).
 constexpr int kSetupThreads = 1024;
-constexpr int kPathChunks = 8;     // chunks of kSetupThreads positions per CTA of spr_paths_kernel
 
-constexpr int kPathStudies = 8;    // studies per CTA of spr_paths_kernel: studies of the same tree share every subtree_size load
-__global__ void __launch_bounds__(kSetupThreads) spr_paths_kernel(ForestDev f, SprBatchDev B) {
-  __shared__ int s_pos0[kPathStudies], s_posX[kPathStudies], s_d0[kPathStudies], s_dX[kPathStudies];
-  __shared__ int s_nb[kPathStudies], s_N[kPathStudies], s_tree[kPathStudies];
-  __shared__ long long s_path[kPathStudies], s_pae[kPathStudies], s_xpath[kPathStudies];
-  const int tid = threadIdx.x;
-  const int sb = blockIdx.y * kPathStudies;
-  const int ns = min(kPathStudies, B.num_studies - sb);
-  if (tid < ns) {
-    SprStudy& S = B.studies[sb + tid];
+// (a) spr_init_kernel (one CTA per tree of the batch): per study -- node positions, P / S, the derived fields, and the study's two
+//     path TARGETS (its start node and X); then the tree's targets sorted by position (rank by counting: a batch has a few
+//     hundred);  (b) spr_paths_kernel: ONE sweep over the tree for all its studies -- position p is an ancestor-or-self of
+//     target t iff p <= t < p + subtree_size[p], i.e. the targets of p are a contiguous run of the sorted list, found by two binary
+//     searches in shared memory; cost per position independent of the number of studies (the per-study sweep it replaces issued
+//     26 M instructions for 128 studies of a 100k-tip tree).
+struct SprPathTree { int32_t tree, first, count, pad; };     // studies order[first .. first + count) address this tree
+
+// Per path target (sorted by position): where its ancestors go.  base = (length of the study's path to that target) - 1.
+struct alignas(16) SprPathTarget { int32_t pos, base; uint32_t off_lo, off_hi; };      // off = slab offset of path[] (start) / xpath[] (X)
+struct alignas(8) SprPathTargetAux { uint32_t pae_lo, pae_hi; };                        // slab offset of pae[] (start targets), 0 for X
+
+__global__ void __launch_bounds__(256) spr_init_kernel(ForestDev f, SprBatchDev B, const SprPathTree* __restrict__ ptrees,
+                                                       const int32_t* __restrict__ order, int32_t* __restrict__ traw,
+                                                       SprPathTarget* __restrict__ tgt, SprPathTargetAux* __restrict__ aux) {
+  const SprPathTree PT = ptrees[blockIdx.x];
+  for (int w = threadIdx.x; w < PT.count; w += 256) {
+    const int i = order[PT.first + w];
+    SprStudy& S = B.studies[i];
     const TreeDev T = f.trees[S.tree];
     const int pos0 = T.node_base + f.pos_of_node[T.node_base + S.start_branch];
     const int posX = S.X >= 0 ? T.node_base + f.pos_of_node[T.node_base + S.X] : -1;
     const int dep0 = f.depth[pos0], depX = posX >= 0 ? f.depth[posX] : -1;
-    s_pos0[tid] = pos0; s_posX[tid] = posX;
-    s_d0[tid] = min(dep0 + 1, S.path_cap) - 1; s_dX[tid] = posX >= 0 ? min(depX + 1, S.path_cap) - 1 : -1;
-    s_nb[tid] = T.node_base; s_N[tid] = T.num_nodes; s_tree[tid] = S.tree;
-    s_path[tid] = S.off_path; s_pae[tid] = S.off_pae; s_xpath[tid] = S.off_xpath;
-    if (blockIdx.x == 0) {
-      S.node_base = T.node_base; S.num_nodes = T.num_nodes; S.num_tiles = T.num_tiles; S.L = f.sites[T.sites_id].L;
-      S.root_pos = T.node_base; S.error = 0; S.scanned = 0; S.C0 = 0; S.H0 = 0;
-      S.num_missing = 0;
-      S.total_regions = 0; S.max_key = 0ULL; S.log_Wmax = 0.0; S.sum_W = 0.0;
-      int posP = -1, posS = -1, nP = 0, nS = 0, Proot = 0;
-      if (posX >= 0) {
-        posP = f.parent_pos[posX];
-        if (posP < 0) { S.error = 1; posP = posX; }
-        const int c1 = posP + 1, c0 = posP + 1 + f.subtree_size[posP + 1];
-        posS = (posX == c1) ? c0 : c1;
-        nP = f.mut_off[posP + 1] - f.mut_off[posP];
-        nS = f.mut_off[posS + 1] - f.mut_off[posS];
-        Proot = f.parent_pos[posP] < 0;
-      }
-      S.posX = posX; S.posP = posP; S.posS = posS; S.nP = nP; S.nS = nS; S.P_is_root = Proot;
-      S.pos0 = pos0; S.k0 = S.start_mut_idx; S.n0 = f.mut_off[pos0 + 1] - f.mut_off[pos0];
-      if (S.k0 < 0 || S.k0 > S.n0 || (pos0 == T.node_base && S.k0 != S.n0)) S.error = 2;
-      if (posX >= 0 && pos0 >= posX && pos0 < posX + f.subtree_size[posX]) S.error = 3;   // start inside X's subtree
-      S.path_len = min(dep0 + 1, S.path_cap);
-      S.xpath_len = posX >= 0 ? min(depX + 1, S.path_cap) : 0;
+    S.node_base = T.node_base; S.num_nodes = T.num_nodes; S.num_tiles = T.num_tiles; S.L = f.sites[T.sites_id].L;
+    S.root_pos = T.node_base; S.error = 0; S.scanned = 0; S.C0 = 0; S.H0 = 0;
+    S.num_missing = 0;
+    S.total_regions = 0; S.max_key = 0ULL; S.log_Wmax = 0.0; S.sum_W = 0.0;
+    int posP = -1, posS = -1, nP = 0, nS = 0, Proot = 0;
+    if (posX >= 0) {
+      posP = f.parent_pos[posX];
+      if (posP < 0) { S.error = 1; posP = posX; }
+      const int c1 = posP + 1, c0 = posP + 1 + f.subtree_size[posP + 1];
+      posS = (posX == c1) ? c0 : c1;
+      nP = f.mut_off[posP + 1] - f.mut_off[posP];
+      nS = f.mut_off[posS + 1] - f.mut_off[posS];
+      Proot = f.parent_pos[posP] < 0;
     }
+    S.posX = posX; S.posP = posP; S.posS = posS; S.nP = nP; S.nS = nS; S.P_is_root = Proot;
+    S.pos0 = pos0; S.k0 = S.start_mut_idx; S.n0 = f.mut_off[pos0 + 1] - f.mut_off[pos0];
+    if (S.k0 < 0 || S.k0 > S.n0 || (pos0 == T.node_base && S.k0 != S.n0)) S.error = 2;
+    if (posX >= 0 && pos0 >= posX && pos0 < posX + f.subtree_size[posX]) S.error = 3;   // start inside X's subtree
+    S.path_len = min(dep0 + 1, S.path_cap);
+    S.xpath_len = posX >= 0 ? min(depX + 1, S.path_cap) : 0;
+    traw[2 * (PT.first + w)] = pos0; traw[2 * (PT.first + w) + 1] = posX >= 0 ? posX : INT_MAX;
   }
   __syncthreads();
-  // each CTA sweeps kPathChunks chunks of positions for its studies: the dependent loads above are paid once per 8,192 positions
-  for (int ch = 0; ch < kPathChunks; ++ch) {
-    const int q = (blockIdx.x * kPathChunks + ch) * kSetupThreads + tid;      // tree-local position
-    int size = 0, dep = -1, cur_tree = -1;
-    for (int k = 0; k < ns; ++k) {
-      const int pos0 = s_pos0[k], posX = s_posX[k];
-      const int p = s_nb[k] + q;
-      if (q >= s_N[k] || p > max(pos0, posX)) continue;
-      if (s_tree[k] != cur_tree) { size = f.subtree_size[p]; dep = -1; cur_tree = s_tree[k]; }
-      const int end = p + size;
-      const bool a0 = p <= pos0 && end > pos0, aX = posX >= 0 && p <= posX && end > posX;
-      if (a0 || aX) {
-        if (dep < 0) dep = f.depth[p];
-        const int d0 = s_d0[k], dX = s_dX[k];
-        if (a0 && d0 - dep >= 0) {
-          ((int32_t*)(B.slab + s_path[k]))[d0 - dep] = p;
-          ((int2*)(B.slab + s_pae[k]))[d0 - dep] = make_int2(p, end);     // classify() searches these nested [start, end) ranges
-        }
-        if (aX && dX - dep >= 0) ((int32_t*)(B.slab + s_xpath[k]))[dX - dep] = p;
+  // the tree's targets sorted by position (rank by counting: a batch has a few hundred)
+  const int T2 = 2 * PT.count;
+  const int32_t* tr = traw + 2 * PT.first;
+  for (int a = threadIdx.x; a < T2; a += 256) {
+    const int pa = tr[a];
+    int rank = 0;
+    for (int b2 = 0; b2 < T2; ++b2) { const int pb = tr[b2]; rank += (pb < pa || (pb == pa && b2 < a)) ? 1 : 0; }
+    const SprStudy& S = B.studies[order[PT.first + (a >> 1)]];
+    SprPathTarget t; SprPathTargetAux x;
+    t.pos = pa;
+    if (a & 1) { t.base = S.xpath_len - 1; t.off_lo = (uint32_t)S.off_xpath; t.off_hi = (uint32_t)((unsigned long long)S.off_xpath >> 32); x.pae_lo = 0u; x.pae_hi = 0u; }
+    else {
+      t.base = S.path_len - 1; t.off_lo = (uint32_t)S.off_path; t.off_hi = (uint32_t)((unsigned long long)S.off_path >> 32);
+      x.pae_lo = (uint32_t)S.off_pae; x.pae_hi = (uint32_t)((unsigned long long)S.off_pae >> 32);
+    }
+    tgt[2 * PT.first + rank] = t; aux[2 * PT.first + rank] = x;
+  }
+}
+
+constexpr int kPathTargetsSmem = 1024;      // targets per slice of the sweep (512 studies of one tree)
+__global__ void __launch_bounds__(kSetupThreads) spr_paths_kernel(ForestDev f, SprBatchDev B, const SprPathTree* __restrict__ ptrees,
+                                                                  const SprPathTarget* __restrict__ tgt, const SprPathTargetAux* __restrict__ aux) {
+  __shared__ SprPathTarget s_t[kPathTargetsSmem];
+  __shared__ SprPathTargetAux s_x[kPathTargetsSmem];
+  __shared__ int s_start[kSetupThreads + 1], s_lo[kSetupThreads], s_end[kSetupThreads], s_dep[kSetupThreads];
+  __shared__ int s_ws[kSetupThreads / 32];
+  const SprPathTree PT = ptrees[blockIdx.y];
+  const TreeDev T = f.trees[PT.tree];
+  const int tid = threadIdx.x;
+  const int p = T.node_base + blockIdx.x * kSetupThreads + tid;
+  if ((long long)blockIdx.x * kSetupThreads >= T.num_nodes) return;
+  const bool in_tree = p < T.node_base + T.num_nodes;
+  const int end = in_tree ? p + f.subtree_size[p] : 0;
+  const int dep = in_tree ? f.depth[p] : 0;
+  const int T2 = 2 * PT.count;
+  for (int t0 = 0; t0 < T2; t0 += kPathTargetsSmem) {          // (one slice unless a tree has more than 512 studies in the batch)
+    const int nt = min(kPathTargetsSmem, T2 - t0);
+    __syncthreads();
+    for (int i = tid; i < nt; i += kSetupThreads) { s_t[i] = tgt[2 * PT.first + t0 + i]; s_x[i] = aux[2 * PT.first + t0 + i]; }
+    __syncthreads();
+    // the targets below this node: a run [lo, lo + cnt) of the sorted list
+    int lo = 0, cnt = 0;
+    if (in_tree) {
+      int hi = nt;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_t[mid].pos < p) lo = mid + 1; else hi = mid; }
+      int l2 = lo; hi = nt;
+      while (l2 < hi) { const int mid = (l2 + hi) >> 1; if (s_t[mid].pos < end) l2 = mid + 1; else hi = mid; }
+      cnt = l2 - lo;
+    }
+    // (node, target) pairs spread evenly over the CTA: the nodes near the root are above EVERY target, one thread each would
+    // serialise hundreds of stores; everything a pair needs is in shared memory, so a pair is a search and one or two stores
+    int total;
+    const int incl = block_scan_incl<int, kSetupThreads>(cnt, s_ws, &total);
+    s_start[tid] = incl - cnt; s_lo[tid] = lo; s_end[tid] = end; s_dep[tid] = dep;
+    if (tid == 0) s_start[kSetupThreads] = total;
+    __syncthreads();
+    for (int w = tid; w < total; w += kSetupThreads) {
+      int a = 0, bnd = kSetupThreads - 1;                        // last node whose run starts at or before pair w
+      while (a < bnd) { const int mid = (a + bnd + 1) >> 1; if (s_start[mid] <= w) a = mid; else bnd = mid - 1; }
+      const int node = T.node_base + blockIdx.x * kSetupThreads + a;
+      const int ti = s_lo[a] + (w - s_start[a]);
+      const SprPathTarget t = s_t[ti];
+      const int slot = t.base - s_dep[a];
+      if (slot >= 0) {
+        ((int32_t*)(B.slab + (((unsigned long long)t.off_hi << 32) | t.off_lo)))[slot] = node;
+        const SprPathTargetAux x = s_x[ti];
+        const unsigned long long po = ((unsigned long long)x.pae_hi << 32) | x.pae_lo;
+        if (po) ((int2*)(B.slab + po))[slot] = make_int2(node, s_end[a]);     // classify() searches these nested [start, end) ranges
       }
     }
   }
@@ -338,6 +390,11 @@ struct SprView {
       return (int)g2S[(size_t)e * 32 + g2_lane] + g2aggS[(size_t)(e >> 7) * 32 + g2_lane];
     }
     return Hloc[(size_t)q * stride] + agg[(q >> shift) * 3 + 0];
+  }
+  // H(q, k): potential of region k of branch q (event-scan path only): independent loads, no walk of the branch's mutations
+  __device__ __forceinline__ int Hregion(int q, int k) const {
+    const int e = g2_eopen[node_base + q] + k;
+    return (int)g2S[(size_t)e * 32 + g2_lane] + g2aggS[(size_t)(e >> 7) * 32 + g2_lane];
   }
   __device__ __forceinline__ int C(int q) const { return Cloc[(size_t)q * stride] + agg[(q >> shift) * 3 + 1]; }
   // KB(q): kept regions of the positions before q (q == num_nodes allowed)
@@ -705,7 +762,7 @@ __device__ void g_emit_node_general(const ForestDev& f, const SprStudy& S, const
   const int par = f.parent_pos[p];
   const bool is_root = p == S.root_pos;
   const double tNode = f.t[p], tPar = par >= 0 ? f.t[par] : 0.0;
-  int Hk = is_root ? 0 : V.H(par - S.node_base);
+  int Hk = (is_root || V.g2) ? 0 : V.H(par - S.node_base);
   const int kA = (j == 0) ? S.k0 : np;
   int n_up = 0, n_own = 0, rank = 0;
   unsigned long long best = 0ULL;       // fused weights: largest raw log-weight of this node's regions, as an ordered key
@@ -718,7 +775,7 @@ __device__ void g_emit_node_general(const ForestDev& f, const SprStudy& S, const
       else if (k == kA) idx = sg[0];
       else if (k > kA) idx = sg[1] + n_own++;
       else idx = sg[3] + (sg[4] - 1 - n_up++);
-      const int m = L.init_min_muts + (Hk - L.H0);
+      const int m = L.init_min_muts + ((V.g2 ? V.Hregion(p - S.node_base, k) : Hk) - L.H0);
       g_store_region(L, idx, r.branch, r.mut_idx, r.t_min, r.t_max, m);
       if (S.weights_fused && idx >= 0 && idx < L.region_cap) {
         double lw;
@@ -732,7 +789,7 @@ __device__ void g_emit_node_general(const ForestDev& f, const SprStudy& S, const
         if (lw == lw) { const unsigned long long key = f64_order_key(lw); if (key > best) best = key; }
       }
     }
-    if (k < np && !is_root) { int dh, dc; mut_dc(V.xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc); Hk += dh; }
+    if (!V.g2 && k < np && !is_root) { int dh, dc; mut_dc(V.xtab, f.mut_site[moff + k], f.mut_code[moff + k] & 15, dh, dc); Hk += dh; }
   }
   if (best != 0ULL) atomicMax(L.max_key, best);
 }
@@ -1512,6 +1569,29 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
       copies.push_back({(size_t)S.off_xm_end, r.x_missing_end}); copy_bytes.push_back(sizeof(int32_t) * S.n_x_missing);
     }
   }
+  // path targets: studies grouped by tree, two targets (start node, X) per study, sorted per tree on the device
+  std::vector<int32_t> path_order(n);
+  std::vector<SprPathTree> path_trees;
+  {
+    std::vector<std::vector<int32_t>> by(fo->h.num_trees);
+    for (int i = 0; i < n; ++i) by[reqs[i].tree].push_back(i);
+    int32_t first = 0;
+    for (int k = 0; k < fo->h.num_trees; ++k) {
+      if (by[k].empty()) continue;
+      std::copy(by[k].begin(), by[k].end(), path_order.begin() + first);
+      path_trees.push_back(SprPathTree{k, first, (int32_t)by[k].size(), 0});
+      first += (int32_t)by[k].size();
+    }
+  }
+  const size_t off_porder = off; off = al(off + sizeof(int32_t) * std::max(1, n));
+  const size_t off_ptrees = off; off = al(off + sizeof(SprPathTree) * std::max<size_t>(1, path_trees.size()));
+  const size_t off_traw = off; off = al(off + sizeof(int32_t) * 2 * std::max(1, n));
+  const size_t off_tgt = off; off = al(off + sizeof(SprPathTarget) * 2 * std::max(1, n));
+  const size_t off_taux = off; off = al(off + sizeof(SprPathTargetAux) * 2 * std::max(1, n));
+  if (n > 0) {
+    copies.push_back({off_porder, path_order.data()}); copy_bytes.push_back(sizeof(int32_t) * n);
+    copies.push_back({off_ptrees, path_trees.data()}); copy_bytes.push_back(sizeof(SprPathTree) * path_trees.size());
+  }
   const size_t slab_bytes = off;
   const size_t b_studies = 0;
   const size_t b_agg = al(b_studies + sizeof(SprStudy) * std::max(1, n));
@@ -1569,9 +1649,16 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   for (const SprGroupDev& G : groups) group_L = std::max(group_L, G.L);
   const int ng = (int)groups.size();
   const bool any_single = max_tiles256 > 0;        // studies on the per-study path
-  spr_paths_kernel<<<dim3((max_nodes + kSetupThreads * kPathChunks - 1) / (kSetupThreads * kPathChunks), (n + kPathStudies - 1) / kPathStudies), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
+  {
+    char* sl = b->dev.slab;
+    const SprPathTree* d_pt = (const SprPathTree*)(sl + off_ptrees);
+    spr_init_kernel<<<(unsigned)path_trees.size(), 256, 0, ctx->stream>>>(fo->h, b->dev, d_pt, (const int32_t*)(sl + off_porder), (int32_t*)(sl + off_traw),
+                                                                         (SprPathTarget*)(sl + off_tgt), (SprPathTargetAux*)(sl + off_taux));
+    spr_paths_kernel<<<dim3((max_nodes + kSetupThreads - 1) / kSetupThreads, (unsigned)path_trees.size()), kSetupThreads, 0, ctx->stream>>>(
+        fo->h, b->dev, d_pt, (const SprPathTarget*)(sl + off_tgt), (const SprPathTargetAux*)(sl + off_taux));
+  }
   spr_xtab_kernel<<<dim3(kXtabSlices, n), kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
-  int launched = 2;
+  int launched = 3;
   const dim3 grid_scan((std::max(max_tiles256, 1) + kScanSub - 1) / kScanSub, n);
   if (any_single) { spr_scan_kernel<0><<<grid_scan, kTile, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
   int g2_ev_chunks = 0, g2_t_chunks = 0, g2_templates = 1;
