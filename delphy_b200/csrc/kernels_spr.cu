@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_tile_prefix_kernel(ForestDe
   __shared__ int s_ws[kSetupThreads / 32];
   __shared__ int s_carry;
   SprStudy& S = B.studies[blockIdx.x];
-  if (S.error) return;
+  if (S.error || S.h_stride == 0) return;              // (h_stride 0: the study is walked by spr_frontier_kernel)
   spr_tile_prefix(f, B, S, blockIdx.x, S.limit != INT_MAX ? 1 : 3, s_ws, &s_carry);
 }
 
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
   __shared__ int s_ws[kSetupThreads / 32];
   __shared__ int s_carry;
   SprStudy& S = B.studies[blockIdx.x];
-  if (S.error) return;
+  if (S.error || S.h_stride == 0) return;              // (h_stride 0: the study is walked by spr_frontier_kernel)
   if (threadIdx.x == 0) S.mu = S.lambda_X / (double)(S.L - S.num_missing);   // Spr_study::mu, core/spr_study.cpp:239
   // the path index of S and P (a ten-step search of dependent loads) is found now, by two threads of another warp, rather than at the
   // end of the kernel where it would sit on the critical path
@@ -1282,6 +1282,7 @@ __global__ void __launch_bounds__(256) spr_normalize_kernel(SprBatchDev B) {
 
 #include "kernels_spr_group.cuh"
 #include "kernels_spr_group2.cuh"
+#include "kernels_spr_frontier.cuh"
 
 // ---- pick_nexus_region / find_region ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) spr_pick_kernel(SprBatchDev B, const double* __restrict__ r_in, int32_t* __restrict__ out_idx) {
@@ -1430,6 +1431,9 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   b->num = n; b->forest = fo;
   b->host.resize(n);
   int max_tiles = 1, max_tiles256 = 0;
+  bool any_frontier = false, any_swept_limited = false;
+  int num_bounded = 0;
+  for (int i = 0; i < n; ++i) num_bounded += reqs[i].max_muts_from_start != INT_MAX;
   size_t off = 0;
   std::vector<std::pair<size_t, const void*>> copies;   // (slab offset, host ptr) with sizes below
   std::vector<size_t> copy_bytes;
@@ -1519,7 +1523,16 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
       if (r.x_missing_start[k] < 0 || r.x_missing_end[k] > L || r.x_missing_start[k] >= r.x_missing_end[k]) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_RANGE, "spr: X missing interval out of range"); }
     const int N = T.num_nodes;
     const bool grouped = group_of[i] >= 0;
-    S.h_stride = grouped ? kGroup : 1; S.tile_shift = grouped ? 5 : 8;
+    // bounded studies of a small radius walk their ball (kernels_spr_frontier.cuh; DPHY_SPR_FRONTIER=0: the per-study sweeps instead)
+    // Measured on a 100k-tip tree (tools/spr_bounded_timing.py): radius 1: 7.0 vs 9.7 us per study in a batch of 64, 3.4 vs 7.9 in a
+    // batch of 512; radius 2: 17.4 vs 9.7 (64), 5.0 vs 7.9 (512) -- a walk lasts as long as its largest ball (mutation-free clades make
+    // the ball sizes heavy-tailed) while the sweeps cost the same for every study, so larger radii only walk in large batches.
+    static const int frontier_max = [] { const char* e = getenv("DPHY_SPR_FRONTIER"); return e ? atoi(e) : 4; }();
+    const bool frontier = !grouped && r.max_muts_from_start != INT_MAX && r.max_muts_from_start <= frontier_max &&
+                          (r.max_muts_from_start <= 1 || num_bounded >= 256);
+    any_frontier |= frontier;
+    any_swept_limited |= !grouped && !frontier && r.max_muts_from_start != INT_MAX;
+    S.h_stride = grouped ? kGroup : (frontier ? 0 : 1); S.tile_shift = grouped ? 5 : 8;
     S.num_htiles = grouped ? 1 : T.num_tiles;
     if (grouped && g2) {
       const SprGroupDev& G = groups[group_of[i]];
@@ -1528,7 +1541,7 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     }
     S.weights_fused = (grouped && fuse_weights && r.lambda_X > 0.0) ? 1 : 0;
     max_tiles = std::max(max_tiles, S.num_htiles);
-    if (!grouped) max_tiles256 = std::max(max_tiles256, T.num_tiles);
+    if (!grouped && !frontier) max_tiles256 = std::max(max_tiles256, T.num_tiles);
     // exact upper bound on regions: every non-root node has n+1 regions, the root has 1
     const int64_t cap64 = (int64_t)N + fo->tree_muts[r.tree] + 1;
     if (cap64 > INT_MAX) { delete b; return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: region capacity overflow"); }
@@ -1677,9 +1690,8 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     spr_g2_prefix_kernel<<<dim3(kPfxCtas, ng, 2), 1024, 0, ctx->stream>>>(b->dev, b->d_groups);
     launched += 4;
   }
-  bool any_limited = false;
-  for (int i = 0; i < n; ++i) any_limited |= (b->host[i].limit != INT_MAX);
-  if (any_limited) {
+  if (any_frontier) { spr_frontier_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
+  if (any_swept_limited) {
     spr_tile_prefix_kernel<<<n, kSetupThreads, 0, ctx->stream>>>(fo->h, b->dev);
     spr_scan_kernel<1><<<grid_scan, kTile, 0, ctx->stream>>>(fo->h, b->dev);
     launched += 2;
