@@ -585,9 +585,13 @@ def main():
                                   "frac": ab / (ms / reps * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": ab,
                                   "traffic": measured_traffic("emat_log_G_folded_kernel" if uniform else "emat_log_G_tile_kernel", cfg, chains)}}
             if spr_reqs is not None:
+                # 32 full studies on each of up to 32 trees of the forest in ONE batch (one group of the event-scan path per tree):
+                # small trees only fill the GPU when many chains ask at once
                 sf.eval_log_G()
-                xs2 = pick_spr_nodes(se[0], min(args.spr_studies, 64))
-                rq = db.spr_requests_for_attached(se[0], 0, xs2, sf.lambda_i(0), si[0]["t_max_tip"])
+                rq = []
+                for k in range(min(chains, 32)):
+                    xs2 = pick_spr_nodes(se[k], 32, seed=1234 + k)
+                    rq += db.spr_requests_for_attached(se[k], k, xs2, sf.lambda_i(k), si[k]["t_max_tip"])
                 for _ in range(2):
                     sf.spr_study_batch(rq).close()
                 a, b = ev(), ev()
@@ -598,6 +602,7 @@ def main():
                 b.record(stream); barrier()
                 (sms,) = max_over_ranks([a.elapsed_time(b) / nb])
                 bt = sf.spr_study_batch(rq); nreg = bt.total_regions(); bt.close()
+                entry["spr_studies_per_batch"] = len(rq)
                 entry["spr_candidates_per_s"] = nreg * world / (sms * 1e-3)
                 entry["spr_roofline_frac"] = nreg * 60 / (sms * 1e-3) / 1e9 / peak
             secondary[str(cfg)] = entry

@@ -555,6 +555,7 @@ int flatten_status_to_error(dphy_ctx* ctx, uint32_t bits) {
   if (bits & kFlattenErrMutState) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "mutation state not in ACGT");
   if (bits & kFlattenErrFsState) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "missation from-state not in ACGT");
   if (bits & kFlattenErrTimes) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "a node is earlier than its parent");
+  if (bits & kFlattenErrFswRange) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "more than 32,767 from-state overrides of one state on one branch");
   return DPHY_OK;
 }
 

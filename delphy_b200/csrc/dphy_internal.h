@@ -148,6 +148,7 @@ enum : uint32_t {
   kFlattenErrMissation = 16u,  // missation interval / from-state site out of range (core/mutations.h:187-191)
   kFlattenErrFsState = 32u,    // missation from-state not in ACGT
   kFlattenErrTimes = 64u,      // a node is earlier than its parent (the reference's integrity CHECK, core/phylo_tree.cpp:131)
+  kFlattenErrFswRange = 128u,  // more than 32,767 from-state overrides of one (partition, state) on one branch: the folded int16 counts would wrap
 };
 
 struct FlattenParams {

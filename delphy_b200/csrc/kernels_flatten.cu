@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(kTile) fold_branch_weights_kernel(FlattenParam
     const int p = p0 + tid;
     for (int k = 0; k < stride; ++k) {
       const int fk = k < K ? s_f[tid * kBwRow + k] : 0;
+      if (fk > 32767 || fk < -32768) flag_error(P, kFlattenErrFswRange);
       P.fsw[(size_t)p * stride + k] = (int16_t)fk;
       P.bw[(size_t)p * stride + k] = (k < K ? s_w[tid * kBwRow + k] : 0) + fk;
     }

@@ -25,7 +25,7 @@ fi
 if [[ $SEC == *n* ]]; then
   # one full capture of each hot kernel (the 4th..: warm-up launches are skipped with -s)
   timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"emat_log_G_folded_kernel|emat_log_G_tile_kernel|spr_gscan_kernel|spr_gemit_kernel|spr_xT_kernel|spr_weights_kernel|spr_normalize_kernel|spr_xtab_kernel|spr_paths_kernel|spr_segments_kernel" -s 20 -c 14 \
+    -k regex:"emat_log_G_folded_kernel|emat_log_G_tile_kernel|spr_" -s 48 -c 44 \
     -o $OUT/prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary --no-partitioned --no-mcmc --evals-per-step 2 --spr-batches-per-step 1 > $OUT/ncu_full.log 2>&1
   ncu -i $OUT/prof.ncu-rep --page raw --csv > $OUT/ncu_raw.csv 2>/dev/null
   python tools/summarize_ncu.py $OUT/ncu_raw.csv > $OUT/ncu_summary.txt 2>&1; grep -E "Kernel Name|gpu__time_duration|dram__bytes_(read|write)|dram__bytes.sum.per" $OUT/ncu_summary.txt
