@@ -267,6 +267,28 @@ def mcmc_figures(db, args, which, n_gpus):
                      "tips": (emat.num_nodes + 1) // 2}
         if r["returncode"] != 0:
             out[name]["stderr_tail"] = r["stderr_tail"][-4:]
+        last_case = (name, path, steps)
+    if n_gpus > 1:
+        # weak scaling (BASELINE.json configs[4]: independent chains, replicas only): one CLI process per GPU, one worker thread each,
+        # different seeds, all at once; steps/s summed.  The figures above are the strong-scaling ones (ONE chain, its tree cut into
+        # n_gpus parts, a worker thread and a GPU per part).
+        name, path, steps = last_case
+        res = [None] * n_gpus
+
+        def one(i):
+            env = {"DPHY_DEVICES": 1, "DPHY_DROPIN_STATS": 0}
+            if which == "dropin":
+                env["CUDA_VISIBLE_DEVICES"] = i
+            res[i] = mcmc.run_cli(binary, path, steps, threads=1, seed=20251017 + 1 + i, log_every=max(1, steps // 10), env=env, timeout=900)
+        ths = [threading.Thread(target=one, args=(i,)) for i in range(n_gpus)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        ok = all(r is not None and r["returncode"] == 0 and r["steps_per_s"] for r in res)
+        out[name + "_independent_chains"] = {"chains": n_gpus, "steps_per_s": sum(r["steps_per_s"] for r in res) if ok else None,
+                                             "per_chain_steps_per_s": [r["steps_per_s"] if r else None for r in res], "steps_per_chain": steps,
+                                             "returncodes": [r["returncode"] if r else None for r in res]}
     return out
 
 

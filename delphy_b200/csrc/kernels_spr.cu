@@ -283,14 +283,27 @@ __global__ void __launch_bounds__(kSetupThreads) spr_xtab_kernel(ForestDev f, Sp
   const int32_t* xpath = from_tree ? (const int32_t*)(B.slab + S.off_xpath) : (const int32_t*)(B.slab + S.off_path);
   const int xpath_len = from_tree ? S.xpath_len : (rel_start ? S.path_len : 0);
   if (from_tree) {
-    // missing_at_X = union of the missation intervals on the X->root path (disjoint along a path by invariant):
-    // one warp per path node, lanes stride over the sites of each interval that fall into this CTA's slice
-    for (int jj = warp; jj < xpath_len; jj += kSetupThreads / 32) {
-      const int a = xpath[jj];
-      for (int i = f.miss_off[a]; i < f.miss_off[a + 1]; ++i) {
-        const int2 se = f.miss_se[i];
+    // missing_at_X = union of the missation intervals on the X->root path (disjoint along a path by invariant).  The path nodes'
+    // interval ranges are gathered by all threads at once and scanned, then the warps take the INTERVALS in turn (owner by binary
+    // search in shared memory), lanes striding over the sites that fall into this CTA's slice: one round of dependent loads instead
+    // of one per path node (a warp per path node was a chain of ~13 x 4 load latencies, most of this kernel's 38 us)
+    __shared__ int s_ist[kSetupThreads + 1], s_io0[kSetupThreads];
+    for (int j0 = 0; j0 < xpath_len; j0 += kSetupThreads) {
+      const int j = j0 + tid;
+      int o0 = 0, c = 0;
+      if (j < xpath_len) { const int a = xpath[j]; o0 = f.miss_off[a]; c = f.miss_off[a + 1] - o0; }
+      int tot;
+      const int incl = block_scan_incl<int, kSetupThreads>(c, s_ws, &tot);
+      s_ist[tid] = incl - c; s_io0[tid] = o0;
+      if (tid == 0) s_ist[kSetupThreads] = tot;
+      __syncthreads();
+      for (int w = warp; w < tot; w += kSetupThreads / 32) {
+        int a = 0, b = kSetupThreads - 1;                      // last path node whose intervals start at or before w
+        while (a < b) { const int mid = (a + b + 1) >> 1; if (s_ist[mid] <= w) a = mid; else b = mid - 1; }
+        const int2 se = f.miss_se[s_io0[a] + (w - s_ist[a])];
         for (int l = max(se.x, l0) + lane; l < min(se.y, l1); l += 32) xtab[l] |= 4;
       }
+      __syncthreads();
     }
   } else {
     const int32_t* ms = (const int32_t*)(B.slab + S.off_xm_start);
