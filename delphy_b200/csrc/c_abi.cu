@@ -562,7 +562,7 @@ int flatten_status_to_error(dphy_ctx* ctx, uint32_t bits) {
 }  // namespace
 
 static int forest_upload_impl(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* trees, const TreeTotals* totals, const int32_t* sites_index,
-                              int32_t num_sites_tables, dphy_sites* const* sites, dphy_forest** out) {
+                              int32_t num_sites_tables, dphy_sites* const* sites, dphy_forest** out, const dphy_forest* order_from = nullptr) {
   if (!ctx || !out || num_trees < 0 || (num_trees > 0 && (!trees || !sites)) || num_sites_tables <= 0) return DPHY_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   cudaSetDevice(ctx->device);
@@ -665,6 +665,7 @@ static int forest_upload_impl(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_
   const int64_t scan_tiles = (N + 1023) / 1024;
   const int w_scan = work.reserve(sizeof(int32_t) * 3 * scan_tiles);
   const int w_status = work.reserve(sizeof(uint32_t) * 4 + sizeof(int32_t) * num_trees);
+  const int w_jobs = work.reserve(sizeof(DeviceCopyJob) * ((size_t)num_trees * 15 + 1));     // device-resident sources only (see below)
 
   char* dbase = nullptr; char* tbase = nullptr; char* wbase = nullptr;
   if (cudaMallocAsync((void**)&dbase, slab.total, ctx->stream) != cudaSuccess) { delete fo; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(forest)"); }
@@ -748,7 +749,25 @@ static int forest_upload_impl(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_
   std::vector<char> tree_has_lists(num_trees, 0);
   for (const CopyJob& j : jobs) if (j.group == 2 && j.tree >= 0) tree_has_lists[j.tree] = 1;
   bool two_phase = false;
-  st = staged_upload(ctx, hraw, jobs, tbase, raw_upload_bytes, &two_phase);
+  if (totals) {
+    // device-resident sources (dphy_forest_apply_rows): ONE kernel copies every array (the copy-stream path above costs a driver
+    // call and an event or two per array -- 240 arrays for 16 trees, more host time than all the kernels of the rebuild)
+    DeviceCopyJob* hj = reinterpret_cast<DeviceCopyJob*>(hraw + align_up(tmp.blocks[r_raw].off + sizeof(RawTreeDev) * (size_t)num_trees));
+    int nj = 0;
+    size_t max_bytes = 1;
+    cudaError_t ce2 = cudaSuccess;
+    for (const CopyJob& j : jobs) {
+      if (j.tree < 0) { ce2 = cudaMemcpyAsync(tbase + j.dst_off, j.src, j.bytes, cudaMemcpyHostToDevice, ctx->stream); continue; }   // the per-tree records
+      hj[nj++] = DeviceCopyJob{tbase + j.dst_off, static_cast<const char*>(j.src), j.bytes};
+      max_bytes = std::max(max_bytes, j.bytes);
+    }
+    DeviceCopyJob* dj = work.at<DeviceCopyJob>(wbase, w_jobs);
+    if (ce2 == cudaSuccess && nj > 0) ce2 = cudaMemcpyAsync(dj, hj, sizeof(DeviceCopyJob) * nj, cudaMemcpyHostToDevice, ctx->stream);
+    if (ce2 == cudaSuccess && nj > 0) st = launch_device_copies(ctx, dj, nj, max_bytes);
+    else st = check_cuda(ctx, ce2, "device copy jobs");
+  } else {
+    st = staged_upload(ctx, hraw, jobs, tbase, raw_upload_bytes, &two_phase);
+  }
   if (!two_phase) release_pinned_async(ctx);
   if (st != DPHY_OK) return fail(st);
 
@@ -796,6 +815,10 @@ static int forest_upload_impl(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_
   P.fs_off = const_cast<int32_t*>(h.fs_off); P.fs_site = const_cast<int32_t*>(h.fs_site); P.fs_code = const_cast<uint8_t*>(h.fs_code);
   P.fsw = const_cast<int16_t*>(h.fsw); P.fsw_stride = fsw_stride;
   P.bw = const_cast<int32_t*>(h.bw);
+  if (order_from) {
+    P.old_pos_of_node = order_from->h.pos_of_node; P.old_depth = order_from->h.depth; P.old_subtree_size = order_from->h.subtree_size;
+    P.old_parent_pos = order_from->h.parent_pos;
+  }
   if (two_phase) {
     // Euler-tour ranking as soon as the topology arrays have landed; the rest once the lists have
     ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_topo, 0);
@@ -859,11 +882,11 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
 
 // Re-flatten `fo` from device-resident host-order arrays (dphy_forest_apply_rows): a fresh forest is built by the upload path with
 // device sources, then swapped into the caller's handle; the old contents are released stream-ordered.  On failure `fo` is untouched.
-int dphy::rebuild_forest_from_device(dphy_ctx* ctx, dphy_forest* fo, const dphy_emat_host* trees, const TreeTotals* totals) {
+int dphy::rebuild_forest_from_device(dphy_ctx* ctx, dphy_forest* fo, const dphy_emat_host* trees, const TreeTotals* totals, bool same_links) {
   dphy_forest* fresh = nullptr;
   const std::vector<dphy_sites*> sites = fo->sites;
   const std::vector<int32_t> si = fo->sites_index;
-  int st = forest_upload_impl(ctx, fo->h.num_trees, trees, totals, si.data(), (int32_t)sites.size(), sites.data(), &fresh);
+  int st = forest_upload_impl(ctx, fo->h.num_trees, trees, totals, si.data(), (int32_t)sites.size(), sites.data(), &fresh, same_links ? fo : nullptr);
   if (st != DPHY_OK) return st;
   fresh->cnt_mut = std::move(fo->cnt_mut); fresh->cnt_miss = std::move(fo->cnt_miss); fresh->cnt_fs = std::move(fo->cnt_fs);
   std::swap(*fo, *fresh);

@@ -169,6 +169,10 @@ struct FlattenParams {
   int32_t* fs_off; int32_t* fs_site; uint8_t* fs_code;
   int16_t* fsw; int32_t fsw_stride;
   int32_t* bw;
+  // re-flatten of trees whose links did not change (dphy_forest_apply_rows): the DFS order of the forest being replaced is reused
+  // and the Euler-tour ranking skipped (null: rank from scratch)
+  const int32_t* old_pos_of_node = nullptr; const int32_t* old_depth = nullptr; const int32_t* old_subtree_size = nullptr;
+  const int32_t* old_parent_pos = nullptr;
 };
 
 }  // namespace dphy
@@ -260,7 +264,7 @@ struct dphy_forest {
 namespace dphy {
 // List totals of one tree whose arrays are NOT host-readable (device-resident sources of dphy_forest_apply_rows).
 struct TreeTotals { int64_t m, iv, fs, root_m; };
-int rebuild_forest_from_device(dphy_ctx* ctx, dphy_forest* fo, const dphy_emat_host* trees, const TreeTotals* totals);   // c_abi.cu
+int rebuild_forest_from_device(dphy_ctx* ctx, dphy_forest* fo, const dphy_emat_host* trees, const TreeTotals* totals, bool same_links);   // c_abi.cu
 int launch_raw_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count);   // kernels_delta.cu
 int set_error(dphy_ctx* ctx, int status, const std::string& msg);
 int check_cuda(dphy_ctx* ctx, cudaError_t e, const char* what);
@@ -282,6 +286,9 @@ int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max
 // stage 2 split per tree (direct uploads: each tree's lists are gathered as soon as its own arrays have landed)
 int launch_flatten_lists(dphy_ctx* ctx, FlattenParams P, int first_tile, int num_tiles);
 int launch_flatten_ctiles(dphy_ctx* ctx, const FlattenParams& P);
+// many device-to-device array copies in one launch (16-byte aligned sources and destinations)
+struct DeviceCopyJob { char* dst; const char* src; size_t bytes; };
+int launch_device_copies(dphy_ctx* ctx, const DeviceCopyJob* d_jobs, int num_jobs, size_t max_bytes);
 int launch_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count, uint32_t* d_status);
 // Pinned staging buffer of the ctx: acquire waits for the previous async copy out of it; release records an event.
 int acquire_pinned(dphy_ctx* ctx, size_t bytes, void** out);

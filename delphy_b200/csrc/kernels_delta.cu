@@ -44,9 +44,14 @@ __global__ void delta_mark_kernel(int32_t* __restrict__ row_of, int num_nodes, c
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < num_nodes) row_of[i] = -1;
 }
-__global__ void delta_mark_rows_kernel(int32_t* __restrict__ row_of, const RowDev* __restrict__ rows, int row0, int row1) {
+__global__ void delta_mark_rows_kernel(int32_t* __restrict__ row_of, const RowDev* __restrict__ rows, int row0, int row1, RawTreeDev old,
+                                       uint32_t* __restrict__ links_changed) {
   const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < row1) row_of[rows[i].node] = i;      // a node listed twice: the later row wins deterministically only if callers avoid it (checked on the host)
+  if (i >= row1) return;
+  const RowDev r = rows[i];
+  row_of[r.node] = i;      // a node listed twice: the later row wins deterministically only if callers avoid it (checked on the host)
+  // a row that keeps its node's links (displacements, branch reforms) leaves the DFS order alone: the re-flatten then skips the ranking
+  if (r.parent != old.parent[r.node] || r.child0 != old.child0[r.node] || r.child1 != old.child1[r.node]) atomicOr(links_changed, 1u);
 }
 
 // New CSR offsets of the three lists (blockIdx.y = list kind) from the patched per-node lengths, two levels: every CTA scans one
@@ -249,9 +254,16 @@ extern "C" int dphy_forest_apply_rows(dphy_ctx* ctx, dphy_forest* fo, int32_t co
   std::vector<void*> scratch;       // new raw blocks + row maps: consumed by the re-flatten below, freed stream-ordered after it
   scratch.push_back(d_pay);
   auto free_scratch = [&]() { for (void* p : scratch) cudaFreeAsync(p, ctx->stream); };
+  // one word: set by a row whose links differ from its node's current ones
+  uint32_t* d_links = nullptr;
+  if (cudaMallocAsync((void**)&d_links, 256, ctx->stream) != cudaSuccess) { free_scratch(); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(apply_rows flag)"); }
+  scratch.push_back(d_links);
+  cudaMemsetAsync(d_links, 0, sizeof(uint32_t), ctx->stream);
+  bool root_changed = false;
   int row0 = 0;
   for (int k = 0; k < nt; ++k) {
     const RawTreeDev& R = fo->raw[k];
+    if (new_roots && new_roots[k] != R.root) root_changed = true;
     const int n = R.num_nodes;
     dphy_emat_host& e = views[k];
     std::memset(&e, 0, sizeof(e));
@@ -292,7 +304,7 @@ extern "C" int dphy_forest_apply_rows(dphy_ctx* ctx, dphy_forest* fo, int32_t co
     out.fs_off = (int32_t*)(nb + a_foff); out.fs_site = (int32_t*)(nb + a_fsite); out.fs_from = (uint8_t*)(nb + a_ffrom);
     int32_t* row_of = (int32_t*)(nb + a_map);
     delta_mark_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(row_of, n, P.rows, row0, row0 + nrows);
-    delta_mark_rows_kernel<<<(nrows + 255) / 256, 256, 0, ctx->stream>>>(row_of, P.rows, row0, row0 + nrows);
+    delta_mark_rows_kernel<<<(nrows + 255) / 256, 256, 0, ctx->stream>>>(row_of, P.rows, row0, row0 + nrows, R, d_links);
     delta_offsets_kernel<<<dim3(ntiles, 3), 1024, 0, ctx->stream>>>(R, out, row_of, P.rows, (int32_t*)(nb + a_tt));
     delta_offsets_fix_kernel<<<dim3(ntiles, 3), 1024, 0, ctx->stream>>>(out, n, (const int32_t*)(nb + a_tt));
     delta_gather_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(R, out, row_of, P);
@@ -304,8 +316,12 @@ extern "C" int dphy_forest_apply_rows(dphy_ctx* ctx, dphy_forest* fo, int32_t co
     e.fs_off = out.fs_off; e.fs_site = out.fs_site; e.fs_from = out.fs_from;
   }
   st = check_cuda(ctx, cudaGetLastError(), "apply_rows kernels");
+  uint32_t links = 1u;
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(&links, d_links, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  if (st == DPHY_OK) st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "apply_rows");
+  const bool same_links = links == 0u && !root_changed;
   // ---- re-flatten from the device-resident arrays (the same kernels as an upload; validation included) ----------------------------------------------
-  if (st == DPHY_OK) st = rebuild_forest_from_device(ctx, fo, views.data(), totals.data());
+  if (st == DPHY_OK) st = rebuild_forest_from_device(ctx, fo, views.data(), totals.data(), same_links);
   free_scratch();
   if (st != DPHY_OK) {
     // the forest is unchanged (the rebuild swaps only on success), but the host mirror of the list lengths is now ahead of it

@@ -20,6 +20,8 @@
 #include "dphy_internal.h"
 #include "device_utils.cuh"
 
+#include <algorithm>
+
 namespace dphy {
 
 constexpr int kScanItems = 4;                       // items per thread in the offset scans
@@ -362,12 +364,50 @@ int launch_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_
   return check_cuda(ctx, cudaGetLastError(), "set_node_times_kernel");
 }
 
+// The node records of trees whose links are those of the forest being replaced: same DFS order, depth and subtree sizes (copied through
+// the old position of every node), fresh times and list lengths, the same checks as flatten_nodes_kernel.
+__global__ void __launch_bounds__(kTile) flatten_nodes_reuse_kernel(FlattenParams P) {
+  const int tile = blockIdx.x;
+  const int tree = P.tile_tree[tile];
+  const TreeDev T = P.trees[tree];
+  const RawTreeDev R = P.raw[tree];
+  const int v = (tile - T.first_tile) * kTile + threadIdx.x;
+  if (v >= T.num_nodes) return;
+  const int n = T.num_nodes;
+  const int g = T.node_base + v;
+  const int pre = P.old_pos_of_node[g];
+  const int p = T.node_base + pre;
+  const int depth = P.old_depth[p], size = P.old_subtree_size[p];
+  P.node_id[p] = v;
+  P.pos_of_node[g] = pre;
+  P.depth[p] = depth;
+  P.subtree_size[p] = size;
+  P.t[p] = R.t[v];
+  P.post_node[T.node_base + pre + size - 1 - depth] = p;        // post-order index of a node = pre + size - 1 - depth
+  const int par = R.parent[v];
+  P.parent_pos[p] = P.old_parent_pos[p];
+  if (par >= 0 && R.t[v] < R.t[par]) flag_error(P, kFlattenErrTimes);
+  int cm = R.mut_off[v + 1] - R.mut_off[v], ci = R.miss_off[v + 1] - R.miss_off[v], cf = R.fs_off[v + 1] - R.fs_off[v];
+  if (cm < 0 || ci < 0 || cf < 0 || R.mut_off[v] < 0 || R.miss_off[v] < 0 || R.fs_off[v] < 0 ||
+      R.mut_off[v + 1] > R.num_muts || R.miss_off[v + 1] > R.num_ivls || R.fs_off[v + 1] > R.num_fs) {
+    flag_error(P, kFlattenErrOffsets); cm = ci = cf = 0;
+  }
+  P.mut_off[p] = cm; P.miss_off[p] = ci; P.fs_off[p] = cf;
+  atomicMax(P.max_depth + tree, depth);
+  if (pre + size < n && pre / kLgTile != (pre + size) / kLgTile) {
+    const uint32_t slot = atomicAdd(P.status + 1, 1u);
+    P.strad_list[2 * slot] = p; P.strad_list[2 * slot + 1] = T.sites_id;
+  }
+}
+
 int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max_tree_nodes, int stage) {
   if (P.num_nodes == 0) return DPHY_OK;
   const int num_arcs = 2 * P.num_nodes;
   int rounds = 0;
   while ((1LL << rounds) < 2LL * max_tree_nodes) ++rounds;
-  if (stage < 0 || stage == 0) {
+  const bool reuse = P.old_pos_of_node != nullptr;
+  if (reuse && stage == 0) return DPHY_OK;       // nothing to rank
+  if ((stage < 0 || stage == 0) && !reuse) {
     flatten_arcs_init_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
     for (int r = 0; r < rounds; ++r)
       flatten_rank_round_kernel<<<(num_arcs + 255) / 256, 256, 0, ctx->stream>>>(P.arcs[r & 1], P.arcs[(r + 1) & 1], num_arcs);
@@ -375,7 +415,8 @@ int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max
     if (stage == 0) return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch (topology)");
   }
   if (stage < 0 || stage == 1) {
-    flatten_nodes_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P, rounds & 1);
+    if (reuse) flatten_nodes_reuse_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P);
+    else flatten_nodes_kernel<<<num_tiles, kTile, 0, ctx->stream>>>(P, rounds & 1);
     const int nst = (P.num_nodes + kScanTile - 1) / kScanTile;
     flatten_scan_reduce_kernel<<<nst, kTile, 0, ctx->stream>>>(P);
     flatten_scan_spine_kernel<<<1, 1024, 0, ctx->stream>>>(P, nst);
@@ -388,6 +429,24 @@ int launch_flatten(dphy_ctx* ctx, const FlattenParams& P, int num_tiles, int max
   flatten_ctiles_kernel<<<(P.num_ctiles + 255) / 256, 256, 0, ctx->stream>>>(P);
   ctx->launches += 3;
   return check_cuda(ctx, cudaGetLastError(), "flatten kernels launch");
+}
+
+// grid = (slices, jobs): job blockIdx.y copied by its slices in 16-byte pieces (+ a byte tail)
+__global__ void __launch_bounds__(256) device_copies_kernel(const DeviceCopyJob* __restrict__ jobs) {
+  const DeviceCopyJob J = jobs[blockIdx.y];
+  const size_t n16 = J.bytes / 16;
+  const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(J.src);
+  uint4* __restrict__ d4 = reinterpret_cast<uint4*>(J.dst);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (size_t)gridDim.x * 256) d4[i] = s4[i];
+  if (blockIdx.x == 0) for (size_t i = n16 * 16 + threadIdx.x; i < J.bytes; i += 256) J.dst[i] = J.src[i];
+}
+
+int launch_device_copies(dphy_ctx* ctx, const DeviceCopyJob* d_jobs, int num_jobs, size_t max_bytes) {
+  if (num_jobs <= 0) return DPHY_OK;
+  const int slices = (int)std::min<size_t>(64, std::max<size_t>(1, max_bytes / (256 * 16 * 4)));
+  device_copies_kernel<<<dim3(slices, num_jobs), 256, 0, ctx->stream>>>(d_jobs);
+  ctx->launches += 1;
+  return check_cuda(ctx, cudaGetLastError(), "device_copies_kernel");
 }
 
 int launch_flatten_lists(dphy_ctx* ctx, FlattenParams P, int first_tile, int num_tiles) {
