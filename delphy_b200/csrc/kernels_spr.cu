@@ -1298,29 +1298,32 @@ __global__ void __launch_bounds__(256) spr_normalize_kernel(SprBatchDev B) {
 #include "kernels_spr_frontier.cuh"
 
 // ---- pick_nexus_region / find_region ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) spr_pick_kernel(SprBatchDev B, const double* __restrict__ r_in, int32_t* __restrict__ out_idx) {
-  __shared__ double s_ws[32];
-  __shared__ int s_found;
-  __shared__ double s_carry;
-  const SprStudy& S = B.studies[blockIdx.x];
+// Spr_study::pick_nexus_region (core/spr_study.cpp:404-422) scans "if (W_i >= r) pick i; else r -= W_i": a chain of fp64 subtractions
+// whose rounding decides the index when r falls next to a boundary.  A prefix sum in any other association can pick the neighbour
+// (round 1 did, and its test allowed it), so the scan is replayed in the reference's own order: one warp per study, the weights
+// loaded 32 at a time (the next chunk already in flight), every lane carrying the same r.  ~1 ms for the studies of a batch, once
+// per study at most.
+__global__ void __launch_bounds__(128) spr_pick_kernel(SprBatchDev B, const double* __restrict__ r_in, int32_t* __restrict__ out_idx) {
+  const unsigned full = 0xffffffffu;
+  const int study = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (study >= B.num_studies) return;
+  const SprStudy& S = B.studies[study];
   const int n = min(S.total_regions, S.region_cap);
-  const double2* nw = (const double2*)(B.slab + S.off_nw);
-  const double r = r_in[blockIdx.x];
-  if (threadIdx.x == 0) { s_found = INT_MAX; s_carry = 0.0; }
-  __syncthreads();
-  for (int i0 = 0; i0 < n; i0 += 1024) {
-    const int i = i0 + threadIdx.x;
-    const double w = i < n ? nw[i].y : 0.0;
-    double tot;
-    const double incl = block_scan_incl<double, 1024>(w, s_ws, &tot);
-    // the reference scans "if (W_i >= r) pick i; else r -= W_i"  <=>  first i with r - sum_{j<i} W_j <= W_i
-    if (i < n && w >= r - (s_carry + incl - w)) atomicMin(&s_found, i);
-    __syncthreads();
-    if (s_found != INT_MAX) break;
-    if (threadIdx.x == 0) s_carry += tot;
-    __syncthreads();
+  const double2* __restrict__ nw = (const double2*)(B.slab + S.off_nw);
+  double r = r_in[study];
+  int found = -1;
+  double w_next = lane < n ? nw[lane].y : 0.0;
+  for (int i0 = 0; i0 < n && found < 0; i0 += 32) {
+    const double w = w_next;
+    w_next = i0 + 32 + lane < n ? nw[i0 + 32 + lane].y : 0.0;
+    const int cnt = min(32, n - i0);
+    for (int j = 0; j < cnt; ++j) {
+      const double wj = __shfl_sync(full, w, j);
+      if (wj >= r) { found = i0 + j; break; }
+      r -= wj;
+    }
   }
-  if (threadIdx.x == 0) out_idx[blockIdx.x] = s_found == INT_MAX ? 0 : s_found;
+  if (lane == 0) out_idx[study] = found < 0 ? 0 : found;
 }
 
 __global__ void __launch_bounds__(256) spr_find_kernel(SprBatchDev B, int study, int branch, double t, int32_t* out_idx) {
@@ -1887,7 +1890,7 @@ int dphy_spr_batch_pick_nexus_regions(dphy_ctx* ctx, dphy_spr_batch* b, const do
   int32_t* d_o = (int32_t*)ctx->arena.alloc(sizeof(int32_t) * b->num);
   if (!d_r || !d_o) { ctx->arena.release(mark); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (spr pick)"); }
   DPHY_CUDA(ctx, cudaMemcpyAsync(d_r, r, sizeof(double) * b->num, cudaMemcpyHostToDevice, ctx->stream));
-  spr_pick_kernel<<<b->num, 1024, 0, ctx->stream>>>(b->dev, d_r, d_o);
+  spr_pick_kernel<<<(b->num + 3) / 4, 128, 0, ctx->stream>>>(b->dev, d_r, d_o);
   ctx->launches += 1;
   int st = check_cuda(ctx, cudaGetLastError(), "spr_pick_kernel");
   if (st == DPHY_OK) st = check_cuda(ctx, cudaMemcpyAsync(out_idx, d_o, sizeof(int32_t) * b->num, cudaMemcpyDeviceToHost, ctx->stream), "D2H");

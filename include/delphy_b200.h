@@ -294,8 +294,9 @@ int64_t dphy_spr_batch_total_regions(dphy_ctx* ctx, dphy_spr_batch* batch);
 /* copies the regions of study `request` (or of all studies if request < 0) to out[cap]; returns count or <0 */
 int64_t dphy_spr_batch_get_regions(dphy_ctx* ctx, dphy_spr_batch* batch, int32_t request,
                                    dphy_candidate_region* out, int64_t cap);
-/* Spr_study::pick_nexus_region (core/spr_study.cpp:404-422) with the caller's uniform draw r in [0,sum_W): the
- * device does the CDF search (prefix sums); out_region_idx[i] for every study i given r[i]. */
+/* Spr_study::pick_nexus_region (core/spr_study.cpp:404-422) with the caller's uniform draw r in [0,sum_W): the device replays
+ * the reference's scan (if W_i >= r pick i, else r -= W_i) in the same order, so the index is the one the reference's code returns
+ * for these weights; out_region_idx[i] for every study i given r[i]. */
 int  dphy_spr_batch_pick_nexus_regions(dphy_ctx* ctx, dphy_spr_batch* batch, const double* r, int32_t* out_region_idx);
 /* Spr_study::find_region (core/spr_study.cpp:474-484) for study `request` */
 int  dphy_spr_batch_find_region(dphy_ctx* ctx, dphy_spr_batch* batch, int32_t request, int32_t branch, double t,

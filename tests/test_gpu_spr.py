@@ -139,9 +139,7 @@ def test_synthetic_studies(ctx, orc, cfg, ov, nx, limit):
             w_ref = orc.lib.orc_spr_pick_nexus_region(want.ctypes.data_as(C.POINTER(OrcRegion)), len(want), float(r[i]))
             w_dev = orc.lib.orc_spr_pick_nexus_region(got.ctypes.data_as(C.POINTER(OrcRegion)), len(got), float(r[i]))
             assert w_dev == w_ref                       # the reference's own scan over the device's weights
-            cum = np.cumsum(want["W_over_Wmax"])
-            near_boundary = np.min(np.abs(cum - r[i])) < 1e-9 * max(1.0, cum[-1])
-            assert picked[i] == w_ref or near_boundary  # device-side CDF search
+            assert picked[i] == w_dev                   # the device replays the reference's scan in its own order: same index, always
         batch.close()
     fo.close(); ds.close()
 
