@@ -134,6 +134,9 @@ void dphy_ctx_destroy(dphy_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->pinned_ev) cudaEventDestroy(ctx->pinned_ev);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);

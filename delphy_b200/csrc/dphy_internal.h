@@ -196,6 +196,10 @@ struct dphy_ctx {
   cudaEvent_t ev_copy[kCopyStreams] = {};
   std::vector<cudaEvent_t> ev_tree;   // per-tree "lists have landed" events of a direct upload (grown on demand)
   cudaEvent_t ev_main = nullptr, ev_topo = nullptr, ev_nodes = nullptr, ev_lists = nullptr;
+  // side stream of the SPR batches: the study-independent template / keep-mask kernels run next to the latency-bound path / X-table
+  // chain of the main stream (fork after spr_init_kernel, join before the prefix kernel)
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   struct DeferredCopy { void* dst; const void* src; size_t bytes; };
   std::vector<DeferredCopy> deferred_d2h;   // device->host copies of a batched getter, issued once all its kernels are enqueued
   bool logg_attr_set = false;   // opt-in dynamic shared memory of the log-G tile kernel

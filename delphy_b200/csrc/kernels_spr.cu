@@ -1678,11 +1678,25 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   for (const SprGroupDev& G : groups) group_L = std::max(group_L, G.L);
   const int ng = (int)groups.size();
   const bool any_single = max_tiles256 > 0;        // studies on the per-study path
+  static const bool use_aux = [] { const char* e = getenv("DPHY_SPR_AUX_STREAM"); return !(e && atoi(e) == 0); }();
   {
     char* sl = b->dev.slab;
     const SprPathTree* d_pt = (const SprPathTree*)(sl + off_ptrees);
     spr_init_kernel<<<(unsigned)path_trees.size(), 256, 0, ctx->stream>>>(fo->h, b->dev, d_pt, (const int32_t*)(sl + off_porder), (int32_t*)(sl + off_traw),
                                                                          (SprPathTarget*)(sl + off_tgt), (SprPathTargetAux*)(sl + off_taux));
+    // fork: what depends on the tree and the studies' positions alone (constants, template records, keep masks) runs on the side stream
+    // while the main stream walks the latency-bound chain paths -> X tables -> event scan
+    if (ng > 0 && g2 && use_aux) {
+      if (!ctx->aux_stream) {
+        if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+          cudaFreeAsync(d, ctx->stream); delete b; return set_error(ctx, DPHY_ERR_CUDA, "spr: side stream");
+        }
+      }
+      cudaEventRecord(ctx->ev_fork, ctx->stream);
+      cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0);
+    }
     spr_paths_kernel<<<dim3((max_nodes + kSetupThreads - 1) / kSetupThreads, (unsigned)path_trees.size()), kSetupThreads, 0, ctx->stream>>>(
         fo->h, b->dev, d_pt, (const SprPathTarget*)(sl + off_tgt), (const SprPathTargetAux*)(sl + off_taux));
   }
@@ -1697,12 +1711,14 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   }
   const dim3 grid_g2t((g2_t_chunks + kG2Warps - 1) / kG2Warps, std::max(ng, 1));
   if (ng > 0 && g2) {
+    cudaStream_t side = use_aux ? ctx->aux_stream : ctx->stream;
     spr_xT_kernel<<<dim3((group_L + 255) / 256, ng), 256, 0, ctx->stream>>>(b->dev, b->d_groups);
-    spr_g2_consts_kernel<<<ng, kGroup, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
-    spr_g2_templ_kernel<<<dim3((g2_t_chunks * 32 + 255) / 256, ng), 256, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    spr_g2_consts_kernel<<<ng, kGroup, 0, side>>>(fo->h, b->dev, b->d_groups);
+    spr_g2_templ_kernel<<<dim3((g2_t_chunks * 32 + 255) / 256, ng), 256, 0, side>>>(fo->h, b->dev, b->d_groups);
     launched += 2;
+    spr_g2_count_kernel<<<dim3((g2_t_chunks + kCountWarps * kCountPerWarp - 1) / (kCountWarps * kCountPerWarp), ng), kCountWarps * 32, 0, side>>>(fo->h, b->dev, b->d_groups);
     spr_g2_scan_kernel<<<dim3((g2_ev_chunks + kG2Warps - 1) / kG2Warps, ng), kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
-    spr_g2_count_kernel<<<dim3((g2_t_chunks + kCountWarps * kCountPerWarp - 1) / (kCountWarps * kCountPerWarp), ng), kCountWarps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    if (use_aux) { cudaEventRecord(ctx->ev_join, ctx->aux_stream); cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); }
     spr_g2_prefix_kernel<<<dim3(kPfxCtas, ng, 2), 1024, 0, ctx->stream>>>(b->dev, b->d_groups);
     launched += 4;
   }

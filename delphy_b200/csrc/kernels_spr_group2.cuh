@@ -475,7 +475,8 @@ __global__ void __launch_bounds__(kG2Warps * 32) spr_g2_emit_kernel(ForestDev f,
     s_wt[warp][lane] = w;
     fused_lane = o0.y != 0;
   }
-  if (st.c.tX == -DBL_MAX) mymask = 0u;
+  // (the constants were written on the side stream, before the X-table kernel could flag its study: look at the study itself)
+  if (st.c.tX == -DBL_MAX || (lane < G.num && B.studies[G.study[lane]].error)) mymask = 0u;
   // ---- the lane's template ---------------------------------------------------------------------------------------------------------------
   const int r = tc * 32 + lane;
   const bool valid = r < NT;
