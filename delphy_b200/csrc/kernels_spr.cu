@@ -811,9 +811,16 @@ __device__ void g_emit_node_general(const ForestDev& f, const SprStudy& S, const
 __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f, SprBatchDev B) {
   __shared__ int s_ws[kSetupThreads / 32];
   __shared__ int s_carry;
-  SprStudy& S = B.studies[blockIdx.x];
-  if (S.error || S.h_stride == 0) return;              // (h_stride 0: the study is walked by spr_frontier_kernel)
-  if (threadIdx.x == 0) S.mu = S.lambda_X / (double)(S.L - S.num_missing);   // Spr_study::mu, core/spr_study.cpp:239
+  // the study record, read once: every region evaluated below consults a dozen of its fields, and a reference into global memory
+  // would re-load each of them after every store
+  __shared__ SprStudy sS;
+  SprStudy& Sg = B.studies[blockIdx.x];
+  if (Sg.error || Sg.h_stride == 0) return;            // (h_stride 0: the study is walked by spr_frontier_kernel)
+  static_assert(sizeof(SprStudy) % sizeof(int) == 0, "SprStudy is copied word by word");
+  for (int i = threadIdx.x; i < (int)(sizeof(SprStudy) / sizeof(int)); i += kSetupThreads) reinterpret_cast<int*>(&sS)[i] = reinterpret_cast<const int*>(&Sg)[i];
+  __syncthreads();
+  const SprStudy& S = sS;
+  if (threadIdx.x == 0) { const double mu = S.lambda_X / (double)(S.L - S.num_missing); sS.mu = mu; Sg.mu = mu; }   // Spr_study::mu, core/spr_study.cpp:239
   // the path index of S and P (a ten-step search of dependent loads) is found now, by two threads of another warp, rather than at the
   // end of the kernel where it would sit on the critical path
   __shared__ int s_jsp[2];
@@ -832,12 +839,15 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
         const int mo = f.mut_off[S.pos0];
         for (int i = 0; i < S.k0; ++i) { int dh, dc; mut_dc(V0.xtab, f.mut_site[mo + i], f.mut_code[mo + i] & 15, dh, dc); h += dh; }
       }
-      S.C0 = 0; S.H0 = h; S.scanned = 3;
+      Sg.C0 = 0; Sg.H0 = h; Sg.scanned = 3;
+      sS.C0 = 0; sS.H0 = h; sS.scanned = 3;
       __threadfence_block();
     }
     __syncthreads();
   } else {
-    spr_tile_prefix(f, B, S, blockIdx.x, 3, s_ws, &s_carry);
+    spr_tile_prefix(f, B, Sg, blockIdx.x, 3, s_ws, &s_carry);
+    if (threadIdx.x == 0) { sS.C0 = Sg.C0; sS.H0 = Sg.H0; sS.scanned = Sg.scanned; }
+    __syncthreads();
   }
   const int tid = threadIdx.x;
   const SprView V = make_view(B, S, blockIdx.x);
@@ -893,7 +903,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
         GLane L;
         L.out = (RegionHead*)(B.slab + S.off_regions); L.pae = V.pae; L.seg = V.seg; L.agg = V.agg;
         L.region_cap = S.region_cap; L.path_len = S.path_len; L.H0 = S.H0; L.init_min_muts = S.init_min_muts; L.tX = S.t_X;
-        L.lw = (double*)(B.slab + S.off_lw); L.max_key = &S.max_key;
+        L.lw = (double*)(B.slab + S.off_lw); L.max_key = &Sg.max_key;
         g_emit_node_general(f, S, V, L, V.path[j], sg, j, true);
       }
     }
@@ -901,7 +911,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
     if (tid == 0) s_carry += btot;
     __syncthreads();
   }
-  if (tid == 0) S.total_regions = s_carry;
+  if (tid == 0) Sg.total_regions = s_carry;
   if (S.h_stride != 1 && tid < 2) {
     // ... and so are S and P when they are not on the path (their regions are relabelled by account_for_Xs_detachment)
     const int p = tid == 0 ? S.posS : S.posP;
@@ -911,7 +921,7 @@ __global__ void __launch_bounds__(kSetupThreads) spr_segments_kernel(ForestDev f
         GLane L;
         L.out = (RegionHead*)(B.slab + S.off_regions); L.pae = V.pae; L.seg = V.seg; L.agg = V.agg;
         L.region_cap = S.region_cap; L.path_len = S.path_len; L.H0 = S.H0; L.init_min_muts = S.init_min_muts; L.tX = S.t_X;
-        L.lw = (double*)(B.slab + S.off_lw); L.max_key = &S.max_key;
+        L.lw = (double*)(B.slab + S.off_lw); L.max_key = &Sg.max_key;
         g_emit_node_general(f, S, V, L, p, seg + (size_t)j * kSegStride, j, false);
       }
     }
@@ -1717,10 +1727,11 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     spr_g2_templ_kernel<<<dim3((g2_t_chunks * 32 + 255) / 256, ng), 256, 0, side>>>(fo->h, b->dev, b->d_groups);
     launched += 2;
     spr_g2_count_kernel<<<dim3((g2_t_chunks + kCountWarps * kCountPerWarp - 1) / (kCountWarps * kCountPerWarp), ng), kCountWarps * 32, 0, side>>>(fo->h, b->dev, b->d_groups);
+    spr_g2_prefix_kernel<<<dim3(kPfxCtas, ng), 1024, 0, side>>>(b->dev, b->d_groups, 1);
     spr_g2_scan_kernel<<<dim3((g2_ev_chunks + kG2Warps - 1) / kG2Warps, ng), kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
+    spr_g2_prefix_kernel<<<dim3(kPfxCtas, ng), 1024, 0, ctx->stream>>>(b->dev, b->d_groups, 0);
     if (use_aux) { cudaEventRecord(ctx->ev_join, ctx->aux_stream); cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); }
-    spr_g2_prefix_kernel<<<dim3(kPfxCtas, ng, 2), 1024, 0, ctx->stream>>>(b->dev, b->d_groups);
-    launched += 4;
+    launched += 5;
   }
   if (any_frontier) { spr_frontier_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
   if (any_swept_limited) {

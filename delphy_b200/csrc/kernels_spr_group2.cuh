@@ -123,17 +123,17 @@ __global__ void __launch_bounds__(kG2Warps * 32) spr_g2_scan_kernel(ForestDev f,
 // ---- exclusive prefixes over the chunk rows of a group: [rows][32] -> in place, totals in row [rows] ---------------------------------------
 // A thread-block cluster of 8 CTAs per (group, table): CTA r owns a contiguous eighth of the rows (warp w a 32nd of that), sums it,
 // publishes its column totals into the shared memory of every CTA of the cluster (distributed shared memory) and, after one cluster
-// barrier, rewrites its rows as exclusive prefixes.  grid = (8, groups, 2).
+// barrier, rewrites its rows as exclusive prefixes.  grid = (8, groups); one launch per table (the kept counts on the side stream).
 constexpr int kPfxCtas = 8;
-__global__ void __cluster_dims__(kPfxCtas, 1, 1) __launch_bounds__(1024) spr_g2_prefix_kernel(SprBatchDev B, const SprGroupDev* __restrict__ groups) {
+__global__ void __cluster_dims__(kPfxCtas, 1, 1) __launch_bounds__(1024) spr_g2_prefix_kernel(SprBatchDev B, const SprGroupDev* __restrict__ groups, int which) {
   __shared__ int s_w[32][33];                 // per-warp column sums of this CTA
   __shared__ int s_cta[kPfxCtas][32];         // column totals of every CTA of the cluster
   namespace cgx = cooperative_groups;
   cgx::cluster_group cluster = cgx::this_cluster();
   const int rank = (int)cluster.block_rank();
   const SprGroupDev& G = groups[blockIdx.y];
-  const int rows = blockIdx.z == 0 ? G.num_ev_chunks : G.num_t_chunks + 1;
-  int32_t* a = (int32_t*)(B.slab + (blockIdx.z == 0 ? G.off_aggS : G.off_aggK));
+  const int rows = which == 0 ? G.num_ev_chunks : G.num_t_chunks + 1;      // which: 0 = event-chunk totals, 1 = kept counts
+  int32_t* a = (int32_t*)(B.slab + (which == 0 ? G.off_aggS : G.off_aggK));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (rows + kPfxCtas * 32 - 1) / (kPfxCtas * 32);
   const int r0 = min((rank * 32 + warp) * per, rows), r1 = min(r0 + per, rows);
