@@ -135,6 +135,10 @@ void dphy_ctx_destroy(dphy_ctx* ctx) {
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  for (int i = 0; i < dphy_ctx::kTallyStreams; ++i) {
+    if (ctx->tally_streams[i]) { cudaStreamSynchronize(ctx->tally_streams[i]); cudaStreamDestroy(ctx->tally_streams[i]); }
+    if (ctx->ev_tally[i]) cudaEventDestroy(ctx->ev_tally[i]);
+  }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->pinned_ev) cudaEventDestroy(ctx->pinned_ev);

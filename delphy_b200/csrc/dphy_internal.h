@@ -200,6 +200,10 @@ struct dphy_ctx {
   // chain of the main stream (fork after spr_init_kernel, join before the prefix kernel)
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // side streams of the per-site tallies of a whole forest: the trees' (small) kernel sequences run side by side
+  static constexpr int kTallyStreams = 4;
+  cudaStream_t tally_streams[kTallyStreams] = {};
+  cudaEvent_t ev_tally[kTallyStreams] = {};
   struct DeferredCopy { void* dst; const void* src; size_t bytes; };
   std::vector<DeferredCopy> deferred_d2h;   // device->host copies of a batched getter, issued once all its kernels are enqueued
   bool logg_attr_set = false;   // opt-in dynamic shared memory of the log-G tile kernel

@@ -460,18 +460,46 @@ int dphy_forest_calc_site_tallies(dphy_ctx* ctx, dphy_forest* fo, int64_t ld, do
     ctx->arena.release(mark);
     return r != DPHY_OK ? r : r2;
   };
-  // every tree's kernels are enqueued back to back; one synchronization per arena-full of trees
+  // Every tree's kernels are enqueued back to back, tree k on side stream k % 4: a tree's sequence is a branch-length scan, an
+  // atomics-bound scatter and a one-CTA per-site finalize, none of which fills the GPU, so four trees run side by side (fork after
+  // what the main stream holds so far, join before the results are copied back).  One synchronization per arena-full of trees.
+  constexpr int kS = dphy_ctx::kTallyStreams;
+  cudaStream_t main_stream = ctx->stream;
+  bool forked = false;
+  if (fo->h.num_trees > 1) {
+    bool ok = true;
+    for (int i = 0; i < kS && ok; ++i) {
+      if (!ctx->tally_streams[i]) ok = cudaStreamCreateWithFlags(&ctx->tally_streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+                                       cudaEventCreateWithFlags(&ctx->ev_tally[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (ok && !ctx->ev_fork) ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) {
+      st = refresh_sites(ctx, fo);                      // (on the main stream, before the fork; the per-tree calls then find it done)
+      cudaEventRecord(ctx->ev_fork, main_stream);
+      for (int i = 0; i < kS; ++i) cudaStreamWaitEvent(ctx->tally_streams[i], ctx->ev_fork, 0);
+      forked = true;
+    } else cudaGetLastError();
+  }
+  auto join = [&]() {
+    if (!forked) return;
+    for (int i = 0; i < kS; ++i) { cudaEventRecord(ctx->ev_tally[i], ctx->tally_streams[i]); cudaStreamWaitEvent(main_stream, ctx->ev_tally[i], 0); }
+  };
   for (int k = 0; k < fo->h.num_trees && st == DPHY_OK; ++k) {
     for (int attempt = 0; attempt < 2; ++attempt) {
       st = DPHY_OK;
+      if (forked) ctx->stream = ctx->tally_streams[k % kS];        // the per-tree launchers enqueue on ctx->stream
       if (out_Ttwiddle_l) st = tally_times(ctx, fo, k, nullptr, out_Ttwiddle_l + (size_t)k * ld, nullptr, true);
       if (st == DPHY_OK && out_num_muts_l) st = tally_num_muts(ctx, fo, k, nullptr, out_num_muts_l + (size_t)k * ld, nullptr, true);
+      ctx->stream = main_stream;
       if (st != DPHY_ERR_OUT_OF_MEMORY || attempt == 1) break;
       // arena full: drain what is in flight, reopen the scope, retry this tree once
+      join();
       st = drain();
       if (st != DPHY_OK) break;
+      if (forked) { cudaEventRecord(ctx->ev_fork, main_stream); for (int i = 0; i < kS; ++i) cudaStreamWaitEvent(ctx->tally_streams[i], ctx->ev_fork, 0); }
     }
   }
+  join();
   const int st2 = drain();
   return st != DPHY_OK ? st : st2;
 }
