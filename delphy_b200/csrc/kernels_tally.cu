@@ -255,10 +255,14 @@ static int scan_branch_lengths(dphy_ctx* ctx, dphy_forest* fo, int tree, double*
   double* PL = (double*)ctx->arena.alloc(sizeof(double) * T.num_nodes);
   // own scan workspace: d_tile_agg holds the log-G tile prefixes that the lambda_i getter still needs
   double* agg = (double*)ctx->arena.alloc(sizeof(double) * T.num_tiles);
-  if (!PL || !agg) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (tally PL)");
+  // ... and its own tile ticket: the trees of a forest are scanned side by side on several streams (dphy_forest_calc_site_tallies),
+  // and a ticket shared by two running scans would hand one tree's tiles to the other -- its CTAs would wait for ever
+  uint32_t* ticket = (uint32_t*)ctx->arena.alloc(sizeof(uint32_t));
+  if (!PL || !agg || !ticket) return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (tally PL)");
+  DPHY_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), ctx->stream));
   fo->epoch += 1; if (fo->epoch == 0) fo->epoch = 1;
   tally_branch_len_scan_kernel<<<T.num_tiles, kTile, 0, ctx->stream>>>(fo->h, tree, PL, agg,
-                                                                       fo->d_tile_flag + T.first_tile, fo->d_ticket + 2, fo->epoch);
+                                                                       fo->d_tile_flag + T.first_tile, ticket, fo->epoch);
   ctx->launches += 1;
   *PL_out = PL;
   return check_cuda(ctx, cudaGetLastError(), "tally_branch_len_scan_kernel");
