@@ -280,7 +280,12 @@ def mcmc_figures(db, args, which, n_gpus):
             if which == "dropin":
                 env["CUDA_VISIBLE_DEVICES"] = i
             res[i] = mcmc.run_cli(binary, path, steps, threads=1, seed=20251017 + 1 + i, log_every=max(1, steps // 10), env=env, timeout=900)
-        ths = [threading.Thread(target=one, args=(i,)) for i in range(n_gpus)]
+        def guarded(i):
+            try:
+                one(i)
+            except Exception as ex:          # a failed side figure must not cost the whole line
+                res[i] = {"returncode": -1, "steps_per_s": None, "error": repr(ex)[:200]}
+        ths = [threading.Thread(target=guarded, args=(i,)) for i in range(n_gpus)]
         for t in ths:
             t.start()
         for t in ths:
