@@ -227,6 +227,28 @@ def test_grouped_studies_on_several_trees_of_a_forest(ctx, orc):
         t.close()
 
 
+@pytest.mark.parametrize("limit", [2, 3])
+def test_bounded_studies_in_a_large_batch(ctx, orc, limit):
+    """Radius-2 / 3 studies take the ball walk (kernels_spr_frontier.cuh) only in batches of 256 or more (a walk lasts as long as the
+    largest ball of the batch): 300 of them on one tree, root children and both can_change_root settings included, against the
+    reference's builder region by region."""
+    emat, sites, info = synth(1, seed=77, num_root_mutations=3)
+    e, s = to_oracle(emat, sites)
+    ds = db.DeviceSites(ctx, sites)
+    fo = db.Forest(ctx, [emat], [ds])
+    lam = fo.lambda_i(0)
+    xs = [int(v) for v in np.random.default_rng(5).permutation(emat.num_nodes) if v != emat.root][:298]
+    xs += [int(emat.child0[emat.root]), int(emat.child1[emat.root])]
+    for ccr in (True, False):
+        reqs = db.spr_requests_for_attached(emat, 0, xs, lam, info["t_max_tip"], limit, ccr)
+        batch = fo.spr_study_batch(reqs)
+        for i, X in enumerate(xs):
+            want, _ = orc.spr_study_from_attached(e, s, X, lam, limit, ccr, 0.8, info["t_max_tip"])
+            _cmp_regions(batch.regions(i), want)
+        batch.close()
+    fo.close(); ds.close()
+
+
 def _state_at_region(emat, sites, branch, k):
     """Sequence at region (branch, k): the reference overlaid with the mutations from the root down to the k-th of `branch`."""
     path = []
