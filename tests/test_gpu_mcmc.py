@@ -74,8 +74,8 @@ def test_usher_like_initial_tree_through_the_drop_in(tmp_path):
     (X == k_no_node) per tip, over the tree built so far -- every one of them on the device in the substituted build, each re-run
     by the reference's builder (DPHY_DROPIN_VERIFY).  The resulting initial trees must coincide with the stock build's."""
     _need_binaries()
-    emat, sites, info = db.synth_generate(db.synth_params(3, num_tips=600))
-    path = str(tmp_path / "t600.maple")
+    emat, sites, info = db.synth_generate(db.synth_params(3, num_tips=1200))
+    path = str(tmp_path / "t1200.maple")
     write_maple(emat, sites, path, info["t_max_tip"])
     args = ["--v0-init", "old-usher-like"]
     a = mcmc.run_cli(mcmc.DROPIN_CLI, path, 2000, threads=1, seed=9, log_every=1000, extra_args=args, env=dict(DPHY_DROPIN_VERIFY=1), timeout=900)
