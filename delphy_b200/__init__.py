@@ -119,6 +119,35 @@ class Tallies(C.Structure):
     ]
 
 
+class ApiTreeView(C.Structure):
+    """dphy_api_tree_view: where the vectors of a delphy.api.Tree buffer (core/api.fbs:13-49) lie."""
+    _fields_ = [("num_nodes", C.c_int32), ("root", C.c_int32), ("num_sites", C.c_int32), ("reserved", C.c_int32),
+                ("num_mutations", C.c_int64), ("num_missation_intervals", C.c_int64),
+                ("nodes", C.c_void_p), ("mutations", C.c_void_p), ("missation_intervals", C.c_void_p), ("ref_seq", C.c_void_p)]
+
+
+class TreeCounts(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("root", C.c_int32), ("num_mutations", C.c_int64),
+                ("num_missation_intervals", C.c_int64), ("num_from_states", C.c_int64)]
+
+
+def api_tree_parse(data: bytes) -> dict:
+    """dphy_api_tree_parse (host only): the sizes, the root and the reference sequence of a delphy.api.Tree buffer."""
+    buf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data if len(data) else b"\0")
+    v = ApiTreeView()
+    st = lib().dphy_api_tree_parse(buf, len(data), C.byref(v))
+    if st != DPHY_OK:
+        raise DphyError(st, "malformed delphy.api.Tree buffer")
+    ref = np.ctypeslib.as_array(C.cast(v.ref_seq, u8p), shape=(max(v.num_sites, 1),))[:v.num_sites].copy() if v.num_sites else np.zeros(0, np.uint8)
+    return dict(num_nodes=v.num_nodes, root=v.root, num_sites=v.num_sites, num_mutations=int(v.num_mutations),
+                num_missation_intervals=int(v.num_missation_intervals), ref_seq=ref)
+
+
+class _ApiTreeShape:
+    def __init__(self, num_nodes):
+        self.num_nodes = num_nodes
+
+
 class SynthParams(C.Structure):
     _fields_ = [
         ("num_tips", C.c_int32), ("num_sites", C.c_int32), ("seed", C.c_uint64),
@@ -240,6 +269,11 @@ def lib() -> C.CDLL:
     L.dphy_gamma_q_inv.argtypes = [vp, C.c_int32, f64p, f64p, f64p]
     L.dphy_spr_batch_pick_nexus_regions.argtypes = [vp, vp, f64p, i32p]
     L.dphy_spr_batch_find_region.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_double, i32p]
+    L.dphy_api_tree_parse.argtypes = [vp, C.c_size_t, C.POINTER(ApiTreeView)]
+    L.dphy_forest_upload_api_trees.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t), i32p, i32p, C.c_int32, C.POINTER(vp), C.c_uint32, C.POINTER(vp)]
+    L.dphy_forest_write_api_tree.argtypes = [vp, vp, C.c_int32, vp, C.c_size_t]; L.dphy_forest_write_api_tree.restype = C.c_int64
+    L.dphy_forest_tree_counts.argtypes = [vp, vp, C.c_int32, C.POINTER(TreeCounts)]
+    L.dphy_forest_download_tree.argtypes = [vp, vp, C.c_int32, C.POINTER(EmatHost)]
     _bind_partition(L)
     _LIB = L
     return L
@@ -578,6 +612,52 @@ class Forest:
         sp = (C.c_void_p * len(self.sites_tables))(*[s._h for s in self.sites_tables])
         self._h = C.c_void_p()
         ctx.check(lib().dphy_forest_upload(ctx._h, n, arr, _p(idx, i32p), len(self.sites_tables), sp, C.byref(self._h)))
+
+    @classmethod
+    def from_api_trees(cls, ctx: "Context", buffers, sites_tables, sites_index=None, includes_run_root=None, check_paths=False) -> "Forest":
+        """dphy_forest_upload_api_trees: delphy.api.Tree buffers (core/api.fbs) straight to the device (check_paths:
+        DPHY_API_TREE_CHECK_PATHS, the O(nodes x depth) half of the normal-form check)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.emats = [_ApiTreeShape(api_tree_parse(b)["num_nodes"]) for b in buffers]
+        self.sites_tables = list(sites_tables)
+        n = len(buffers)
+        keep = [(C.c_uint8 * len(b)).from_buffer_copy(b) for b in buffers]
+        bp = (C.c_void_p * n)(*[C.addressof(k) for k in keep])
+        lens = (C.c_size_t * n)(*[len(b) for b in buffers])
+        idx = np.ascontiguousarray(sites_index if sites_index is not None else np.zeros(n), np.int32)
+        self.sites_index = idx
+        irr = None if includes_run_root is None else np.ascontiguousarray(includes_run_root, np.int32)
+        sp = (C.c_void_p * len(self.sites_tables))(*[s._h for s in self.sites_tables])
+        self._h = C.c_void_p()
+        ctx.check(lib().dphy_forest_upload_api_trees(ctx._h, n, bp, lens, None if irr is None else _p(irr, i32p), _p(idx, i32p),
+                                                     len(self.sites_tables), sp, 1 if check_paths else 0, C.byref(self._h)))
+        return self
+
+    def write_api_tree(self, tree=0) -> bytes:
+        """dphy_forest_write_api_tree: phylo_tree_to_api_tree (core/api.cpp:34-98) of a resident tree."""
+        n = int(lib().dphy_forest_write_api_tree(self.ctx._h, self._h, tree, None, 0))
+        if n < 0:
+            self.ctx.check(n)
+        buf = bytearray(n)
+        got = int(lib().dphy_forest_write_api_tree(self.ctx._h, self._h, tree, (C.c_uint8 * n).from_buffer(buf), n))
+        if got < 0:
+            self.ctx.check(got)
+        return bytes(memoryview(buf)[:got])
+
+    def download_tree(self, tree=0) -> "HostEmat":
+        """dphy_forest_download_tree: the host-order arrays of a tree as they are resident on the device."""
+        c = TreeCounts()
+        self.ctx.check(lib().dphy_forest_tree_counts(self.ctx._h, self._h, tree, C.byref(c)))
+        N, M, I, F = c.num_nodes, int(c.num_mutations), int(c.num_missation_intervals), int(c.num_from_states)
+        e = HostEmat(c.root, 1, parent=np.zeros(N, np.int32), child0=np.zeros(N, np.int32), child1=np.zeros(N, np.int32), t=np.zeros(N, np.float64),
+                     mut_off=np.zeros(N + 1, np.int32), mut_site=np.zeros(M, np.int32), mut_from=np.zeros(M, np.uint8), mut_to=np.zeros(M, np.uint8),
+                     mut_t=np.zeros(M, np.float64), miss_off=np.zeros(N + 1, np.int32), miss_start=np.zeros(I, np.int32), miss_end=np.zeros(I, np.int32),
+                     fs_off=np.zeros(N + 1, np.int32), fs_site=np.zeros(F, np.int32), fs_from=np.zeros(F, np.uint8))
+        st = e.as_struct()
+        self.ctx.check(lib().dphy_forest_download_tree(self.ctx._h, self._h, tree, C.byref(st)))
+        e.root = st.root; e.includes_run_root = st.includes_run_root
+        return e
 
     @property
     def num_trees(self):

@@ -887,6 +887,12 @@ int dphy_forest_upload(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* t
 
 }  // extern "C"
 
+// A new forest from host-order arrays that already lie on the device (dphy_forest_upload_api_trees): the upload path with device sources.
+int dphy::forest_from_device_arrays(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* views, const TreeTotals* totals, const int32_t* sites_index,
+                                    int32_t num_sites_tables, dphy_sites* const* sites, dphy_forest** out) {
+  return forest_upload_impl(ctx, num_trees, views, totals, sites_index, num_sites_tables, sites, out);
+}
+
 // Re-flatten `fo` from device-resident host-order arrays (dphy_forest_apply_rows): a fresh forest is built by the upload path with
 // device sources, then swapped into the caller's handle; the old contents are released stream-ordered.  On failure `fo` is untouched.
 int dphy::rebuild_forest_from_device(dphy_ctx* ctx, dphy_forest* fo, const dphy_emat_host* trees, const TreeTotals* totals, bool same_links) {

@@ -272,6 +272,8 @@ struct dphy_forest {
 namespace dphy {
 // List totals of one tree whose arrays are NOT host-readable (device-resident sources of dphy_forest_apply_rows).
 struct TreeTotals { int64_t m, iv, fs, root_m; };
+int forest_from_device_arrays(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_host* views, const TreeTotals* totals, const int32_t* sites_index,
+                              int32_t num_sites_tables, dphy_sites* const* sites, dphy_forest** out);   // c_abi.cu
 int rebuild_forest_from_device(dphy_ctx* ctx, dphy_forest* fo, const dphy_emat_host* trees, const TreeTotals* totals, bool same_links);   // c_abi.cu
 int launch_raw_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int tree, const int32_t* d_nodes, const double* d_vals, int count);   // kernels_delta.cu
 int set_error(dphy_ctx* ctx, int status, const std::string& msg);

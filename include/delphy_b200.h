@@ -235,6 +235,51 @@ typedef struct dphy_node_row {
  * refer to the old forest and must be destroyed first. */
 int  dphy_forest_apply_rows(dphy_ctx* ctx, dphy_forest* forest, int32_t count, const dphy_node_row* rows, const int32_t* new_roots);
 
+/* ---- the reference's wire / on-disk tree format, straight to and from the device ------------------------
+ * delphy.api.Tree (core/api.fbs:13-49): the size-prefixed FlatBuffers buffer phylo_tree_to_api_tree writes (core/api.cpp:34-98) --
+ * `.dphy` files (core/delphy_output.cpp:111-121) and the WASM API (tools/delphy_wasm.cpp:500-534) carry it. */
+typedef struct dphy_api_tree_view {
+  int32_t num_nodes, root, num_sites, reserved;
+  int64_t num_mutations, num_missation_intervals;
+  const void* nodes;                  /* num_nodes x 16 B  {parent i32, left_child i32, right_child i32, t f32}            (core/api_generated.h:157-190) */
+  const void* mutations;              /* 16 B each         {branch i32, site i32, from u8, to u8, 2 B padding, t f32}     (:192-236) */
+  const void* missation_intervals;    /* 12 B each         {branch i32, start_site i32, end_site i32}                    (:238-265) */
+  const uint8_t* ref_seq;             /* num_sites letters A=0 C=1 G=2 T=3 */
+} dphy_api_tree_view;
+/* Host only: GetSizePrefixedRoot<api::Tree> + the field accessors (core/api_generated.h:267-304) with every offset bounds-checked (the
+ * buffer is untrusted).  The view points into `buf`.  DPHY_ERR_INVALID_ARGUMENT for a malformed buffer. */
+int  dphy_api_tree_parse(const void* buf, size_t len, dphy_api_tree_view* out);
+/* api_tree_and_tree_info_to_phylo_tree (core/api.cpp:127-186) + the flattening of dphy_forest_upload, without the AoS Phylo_tree in
+ * between: the struct vectors of every buffer are DMA'd as they lie; the struct-of-arrays split, the CSR offsets and the
+ * Missation_map::from_states (which the format does not store; fix_up_missations, core/phylo_tree.cpp:446-459) are computed on the
+ * device.  Tree k is loaded against sites[sites_index[k]], whose reference sequence must equal the buffer's ref_seq;
+ * includes_run_root may be NULL (all 1).  Times are the format's float32 values widened to double, as in the reference.  The result is
+ * the forest dphy_forest_upload would build from the reference's reloaded Phylo_tree.
+ * Precondition, true of every buffer phylo_tree_to_api_tree wrote: fix_up_missations has nothing to rewrite beyond the from_states.
+ * Always checked (DPHY_ERR_INVALID_ARGUMENT): records grouped by ascending branch, a branch's intervals ascending and apart; the
+ * two children of a node share no missing site; no mutation on a site missing at its own node; every mutation's `from` equals the
+ * state of the sequence above it (the reference CHECKs); plus everything dphy_forest_upload validates.  With
+ * flags & DPHY_API_TREE_CHECK_PATHS also the half that needs every root path walked (O(nodes x depth)): no site missing at a node and
+ * again at an ancestor, no mutation on a site missing at an ancestor. */
+#define DPHY_API_TREE_CHECK_PATHS 1u
+int  dphy_forest_upload_api_trees(dphy_ctx* ctx, int32_t num_trees, const void* const* bufs, const size_t* lens,
+                                  const int32_t* includes_run_root, const int32_t* sites_index, int32_t num_sites_tables,
+                                  dphy_sites* const* sites, uint32_t flags, dphy_forest** out);
+/* phylo_tree_to_api_tree (core/api.cpp:34-98) of tree `tree` as it is resident on the device (edits applied by dphy_forest_apply_rows
+ * included): the three struct vectors are packed on the device, the host adds the table header.  Returns the buffer length (out ==
+ * NULL: size query) or a negative dphy_status.  Same content as the reference's writer; FlatBuffers readers follow offsets, so
+ * the vectors' placement inside the buffer (ours: header first) is not part of the format. */
+int64_t dphy_forest_write_api_tree(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, void* out, size_t cap);
+/* The host-order arrays of one tree as they are resident on the device (the inverse of dphy_forest_upload).  dphy_forest_tree_counts
+ * gives the sizes; dphy_forest_download_tree WRITES through the array pointers of `out`, which the caller has pointed at buffers of
+ * those sizes (parent / child0 / child1 / t: num_nodes; *_off: num_nodes + 1; lists: their totals), and fills the scalars. */
+typedef struct dphy_tree_counts {
+  int32_t num_nodes, root;
+  int64_t num_mutations, num_missation_intervals, num_from_states;
+} dphy_tree_counts;
+int  dphy_forest_tree_counts(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, dphy_tree_counts* out);
+int  dphy_forest_download_tree(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, dphy_emat_host* out);
+
 /* ---- log G ------------------------------------------------------------------------------------------- */
 /* One launch evaluates, for EVERY tree of the forest: calc_lambda_i (core/phylo_tree_calc.cpp:420-436),
  * calc_num_sites_missing_at_every_node (:67-76), calc_log_root_prior (:467-504) and calc_log_G_below_root

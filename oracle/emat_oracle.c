@@ -747,4 +747,217 @@ int32_t orc_spr_study_from_attached(const orc_emat* e, const orc_sites* s, int32
   return n;
 }
 
+/* ---- delphy.api.Tree: the FlatBuffers wire format (core/api.fbs:13-49) ------------------------------------------------------------- */
+static uint32_t rd_u32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint16_t rd_u16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+static int32_t rd_i32(const uint8_t* p) { return (int32_t)rd_u32(p); }
+static float rd_f32(const uint8_t* p) { uint32_t u = rd_u32(p); float f; memcpy(&f, &u, 4); return f; }
+static void wr_u32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+static void wr_u16(uint8_t* p, uint16_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+
+/* one vector field of the table at `tpos`: vtable slot `slot` (4 = nodes, 6 = mutations, ...: core/api_generated.h:269-275) */
+static int api_vector(const uint8_t* buf, int64_t len, int64_t tpos, int64_t vt, int vtsize, int slot, int64_t elem, const uint8_t** data, int64_t* count) {
+  *data = NULL; *count = 0;
+  if (slot + 2 > vtsize) return 0;                       /* field absent: an empty vector */
+  int fo = rd_u16(buf + vt + slot);
+  if (fo == 0) return 0;
+  int64_t fpos = tpos + fo;
+  if (fpos + 4 > len) return -1;
+  int64_t vpos = fpos + (int64_t)rd_u32(buf + fpos);
+  if (vpos + 4 > len) return -1;
+  int64_t n = (int64_t)rd_u32(buf + vpos);
+  if (vpos + 4 + n * elem > len) return -1;
+  *data = buf + vpos + 4; *count = n;
+  return 0;
+}
+
+int32_t orc_api_tree_parse(const uint8_t* buf, int64_t len, orc_api_tree_view* out) {
+  memset(out, 0, sizeof(*out));
+  if (len < 12) return -1;
+  int64_t body = (int64_t)rd_u32(buf);                   /* FinishSizePrefixed (core/api.cpp:95) */
+  if (body + 4 > len) return -1;
+  len = body + 4;
+  int64_t tpos = 4 + (int64_t)rd_u32(buf + 4);
+  if (tpos + 4 > len || tpos < 8) return -1;
+  int64_t vt = tpos - (int64_t)rd_i32(buf + tpos);
+  if (vt < 4 || vt + 4 > len) return -1;
+  int vtsize = rd_u16(buf + vt);
+  if (vtsize < 4 || (vtsize & 1) || vt + vtsize > len) return -1;
+  int tsize = rd_u16(buf + vt + 2);
+  if (tpos + tsize > len) return -1;
+  for (int slot = 4; slot + 2 <= vtsize; slot += 2) if (rd_u16(buf + vt + slot) + 4 > tsize && rd_u16(buf + vt + slot) != 0) return -1;
+  int64_t n = 0, L = 0;
+  if (api_vector(buf, len, tpos, vt, vtsize, 4, 16, &out->nodes, &n) != 0) return -1;
+  if (api_vector(buf, len, tpos, vt, vtsize, 6, 16, &out->muts, &out->num_muts) != 0) return -1;
+  if (api_vector(buf, len, tpos, vt, vtsize, 8, 12, &out->ivls, &out->num_ivls) != 0) return -1;
+  if (api_vector(buf, len, tpos, vt, vtsize, 10, 1, &out->ref_seq, &L) != 0) return -1;
+  if (n > INT32_MAX || L > INT32_MAX || out->num_muts > INT32_MAX || out->num_ivls > INT32_MAX) return -1;
+  out->num_nodes = (int32_t)n; out->num_sites = (int32_t)L;
+  out->root = (12 + 2 <= vtsize && rd_u16(buf + vt + 12) != 0) ? rd_i32(buf + tpos + rd_u16(buf + vt + 12)) : 0;   /* default 0 (:289) */
+  return 0;
+}
+
+int32_t orc_api_tree_to_emat(const orc_api_tree_view* v, int32_t* counts, int32_t* parent, int32_t* child0, int32_t* child1, double* t,
+                             int32_t* mut_off, int32_t* mut_site, uint8_t* mut_from, uint8_t* mut_to, double* mut_t,
+                             int32_t* miss_off, int32_t* miss_start, int32_t* miss_end,
+                             int32_t* fs_off, int32_t* fs_site, uint8_t* fs_from) {
+  const int n = v->num_nodes, L = v->num_sites;
+  const int64_t M = v->num_muts, I = v->num_ivls;
+  if (n <= 0 || v->root < 0 || v->root >= n) return -1;
+  for (int l = 0; l != L; ++l) if (v->ref_seq[l] > 3) return -1;                                  /* to_real_seq_letter throws (core/api.cpp:14-22) */
+  /* the lists by branch (core/api.cpp:165-180 appends each record to its branch in file order; the writer emits them branch-major) */
+  int32_t* moff = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t));
+  int32_t* ioff = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t));
+  int32_t* morder = (int32_t*)malloc(sizeof(int32_t) * (size_t)(M > 0 ? M : 1));
+  int32_t* iorder = (int32_t*)malloc(sizeof(int32_t) * (size_t)(I > 0 ? I : 1));
+  int32_t* foff = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t));
+  uint8_t* cur = (uint8_t*)malloc((size_t)(L > 0 ? L : 1));
+  int32_t* nmiss = (int32_t*)calloc((size_t)(L > 0 ? L : 1), sizeof(int32_t));
+  int32_t* stack = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)n);
+  int32_t rc = 0;
+  for (int64_t i = 0; i != M && rc == 0; ++i) {
+    const uint8_t* r = v->muts + 16 * i;
+    int b = rd_i32(r), l = rd_i32(r + 4);
+    if (b < 0 || b >= n || l < 0 || l >= L || r[8] > 3 || r[9] > 3) rc = -1; else ++moff[b + 1];
+  }
+  for (int64_t i = 0; i != I && rc == 0; ++i) {
+    const uint8_t* r = v->ivls + 12 * i;
+    int b = rd_i32(r), s = rd_i32(r + 4), e = rd_i32(r + 8);
+    if (b < 0 || b >= n || s < 0 || e > L || s >= e) rc = -1; else ++ioff[b + 1];
+  }
+  for (int x = 0; x != n && rc == 0; ++x) {
+    const uint8_t* r = v->nodes + 16 * (size_t)x;
+    int p = rd_i32(r), c0 = rd_i32(r + 4), c1 = rd_i32(r + 8);
+    if (p < -1 || p >= n || c0 < -1 || c0 >= n || c1 < -1 || c1 >= n || ((c0 < 0) != (c1 < 0))) rc = -1;
+  }
+  if (rc == 0) {
+    for (int x = 0; x != n; ++x) { moff[x + 1] += moff[x]; ioff[x + 1] += ioff[x]; }
+    int32_t* fill = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    memcpy(fill, moff, sizeof(int32_t) * (size_t)n);
+    for (int64_t i = 0; i != M; ++i) morder[fill[rd_i32(v->muts + 16 * i)]++] = (int32_t)i;
+    memcpy(fill, ioff, sizeof(int32_t) * (size_t)n);
+    for (int64_t i = 0; i != I; ++i) iorder[fill[rd_i32(v->ivls + 12 * i)]++] = (int32_t)i;
+    free(fill);
+    /* Interval_set::insert keeps a branch's intervals sorted and merged; a normal-form buffer already has them so */
+    for (int x = 0; x != n && rc == 0; ++x)
+      for (int k = ioff[x] + 1; k < ioff[x + 1]; ++k)
+        if (rd_i32(v->ivls + 12 * (size_t)iorder[k] + 4) <= rd_i32(v->ivls + 12 * (size_t)iorder[k - 1] + 8)) rc = -2;
+  }
+  /* pass 1 of fix_up_missations (core/phylo_tree.cpp:383-398) must find nothing to bubble up: the children of an inner node share no missing site */
+  for (int x = 0; x != n && rc == 0; ++x) {
+    int c0 = rd_i32(v->nodes + 16 * (size_t)x + 4), c1 = rd_i32(v->nodes + 16 * (size_t)x + 8);
+    if (c0 < 0) continue;
+    int a = ioff[c0], b = ioff[c1];
+    while (a < ioff[c0 + 1] && b < ioff[c1 + 1]) {
+      int as = rd_i32(v->ivls + 12 * (size_t)iorder[a] + 4), ae = rd_i32(v->ivls + 12 * (size_t)iorder[a] + 8);
+      int bs = rd_i32(v->ivls + 12 * (size_t)iorder[b] + 4), be = rd_i32(v->ivls + 12 * (size_t)iorder[b] + 8);
+      if (as < be && bs < ae) { rc = -2; break; }
+      if (ae <= be) ++a; else ++b;
+    }
+  }
+  /* passes 2 and 3 (core/phylo_tree.cpp:400-478): a traversal carrying the current sequence and the set of missing sites */
+  int F = 0;
+  for (int pass = 0; pass != 2 && rc == 0; ++pass) {
+    if (pass == 1 && !parent) break;
+    if (L > 0) memcpy(cur, v->ref_seq, (size_t)L);
+    int sp = 0, f = 0;
+    stack[sp++] = v->root; stack[sp++] = 0;
+    int visited = 0;
+    while (sp > 0 && rc == 0) {
+      int state = stack[--sp], x = stack[--sp];
+      int c0 = rd_i32(v->nodes + 16 * (size_t)x + 4), c1 = rd_i32(v->nodes + 16 * (size_t)x + 8);
+      if (state == 0) {
+        if (++visited > n) { rc = -1; break; }
+        if (x != v->root && rd_i32(v->nodes + 16 * (size_t)x) < 0) { rc = -1; break; }
+        /* entering x: from_states = the sites of its missations whose current state is not the reference's (:451-458) */
+        const int f_in = f;
+        int w = foff[x];                                                               /* (pass 1) where this node's overrides go: CSR by node index */
+        for (int k = ioff[x]; k != ioff[x + 1] && rc == 0; ++k) {
+          const uint8_t* r = v->ivls + 12 * (size_t)iorder[k];
+          for (int l = rd_i32(r + 4); l != rd_i32(r + 8); ++l) {
+            if (nmiss[l]++ != 0) { rc = -2; break; }                                   /* pass 2 would rewrite this node's missations (:412-426) */
+            if (cur[l] != v->ref_seq[l]) { if (pass == 1) { fs_site[w] = l; fs_from[w] = cur[l]; ++w; } ++f; }
+          }
+        }
+        if (pass == 0) foff[x + 1] = f - f_in;
+        for (int k = moff[x]; k != moff[x + 1] && rc == 0; ++k) {
+          const uint8_t* r = v->muts + 16 * (size_t)morder[k];
+          int l = rd_i32(r + 4);
+          if (nmiss[l] != 0) { rc = -2; break; }                                      /* :461 would erase it */
+          if (r[8] != cur[l]) { rc = -3; break; }                                     /* CHECK_EQ(m.from, cur_seq[m.site]) (:465) */
+          cur[l] = r[9];
+        }
+        stack[sp++] = x; stack[sp++] = 1;
+        if (c0 >= 0) { stack[sp++] = c1; stack[sp++] = 0; stack[sp++] = c0; stack[sp++] = 0; }
+      } else {
+        for (int k = moff[x + 1] - 1; k >= moff[x]; --k) { const uint8_t* r = v->muts + 16 * (size_t)morder[k]; cur[rd_i32(r + 4)] = r[8]; }
+        for (int k = ioff[x]; k != ioff[x + 1]; ++k) {
+          const uint8_t* r = v->ivls + 12 * (size_t)iorder[k];
+          for (int l = rd_i32(r + 4); l != rd_i32(r + 8); ++l) --nmiss[l];
+        }
+      }
+    }
+    if (rc == 0 && visited != n) rc = -1;
+    if (pass == 0) { F = f; for (int x = 0; x != n; ++x) foff[x + 1] += foff[x]; }
+    else memcpy(fs_off, foff, sizeof(int32_t) * ((size_t)n + 1));
+    /* an aborted traversal leaves marks behind; the arrays are only reused after a clean pass 0 */
+  }
+  counts[0] = n; counts[1] = v->root; counts[2] = (int32_t)M; counts[3] = (int32_t)I; counts[4] = F;
+  if (rc == 0 && parent) {
+    for (int x = 0; x != n; ++x) {
+      const uint8_t* r = v->nodes + 16 * (size_t)x;
+      parent[x] = rd_i32(r); child0[x] = rd_i32(r + 4); child1[x] = rd_i32(r + 8); t[x] = (double)rd_f32(r + 12);
+    }
+    memcpy(mut_off, moff, sizeof(int32_t) * ((size_t)n + 1));
+    memcpy(miss_off, ioff, sizeof(int32_t) * ((size_t)n + 1));
+    for (int64_t k = 0; k != M; ++k) {
+      const uint8_t* r = v->muts + 16 * (size_t)morder[k];
+      mut_site[k] = rd_i32(r + 4); mut_from[k] = r[8]; mut_to[k] = r[9]; mut_t[k] = (double)rd_f32(r + 12);
+    }
+    for (int64_t k = 0; k != I; ++k) {
+      const uint8_t* r = v->ivls + 12 * (size_t)iorder[k];
+      miss_start[k] = rd_i32(r + 4); miss_end[k] = rd_i32(r + 8);
+    }
+  }
+  free(moff); free(ioff); free(morder); free(iorder); free(foff); free(cur); free(nmiss); free(stack);
+  return rc;
+}
+
+int64_t orc_api_tree_write(const orc_emat* e, const uint8_t* ref, int32_t num_sites, uint8_t* out, int64_t cap) {
+  const int n = e->num_nodes;
+  const int64_t M = e->mut_off[n], I = e->miss_off[n];
+  /* [size][root uoffset][vtable 14 B + 2][table 24 B][nodes][mutations][missation_intervals][ref_seq] */
+  const int64_t vt = 8, tpos = 24, v_nodes = 48, v_muts = v_nodes + 4 + 16 * (int64_t)n, v_ivls = v_muts + 4 + 16 * M,
+                v_ref = v_ivls + 4 + 12 * I, total = (v_ref + 4 + num_sites + 3) / 4 * 4;
+  if (total > cap) return -1;
+  memset(out, 0, (size_t)total);
+  wr_u32(out, (uint32_t)(total - 4));
+  wr_u32(out + 4, (uint32_t)(tpos - 4));
+  wr_u16(out + vt, 14); wr_u16(out + vt + 2, 24);
+  for (int i = 0; i != 5; ++i) wr_u16(out + vt + 4 + 2 * i, (uint16_t)(4 + 4 * i));
+  wr_u32(out + tpos, (uint32_t)(tpos - vt));
+  wr_u32(out + tpos + 4, (uint32_t)(v_nodes - (tpos + 4)));
+  wr_u32(out + tpos + 8, (uint32_t)(v_muts - (tpos + 8)));
+  wr_u32(out + tpos + 12, (uint32_t)(v_ivls - (tpos + 12)));
+  wr_u32(out + tpos + 16, (uint32_t)(v_ref - (tpos + 16)));
+  wr_u32(out + tpos + 20, (uint32_t)e->root);
+  wr_u32(out + v_nodes, (uint32_t)n); wr_u32(out + v_muts, (uint32_t)M); wr_u32(out + v_ivls, (uint32_t)I); wr_u32(out + v_ref, (uint32_t)num_sites);
+  for (int x = 0; x != n; ++x) {
+    uint8_t* r = out + v_nodes + 4 + 16 * (size_t)x;
+    float tf = (float)e->t[x]; uint32_t u; memcpy(&u, &tf, 4);
+    wr_u32(r, (uint32_t)e->parent[x]); wr_u32(r + 4, (uint32_t)e->child0[x]); wr_u32(r + 8, (uint32_t)e->child1[x]); wr_u32(r + 12, u);   /* tips: -1, -1 (core/api.cpp:64-68) */
+    for (int k = e->mut_off[x]; k != e->mut_off[x + 1]; ++k) {
+      uint8_t* m = out + v_muts + 4 + 16 * (size_t)k;
+      float mf = (float)e->mut_t[k]; memcpy(&u, &mf, 4);
+      wr_u32(m, (uint32_t)x); wr_u32(m + 4, (uint32_t)e->mut_site[k]); m[8] = e->mut_from[k]; m[9] = e->mut_to[k]; wr_u32(m + 12, u);
+    }
+    for (int k = e->miss_off[x]; k != e->miss_off[x + 1]; ++k) {
+      uint8_t* m = out + v_ivls + 4 + 12 * (size_t)k;
+      wr_u32(m, (uint32_t)x); wr_u32(m + 4, (uint32_t)e->miss_start[k]); wr_u32(m + 8, (uint32_t)e->miss_end[k]);
+    }
+  }
+  if (num_sites > 0) memcpy(out + v_ref + 4, ref, (size_t)num_sites);
+  return total;
+}
+
 double orc_gamma_q_export(double a, double x) { return orc_gamma_q(a, x); }

@@ -131,6 +131,34 @@ int32_t orc_spr_study_from_attached(const orc_emat* e, const orc_sites* s, int32
                                     double annealing_factor, double t_max_tip, const double* lambda_i,
                                     orc_region* out, int32_t cap, orc_study_summary* summary);
 
+/* ---- the FlatBuffers wire format of a tree: delphy.api.Tree (core/api.fbs:13-49) ------------------------------------------------
+ * A view of the four vectors of a size-prefixed Tree buffer (as phylo_tree_to_api_tree writes it, core/api.cpp:34-98).  Records are
+ * FlatBuffers structs, little endian (core/api_generated.h:157-265): Node 16 B {parent i32, left_child i32, right_child i32, t f32},
+ * Mutation 16 B {branch i32, site i32, from u8, to u8, 2 B padding, t f32}, MissationInterval 12 B {branch, start_site, end_site}. */
+typedef struct orc_api_tree_view {
+  int32_t num_nodes, root, num_sites, pad_;
+  int64_t num_muts, num_ivls;
+  const uint8_t* nodes;
+  const uint8_t* muts;
+  const uint8_t* ivls;
+  const uint8_t* ref_seq;
+} orc_api_tree_view;
+/* flatbuffers::GetSizePrefixedRoot<api::Tree> + the field accessors (core/api_generated.h:267-304), with every offset bounds-checked.
+ * 0, or -1 if the buffer is malformed. */
+int32_t orc_api_tree_parse(const uint8_t* buf, int64_t len, orc_api_tree_view* out);
+/* api_tree_and_tree_info_to_phylo_tree (core/api.cpp:127-186) for a tree in normal form -- one that fix_up_missations
+ * (core/phylo_tree.cpp:379-478) changes only by reconstructing the from_states.  counts[5] = {num_nodes, root, M, I, F} is always
+ * filled; the arrays (sized from a first call with parent == NULL) are filled when parent != NULL.  Returns 0; -2 if the tree is not in
+ * normal form (common missations not factored up, a site missing twice along a root path, a mutation on a missing site), -3 if a
+ * mutation's `from` contradicts the sequence above it (the reference CHECKs), -1 for out-of-range indices. */
+int32_t orc_api_tree_to_emat(const orc_api_tree_view* v, int32_t* counts, int32_t* parent, int32_t* child0, int32_t* child1, double* t,
+                             int32_t* mut_off, int32_t* mut_site, uint8_t* mut_from, uint8_t* mut_to, double* mut_t,
+                             int32_t* miss_off, int32_t* miss_start, int32_t* miss_end,
+                             int32_t* fs_off, int32_t* fs_site, uint8_t* fs_from);
+/* phylo_tree_to_api_tree (core/api.cpp:34-98): same content, a layout of our own (a FlatBuffers reader follows offsets, it does not
+ * care where the vectors lie).  Returns the length, or -1 if cap is too small. */
+int64_t orc_api_tree_write(const orc_emat* e, const uint8_t* ref, int32_t num_sites, uint8_t* out, int64_t cap);
+
 double orc_gamma_q_export(double a, double x);
 
 #ifdef __cplusplus

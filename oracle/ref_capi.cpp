@@ -17,6 +17,7 @@
 #include "site_deltas.h"
 #include "evo_model.h"
 #include "tree_partitioning.h"
+#include "api.h"
 #include <random>
 
 #include "emat_oracle.h"
@@ -388,6 +389,63 @@ double ref_bench_log_G_parts(const orc_emat* const* parts, int32_t n_parts, cons
   auto t1 = std::chrono::steady_clock::now();
   if (out_log_G) { *out_log_G = 0.0; for (auto v : results) { *out_log_G += v; } }
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- the FlatBuffers wire format of a tree (core/api.fbs:13-49) -------------------------------------------------------------------
+// phylo_tree_to_api_tree (core/api.cpp:34-98): the bytes the reference writes for this EMAT (size-prefixed buffer).
+// Returns the length, or -1 if cap is too small.
+int64_t ref_api_tree_write(const orc_emat* e, const orc_sites* s, uint8_t* out, int64_t cap) {
+  auto scope = Local_arena_scope{};
+  auto tree = make_tree(e, s);
+  auto fb = phylo_tree_to_api_tree(tree);
+  if ((int64_t)fb.size() > cap) return -1;
+  std::memcpy(out, fb.data(), fb.size());
+  return (int64_t)fb.size();
+}
+
+// api_tree_and_tree_info_to_phylo_tree (core/api.cpp:127-186, which ends in fix_up_missations, core/phylo_tree.cpp:379-478)
+// on `buf`, flattened to the arrays of orc_emat.  Two calls: with arrays == NULL it returns the totals in counts[5] =
+// {num_nodes, root, M, I, F}; with arrays it fills them (caller-allocated to those sizes; ref_out[L] = ref_sequence).
+int32_t ref_api_tree_read(const uint8_t* buf, int32_t* counts, int32_t* parent, int32_t* child0, int32_t* child1, double* t,
+                          int32_t* mut_off, int32_t* mut_site, uint8_t* mut_from, uint8_t* mut_to, double* mut_t,
+                          int32_t* miss_off, int32_t* miss_start, int32_t* miss_end,
+                          int32_t* fs_off, int32_t* fs_site, uint8_t* fs_from, uint8_t* ref_out) {
+  auto scope = Local_arena_scope{};
+  // the reader wants a TreeInfo buffer next to the tree (names, tip-date ranges): one with empty names and no uncertain dates
+  auto api_tree = flatbuffers::GetSizePrefixedRoot<api::Tree>(buf);
+  auto n = static_cast<int32_t>(api_tree->nodes()->size());
+  auto blank = Phylo_tree{n};
+  for (auto v = 0; v != n; ++v) {
+    auto api_node = api_tree->nodes()->Get(v);
+    if (api_node->left_child() != k_no_node) { blank.at(v).children = {api_node->left_child(), api_node->right_child()}; }
+    blank.at(v).t_min = blank.at(v).t_max = 0.0;
+  }
+  auto info = phylo_tree_to_api_tree_info(blank);
+  auto tree = api_tree_and_tree_info_to_phylo_tree(buf, info.data());
+  auto M = 0, I = 0, F = 0;
+  for (auto v = 0; v != n; ++v) {
+    M += (int)std::ssize(tree.at(v).mutations);
+    I += (int)tree.at(v).missations.intervals.num_intervals();
+    F += (int)std::ssize(tree.at(v).missations.from_states);
+  }
+  counts[0] = n; counts[1] = tree.root; counts[2] = M; counts[3] = I; counts[4] = F;
+  if (!parent) return 0;
+  auto m = 0, i = 0, f = 0;
+  for (auto v = 0; v != n; ++v) {
+    const auto& node = tree.at(v);
+    parent[v] = node.parent;
+    if (node.is_tip()) { child0[v] = -1; child1[v] = -1; } else { child0[v] = node.children[0]; child1[v] = node.children[1]; }
+    t[v] = node.t;
+    mut_off[v] = m; miss_off[v] = i; fs_off[v] = f;
+    for (const auto& mu : node.mutations) {
+      mut_site[m] = mu.site; mut_from[m] = static_cast<uint8_t>(mu.from); mut_to[m] = static_cast<uint8_t>(mu.to); mut_t[m] = mu.t; ++m;
+    }
+    for (const auto& [a, b] : node.missations.intervals) { miss_start[i] = a; miss_end[i] = b; ++i; }
+    for (const auto& [l, st] : node.missations.from_states) { fs_site[f] = l; fs_from[f] = static_cast<uint8_t>(st); ++f; }
+  }
+  mut_off[n] = m; miss_off[n] = i; fs_off[n] = f;
+  for (auto l = 0; l != std::ssize(tree.ref_sequence); ++l) { ref_out[l] = static_cast<uint8_t>(tree.ref_sequence[l]); }
+  return 0;
 }
 
 }  // extern "C"

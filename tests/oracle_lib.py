@@ -162,6 +162,89 @@ def emat_from_lists(root, parent, children, t, mutations, miss_intervals, from_s
     return Emat(root, parent, c0, c1, t, mo, ms, mf, mt, mtt, io, ist, ien, fo, fs, ff, includes_run_root)
 
 
+class OrcApiTreeView(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("root", C.c_int32), ("num_sites", C.c_int32), ("pad_", C.c_int32),
+                ("num_muts", C.c_int64), ("num_ivls", C.c_int64),
+                ("nodes", C.c_void_p), ("muts", C.c_void_p), ("ivls", C.c_void_p), ("ref_seq", C.c_void_p)]
+
+
+# parent, child0, child1, t, mut_off, mut_site, mut_from, mut_to, mut_t, miss_off, miss_start, miss_end, fs_off, fs_site, fs_from
+_EMAT_OUT_ARGS = [i32p, i32p, i32p, f64p, i32p, i32p, u8p, u8p, f64p, i32p, i32p, i32p, i32p, i32p, u8p]
+
+
+def _alloc_emat_arrays(counts):
+    n, _, M, I, F = (int(c) for c in counts)
+    return [np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64),
+            np.zeros(n + 1, np.int32), np.zeros(max(M, 1), np.int32), np.zeros(max(M, 1), np.uint8), np.zeros(max(M, 1), np.uint8),
+            np.zeros(max(M, 1), np.float64),
+            np.zeros(n + 1, np.int32), np.zeros(max(I, 1), np.int32), np.zeros(max(I, 1), np.int32),
+            np.zeros(n + 1, np.int32), np.zeros(max(F, 1), np.int32), np.zeros(max(F, 1), np.uint8)]
+
+
+def _emat_from_arrays(counts, arrs) -> "Emat":
+    n, root, M, I, F = (int(c) for c in counts)
+    a = list(arrs)
+    for i in (5, 6, 7, 8): a[i] = a[i][:M]
+    for i in (10, 11): a[i] = a[i][:I]
+    for i in (13, 14): a[i] = a[i][:F]
+    return Emat(root, *a)
+
+
+def _ptrs(arrs):
+    tys = _EMAT_OUT_ARGS
+    return [_p(a, ty) for a, ty in zip(arrs, tys)]
+
+
+def api_tree_write(e: "Emat", ref_seq: np.ndarray, impl: str = "oracle", sites: "Sites | None" = None) -> bytes:
+    """phylo_tree_to_api_tree (core/api.cpp:34-98): the size-prefixed FlatBuffers bytes of a tree, written by the oracle (its own
+    layout) or by the reference's FlatBufferBuilder (impl='ref'; needs `sites` for the tree's reference sequence)."""
+    n = e.num_nodes
+    cap = 4096 + 16 * n + 16 * int(e.mut_off[n]) + 12 * int(e.miss_off[n]) + len(ref_seq)
+    buf = (C.c_uint8 * cap)()
+    es = e.as_struct()
+    if impl == "ref":
+        ss = sites.as_struct()
+        got = ref().ref_api_tree_write(C.byref(es), C.byref(ss), buf, cap)
+    else:
+        r = np.ascontiguousarray(ref_seq, dtype=np.uint8)
+        got = oracle().orc_api_tree_write(C.byref(es), _p(r, u8p), len(r), buf, cap)
+    assert got > 0, got
+    return bytes(buf[:got])
+
+
+def api_tree_read(data: bytes, impl: str = "oracle"):
+    """api_tree_and_tree_info_to_phylo_tree (core/api.cpp:127-186) -> (Emat, ref_seq).  impl='ref' runs the reference's reader (and its
+    fix_up_missations); impl='oracle' the restatement, which raises ValueError(code) for buffers it does not take."""
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    counts = np.zeros(5, np.int32)
+    if impl == "ref":
+        lib = ref()
+        nul = [None] * 15
+        lib.ref_api_tree_read(buf, _p(counts, i32p), *nul, None)
+        arrs = _alloc_emat_arrays(counts)
+        view = OrcApiTreeView()
+        if oracle().orc_api_tree_parse(buf, len(data), C.byref(view)) != 0:
+            raise ValueError(-1)
+        ref_seq = np.zeros(max(view.num_sites, 1), np.uint8)
+        lib.ref_api_tree_read(buf, _p(counts, i32p), *_ptrs(arrs), _p(ref_seq, u8p))
+        return _emat_from_arrays(counts, arrs), ref_seq[:view.num_sites]
+    lib = oracle()
+    view = OrcApiTreeView()
+    rc = lib.orc_api_tree_parse(buf, len(data), C.byref(view))
+    if rc != 0:
+        raise ValueError(rc)
+    nul = [None] * 15
+    rc = lib.orc_api_tree_to_emat(C.byref(view), _p(counts, i32p), *nul)
+    if rc != 0:
+        raise ValueError(rc)
+    arrs = _alloc_emat_arrays(counts)
+    rc = lib.orc_api_tree_to_emat(C.byref(view), _p(counts, i32p), *_ptrs(arrs))
+    if rc != 0:
+        raise ValueError(rc)
+    ref_seq = np.ctypeslib.as_array(C.cast(view.ref_seq, u8p), shape=(max(view.num_sites, 1),))[:view.num_sites].copy()
+    return _emat_from_arrays(counts, arrs), ref_seq
+
+
 # ------------------------------------------------------------------------------------------------
 def _build(target: str):
     subprocess.run(["make", "-s", "-C", ORACLE_DIR, target], check=True, capture_output=True)
@@ -214,6 +297,9 @@ def oracle() -> C.CDLL:
                                                     R, C.c_int32, C.POINTER(OrcStudySummary)]
         lib.orc_spr_study_from_attached.restype = C.c_int32
         lib.orc_gamma_q_export.argtypes = [C.c_double, C.c_double]; lib.orc_gamma_q_export.restype = C.c_double
+        lib.orc_api_tree_parse.argtypes = [C.c_void_p, C.c_int64, C.POINTER(OrcApiTreeView)]; lib.orc_api_tree_parse.restype = C.c_int32
+        lib.orc_api_tree_to_emat.argtypes = [C.POINTER(OrcApiTreeView), i32p] + _EMAT_OUT_ARGS; lib.orc_api_tree_to_emat.restype = C.c_int32
+        lib.orc_api_tree_write.argtypes = [E, u8p, C.c_int32, C.c_void_p, C.c_int64]; lib.orc_api_tree_write.restype = C.c_int64
         _ORACLE = lib
     return _ORACLE
 
@@ -261,6 +347,8 @@ def ref() -> C.CDLL:
         lib.ref_bench_log_G.argtypes = [E, S, C.c_int32, C.c_int32, f64p]; lib.ref_bench_log_G.restype = C.c_double
         lib.ref_bench_spr.argtypes = [E, S, i32p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int64)]
         lib.ref_bench_spr.restype = C.c_double
+        lib.ref_api_tree_write.argtypes = [E, S, C.c_void_p, C.c_int64]; lib.ref_api_tree_write.restype = C.c_int64
+        lib.ref_api_tree_read.argtypes = [C.c_void_p, i32p] + _EMAT_OUT_ARGS + [u8p]; lib.ref_api_tree_read.restype = C.c_int32
         _REF = lib
     return _REF
 
