@@ -235,6 +235,17 @@ def cpu_spr(emat, sites, xs, budget_s, threads, t_max_tip):
                 sample=f"{n_x} full SPR studies (reconstruct_missing_sites_at + seed_fill_from + Spr_study), {nreg.value} regions, {t:.1f} s")
 
 
+def cpu_api_tree_read(buf):
+    """api_tree_and_tree_info_to_phylo_tree (core/api.cpp:127-186, fix_up_missations included) on one buffer, one thread: the compiled
+    reference when it travelled, else the oracle's restatement."""
+    ol, _ = _oracle_modules()
+    kind = "reference" if ol.ref_available() else "port"
+    t0 = time.perf_counter()
+    ol.api_tree_read(buf, "ref" if kind == "reference" else "oracle")
+    return {"load_ms_per_tree": (time.perf_counter() - t0) * 1e3, "kind": kind, "cores": 1,
+            "sample": "one buffer -> Phylo_tree (-> flat arrays), single thread"}
+
+
 def pick_spr_nodes(emat, n, seed=1234):
     rng = np.random.default_rng(seed)
     cand = np.array([v for v in rng.permutation(emat.num_nodes)[: 8 * n + 8] if v != emat.root and emat.parent[v] != emat.root], np.int32)
@@ -450,6 +461,7 @@ def main():
         a.record(stream)
         for _ in range(args.steps * SB):
             spr_batch()
+        ctx.join_side_streams()       # the last batches' normalisation passes run on the library's tail stream: inside the timed region
         b.record(stream)
         barrier()
         spr_ms = a.elapsed_time(b) / (args.steps * SB)        # per batch
@@ -584,6 +596,32 @@ def main():
             t.close()
         c.close()
     del e2e_emats
+    # ---- the reference's wire format (delphy.api.Tree, core/api.fbs) straight to the device and back --------------------------------------------
+    wire = None
+    wire_buf0 = None
+    if not args.no_secondary:
+        n_w = min(4, args.chains)
+        t0 = time.perf_counter()
+        bufs = [forest.write_api_tree(k) for k in range(n_w)]                  # phylo_tree_to_api_tree of the resident trees
+        wr_ms = (time.perf_counter() - t0) * 1e3 / n_w
+        wire_buf0 = bufs[0]
+        db.Forest.from_api_trees(ctx, bufs, tables[:n_w], sites_index=np.arange(n_w)).close()
+        reps_w = 3
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps_w):
+            fw = db.Forest.from_api_trees(ctx, bufs, tables[:n_w], sites_index=np.arange(n_w))
+            lgw = fw.log_G()[2]
+            fw.close()
+        torch.cuda.synchronize()
+        (ld_s,) = max_over_ranks([time.perf_counter() - t0])
+        # the trees went device -> float32 times -> device: same integers, log G close to the resident trees' (times rounded to float32)
+        assert np.allclose(lgw, lg[:n_w], rtol=1e-4)
+        wire = {"format": "delphy.api.Tree (FlatBuffers; core/api.fbs:13-49)", "trees_per_call": n_w, "buffer_bytes_per_tree": len(bufs[0]),
+                "load_ms_per_tree": ld_s / reps_w / n_w * 1e3, "write_ms_per_tree": wr_ms,
+                "note": "load: host buffer -> dphy_forest_upload_api_trees (struct vectors DMA'd as they lie; SoA split, CSR offsets, from_states "
+                        "reconstruction, two flattens on the device) -> first evaluation -> log G read back, wall clock; write: "
+                        "dphy_forest_write_api_tree (pack on the device + D2H)"}
     forest_bytes = forest.device_bytes
     nodes0, info0 = emats[0].num_nodes, infos[0]
     whole_emat, whole_sites = emats[0], host_sites[0]
@@ -626,6 +664,7 @@ def main():
                 barrier(); a.record(stream)
                 for _ in range(nb):
                     sf.spr_study_batch(rq).close()
+                ctx.join_side_streams()
                 b.record(stream); barrier()
                 (sms,) = max_over_ranks([a.elapsed_time(b) / nb])
                 bt = sf.spr_study_batch(rq); nreg = bt.total_regions(); bt.close()
@@ -711,12 +750,16 @@ def main():
             line["configs"] = secondary
         if partitioned:
             line["partitioned"] = partitioned
+        if wire:
+            line["wire_format"] = wire
         if world == 1 and not args.no_cpu_baseline:
             threads = host_cores()
             cb = cpu_log_G(whole_emat, whole_sites, args.cpu_seconds, threads)
             cb["spr"] = cpu_spr(whole_emat, whole_sites, spr_xs if spr_reqs is not None else None, args.cpu_seconds, threads, info0["t_max_tip"])
             if not args.no_partitioned:
                 cb["partitioned"] = cpu_log_G_partitioned(db, whole_emat, whole_sites, args.cpu_seconds / 2, threads)
+            if wire_buf0 is not None:
+                cb["wire_format"] = cpu_api_tree_read(wire_buf0)
             line["cpu_baseline"] = cb
     tables[0].close()
     ctx.close()

@@ -224,6 +224,7 @@ def lib() -> C.CDLL:
     L.dphy_ctx_destroy.argtypes = [vp]
     L.dphy_last_error.argtypes = [vp]; L.dphy_last_error.restype = C.c_char_p
     L.dphy_ctx_synchronize.argtypes = [vp]
+    L.dphy_ctx_join_side_streams.argtypes = [vp]
     L.dphy_arena_stats.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.dphy_ctx_stream.argtypes = [vp]; L.dphy_ctx_stream.restype = vp
     L.dphy_ctx_launch_count.argtypes = [vp]; L.dphy_ctx_launch_count.restype = C.c_int64
@@ -482,6 +483,10 @@ class Context:
     def check(self, st: int):
         if st != DPHY_OK:
             raise DphyError(st, lib().dphy_last_error(self._h).decode())
+
+    def join_side_streams(self):
+        """dphy_ctx_join_side_streams: the main stream waits (on the device) for the library's side streams."""
+        self.check(lib().dphy_ctx_join_side_streams(self._h))
 
     def synchronize(self):
         self.check(lib().dphy_ctx_synchronize(self._h))

@@ -135,6 +135,9 @@ void dphy_ctx_destroy(dphy_ctx* ctx) {
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  if (ctx->tail_stream) { cudaStreamSynchronize(ctx->tail_stream); cudaStreamDestroy(ctx->tail_stream); }
+  for (auto& blk : ctx->spr_blocks) { if (blk.ev) cudaEventDestroy(blk.ev); cudaFree(blk.ptr); }
+  if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
   for (int i = 0; i < dphy_ctx::kTallyStreams; ++i) {
     if (ctx->tally_streams[i]) { cudaStreamSynchronize(ctx->tally_streams[i]); cudaStreamDestroy(ctx->tally_streams[i]); }
     if (ctx->ev_tally[i]) cudaEventDestroy(ctx->ev_tally[i]);
@@ -157,8 +160,21 @@ void dphy_ctx_destroy(dphy_ctx* ctx) {
 
 const char* dphy_last_error(const dphy_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context (CUDA device unavailable?)"; }
 
+int dphy_ctx_join_side_streams(dphy_ctx* ctx) {
+  if (!ctx) return DPHY_ERR_INVALID_ARGUMENT;
+  if (ctx->tail_stream && ctx->tail_dirty) {
+    cudaSetDevice(ctx->device);
+    DPHY_CUDA(ctx, cudaEventRecord(ctx->ev_tail, ctx->tail_stream));
+    DPHY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tail, 0));
+    ctx->tail_dirty = false;
+  }
+  return DPHY_OK;
+}
+
 int dphy_ctx_synchronize(dphy_ctx* ctx) {
   if (!ctx) return DPHY_ERR_INVALID_ARGUMENT;
+  int st = dphy_ctx_join_side_streams(ctx);
+  if (st != DPHY_OK) return st;
   DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return DPHY_OK;
 }
@@ -911,6 +927,14 @@ extern "C" {
 
 void dphy_forest_destroy(dphy_ctx* ctx, dphy_forest* fo) {
   if (!fo) return;
+  if (ctx) {
+    // blocks parked by destroyed SPR batches (dphy_ctx::spr_blocks) go back to the pool with the forest they were sized for
+    for (auto& blk : ctx->spr_blocks) {
+      if (blk.ev) { cudaStreamWaitEvent(ctx->stream, blk.ev, 0); cudaEventDestroy(blk.ev); }
+      cudaFreeAsync(blk.ptr, ctx->stream);
+    }
+    ctx->spr_blocks.clear();
+  }
   if (ctx) {
     cudaSetDevice(ctx->device);
     for (void* p : fo->allocs) cudaFreeAsync(p, ctx->stream);   // stream-ordered: returns to the pool, no device sync

@@ -200,6 +200,18 @@ struct dphy_ctx {
   // chain of the main stream (fork after spr_init_kernel, join before the prefix kernel)
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // tail stream of the SPR batches: the normalisation pass of a batch (bandwidth-bound, touches only the batch's own block) runs
+  // here, next to the latency-bound setup chain of the NEXT batch on the main stream; every accessor of the batch joins first
+  cudaStream_t tail_stream = nullptr;
+  cudaEvent_t ev_tail = nullptr;
+  bool tail_dirty = false;      // work has been put on tail_stream since the main stream last joined it
+  // Blocks of destroyed SPR batches whose tail may still be running: kept here with the tail's event instead of being returned to
+  // the stream-ordered pool (a free in the tail stream's order makes the pool grow by one block per batch while the host enqueues
+  // ahead of the device; a free in the main stream's order would make the next batch's set-up wait for the tail).  The next batch
+  // takes the OLDEST block -- two batches back, its tail long finished -- after a device-side wait on that event.
+  struct SprBlock { void* ptr; size_t bytes; cudaEvent_t ev; };
+  std::vector<SprBlock> spr_blocks;
+  static constexpr size_t kSprBlocksKept = 3;
   // side streams of the per-site tallies of a whole forest: the trees' (small) kernel sequences run side by side
   static constexpr int kTallyStreams = 4;
   cudaStream_t tally_streams[kTallyStreams] = {};

@@ -1412,7 +1412,18 @@ struct dphy_spr_batch {
   int status = DPHY_OK;           // sticky: the first per-study error found by spr_fetch, returned by every accessor
   std::string status_msg;
   dphy_forest* forest = nullptr;
+  // the batch's normalisation pass was put on the ctx's tail stream: ev_done fires when it is through.  Accessors join first.
+  cudaEvent_t ev_done = nullptr;
+  bool tail_pending = false;
 };
+
+// order the main stream after the batch's tail (device-side wait; no host block)
+static int spr_join_tail(dphy_ctx* ctx, dphy_spr_batch* b) {
+  if (!b->tail_pending) return DPHY_OK;
+  DPHY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, b->ev_done, 0));
+  b->tail_pending = false;
+  return DPHY_OK;
+}
 
 namespace {
 size_t al(size_t x) { return (x + 255) / 256 * 256; }
@@ -1640,9 +1651,22 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   const size_t b_slab = al(b_groups + sizeof(SprGroupDev) * std::max<size_t>(1, groups.size()));
   const size_t total = b_slab + slab_bytes;
   char* d = nullptr;
-  cudaError_t ce = cudaMallocAsync((void**)&d, total, ctx->stream);
+  cudaError_t ce = cudaSuccess;
+  size_t block_bytes = total;
+  // a block left by an earlier batch (see dphy_ctx::spr_blocks): the oldest one that is large enough, once two are waiting
+  if (ctx->spr_blocks.size() >= 2) {
+    for (size_t i = 0; i < ctx->spr_blocks.size(); ++i) {
+      dphy_ctx::SprBlock blk = ctx->spr_blocks[i];
+      if (blk.bytes < total || blk.bytes > 2 * total + (64u << 20)) continue;
+      ctx->spr_blocks.erase(ctx->spr_blocks.begin() + i);
+      if (blk.ev) { cudaStreamWaitEvent(ctx->stream, blk.ev, 0); cudaEventDestroy(blk.ev); }
+      d = (char*)blk.ptr; block_bytes = blk.bytes;
+      break;
+    }
+  }
+  if (!d) ce = cudaMallocAsync((void**)&d, total, ctx->stream);
   if (ce != cudaSuccess) { delete b; return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, std::string("cudaMallocAsync(spr batch): ") + cudaGetErrorString(ce)); }
-  b->d_block = d; b->bytes = total;
+  b->d_block = d; b->bytes = block_bytes;
   b->dev.studies = (SprStudy*)(d + b_studies);
   b->dev.tile_agg = (int32_t*)(d + b_agg);
   b->dev.tile_flag = (uint32_t*)(d + b_flag);
@@ -1763,25 +1787,62 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
   }
   if (any_weighted) {
     if (any_unfused) { spr_weights_kernel<<<dim3(kWeightBlocks, n), 256, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
-    spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ctx->stream>>>(b->dev);
+    // The normalisation pass streams the batch's own arrays (raw log-weights in, tails out) and nothing else: it goes to the tail
+    // stream, so that the next batch's set-up chain (paths, X tables, event scan: latency-bound, small grids) runs next to it.
+    static const bool use_tail = [] { const char* e = getenv("DPHY_SPR_TAIL_STREAM"); return !e || atoi(e) != 0; }();
+    cudaStream_t ns = ctx->stream;
+    if (use_tail) {
+      if (!ctx->tail_stream) {
+        if (cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming) != cudaSuccess) {
+          cudaFreeAsync(d, ctx->stream); delete b; return set_error(ctx, DPHY_ERR_CUDA, "spr: tail stream");
+        }
+      }
+      if (cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaFreeAsync(d, ctx->stream); delete b; return set_error(ctx, DPHY_ERR_CUDA, "spr: tail event");
+      }
+      cudaEventRecord(ctx->ev_tail, ctx->stream);
+      cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_tail, 0);
+      ns = ctx->tail_stream;
+    }
+    spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ns>>>(b->dev);
+    if (use_tail) { cudaEventRecord(b->ev_done, ctx->tail_stream); b->tail_pending = true; ctx->tail_dirty = true; }
     ++launched;
     b->weighted = true;
   }
   ctx->launches += launched;
   st = check_cuda(ctx, cudaGetLastError(), "spr kernels launch");
-  if (st != DPHY_OK) { cudaFreeAsync(d, ctx->stream); delete b; return st; }
+  if (st != DPHY_OK) { dphy_spr_batch_destroy(ctx, b); return st; }
   *out = b;
   return DPHY_OK;
 }
 
 void dphy_spr_batch_destroy(dphy_ctx* ctx, dphy_spr_batch* b) {
   if (!b) return;
-  if (ctx && b->d_block) { cudaSetDevice(ctx->device); cudaFreeAsync(b->d_block, ctx->stream); }
+  if (ctx && b->d_block) {
+    cudaSetDevice(ctx->device);
+    if (b->tail_pending && ctx->tail_stream) {
+      // the tail may still be running: the block is parked with the tail's event (the main stream does not wait, so the next
+      // batch's set-up proceeds) and handed to a later batch; the oldest parked block is released when too many are waiting
+      ctx->spr_blocks.push_back({b->d_block, b->bytes, b->ev_done});
+      b->ev_done = nullptr;
+      while (ctx->spr_blocks.size() > dphy_ctx::kSprBlocksKept) {
+        dphy_ctx::SprBlock old = ctx->spr_blocks.front();
+        ctx->spr_blocks.erase(ctx->spr_blocks.begin());
+        if (old.ev) { cudaStreamWaitEvent(ctx->stream, old.ev, 0); cudaEventDestroy(old.ev); }
+        cudaFreeAsync(old.ptr, ctx->stream);
+      }
+    } else {
+      cudaFreeAsync(b->d_block, ctx->stream);
+    }
+  }
+  if (b->ev_done) cudaEventDestroy(b->ev_done);
   delete b;
 }
 
 static int spr_fetch(dphy_ctx* ctx, dphy_spr_batch* b) {
   if (b->status != DPHY_OK) return set_error(ctx, b->status, b->status_msg);
+  { const int js = spr_join_tail(ctx, b); if (js != DPHY_OK) return js; }
   if (b->fetched || b->num == 0) return DPHY_OK;
   DPHY_CUDA(ctx, cudaMemcpyAsync(b->host.data(), b->dev.studies, sizeof(SprStudy) * b->num, cudaMemcpyDeviceToHost, ctx->stream));
   DPHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1861,6 +1922,7 @@ int dphy_spr_batch_set_weights(dphy_ctx* ctx, dphy_spr_batch* b, const dphy_spr_
   if (b->status != DPHY_OK) return set_error(ctx, b->status, b->status_msg);
   if (b->num == 0) return DPHY_OK;
   cudaSetDevice(ctx->device);
+  { const int js = spr_join_tail(ctx, b); if (js != DPHY_OK) return js; }
   for (int i = 0; i < b->num; ++i)
     if (!(params[i].lambda_X > 0.0)) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "spr: lambda_X must be > 0");
   void* hbv = nullptr;

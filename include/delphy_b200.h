@@ -158,6 +158,10 @@ int  dphy_ctx_create(int device, dphy_ctx** out);
 void dphy_ctx_destroy(dphy_ctx* ctx);
 const char* dphy_last_error(const dphy_ctx* ctx);
 int  dphy_ctx_synchronize(dphy_ctx* ctx);
+/* Makes the ctx's main stream wait (on the device, no host block) for whatever the library has put on its side streams -- the
+ * normalisation pass of the latest SPR batches runs on one, next to the set-up of the following batch.  Every accessor of a batch
+ * joins on its own; callers that time a region with events on dphy_ctx_stream() call this before recording the closing event. */
+int  dphy_ctx_join_side_streams(dphy_ctx* ctx);
 /* Device arena replacing scratch_space (core/scratch_space.h:49-267): stats + explicit reset (scope close). */
 int  dphy_arena_stats(const dphy_ctx* ctx, size_t* capacity, size_t* high_water);
 /* cudaStream_t of the ctx as a void* (so callers can record CUDA events on the launching stream). */

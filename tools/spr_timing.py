@@ -17,7 +17,7 @@ for keep in (False, True):
     for it in range(6):
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        a.record(st); bt = fo.spr_study_batch(reqs); b.record(st)
+        a.record(st); bt = fo.spr_study_batch(reqs); ctx.join_side_streams(); b.record(st)
         t1 = time.perf_counter()
         ctx.synchronize()
         t2 = time.perf_counter()
