@@ -110,7 +110,14 @@ int dphy_ctx_create(int device, dphy_ctx** out) {
   if (!ctx) return DPHY_ERR_OUT_OF_MEMORY;
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DPHY_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DPHY_ERR_CUDA; }
+  // the main stream outranks the library's side streams (created at the default, lowest priority): where a bandwidth-bound tail
+  // kernel of one SPR batch runs next to the latency-bound set-up chain of the next, freed SM slots go to the chain first
+  {
+    int prio_least = 0, prio_greatest = 0;
+    static const bool prio = [] { const char* e = getenv("DPHY_MAIN_STREAM_PRIORITY"); return !e || atoi(e) != 0; }();
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio ? prio_greatest : prio_least) != cudaSuccess) { delete ctx; return DPHY_ERR_CUDA; }
+  }
   if (cudaEventCreateWithFlags(&ctx->pinned_ev, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return DPHY_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -321,6 +328,7 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
 }
 
 int dphy_sites_update(dphy_ctx* ctx, dphy_sites* s, const dphy_sites_host* host) {
+  if (ctx) dphy_ctx_join_side_streams(ctx);
   if (!ctx || !s || !host) return DPHY_ERR_INVALID_ARGUMENT;
   if (host->num_sites != s->L || host->num_partitions != s->P) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "sites update: number of sites / partitions differs from the table's");
   int st = validate_sequence(ctx, host);
@@ -333,6 +341,7 @@ int dphy_sites_update(dphy_ctx* ctx, dphy_sites* s, const dphy_sites_host* host)
 }
 
 void dphy_sites_destroy(dphy_ctx* ctx, dphy_sites* s) {
+  if (ctx) dphy_ctx_join_side_streams(ctx);
   if (!s) return;
   if (s->d_ref) {   // base of the slab
     if (ctx) { cudaSetDevice(ctx->device); cudaFreeAsync(s->d_ref, ctx->stream); }   // stream-ordered: after the last kernel that reads it
@@ -928,6 +937,7 @@ extern "C" {
 void dphy_forest_destroy(dphy_ctx* ctx, dphy_forest* fo) {
   if (!fo) return;
   if (ctx) {
+    dphy_ctx_join_side_streams(ctx);      // the tail of an SPR batch may still be reading this forest
     // blocks parked by destroyed SPR batches (dphy_ctx::spr_blocks) go back to the pool with the forest they were sized for
     for (auto& blk : ctx->spr_blocks) {
       if (blk.ev) { cudaStreamWaitEvent(ctx->stream, blk.ev, 0); cudaEventDestroy(blk.ev); }
@@ -959,6 +969,7 @@ int64_t dphy_forest_log_G_algorithmic_bytes(const dphy_forest* fo) {
 }
 
 int dphy_forest_set_node_times(dphy_ctx* ctx, dphy_forest* fo, int32_t tree, int32_t count, const int32_t* nodes, const double* t) {
+  if (ctx) dphy_ctx_join_side_streams(ctx);        // the tail of an SPR batch may still be reading the node times
   if (!ctx || !fo || tree < 0 || tree >= fo->h.num_trees || count < 0 || (count > 0 && (!nodes || !t))) return DPHY_ERR_INVALID_ARGUMENT;
   if (count == 0) return DPHY_OK;
   cudaSetDevice(ctx->device);

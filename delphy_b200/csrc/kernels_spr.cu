@@ -1774,42 +1774,48 @@ int dphy_spr_study_batch(dphy_ctx* ctx, dphy_forest* fo, int32_t n, const dphy_s
     else spr_emit_kernel<4><<<grid_emit, kTile, 0, ctx->stream>>>(fo->h, b->dev);
     ++launched;
   }
-  if (ng > 0 && g2) {
-    spr_g2_bases_kernel<<<dim3(kGroup, ng, kBasesSlices), kBasesThreads, 0, ctx->stream>>>(b->dev, b->d_groups);
-    if (fuse_weights) spr_g2_emit_kernel<2><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
-    else spr_g2_emit_kernel<1><<<grid_g2t, kG2Warps * 32, 0, ctx->stream>>>(fo->h, b->dev, b->d_groups);
-    launched += 2;
-  }
   bool any_weighted = false, any_unfused = false;
   for (int i = 0; i < n; ++i) {
     any_weighted |= b->host[i].lambda_X > 0.0;
     any_unfused |= b->host[i].lambda_X > 0.0 && !b->host[i].weights_fused;
   }
-  if (any_weighted) {
-    if (any_unfused) { spr_weights_kernel<<<dim3(kWeightBlocks, n), 256, 0, ctx->stream>>>(fo->h, b->dev); ++launched; }
-    // The normalisation pass streams the batch's own arrays (raw log-weights in, tails out) and nothing else: it goes to the tail
-    // stream, so that the next batch's set-up chain (paths, X tables, event scan: latency-bound, small grids) runs next to it.
-    static const bool use_tail = [] { const char* e = getenv("DPHY_SPR_TAIL_STREAM"); return !e || atoi(e) != 0; }();
-    cudaStream_t ns = ctx->stream;
-    if (use_tail) {
-      if (!ctx->tail_stream) {
-        if (cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming) != cudaSuccess) {
-          cudaFreeAsync(d, ctx->stream); delete b; return set_error(ctx, DPHY_ERR_CUDA, "spr: tail stream");
-        }
-      }
-      if (cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming) != cudaSuccess) {
-        cudaFreeAsync(d, ctx->stream); delete b; return set_error(ctx, DPHY_ERR_CUDA, "spr: tail event");
-      }
-      cudaEventRecord(ctx->ev_tail, ctx->stream);
-      cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_tail, 0);
-      ns = ctx->tail_stream;
+  const bool g2_emit = ng > 0 && g2;
+  if (g2_emit) { spr_g2_bases_kernel<<<dim3(kGroup, ng, kBasesSlices), kBasesThreads, 0, ctx->stream>>>(b->dev, b->d_groups); ++launched; }
+  // The bulk passes of a batch -- the template emit (heads + raw log-weights: issue- and bandwidth-bound), the dense weights pass if
+  // any, the normalisation (bandwidth-bound) -- read the forest and write only the batch's own block: they go to the TAIL stream, so
+  // that the set-up chain of the NEXT batch (paths, X tables, event scan, segments, bases: latency-bound kernels with small grids,
+  // on the higher-priority main stream) runs next to them.  Every accessor of the batch, and every entry point that edits or frees
+  // the forest, joins the tail first.
+  static const int tail_mode = [] { const char* e = getenv("DPHY_SPR_TAIL_STREAM"); return e ? atoi(e) : 2; }();   // 0 off, 1 normalize only, 2 emit too
+  const bool use_tail = tail_mode != 0 && (g2_emit || any_weighted);
+  cudaStream_t ts = ctx->stream;
+  auto fork_tail = [&]() -> int {
+    if (ts != ctx->stream) return DPHY_OK;
+    if (!ctx->tail_stream) {
+      if (cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming) != cudaSuccess)
+        return set_error(ctx, DPHY_ERR_CUDA, "spr: tail stream");
     }
-    spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ns>>>(b->dev);
-    if (use_tail) { cudaEventRecord(b->ev_done, ctx->tail_stream); b->tail_pending = true; ctx->tail_dirty = true; }
+    if (!b->ev_done && cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming) != cudaSuccess) return set_error(ctx, DPHY_ERR_CUDA, "spr: tail event");
+    cudaEventRecord(ctx->ev_tail, ctx->stream);
+    cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_tail, 0);
+    ts = ctx->tail_stream;
+    return DPHY_OK;
+  };
+  if (g2_emit) {
+    if (use_tail && tail_mode >= 2) { st = fork_tail(); if (st != DPHY_OK) { cudaFreeAsync(d, ctx->stream); delete b; return st; } }
+    if (fuse_weights) spr_g2_emit_kernel<2><<<grid_g2t, kG2Warps * 32, 0, ts>>>(fo->h, b->dev, b->d_groups);
+    else spr_g2_emit_kernel<1><<<grid_g2t, kG2Warps * 32, 0, ts>>>(fo->h, b->dev, b->d_groups);
+    ++launched;
+  }
+  if (any_weighted) {
+    if (use_tail) { st = fork_tail(); if (st != DPHY_OK) { cudaFreeAsync(d, ctx->stream); delete b; return st; } }
+    if (any_unfused) { spr_weights_kernel<<<dim3(kWeightBlocks, n), 256, 0, ts>>>(fo->h, b->dev); ++launched; }
+    spr_normalize_kernel<<<dim3(kNormBlocks, n), 256, 0, ts>>>(b->dev);
     ++launched;
     b->weighted = true;
   }
+  if (ts != ctx->stream) { cudaEventRecord(b->ev_done, ctx->tail_stream); b->tail_pending = true; ctx->tail_dirty = true; }
   ctx->launches += launched;
   st = check_cuda(ctx, cudaGetLastError(), "spr kernels launch");
   if (st != DPHY_OK) { dphy_spr_batch_destroy(ctx, b); return st; }

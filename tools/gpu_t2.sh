@@ -6,7 +6,7 @@ timeout 300 python bench.py --no-secondary --no-partitioned --no-mcmc --no-cpu-b
 python -c "
 import json; d=json.load(open('gpurun_out/t2/bench.json'))
 print('spr ms', d['spr_ms_per_batch'], 'frac', d['roofline_spr']['frac'], 'value', d['value'])"
-DPHY_SPR_TAIL_STREAM=0 timeout 300 python bench.py --no-secondary --no-partitioned --no-mcmc --no-cpu-baseline > gpurun_out/t2/bench_notail.json 2> gpurun_out/t2/bench_notail.err
+DPHY_SPR_TAIL_STREAM=1 timeout 300 python bench.py --no-secondary --no-partitioned --no-mcmc --no-cpu-baseline > gpurun_out/t2/bench_notail.json 2> gpurun_out/t2/bench_notail.err
 python -c "
 import json; d=json.load(open('gpurun_out/t2/bench_notail.json'))
-print('no tail: spr ms', d['spr_ms_per_batch'], 'frac', d['roofline_spr']['frac'])"
+print('tail mode 1: spr ms', d['spr_ms_per_batch'], 'frac', d['roofline_spr']['frac'])"
