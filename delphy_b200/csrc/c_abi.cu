@@ -220,8 +220,9 @@ static void fill_tables(dphy_sites* s) {
       s->h.tab_dq[i] = dq;
       s->h.tab_md[i] = s->h.mu[pt] * s->h.nu_const * dq;
       s->h.tab_lq[i] = x != y ? std::log(s->h.mu[pt] * s->h.nu_const * s->h.q[i]) : 0.0;
+      s->h.tab_logq[i] = x != y ? std::log(s->h.q[i]) : 0.0;
     } else {
-      s->h.tab_dq[i] = 0.0; s->h.tab_md[i] = 0.0; s->h.tab_lq[i] = 0.0;
+      s->h.tab_dq[i] = 0.0; s->h.tab_md[i] = 0.0; s->h.tab_lq[i] = 0.0; s->h.tab_logq[i] = 0.0;
     }
   }
   for (int i = 0; i < kMaxPartitions * 4; ++i) {
@@ -308,6 +309,7 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
   Slab slab;
   const int b_ref = slab.reserve(L), b_part = slab.reserve(L), b_nu = slab.reserve(sizeof(double) * L);
   const int b_munu = slab.reserve(sizeof(double) * L), b_cumQ = slab.reserve(sizeof(double) * (L + 1));
+  const int b_munu2 = slab.reserve(sizeof(double2) * L);
   const int b_freq = slab.reserve(sizeof(int32_t) * kMaxPartitions * 4);
   const int b_cnu = slab.reserve(sizeof(double) * (size_t)P * 4 * (L + 1));
   const int b_cref = slab.reserve(sizeof(int32_t) * (size_t)P * 4 * (L + 1));
@@ -317,6 +319,7 @@ int dphy_sites_upload(dphy_ctx* ctx, const dphy_sites_host* host, dphy_sites** o
   s->bytes = slab.total;
   s->d_ref = slab.at<uint8_t>(dbase, b_ref); s->d_part = slab.at<uint8_t>(dbase, b_part); s->d_nu = slab.at<double>(dbase, b_nu);
   s->d_munu = slab.at<double>(dbase, b_munu); s->d_cumQ = slab.at<double>(dbase, b_cumQ);
+  s->d_munu2 = slab.at<double2>(dbase, b_munu2); s->h.munu2 = s->d_munu2;
   s->d_ref_freq = slab.at<int32_t>(dbase, b_freq); s->d_cum_nu_ba = slab.at<double>(dbase, b_cnu);
   s->d_cref = slab.at<int32_t>(dbase, b_cref);
   s->h.L = L; s->h.P = P; s->h.ref = s->d_ref; s->h.part = s->d_part; s->h.nu = s->d_nu; s->h.munu = s->d_munu;

@@ -44,6 +44,7 @@ struct SitesDev {
   const uint8_t* part;       // [L]
   const double* nu;          // [L]
   const double* munu;        // [L]  mu_{beta(l)} * nu_l
+  const double2* munu2;      // [L]  (mu nu_l, log(mu nu_l)): one 16-byte gather per mutation on the general log-G path (filled when nu_l varies)
   const double* cumQ;        // [L+1] calc_cum_Q_l_for_sequence
   const int32_t* ref_freq;   // [P*4] state frequencies of the reference sequence per partition
   const int32_t* cref;       // [L+1][P*4] cref[l*4P + b*4+a] = #{l' < l : partition(l') == b, ref[l'] == a}  (structure only; 16-byte aligned)
@@ -59,6 +60,7 @@ struct SitesDev {
   double tab_md[kMaxPartitions * 16];   // mu nu_const (q_a(y) - q_a(x))              (uniform nu only)
   double tab_lq[kMaxPartitions * 16];   // log(mu nu_const q_xy), 0 on the diagonal   (uniform nu only)
   double tab_muq[kMaxPartitions * 4];   // mu nu_const q_a(a)                          (uniform nu only)
+  double tab_logq[kMaxPartitions * 16]; // log(q_xy), 0 on the diagonal: log(mu nu_l q_xy) = munu2[l].y + tab_logq[code]
 };
 
 // Per log-G tile descriptor: everything the streaming kernel needs to issue its bulk copies without touching memory first.
@@ -225,7 +227,7 @@ struct dphy_ctx {
 struct dphy_sites {
   dphy::SitesDev h{};           // host mirror of the device view (pointers are device pointers)
   int32_t L = 0, P = 0;
-  uint8_t* d_ref = nullptr; uint8_t* d_part = nullptr; double* d_nu = nullptr; double* d_munu = nullptr;
+  uint8_t* d_ref = nullptr; uint8_t* d_part = nullptr; double* d_nu = nullptr; double* d_munu = nullptr; double2* d_munu2 = nullptr;
   double* d_cumQ = nullptr; int32_t* d_ref_freq = nullptr;
   // per-(partition,state) cumulative nu tables for O(1) interval tallies (Ttwiddle): [P*4][L+1]
   double* d_cum_nu_ba = nullptr;

@@ -314,9 +314,11 @@ __global__ void __launch_bounds__(kLgThreads, kMinBlocks) emat_log_G_tile_kernel
             double dd, lg;
             if (uni) { dd = __ldg(S.tab_md + code); lg = __ldg(S.tab_lq + code); }
             else {
-              const double mn = __ldg(S.munu + __ldg(f.mut_site + i));
-              dd = mn * __ldg(S.tab_dq + code);
-              lg = ((code >> 2) & 3) != (code & 3) ? log(mn * S.q[code]) : 0.0;
+              // log(mu nu_l q_xy) = log(mu nu_l) [per site, tabulated with mu nu_l] + log(q_xy) [64-entry table]: one 16-byte gather
+              // instead of an fp64 log per mutation (a third of this kernel's instructions with site-rate heterogeneity on)
+              const double2 mn = __ldg(S.munu2 + __ldg(f.mut_site + i));
+              dd = mn.x * __ldg(S.tab_dq + code);
+              lg = ((code >> 2) & 3) != (code & 3) ? mn.y + __ldg(S.tab_logq + code) : 0.0;
             }
             R.dm[k] += dd;
             if (R.par[k] >= 0) {     // the root's list ("mutations" above the root) is not part of log G nor of the counts

@@ -28,7 +28,7 @@ struct EvoArgs { double mu[kMaxPartitions]; double q[kMaxPartitions * 16]; };   
 
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kScanThreads) sites_derive_kernel(
     int L, int P, const uint8_t* __restrict__ ref, const uint8_t* __restrict__ part, const double* __restrict__ nu,
-    const __grid_constant__ EvoArgs evo, double* __restrict__ munu, double* __restrict__ cumQ,
+    const __grid_constant__ EvoArgs evo, double* __restrict__ munu, double2* __restrict__ munu2, double* __restrict__ cumQ,
     int32_t* __restrict__ ref_freq, double* __restrict__ cum_nu_ba) {
   __shared__ double s_q[kMaxPartitions * 16];
   __shared__ double s_mu[kMaxPartitions];
@@ -87,6 +87,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kScanThre
         nuv[u] = nu[l]; key[u] = pt * 4 + a;
         const double mn = s_mu[pt] * nuv[u];
         munu[l] = mn;
+        if (munu2 != nullptr) munu2[l] = make_double2(mn, log(mn));      // site-rate heterogeneity: the log of every mutation's rate, once per site
         v[u] = mn * (-s_q[pt * 16 + a * 5]);
 #pragma unroll
         for (int i = 0; i < kMaxPartitions * 4; ++i) cnt[i] += (i == key[u]);
@@ -165,7 +166,7 @@ int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s, bool with_nu_tables) {
   for (int i = 0; i < kMaxPartitions; ++i) evo.mu[i] = s->h.mu[i];
   for (int i = 0; i < kMaxPartitions * 16; ++i) evo.q[i] = s->h.q[i];
   sites_derive_kernel<<<kClusterCtas, kScanThreads, 0, ctx->stream>>>(s->L, s->P, s->d_ref, s->d_part, s->d_nu, evo, s->d_munu,
-                                                           s->d_cumQ, s->d_ref_freq, with_nu_tables ? s->d_cum_nu_ba : nullptr);
+                                                           s->h.nu_uniform ? nullptr : s->d_munu2, s->d_cumQ, s->d_ref_freq, with_nu_tables ? s->d_cum_nu_ba : nullptr);
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "sites_derive_kernel launch");
 }
