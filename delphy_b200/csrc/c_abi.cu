@@ -647,6 +647,7 @@ static int forest_upload_impl(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_
   const int b_tile_tree = slab.reserve(sizeof(int32_t) * tiles);
   const int b_ctile_tree = slab.reserve(sizeof(int32_t) * ctiles);
   const int b_ctiles = slab.reserve(sizeof(CTileDesc) * ctiles);
+  const int b_corder = slab.reserve(sizeof(int32_t) * ctiles);
   const size_t header_bytes = slab.total;
   const int b_node_id = slab.reserve(sizeof(int32_t) * N), b_parent = slab.reserve(sizeof(int32_t) * N);
   const int b_depth = slab.reserve(sizeof(int32_t) * N), b_size = slab.reserve(sizeof(int32_t) * N);
@@ -730,6 +731,7 @@ static int forest_upload_impl(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_
   auto* h_tile_tree = slab.at<int32_t>(hb, b_tile_tree);
   auto* h_ctile_tree = slab.at<int32_t>(hb, b_ctile_tree);
   auto* h_ctiles = slab.at<CTileDesc>(hb, b_ctiles);
+  auto* h_corder = slab.at<int32_t>(hb, b_corder);
   auto* h_raw = tmp.at<RawTreeDev>(hraw, r_raw);
   for (int i = 0; i < num_sites_tables; ++i) { h_sites[i] = sites[i]->h; fo->sites_version[i] = sites[i]->version; }
   std::vector<CopyJob> jobs;
@@ -770,6 +772,15 @@ static int forest_upload_impl(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_
     base += n;
   }
 
+  // launch order of the general log-G tile kernel: full tiles first, every tree's partly filled last tile at the end (fullest
+  // first), so that the last wave of a many-small-trees forest is made of the cheap tiles
+  {
+    int w = 0;
+    for (int j = 0; j < (int)ctiles; ++j) if (h_ctiles[j].n_act == kLgTile) h_corder[w++] = j;
+    const int first_partial = w;
+    for (int j = 0; j < (int)ctiles; ++j) if (h_ctiles[j].n_act != kLgTile) h_corder[w++] = j;
+    std::stable_sort(h_corder + first_partial, h_corder + w, [&](int a, int b) { return h_ctiles[a].n_act > h_ctiles[b].n_act; });
+  }
   cudaError_t ce = cudaMemcpyAsync(dbase, hb, header_bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (ce == cudaSuccess) ce = cudaMemsetAsync(dbase + header_bytes, 0, slab.total - header_bytes, ctx->stream);
   if (ce == cudaSuccess) ce = cudaMemsetAsync(wbase + work.blocks[w_status].off, 0, work.blocks[w_status].bytes, ctx->stream);
@@ -828,6 +839,7 @@ static int forest_upload_impl(dphy_ctx* ctx, int32_t num_trees, const dphy_emat_
   fo->d_tile_part = slab.at<double>(dbase, b_tpart); fo->d_tile_ipart = slab.at<int32_t>(dbase, b_tipart);
   fo->d_tile_flag = slab.at<uint32_t>(dbase, b_tflag); fo->d_tree_done = slab.at<uint32_t>(dbase, b_tdone);
   fo->d_ticket = slab.at<uint32_t>(dbase, b_ticket);
+  fo->d_ctile_order = slab.at<int32_t>(dbase, b_corder);
   fo->d_strad_list = slab.at<int32_t>(dbase, b_strad); fo->d_sd_delta = slab.at<double>(dbase, b_sdd); fo->d_sd_n = slab.at<int32_t>(dbase, b_sdn);
 
   // ---- device side: Euler tour + list ranking -> DFS order; CSR offsets; lists ------------------------------------------

@@ -269,6 +269,7 @@ struct dphy_forest {
   int32_t* d_tile_ipart = nullptr;  // [num_tiles * 17]
   uint32_t* d_tree_done = nullptr;  // [num_trees] tiles finished (for last-tile reduction)
   uint32_t* d_ticket = nullptr;     // [1] dynamic tile ticket
+  const int32_t* d_ctile_order = nullptr;   // [num_ctiles] launch order of the general log-G tile kernel (full tiles first)
   // study-independent tables of the event-scan SPR path (kernels_spr_group2.cuh), built by the first grouped batch on this forest
   int32_t* d_spr_eopen = nullptr; int32_t* d_spr_tnode = nullptr; int32_t* d_spr_ev = nullptr;
   bool evaluated = false;

@@ -727,10 +727,12 @@ int launch_log_G_general(dphy_ctx* ctx, dphy_forest* fo) {
   {
     // resident CTAs per SM (tuning knob DPHY_TILE_OCC = 3 | 4 | 5 | 6)
     static const int tocc = [] { const char* e = getenv("DPHY_TILE_OCC"); return e ? atoi(e) : 4; }();
-    if (tocc == 3) emat_log_G_tile_kernel<3><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);
-    else if (tocc == 5) emat_log_G_tile_kernel<5><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);
-    else if (tocc == 6) emat_log_G_tile_kernel<6><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);
-    else emat_log_G_tile_kernel<4><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, nullptr);
+    static const bool ordered = [] { const char* e = getenv("DPHY_TILE_ORDER"); return !e || atoi(e) != 0; }();
+    const int32_t* order = ordered ? fo->d_ctile_order : nullptr;      // full tiles first, the partly filled ones last
+    if (tocc == 3) emat_log_G_tile_kernel<3><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, order);
+    else if (tocc == 5) emat_log_G_tile_kernel<5><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, order);
+    else if (tocc == 6) emat_log_G_tile_kernel<6><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, order);
+    else emat_log_G_tile_kernel<4><<<fo->h.num_ctiles, kLgThreads, 0, ctx->stream>>>(P, order);
     ctx->launches += 1;
   }
   emat_log_G_tree_kernel<<<fo->h.num_trees, kTreeThreads, 0, ctx->stream>>>(P);
