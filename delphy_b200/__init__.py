@@ -131,11 +131,16 @@ class TreeCounts(C.Structure):
                 ("num_missation_intervals", C.c_int64), ("num_from_states", C.c_int64)]
 
 
+def _bytes_ptr(data: bytes) -> C.c_void_p:
+    """address of a bytes object's buffer (no copy; the caller keeps `data` alive)"""
+    return C.cast(C.c_char_p(data), C.c_void_p)
+
+
 def api_tree_parse(data: bytes) -> dict:
     """dphy_api_tree_parse (host only): the sizes, the root and the reference sequence of a delphy.api.Tree buffer."""
-    buf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data if len(data) else b"\0")
+    data = bytes(data)
     v = ApiTreeView()
-    st = lib().dphy_api_tree_parse(buf, len(data), C.byref(v))
+    st = lib().dphy_api_tree_parse(_bytes_ptr(data) if len(data) else None, len(data), C.byref(v))
     if st != DPHY_OK:
         raise DphyError(st, "malformed delphy.api.Tree buffer")
     ref = np.ctypeslib.as_array(C.cast(v.ref_seq, u8p), shape=(max(v.num_sites, 1),))[:v.num_sites].copy() if v.num_sites else np.zeros(0, np.uint8)
@@ -624,11 +629,16 @@ class Forest:
         DPHY_API_TREE_CHECK_PATHS, the O(nodes x depth) half of the normal-form check)."""
         self = cls.__new__(cls)
         self.ctx = ctx
-        self.emats = [_ApiTreeShape(api_tree_parse(b)["num_nodes"]) for b in buffers]
+        buffers = [bytes(b) for b in buffers]                 # (no copy for bytes; the C side reads them in place)
+        self.emats = []
+        for b in buffers:
+            v = ApiTreeView()
+            if lib().dphy_api_tree_parse(_bytes_ptr(b) if len(b) else None, len(b), C.byref(v)) != DPHY_OK:
+                raise DphyError(ERR_INVALID_ARGUMENT, "api tree: malformed FlatBuffers Tree buffer")
+            self.emats.append(_ApiTreeShape(v.num_nodes))
         self.sites_tables = list(sites_tables)
         n = len(buffers)
-        keep = [(C.c_uint8 * len(b)).from_buffer_copy(b) for b in buffers]
-        bp = (C.c_void_p * n)(*[C.addressof(k) for k in keep])
+        bp = (C.c_void_p * n)(*[_bytes_ptr(b).value for b in buffers])
         lens = (C.c_size_t * n)(*[len(b) for b in buffers])
         idx = np.ascontiguousarray(sites_index if sites_index is not None else np.zeros(n), np.int32)
         self.sites_index = idx
@@ -648,7 +658,7 @@ class Forest:
         got = int(lib().dphy_forest_write_api_tree(self.ctx._h, self._h, tree, (C.c_uint8 * n).from_buffer(buf), n))
         if got < 0:
             self.ctx.check(got)
-        return bytes(memoryview(buf)[:got])
+        return bytes(buf) if got == n else bytes(memoryview(buf)[:got])
 
     def download_tree(self, tree=0) -> "HostEmat":
         """dphy_forest_download_tree: the host-order arrays of a tree as they are resident on the device."""

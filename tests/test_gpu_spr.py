@@ -408,3 +408,49 @@ def test_errors_are_sticky_and_name_the_request(ctx):
             call()
         assert "request 1" in str(ei.value)
     batch.close(); fo.close(); ds.close()
+
+
+def test_batches_in_flight_share_parked_blocks(ctx):
+    """Two batches are in flight at a time: the emit / normalisation passes of one run on the context's tail stream next to the
+    set-up of the next, and the block of a batch destroyed before its tail has finished is parked and handed to a later batch
+    (dphy_ctx::spr_blocks).  Results must not depend on any of it: a batch read after a burst of create / destroy pairs (different
+    requests in between, so a reused block holds another batch's leftovers), after a forest edit that joins the tail, and two batches
+    alive at once, are bit for bit the first batch's."""
+    emat, sites, info = synth(0, seed=77, num_tips=1500)
+    ds = db.DeviceSites(ctx, sites)
+    fo = db.Forest(ctx, [emat], [ds])
+    lam = fo.lambda_i(0)
+    rng = np.random.default_rng(9)
+    nodes = [int(v) for v in rng.permutation(emat.num_nodes) if v != emat.root]
+    reqs_a = db.spr_requests_for_attached(emat, 0, nodes[:40], lam, info["t_max_tip"])
+    reqs_b = db.spr_requests_for_attached(emat, 0, nodes[40:75], lam, info["t_max_tip"])
+
+    def snapshot(reqs):
+        b = fo.spr_study_batch(reqs)
+        out = (b.regions(-1).copy(), [(s.num_regions, s.log_Wmax, s.sum_W_over_Wmax) for s in b.summaries()])
+        b.close()
+        return out
+
+    def same(x, y):
+        assert x[1] == y[1]
+        assert x[0].tobytes() == y[0].tobytes()
+
+    want_a, want_b = snapshot(reqs_a), snapshot(reqs_b)
+    for _ in range(7):                                   # nothing read: every destroy finds its tail pending
+        fo.spr_study_batch(reqs_b).close()
+        fo.spr_study_batch(reqs_a).close()
+    same(snapshot(reqs_a), want_a)
+    same(snapshot(reqs_b), want_b)
+    # two batches alive at once, read in the opposite order of their creation
+    b1, b2 = fo.spr_study_batch(reqs_a), fo.spr_study_batch(reqs_b)
+    got2 = (b2.regions(-1).copy(), [(s.num_regions, s.log_Wmax, s.sum_W_over_Wmax) for s in b2.summaries()])
+    got1 = (b1.regions(-1).copy(), [(s.num_regions, s.log_Wmax, s.sum_W_over_Wmax) for s in b1.summaries()])
+    b1.close(); b2.close()
+    same(got1, want_a); same(got2, want_b)
+    # an edit of the forest right behind an unread batch: set_node_times joins the tail before it touches the times
+    fo.spr_study_batch(reqs_a).close()
+    v = next(x for x in range(emat.num_nodes) if emat.child0[x] >= 0 and x != emat.root)
+    fo.set_node_times(0, [v], [float(emat.t[v])])
+    same(snapshot(reqs_a), want_a)
+    ctx.join_side_streams(); ctx.synchronize()
+    fo.close(); ds.close()
