@@ -455,6 +455,7 @@ extern "C" int dphy_forest_upload_api_trees(dphy_ctx* ctx, int32_t num_trees, co
     char* nb = dalloc(o);
     if (!nb) { free_scratch(); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(api tree arrays)"); }
     cudaMemsetAsync(nb + zero_from, 0, zero_to - zero_from, ctx->stream);
+    cudaMemsetAsync(nb + a_ivo, 0, 4 * (I + 1), ctx->stream);        // a tree without missations: F is read from ivl_off[0]
     RawOut& O = outs[k];
     O.parent = (int32_t*)(nb + a_par); O.child0 = (int32_t*)(nb + a_c0); O.child1 = (int32_t*)(nb + a_c1); O.t = (double*)(nb + a_t);
     O.mut_off = (int32_t*)(nb + a_moff); O.mut_site = (int32_t*)(nb + a_msite); O.mut_from = (uint8_t*)(nb + a_mfrom);
