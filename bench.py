@@ -356,6 +356,18 @@ def reference_arm(db, args, rank):
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if not args.no_partitioned:
         line["partitioned"] = cpu_log_G_partitioned(db, emat, sites, args.cpu_seconds, threads)
+    if not args.no_secondary:
+        # the wire format on the reference's side: its own writer, then its own reader (api_tree_and_tree_info_to_phylo_tree incl.
+        # fix_up_missations), one thread -- what `wire_format.load_ms_per_tree` of our arm replaces
+        ol, to_oracle = _oracle_modules()
+        if ol.ref_available():
+            e, s = to_oracle(emat, sites)
+            t0 = time.perf_counter()
+            buf = ol.api_tree_write(e, s.ref, "ref", s)
+            wr_ms = (time.perf_counter() - t0) * 1e3
+            wf = cpu_api_tree_read(buf)
+            wf.update({"format": "delphy.api.Tree (FlatBuffers; core/api.fbs:13-49)", "buffer_bytes_per_tree": len(buf), "write_ms_per_tree": wr_ms})
+            line["wire_format"] = wf
     if not args.no_mcmc:
         line["mcmc"] = mcmc_figures(db, args, "stock", args.gpus)
     emit_line(line)
