@@ -629,17 +629,21 @@ class Forest:
         DPHY_API_TREE_CHECK_PATHS, the O(nodes x depth) half of the normal-form check)."""
         self = cls.__new__(cls)
         self.ctx = ctx
-        buffers = [bytes(b) for b in buffers]                 # (no copy for bytes; the C side reads them in place)
+        # bytes are read in place (no copy); a uint8 numpy array too -- e.g. one in page-locked memory (Context.host_array_like), which
+        # the library DMAs from where it lies instead of staging it
+        buffers = [b if isinstance(b, np.ndarray) else bytes(b) for b in buffers]
+        ptrs = [b.ctypes.data if isinstance(b, np.ndarray) else _bytes_ptr(b).value for b in buffers]
+        sizes = [b.nbytes if isinstance(b, np.ndarray) else len(b) for b in buffers]
         self.emats = []
-        for b in buffers:
+        for ptr, sz in zip(ptrs, sizes):
             v = ApiTreeView()
-            if lib().dphy_api_tree_parse(_bytes_ptr(b) if len(b) else None, len(b), C.byref(v)) != DPHY_OK:
+            if lib().dphy_api_tree_parse(ptr if sz else None, sz, C.byref(v)) != DPHY_OK:
                 raise DphyError(ERR_INVALID_ARGUMENT, "api tree: malformed FlatBuffers Tree buffer")
             self.emats.append(_ApiTreeShape(v.num_nodes))
         self.sites_tables = list(sites_tables)
         n = len(buffers)
-        bp = (C.c_void_p * n)(*[_bytes_ptr(b).value for b in buffers])
-        lens = (C.c_size_t * n)(*[len(b) for b in buffers])
+        bp = (C.c_void_p * n)(*ptrs)
+        lens = (C.c_size_t * n)(*sizes)
         idx = np.ascontiguousarray(sites_index if sites_index is not None else np.zeros(n), np.int32)
         self.sites_index = idx
         irr = None if includes_run_root is None else np.ascontiguousarray(includes_run_root, np.int32)

@@ -318,6 +318,12 @@ __global__ void apitree_pack_kernel(RawTreeDev R, ApiNode* __restrict__ nodes, A
 
 size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
+bool pinned_host(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;        // (the host parses the table header itself: device memory will not do)
+}
+
 // ---- the host side of the format: follow the table's offsets, nothing else -----------------------------------------------------------------------
 uint32_t rd_u32(const uint8_t* p) { uint32_t v; std::memcpy(&v, p, 4); return v; }      // FlatBuffers is little endian, and so is every CUDA host
 uint16_t rd_u16(const uint8_t* p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
@@ -405,8 +411,10 @@ extern "C" int dphy_forest_upload_api_trees(dphy_ctx* ctx, int32_t num_trees, co
     stage += al256(16 * (size_t)v.num_nodes) + al256(16 * (size_t)v.num_mutations) + al256(12 * (size_t)v.num_missation_intervals) + al256((size_t)v.num_sites);
   }
   // ---- the struct vectors cross PCIe as they lie (one pinned staging pass; nothing is converted on the host) ------------------------------------
+  bool staged_any = false;
+  for (int k = 0; k < num_trees; ++k) staged_any = staged_any || !pinned_host(bufs[k]);
   void* hbv = nullptr;
-  int st = acquire_pinned(ctx, stage, &hbv);
+  int st = staged_any ? acquire_pinned(ctx, stage, &hbv) : DPHY_OK;
   if (st != DPHY_OK) return st;
   char* hb = static_cast<char*>(hbv);
   std::vector<void*> scratch;
@@ -421,21 +429,37 @@ extern "C" int dphy_forest_upload_api_trees(dphy_ctx* ctx, int32_t num_trees, co
   uint32_t* d_status = reinterpret_cast<uint32_t*>(dalloc(256));
   if (!d_in || !d_status) { free_scratch(); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "cudaMallocAsync(api tree)"); }
   std::vector<ApiTreeDev> dev(num_trees);
+  struct DirectCopy { size_t at; const void* src; size_t bytes; };
+  std::vector<DirectCopy> direct_copies;
   {
     size_t o = 0;
     for (int k = 0; k < num_trees; ++k) {
       const dphy_api_tree_view& v = views[k];
       ApiTreeDev& A = dev[k];
       A.n = v.num_nodes; A.M = (int32_t)v.num_mutations; A.I = (int32_t)v.num_missation_intervals; A.L = v.num_sites; A.root = v.root;
-      auto put = [&](const void* src, size_t bytes) { const size_t at = o; if (bytes) std::memcpy(hb + o, src, bytes); o += al256(bytes); return at; };
+      // a buffer in page-locked memory (dphy_host_alloc, or registered by the caller) is DMA'd from where it lies; a pageable one
+      // is staged through the context's pinned slab (one pass of memcpy, the only touch the host gives the data)
+      const bool direct = pinned_host(bufs[k]);
+      auto put = [&](const void* src, size_t bytes) {
+        const size_t at = o;
+        if (bytes) {
+          if (direct) direct_copies.push_back({at, src, bytes});
+          else std::memcpy(hb + o, src, bytes);
+        }
+        o += al256(bytes);
+        return at;
+      };
       A.nodes = reinterpret_cast<const ApiNode*>(d_in + put(v.nodes, 16 * (size_t)A.n));
       A.muts = reinterpret_cast<const ApiMutation*>(d_in + put(v.mutations, 16 * (size_t)A.M));
       A.ivls = reinterpret_cast<const ApiInterval*>(d_in + put(v.missation_intervals, 12 * (size_t)A.I));
       A.ref_seq = reinterpret_cast<const uint8_t*>(d_in + put(v.ref_seq, (size_t)A.L));
     }
   }
-  cudaError_t ce = stage ? cudaMemcpyAsync(d_in, hb, stage, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
-  release_pinned_async(ctx);
+  cudaError_t ce = cudaSuccess;
+  if (stage && staged_any) ce = cudaMemcpyAsync(d_in, hb, stage, cudaMemcpyHostToDevice, ctx->stream);   // (gaps left by direct buffers: garbage, overwritten next)
+  if (staged_any) release_pinned_async(ctx);
+  for (size_t i = 0; i < direct_copies.size() && ce == cudaSuccess; ++i)
+    ce = cudaMemcpyAsync(d_in + direct_copies[i].at, direct_copies[i].src, direct_copies[i].bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (ce == cudaSuccess) ce = cudaMemsetAsync(d_status, 0, 256, ctx->stream);
   if (ce != cudaSuccess) { free_scratch(); return check_cuda(ctx, ce, "H2D api tree"); }
 

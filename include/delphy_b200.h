@@ -254,7 +254,8 @@ typedef struct dphy_api_tree_view {
  * buffer is untrusted).  The view points into `buf`.  DPHY_ERR_INVALID_ARGUMENT for a malformed buffer. */
 int  dphy_api_tree_parse(const void* buf, size_t len, dphy_api_tree_view* out);
 /* api_tree_and_tree_info_to_phylo_tree (core/api.cpp:127-186) + the flattening of dphy_forest_upload, without the AoS Phylo_tree in
- * between: the struct vectors of every buffer are DMA'd as they lie; the struct-of-arrays split, the CSR offsets and the
+ * between: the struct vectors of every buffer are DMA'd as they lie (from where they lie when the buffer is page-locked; through
+ * the context's pinned slab otherwise); the struct-of-arrays split, the CSR offsets and the
  * Missation_map::from_states (which the format does not store; fix_up_missations, core/phylo_tree.cpp:446-459) are computed on the
  * device.  Tree k is loaded against sites[sites_index[k]], whose reference sequence must equal the buffer's ref_seq;
  * includes_run_root may be NULL (all 1).  Times are the format's float32 values widened to double, as in the reference.  The result is

@@ -23,8 +23,11 @@ for cfg, tips in ((4, 100000), (5, 50000)):
             back, _ = ol.api_tree_read(out)
             ok2 = all(np.array_equal(getattr(back, f), getattr(want, f)) for f in ("fs_off", "fs_site", "fs_from", "mut_site", "miss_start", "t"))
         fo.close()
+        pin = ctx.host_array_like(np.frombuffer(data, np.uint8))
+        t0 = time.perf_counter(); fo = db.Forest.from_api_trees(ctx, [pin], [ds]); ctx.synchronize(); t_pin = time.perf_counter() - t0
+        fo.close()
         t0 = time.perf_counter(); fp = db.Forest(ctx, [emat], [ds]); ctx.synchronize(); t_up = time.perf_counter() - t0
         fp.close()
-    print(f"cfg {cfg} tips {tips}: buffer {len(data)/1e6:.1f} MB, F={int(want.fs_off[-1])}; api->device {t_api*1e3:.2f} ms, plain upload {t_up*1e3:.2f} ms, "
+    print(f"cfg {cfg} tips {tips}: buffer {len(data)/1e6:.1f} MB, F={int(want.fs_off[-1])}; api->device {t_api*1e3:.2f} ms ({t_pin*1e3:.2f} ms from a page-locked buffer), plain upload {t_up*1e3:.2f} ms, "
           f"device->api {t_wr*1e3:.2f} ms, oracle CPU reader {t_orc*1e3:.0f} ms; arrays match {ok}, round trip {ok2}")
     ds.close(); ctx.close()
