@@ -129,7 +129,7 @@ def test_parsers_survive_damaged_buffers():
         with pytest.raises(ValueError):
             ol.api_tree_read(data[:cut])
     # random 32-bit words in the header region (size prefix, root offset, vtable, table): either refused, or a view that stays inside
-    for _ in range(300):
+    for _ in range(2000):
         b = bytearray(data)
         at = int(rng.integers(0, len(data) - 4))
         b[at:at + 4] = rng.integers(0, 256, 4, dtype=np.uint8).tobytes()
@@ -137,7 +137,8 @@ def test_parsers_survive_damaged_buffers():
             v = db.api_tree_parse(bytes(b))
         except db.DphyError:
             continue
-        assert 0 <= v["num_nodes"] and 16 * v["num_nodes"] + 16 * v["num_mutations"] + 12 * v["num_missation_intervals"] + v["num_sites"] <= len(data)
+        # every vector lies inside the buffer (a damaged table may make two of them overlap: still memory-safe)
+        assert 0 <= v["num_nodes"] and max(16 * v["num_nodes"], 16 * v["num_mutations"], 12 * v["num_missation_intervals"], v["num_sites"]) <= len(data)
         try:
             ol.api_tree_read(bytes(b))
         except ValueError:
