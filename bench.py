@@ -499,8 +499,8 @@ def main():
     mus = [t.host.mu.copy() for t in tables]
 
     def model_change_cycle(i):
-        for k, t in enumerate(tables):
-            t.set_evo(mu=mus[k] * (1.0 + 1e-3 * ((i % 7) + 1)))
+        # Run::push_global_params_to_subruns (core/run.cpp:267-275): the new model goes to every chain's table -- one launch for all
+        db.sites_set_evo_many(ctx, tables, mus=[mus[k] * (1.0 + 1e-3 * ((i % 7) + 1)) for k in range(len(tables))])
         forest.eval_log_G()
         return forest.log_G()
     for i in range(2):
@@ -742,7 +742,7 @@ def main():
                                         "traffic": measured_traffic("emat_log_G_tile_kernel", args.config, args.chains),
                                         "note": "every mutation / missation / from-state list re-read per evaluation (also refreshes nsmn and the num_muts tallies)"},
             "model_change_cycle": {"value": args.chains * mc_steps * world / mc_s, "unit": UNIT, "ms_per_cycle": mc_s / mc_steps * 1e3,
-                                   "note": "dphy_sites_set_evo(new mu) on every chain's site table + evaluation of every chain + log G read back, wall clock"},
+                                   "note": "dphy_sites_set_evo_many(new mu on every chain's site table, one launch) + evaluation of every chain + log G read back, wall clock"},
             "spr_candidates_per_s": (spr_regions * world / (spr_ms_max * 1e-3)) if spr_ms else None,
             "spr_regions_per_batch": spr_regions, "spr_ms_per_batch": spr_ms_max if spr_ms else None,
             "e2e": {"value": n_e2e * e2e_steps * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -239,6 +239,7 @@ def lib() -> C.CDLL:
     L.dphy_sites_upload.argtypes = [vp, C.POINTER(SitesHost), C.POINTER(vp)]
     L.dphy_sites_destroy.argtypes = [vp, vp]
     L.dphy_sites_set_evo.argtypes = [vp, vp, f64p, f64p, f64p, f64p]
+    L.dphy_sites_set_evo_many.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(f64p), C.POINTER(f64p), C.POINTER(f64p)]
     L.dphy_calc_state_frequencies_per_partition.argtypes = [vp, vp, i32p]
     L.dphy_calc_cum_Q_l.argtypes = [vp, vp, f64p]
     L.dphy_forest_upload.argtypes = [vp, C.c_int32, C.POINTER(EmatHost), i32p, C.c_int32, C.POINTER(vp), C.POINTER(vp)]
@@ -606,6 +607,25 @@ class DeviceSites:
         if self._h:
             lib().dphy_sites_destroy(self.ctx._h, self._h)
             self._h = C.c_void_p()
+
+
+def sites_set_evo_many(ctx: Context, tables, mus=None, pis=None, qs=None):
+    """dphy_sites_set_evo_many: new mu / pi / q (site rates kept) on several tables in one launch -- Run::push_global_params_to_subruns
+    (core/run.cpp:267-275).  mus / pis / qs: one entry per table, or None to keep what the table has."""
+    n = len(tables)
+    for k, t in enumerate(tables):
+        h = t.host
+        if mus is not None and mus[k] is not None:
+            h.mu = np.ascontiguousarray(mus[k], np.float64).reshape(-1)
+        if pis is not None and pis[k] is not None:
+            h.pi_a = np.ascontiguousarray(pis[k], np.float64).reshape(-1, 4)
+        if qs is not None and qs[k] is not None:
+            h.q_ab = np.ascontiguousarray(qs[k], np.float64).reshape(-1, 4, 4)
+    hp = (C.c_void_p * max(n, 1))(*[t._h for t in tables])
+    pm = (f64p * max(n, 1))(*[_p(t.host.mu, f64p) for t in tables])
+    pp = (f64p * max(n, 1))(*[_p(t.host.pi_a, f64p) for t in tables])
+    pq = (f64p * max(n, 1))(*[_p(t.host.q_ab, f64p) for t in tables])
+    ctx.check(lib().dphy_sites_set_evo_many(ctx._h, n, hp, pm, pp, pq))
 
 
 class Forest:

@@ -374,6 +374,25 @@ int dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* s, const double* nu_l, const d
   return launch_sites_derive(ctx, s, /*with_nu_tables=*/nu_l != nullptr);
 }
 
+int dphy_sites_set_evo_many(dphy_ctx* ctx, int32_t n, dphy_sites* const* tables, const double* const* mu, const double* const* pi_a,
+                            const double* const* q_ab) {
+  if (!ctx || n < 0 || (n > 0 && (!tables || !mu || !pi_a || !q_ab))) return DPHY_ERR_INVALID_ARGUMENT;
+  // validate everything before anything is committed
+  for (int k = 0; k < n; ++k) {
+    if (!tables[k] || !mu[k] || !pi_a[k] || !q_ab[k]) return DPHY_ERR_INVALID_ARGUMENT;
+    for (int j = 0; j < k; ++j) if (tables[j] == tables[k]) return set_error(ctx, DPHY_ERR_INVALID_ARGUMENT, "set_evo_many: a table is listed twice");
+    const int st = validate_evo(ctx, tables[k]->P, tables[k]->L, nullptr, mu[k], pi_a[k], q_ab[k]);
+    if (st != DPHY_OK) return st;
+  }
+  cudaSetDevice(ctx->device);
+  for (int k = 0; k < n; ++k) {
+    fill_evo(tables[k], mu[k], pi_a[k], q_ab[k]);
+    fill_tables(tables[k]);
+    tables[k]->version += 1;
+  }
+  return launch_sites_derive_many(ctx, tables, n);
+}
+
 int dphy_calc_state_frequencies_per_partition(dphy_ctx* ctx, dphy_sites* s, int32_t* out) {
   if (!ctx || !s || !out) return DPHY_ERR_INVALID_ARGUMENT;
   DPHY_CUDA(ctx, cudaMemcpyAsync(out, s->d_ref_freq, sizeof(int32_t) * s->P * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -298,6 +298,7 @@ int check_cuda(dphy_ctx* ctx, cudaError_t e, const char* what);
 // kernels_sites.cu
 int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s, bool with_nu_tables = true);
 int launch_sites_ref_counts(dphy_ctx* ctx, dphy_sites* s);
+int launch_sites_derive_many(dphy_ctx* ctx, dphy_sites* const* tables, int n);
 // kernels_logg.cu
 int launch_log_G(dphy_ctx* ctx, dphy_forest* f);            // picks the path (ctx->logg_path, site tables, struct_valid)
 int launch_log_G_general(dphy_ctx* ctx, dphy_forest* f);    // every output incl. nsmn and the num_muts tallies

@@ -26,9 +26,9 @@ constexpr int kSitesPerThread = 4;
 constexpr int kClusterCtas = 8;
 struct EvoArgs { double mu[kMaxPartitions]; double q[kMaxPartitions * 16]; };   // passed by value: no staging copies
 
-__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kScanThreads) sites_derive_kernel(
+__device__ __forceinline__ void sites_derive_body(
     int L, int P, const uint8_t* __restrict__ ref, const uint8_t* __restrict__ part, const double* __restrict__ nu,
-    const __grid_constant__ EvoArgs evo, double* __restrict__ munu, double2* __restrict__ munu2, double* __restrict__ cumQ,
+    const EvoArgs& evo, double* __restrict__ munu, double2* __restrict__ munu2, double* __restrict__ cumQ,
     int32_t* __restrict__ ref_freq, double* __restrict__ cum_nu_ba) {
   __shared__ double s_q[kMaxPartitions * 16];
   __shared__ double s_mu[kMaxPartitions];
@@ -131,6 +131,27 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kScanThre
   if (rank == 0 && tid < P * 4) ref_freq[tid] = s_freq[tid];
 }
 
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kScanThreads) sites_derive_kernel(
+    int L, int P, const uint8_t* __restrict__ ref, const uint8_t* __restrict__ part, const double* __restrict__ nu,
+    const __grid_constant__ EvoArgs evo, double* __restrict__ munu, double2* __restrict__ munu2, double* __restrict__ cumQ,
+    int32_t* __restrict__ ref_freq, double* __restrict__ cum_nu_ba) {
+  sites_derive_body(L, P, ref, part, nu, evo, munu, munu2, cumQ, ref_freq, cum_nu_ba);
+}
+
+// The same for MANY tables in one launch: cluster c derives table c.  What Run::push_global_params_to_subruns does once per cycle
+// (core/run.cpp:267-275: the new mu / pi / q go to every subrun's evo model): sixteen 13-us launches of one cluster each leave
+// 140 of the 148 SMs idle sixteen times over.
+struct DeriveArgs {
+  int32_t L, P;
+  const uint8_t* ref; const uint8_t* part; const double* nu;
+  double* munu; double2* munu2; double* cumQ; int32_t* ref_freq; double* cum_nu_ba;
+  EvoArgs evo;
+};
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kScanThreads) sites_derive_many_kernel(const DeriveArgs* __restrict__ args) {
+  const DeriveArgs& a = args[blockIdx.x / kClusterCtas];
+  sites_derive_body(a.L, a.P, a.ref, a.part, a.nu, a.evo, a.munu, a.munu2, a.cumQ, a.ref_freq, a.cum_nu_ba);
+}
+
 // Cumulative reference-state counts per (partition, state), interleaved by site:
 // cref[l*(4P) + b*4+a] = #{l' < l : beta(l') == b, ref[l'] == a}  (one 16-byte look-up per partition and interval end).
 // Structure only (reference sequence + partition map), so it is built once per sites table.  One CTA per (b, a) row.
@@ -169,6 +190,35 @@ int launch_sites_derive(dphy_ctx* ctx, dphy_sites* s, bool with_nu_tables) {
                                                            s->h.nu_uniform ? nullptr : s->d_munu2, s->d_cumQ, s->d_ref_freq, with_nu_tables ? s->d_cum_nu_ba : nullptr);
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "sites_derive_kernel launch");
+}
+
+// mu / pi / q changed on every table of `tables` (site rates untouched): one launch, one cluster per table
+int launch_sites_derive_many(dphy_ctx* ctx, dphy_sites* const* tables, int n) {
+  if (n <= 0) return DPHY_OK;
+  void* hbv = nullptr;
+  int st = acquire_pinned(ctx, sizeof(DeriveArgs) * (size_t)n, &hbv);
+  if (st != DPHY_OK) return st;
+  DeriveArgs* h = static_cast<DeriveArgs*>(hbv);
+  for (int k = 0; k < n; ++k) {
+    dphy_sites* s = tables[k];
+    DeriveArgs& a = h[k];
+    a.L = s->L; a.P = s->P; a.ref = s->d_ref; a.part = s->d_part; a.nu = s->d_nu;
+    a.munu = s->d_munu; a.munu2 = s->h.nu_uniform ? nullptr : s->d_munu2; a.cumQ = s->d_cumQ; a.ref_freq = s->d_ref_freq; a.cum_nu_ba = nullptr;
+    for (int i = 0; i < kMaxPartitions; ++i) a.evo.mu[i] = s->h.mu[i];
+    for (int i = 0; i < kMaxPartitions * 16; ++i) a.evo.q[i] = s->h.q[i];
+  }
+  const size_t mark = ctx->arena.mark();
+  DeriveArgs* d = static_cast<DeriveArgs*>(ctx->arena.alloc(sizeof(DeriveArgs) * (size_t)n));
+  if (!d) { ctx->arena.release(mark); return set_error(ctx, DPHY_ERR_OUT_OF_MEMORY, "arena exhausted (set_evo_many)"); }
+  cudaError_t ce = cudaMemcpyAsync(d, h, sizeof(DeriveArgs) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+  release_pinned_async(ctx);
+  if (ce == cudaSuccess) {
+    sites_derive_many_kernel<<<kClusterCtas * n, kScanThreads, 0, ctx->stream>>>(d);
+    ctx->launches += 1;
+    ce = cudaGetLastError();
+  }
+  ctx->arena.release(mark);      // (the next user of the arena enqueues behind this launch on the same stream)
+  return check_cuda(ctx, ce, "sites_derive_many_kernel launch");
 }
 
 }  // namespace dphy

@@ -191,6 +191,11 @@ void dphy_sites_destroy(dphy_ctx* ctx, dphy_sites* sites);
  * rates (the cumulative-nu tables are then not rebuilt).  Asynchronous: consumers are ordered after it on the ctx's stream. */
 int  dphy_sites_set_evo(dphy_ctx* ctx, dphy_sites* sites, const double* nu_l, const double* mu,
                         const double* pi_a, const double* q_ab);
+/* dphy_sites_set_evo (site rates kept) on `n` different tables in ONE launch: what Run::push_global_params_to_subruns does once per
+ * cycle -- the new mu / pi / q go to every subrun's evo model (core/run.cpp:267-275).  mu[k] / pi_a[k] / q_ab[k] are table k's
+ * arrays ([P_k], [P_k][4], [P_k][4][4]).  Everything is validated before anything is committed.  Asynchronous. */
+int  dphy_sites_set_evo_many(dphy_ctx* ctx, int32_t n, dphy_sites* const* tables, const double* const* mu, const double* const* pi_a,
+                             const double* const* q_ab);
 /* Replace the reference sequence, the site partitioning and the whole model of an existing table in place (same number of sites
  * and partitions): what Run::normalize_root -> rereference_to_root_sequence does to every subrun's tables once per cycle
  * (core/run.cpp:258-265, core/phylo_tree.cpp:299-312).  No allocation; every derived table is rebuilt on the device.

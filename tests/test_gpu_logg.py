@@ -418,3 +418,49 @@ def test_site_tallies_are_bit_reproducible(ctx):
     st = fo.site_tallies()
     assert np.array_equal(st[0][0], first[0])
     fo.close(); fo2.close(); ds.close(); dso.close()
+
+
+def test_set_evo_on_many_tables_in_one_launch(ctx, orc):
+    """dphy_sites_set_evo_many (Run::push_global_params_to_subruns, core/run.cpp:267-275) == dphy_sites_set_evo table by table: the
+    derived tables bit for bit, and log G of a forest over them; P = 1 and P = 2 tables, uniform and varying site rates, in one call."""
+    items = [synth(0, seed=3, num_tips=300), synth(2, seed=4, num_tips=200), synth(5, seed=5, num_tips=150), synth(0, seed=6, num_tips=120)]
+    many = [db.DeviceSites(ctx, it[1]) for it in items]
+    single = [db.DeviceSites(ctx, it[1]) for it in items]
+    fa = db.Forest(ctx, [it[0] for it in items], many, sites_index=np.arange(len(items)))
+    fb = db.Forest(ctx, [it[0] for it in items], single, sites_index=np.arange(len(items)))
+    try:
+        for rnd in range(3):
+            mus = [it[1].mu * (1.0 + 0.07 * (rnd + 1) + 0.01 * k) for k, it in enumerate(items)]
+            qs = None
+            if rnd == 1:          # another rate matrix too (rows still sum to zero)
+                qs = []
+                for it in items:
+                    q = it[1].q_ab.reshape(-1, 4, 4).copy()
+                    q[:, 0, 1] *= 1.5; q[:, 0, 0] = 0.0; q[:, 0, 0] = -q[:, 0, :].sum(axis=1)
+                    qs.append(q)
+            db.sites_set_evo_many(ctx, many, mus=mus, qs=qs)
+            for k, t in enumerate(single):
+                t.set_evo(mu=mus[k], q_ab=None if qs is None else qs[k])
+            for a, b in zip(many, single):
+                np.testing.assert_array_equal(a.cum_Q_l(), b.cum_Q_l())
+                np.testing.assert_array_equal(a.state_frequencies(), b.state_frequencies())
+            fa.eval_log_G(); fb.eval_log_G()
+            for x, y in zip(fa.log_G(), fb.log_G()):
+                np.testing.assert_array_equal(x, y)
+            for k in range(len(items)):
+                np.testing.assert_array_equal(fa.lambda_i(k), fb.lambda_i(k))
+        # and against the oracle once
+        e, s = to_oracle(items[1][0], many[1].host)
+        lam = orc.lambda_i(e, s, orc.cum_Q_l(s))
+        assert fa.log_G()[1][1] == pytest.approx(orc.log_G_below_root(e, s, lam), rel=RTOL)
+        # a bad entry anywhere: nothing is committed
+        before = many[0].cum_Q_l()
+        with pytest.raises(db.DphyError):
+            db.sites_set_evo_many(ctx, many, mus=[it[1].mu for it in items[:-1]] + [np.array([-1.0] * items[-1][1].num_partitions)])
+        for t, it in zip(many, items):      # (the wrapper's mirror was updated before the call: put it back)
+            t.host.mu = it[1].mu.copy()
+        np.testing.assert_array_equal(many[0].cum_Q_l(), before)
+    finally:
+        fa.close(); fb.close()
+        for t in many + single:
+            t.close()
