@@ -261,6 +261,8 @@ extern "C" int dphy_forest_apply_rows(dphy_ctx* ctx, dphy_forest* fo, int32_t co
   cudaMemsetAsync(d_links, 0, sizeof(uint32_t), ctx->stream);
   bool root_changed = false;
   int row0 = 0;
+  struct TreeJob { RawTreeDev R; RawTreeOut out; int32_t* row_of; int32_t* tt; int n, ntiles, row0, nrows; };
+  std::vector<TreeJob> jobs;        // the edited trees: blocks allocated first (main stream), kernels launched after the fork below
   for (int k = 0; k < nt; ++k) {
     const RawTreeDev& R = fo->raw[k];
     if (new_roots && new_roots[k] != R.root) root_changed = true;
@@ -303,17 +305,45 @@ extern "C" int dphy_forest_apply_rows(dphy_ctx* ctx, dphy_forest* fo, int32_t co
     out.miss_off = (int32_t*)(nb + a_ioff); out.miss_start = (int32_t*)(nb + a_is); out.miss_end = (int32_t*)(nb + a_ie);
     out.fs_off = (int32_t*)(nb + a_foff); out.fs_site = (int32_t*)(nb + a_fsite); out.fs_from = (uint8_t*)(nb + a_ffrom);
     int32_t* row_of = (int32_t*)(nb + a_map);
-    delta_mark_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(row_of, n, P.rows, row0, row0 + nrows);
-    delta_mark_rows_kernel<<<(nrows + 255) / 256, 256, 0, ctx->stream>>>(row_of, P.rows, row0, row0 + nrows, R, d_links);
-    delta_offsets_kernel<<<dim3(ntiles, 3), 1024, 0, ctx->stream>>>(R, out, row_of, P.rows, (int32_t*)(nb + a_tt));
-    delta_offsets_fix_kernel<<<dim3(ntiles, 3), 1024, 0, ctx->stream>>>(out, n, (const int32_t*)(nb + a_tt));
-    delta_gather_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(R, out, row_of, P);
-    ctx->launches += 5;
+    jobs.push_back({R, out, row_of, (int32_t*)(nb + a_tt), n, ntiles, row0, nrows});
     row0 += nrows;
     e.parent = out.parent; e.child0 = out.child0; e.child1 = out.child1; e.t = out.t;
     e.mut_off = out.mut_off; e.mut_site = out.mut_site; e.mut_from = out.mut_from; e.mut_to = out.mut_to; e.mut_t = out.mut_t;
     e.miss_off = out.miss_off; e.miss_start = out.miss_start; e.miss_end = out.miss_end;
     e.fs_off = out.fs_off; e.fs_site = out.fs_site; e.fs_from = out.fs_from;
+  }
+  // Every edited tree's sequence is five small kernels (25 - 800 CTAs each): tree j runs on side stream j % 4, forked after the
+  // allocations and the payload upload on the main stream, joined before the re-flatten (DPHY_DELTA_STREAMS=0: all on the main stream)
+  {
+    constexpr int kS = dphy_ctx::kTallyStreams;
+    static const bool side = [] { const char* e = getenv("DPHY_DELTA_STREAMS"); return !e || atoi(e) != 0; }();
+    cudaStream_t main_stream = ctx->stream;
+    bool forked = false;
+    if (side && jobs.size() > 1) {
+      bool ok = true;
+      for (int i = 0; i < kS && ok; ++i) {
+        if (!ctx->tally_streams[i]) ok = cudaStreamCreateWithFlags(&ctx->tally_streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+                                         cudaEventCreateWithFlags(&ctx->ev_tally[i], cudaEventDisableTiming) == cudaSuccess;
+      }
+      if (ok && !ctx->ev_fork) ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+      if (ok) {
+        cudaEventRecord(ctx->ev_fork, main_stream);
+        for (int i = 0; i < kS; ++i) cudaStreamWaitEvent(ctx->tally_streams[i], ctx->ev_fork, 0);
+        forked = true;
+      } else cudaGetLastError();
+    }
+    for (size_t j = 0; j < jobs.size(); ++j) {
+      const TreeJob& J = jobs[j];
+      cudaStream_t s = forked ? ctx->tally_streams[j % kS] : main_stream;
+      delta_mark_kernel<<<(J.n + 255) / 256, 256, 0, s>>>(J.row_of, J.n, P.rows, J.row0, J.row0 + J.nrows);
+      delta_mark_rows_kernel<<<(J.nrows + 255) / 256, 256, 0, s>>>(J.row_of, P.rows, J.row0, J.row0 + J.nrows, J.R, d_links);
+      delta_offsets_kernel<<<dim3(J.ntiles, 3), 1024, 0, s>>>(J.R, J.out, J.row_of, P.rows, J.tt);
+      delta_offsets_fix_kernel<<<dim3(J.ntiles, 3), 1024, 0, s>>>(J.out, J.n, J.tt);
+      delta_gather_kernel<<<(J.n + 255) / 256, 256, 0, s>>>(J.R, J.out, J.row_of, P);
+      ctx->launches += 5;
+    }
+    if (forked)
+      for (int i = 0; i < kS; ++i) { cudaEventRecord(ctx->ev_tally[i], ctx->tally_streams[i]); cudaStreamWaitEvent(main_stream, ctx->ev_tally[i], 0); }
   }
   st = check_cuda(ctx, cudaGetLastError(), "apply_rows kernels");
   uint32_t links = 1u;
