@@ -148,6 +148,37 @@ def api_tree_parse(data: bytes) -> dict:
                 num_missation_intervals=int(v.num_missation_intervals), ref_seq=ref)
 
 
+class MapleView(C.Structure):
+    _fields_ = [("num_sites", C.c_int32), ("num_tips", C.c_int32), ("num_warnings", C.c_int64),
+                ("ref", u8p), ("t_min", f64p), ("t_max", f64p), ("name_off", C.POINTER(C.c_int64)), ("names", C.c_void_p),
+                ("delta_off", i32p), ("delta_site", i32p), ("delta_from", u8p), ("delta_to", u8p),
+                ("miss_off", i32p), ("miss_start", i32p), ("miss_end", i32p)]
+
+
+def maple_parse(text: bytes) -> dict:
+    """dphy_maple_parse (host only): read_maple (core/io.cpp:98-254) straight to CSR arrays.  Raises DphyError where the reference throws."""
+    text = bytes(text)
+    h = C.c_void_p()
+    st = lib().dphy_maple_parse(text, len(text), C.byref(h))
+    if st != DPHY_OK:
+        raise DphyError(st, lib().dphy_maple_last_error().decode(errors="replace"))
+    try:
+        v = MapleView()
+        lib().dphy_maple_get(h, C.byref(v))
+        n, L = v.num_tips, v.num_sites
+        name_off = _np_from(v.name_off, n + 1, np.int64)
+        names_raw = C.string_at(v.names, int(name_off[-1])) if n and name_off[-1] else b""
+        delta_off = _np_from(v.delta_off, n + 1, np.int32); miss_off = _np_from(v.miss_off, n + 1, np.int32)
+        D, I = int(delta_off[-1]), int(miss_off[-1])
+        return dict(num_warnings=int(v.num_warnings), ref=_np_from(v.ref, L, np.uint8), t_min=_np_from(v.t_min, n, np.float64),
+                    t_max=_np_from(v.t_max, n, np.float64), names=[names_raw[name_off[k]:name_off[k + 1]] for k in range(n)],
+                    delta_off=delta_off, delta_site=_np_from(v.delta_site, D, np.int32), delta_from=_np_from(v.delta_from, D, np.uint8),
+                    delta_to=_np_from(v.delta_to, D, np.uint8), miss_off=miss_off, miss_start=_np_from(v.miss_start, I, np.int32),
+                    miss_end=_np_from(v.miss_end, I, np.int32))
+    finally:
+        lib().dphy_maple_free(h)
+
+
 class _ApiTreeShape:
     def __init__(self, num_nodes):
         self.num_nodes = num_nodes
@@ -281,6 +312,10 @@ def lib() -> C.CDLL:
     L.dphy_forest_write_api_tree.argtypes = [vp, vp, C.c_int32, vp, C.c_size_t]; L.dphy_forest_write_api_tree.restype = C.c_int64
     L.dphy_forest_tree_counts.argtypes = [vp, vp, C.c_int32, C.POINTER(TreeCounts)]
     L.dphy_forest_download_tree.argtypes = [vp, vp, C.c_int32, C.POINTER(EmatHost)]
+    L.dphy_maple_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp)]
+    L.dphy_maple_get.argtypes = [vp, C.POINTER(MapleView)]
+    L.dphy_maple_free.argtypes = [vp]; L.dphy_maple_free.restype = None
+    L.dphy_maple_last_error.restype = C.c_char_p
     _bind_partition(L)
     _LIB = L
     return L

@@ -290,6 +290,32 @@ typedef struct dphy_tree_counts {
 int  dphy_forest_tree_counts(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, dphy_tree_counts* out);
 int  dphy_forest_download_tree(dphy_ctx* ctx, dphy_forest* forest, int32_t tree, dphy_emat_host* out);
 
+/* ---- MAPLE input (host only) ------------------------------------------------------------------------------------------------------
+ * read_maple (core/io.cpp:98-254): a MAPLE alignment -- reference sequence + per-sample differences -- parsed in one pass over the
+ * text into CSR arrays in the shape the SPR studies of a sequence that is not in the tree yet take (dphy_spr_request with
+ * DPHY_SPR_X_REL_REF: x_delta_site / x_delta_to and x_missing_start / x_missing_end of sample k are the slices
+ * [delta_off[k], delta_off[k+1]) and [miss_off[k], miss_off[k+1]) below), i.e. what build_usher_like_tree feeds them tip by tip
+ * (core/phylo_tree.cpp:918-932) without the vector<Tip_desc> in between.  Same tolerances and same dropped samples as the reference
+ * (see maple.cpp).  DPHY_ERR_INVALID_ARGUMENT where read_maple throws; dphy_maple_last_error() then holds the message (per thread). */
+typedef struct dphy_maple dphy_maple;
+typedef struct dphy_maple_view {
+  int32_t num_sites, num_tips;
+  int64_t num_warnings;               /* calls the reference would have made to its warning hook (dropped samples, bad lines) */
+  const uint8_t* ref;                 /* [num_sites] A=0 C=1 G=2 T=3; ambiguous reference letters read as A */
+  const double* t_min;                /* [num_tips] Tip_desc::t_min / t_max (float precision), days since 2020-01-01 */
+  const double* t_max;
+  const int64_t* name_off;            /* [num_tips + 1] into names (not NUL-terminated) */
+  const char* names;
+  const int32_t* delta_off;           /* [num_tips + 1] Tip_desc::seq_deltas, file order */
+  const int32_t* delta_site; const uint8_t* delta_from; const uint8_t* delta_to;
+  const int32_t* miss_off;            /* [num_tips + 1] Tip_desc::missations.intervals: ascending, merged */
+  const int32_t* miss_start; const int32_t* miss_end;
+} dphy_maple_view;
+int  dphy_maple_parse(const char* text, size_t len, dphy_maple** out);
+int  dphy_maple_get(const dphy_maple* m, dphy_maple_view* out);      /* pointers stay valid until dphy_maple_free */
+void dphy_maple_free(dphy_maple* m);
+const char* dphy_maple_last_error(void);
+
 /* ---- log G ------------------------------------------------------------------------------------------- */
 /* One launch evaluates, for EVERY tree of the forest: calc_lambda_i (core/phylo_tree_calc.cpp:420-436),
  * calc_num_sites_missing_at_every_node (:67-76), calc_log_root_prior (:467-504) and calc_log_G_below_root

@@ -18,11 +18,20 @@
 #include "evo_model.h"
 #include "tree_partitioning.h"
 #include "api.h"
+#include "io.h"
+#include <sstream>
 #include <random>
 
 #include "emat_oracle.h"
 
 using namespace delphy;
+
+// core/io.cpp reads these two globals of core/cmdline.cpp (the CLI's own argv); defined here so that linking read_maple does not drag
+// the flag parser -- and the static initializers of its regex-based option library -- into a library loaded by a Python process
+namespace delphy {
+bool delphy_invoked_via_cli{false};
+std::vector<std::string> delphy_cli_args{};
+}
 
 namespace {
 
@@ -445,6 +454,44 @@ int32_t ref_api_tree_read(const uint8_t* buf, int32_t* counts, int32_t* parent, 
   }
   mut_off[n] = m; miss_off[n] = i; fs_off[n] = f;
   for (auto l = 0; l != std::ssize(tree.ref_sequence); ++l) { ref_out[l] = static_cast<uint8_t>(tree.ref_sequence[l]); }
+  return 0;
+}
+
+// ---- MAPLE input (core/io.cpp:98-254) ----------------------------------------------------------------------------------------------
+// read_maple on `text`.  Two calls: with ref_out == NULL only counts[6] = {L, num_tips, total deltas, total intervals, total name
+// bytes, number of warnings} is filled; with the arrays (sized from the first call) everything.  Returns 0, or -1 if read_maple throws.
+int32_t ref_maple_read(const char* text, int64_t len, int64_t* counts, uint8_t* ref_out, double* t_min, double* t_max,
+                       int64_t* name_off, char* names, int32_t* delta_off, int32_t* delta_site, uint8_t* delta_from, uint8_t* delta_to,
+                       int32_t* miss_off, int32_t* miss_start, int32_t* miss_end) {
+  auto scope = Local_arena_scope{};
+  auto is = std::istringstream{std::string(text, static_cast<size_t>(len))};
+  auto num_warnings = int64_t{0};
+  auto mf = Maple_file{};
+  try {
+    mf = read_maple(is, [](int, std::size_t) {}, [&](const std::string&, const Sequence_warning&) { ++num_warnings; });
+  } catch (const std::exception&) {
+    return -1;
+  }
+  auto nd = int64_t{0}, ni = int64_t{0}, nb = int64_t{0};
+  for (const auto& tip : mf.tip_descs) {
+    nd += std::ssize(tip.seq_deltas); ni += tip.missations.intervals.num_intervals(); nb += std::ssize(tip.name);
+  }
+  counts[0] = std::ssize(mf.ref_sequence); counts[1] = std::ssize(mf.tip_descs); counts[2] = nd; counts[3] = ni; counts[4] = nb;
+  counts[5] = num_warnings;
+  if (!ref_out) return 0;
+  for (auto l = 0; l != std::ssize(mf.ref_sequence); ++l) { ref_out[l] = static_cast<uint8_t>(mf.ref_sequence[l]); }
+  auto d = 0, i = 0; auto b = int64_t{0};
+  for (auto k = 0; k != std::ssize(mf.tip_descs); ++k) {
+    const auto& tip = mf.tip_descs[k];
+    t_min[k] = tip.t_min; t_max[k] = tip.t_max;
+    name_off[k] = b; std::memcpy(names + b, tip.name.data(), tip.name.size()); b += std::ssize(tip.name);
+    delta_off[k] = d; miss_off[k] = i;
+    for (const auto& sd : tip.seq_deltas) {
+      delta_site[d] = sd.site; delta_from[d] = static_cast<uint8_t>(sd.from); delta_to[d] = static_cast<uint8_t>(sd.to); ++d;
+    }
+    for (const auto& [a, e] : tip.missations.intervals) { miss_start[i] = a; miss_end[i] = e; ++i; }
+  }
+  name_off[mf.tip_descs.size()] = b; delta_off[mf.tip_descs.size()] = d; miss_off[mf.tip_descs.size()] = i;
   return 0;
 }
 

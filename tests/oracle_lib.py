@@ -245,6 +245,27 @@ def api_tree_read(data: bytes, impl: str = "oracle"):
     return _emat_from_arrays(counts, arrs), ref_seq
 
 
+def ref_maple_read(text: bytes):
+    """read_maple (core/io.cpp:98-254) of the compiled reference -> the dict delphy_b200.maple_parse returns, or None where it throws."""
+    lib = ref()
+    counts = np.zeros(6, np.int64)
+    i64p = C.POINTER(C.c_int64)
+    nul = [None] * 12
+    if lib.ref_maple_read(text, len(text), _p(counts, i64p), *nul) != 0:
+        return None
+    L, n, D, I, B, W = (int(c) for c in counts)
+    ref_seq = np.zeros(max(L, 1), np.uint8); t_min = np.zeros(max(n, 1)); t_max = np.zeros(max(n, 1))
+    name_off = np.zeros(n + 1, np.int64); names = C.create_string_buffer(max(B, 1))
+    d_off = np.zeros(n + 1, np.int32); d_site = np.zeros(max(D, 1), np.int32); d_from = np.zeros(max(D, 1), np.uint8); d_to = np.zeros(max(D, 1), np.uint8)
+    m_off = np.zeros(n + 1, np.int32); m_s = np.zeros(max(I, 1), np.int32); m_e = np.zeros(max(I, 1), np.int32)
+    rc = lib.ref_maple_read(text, len(text), _p(counts, i64p), _p(ref_seq, u8p), _p(t_min, f64p), _p(t_max, f64p), _p(name_off, i64p), names,
+                            _p(d_off, i32p), _p(d_site, i32p), _p(d_from, u8p), _p(d_to, u8p), _p(m_off, i32p), _p(m_s, i32p), _p(m_e, i32p))
+    assert rc == 0
+    raw = names.raw[:B]
+    return dict(num_warnings=W, ref=ref_seq[:L], t_min=t_min[:n], t_max=t_max[:n], names=[raw[name_off[k]:name_off[k + 1]] for k in range(n)],
+                delta_off=d_off, delta_site=d_site[:D], delta_from=d_from[:D], delta_to=d_to[:D], miss_off=m_off, miss_start=m_s[:I], miss_end=m_e[:I])
+
+
 # ------------------------------------------------------------------------------------------------
 def _build(target: str):
     subprocess.run(["make", "-s", "-C", ORACLE_DIR, target], check=True, capture_output=True)
@@ -349,6 +370,9 @@ def ref() -> C.CDLL:
         lib.ref_bench_spr.restype = C.c_double
         lib.ref_api_tree_write.argtypes = [E, S, C.c_void_p, C.c_int64]; lib.ref_api_tree_write.restype = C.c_int64
         lib.ref_api_tree_read.argtypes = [C.c_void_p, i32p] + _EMAT_OUT_ARGS + [u8p]; lib.ref_api_tree_read.restype = C.c_int32
+        i64p = C.POINTER(C.c_int64)
+        lib.ref_maple_read.argtypes = [C.c_char_p, C.c_int64, i64p, u8p, f64p, f64p, i64p, C.c_char_p, i32p, i32p, u8p, u8p, i32p, i32p, i32p]
+        lib.ref_maple_read.restype = C.c_int32
         _REF = lib
     return _REF
 
